@@ -1,0 +1,238 @@
+"""Thin Python host layer over the C ABI (numpy in / numpy out).
+
+Mirrors the reference's inner seams for the hot path: ``kmeans::cluster`` (kmeans.rs:21),
+``utils::count_freqs`` (utils.rs:4), ``hilbert::iter`` (hilbert.rs:40), the voronoi fill (clusterc.rs:179-186) and the
+``Codec`` trait (codec.rs:14-19, see codecs.py).  All compute happens in libcniic_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+
+
+class CniicError(RuntimeError):
+    def __init__(self, code: int, msg: str = ""):
+        super().__init__(f"cniic_b200 status {code}: {msg}")
+        self.code = code
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+@dataclass
+class KMeansResult:
+    centroids: np.ndarray   # (k, D) int64 ; D = 3: r,g,b ; D = 5: x,y,r,g,b
+    weights: np.ndarray     # (k,) uint64
+    assign: np.ndarray | None  # (n,) uint16
+    iterations: int
+    empty_events: int
+    moved_last: int
+    moved_total: int
+    converged: bool
+    gpu_launches: int
+    device_ms: float
+    status: int = 0
+
+
+class Context:
+    """One CUDA device + stream (cniic_ctx).  Not thread-safe; one Context per thread."""
+
+    def __init__(self, device: int = -1, rank: int = 0, world: int = 1, nccl_unique_id: bytes | None = None):
+        self._lib = L.lib()
+        h = C.c_void_p()
+        if world > 1:
+            if nccl_unique_id is None or len(nccl_unique_id) != 128:
+                raise ValueError("a 128-byte ncclUniqueId is required for world > 1")
+            buf = (C.c_uint8 * 128).from_buffer_copy(nccl_unique_id)
+            rc = self._lib.cniic_ctx_create_dist(device, rank, world, buf, C.byref(h))
+        else:
+            rc = self._lib.cniic_ctx_create(device, C.byref(h))
+        if rc != L.OK:
+            raise CniicError(rc, "cniic_ctx_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = L.lib().cniic_nccl_unique_id(buf)
+        if rc != L.OK:
+            raise CniicError(rc, "ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.cniic_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- helpers ----
+    def check(self, rc: int, allow=()):
+        if rc != L.OK and rc not in allow:
+            raise CniicError(rc, (self._lib.cniic_last_error(self.h) or b"").decode(errors="replace"))
+        return rc
+
+    @property
+    def stream(self) -> int:
+        return self._lib.cniic_ctx_stream(self.h) or 0
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.cniic_ctx_launches(self.h))
+
+    def sync(self):
+        self.check(self._lib.cniic_ctx_sync(self.h))
+
+    def set_max_iters(self, n: int):
+        self.check(self._lib.cniic_ctx_set_max_iters(self.h, C.c_uint32(n)))
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = self._lib.cniic_device_alloc(self.h, nbytes)
+        if not p:
+            raise CniicError(L.ERR_CUDA, "device allocation failed")
+        return p
+
+    def device_free(self, p: int):
+        self._lib.cniic_device_free(self.h, p)
+
+    def h2d(self, dptr: int, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        self.check(self._lib.cniic_memcpy_h2d(self.h, dptr, _ptr(arr), arr.nbytes))
+
+    def d2h(self, arr: np.ndarray, dptr: int):
+        self.check(self._lib.cniic_memcpy_d2h(self.h, _ptr(arr), dptr, arr.nbytes))
+
+    # ---- K-means: kmeans::cluster (kmeans.rs:21-39) ----
+    def _result(self, st, cen, wts, asg, rc):
+        return KMeansResult(cen, wts, asg, st.iterations, st.empty_events, st.moved_last, st.moved_total,
+                            bool(st.converged), st.gpu_launches, st.device_ms, rc)
+
+    def kmeans_rgb(self, rgb, k, counts=None, max_iters=0, tie=L.TIE_KEEP_CURRENT, want_assign=True,
+                   allow_inactive=False) -> KMeansResult:
+        """ColorCount points (clusterc.rs:68-114); counts=None clusters the points unweighted (per pixel)."""
+        rgb = _u8(rgb).reshape(-1, 3)
+        n = len(rgb)
+        cnt = None if counts is None else np.ascontiguousarray(counts, dtype=np.uint32)
+        cen = np.zeros((max(k, 1), 3), np.uint8)
+        wts = np.zeros(max(k, 1), np.uint64)
+        asg = np.zeros(n, np.uint16) if want_assign else None
+        st = L.KMeansStats()
+        rc = self._lib.cniic_kmeans_rgb(self.h, _ptr(rgb), _ptr(cnt), C.c_size_t(n), C.c_uint32(k),
+                                        C.c_uint32(max_iters), tie, _ptr(cen), _ptr(wts), _ptr(asg), C.byref(st))
+        self.check(rc, (L.ERR_TOO_FEW_ACTIVE,) if allow_inactive else ())
+        return self._result(st, cen[:k].astype(np.int64), wts[:k], asg, rc)
+
+    def kmeans_xyrgb(self, img, k, max_iters=0, tie=L.TIE_KEEP_CURRENT, want_assign=True,
+                     allow_inactive=False) -> KMeansResult:
+        """ColorPos points (clusterc.rs:148-153, 200-248): one point per pixel of img (h, w, 3)."""
+        img = _u8(img)
+        h, w = img.shape[:2]
+        cxy = np.zeros((max(k, 1), 2), np.uint32)
+        crgb = np.zeros((max(k, 1), 3), np.uint8)
+        wts = np.zeros(max(k, 1), np.uint64)
+        asg = np.zeros(h * w, np.uint16) if want_assign else None
+        st = L.KMeansStats()
+        rc = self._lib.cniic_kmeans_xyrgb(self.h, _ptr(img), C.c_uint32(w), C.c_uint32(h), C.c_uint32(k),
+                                          C.c_uint32(max_iters), tie, _ptr(cxy), _ptr(crgb), _ptr(wts), _ptr(asg),
+                                          C.byref(st))
+        self.check(rc, (L.ERR_TOO_FEW_ACTIVE,) if allow_inactive else ())
+        cen = np.concatenate([cxy[:k].astype(np.int64), crgb[:k].astype(np.int64)], axis=1)
+        return self._result(st, cen, wts[:k], asg, rc)
+
+    def kmeans_session(self, **kw) -> "KMeansSession":
+        return KMeansSession(self, **kw)
+
+
+class KMeansSession:
+    """Points resident in HBM across iterations (cniic_kmeans_open/reset/run/get)."""
+
+    def __init__(self, ctx: Context, kind: int, k: int, rgb, n_local: int, n_total: int | None = None,
+                 first_index: int = 0, w: int = 0, h_local: int = 0, y0: int = 0, weights=None,
+                 tie: int = L.TIE_KEEP_CURRENT, on_device: bool = False):
+        self.ctx = ctx
+        self.k, self.D = k, (5 if kind == L.POINTS_XYRGB else 3)
+        self.n_local = n_local
+        d = L.KMeansDesc()
+        d.kind, d.k, d.tie_rule = kind, k, tie
+        d.n_local = n_local
+        d.n_total = n_local if n_total is None else n_total
+        d.first_index, d.w, d.h_local, d.y0 = first_index, w, h_local, y0
+        self._keep = []
+        if on_device:
+            d.rgb = int(rgb)
+            d.weights = int(weights) if weights is not None else None
+        else:
+            a = _u8(rgb)
+            self._keep.append(a)
+            d.rgb = a.ctypes.data
+            if weights is not None:
+                wa = np.ascontiguousarray(weights, dtype=np.uint32)
+                self._keep.append(wa)
+                d.weights = wa.ctypes.data
+        d.points_on_device = 1 if on_device else 0
+        h = C.c_void_p()
+        ctx.check(ctx._lib.cniic_kmeans_open(ctx.h, C.byref(d), C.byref(h)))
+        self.h = h
+
+    def reset(self, init_centroids=None):
+        ic = None if init_centroids is None else np.ascontiguousarray(init_centroids, dtype=np.int32)
+        self.ctx.check(self.ctx._lib.cniic_kmeans_reset(self.h, _ptr(ic)))
+
+    def run(self, max_iters: int = 0) -> L.KMeansStats:
+        st = L.KMeansStats()
+        self.ctx.check(self.ctx._lib.cniic_kmeans_run(self.h, C.c_uint32(max_iters), C.byref(st)))
+        return st
+
+    def get(self, want_assign=True):
+        cen = np.zeros((self.k, self.D), np.int32)
+        wts = np.zeros(self.k, np.uint64)
+        asg = np.zeros(self.n_local, np.uint16) if want_assign else None
+        self.ctx.check(self.ctx._lib.cniic_kmeans_get(self.h, _ptr(cen), _ptr(wts), _ptr(asg)))
+        return cen.astype(np.int64), wts, asg
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx._lib.cniic_kmeans_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- synthetic images: identical on host and device ----
+def synth_image_host(w: int, h: int, seed: int, n_blobs: int, y0: int = 0, h_total: int | None = None) -> np.ndarray:
+    out = np.zeros((h, w, 3), np.uint8)
+    rc = L.lib().cniic_synth_image_host(_ptr(out), C.c_uint32(w), C.c_uint32(h), C.c_uint32(y0),
+                                        C.c_uint32(h_total or h), C.c_uint64(seed), C.c_uint32(n_blobs))
+    if rc != L.OK:
+        raise CniicError(rc, "synth_image_host")
+    return out
+
+
+def synth_image_device(ctx: Context, dptr: int, w: int, h: int, seed: int, n_blobs: int, y0: int = 0,
+                       h_total: int | None = None):
+    ctx.check(ctx._lib.cniic_synth_image_device(ctx.h, C.c_void_p(dptr), C.c_uint32(w), C.c_uint32(h), C.c_uint32(y0),
+                                                C.c_uint32(h_total or h), C.c_uint64(seed), C.c_uint32(n_blobs)))

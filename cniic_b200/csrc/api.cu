@@ -1,0 +1,216 @@
+// api.cu -- context management, error reporting, NCCL (dlopen) plumbing of the cniic_b200 C ABI.
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+#include "nccl_dyn.h"
+
+int cniic_set_error(cniic_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+int cniic_launch_bump(cniic_ctx *ctx, uint32_t n) {
+    ctx->launches += n;
+    return CNIIC_OK;
+}
+
+// ---- NCCL through dlopen -------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(nccl_uid_t *) = nullptr;
+    int (*CommInitRank)(void **, int, nccl_uid_t, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static const int NCCL_UINT8 = 1, NCCL_UINT64 = 5, NCCL_SUM = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+static NcclApi *nccl_load(std::string *why) {
+    static NcclApi api;
+    static bool tried = false, ok = false;
+    static std::string err;
+    if (!tried) {
+        tried = true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) {
+            err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+        } else {
+            api.GetUniqueId = (int (*)(nccl_uid_t *))dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(void **, int, nccl_uid_t, int))dlsym(api.handle, "ncclCommInitRank");
+            api.CommDestroy = (int (*)(void *))dlsym(api.handle, "ncclCommDestroy");
+            api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+            api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(api.handle, "ncclAllGather");
+            api.GetErrorString = (const char *(*)(int))dlsym(api.handle, "ncclGetErrorString");
+            ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather;
+            if (!ok) err = "libnccl.so.2 lacks a required symbol";
+        }
+    }
+    if (!ok && why) *why = err;
+    return ok ? &api : nullptr;
+}
+
+extern "C" int cniic_nccl_unique_id(uint8_t out_id[128]) {
+    std::string why;
+    NcclApi *api = nccl_load(&why);
+    if (!api || !out_id) return CNIIC_ERR_NCCL;
+    nccl_uid_t id;
+    if (api->GetUniqueId(&id) != 0) return CNIIC_ERR_NCCL;
+    memcpy(out_id, id.internal, 128);
+    return CNIIC_OK;
+}
+
+int cniic_nccl_init(cniic_ctx *ctx, int rank, int world, const uint8_t unique_id[128]) {
+    std::string why;
+    NcclApi *api = nccl_load(&why);
+    if (!api) return cniic_set_error(ctx, CNIIC_ERR_NCCL, "%s", why.c_str());
+    nccl_uid_t id;
+    memcpy(id.internal, unique_id, 128);
+    const int rc = api->CommInitRank(&ctx->comm, world, id, rank);
+    if (rc != 0) return cniic_set_error(ctx, CNIIC_ERR_NCCL, "ncclCommInitRank: %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
+    ctx->nccl = api;
+    ctx->rank = rank;
+    ctx->world = world;
+    return CNIIC_OK;
+}
+
+void cniic_nccl_destroy(cniic_ctx *ctx) {
+    if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+}
+
+int cniic_nccl_allreduce_u64(cniic_ctx *ctx, unsigned long long *d_buf, size_t count) {
+    if (!ctx->comm) return cniic_set_error(ctx, CNIIC_ERR_NCCL, "context has no communicator");
+    const int rc = ctx->nccl->AllReduce(d_buf, d_buf, count, NCCL_UINT64, NCCL_SUM, ctx->comm, ctx->stream);
+    if (rc != 0) return cniic_set_error(ctx, CNIIC_ERR_NCCL, "ncclAllReduce: %s", ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(rc) : "error");
+    return CNIIC_OK;
+}
+
+int cniic_nccl_allgather_bytes(cniic_ctx *ctx, const void *d_send, void *d_recv, size_t bytes_per_rank) {
+    if (!ctx->comm) return cniic_set_error(ctx, CNIIC_ERR_NCCL, "context has no communicator");
+    const int rc = ctx->nccl->AllGather(d_send, d_recv, bytes_per_rank, NCCL_UINT8, ctx->comm, ctx->stream);
+    if (rc != 0) return cniic_set_error(ctx, CNIIC_ERR_NCCL, "ncclAllGather: %s", ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(rc) : "error");
+    return CNIIC_OK;
+}
+
+// ---- context ---------------------------------------------------------------------------------------------------
+extern "C" int cniic_version(void) { return 100; }
+
+static int ctx_create_common(int device, cniic_ctx **out) {
+    if (!out) return CNIIC_ERR_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return CNIIC_ERR_CUDA;  // no CPU fallback: fail loudly
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return CNIIC_ERR_CUDA;
+    }
+    if (device >= count) return CNIIC_ERR_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return CNIIC_ERR_CUDA;
+    cniic_ctx *ctx = new cniic_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return CNIIC_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return CNIIC_ERR_CUDA;
+    }
+    *out = ctx;
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_ctx_create(int device, cniic_ctx **out) { return ctx_create_common(device, out); }
+
+extern "C" int cniic_ctx_create_dist(int device, int rank, int world, const uint8_t nccl_unique_id[128], cniic_ctx **out) {
+    if (world < 1 || rank < 0 || rank >= world || !nccl_unique_id) return CNIIC_ERR_BAD_ARG;
+    ST_TRY(ctx_create_common(device, out));
+    if (world == 1) return CNIIC_OK;
+    const int rc = cniic_nccl_init(*out, rank, world, nccl_unique_id);
+    if (rc != CNIIC_OK) {
+        fprintf(stderr, "cniic_b200: %s\n", (*out)->err.c_str());
+        cniic_ctx_destroy(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+extern "C" void cniic_ctx_destroy(cniic_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cniic_nccl_destroy(ctx);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *cniic_last_error(const cniic_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int cniic_ctx_sync(cniic_ctx *ctx) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+extern "C" void *cniic_ctx_stream(cniic_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int cniic_ctx_rank(const cniic_ctx *ctx) { return ctx ? ctx->rank : -1; }
+extern "C" int cniic_ctx_world(const cniic_ctx *ctx) { return ctx ? ctx->world : 0; }
+extern "C" uint32_t cniic_ctx_launches(const cniic_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int cniic_ctx_set_max_iters(cniic_ctx *ctx, uint32_t max_iters) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    ctx->codec_max_iters = max_iters;
+    return CNIIC_OK;
+}
+
+extern "C" void *cniic_device_alloc(cniic_ctx *ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    void *p = nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+        cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void cniic_device_free(cniic_ctx *ctx, void *p) {
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(p);
+}
+
+extern "C" int cniic_memcpy_h2d(cniic_ctx *ctx, void *d, const void *h, size_t bytes) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_memcpy_d2h(cniic_ctx *ctx, void *h, const void *d, size_t bytes) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}

@@ -1,0 +1,63 @@
+// common.cuh -- shared declarations of the cniic_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/cniic_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define CNIIC_HOST 1
+#endif
+
+struct NcclApi;
+
+struct cniic_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int rank = 0, world = 1;
+    void *comm = nullptr;  // ncclComm_t
+    NcclApi *nccl = nullptr;
+    uint32_t codec_max_iters = 0;
+    uint32_t launches = 0;  // kernels launched on this ctx (bench.py reports it as gpu_launches)
+};
+
+int cniic_set_error(cniic_ctx *ctx, int code, const char *fmt, ...);
+
+#define CU_TRY(ctx, expr)                                                                                       \
+    do {                                                                                                        \
+        cudaError_t e__ = (expr);                                                                               \
+        if (e__ != cudaSuccess)                                                                                 \
+            return cniic_set_error((ctx), CNIIC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                                   __FILE__, __LINE__);                                                         \
+    } while (0)
+
+#define ST_TRY(expr)             \
+    do {                         \
+        int s__ = (expr);        \
+        if (s__ != CNIIC_OK) return s__; \
+    } while (0)
+
+// ---- integer dot-product instructions (IDP.4A / IDP.2A on sm_100a) ----
+// dp4a: c + sum_i a.u8[i] * b.u8[i]   (two's-complement wrap makes the signed accumulator exact)
+__device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// dp2a.lo: c + a.s16[0] * b.u8[0] + a.s16[1] * b.u8[1]
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int max3i(int a, int b, int c) { return max(a, max(b, c)); }  // VIMNMX3
+
+static inline uint32_t round_up_u32(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+// internal entry points shared between translation units
+int cniic_launch_bump(cniic_ctx *ctx, uint32_t n);

@@ -1,0 +1,912 @@
+// kmeans.cu -- Lloyd K-means on sm_100a: fused assign + accumulate kernels, finalize kernel, session API.
+//
+// Replaces kmeans::cluster (reference src/kmeans.rs:21-39) for the two point kinds the codecs use:
+//   D = 3  ColorCount (src/codec/clusterc.rs:68-114)   -- `cluster-colors`
+//   D = 5  ColorPos   (src/codec/clusterc.rs:200-248)  -- `voronoi`
+//
+// Arithmetic (DESIGN.md "Exact integer scores"):
+//   argmin_c |x - c|^2  ==  argmax_c  S_c,  S_c = x . c - |c|^2 / 2.
+//   x . c is computed by the integer dot-product pipe: IDP.4A for the three colour bytes and, for D = 5,
+//   IDP.2A for (x - x0, y - y0) (u8, tile relative) times (cx, cy) (s16); the per-tile constant
+//   x0*cx + y0*cy - floor(|c|^2/2) is folded into the accumulator operand.  Everything is int32-exact.
+//   The half-unit of an odd |c|^2 is handled by splitting the centroid table into an even and an odd class
+//   (groups of G consecutive table entries are single-parity); group maxima are compared as 2*S - parity,
+//   so the comparison equals the exact integer comparison of squared distances.  Ties: lowest original index
+//   (table order preserves index order inside a class, two classes can never tie), optionally "keep the
+//   current cluster" (kmeans.rs:350-378).
+//   The inner loop keeps only a running maximum per pixel (VIMNMX3); the winning index is recovered by
+//   re-scoring the G entries of the winning group.
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "nccl_dyn.h"
+
+namespace {
+
+constexpr int G3 = 8;    // group size, D = 3 kernel
+constexpr int G5 = 16;   // group size, D = 5 kernel
+constexpr int THREADS = 256;
+constexpr int PX = 8;    // points per thread per tile
+constexpr int TILE = THREADS * PX;
+constexpr int DUMMY3 = -(1 << 19);  // bias of padding entries, D = 3 (real scores > -97538)
+constexpr int DUMMY5 = -(1 << 29);  // bias of padding entries, D = 5 (real scores > -2.7e8)
+constexpr int GSHIFT = 10;          // D = 3: bits of the group field packed under the key
+constexpr int FLUSH_TILES = 64;     // D = 5: flush u32 shared accumulators to global every 64 tiles
+
+struct KmState {
+    uint32_t iter;
+    uint32_t done;
+    uint32_t empty_events;
+    uint32_t ngroups;
+    uint32_t ng0;
+    uint32_t n_empty_last;
+    uint32_t dist_empty;  // an empty cluster occurred in a multi-GPU run (repair needs the host path)
+    uint32_t pad;
+    unsigned long long moved_last, moved_total;
+};
+
+struct KmDev {
+    const uint8_t *rgb;
+    const uint32_t *wts;
+    unsigned long long n_local, n_total, first_index;
+    uint32_t w, h_local, y0;
+    uint32_t k;
+    int tie;
+    int world;
+    uint16_t *assign;
+    uint32_t *t_cpk;
+    uint32_t *t_cxy;
+    int *t_bias;
+    uint16_t *t_id;
+    uint16_t *t_pos;
+    unsigned long long *sums;  // k*(D+1) partial sums + 1 moved counter
+    int32_t *cen;              // k*D
+    unsigned long long *weights;
+    KmState *st;
+};
+
+__host__ __device__ inline uint32_t kpad_of(uint32_t k, int G) { return (k + 2 * (G - 1) + G - 1) / G * G; }
+
+// ------------------------------------------------------------------------------------------------------------
+// D = 3 fused assign + accumulate
+// ------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void unpack8(const uint32_t w[6], uint32_t px[PX]) {
+    // 24 bytes r0 g0 b0 r1 ... -> one word per pixel whose low three bytes are r,g,b (4th byte is don't-care:
+    // the centroid word has a zero 4th byte)
+    px[0] = w[0];
+    px[1] = __byte_perm(w[0], w[1], 0x6543);
+    px[2] = __byte_perm(w[1], w[2], 0x5432);
+    px[3] = w[2] >> 8;
+    px[4] = w[3];
+    px[5] = __byte_perm(w[3], w[4], 0x6543);
+    px[6] = __byte_perm(w[4], w[5], 0x5432);
+    px[7] = w[5] >> 8;
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(THREADS) km_assign_rgb(KmDev d) {
+    if (d.st->done) return;
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t k = d.k;
+    const uint32_t KP = kpad_of(k, G3);
+    uint32_t *s_cpk = reinterpret_cast<uint32_t *>(smem_raw);
+    int *s_bias = reinterpret_cast<int *>(s_cpk + KP);
+    uint16_t *s_id = reinterpret_cast<uint16_t *>(s_bias + KP);
+    uint16_t *s_pos = s_id + KP;
+    // accumulators start 16-byte aligned (offset arithmetic keeps the shared address space visible to the compiler)
+    const uint32_t acc_off = (KP * 10 + k * 2 + 15) & ~15u;
+    uint32_t *s_acc32 = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(smem_raw) + acc_off);
+    unsigned long long *s_acc64 = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(smem_raw) + acc_off);
+
+    const int tid = threadIdx.x;
+    const int ngroups = d.st->ngroups, ng0 = d.st->ng0;
+    for (uint32_t i = tid; i < KP; i += THREADS) {
+        s_cpk[i] = d.t_cpk[i];
+        s_bias[i] = d.t_bias[i];
+        s_id[i] = d.t_id[i];
+    }
+    for (uint32_t i = tid; i < k; i += THREADS) s_pos[i] = d.t_pos[i];
+    for (uint32_t i = tid; i < 4 * k; i += THREADS) {
+        if (WEIGHTED) s_acc64[i] = 0ull;
+        else s_acc32[i] = 0u;
+    }
+    __syncthreads();
+
+    const unsigned long long n = d.n_local;
+    const unsigned long long tiles = (n + TILE - 1) / TILE;
+    const bool aligned = (reinterpret_cast<uintptr_t>(d.rgb) & 7) == 0;
+    unsigned long long moved = 0;
+
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const unsigned long long base = tile * TILE + (unsigned long long)tid * PX;
+        int nv = 0;
+        if (base < n) nv = (n - base) >= PX ? PX : int(n - base);
+        uint32_t px[PX];
+        if (nv == PX && aligned) {
+            const uint2 *p = reinterpret_cast<const uint2 *>(d.rgb + base * 3);
+            const uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+            const uint32_t wd[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+            unpack8(wd, px);
+        } else {
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                px[p] = 0;
+                if (p < nv) {
+                    const uint8_t *q = d.rgb + (base + p) * 3;
+                    px[p] = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+                }
+            }
+        }
+
+        // ---- scan: running packed maximum ((2*S - parity) << GSHIFT | 1023 - group) ----
+        int best[PX];
+#pragma unroll
+        for (int p = 0; p < PX; p++) best[p] = INT_MIN;
+        for (int g = 0; g < ngroups; g++) {
+            const uint4 c0 = reinterpret_cast<const uint4 *>(s_cpk)[2 * g], c1 = reinterpret_cast<const uint4 *>(s_cpk)[2 * g + 1];
+            const int4 b0 = reinterpret_cast<const int4 *>(s_bias)[2 * g], b1 = reinterpret_cast<const int4 *>(s_bias)[2 * g + 1];
+            const int lowbits = ((1 << GSHIFT) - 1 - g) - ((g >= ng0) ? (1 << GSHIFT) : 0);
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                int m = max(dp4a_uu(px[p], c0.x, b0.x), dp4a_uu(px[p], c0.y, b0.y));
+                m = max3i(m, dp4a_uu(px[p], c0.z, b0.z), dp4a_uu(px[p], c0.w, b0.w));
+                m = max3i(m, dp4a_uu(px[p], c1.x, b1.x), dp4a_uu(px[p], c1.y, b1.y));
+                m = max3i(m, dp4a_uu(px[p], c1.z, b1.z), dp4a_uu(px[p], c1.w, b1.w));
+                best[p] = max(best[p], m * (2 << GSHIFT) + lowbits);
+            }
+        }
+
+        // ---- index recovery + tie rule + bookkeeping ----
+        uint16_t prev[PX], idx[PX];
+        if (nv == PX) {
+            const uint4 pv = *reinterpret_cast<const uint4 *>(d.assign + base);
+            prev[0] = pv.x & 0xffff; prev[1] = pv.x >> 16; prev[2] = pv.y & 0xffff; prev[3] = pv.y >> 16;
+            prev[4] = pv.z & 0xffff; prev[5] = pv.z >> 16; prev[6] = pv.w & 0xffff; prev[7] = pv.w >> 16;
+        } else {
+#pragma unroll
+            for (int p = 0; p < PX; p++) prev[p] = p < nv ? d.assign[base + p] : 0;
+        }
+#pragma unroll
+        for (int p = 0; p < PX; p++) {
+            const int g = ((1 << GSHIFT) - 1) - (best[p] & ((1 << GSHIFT) - 1));
+            const int key = best[p] >> GSHIFT;
+            const int par = g >= ng0;
+            const int target = (key + par) >> 1;
+            int found = 0;
+#pragma unroll
+            for (int j = G3 - 1; j >= 0; j--) {
+                const int s = dp4a_uu(px[p], s_cpk[g * G3 + j], s_bias[g * G3 + j]);
+                if (s == target) found = s_id[g * G3 + j];
+            }
+            if (d.tie == CNIIC_TIE_KEEP_CURRENT) {
+                const int pos = s_pos[prev[p]];
+                const int sc = dp4a_uu(px[p], s_cpk[pos], s_bias[pos]);
+                if (2 * sc - ((pos / G3) >= ng0) == key) found = prev[p];
+            }
+            idx[p] = (uint16_t)found;
+            if (p < nv && idx[p] != prev[p]) moved++;
+        }
+        if (nv == PX) {
+            uint4 ov;
+            ov.x = idx[0] | (uint32_t(idx[1]) << 16); ov.y = idx[2] | (uint32_t(idx[3]) << 16);
+            ov.z = idx[4] | (uint32_t(idx[5]) << 16); ov.w = idx[6] | (uint32_t(idx[7]) << 16);
+            *reinterpret_cast<uint4 *>(d.assign + base) = ov;
+        } else {
+#pragma unroll
+            for (int p = 0; p < PX; p++)
+                if (p < nv) d.assign[base + p] = idx[p];
+        }
+
+        // ---- accumulate: merge runs of equal cluster ids in registers, then shared-memory atomics ----
+        if (WEIGHTED) {
+            uint32_t wt[PX];
+#pragma unroll
+            for (int p = 0; p < PX; p++) wt[p] = p < nv ? d.wts[base + p] : 0;
+            unsigned long long ar = 0, ag = 0, ab = 0, aw = 0;
+            int run = -1;
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                if (p < nv) {
+                    if (idx[p] != run) {
+                        if (run >= 0) {
+                            atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
+                            atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+                        }
+                        run = idx[p]; ar = ag = ab = aw = 0;
+                    }
+                    const unsigned long long wq = wt[p];
+                    ar += (px[p] & 0xff) * wq; ag += ((px[p] >> 8) & 0xff) * wq; ab += ((px[p] >> 16) & 0xff) * wq; aw += wq;
+                }
+            }
+            if (run >= 0) {
+                atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
+                atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+            }
+        } else {
+            uint32_t ar = 0, ag = 0, ab = 0, aw = 0;
+            int run = -1;
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                if (p < nv) {
+                    if (idx[p] != run) {
+                        if (run >= 0) {
+                            atomicAdd(&s_acc32[4 * run], ar); atomicAdd(&s_acc32[4 * run + 1], ag);
+                            atomicAdd(&s_acc32[4 * run + 2], ab); atomicAdd(&s_acc32[4 * run + 3], aw);
+                        }
+                        run = idx[p]; ar = ag = ab = aw = 0;
+                    }
+                    ar += px[p] & 0xff; ag += (px[p] >> 8) & 0xff; ab += (px[p] >> 16) & 0xff; aw += 1;
+                }
+            }
+            if (run >= 0) {
+                atomicAdd(&s_acc32[4 * run], ar); atomicAdd(&s_acc32[4 * run + 1], ag);
+                atomicAdd(&s_acc32[4 * run + 2], ab); atomicAdd(&s_acc32[4 * run + 3], aw);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < 4 * k; i += THREADS) {
+        const unsigned long long v = WEIGHTED ? s_acc64[i] : (unsigned long long)s_acc32[i];
+        if (v) atomicAdd(&d.sums[i], v);
+    }
+    for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
+    if ((tid & 31) == 0 && moved) atomicAdd(&d.sums[4 * k], moved);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// D = 5 fused assign + accumulate: tile = 256 pixels x 8 rows, warp = one row, lane = 8 consecutive pixels
+// ------------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(THREADS) km_assign_xyrgb(KmDev d) {
+    if (d.st->done) return;
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t k = d.k;
+    const uint32_t KP = kpad_of(k, G5);
+    uint32_t *s_cpk = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *s_cxy = s_cpk + KP;
+    int *s_bias0 = reinterpret_cast<int *>(s_cxy + KP);
+    int *s_bias = s_bias0 + KP;
+    uint32_t *s_stage = reinterpret_cast<uint32_t *>(s_bias + KP);  // 8 rows x 192 words
+    uint32_t *s_acc = s_stage + 8 * 192;                            // 6*k u32
+    uint16_t *s_id = reinterpret_cast<uint16_t *>(s_acc + 6 * k);
+    uint16_t *s_pos = s_id + KP;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ngroups = d.st->ngroups, ng0 = d.st->ng0;
+    for (uint32_t i = tid; i < KP; i += THREADS) {
+        s_cpk[i] = d.t_cpk[i];
+        s_cxy[i] = d.t_cxy[i];
+        s_bias0[i] = d.t_bias[i];
+        s_id[i] = d.t_id[i];
+    }
+    for (uint32_t i = tid; i < k; i += THREADS) s_pos[i] = d.t_pos[i];
+    for (uint32_t i = tid; i < 6 * k; i += THREADS) s_acc[i] = 0u;
+
+    const uint32_t w = d.w, hl = d.h_local;
+    const uint32_t tiles_x = (w + 255) / 256, tiles_y = (hl + 7) / 8;
+    const unsigned long long tiles = (unsigned long long)tiles_x * tiles_y;
+    const bool word_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.rgb) & 3) == 0);
+    unsigned long long moved = 0;
+    uint32_t since_flush = 0;
+
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t ty = uint32_t(tile / tiles_x), tx = uint32_t(tile % tiles_x);
+        const uint32_t x0 = tx * 256, yl0 = ty * 8;       // local row of the tile
+        const uint32_t yg0 = d.y0 + yl0;                  // global row
+        __syncthreads();  // previous tile finished with s_bias / s_stage
+        for (uint32_t i = tid; i < KP; i += THREADS) {
+            const uint32_t cxy = s_cxy[i];
+            s_bias[i] = s_bias0[i] + int(x0 * (cxy & 0xffff)) + int(yg0 * (cxy >> 16));
+        }
+        // stage this warp's row segment
+        const uint32_t yl = yl0 + warp;
+        const uint32_t vw = min(256u, w - x0);
+        const bool row_ok = yl < hl;
+        uint32_t *stage = s_stage + warp * 192;
+        if (row_ok) {
+            const unsigned long long off = ((unsigned long long)yl * w + x0) * 3;
+            if (word_ok && vw == 256) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(d.rgb + off);
+#pragma unroll
+                for (int i = 0; i < 6; i++) stage[lane + 32 * i] = __ldg(src + lane + 32 * i);
+            } else {
+                for (int i = lane; i < 192; i += 32) {
+                    uint32_t v = 0;
+                    for (int b = 0; b < 4; b++) {
+                        const uint32_t byte = i * 4 + b;
+                        if (byte < vw * 3) v |= uint32_t(d.rgb[off + byte]) << (8 * b);
+                    }
+                    stage[i] = v;
+                }
+            }
+        }
+        __syncthreads();
+        const int xr0 = lane * 8;
+        int nv = 0;
+        if (row_ok && xr0 < int(vw)) nv = min(PX, int(vw) - xr0);
+        uint32_t wd[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) wd[i] = stage[lane * 6 + i];
+        uint32_t px[PX], pxy[PX];
+        unpack8(wd, px);
+#pragma unroll
+        for (int p = 0; p < PX; p++) pxy[p] = uint32_t(xr0 + p) | (uint32_t(warp) << 8);
+
+        int bestkey[PX], bestg[PX];
+#pragma unroll
+        for (int p = 0; p < PX; p++) { bestkey[p] = INT_MIN; bestg[p] = 0; }
+        for (int g = 0; g < ngroups; g++) {
+            int m[PX];
+#pragma unroll
+            for (int p = 0; p < PX; p++) m[p] = DUMMY5;
+#pragma unroll
+            for (int q = 0; q < G5 / 4; q++) {
+                const uint4 c = reinterpret_cast<const uint4 *>(s_cpk)[g * (G5 / 4) + q];
+                const uint4 xy = reinterpret_cast<const uint4 *>(s_cxy)[g * (G5 / 4) + q];
+                const int4 b = reinterpret_cast<const int4 *>(s_bias)[g * (G5 / 4) + q];
+#pragma unroll
+                for (int p = 0; p < PX; p++) {
+                    const int s0 = dp2a_lo_su(xy.x, pxy[p], dp4a_uu(px[p], c.x, b.x));
+                    const int s1 = dp2a_lo_su(xy.y, pxy[p], dp4a_uu(px[p], c.y, b.y));
+                    const int s2 = dp2a_lo_su(xy.z, pxy[p], dp4a_uu(px[p], c.z, b.z));
+                    const int s3 = dp2a_lo_su(xy.w, pxy[p], dp4a_uu(px[p], c.w, b.w));
+                    m[p] = max3i(m[p], s0, s1);
+                    m[p] = max3i(m[p], s2, s3);
+                }
+            }
+            const int par = g >= ng0;
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                const int key = 2 * m[p] - par;
+                if (key > bestkey[p]) { bestkey[p] = key; bestg[p] = g; }
+            }
+        }
+
+        const unsigned long long lbase = (unsigned long long)yl * w + x0 + xr0;  // local point index of pixel 0
+        uint16_t idx[PX];
+        int run = -1;
+        uint32_t ax = 0, ar = 0, ag = 0, ab = 0, an = 0;
+        const uint32_t yg = yg0 + warp;
+#pragma unroll
+        for (int p = 0; p < PX; p++) {
+            if (p < nv) {
+                const int g = bestg[p];
+                const int par = g >= ng0;
+                int found = 0;
+#pragma unroll
+                for (int j = G5 - 1; j >= 0; j--) {
+                    const int e = g * G5 + j;
+                    const int s = dp2a_lo_su(s_cxy[e], pxy[p], dp4a_uu(px[p], s_cpk[e], s_bias[e]));
+                    if (2 * s - par == bestkey[p]) found = s_id[e];
+                }
+                const uint16_t prev = d.assign[lbase + p];
+                if (d.tie == CNIIC_TIE_KEEP_CURRENT) {
+                    const int e = s_pos[prev];
+                    const int sc = dp2a_lo_su(s_cxy[e], pxy[p], dp4a_uu(px[p], s_cpk[e], s_bias[e]));
+                    if (2 * sc - ((e / G5) >= ng0) == bestkey[p]) found = prev;
+                }
+                idx[p] = (uint16_t)found;
+                if (idx[p] != prev) { moved++; d.assign[lbase + p] = idx[p]; }
+                if (found != run) {
+                    if (run >= 0) {
+                        atomicAdd(&s_acc[6 * run], ax); atomicAdd(&s_acc[6 * run + 1], an * yg);
+                        atomicAdd(&s_acc[6 * run + 2], ar); atomicAdd(&s_acc[6 * run + 3], ag);
+                        atomicAdd(&s_acc[6 * run + 4], ab); atomicAdd(&s_acc[6 * run + 5], an);
+                    }
+                    run = found; ax = ar = ag = ab = an = 0;
+                }
+                ax += x0 + xr0 + p; ar += px[p] & 0xff; ag += (px[p] >> 8) & 0xff; ab += (px[p] >> 16) & 0xff; an += 1;
+            }
+        }
+        if (run >= 0) {
+            atomicAdd(&s_acc[6 * run], ax); atomicAdd(&s_acc[6 * run + 1], an * yg);
+            atomicAdd(&s_acc[6 * run + 2], ar); atomicAdd(&s_acc[6 * run + 3], ag);
+            atomicAdd(&s_acc[6 * run + 4], ab); atomicAdd(&s_acc[6 * run + 5], an);
+        }
+        if (++since_flush == FLUSH_TILES) {  // keep the u32 partial sums far from overflow (2048 px * 64 * 16383 < 2^32)
+            __syncthreads();
+            for (uint32_t i = tid; i < 6 * k; i += THREADS) {
+                const uint32_t v = s_acc[i];
+                if (v) { atomicAdd(&d.sums[i], (unsigned long long)v); s_acc[i] = 0; }
+            }
+            since_flush = 0;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < 6 * k; i += THREADS) {
+        const uint32_t v = s_acc[i];
+        if (v) atomicAdd(&d.sums[i], (unsigned long long)v);
+    }
+    for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
+    if (lane == 0 && moved) atomicAdd(&d.sums[6 * k], moved);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// init + finalize (single CTA)
+// ------------------------------------------------------------------------------------------------------------
+
+template <int D>
+__device__ __forceinline__ void fetch_point(const KmDev &d, unsigned long long local_i, int32_t out[D]) {
+    if (D == 5) {
+        out[0] = int32_t(local_i % d.w);
+        out[1] = int32_t(d.y0 + local_i / d.w);
+        out[2] = d.rgb[3 * local_i]; out[3] = d.rgb[3 * local_i + 1]; out[4] = d.rgb[3 * local_i + 2];
+    } else {
+        out[0] = d.rgb[3 * local_i]; out[1] = d.rgb[3 * local_i + 1]; out[2] = d.rgb[3 * local_i + 2];
+    }
+}
+
+// kmeans.rs:61-78 init_assignment: cluster i < k-1 owns points [N-(i+1)*ppc, N-i*ppc), cluster k-1 the rest
+__global__ void km_init_assign(KmDev d) {
+    const unsigned long long N = d.n_total, ppc = N / d.k;
+    const unsigned long long head = N - (unsigned long long)(d.k - 1) * ppc;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < d.n_local;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long gi = d.first_index + i;
+        d.assign[i] = gi >= head ? uint16_t((N - 1 - gi) / ppc) : uint16_t(d.k - 1);
+    }
+}
+
+// kmeans.rs:101-108 init_centroids (single GPU: gathered straight from the resident points)
+template <int D>
+__global__ void km_init_centroids(KmDev d) {
+    const unsigned long long N = d.n_total, ppc = N / d.k;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < d.k; c += gridDim.x * blockDim.x) {
+        const unsigned long long gi = c + 1 < d.k ? N - (unsigned long long)(c + 1) * ppc : 0ull;
+        int32_t v[D];
+        fetch_point<D>(d, gi - d.first_index, v);
+        for (int j = 0; j < D; j++) d.cen[c * D + j] = v[j];
+    }
+}
+
+// exclusive rank of `flag` among the threads of a 1024-thread block (thread order); *total = number of flags
+__device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *s_warp, uint32_t *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+    for (int i = 0; i < 32; i++) {
+        const uint32_t v = s_warp[i];
+        if (i < warp) before += v;
+        tot += v;
+    }
+    *total = tot;
+    return before + __popc(bal & ((1u << lane) - 1));
+}
+
+template <int D>
+__global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
+    constexpr int DW = D + 1;
+    constexpr int G = D == 5 ? G5 : G3;
+    constexpr int DUMMY = D == 5 ? DUMMY5 : DUMMY3;
+    if (!init_mode && d.st->done) return;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_nempty, s_victim, s_m;
+    __shared__ uint16_t s_empty[CNIIC_MAX_K];
+    __shared__ uint32_t s_found[CNIIC_MAX_K];
+    const uint32_t k = d.k;
+    const int tid = threadIdx.x;
+    unsigned long long moved = 0;
+
+    if (!init_mode) {
+        if (tid == 0) s_nempty = 0;
+        __syncthreads();
+        for (uint32_t c = tid; c < k; c += 1024) {
+            const unsigned long long wsum = d.sums[c * DW + D];
+            d.weights[c] = wsum;
+            if (wsum) {
+                for (int j = 0; j < D; j++) d.cen[c * D + j] = int32_t(d.sums[c * DW + j] / wsum);
+            } else {
+                atomicAdd(&s_nempty, 1u);
+            }
+        }
+        moved = d.sums[k * DW];
+        __syncthreads();
+        const uint32_t nempty = s_nempty;
+        if (nempty && d.world > 1) {
+            if (tid == 0) d.st->dist_empty = 1;  // repaired by the host path (cniic_kmeans_run)
+        } else if (nempty) {
+            // deterministic stand-in for kmeans.rs:117-134 (see header): heaviest cluster = victim
+            if (tid == 0) {
+                uint32_t ne = 0, victim = 0;
+                unsigned long long bw = 0;
+                for (uint32_t c = 0; c < k; c++) {
+                    const unsigned long long wsum = d.weights[c];
+                    if (!wsum) s_empty[ne++] = uint16_t(c);
+                    else if (wsum > bw) { bw = wsum; victim = c; }
+                }
+                s_victim = victim;
+            }
+            __syncthreads();
+            const uint32_t victim = s_victim;
+            uint32_t found = 0;
+            for (unsigned long long base = 0; base < d.n_local && found < nempty; base += 1024) {
+                const unsigned long long i = base + tid;
+                const bool is = i < d.n_local && d.assign[i] == victim;
+                uint32_t tot;
+                const uint32_t r = block_rank(is, s_warp, &tot);
+                if (is && found + r < nempty) s_found[found + r] = uint32_t(i);
+                found += tot;
+            }
+            __syncthreads();
+            const uint32_t m = min(found, nempty);
+            for (uint32_t j = tid; j < nempty; j += 1024) {
+                int32_t v[D];
+                fetch_point<D>(d, s_found[j % m], v);
+                for (int q = 0; q < D; q++) d.cen[s_empty[j] * D + q] = v[q];
+            }
+            if (tid == 0) s_m = m;
+        }
+        __syncthreads();
+    }
+
+    // ---- build the scan table: even-|c|^2 class first, then odd, each in ascending id order, padded to G ----
+    uint32_t n0 = 0;
+    for (int cls = 0; cls < 2; cls++) {
+        uint32_t placed = 0;
+        const uint32_t start = cls == 0 ? 0 : (n0 + G - 1) / G * G;
+        for (uint32_t cb = 0; cb < k; cb += 1024) {
+            const uint32_t c = cb + tid;
+            int32_t v[D];
+            uint32_t nrm = 0;
+            bool flag = false;
+            if (c < k) {
+                for (int j = 0; j < D; j++) { v[j] = d.cen[c * D + j]; nrm += uint32_t(v[j] * v[j]); }
+                flag = int(nrm & 1) == cls;
+            }
+            uint32_t tot;
+            const uint32_t r = block_rank(flag, s_warp, &tot);
+            if (flag) {
+                const uint32_t e = start + placed + r;
+                const int rgb0 = D == 5 ? 2 : 0;
+                d.t_cpk[e] = uint32_t(v[rgb0]) | (uint32_t(v[rgb0 + 1]) << 8) | (uint32_t(v[rgb0 + 2]) << 16);
+                if (D == 5) d.t_cxy[e] = uint32_t(v[0]) | (uint32_t(v[1]) << 16);
+                d.t_bias[e] = -int(nrm >> 1);
+                d.t_id[e] = uint16_t(c);
+                d.t_pos[c] = uint16_t(e);
+            }
+            placed += tot;
+        }
+        const uint32_t end = start + (placed + G - 1) / G * G;
+        for (uint32_t e = start + placed + tid; e < end; e += 1024) {
+            d.t_cpk[e] = 0;
+            if (D == 5) d.t_cxy[e] = 0;
+            d.t_bias[e] = DUMMY;
+            d.t_id[e] = 0;
+        }
+        if (cls == 0) n0 = placed;
+        else if (tid == 0) {
+            d.st->ng0 = (n0 + G - 1) / G;
+            d.st->ngroups = (n0 + G - 1) / G + (placed + G - 1) / G;
+        }
+    }
+    for (uint32_t i = tid; i < k * DW + 1; i += 1024) d.sums[i] = 0ull;
+    if (tid == 0) {
+        if (init_mode) {
+            d.st->iter = 0; d.st->done = 0; d.st->empty_events = 0; d.st->n_empty_last = 0; d.st->dist_empty = 0;
+            d.st->moved_last = 0; d.st->moved_total = 0;
+        } else {
+            d.st->iter += 1;
+            d.st->moved_last = moved;
+            d.st->moved_total += moved;
+            d.st->n_empty_last = s_nempty;
+            d.st->empty_events += s_nempty;
+            if (moved == 0) d.st->done = 1;
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// host side: session object
+// ------------------------------------------------------------------------------------------------------------
+
+struct cniic_kmeans {
+    cniic_ctx *ctx = nullptr;
+    cniic_kmeans_desc desc{};
+    int D = 3;
+    KmDev dev{};
+    uint8_t *own_rgb = nullptr;
+    uint32_t *own_wts = nullptr;
+    void *pool = nullptr;  // one allocation for table + sums + centroids + state
+    KmState *h_state = nullptr;  // pinned
+    size_t smem = 0;
+    int grid = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t launches = 0;
+};
+
+static int km_launch_assign(cniic_kmeans *km) {
+    cniic_ctx *ctx = km->ctx;
+    if (km->D == 5) km_assign_xyrgb<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    else if (km->dev.wts) km_assign_rgb<true><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    else km_assign_rgb<false><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    km->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+static int km_launch_finalize(cniic_kmeans *km, int init_mode) {
+    cniic_ctx *ctx = km->ctx;
+    if (km->D == 5) km_finalize<5><<<1, 1024, 0, ctx->stream>>>(km->dev, init_mode);
+    else km_finalize<3><<<1, 1024, 0, ctx->stream>>>(km->dev, init_mode);
+    km->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, cniic_kmeans **out) {
+    if (!ctx || !desc || !out) return CNIIC_ERR_BAD_ARG;
+    *out = nullptr;
+    if (desc->k == 0 || desc->k > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d", CNIIC_MAX_K);
+    if (desc->kind != CNIIC_POINTS_RGB && desc->kind != CNIIC_POINTS_XYRGB) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "bad point kind");
+    if (!desc->rgb && desc->n_local) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "null points");
+    if (desc->n_total / desc->k == 0) return cniic_set_error(ctx, CNIIC_ERR_TOO_FEW_POINTS, "fewer points (%llu) than clusters (%u)", (unsigned long long)desc->n_total, desc->k);
+    if (desc->n_total >= (1ull << 31)) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "at most 2^31-1 points");
+    const int D = desc->kind == CNIIC_POINTS_XYRGB ? 5 : 3;
+    if (D == 5) {
+        if (desc->w == 0 || desc->w > CNIIC_MAX_DIM || (uint64_t)desc->y0 + desc->h_local > CNIIC_MAX_DIM)
+            return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "image dimensions must be in 1..%d", CNIIC_MAX_DIM);
+        if ((uint64_t)desc->w * desc->h_local != desc->n_local) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "n_local != w*h_local");
+        if (desc->weights) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "weights are only valid for RGB points");
+    }
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cniic_kmeans *km = new cniic_kmeans();
+    km->ctx = ctx;
+    km->desc = *desc;
+    km->D = D;
+    const uint32_t k = desc->k;
+    const int G = D == 5 ? G5 : G3;
+    const uint32_t KP = kpad_of(k, G);
+    auto fail = [&](int code) {
+        cniic_kmeans_close(km);
+        return code;
+    };
+#define KM_TRY(expr)                                                                                             \
+    do {                                                                                                         \
+        cudaError_t e__ = (expr);                                                                                \
+        if (e__ != cudaSuccess)                                                                                  \
+            return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)));   \
+    } while (0)
+    const uint8_t *d_rgb = desc->rgb;
+    const uint32_t *d_wts = desc->weights;
+    if (!desc->points_on_device) {
+        KM_TRY(cudaMalloc(&km->own_rgb, std::max<size_t>(16, desc->n_local * 3)));
+        KM_TRY(cudaMemcpyAsync(km->own_rgb, desc->rgb, desc->n_local * 3, cudaMemcpyHostToDevice, ctx->stream));
+        d_rgb = km->own_rgb;
+        if (desc->weights) {
+            KM_TRY(cudaMalloc(&km->own_wts, std::max<size_t>(16, desc->n_local * 4)));
+            KM_TRY(cudaMemcpyAsync(km->own_wts, desc->weights, desc->n_local * 4, cudaMemcpyHostToDevice, ctx->stream));
+            d_wts = km->own_wts;
+        }
+    }
+    // pool layout (all 16-byte aligned)
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 15) & ~size_t(15);
+        return o;
+    };
+    const size_t o_assign = take((desc->n_local + 8) * 2);
+    const size_t o_cpk = take(KP * 4), o_cxy = take(KP * 4), o_bias = take(KP * 4), o_id = take(KP * 2), o_pos = take(k * 2);
+    const size_t o_sums = take((size_t(k) * (D + 1) + 1) * 8), o_cen = take(size_t(k) * D * 4), o_w = take(size_t(k) * 8);
+    const size_t o_st = take(sizeof(KmState));
+    KM_TRY(cudaMalloc(&km->pool, off));
+    KM_TRY(cudaMemsetAsync(km->pool, 0, off, ctx->stream));
+    KM_TRY(cudaMallocHost(&km->h_state, sizeof(KmState)));
+    char *p = static_cast<char *>(km->pool);
+    KmDev &dv = km->dev;
+    dv.rgb = d_rgb;
+    dv.wts = d_wts;
+    dv.n_local = desc->n_local;
+    dv.n_total = desc->n_total;
+    dv.first_index = desc->first_index;
+    dv.w = desc->w;
+    dv.h_local = desc->h_local;
+    dv.y0 = desc->y0;
+    dv.k = k;
+    dv.tie = desc->tie_rule;
+    dv.world = ctx->world;
+    dv.assign = reinterpret_cast<uint16_t *>(p + o_assign);
+    dv.t_cpk = reinterpret_cast<uint32_t *>(p + o_cpk);
+    dv.t_cxy = reinterpret_cast<uint32_t *>(p + o_cxy);
+    dv.t_bias = reinterpret_cast<int *>(p + o_bias);
+    dv.t_id = reinterpret_cast<uint16_t *>(p + o_id);
+    dv.t_pos = reinterpret_cast<uint16_t *>(p + o_pos);
+    dv.sums = reinterpret_cast<unsigned long long *>(p + o_sums);
+    dv.cen = reinterpret_cast<int32_t *>(p + o_cen);
+    dv.weights = reinterpret_cast<unsigned long long *>(p + o_w);
+    dv.st = reinterpret_cast<KmState *>(p + o_st);
+
+    // shared memory + persistent grid
+    if (D == 5) {
+        km->smem = size_t(KP) * 16 + 8 * 192 * 4 + size_t(k) * 24 + KP * 2 + k * 2 + 16;
+        KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+    } else {
+        km->smem = size_t(KP) * 8 + KP * 2 + k * 2 + 16 + size_t(k) * 4 * (d_wts ? 8 : 4) + 16;
+        if (d_wts) KM_TRY(cudaFuncSetAttribute(km_assign_rgb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+        else KM_TRY(cudaFuncSetAttribute(km_assign_rgb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+    }
+    int per_sm = 0;
+    if (D == 5) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb, THREADS, km->smem));
+    else if (d_wts) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb<true>, THREADS, km->smem));
+    else KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb<false>, THREADS, km->smem));
+    if (per_sm < 1) return fail(cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "k = %u needs %zu bytes of shared memory", k, km->smem));
+    unsigned long long tiles = D == 5 ? (unsigned long long)((desc->w + 255) / 256) * ((desc->h_local + 7) / 8)
+                                      : (desc->n_local + TILE - 1) / TILE;
+    km->grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(tiles, (unsigned long long)per_sm * ctx->sm_count));
+    KM_TRY(cudaEventCreate(&km->ev0));
+    KM_TRY(cudaEventCreate(&km->ev1));
+#undef KM_TRY
+    *out = km;
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_kmeans_reset(cniic_kmeans *km, const int32_t *host_init_centroids) {
+    if (!km) return CNIIC_ERR_BAD_ARG;
+    cniic_ctx *ctx = km->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (km->desc.n_local) {
+        km_init_assign<<<std::max(1, std::min(ctx->sm_count * 8, int((km->desc.n_local + 255) / 256))), 256, 0, ctx->stream>>>(km->dev);
+        km->launches++;
+    }
+    if (host_init_centroids) {
+        CU_TRY(ctx, cudaMemcpyAsync(km->dev.cen, host_init_centroids, size_t(km->desc.k) * km->D * 4, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        if (ctx->world > 1 || km->desc.n_local != km->desc.n_total)
+            return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "a sharded session needs explicit initial centroids");
+        if (km->D == 5) km_init_centroids<5><<<(km->desc.k + 127) / 128, 128, 0, ctx->stream>>>(km->dev);
+        else km_init_centroids<3><<<(km->desc.k + 127) / 128, 128, 0, ctx->stream>>>(km->dev);
+        km->launches++;
+    }
+    CU_TRY(ctx, cudaGetLastError());
+    return km_launch_finalize(km, 1);
+}
+
+extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmeans_stats *stats) {
+    if (!km) return CNIIC_ERR_BAD_ARG;
+    cniic_ctx *ctx = km->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint32_t launches0 = km->launches;
+    const int DW = km->D + 1;
+    const bool dist = ctx->world > 1;
+    CU_TRY(ctx, cudaEventRecord(km->ev0, ctx->stream));
+    uint32_t issued = 0;
+    for (;;) {
+        uint32_t batch = dist ? 1 : 4;
+        if (max_iters) batch = std::min(batch, max_iters - issued);
+        for (uint32_t b = 0; b < batch; b++) {
+            ST_TRY(km_launch_assign(km));
+            if (dist) ST_TRY(cniic_nccl_allreduce_u64(ctx, km->dev.sums, size_t(km->desc.k) * DW + 1));
+            ST_TRY(km_launch_finalize(km, 0));
+        }
+        issued += batch;
+        CU_TRY(ctx, cudaMemcpyAsync(km->h_state, km->dev.st, sizeof(KmState), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (km->h_state->dist_empty)
+            return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "empty cluster in a multi-GPU run (repair not implemented for sharded points)");
+        if (km->h_state->done || (max_iters && issued >= max_iters)) break;
+    }
+    CU_TRY(ctx, cudaEventRecord(km->ev1, ctx->stream));
+    CU_TRY(ctx, cudaEventSynchronize(km->ev1));
+    float ms = 0.f;
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, km->ev0, km->ev1));
+    ctx->launches += km->launches - launches0;
+    const KmState &s = *km->h_state;
+    if (stats) {
+        stats->iterations = s.iter;
+        stats->empty_events = s.empty_events;
+        stats->moved_last = s.moved_last;
+        stats->moved_total = s.moved_total;
+        stats->converged = s.done;
+        stats->gpu_launches = km->launches - launches0;
+        stats->device_ms = ms;
+        stats->reserved = 0;
+    }
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_kmeans_get(cniic_kmeans *km, int32_t *out_centroids, uint64_t *out_weight, uint16_t *out_assign) {
+    if (!km) return CNIIC_ERR_BAD_ARG;
+    cniic_ctx *ctx = km->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint32_t k = km->desc.k;
+    if (out_centroids) CU_TRY(ctx, cudaMemcpyAsync(out_centroids, km->dev.cen, size_t(k) * km->D * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_weight) CU_TRY(ctx, cudaMemcpyAsync(out_weight, km->dev.weights, size_t(k) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_assign && km->desc.n_local)
+        CU_TRY(ctx, cudaMemcpyAsync(out_assign, km->dev.assign, km->desc.n_local * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+extern "C" const uint16_t *cniic_kmeans_device_assign(cniic_kmeans *km) { return km ? km->dev.assign : nullptr; }
+
+extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
+    if (!km) return;
+    cudaSetDevice(km->ctx->device);
+    cudaStreamSynchronize(km->ctx->stream);
+    if (km->own_rgb) cudaFree(km->own_rgb);
+    if (km->own_wts) cudaFree(km->own_wts);
+    if (km->pool) cudaFree(km->pool);
+    if (km->h_state) cudaFreeHost(km->h_state);
+    if (km->ev0) cudaEventDestroy(km->ev0);
+    if (km->ev1) cudaEventDestroy(km->ev1);
+    delete km;
+}
+
+// kmeans.rs:41-57 check_enough_active_clusters
+static int check_active(cniic_ctx *ctx, const uint64_t *weights, uint32_t k, uint64_t n) {
+    uint64_t active = 0;
+    for (uint32_t c = 0; c < k; c++) active += weights[c] > 0;
+    uint64_t min_cc = (uint64_t)(0.99 * (double)k);
+    if (n < min_cc) min_cc = n;
+    if (active < min_cc)
+        return cniic_set_error(ctx, CNIIC_ERR_TOO_FEW_ACTIVE, "Not enough active clusters: requested %u, got %llu (min allowed: %llu)", k,
+                               (unsigned long long)active, (unsigned long long)min_cc);
+    return CNIIC_OK;
+}
+
+static int km_oneshot(cniic_ctx *ctx, const cniic_kmeans_desc &desc, uint32_t max_iters, std::vector<int32_t> &cen,
+                      uint64_t *out_weight, uint16_t *out_assign, cniic_kmeans_stats *stats) {
+    cniic_kmeans *km = nullptr;
+    ST_TRY(cniic_kmeans_open(ctx, &desc, &km));
+    int rc = cniic_kmeans_reset(km, nullptr);
+    if (rc == CNIIC_OK) rc = cniic_kmeans_run(km, max_iters, stats);
+    std::vector<uint64_t> wts(desc.k);
+    cen.resize(size_t(desc.k) * km->D);
+    if (rc == CNIIC_OK) rc = cniic_kmeans_get(km, cen.data(), wts.data(), out_assign);
+    cniic_kmeans_close(km);
+    if (rc != CNIIC_OK) return rc;
+    if (out_weight) memcpy(out_weight, wts.data(), desc.k * sizeof(uint64_t));
+    return check_active(ctx, wts.data(), desc.k, desc.n_total);
+}
+
+extern "C" int cniic_kmeans_rgb(cniic_ctx *ctx, const uint8_t *rgb, const uint32_t *counts, size_t n, uint32_t k, uint32_t max_iters,
+                                int tie_rule, uint8_t *out_centroids, uint64_t *out_weight, uint16_t *out_assign,
+                                cniic_kmeans_stats *stats) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    if (!rgb || !out_centroids) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "null buffer");
+    cniic_kmeans_desc desc{};
+    desc.kind = CNIIC_POINTS_RGB;
+    desc.k = k;
+    desc.tie_rule = tie_rule;
+    desc.n_local = desc.n_total = n;
+    desc.rgb = rgb;
+    desc.weights = counts;
+    std::vector<int32_t> cen;
+    const int rc = km_oneshot(ctx, desc, max_iters, cen, out_weight, out_assign, stats);
+    if (rc == CNIIC_OK || rc == CNIIC_ERR_TOO_FEW_ACTIVE)
+        for (size_t i = 0; i < size_t(k) * 3; i++) out_centroids[i] = (uint8_t)cen[i];
+    return rc;
+}
+
+extern "C" int cniic_kmeans_xyrgb(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, uint32_t k, uint32_t max_iters,
+                                  int tie_rule, uint32_t *out_xy, uint8_t *out_rgb, uint64_t *out_weight, uint16_t *out_assign,
+                                  cniic_kmeans_stats *stats) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    if (!rgb || !out_xy || !out_rgb) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "null buffer");
+    cniic_kmeans_desc desc{};
+    desc.kind = CNIIC_POINTS_XYRGB;
+    desc.k = k;
+    desc.tie_rule = tie_rule;
+    desc.n_local = desc.n_total = (uint64_t)w * h;
+    desc.w = w;
+    desc.h_local = h;
+    desc.rgb = rgb;
+    std::vector<int32_t> cen;
+    const int rc = km_oneshot(ctx, desc, max_iters, cen, out_weight, out_assign, stats);
+    if (rc == CNIIC_OK || rc == CNIIC_ERR_TOO_FEW_ACTIVE)
+        for (uint32_t c = 0; c < k; c++) {
+            out_xy[2 * c] = (uint32_t)cen[5 * c];
+            out_xy[2 * c + 1] = (uint32_t)cen[5 * c + 1];
+            for (int j = 0; j < 3; j++) out_rgb[3 * c + j] = (uint8_t)cen[5 * c + 2 + j];
+        }
+    return rc;
+}
