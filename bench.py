@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the cniic_b200 hot path (BASELINE.json metric: Mpixel*iterations/s of Lloyd K-means).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1|c4] [--impl ours|reference]
+
+A "step" = one pass of the hot path over one batch of synthetic input = kmeans::cluster with max_iters = ITERS
+(chunked init + ITERS fused assign/accumulate/finalize iterations) on the workload's image.
+  value  : whole-job throughput, points resident in HBM when the timed region starts (CUDA events, max over ranks)
+  e2e    : same metric through the host-buffer C-ABI call (cniic_kmeans_rgb / cniic_kmeans_xyrgb): pinned host image
+           -> H2D -> kernels -> centroids/weights D2H, all inside the timed region
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ITERS = 10          # Lloyd iterations per step (fixed max_iters = 10 for throughput)
+SEED = 0xC0FFEE
+
+WORKLOADS = {
+    # name: (kind, w, h, k, blobs, description, scaling)
+    "c1": ("rgb", 512, 512, 16, 24, "cluster-colors k=16 on one 512x512 synthetic RGB image", "weak"),
+    "c2": ("rgb", 4096, 4096, 256, 192, "cluster-colors k=256 on a 4096x4096 synthetic RGB image", "weak"),
+    "c3": ("xyrgb", 7680, 4320, 2048, 2048, "voronoi k=2048 (x,y,r,g,b) on a 7680x4320 synthetic image", "strong"),
+    "c4": ("rgb", 1024, 1024, 64, 16, "cluster-colors k=64, 1024x1024 synthetic images (one image per step per GPU)", "weak"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "sm_max_mhz": d.get("sm_max_mhz", 1965.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_leg(kind, w, h, k, blobs, seed, budget_px, threads):
+    """Times the CPU restatement of the reference's kmeans.rs (oracle, VERBATIM mode = neighbour-list pruning) on a
+    bounded sample of the workload: `threads` independent crops, one per host thread, like bench.rs:27 (rayon, one
+    image per worker).  Returns (Mpx*iter/s aggregate, description, seconds)."""
+    import oracle as O
+    import cniic_b200 as cb
+    side_w = min(w, 1024)
+    side_h = max(8, min(h, budget_px // side_w))
+    crops = [cb.synth_image_host(side_w, side_h, seed + 1000 * i, max(1, blobs * side_w * side_h // (w * h)), 0, side_h)
+             for i in range(threads)]
+    kk = min(k, side_w * side_h)
+    iters_done = [0] * threads
+
+    def work(i):
+        if kind == "rgb":
+            r = O.kmeans_rgb(crops[i], kk, mode=O.MODE_VERBATIM, max_iters=ITERS, allow_inactive=True)
+        else:
+            r = O.kmeans_xyrgb(crops[i], kk, mode=O.MODE_VERBATIM, max_iters=ITERS, allow_inactive=True)
+        iters_done[i] = r.iterations
+
+    O.lib()
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    px_iter = sum(side_w * side_h * it for it in iters_done)
+    desc = (f"{threads} independent {side_w}x{side_h} crops of the workload image generator, k={kk}, {ITERS} Lloyd iterations each, "
+            f"one crop per host thread (bench.rs:27 image-level parallelism); oracle VERBATIM mode = C restatement of kmeans.rs "
+            f"incl. neighbour-list pruning, not the Rust binary")
+    return px_iter / dt / 1e6, desc, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-px", type=int, default=0, help="pixels per CPU-baseline crop (0 = default for the workload)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    K = max(args.steps, 1)
+    kind, w, h, k, blobs, desc, scaling = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    D = 5 if kind == "xyrgb" else 3
+    cores = os.cpu_count() or 1
+    cpu_px = args.cpu_px or (512 * 512 if kind == "rgb" else 256 * 256)
+
+    # ------------------------------------------------------------------ reference arm (CPU) -----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = max(1, min(cores, 32))
+        vals, descr = [], ""
+        for i in range(W + K):
+            v, descr, dt = cpu_reference_leg(kind, w, h, k, blobs, SEED + i, cpu_px, threads)
+            if i >= W:
+                vals.append((v, dt))
+        value = float(np.mean([v for v, _ in vals]))
+        ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+        line = {"impl": "reference", "metric": "Mpixel*iter/s Lloyd K-means", "value": value, "unit": "Mpx*iter/s",
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "k": k, "iters_per_step": ITERS, "sample": descr},
+                "cpu_baseline": {"value": value, "unit": "Mpx*iter/s", "cores": threads, "kind": "port", "sample": descr},
+                "e2e": {"value": value, "unit": "Mpx*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU) -----------------------
+    import torch
+    import torch.distributed as dist
+    import cniic_b200 as cb
+    from cniic_b200 import dist as cdist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    independent = world == 1 or args.workload == "c4"   # no data-path collective: plain per-GPU context
+    ctx = cb.Context(local_rank) if independent else cdist.make_context(local_rank)
+    sctx = ctx
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    # shard plan: weak scaling = every rank owns a full w x h slab of a w x (h*world) image; strong = rows of one image
+    if independent:
+        h_total, y0, h_local = h, 0, h
+    elif scaling == "weak":
+        h_total, y0, h_local = h * world, h * rank, h
+    else:
+        h_total = h
+        y0, h_local = cdist.row_shard(h, world, rank)
+    n_local, n_total = w * h_local, w * h_total
+    d_img = ctx.device_alloc(n_local * 3)
+    cb.synth_image_device(ctx, d_img, w, h_local, SEED + int(args.workload[1]) + (rank if independent else 0), blobs, y0=y0,
+                          h_total=h_total)
+    ctx.sync()
+    d_img_s = d_img
+    kind_id = cb.POINTS_XYRGB if kind == "xyrgb" else cb.POINTS_RGB
+    if independent:
+        sess = cb.KMeansSession(sctx, kind_id, k, d_img_s, n_local, w=w, h_local=h_local, on_device=True)
+        init = None
+    else:
+        first = y0 * w
+        sess = cb.KMeansSession(sctx, kind_id, k, d_img_s, n_local, n_total=n_total, first_index=first, w=w, h_local=h_local,
+                                y0=y0, on_device=True)
+        host_local = np.zeros((h_local, w, 3), np.uint8)
+        ctx.d2h(host_local, d_img)
+        init = cdist.gather_init_centroids(D, host_local, w, y0 if D == 5 else first, n_total, k, device=torch.device("cuda", local_rank))
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        sess.reset(init)
+        return sess.run(ITERS)
+
+    for _ in range(W):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sctx.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    assign_ms, iters_run = [], 0
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xff)           # evict the image from L2 between timed steps (untimed)
+        torch.cuda.synchronize()
+        ev[i][0].record(stream)
+        st = one_step()
+        ev[i][1].record(stream)
+        assign_ms.append(st.assign_ms_avg)
+        iters_run += st.iterations
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = sctx.launches - launches0
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    px_total = n_total if not independent else n_local * world
+    value = px_total * ITERS * K / (total_ms * 1e-3) / 1e6
+
+    # ---- e2e: host buffers through the one-shot C-ABI call (H2D + kernels + D2H inside the timed region) ----
+    pinned = torch.empty((h_local, w, 3), dtype=torch.uint8).pin_memory()
+    host_img = pinned.numpy()
+    ctx.d2h(host_img, d_img)
+    e2e = None
+    if independent:
+        def e2e_step():
+            if kind == "rgb":
+                return sctx.kmeans_rgb(host_img, k, max_iters=ITERS, want_assign=False)
+            return sctx.kmeans_xyrgb(host_img, k, max_iters=ITERS, want_assign=False)
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            r = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_local * world * ITERS * K / float(tt.item()) / 1e6, "unit": "Mpx*iter/s",
+               "h2d_bytes_per_step": int(n_local * 3), "d2h_bytes_per_step": int(k * 3 * 4 + k * 8 + 64),
+               "api": "cniic_kmeans_rgb" if kind == "rgb" else "cniic_kmeans_xyrgb"}
+    else:
+        # sharded session: per step the shard is re-uploaded from pinned host memory and centroids/weights read back
+        def e2e_step():
+            s2 = cb.KMeansSession(sctx, kind_id, k, host_img, n_local, n_total=n_total, first_index=y0 * w, w=w, h_local=h_local,
+                                  y0=y0, on_device=False)
+            s2.reset(init)
+            s2.run(ITERS)
+            out = s2.get(want_assign=False)
+            s2.close()
+            return out
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_total * ITERS * K / float(tt.item()) / 1e6, "unit": "Mpx*iter/s",
+               "h2d_bytes_per_step": int(n_local * 3), "d2h_bytes_per_step": int(k * D * 4 + k * 8),
+               "api": "cniic_kmeans_open/reset/run/get (row-sharded session, host points)"}
+
+    if rank != 0:
+        sess.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (fused assign+accumulate), measured live with CUDA events ----
+    pk = peaks()
+    a_ms = float(np.mean(assign_ms))
+    flops_per_launch = (2 * D + 1) * n_local * k            # D FMA + 1 compare per pixel-centroid pair
+    fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+    achieved = flops_per_launch / (a_ms * 1e-3) / 1e12
+    bytes_per_launch = 3 * n_local                          # RGB read once per iteration (assignments: +2 B r/w not counted)
+    roofline = {"bound": "fp32", "kernel": "km_assign_xyrgb" if D == 5 else "km_assign_rgb", "achieved": achieved,
+                "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                "peak_source": f"148 SM x 128 FP32 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']} sm_max_mhz); the kernel issues "
+                               "IDP.4A/IDP.2A integer dot products, so frac > FFMA-issue ceilings is possible (DESIGN.md)",
+                "launch_ms": a_ms, "algorithmic_flops_per_launch": flops_per_launch,
+                "hbm": {"achieved": bytes_per_launch / (a_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": bytes_per_launch / (a_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "source": pk["source"]}}
+
+    cpu = None
+    if not args.no_cpu:
+        threads = 1
+        v, descr, dt = cpu_reference_leg(kind, w, h, k, blobs, SEED, cpu_px, threads)
+        cpu = {"value": v, "unit": "Mpx*iter/s", "cores": threads, "kind": "port", "sample": descr, "seconds": dt}
+
+    line = {"metric": "Mpixel*iter/s Lloyd K-means", "value": value, "unit": "Mpx*iter/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": desc + (f", {world} slabs of {w}x{h} (row-sharded {w}x{h_total}, NCCL u64 partial-sum all-reduce)"
+                                           if world > 1 and not independent else ""),
+                       "k": k, "dims": D, "iters_per_step": ITERS, "pixels": int(px_total),
+                       "parallelism": "1 GPU" if world == 1 else (f"{world} independent images" if independent else f"row-sharded x{world}"),
+                       "l2": "512 MiB buffer written between timed steps (L2 flush); the image stays L2/HBM resident across the "
+                             "iterations of one step, as the algorithm iterates over it"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches // K), "clocks": clocks,
+            "iterations_run": iters_run, "wall_s": t_wall}
+    print(json.dumps(line), flush=True)
+    sess.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

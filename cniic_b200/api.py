@@ -162,6 +162,131 @@ class Context:
     def kmeans_session(self, **kw) -> "KMeansSession":
         return KMeansSession(self, **kw)
 
+    # ---- utils::count_freqs (utils.rs:4-16) in canonical ascending-key order ----
+    def hist_rgb(self, rgb):
+        """Distinct colours and their counts; keys = r<<16|g<<8|b ascending (clusterc.rs:21, huf.rs:30)."""
+        rgb = _u8(rgb).reshape(-1, 3)
+        n = len(rgb)
+        cap = max(1, min(n, 1 << 24))
+        keys = np.zeros(cap, np.uint32)
+        cnts = np.zeros(cap, np.uint64)
+        u = C.c_size_t(0)
+        self.check(self._lib.cniic_hist_rgb(self.h, _ptr(rgb), C.c_size_t(n), _ptr(keys), _ptr(cnts), C.c_size_t(cap),
+                                            C.byref(u)))
+        return keys[:u.value].copy(), cnts[:u.value].copy()
+
+    def hist_delta(self, img):
+        """Histogram of the joint SignedColor symbols of the delta stream (hilbertc.rs:409-414 via huf.rs:30)."""
+        img = _u8(img)
+        h, w = img.shape[:2]
+        cap = max(1, h * w)
+        keys = np.zeros(cap, np.uint32)
+        cnts = np.zeros(cap, np.uint64)
+        u = C.c_size_t(0)
+        self.check(self._lib.cniic_hist_delta(self.h, _ptr(img), C.c_uint32(w), C.c_uint32(h), _ptr(keys), _ptr(cnts),
+                                              C.c_size_t(cap), C.byref(u)))
+        return keys[:u.value].copy(), cnts[:u.value].copy()
+
+    def recolor_rgb(self, rgb, keys, assign, centroids):
+        """clusterc.rs:31-47: map every pixel to the colour of the centroid its colour belongs to."""
+        rgb = _u8(rgb)
+        flat = rgb.reshape(-1, 3)
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        assign = np.ascontiguousarray(assign, dtype=np.uint16)
+        cen = _u8(centroids).reshape(-1, 3)
+        out = np.zeros_like(flat)
+        self.check(self._lib.cniic_recolor_rgb(self.h, _ptr(flat), C.c_size_t(len(flat)), _ptr(keys), _ptr(assign),
+                                               C.c_size_t(len(keys)), _ptr(cen), C.c_uint32(len(cen)), _ptr(out)))
+        return out.reshape(rgb.shape)
+
+    def cluster_colors(self, img, k, max_iters=0, tie=L.TIE_KEEP_CURRENT):
+        """Front half of ClusterColors::encode (clusterc.rs:19-47): returns (recoloured image, centroids, stats)."""
+        img = _u8(img)
+        h, w = img.shape[:2]
+        out = np.zeros_like(img)
+        cen = np.zeros((max(k, 1), 3), np.uint8)
+        st = L.KMeansStats()
+        self.check(self._lib.cniic_cluster_colors(self.h, _ptr(img), C.c_uint32(w), C.c_uint32(h), C.c_uint32(k),
+                                                  C.c_uint32(max_iters), tie, _ptr(out), _ptr(cen), C.byref(st)))
+        return out, cen[:k], st
+
+    # ---- voronoi decode fill (clusterc.rs:179-186) ----
+    def voronoi_fill(self, cxy, crgb, w, h):
+        cxy = np.ascontiguousarray(cxy, dtype=np.uint32).reshape(-1, 2)
+        crgb = _u8(crgb).reshape(-1, 3)
+        out = np.zeros((h, w, 3), np.uint8)
+        self.check(self._lib.cniic_voronoi_fill(self.h, _ptr(cxy), _ptr(crgb), C.c_uint32(len(cxy)), C.c_uint32(w),
+                                                C.c_uint32(h), _ptr(out)))
+        return out
+
+    # ---- hilbert::iter / linearize (hilbert.rs:34-43), DiffStream (hilbertc.rs:449-477) ----
+    def hilbert_xy(self, w, h):
+        out = np.zeros((w * h, 2), np.uint32)
+        self.check(self._lib.cniic_hilbert_xy(self.h, C.c_uint32(w), C.c_uint32(h), _ptr(out)))
+        return out
+
+    def hilbert_gather(self, img):
+        img = _u8(img)
+        h, w = img.shape[:2]
+        out = np.zeros((w * h, 3), np.uint8)
+        self.check(self._lib.cniic_hilbert_gather_rgb(self.h, _ptr(img), C.c_uint32(w), C.c_uint32(h), _ptr(out)))
+        return out
+
+    def delta(self, img):
+        img = _u8(img)
+        h, w = img.shape[:2]
+        out = np.zeros((w * h, 3), np.int16)
+        self.check(self._lib.cniic_delta_i16(self.h, _ptr(img), C.c_uint32(w), C.c_uint32(h), _ptr(out)))
+        return out
+
+    def undelta(self, diff, w, h):
+        diff = np.ascontiguousarray(diff, dtype=np.int16)
+        out = np.zeros((h, w, 3), np.uint8)
+        self.check(self._lib.cniic_undelta_rgb(self.h, _ptr(diff), C.c_uint32(w), C.c_uint32(h), _ptr(out)))
+        return out
+
+    def sse(self, a, b) -> int:
+        """Exact integer sum of squared channel errors; MSE = sse / (w*h) (bench.rs:95-104)."""
+        a, b = _u8(a), _u8(b)
+        out = C.c_uint64(0)
+        self.check(self._lib.cniic_sse_rgb(self.h, _ptr(a), _ptr(b), C.c_size_t(a.size // 3), C.byref(out)))
+        return int(out.value)
+
+    # ---- Codec::encode / Codec::decode (codec.rs:14-19) ----
+    def codec_encode(self, codec: str, img) -> bytes:
+        img = _u8(img)
+        h, w = img.shape[:2]
+        need = C.c_size_t(0)
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, np.uint8)
+            rc = self._lib.cniic_codec_encode(self.h, codec.encode(), _ptr(img), C.c_uint32(w), C.c_uint32(h), _ptr(out),
+                                              C.c_size_t(cap), C.byref(need))
+            if rc == L.ERR_BUFFER_TOO_SMALL and need.value > cap:
+                cap = need.value
+                continue
+            self.check(rc)
+            return out[:need.value].tobytes()
+
+    def codec_decode(self, codec: str, data: bytes):
+        """Returns the decoded (h, w, 3) image or None (Codec::decode -> Option<Img>)."""
+        buf = np.frombuffer(data, np.uint8)
+        w, h = C.c_uint32(0), C.c_uint32(0)
+        rc = self._lib.cniic_codec_decode(self.h, codec.encode(), _ptr(buf), C.c_size_t(len(buf)), C.byref(w),
+                                          C.byref(h), None, C.c_size_t(0))
+        if rc == L.ERR_DECODE:
+            return None
+        self.check(rc)
+        if w.value * h.value > (1 << 28):
+            return None
+        out = np.zeros((h.value, w.value, 3), np.uint8)
+        rc = self._lib.cniic_codec_decode(self.h, codec.encode(), _ptr(buf), C.c_size_t(len(buf)), C.byref(w),
+                                          C.byref(h), _ptr(out), C.c_size_t(out.size // 3))
+        if rc == L.ERR_DECODE:
+            return None
+        self.check(rc)
+        return out
+
 
 class KMeansSession:
     """Points resident in HBM across iterations (cniic_kmeans_open/reset/run/get)."""

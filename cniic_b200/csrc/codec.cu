@@ -1,0 +1,459 @@
+// codec.cu -- host side of the reference's Codec trait (src/codec.rs:14-19) for the codecs on the hot path:
+//   ClusterColors (src/codec/clusterc.rs:14-62), VoronoiCluster (clusterc.rs:143-194), Delta (src/codec/hilbertc.rs:402-439),
+//   Hufman (src/codec/hufc.rs), Hilbert RLE exact (hilbertc.rs:12-96).
+// Wire formats follow src/ser.rs, src/huf.rs and src/bit.rs byte for byte (DESIGN.md "Wire formats").
+// The per-pixel work (K-means, histograms, recolour, Hilbert gather, delta, fill, scatter) runs on the GPU; the Huffman
+// tree (<= #symbols nodes) and the sequential bit packing / run-length pass run on the host.
+#include <cctype>
+#include <cstring>
+#include <queue>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "stages.cuh"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes < 16 ? 16 : bytes); }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+
+// ---- codec expression parsing (clusterc.rs:116-141, 274-297; hilbertc.rs:337-395, 574-582; hufc.rs:51-63) ----
+enum CodecKind { CK_NONE, CK_CLUSTER_COLORS, CK_VORONOI, CK_DELTA, CK_HUFMAN, CK_HILBERT_RLE };
+struct CodecSpec { CodecKind kind = CK_NONE; uint32_t arg = 0; };
+
+// finds name '(' digits ')' anywhere in s (the reference's regexes are unanchored)
+bool find_call(const std::string &s, const std::vector<std::string> &names, uint32_t *arg) {
+    for (const std::string &nm : names) {
+        size_t pos = 0;
+        while ((pos = s.find(nm + "(", pos)) != std::string::npos) {
+            size_t i = pos + nm.size() + 1, j = i;
+            unsigned long long v = 0;
+            while (j < s.size() && isdigit((unsigned char)s[j]) && j - i < 10) v = v * 10 + (s[j++] - '0');
+            if (j > i && j < s.size() && s[j] == ')' && v <= 0xffffffffull) { *arg = (uint32_t)v; return true; }
+            pos++;
+        }
+    }
+    return false;
+}
+
+CodecSpec parse_codec(const char *expr) {
+    CodecSpec sp;
+    if (!expr) return sp;
+    const std::string s(expr);
+    std::string lower;
+    for (char c : s) lower.push_back((char)tolower((unsigned char)c));
+    if (lower == "hufman") { sp.kind = CK_HUFMAN; return sp; }
+    // c(?:luster)?-?col(?:ors)?\((\d+)\)
+    std::vector<std::string> cc;
+    for (const char *a : {"cluster", "c"})
+        for (const char *b : {"-", ""})
+            for (const char *c : {"colors", "col"}) cc.push_back(std::string(a) + b + c);
+    uint32_t arg = 0;
+    if (find_call(s, cc, &arg)) { sp.kind = CK_CLUSTER_COLORS; sp.arg = arg; return sp; }
+    if (find_call(s, {"voronoi"}, &arg)) { sp.kind = CK_VORONOI; sp.arg = arg; return sp; }
+    if (s == "delta") { sp.kind = CK_DELTA; return sp; }
+    if (s == "hilbert(rle)" || s == "hilbert(rle(0))") { sp.kind = CK_HILBERT_RLE; return sp; }
+    return sp;
+}
+
+// ---- byte sink / source (ser.rs: little endian, usize as u64, Rgb as a slice = u64 length + 3 bytes) ----
+struct Sink {
+    std::vector<uint8_t> v;
+    uint8_t cur = 0;
+    int nbits = 0;
+    void u8(uint8_t b) { v.push_back(b); }
+    void u32(uint32_t x) { for (int i = 0; i < 4; i++) v.push_back((uint8_t)(x >> (8 * i))); }
+    void u64(uint64_t x) { for (int i = 0; i < 8; i++) v.push_back((uint8_t)(x >> (8 * i))); }
+    void rgb(uint32_t key) { u64(3); u8(key >> 16); u8(key >> 8); u8(key); }
+    // bit.rs:209-253 : MSB first, zero padded
+    void bits(uint64_t code, uint32_t len) {
+        while (len) {
+            const uint32_t take = std::min<uint32_t>(len, 8 - nbits);
+            const uint32_t chunk = (uint32_t)((code >> (len - take)) & ((1u << take) - 1));
+            cur = (uint8_t)(cur | (chunk << (8 - nbits - take)));
+            nbits += take;
+            len -= take;
+            if (nbits == 8) { v.push_back(cur); cur = 0; nbits = 0; }
+        }
+    }
+    void flush() { if (nbits) { v.push_back(cur); cur = 0; nbits = 0; } }
+};
+
+struct Source {
+    const uint8_t *p;
+    size_t len, pos = 0;
+    bool u8(uint8_t *b) { if (pos >= len) return false; *b = p[pos++]; return true; }
+    bool u32(uint32_t *x) { if (len - pos < 4) return false; *x = 0; for (int i = 0; i < 4; i++) *x |= (uint32_t)p[pos++] << (8 * i); return true; }
+    bool u64(uint64_t *x) { if (len - pos < 8) return false; *x = 0; for (int i = 0; i < 8; i++) *x |= (uint64_t)p[pos++] << (8 * i); return true; }
+};
+
+// ---- Huffman (huf.rs:58-117): deterministic heap order (freq, creation sequence); first pop = left = bit 0 ----
+struct HufTree {
+    struct Node { int left, right; uint32_t sym; };
+    std::vector<Node> nodes;
+    int root = -1;
+    std::vector<uint64_t> code;   // per symbol, MSB-first in the low `len` bits
+    std::vector<uint8_t> len;
+};
+
+bool huf_build(const std::vector<uint64_t> &freq, HufTree *T) {
+    const size_t n = freq.size();
+    if (n == 0) return false;
+    typedef std::pair<std::pair<uint64_t, uint32_t>, int> Item;  // ((freq, seq), node)
+    std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
+    T->nodes.reserve(2 * n);
+    std::vector<uint64_t> nf;
+    nf.reserve(2 * n);
+    for (size_t i = 0; i < n; i++) {
+        T->nodes.push_back({-1, -1, (uint32_t)i});
+        nf.push_back(freq[i]);
+        heap.push({{freq[i], (uint32_t)i}, (int)i});
+    }
+    while (heap.size() > 1) {
+        const int l = heap.top().second; heap.pop();
+        const int r = heap.top().second; heap.pop();
+        const int id = (int)T->nodes.size();
+        T->nodes.push_back({l, r, 0});
+        nf.push_back(nf[l] + nf[r]);
+        heap.push({{nf[id], (uint32_t)id}, id});
+    }
+    T->root = heap.top().second;
+    T->code.assign(n, 0);
+    T->len.assign(n, 0);
+    // iterative DFS assigning codes
+    struct Fr { int node; uint64_t code; uint32_t len; };
+    std::vector<Fr> st{{T->root, 0, 0}};
+    while (!st.empty()) {
+        const Fr f = st.back();
+        st.pop_back();
+        const HufTree::Node &nd = T->nodes[f.node];
+        if (nd.left < 0) {
+            if (f.len > 64) return false;
+            T->code[nd.sym] = f.code;
+            T->len[nd.sym] = (uint8_t)f.len;
+        } else {
+            st.push_back({nd.right, (f.code << 1) | 1, f.len + 1});
+            st.push_back({nd.left, f.code << 1, f.len + 1});
+        }
+    }
+    return true;
+}
+
+// huf.rs:296-321 pre-order: 0x00 + leaf payload | 0x01 + left + right
+template <class LeafFn>
+void huf_serialize(const HufTree &T, Sink &s, LeafFn leaf) {
+    std::vector<int> st{T.root};
+    while (!st.empty()) {
+        const int id = st.back();
+        st.pop_back();
+        const HufTree::Node &nd = T.nodes[id];
+        if (nd.left < 0) { s.u8(0); leaf(nd.sym); }
+        else { s.u8(1); st.push_back(nd.right); st.push_back(nd.left); }
+    }
+}
+
+struct DecTrie {
+    struct Node { int left, right; uint8_t val[11]; };
+    std::vector<Node> nodes;
+};
+
+// huf.rs:330-350 ; iterative to be safe against deep (malformed) tries
+bool huf_deserialize(Source &src, size_t sym_size, DecTrie *T) {
+    // stack of nodes waiting for children: (node id, number of children attached)
+    std::vector<std::pair<int, int>> st;
+    int root = -1;
+    for (;;) {
+        uint8_t tag;
+        if (!src.u8(&tag)) return false;
+        if (tag > 1) return false;
+        if (T->nodes.size() > (size_t(1) << 26)) return false;
+        const int id = (int)T->nodes.size();
+        T->nodes.push_back({-1, -1, {0}});
+        if (root < 0) root = id;
+        if (!st.empty()) {
+            if (st.back().second == 0) T->nodes[st.back().first].left = id;
+            else T->nodes[st.back().first].right = id;
+            st.back().second++;
+        }
+        if (tag == 0) {
+            for (size_t i = 0; i < sym_size; i++)
+                if (!src.u8(&T->nodes[id].val[i])) return false;
+            while (!st.empty() && st.back().second == 2) st.pop_back();
+            if (st.empty()) return true;
+        } else {
+            st.push_back({id, 0});
+        }
+    }
+}
+
+// huf.rs:187-206 trie walk over MSB-first bits; decodes exactly n symbols
+bool huf_decode(Source &src, const DecTrie &T, size_t sym_size, size_t n, uint8_t *out) {
+    size_t bit = src.pos * 8;
+    const size_t end = src.len * 8;
+    for (size_t i = 0; i < n; i++) {
+        int nd = 0;
+        while (T.nodes[nd].left >= 0) {
+            if (bit >= end) return false;
+            const int b = (src.p[bit >> 3] >> (7 - (bit & 7))) & 1;
+            bit++;
+            nd = b ? T.nodes[nd].right : T.nodes[nd].left;
+            if (nd < 0) return false;
+        }
+        memcpy(out + i * sym_size, T.nodes[nd].val, sym_size);
+    }
+    return true;
+}
+
+int finish(cniic_ctx *ctx, const Sink &s, uint8_t *out, size_t cap, size_t *out_len) {
+    *out_len = s.v.size();
+    if (s.v.size() > cap || (!out && !s.v.empty())) return cniic_set_error(ctx, CNIIC_ERR_BUFFER_TOO_SMALL, "need %zu bytes", s.v.size());
+    if (!s.v.empty()) memcpy(out, s.v.data(), s.v.size());
+    return CNIIC_OK;
+}
+
+// Hufman codec body over a DEVICE-resident image whose host copy is `host_rgb` (hufc.rs:12-17, huf.rs:22-43)
+int encode_hufman_body(cniic_ctx *ctx, const uint8_t *d_rgb, const uint8_t *host_rgb, size_t n, Sink &s) {
+    if (n == 0) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "empty image (huf.rs:95 asserts a non-empty alphabet)");
+    uint32_t *d_bins = nullptr, *d_keys = nullptr;
+    unsigned long long *d_counts = nullptr;
+    size_t u = 0;
+    int rc = cniic_dev_hist_rgb_bins(ctx, d_rgb, n, &d_bins);  // pass 1: count_freqs on the GPU
+    if (rc == CNIIC_OK) rc = cniic_dev_dense_compact(ctx, d_bins, size_t(1) << 24, &d_keys, &d_counts, &u);
+    std::vector<uint32_t> keys(u);
+    std::vector<uint64_t> counts(u);
+    if (rc == CNIIC_OK && u) {
+        cudaMemcpyAsync(keys.data(), d_keys, u * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(counts.data(), d_counts, u * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "histogram copy failed");
+    }
+    if (d_bins) cudaFree(d_bins);
+    if (d_keys) cudaFree(d_keys);
+    if (d_counts) cudaFree(d_counts);
+    if (rc != CNIIC_OK) return rc;
+    HufTree T;
+    if (!huf_build(counts, &T)) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "Huffman code longer than 64 bits");
+    huf_serialize(T, s, [&](uint32_t sym) { s.rgb(keys[sym]); });
+    std::vector<uint32_t> lut(size_t(1) << 24);
+    for (size_t i = 0; i < u; i++) lut[keys[i]] = (uint32_t)i;
+    for (size_t i = 0; i < n; i++) {  // pass 2: bit packing
+        const uint32_t sym = lut[((uint32_t)host_rgb[3 * i] << 16) | ((uint32_t)host_rgb[3 * i + 1] << 8) | host_rgb[3 * i + 2]];
+        s.bits(T.code[sym], T.len[sym]);
+    }
+    s.flush();
+    return CNIIC_OK;
+}
+
+int decode_hufman_body(cniic_ctx *ctx, Source &src, size_t n, uint8_t *out_rgb) {
+    if (n == 0) return CNIIC_OK;
+    DecTrie T;
+    if (!huf_deserialize(src, 11, &T)) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "bad Huffman trie");
+    for (const DecTrie::Node &nd : T.nodes)
+        if (nd.left < 0 && (nd.val[0] != 3 || memcmp(nd.val + 1, "\0\0\0\0\0\0\0", 7) != 0)) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "bad Rgb leaf");
+    std::vector<uint8_t> vals(n * 11);
+    if (!huf_decode(src, T, 11, n, vals.data())) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated Huffman payload");
+    for (size_t i = 0; i < n; i++) memcpy(out_rgb + 3 * i, vals.data() + 11 * i + 8, 3);
+    return CNIIC_OK;
+}
+
+}  // namespace
+
+extern "C" int cniic_codec_name(const char *codec, char *out, size_t cap) {
+    const CodecSpec sp = parse_codec(codec);
+    std::string nm;
+    switch (sp.kind) {
+    case CK_CLUSTER_COLORS: nm = "cluster-colors_" + std::to_string(sp.arg); break;  // clusterc.rs:59-61
+    case CK_VORONOI: nm = "voronoi_" + std::to_string(sp.arg); break;                 // clusterc.rs:191-193
+    case CK_DELTA: nm = "delta"; break;                                               // hilbertc.rs:433-435
+    case CK_HUFMAN: nm = "Hufman"; break;                                             // hufc.rs:42-44
+    case CK_HILBERT_RLE: nm = "hilbert-rle"; break;                                   // hilbertc.rs:81-87
+    default: return CNIIC_ERR_BAD_ARG;
+    }
+    if (!out || cap < nm.size() + 1) return CNIIC_ERR_BUFFER_TOO_SMALL;
+    memcpy(out, nm.c_str(), nm.size() + 1);
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8_t *rgb, uint32_t w, uint32_t h, uint8_t *out,
+                                  size_t cap, size_t *out_len) {
+    if (!ctx || !out_len) return CNIIC_ERR_BAD_ARG;
+    const CodecSpec sp = parse_codec(codec);
+    if (sp.kind == CK_NONE) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "unknown codec expression '%s'", codec ? codec : "(null)");
+    const size_t n = (size_t)w * h;
+    if (!rgb && n) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "null image");
+    if (n >= (size_t(1) << 31)) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "image too large");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Sink s;
+    DevBuf din;
+    CU_TRY(ctx, din.alloc(n * 3));
+    if (n) CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    switch (sp.kind) {
+    case CK_HUFMAN: {  // hufc.rs:12-17
+        s.u32(w); s.u32(h);
+        ST_TRY(encode_hufman_body(ctx, din.as<uint8_t>(), rgb, n, s));
+        break;
+    }
+    case CK_CLUSTER_COLORS: {  // clusterc.rs:18-53
+        if (sp.arg == 0 || sp.arg > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d", CNIIC_MAX_K);
+        DevBuf dred;
+        CU_TRY(ctx, dred.alloc(n * 3));
+        ST_TRY(cniic_dev_cluster_colors(ctx, din.as<uint8_t>(), n, sp.arg, ctx->codec_max_iters, CNIIC_TIE_KEEP_CURRENT, dred.as<uint8_t>(), nullptr, nullptr));
+        std::vector<uint8_t> red(n * 3);
+        CU_TRY(ctx, cudaMemcpyAsync(red.data(), dred.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        s.u32(w); s.u32(h);
+        ST_TRY(encode_hufman_body(ctx, dred.as<uint8_t>(), red.data(), n, s));
+        break;
+    }
+    case CK_VORONOI: {  // clusterc.rs:148-166
+        const uint32_t k = sp.arg;
+        if (k == 0 || k > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d", CNIIC_MAX_K);
+        std::vector<uint32_t> cxy(2 * (size_t)k);
+        std::vector<uint8_t> crgb(3 * (size_t)k);
+        ST_TRY(cniic_kmeans_xyrgb(ctx, rgb, w, h, k, ctx->codec_max_iters, CNIIC_TIE_KEEP_CURRENT, cxy.data(), crgb.data(), nullptr, nullptr, nullptr));
+        s.u32(w); s.u32(h);
+        s.u64(k);
+        for (uint32_t c = 0; c < k; c++) {  // clusterc.rs:250-257
+            s.u32(cxy[2 * c]); s.u32(cxy[2 * c + 1]);
+            s.u64(3); s.u8(crgb[3 * c]); s.u8(crgb[3 * c + 1]); s.u8(crgb[3 * c + 2]);
+        }
+        break;
+    }
+    case CK_DELTA: {  // hilbertc.rs:405-415
+        s.u32(w); s.u32(h);
+        if (n == 0) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "empty image (huf.rs:95 asserts a non-empty alphabet)");
+        // pass 1 on the GPU: fused Hilbert gather + diff + histogram (no stream materialised)
+        uint32_t *d_bins = nullptr, *d_keys = nullptr;
+        unsigned long long *d_counts = nullptr;
+        size_t nbins = 0, u = 0;
+        int rc = cniic_dev_hist_delta_bins(ctx, din.as<uint8_t>(), w, h, &d_bins, &nbins);
+        if (rc == CNIIC_OK) rc = cniic_dev_dense_compact(ctx, d_bins, nbins, &d_keys, &d_counts, &u);
+        std::vector<uint32_t> keys(u);
+        std::vector<uint64_t> counts(u);
+        if (rc == CNIIC_OK) {
+            cudaMemcpyAsync(keys.data(), d_keys, u * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(counts.data(), d_counts, u * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "histogram copy failed");
+        }
+        if (d_bins) cudaFree(d_bins);
+        if (d_keys) cudaFree(d_keys);
+        if (d_counts) cudaFree(d_counts);
+        ST_TRY(rc);
+        HufTree T;
+        if (!huf_build(counts, &T)) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "Huffman code longer than 64 bits");
+        huf_serialize(T, s, [&](uint32_t sym) {  // ser.rs:188-195 : [i16;3] LE
+            const uint32_t key = keys[sym];
+            const int16_t d[3] = {(int16_t)(int(key / (511 * 511)) - 255), (int16_t)(int((key / 511) % 511) - 255), (int16_t)(int(key % 511) - 255)};
+            for (int j = 0; j < 3; j++) { s.u8((uint8_t)((uint16_t)d[j] & 0xff)); s.u8((uint8_t)((uint16_t)d[j] >> 8)); }
+        });
+        // pass 2: the delta stream itself (GPU) -> host bit packing
+        DevBuf dd;
+        CU_TRY(ctx, dd.alloc(n * 6));
+        ST_TRY(cniic_delta_i16_device(ctx, din.as<uint8_t>(), w, h, dd.as<int16_t>()));
+        std::vector<int16_t> diff(n * 3);
+        CU_TRY(ctx, cudaMemcpyAsync(diff.data(), dd.p, n * 6, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        std::unordered_map<uint32_t, uint32_t> ids;
+        ids.reserve(u * 2);
+        for (size_t i = 0; i < u; i++) ids[keys[i]] = (uint32_t)i;
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t key = uint32_t(((diff[3 * i] + 255) * 511 + (diff[3 * i + 1] + 255)) * 511 + (diff[3 * i + 2] + 255));
+            const uint32_t sym = ids[key];
+            s.bits(T.code[sym], T.len[sym]);
+        }
+        s.flush();
+        break;
+    }
+    case CK_HILBERT_RLE: {  // hilbertc.rs:26-38, 99-196 ; records = u8 count (1..=255) + Rgb slice
+        s.u32(w); s.u32(h);
+        if (n) {
+            DevBuf dl;
+            CU_TRY(ctx, dl.alloc(n * 3));
+            ST_TRY(cniic_dev_hilbert_gather(ctx, din.as<uint8_t>(), w, h, dl.as<uint8_t>()));
+            std::vector<uint8_t> lin(n * 3);
+            CU_TRY(ctx, cudaMemcpyAsync(lin.data(), dl.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            size_t i = 0;
+            while (i < n) {
+                size_t j = i + 1;
+                uint32_t count = 1;
+                while (j < n && memcmp(&lin[3 * j], &lin[3 * i], 3) == 0) {
+                    count++; j++;
+                    if (count == 255) break;
+                }
+                s.u8((uint8_t)count);
+                s.u64(3); s.u8(lin[3 * i]); s.u8(lin[3 * i + 1]); s.u8(lin[3 * i + 2]);
+                i = j;
+            }
+        }
+        break;
+    }
+    default: return CNIIC_ERR_BAD_ARG;
+    }
+    return finish(ctx, s, out, cap, out_len);
+}
+
+extern "C" int cniic_codec_decode(cniic_ctx *ctx, const char *codec, const uint8_t *data, size_t len, uint32_t *w, uint32_t *h,
+                                  uint8_t *out_rgb, size_t cap_pixels) {
+    if (!ctx || !data || !w || !h) return CNIIC_ERR_BAD_ARG;
+    const CodecSpec sp = parse_codec(codec);
+    if (sp.kind == CK_NONE) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "unknown codec expression '%s'", codec ? codec : "(null)");
+    Source src{data, len};
+    if (!src.u32(w) || !src.u32(h)) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated header");
+    const size_t n = (size_t)*w * *h;
+    if (!out_rgb) return CNIIC_OK;  // dimension query
+    if (n > cap_pixels) return cniic_set_error(ctx, CNIIC_ERR_BUFFER_TOO_SMALL, "need room for %zu pixels", n);
+    if (n >= (size_t(1) << 31)) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "image too large");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    switch (sp.kind) {
+    case CK_HUFMAN:
+    case CK_CLUSTER_COLORS:  // clusterc.rs:55-57 -> hufc.rs:19-40
+        return decode_hufman_body(ctx, src, n, out_rgb);
+    case CK_VORONOI: {  // clusterc.rs:168-189
+        uint64_t k;
+        if (!src.u64(&k)) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated header");
+        if (k > (len - src.pos) / 19) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated centroid list");
+        if (n == 0) return CNIIC_OK;
+        if (k == 0) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "no centroids (clusterc.rs:182-184 unwraps None)");
+        if (k > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "more than %d centroids", CNIIC_MAX_K);
+        std::vector<uint32_t> cxy(2 * k);
+        std::vector<uint8_t> crgb(3 * k);
+        for (uint64_t c = 0; c < k; c++) {
+            uint64_t l;
+            if (!src.u32(&cxy[2 * c]) || !src.u32(&cxy[2 * c + 1]) || !src.u64(&l) || l != 3 || !src.u8(&crgb[3 * c]) ||
+                !src.u8(&crgb[3 * c + 1]) || !src.u8(&crgb[3 * c + 2]))
+                return cniic_set_error(ctx, CNIIC_ERR_DECODE, "bad centroid record");
+        }
+        return cniic_voronoi_fill(ctx, cxy.data(), crgb.data(), (uint32_t)k, *w, *h, out_rgb);
+    }
+    case CK_DELTA: {  // hilbertc.rs:417-431
+        if (n == 0) return CNIIC_OK;
+        DecTrie T;
+        if (!huf_deserialize(src, 6, &T)) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "bad Huffman trie");
+        std::vector<uint8_t> vals(n * 6);
+        if (!huf_decode(src, T, 6, n, vals.data())) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated Huffman payload");
+        // little-endian i16 triples == the in-memory layout cniic_undelta_rgb expects on this (little-endian) host
+        return cniic_undelta_rgb(ctx, reinterpret_cast<const int16_t *>(vals.data()), *w, *h, out_rgb);
+    }
+    case CK_HILBERT_RLE: {  // hilbertc.rs:55-79, 304-333
+        if (n == 0) return CNIIC_OK;
+        std::vector<uint32_t> xy(2 * n);
+        ST_TRY(cniic_hilbert_xy(ctx, *w, *h, xy.data()));
+        size_t i = 0;
+        while (i < n) {
+            uint8_t cnt, c[3];
+            uint64_t l;
+            if (!src.u8(&cnt) || !src.u64(&l) || l != 3 || !src.u8(&c[0]) || !src.u8(&c[1]) || !src.u8(&c[2]))
+                return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated RLE stream");
+            for (uint8_t j = 0; j < cnt && i < n; j++, i++) memcpy(out_rgb + 3 * ((size_t)xy[2 * i + 1] * *w + xy[2 * i]), c, 3);
+        }
+        return CNIIC_OK;
+    }
+    default: return CNIIC_ERR_BAD_ARG;
+    }
+}

@@ -620,7 +620,10 @@ struct cniic_kmeans {
     size_t smem = 0;
     int grid = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    static constexpr int PROF = 32;  // assign launches timed per run (CUDA events on the launching stream)
+    cudaEvent_t pev[2 * PROF] = {};
     uint32_t launches = 0;
+    uint32_t iter_seen = 0;  // state.iter at the end of the previous run (0 after reset)
 };
 
 static int km_launch_assign(cniic_kmeans *km) {
@@ -744,6 +747,7 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     km->grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(tiles, (unsigned long long)per_sm * ctx->sm_count));
     KM_TRY(cudaEventCreate(&km->ev0));
     KM_TRY(cudaEventCreate(&km->ev1));
+    for (int i = 0; i < 2 * cniic_kmeans::PROF; i++) KM_TRY(cudaEventCreate(&km->pev[i]));
 #undef KM_TRY
     *out = km;
     return CNIIC_OK;
@@ -767,6 +771,7 @@ extern "C" int cniic_kmeans_reset(cniic_kmeans *km, const int32_t *host_init_cen
         km->launches++;
     }
     CU_TRY(ctx, cudaGetLastError());
+    km->iter_seen = 0;
     return km_launch_finalize(km, 1);
 }
 
@@ -783,7 +788,10 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
         uint32_t batch = dist ? 1 : 4;
         if (max_iters) batch = std::min(batch, max_iters - issued);
         for (uint32_t b = 0; b < batch; b++) {
+            const bool prof = issued + b < (uint32_t)cniic_kmeans::PROF;
+            if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * (issued + b)], ctx->stream));
             ST_TRY(km_launch_assign(km));
+            if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * (issued + b) + 1], ctx->stream));
             if (dist) ST_TRY(cniic_nccl_allreduce_u64(ctx, km->dev.sums, size_t(km->desc.k) * DW + 1));
             ST_TRY(km_launch_finalize(km, 0));
         }
@@ -808,8 +816,16 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
         stats->converged = s.done;
         stats->gpu_launches = km->launches - launches0;
         stats->device_ms = ms;
-        stats->reserved = 0;
+        // average duration of the fused assign+accumulate kernel over the launches that actually ran
+        const uint32_t np = std::min<uint32_t>(s.iter - km->iter_seen, (uint32_t)cniic_kmeans::PROF);
+        float acc = 0.f;
+        for (uint32_t i = 0; i < np; i++) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, km->pev[2 * i], km->pev[2 * i + 1]) == cudaSuccess) acc += t;
+        }
+        stats->assign_ms_avg = np ? acc / np : 0.f;
     }
+    km->iter_seen = s.iter;
     return CNIIC_OK;
 }
 
@@ -838,6 +854,8 @@ extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
     if (km->h_state) cudaFreeHost(km->h_state);
     if (km->ev0) cudaEventDestroy(km->ev0);
     if (km->ev1) cudaEventDestroy(km->ev1);
+    for (cudaEvent_t e : km->pev)
+        if (e) cudaEventDestroy(e);
     delete km;
 }
 

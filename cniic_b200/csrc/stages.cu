@@ -1,0 +1,860 @@
+// stages.cu -- the per-pixel stages around K-means: voronoi fill, colour / delta histograms, recolour,
+// Hilbert index map, delta stream, SSE.  All HBM-bound integer/byte kernels except the fill (ALU).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "stages.cuh"
+
+namespace {
+
+// ============================================================================================================
+// voronoi decode fill  (reference src/codec/clusterc.rs:179-186)
+//   per pixel: FIRST centroid minimising (cx-x)^2 + (cy-y)^2 ; exact u32 integers.
+//   Tile = 64x64 pixels per CTA.  Exact culling: U = min_c maxdist^2(c, tile) bounds every pixel's minimum, so only
+//   centroids with mindist^2(c, tile) <= U can win; they are compacted IN INDEX ORDER (first minimum = lowest index).
+// ============================================================================================================
+constexpr int FT = 64;
+
+__device__ __forceinline__ uint32_t block_rank256(bool flag, uint32_t *s_warp, uint32_t *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t v = s_warp[i];
+        if (i < warp) before += v;
+        tot += v;
+    }
+    *total = tot;
+    return before + __popc(bal & ((1u << lane) - 1));
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ cxy, const uint8_t *__restrict__ crgb, uint32_t k,
+                                                   uint32_t w, uint32_t y0, uint32_t h_local, uint8_t *__restrict__ out) {
+    extern __shared__ uint4 fsm[];
+    int2 *s_c = reinterpret_cast<int2 *>(fsm);                 // candidate coordinates
+    uint16_t *s_i = reinterpret_cast<uint16_t *>(s_c + k);     // candidate ids
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_U;
+    const int tid = threadIdx.x;
+    const uint32_t tiles_x = (w + FT - 1) / FT, tiles_y = (h_local + FT - 1) / FT;
+    for (uint32_t tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+        const int x0 = (tile % tiles_x) * FT, yl0 = (tile / tiles_x) * FT;
+        const int x1 = min(x0 + FT, (int)w) - 1, yl1 = min(yl0 + FT, (int)h_local) - 1;
+        const int gy0 = y0 + yl0, gy1 = y0 + yl1;
+        __syncthreads();
+        if (tid == 0) s_U = 0xffffffffu;
+        __syncthreads();
+        uint32_t umin = 0xffffffffu;
+        for (uint32_t c = tid; c < k; c += 256) {
+            const int cx = (int)cxy[2 * c], cy = (int)cxy[2 * c + 1];
+            const uint32_t dx = max(abs(cx - x0), abs(cx - x1)), dy = max(abs(cy - gy0), abs(cy - gy1));
+            umin = min(umin, dx * dx + dy * dy);
+        }
+        for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+        if ((tid & 31) == 0) atomicMin(&s_U, umin);
+        __syncthreads();
+        const uint32_t U = s_U;
+        uint32_t ncand = 0;
+        for (uint32_t cb = 0; cb < k; cb += 256) {
+            const uint32_t c = cb + tid;
+            bool keep = false;
+            int cx = 0, cy = 0;
+            if (c < k) {
+                cx = (int)cxy[2 * c]; cy = (int)cxy[2 * c + 1];
+                const uint32_t dx = max(0, max(x0 - cx, cx - x1)), dy = max(0, max(gy0 - cy, cy - gy1));
+                keep = dx * dx + dy * dy <= U;
+            }
+            uint32_t tot;
+            const uint32_t r = block_rank256(keep, s_warp, &tot);
+            if (keep) { s_c[ncand + r] = make_int2(cx, cy); s_i[ncand + r] = (uint16_t)c; }
+            ncand += tot;
+        }
+        __syncthreads();
+        // thread -> one row of the tile, 16 consecutive pixels
+        const int row = tid >> 2, seg = (tid & 3) * 16;
+        const int yl = yl0 + row, gy = y0 + yl;
+        if (yl <= yl1) {
+            uint32_t bd[16];
+            uint32_t bi[16];
+#pragma unroll
+            for (int p = 0; p < 16; p++) { bd[p] = 0xffffffffu; bi[p] = 0; }
+            for (uint32_t j = 0; j < ncand; j++) {
+                const int2 c = s_c[j];
+                const int dy = c.y - gy;
+                const uint32_t dy2 = dy * dy;
+#pragma unroll
+                for (int p = 0; p < 16; p++) {
+                    const int dx = c.x - (x0 + seg + p);
+                    const uint32_t dd = dx * dx + dy2;
+                    if (dd < bd[p]) { bd[p] = dd; bi[p] = j; }
+                }
+            }
+            uint8_t *o = out + ((size_t)yl * w + x0 + seg) * 3;
+#pragma unroll
+            for (int p = 0; p < 16; p++) {
+                if (x0 + seg + p <= x1) {
+                    const uint32_t id = s_i[bi[p]];
+                    o[3 * p] = crgb[3 * id]; o[3 * p + 1] = crgb[3 * id + 1]; o[3 * p + 2] = crgb[3 * id + 2];
+                }
+            }
+        }
+    }
+}
+
+// ============================================================================================================
+// dense histogram + ordered compaction (utils::count_freqs, reference src/utils.rs:4-16)
+// ============================================================================================================
+__device__ __forceinline__ uint32_t rgb_key(const uint8_t *p) { return (uint32_t(p[0]) << 16) | (uint32_t(p[1]) << 8) | p[2]; }
+
+// warp-aggregated atomic increment: lanes holding the same key elect a leader that adds the group's population
+__device__ __forceinline__ void warp_hist_add(uint32_t *bins, uint32_t key, bool valid) {
+    const uint32_t act = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const uint32_t peers = __match_any_sync(act, key);
+    if ((__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(&bins[key], (uint32_t)__popc(peers));
+}
+
+__global__ void hist_rgb_kernel(const uint8_t *__restrict__ rgb, size_t n, uint32_t *bins) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n_round = (n + 31) / 32 * 32;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < n;
+        warp_hist_add(bins, valid ? rgb_key(rgb + 3 * i) : 0, valid);
+    }
+}
+
+constexpr int CB = 4096;  // bins per compaction block (256 threads x 16)
+
+__global__ void __launch_bounds__(256) count_nonzero_kernel(const uint32_t *__restrict__ bins, size_t nbins, uint32_t *block_counts) {
+    const size_t base = (size_t)blockIdx.x * CB;
+    uint32_t c = 0;
+    for (int j = 0; j < 16; j++) {
+        const size_t i = base + (size_t)j * 256 + threadIdx.x;
+        if (i < nbins && bins[i]) c++;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    __shared__ uint32_t s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; i++) t += s[i];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+// single-block exclusive scan of block_counts (u32 -> u64 offsets); total to offsets[nblocks]
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t *__restrict__ counts, size_t nblocks, unsigned long long *offsets) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (size_t base = 0; base < nblocks; base += 1024) {
+        const size_t i = base + threadIdx.x;
+        unsigned long long v = i < nblocks ? counts[i] : 0ull, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        unsigned long long before = s_carry;
+        for (int j = 0; j < warp; j++) before += s_warp[j];
+        if (i < nblocks) offsets[i] = before + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[nblocks] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) compact_kernel(const uint32_t *__restrict__ bins, size_t nbins, const unsigned long long *__restrict__ offsets,
+                                                      uint32_t *out_keys, unsigned long long *out_counts, size_t cap) {
+    __shared__ uint32_t s_warp[8];
+    const size_t base = (size_t)blockIdx.x * CB;
+    unsigned long long pos = offsets[blockIdx.x];
+    if (offsets[blockIdx.x + 1] == pos) return;
+    for (int j = 0; j < 16; j++) {
+        const size_t i = base + (size_t)j * 256 + threadIdx.x;
+        const uint32_t v = i < nbins ? bins[i] : 0;
+        uint32_t tot;
+        const uint32_t r = block_rank256(v != 0, s_warp, &tot);
+        if (v && pos + r < cap) { out_keys[pos + r] = (uint32_t)i; out_counts[pos + r] = v; }
+        pos += tot;
+    }
+}
+
+// ============================================================================================================
+// cluster-colors helpers (reference src/codec/clusterc.rs:19-47)
+// ============================================================================================================
+__global__ void keys_to_points_kernel(const uint32_t *__restrict__ keys, const unsigned long long *__restrict__ counts, size_t n,
+                                      uint8_t *rgb, uint32_t *wts) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t key = keys[i];
+        rgb[3 * i] = key >> 16; rgb[3 * i + 1] = key >> 8; rgb[3 * i + 2] = key;
+        wts[i] = (uint32_t)counts[i];  // clusterc.rs:23 "count as u32"
+    }
+}
+
+// lut[key] = centroid colour packed r | g<<8 | b<<16
+__global__ void build_lut_kernel(const uint32_t *__restrict__ keys, const uint16_t *__restrict__ assign, size_t n,
+                                 const int32_t *__restrict__ cen, uint32_t *lut) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int32_t *c = cen + 3 * assign[i];
+        lut[keys[i]] = uint32_t(c[0]) | (uint32_t(c[1]) << 8) | (uint32_t(c[2]) << 16);
+    }
+}
+
+__global__ void build_lut_u8_kernel(const uint32_t *__restrict__ keys, const uint16_t *__restrict__ assign, size_t n,
+                                    const uint8_t *__restrict__ cen, uint32_t *lut) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint8_t *c = cen + 3 * assign[i];
+        lut[keys[i]] = uint32_t(c[0]) | (uint32_t(c[1]) << 8) | (uint32_t(c[2]) << 16);
+    }
+}
+
+__global__ void recolor_kernel(const uint8_t *__restrict__ rgb, size_t n, const uint32_t *__restrict__ lut, uint8_t *out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t v = lut[rgb_key(rgb + 3 * i)];
+        out[3 * i] = v; out[3 * i + 1] = v >> 8; out[3 * i + 2] = v >> 16;
+    }
+}
+
+// ============================================================================================================
+// Hilbert scan (reference src/hilbert.rs:40-43 -> zhang_hilbert, PARITY UNPINNED; same curve as the oracle)
+// ============================================================================================================
+struct HRect { int x, y, ax, ay, bx, by; };
+
+__device__ __forceinline__ int isgn(int v) { return (v > 0) - (v < 0); }
+__device__ __forceinline__ int half_floor(int v) { return v >> 1; }  // arithmetic shift == floor division by 2
+
+// generic rectangle: descend the recursive halving until the index lands in a 1-wide strip
+__device__ void hilbert_d2xy_generic(uint32_t w, uint32_t h, unsigned long long d, uint32_t *ox, uint32_t *oy) {
+    int x = 0, y = 0, ax, ay, bx, by;
+    if (w >= h) { ax = w; ay = 0; bx = 0; by = h; }
+    else { ax = 0; ay = h; bx = w; by = 0; }
+    for (;;) {
+        const int ww = abs(ax + ay), hh = abs(bx + by);
+        const int dax = isgn(ax), day = isgn(ay), dbx = isgn(bx), dby = isgn(by);
+        if (hh == 1) { *ox = x + dax * (int)d; *oy = y + day * (int)d; return; }
+        if (ww == 1) { *ox = x + dbx * (int)d; *oy = y + dby * (int)d; return; }
+        int ax2 = half_floor(ax), ay2 = half_floor(ay), bx2 = half_floor(bx), by2 = half_floor(by);
+        const int w2 = abs(ax2 + ay2), h2 = abs(bx2 + by2);
+        if (2 * ww > 3 * hh) {
+            if ((w2 & 1) && ww > 2) { ax2 += dax; ay2 += day; }
+            const unsigned long long n1 = (unsigned long long)abs(ax2 + ay2) * hh;
+            if (d < n1) { ax = ax2; ay = ay2; }
+            else { d -= n1; x += ax2; y += ay2; ax -= ax2; ay -= ay2; }
+        } else {
+            if ((h2 & 1) && hh > 2) { bx2 += dbx; by2 += dby; }
+            const unsigned long long n1 = (unsigned long long)abs(bx2 + by2) * abs(ax2 + ay2);
+            const unsigned long long n2 = (unsigned long long)ww * abs((bx - bx2) + (by - by2));
+            if (d < n1) {
+                const int tax = bx2, tay = by2;
+                bx = ax2; by = ay2; ax = tax; ay = tay;
+            } else if (d < n1 + n2) {
+                d -= n1; x += bx2; y += by2; bx -= bx2; by -= by2;
+            } else {
+                d -= n1 + n2;
+                x += (ax - dax) + (bx2 - dbx); y += (ay - day) + (by2 - dby);
+                const int nax = -bx2, nay = -by2, nbx = -(ax - ax2), nby = -(ay - ay2);
+                ax = nax; ay = nay; bx = nbx; by = nby;
+            }
+        }
+    }
+}
+
+// 2^n x 2^n squares: the scan above IS the classic Hilbert curve (first step +y for odd n, +x for even n)
+__device__ __forceinline__ void hilbert_d2xy_pow2(uint32_t n, unsigned long long d, uint32_t *ox, uint32_t *oy) {
+    uint32_t x = 0, y = 0;
+    unsigned long long t = d;
+    for (uint32_t s = 1; s < n; s <<= 1) {
+        const uint32_t rx = 1u & (uint32_t)(t >> 1), ry = 1u & ((uint32_t)t ^ rx);
+        if (ry == 0) {
+            if (rx == 1) { x = s - 1 - x; y = s - 1 - y; }
+            const uint32_t tmp = x; x = y; y = tmp;
+        }
+        x += s * rx; y += s * ry;
+        t >>= 2;
+    }
+    *ox = x; *oy = y;
+}
+
+__device__ __forceinline__ void hilbert_d2xy(uint32_t w, uint32_t h, bool pow2, unsigned long long d, uint32_t *ox, uint32_t *oy) {
+    if (pow2) hilbert_d2xy_pow2(w, d, ox, oy);
+    else hilbert_d2xy_generic(w, h, d, ox, oy);
+}
+
+__global__ void hilbert_xy_kernel(uint32_t w, uint32_t h, bool pow2, uint32_t *out) {
+    const unsigned long long n = (unsigned long long)w * h;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t x, y;
+        hilbert_d2xy(w, h, pow2, i, &x, &y);
+        out[2 * i] = x; out[2 * i + 1] = y;
+    }
+}
+
+// mode 0: gather rgb along the curve; mode 1: delta stream (i16 x 3); mode 2: delta histogram only (fused)
+template <int MODE>
+__global__ void hilbert_stream_kernel(const uint8_t *__restrict__ rgb, uint32_t w, uint32_t h, bool pow2, uint8_t *out_rgb,
+                                      int16_t *out_delta, uint32_t *bins) {
+    const unsigned long long n = (unsigned long long)w * h;
+    const unsigned long long n_round = (n + 31) / 32 * 32;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_round;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const bool valid = i < n;
+        uint32_t x = 0, y = 0;
+        int c0 = 0, c1 = 0, c2 = 0;
+        if (valid) {
+            hilbert_d2xy(w, h, pow2, i, &x, &y);
+            const uint8_t *p = rgb + ((size_t)y * w + x) * 3;
+            c0 = p[0]; c1 = p[1]; c2 = p[2];
+        }
+        if (MODE == 0) {
+            if (valid) { out_rgb[3 * i] = c0; out_rgb[3 * i + 1] = c1; out_rgb[3 * i + 2] = c2; }
+        } else {
+            // predecessor along the curve: neighbouring lane, or one extra index map for lane 0
+            int p0 = __shfl_up_sync(0xffffffffu, c0, 1), p1 = __shfl_up_sync(0xffffffffu, c1, 1), p2 = __shfl_up_sync(0xffffffffu, c2, 1);
+            if ((threadIdx.x & 31) == 0) {
+                p0 = p1 = p2 = 0;  // hilbertc.rs:445 START = [0;3]
+                if (valid && i > 0) {
+                    uint32_t px, py;
+                    hilbert_d2xy(w, h, pow2, i - 1, &px, &py);
+                    const uint8_t *q = rgb + ((size_t)py * w + px) * 3;
+                    p0 = q[0]; p1 = q[1]; p2 = q[2];
+                }
+            }
+            const int d0 = c0 - p0, d1 = c1 - p1, d2 = c2 - p2;
+            if (MODE == 1) {
+                if (valid) { out_delta[3 * i] = d0; out_delta[3 * i + 1] = d1; out_delta[3 * i + 2] = d2; }
+            } else {
+                warp_hist_add(bins, valid ? uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255)) : 0, valid);
+            }
+        }
+    }
+}
+
+// inverse: segmented prefix sum along the curve is sequential per channel; done as a 3-kernel scan over i16 diffs.
+// Values are bounded (reconstructed colours are 0..255) so int32 prefix sums are exact.
+__global__ void __launch_bounds__(256) undelta_partial_kernel(const int16_t *__restrict__ diff, unsigned long long n, int *block_sums) {
+    const unsigned long long base = (unsigned long long)blockIdx.x * 4096;
+    int s0 = 0, s1 = 0, s2 = 0;
+    for (int j = 0; j < 16; j++) {
+        const unsigned long long i = base + (unsigned long long)j * 256 + threadIdx.x;
+        if (i < n) { s0 += diff[3 * i]; s1 += diff[3 * i + 1]; s2 += diff[3 * i + 2]; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    __shared__ int s[8][3];
+    if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5][0] = s0; s[threadIdx.x >> 5][1] = s1; s[threadIdx.x >> 5][2] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        int t = 0;
+        for (int i = 0; i < 8; i++) t += s[i][threadIdx.x];
+        block_sums[3 * blockIdx.x + threadIdx.x] = t;
+    }
+}
+
+__global__ void undelta_scan_blocks_kernel(int *block_sums, size_t nblocks) {
+    // one thread per channel: nblocks <= N/4096 (16K for 8192^2) -- sequential is fine
+    if (threadIdx.x < 3) {
+        int run = 0;
+        for (size_t b = 0; b < nblocks; b++) {
+            const int v = block_sums[3 * b + threadIdx.x];
+            block_sums[3 * b + threadIdx.x] = run;
+            run += v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) undelta_apply_kernel(const int16_t *__restrict__ diff, unsigned long long n, const int *__restrict__ block_sums,
+                                                            uint32_t w, uint32_t h, bool pow2, uint8_t *out) {
+    // each thread owns 16 consecutive stream positions of the 4096-position block
+    const unsigned long long base = (unsigned long long)blockIdx.x * 4096 + (unsigned long long)threadIdx.x * 16;
+    int l0 = 0, l1 = 0, l2 = 0;
+    for (int j = 0; j < 16; j++) {
+        const unsigned long long i = base + j;
+        if (i < n) { l0 += diff[3 * i]; l1 += diff[3 * i + 1]; l2 += diff[3 * i + 2]; }
+    }
+    // exclusive scan of the per-thread sums across the block
+    __shared__ int s_w[8][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x0 = l0, x1 = l1, x2 = l2;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o), y2 = __shfl_up_sync(0xffffffffu, x2, o);
+        if (lane >= o) { x0 += y0; x1 += y1; x2 += y2; }
+    }
+    if (lane == 31) { s_w[warp][0] = x0; s_w[warp][1] = x1; s_w[warp][2] = x2; }
+    __syncthreads();
+    int b0 = block_sums[3 * blockIdx.x], b1 = block_sums[3 * blockIdx.x + 1], b2 = block_sums[3 * blockIdx.x + 2];
+    for (int j = 0; j < warp; j++) { b0 += s_w[j][0]; b1 += s_w[j][1]; b2 += s_w[j][2]; }
+    int r0 = b0 + x0 - l0, r1 = b1 + x1 - l1, r2 = b2 + x2 - l2;
+    for (int j = 0; j < 16; j++) {
+        const unsigned long long i = base + j;
+        if (i < n) {
+            r0 += diff[3 * i]; r1 += diff[3 * i + 1]; r2 += diff[3 * i + 2];
+            uint32_t x, y;
+            hilbert_d2xy(w, h, pow2, i, &x, &y);
+            uint8_t *p = out + ((size_t)y * w + x) * 3;
+            p[0] = (uint8_t)r0; p[1] = (uint8_t)r1; p[2] = (uint8_t)r2;
+        }
+    }
+}
+
+// ============================================================================================================
+// exact integer SSE (reference src/bench.rs:95-104 sums sqrt(n)^2 in f64; the integer sum is the exact value)
+// ============================================================================================================
+__global__ void sse_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, size_t nbytes, unsigned long long *out) {
+    unsigned long long s = 0;
+    const size_t nw = nbytes / 4;
+    const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 3) == 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (al) {
+        for (size_t i = t0; i < nw; i += stride) {
+            const uint32_t x = reinterpret_cast<const uint32_t *>(a)[i], y = reinterpret_cast<const uint32_t *>(b)[i];
+            const uint32_t ad = __vabsdiffu4(x, y);
+            s += __dp4a(ad, ad, 0u);
+        }
+        for (size_t i = nw * 4 + t0; i < nbytes; i += stride) { const int d = int(a[i]) - int(b[i]); s += d * d; }
+    } else {
+        for (size_t i = t0; i < nbytes; i += stride) { const int d = int(a[i]) - int(b[i]); s += d * d; }
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+inline int grid_for(cniic_ctx *ctx, size_t n, int per_thread = 1) {
+    const size_t blocks = (n + 256 * (size_t)per_thread - 1) / (256 * (size_t)per_thread);
+    return (int)std::max<size_t>(1, std::min<size_t>(blocks, (size_t)ctx->sm_count * 16));
+}
+
+inline bool is_pow2_square(uint32_t w, uint32_t h) { return w == h && (w & (w - 1)) == 0; }
+
+}  // namespace
+
+// ---- device-level building blocks (declared in stages.cuh) -----------------------------------------------------
+
+int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins, size_t nbins, uint32_t **d_keys, unsigned long long **d_counts, size_t *n_unique) {
+    const size_t nblocks = (nbins + CB - 1) / CB;
+    uint32_t *d_bc = nullptr;
+    unsigned long long *d_off = nullptr;
+    CU_TRY(ctx, cudaMalloc(&d_bc, nblocks * 4));
+    CU_TRY(ctx, cudaMalloc(&d_off, (nblocks + 1) * 8));
+    count_nonzero_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_bins, nbins, d_bc);
+    scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(d_bc, nblocks, d_off);
+    ctx->launches += 2;
+    unsigned long long total = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&total, d_off + nblocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_unique = (size_t)total;
+    *d_keys = nullptr;
+    *d_counts = nullptr;
+    CU_TRY(ctx, cudaMalloc(d_keys, std::max<size_t>(16, total * 4)));
+    CU_TRY(ctx, cudaMalloc(d_counts, std::max<size_t>(16, total * 8)));
+    compact_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_bins, nbins, d_off, *d_keys, *d_counts, total);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_bc);
+    cudaFree(d_off);
+    return CNIIC_OK;
+}
+
+int cniic_dev_hist_rgb_bins(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t **d_bins) {
+    *d_bins = nullptr;
+    CU_TRY(ctx, cudaMalloc(d_bins, (size_t(1) << 24) * 4));
+    CU_TRY(ctx, cudaMemsetAsync(*d_bins, 0, (size_t(1) << 24) * 4, ctx->stream));
+    if (n) {
+        hist_rgb_kernel<<<grid_for(ctx, n, 4), 256, 0, ctx->stream>>>(d_rgb, n, *d_bins);
+        ctx->launches++;
+    }
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+int cniic_dev_recolor(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, const uint32_t *d_keys, const uint16_t *d_assign, size_t n_unique,
+                      const int32_t *d_cen_i32, const uint8_t *d_cen_u8, uint32_t *d_lut, uint8_t *d_out) {
+    if (n_unique) {
+        if (d_cen_i32) build_lut_kernel<<<grid_for(ctx, n_unique), 256, 0, ctx->stream>>>(d_keys, d_assign, n_unique, d_cen_i32, d_lut);
+        else build_lut_u8_kernel<<<grid_for(ctx, n_unique), 256, 0, ctx->stream>>>(d_keys, d_assign, n_unique, d_cen_u8, d_lut);
+        ctx->launches++;
+    }
+    if (n) {
+        recolor_kernel<<<grid_for(ctx, n, 4), 256, 0, ctx->stream>>>(d_rgb, n, d_lut, d_out);
+        ctx->launches++;
+    }
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+int cniic_dev_keys_to_points(cniic_ctx *ctx, const uint32_t *d_keys, const unsigned long long *d_counts, size_t n, uint8_t *d_rgb, uint32_t *d_wts) {
+    if (n) {
+        keys_to_points_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(d_keys, d_counts, n, d_rgb, d_wts);
+        ctx->launches++;
+    }
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+int cniic_dev_hilbert_gather(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint8_t *d_out) {
+    hilbert_stream_kernel<0><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), d_out, nullptr, nullptr);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+int cniic_dev_hist_delta_bins(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint32_t **d_bins, size_t *nbins) {
+    *nbins = (size_t)511 * 511 * 511;
+    *d_bins = nullptr;
+    CU_TRY(ctx, cudaMalloc(d_bins, *nbins * 4));
+    CU_TRY(ctx, cudaMemsetAsync(*d_bins, 0, *nbins * 4, ctx->stream));
+    hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+// ---- C ABI -----------------------------------------------------------------------------------------------------
+
+struct DevBuf {  // RAII device buffer
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(16, bytes)); }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+
+extern "C" int cniic_voronoi_fill_device(cniic_ctx *ctx, const uint32_t *d_cxy, const uint8_t *d_crgb, uint32_t k, uint32_t w,
+                                         uint32_t h, uint32_t y0, uint32_t h_local, uint8_t *d_out_rgb) {
+    if (!ctx || !d_cxy || !d_crgb || !d_out_rgb) return CNIIC_ERR_BAD_ARG;
+    if (k == 0 || k > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d (clusterc.rs:182-184 unwraps on k = 0)", CNIIC_MAX_K);
+    if (w == 0 || h_local == 0) return CNIIC_OK;
+    if (w > CNIIC_MAX_DIM || h > CNIIC_MAX_DIM || (uint64_t)y0 + h_local > h) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "bad image dimensions");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t smem = (size_t)k * 10 + 16;
+    CU_TRY(ctx, cudaFuncSetAttribute(fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t tiles = (size_t)((w + FT - 1) / FT) * ((h_local + FT - 1) / FT);
+    const int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 8);
+    fill_kernel<<<grid, 256, smem, ctx->stream>>>(d_cxy, d_crgb, k, w, y0, h_local, d_out_rgb);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_voronoi_fill(cniic_ctx *ctx, const uint32_t *cxy, const uint8_t *crgb, uint32_t k, uint32_t w, uint32_t h,
+                                  uint8_t *out_rgb) {
+    if (!ctx || !cxy || !crgb || (!out_rgb && (size_t)w * h)) return CNIIC_ERR_BAD_ARG;
+    if (k == 0 || k > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d", CNIIC_MAX_K);
+    for (uint32_t c = 0; c < k; c++)
+        if (cxy[2 * c] >= 32768 || cxy[2 * c + 1] >= 32768)
+            return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "centroid coordinate >= 32768 (u32 wrap-around of the reference is not reproduced)");
+    if ((size_t)w * h == 0) return CNIIC_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf dxy, drgb, dout;
+    CU_TRY(ctx, dxy.alloc((size_t)k * 8));
+    CU_TRY(ctx, drgb.alloc((size_t)k * 3));
+    CU_TRY(ctx, dout.alloc((size_t)w * h * 3));
+    CU_TRY(ctx, cudaMemcpyAsync(dxy.p, cxy, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(drgb.p, crgb, (size_t)k * 3, cudaMemcpyHostToDevice, ctx->stream));
+    ST_TRY(cniic_voronoi_fill_device(ctx, dxy.as<uint32_t>(), drgb.as<uint8_t>(), k, w, h, 0, h, dout.as<uint8_t>()));
+    CU_TRY(ctx, cudaMemcpyAsync(out_rgb, dout.p, (size_t)w * h * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+static int hist_out(cniic_ctx *ctx, uint32_t *d_bins, size_t nbins, uint32_t *out_keys, uint64_t *out_counts, size_t cap, size_t *out_n) {
+    uint32_t *d_keys = nullptr;
+    unsigned long long *d_counts = nullptr;
+    size_t u = 0;
+    int rc = cniic_dev_dense_compact(ctx, d_bins, nbins, &d_keys, &d_counts, &u);
+    if (rc == CNIIC_OK) {
+        if (out_n) *out_n = u;
+        if (u > cap) rc = cniic_set_error(ctx, CNIIC_ERR_BUFFER_TOO_SMALL, "%zu distinct symbols, capacity %zu", u, cap);
+        else if (u) {
+            cudaMemcpyAsync(out_keys, d_keys, u * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(out_counts, d_counts, u * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "histogram copy failed");
+        }
+    }
+    if (d_keys) cudaFree(d_keys);
+    if (d_counts) cudaFree(d_counts);
+    return rc;
+}
+
+extern "C" int cniic_hist_rgb(cniic_ctx *ctx, const uint8_t *rgb, size_t n, uint32_t *out_keys, uint64_t *out_counts, size_t cap,
+                              size_t *out_n) {
+    if (!ctx || (!rgb && n) || !out_n || (cap && (!out_keys || !out_counts))) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf din;
+    CU_TRY(ctx, din.alloc(n * 3));
+    CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *d_bins = nullptr;
+    int rc = cniic_dev_hist_rgb_bins(ctx, din.as<uint8_t>(), n, &d_bins);
+    if (rc == CNIIC_OK) rc = hist_out(ctx, d_bins, size_t(1) << 24, out_keys, out_counts, cap, out_n);
+    if (d_bins) cudaFree(d_bins);
+    return rc;
+}
+
+extern "C" int cniic_recolor_rgb(cniic_ctx *ctx, const uint8_t *rgb, size_t n, const uint32_t *keys, const uint16_t *assign,
+                                 size_t n_unique, const uint8_t *centroids, uint32_t k, uint8_t *out_rgb) {
+    if (!ctx || (!rgb && n) || !keys || !assign || !centroids || (!out_rgb && n) || k == 0) return CNIIC_ERR_BAD_ARG;
+    for (size_t i = 0; i < n_unique; i++)
+        if (assign[i] >= k || keys[i] >= (1u << 24)) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "assignment / key out of range");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf din, dkeys, dasg, dcen, dlut, dout;
+    CU_TRY(ctx, din.alloc(n * 3));
+    CU_TRY(ctx, dkeys.alloc(n_unique * 4));
+    CU_TRY(ctx, dasg.alloc(n_unique * 2));
+    CU_TRY(ctx, dcen.alloc((size_t)k * 3));
+    CU_TRY(ctx, dlut.alloc((size_t(1) << 24) * 4));
+    CU_TRY(ctx, dout.alloc(n * 3));
+    CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(dkeys.p, keys, n_unique * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(dasg.p, assign, n_unique * 2, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(dcen.p, centroids, (size_t)k * 3, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(dlut.p, 0, (size_t(1) << 24) * 4, ctx->stream));
+    ST_TRY(cniic_dev_recolor(ctx, din.as<uint8_t>(), n, dkeys.as<uint32_t>(), dasg.as<uint16_t>(), n_unique, nullptr, dcen.as<uint8_t>(),
+                             dlut.as<uint32_t>(), dout.as<uint8_t>()));
+    CU_TRY(ctx, cudaMemcpyAsync(out_rgb, dout.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+// device-resident cluster-colors front half; d_out may alias nothing; returns centroids (k x 3 i32 on host)
+int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t k, uint32_t max_iters, int tie_rule, uint8_t *d_out,
+                             std::vector<int32_t> *cen_host, cniic_kmeans_stats *stats) {
+    uint32_t *d_bins = nullptr, *d_keys = nullptr;
+    unsigned long long *d_counts = nullptr;
+    size_t u = 0;
+    int rc = cniic_dev_hist_rgb_bins(ctx, d_rgb, n, &d_bins);
+    if (rc == CNIIC_OK) rc = cniic_dev_dense_compact(ctx, d_bins, size_t(1) << 24, &d_keys, &d_counts, &u);
+    DevBuf upts, uwts;
+    cniic_kmeans *km = nullptr;
+    if (rc == CNIIC_OK && u / k == 0) rc = cniic_set_error(ctx, CNIIC_ERR_TOO_FEW_POINTS, "only %zu distinct colours for k = %u (kmeans.rs:67-68)", u, k);
+    if (rc == CNIIC_OK && (upts.alloc(u * 3) != cudaSuccess || uwts.alloc(u * 4) != cudaSuccess)) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc failed");
+    if (rc == CNIIC_OK) rc = cniic_dev_keys_to_points(ctx, d_keys, d_counts, u, upts.as<uint8_t>(), uwts.as<uint32_t>());
+    if (rc == CNIIC_OK) {
+        cniic_kmeans_desc desc{};
+        desc.kind = CNIIC_POINTS_RGB;
+        desc.k = k;
+        desc.tie_rule = tie_rule;
+        desc.n_local = desc.n_total = u;
+        desc.rgb = upts.as<uint8_t>();
+        desc.weights = uwts.as<uint32_t>();
+        desc.points_on_device = 1;
+        rc = cniic_kmeans_open(ctx, &desc, &km);
+    }
+    if (rc == CNIIC_OK) rc = cniic_kmeans_reset(km, nullptr);
+    if (rc == CNIIC_OK) rc = cniic_kmeans_run(km, max_iters, stats);
+    std::vector<uint64_t> wts(k);
+    std::vector<int32_t> cen(size_t(k) * 3);
+    if (rc == CNIIC_OK) rc = cniic_kmeans_get(km, cen.data(), wts.data(), nullptr);
+    if (rc == CNIIC_OK) {
+        // the histogram bins are dead now: reuse them as the colour -> centroid colour lookup table
+        DevBuf dcen;
+        if (dcen.alloc(cen.size() * 4) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc failed");
+        if (rc == CNIIC_OK) {
+            cudaMemcpyAsync(dcen.p, cen.data(), cen.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+            rc = cniic_dev_recolor(ctx, d_rgb, n, d_keys, cniic_kmeans_device_assign(km), u, dcen.as<int32_t>(), nullptr, d_bins, d_out);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "recolour failed");
+        }
+    }
+    if (km) cniic_kmeans_close(km);
+    if (d_bins) cudaFree(d_bins);
+    if (d_keys) cudaFree(d_keys);
+    if (d_counts) cudaFree(d_counts);
+    if (rc != CNIIC_OK) return rc;
+    if (cen_host) *cen_host = cen;
+    // kmeans.rs:41-57
+    uint64_t active = 0;
+    for (uint32_t c = 0; c < k; c++) active += wts[c] > 0;
+    uint64_t min_cc = (uint64_t)(0.99 * (double)k);
+    if (u < min_cc) min_cc = u;
+    if (active < min_cc) return cniic_set_error(ctx, CNIIC_ERR_TOO_FEW_ACTIVE, "Not enough active clusters: requested %u, got %llu", k, (unsigned long long)active);
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_cluster_colors(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, uint32_t k, uint32_t max_iters,
+                                    int tie_rule, uint8_t *out_rgb, uint8_t *out_centroids, cniic_kmeans_stats *stats) {
+    if (!ctx || !rgb || !out_rgb) return CNIIC_ERR_BAD_ARG;
+    if (k == 0 || k > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d", CNIIC_MAX_K);
+    const size_t n = (size_t)w * h;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf din, dout;
+    CU_TRY(ctx, din.alloc(n * 3));
+    CU_TRY(ctx, dout.alloc(n * 3));
+    CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int32_t> cen;
+    const int rc = cniic_dev_cluster_colors(ctx, din.as<uint8_t>(), n, k, max_iters, tie_rule, dout.as<uint8_t>(), &cen, stats);
+    if (rc != CNIIC_OK && rc != CNIIC_ERR_TOO_FEW_ACTIVE) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(out_rgb, dout.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_centroids)
+        for (size_t i = 0; i < cen.size(); i++) out_centroids[i] = (uint8_t)cen[i];
+    return rc;
+}
+
+static int check_dims(cniic_ctx *ctx, uint32_t w, uint32_t h) {
+    if ((uint64_t)w * h >= (1ull << 31) || w > 32768 || h > 32768) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "image too large");
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_hilbert_xy(cniic_ctx *ctx, uint32_t w, uint32_t h, uint32_t *out_xy) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    ST_TRY(check_dims(ctx, w, h));
+    const size_t n = (size_t)w * h;
+    if (n == 0) return CNIIC_OK;
+    if (!out_xy) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf d;
+    CU_TRY(ctx, d.alloc(n * 8));
+    hilbert_xy_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(w, h, is_pow2_square(w, h), d.as<uint32_t>());
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaMemcpyAsync(out_xy, d.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_hilbert_gather_rgb(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, uint8_t *out_rgb) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    ST_TRY(check_dims(ctx, w, h));
+    const size_t n = (size_t)w * h;
+    if (n == 0) return CNIIC_OK;
+    if (!rgb || !out_rgb) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf din, dout;
+    CU_TRY(ctx, din.alloc(n * 3));
+    CU_TRY(ctx, dout.alloc(n * 3));
+    CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    ST_TRY(cniic_dev_hilbert_gather(ctx, din.as<uint8_t>(), w, h, dout.as<uint8_t>()));
+    CU_TRY(ctx, cudaMemcpyAsync(out_rgb, dout.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_delta_i16_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, int16_t *d_out) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    ST_TRY(check_dims(ctx, w, h));
+    if ((size_t)w * h == 0) return CNIIC_OK;
+    if (!d_rgb || !d_out) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    hilbert_stream_kernel<1><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, d_out, nullptr);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_delta_i16(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, int16_t *out) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    ST_TRY(check_dims(ctx, w, h));
+    const size_t n = (size_t)w * h;
+    if (n == 0) return CNIIC_OK;
+    if (!rgb || !out) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf din, dout;
+    CU_TRY(ctx, din.alloc(n * 3));
+    CU_TRY(ctx, dout.alloc(n * 6));
+    CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    ST_TRY(cniic_delta_i16_device(ctx, din.as<uint8_t>(), w, h, dout.as<int16_t>()));
+    CU_TRY(ctx, cudaMemcpyAsync(out, dout.p, n * 6, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+int cniic_dev_undelta(cniic_ctx *ctx, const int16_t *d_diff, uint32_t w, uint32_t h, uint8_t *d_out) {
+    const unsigned long long n = (unsigned long long)w * h;
+    const size_t nblocks = (n + 4095) / 4096;
+    DevBuf bs;
+    CU_TRY(ctx, bs.alloc(nblocks * 12));
+    undelta_partial_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_diff, n, bs.as<int>());
+    undelta_scan_blocks_kernel<<<1, 32, 0, ctx->stream>>>(bs.as<int>(), nblocks);
+    undelta_apply_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_diff, n, bs.as<int>(), w, h, is_pow2_square(w, h), d_out);
+    ctx->launches += 3;
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_undelta_rgb(cniic_ctx *ctx, const int16_t *diff, uint32_t w, uint32_t h, uint8_t *out_rgb) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    ST_TRY(check_dims(ctx, w, h));
+    const size_t n = (size_t)w * h;
+    if (n == 0) return CNIIC_OK;
+    if (!diff || !out_rgb) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf din, dout;
+    CU_TRY(ctx, din.alloc(n * 6));
+    CU_TRY(ctx, dout.alloc(n * 3));
+    CU_TRY(ctx, cudaMemcpyAsync(din.p, diff, n * 6, cudaMemcpyHostToDevice, ctx->stream));
+    ST_TRY(cniic_dev_undelta(ctx, din.as<int16_t>(), w, h, dout.as<uint8_t>()));
+    CU_TRY(ctx, cudaMemcpyAsync(out_rgb, dout.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_hist_delta_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, size_t *out_n) {
+    if (!ctx || !d_rgb || !out_n) return CNIIC_ERR_BAD_ARG;
+    ST_TRY(check_dims(ctx, w, h));
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    uint32_t *d_bins = nullptr, *d_keys = nullptr;
+    unsigned long long *d_counts = nullptr;
+    size_t nbins = 0;
+    int rc = cniic_dev_hist_delta_bins(ctx, d_rgb, w, h, &d_bins, &nbins);
+    if (rc == CNIIC_OK) rc = cniic_dev_dense_compact(ctx, d_bins, nbins, &d_keys, &d_counts, out_n);
+    if (d_bins) cudaFree(d_bins);
+    if (d_keys) cudaFree(d_keys);
+    if (d_counts) cudaFree(d_counts);
+    return rc;
+}
+
+extern "C" int cniic_hist_delta(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, uint32_t *out_keys, uint64_t *out_counts,
+                                size_t cap, size_t *out_n) {
+    if (!ctx || !out_n || (cap && (!out_keys || !out_counts))) return CNIIC_ERR_BAD_ARG;
+    ST_TRY(check_dims(ctx, w, h));
+    const size_t n = (size_t)w * h;
+    *out_n = 0;
+    if (n == 0) return CNIIC_OK;
+    if (!rgb) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf din;
+    CU_TRY(ctx, din.alloc(n * 3));
+    CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *d_bins = nullptr;
+    size_t nbins = 0;
+    int rc = cniic_dev_hist_delta_bins(ctx, din.as<uint8_t>(), w, h, &d_bins, &nbins);
+    if (rc == CNIIC_OK) rc = hist_out(ctx, d_bins, nbins, out_keys, out_counts, cap, out_n);
+    if (d_bins) cudaFree(d_bins);
+    return rc;
+}
+
+int cniic_dev_sse(cniic_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, size_t nbytes, uint64_t *out) {
+    DevBuf acc;
+    CU_TRY(ctx, acc.alloc(8));
+    CU_TRY(ctx, cudaMemsetAsync(acc.p, 0, 8, ctx->stream));
+    if (nbytes) {
+        sse_kernel<<<grid_for(ctx, nbytes / 4 + 1, 4), 256, 0, ctx->stream>>>(d_a, d_b, nbytes, acc.as<unsigned long long>());
+        ctx->launches++;
+    }
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaMemcpyAsync(out, acc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_sse_rgb(cniic_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n_pixels, uint64_t *out_sse) {
+    if (!ctx || !out_sse || ((!a || !b) && n_pixels)) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf da, db;
+    CU_TRY(ctx, da.alloc(n_pixels * 3));
+    CU_TRY(ctx, db.alloc(n_pixels * 3));
+    CU_TRY(ctx, cudaMemcpyAsync(da.p, a, n_pixels * 3, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(db.p, b, n_pixels * 3, cudaMemcpyHostToDevice, ctx->stream));
+    return cniic_dev_sse(ctx, da.as<uint8_t>(), db.as<uint8_t>(), n_pixels * 3, out_sse);
+}

@@ -1,0 +1,17 @@
+// stages.cuh -- device-level building blocks shared by stages.cu and codec.cu (all pointers are DEVICE pointers).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins, size_t nbins, uint32_t **d_keys, unsigned long long **d_counts, size_t *n_unique);
+int cniic_dev_hist_rgb_bins(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t **d_bins);
+int cniic_dev_hist_delta_bins(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint32_t **d_bins, size_t *nbins);
+int cniic_dev_recolor(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, const uint32_t *d_keys, const uint16_t *d_assign, size_t n_unique,
+                      const int32_t *d_cen_i32, const uint8_t *d_cen_u8, uint32_t *d_lut, uint8_t *d_out);
+int cniic_dev_keys_to_points(cniic_ctx *ctx, const uint32_t *d_keys, const unsigned long long *d_counts, size_t n, uint8_t *d_rgb, uint32_t *d_wts);
+int cniic_dev_hilbert_gather(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint8_t *d_out);
+int cniic_dev_undelta(cniic_ctx *ctx, const int16_t *d_diff, uint32_t w, uint32_t h, uint8_t *d_out);
+int cniic_dev_sse(cniic_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, size_t nbytes, uint64_t *out);
+int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t k, uint32_t max_iters, int tie_rule, uint8_t *d_out,
+                             std::vector<int32_t> *cen_host, cniic_kmeans_stats *stats);

@@ -1,0 +1,167 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, host logic (codec names, synthetic
+image generator, sharding plan), and the oracle pipelines against each other.  No GPU compute."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from cniic_b200 import _lib, codecs, dist
+import cniic_b200 as cb
+
+
+def test_library_exports_every_declared_symbol():
+    L = ctypes.CDLL(_lib.SO_PATH)
+    names = _lib.declared_symbols()
+    assert len(names) >= 40
+    missing = [s for s in names if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(cb.CniicError) as e:
+        cb.Context()
+    assert e.value.code == cb.ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(_lib.__file__)
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in text and "liboracle" not in text and "cniic_oracle" not in text, f
+
+
+@pytest.mark.parametrize("expr,name", [
+    ("cluster-colors(256)", "cluster-colors_256"), ("ccol(16)", "cluster-colors_16"), ("ccolors(7)", "cluster-colors_7"),
+    ("cluster-col(9)", "cluster-colors_9"), ("voronoi(2048)", "voronoi_2048"), ("delta", "delta"), ("hufman", "Hufman"),
+    ("HUFMAN", "Hufman"), ("hilbert(rle)", "hilbert-rle")])
+def test_codec_names(expr, name):  # clusterc.rs:59-61,116-141,191-193,274-297 ; hilbertc.rs:81-87,433-435 ; hufc.rs:42-62
+    assert codecs.codec_name(expr) == name
+
+
+@pytest.mark.parametrize("expr", ["", "voronoi", "voronoi()", "cluster-colors(x)", "zip(dict)", "Delta", "hilbert(zip)"])
+def test_codec_names_rejected(expr):
+    with pytest.raises(ValueError):
+        codecs.codec_name(expr)
+
+
+def test_synth_image_is_deterministic_and_shardable():
+    a = cb.synth_image_host(96, 64, 42, 12)
+    b = cb.synth_image_host(96, 64, 42, 12)
+    assert np.array_equal(a, b)
+    top = cb.synth_image_host(96, 40, 42, 12, y0=0, h_total=64)
+    bot = cb.synth_image_host(96, 24, 42, 12, y0=40, h_total=64)
+    assert np.array_equal(np.concatenate([top, bot]), a)
+    assert len(np.unique(a.reshape(-1, 3), axis=0)) >= 256  # enough distinct colours for every k used in the tests
+    assert not np.array_equal(a, cb.synth_image_host(96, 64, 43, 12))
+
+
+def test_row_shard_covers_image():
+    for h in (1, 7, 540, 4320):
+        for world in (1, 2, 3, 8):
+            rows = [dist.row_shard(h, world, r) for r in range(world)]
+            assert rows[0][0] == 0 and sum(n for _, n in rows) == h
+            for (y0, n), (y1, _) in zip(rows, rows[1:]):
+                assert y0 + n == y1
+
+
+def test_init_point_indices_match_oracle():
+    img = cb.synth_image_host(40, 30, 7, 6)
+    for k in (1, 3, 16, 37):
+        idx = dist.init_point_indices(40 * 30, k)
+        o = O.kmeans_xyrgb(img, k, max_iters=1, tie=O.TIE_KEEP_CURRENT)
+        # after the init the oracle's first pass uses exactly these points as centroids; reproduce the first pass
+        flat = img.reshape(-1, 3).astype(np.int64)
+        pts = np.concatenate([(np.arange(1200) % 40)[:, None], (np.arange(1200) // 40)[:, None], flat], axis=1)
+        cen = pts[idx]
+        d2 = ((pts[:, None, :] - cen[None, :, :]) ** 2).sum(-1)
+        # keep-current tie rule: current = chunk assignment
+        ppc = 1200 // k
+        cur = np.where(np.arange(1200) >= 1200 - (k - 1) * ppc, (1199 - np.arange(1200)) // ppc, k - 1)
+        best = d2.argmin(1)
+        keep = d2[np.arange(1200), cur] == d2.min(1)
+        best = np.where(keep, cur, best)
+        assert np.array_equal(best, o.assign)
+
+
+def test_local_init_contributions_sum_to_global():
+    img = cb.synth_image_host(33, 21, 3, 6)
+    n, k = 33 * 21, 16
+    full = dist.local_init_contribution(5, img, 33, 0, n, k)
+    parts = np.zeros_like(full)
+    for r in range(3):
+        y0, hl = dist.row_shard(21, 3, r)
+        parts += dist.local_init_contribution(5, img[y0:y0 + hl], 33, y0, n, k)
+    assert np.array_equal(parts, full)
+    idx = dist.init_point_indices(n, k)
+    assert np.array_equal(full[:, 0], idx % 33) and np.array_equal(full[:, 1], idx // 33)
+
+
+# ---- oracle self-consistency (exercises the checker the GPU tests rely on) ----
+
+def test_oracle_hilbert_invariants():  # hilbert.rs:40-43 ; SURVEY 8c invariants (curve parity is UNPINNED)
+    for (w, h) in [(1, 1), (1, 7), (7, 1), (4, 4), (8, 8), (5, 3), (3, 5), (13, 29), (64, 48), (100, 7)]:
+        xy = O.hilbert_xy(w, h)
+        assert len(xy) == w * h
+        lin = xy[:, 1].astype(np.int64) * w + xy[:, 0]
+        assert len(np.unique(lin)) == w * h and xy[:, 0].max() < w and xy[:, 1].max() < h  # bijection
+        assert tuple(xy[0]) == (0, 0)
+        step = np.abs(np.diff(xy.astype(np.int64), axis=0)).max(axis=1)
+        assert step.max(initial=0) <= 1  # consecutive cells are 8-adjacent
+    # README.md:87-106 4x4 diagram (y drawn upward)
+    assert O.hilbert_xy(4, 4).tolist() == [[0, 0], [1, 0], [1, 1], [0, 1], [0, 2], [0, 3], [1, 3], [1, 2], [2, 2], [2, 3],
+                                          [3, 3], [3, 2], [3, 1], [2, 1], [2, 0], [3, 0]]
+
+
+def test_oracle_delta_roundtrip_and_codecs():
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(9, 14, 3), dtype=np.uint8)
+    d = O.delta(img)
+    assert d[0].tolist() == O.hilbert_gather(img)[0].tolist()  # first diff is the first colour (hilbertc.rs:441-445)
+    assert np.array_equal(O.undelta(d, 14, 9), img)
+    for enc, dec in [(O.encode_delta, O.decode_delta), (O.encode_hufman, O.decode_hufman),
+                     (O.encode_hilbert_rle, O.decode_hilbert_rle)]:
+        assert np.array_equal(dec(enc(img)), img)  # bench.rs:57-59 lossless check
+    keys, cnts = O.hist_delta(d)
+    assert int(cnts.sum()) == 9 * 14 and np.all(np.diff(keys.astype(np.int64)) > 0)
+
+
+def test_oracle_rle_run_cap():  # hilbertc.rs:23,130 : runs are capped at 255
+    s = np.zeros((600, 3), np.uint8)
+    s[599] = 1
+    cnt, col = O.rle_exact(s)
+    assert cnt.tolist() == [255, 255, 89, 1] and col[-1].tolist() == [1, 1, 1]
+
+
+def test_oracle_voronoi_codec():  # clusterc.rs:148-189 ; stream = 16 + 19k bytes
+    img = cb.synth_image_host(48, 32, 11, 6)
+    data = O.encode_voronoi(img, 8)
+    assert len(data) == 16 + 19 * 8
+    dec = O.decode_voronoi(data)
+    assert dec.shape == img.shape
+    o = O.kmeans_xyrgb(img, 8)
+    assert np.array_equal(dec, O.voronoi_fill(o.centroids[:, :2], o.centroids[:, 2:], 48, 32))
+    assert O.mse(img, dec) == pytest.approx(O.sse(img, dec) / (48 * 32), rel=1e-12)  # bench.rs:95-104 vs exact integer SSE
+
+
+def test_oracle_verbatim_vs_exact_divergence_is_small():
+    """the reference's truncated neighbour lists make later iterations approximate; iteration 1 is exact."""
+    img = cb.synth_image_host(64, 48, 5, 12)
+    v = O.kmeans_xyrgb(img, 16, mode=O.MODE_VERBATIM, max_iters=1)
+    e = O.kmeans_xyrgb(img, 16, mode=O.MODE_EXACT, max_iters=1)
+    # distinct integer distances are never mis-ordered by the f64 path; only exact integer ties may differ (F4)
+    diff = v.assign != e.assign
+    flat = img.reshape(-1, 3).astype(np.int64)
+    pts = np.concatenate([(np.arange(64 * 48) % 64)[:, None], (np.arange(64 * 48) // 64)[:, None], flat], axis=1)
+    idx = dist.init_point_indices(64 * 48, 16)
+    d2 = ((pts[:, None, :] - pts[idx][None]) ** 2).sum(-1)
+    rows = np.nonzero(diff)[0]
+    assert np.all(d2[rows, v.assign[rows]] == d2[rows, e.assign[rows]])
+    full = O.kmeans_xyrgb(img, 16, mode=O.MODE_VERBATIM)
+    assert full.dist_evals < O.kmeans_xyrgb(img, 16, mode=O.MODE_EXACT, max_iters=full.iterations).dist_evals

@@ -1,0 +1,123 @@
+"""GPU tests at BASELINE.json's full sizes, through size-independent properties (the oracle would take hours)."""
+import numpy as np
+import pytest
+
+import cniic_b200 as cb
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cb.Context()
+    yield c
+    c.close()
+
+
+def check_kmeans_properties(pts, cen, wts, asg, k, rng, D):
+    n = len(asg)
+    assert int(wts.sum()) == n
+    cnt = np.bincount(asg, minlength=k)
+    assert np.array_equal(cnt.astype(np.uint64), wts)
+    # every non-empty centroid is the truncated integer mean of its members (clusterc.rs:81-114 / 215-248)
+    for j in range(D):
+        sums = np.bincount(asg, weights=None if False else pts[:, j].astype(np.float64), minlength=k)
+        nz = cnt > 0
+        assert np.array_equal((sums[nz].astype(np.int64) // cnt[nz]), cen[nz, j])
+    # a sample of points: the assignment is an exact nearest centroid of the PREVIOUS centroids is not observable here,
+    # so check the fixed-point property after convergence instead (done by the caller when converged)
+
+
+def test_c2_cluster_colors_k256_4096(ctx):
+    w = h = 4096
+    k = 256
+    img = cb.synth_image_host(w, 8, 0xC0FFEE + 2, 192, y0=0, h_total=h)  # only to cross-check the device generator
+    d = ctx.device_alloc(w * h * 3)
+    cb.synth_image_device(ctx, d, w, h, 0xC0FFEE + 2, 192)
+    s = cb.KMeansSession(ctx, cb.POINTS_RGB, k, d, w * h, on_device=True)
+    s.reset()
+    st = s.run(3)
+    cen, wts, asg = s.get()
+    host = np.zeros((h, w, 3), np.uint8)
+    ctx.d2h(host, d)
+    assert np.array_equal(host[:8], img)  # device generator == host generator
+    pts = host.reshape(-1, 3)
+    assert st.iterations == 3
+    check_kmeans_properties(pts, cen, wts, asg, k, None, 3)
+    # idempotence: one more pass from these centroids must reproduce itself exactly (same assign kernel, same sums)
+    s.reset()
+    st2 = s.run(3)
+    cen2, wts2, asg2 = s.get()
+    assert np.array_equal(cen, cen2) and np.array_equal(asg, asg2)
+    s.close()
+    ctx.device_free(d)
+
+
+def test_c3_voronoi_k2048_8k(ctx):
+    w, h, k = 7680, 4320, 2048
+    d = ctx.device_alloc(w * h * 3)
+    cb.synth_image_device(ctx, d, w, h, 0xC0FFEE + 3, 2048)
+    s = cb.KMeansSession(ctx, cb.POINTS_XYRGB, k, d, w * h, w=w, h_local=h, on_device=True)
+    s.reset()
+    st = s.run(2)
+    cen, wts, asg = s.get()
+    host = np.zeros((h, w, 3), np.uint8)
+    ctx.d2h(host, d)
+    n = w * h
+    pts = np.empty((n, 5), np.int32)
+    pts[:, 0] = np.arange(n, dtype=np.int64) % w
+    pts[:, 1] = np.arange(n, dtype=np.int64) // w
+    pts[:, 2:] = host.reshape(-1, 3)
+    check_kmeans_properties(pts, cen, wts, asg, k, None, 5)
+    # sample check of exact nearest-centroid: run ONE iteration, fetch its centroids, run a second, and verify a
+    # random sample of second-pass assignments against numpy int64 distances to the first-pass centroids
+    s.reset()
+    s.run(1)
+    cen1, _, asg1 = s.get()
+    s.run(1)
+    _, _, asg2 = s.get()
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, n, 4000)
+    d2 = ((pts[idx].astype(np.int64)[:, None, :] - cen1[None].astype(np.int64)) ** 2).sum(-1)
+    best = d2.min(1)
+    assert np.array_equal(d2[np.arange(len(idx)), asg2[idx]], best)
+    # keep-current tie rule: a point whose previous cluster is also a minimiser must not have moved
+    tied_prev = d2[np.arange(len(idx)), asg1[idx]] == best
+    assert np.array_equal(asg2[idx][tied_prev], asg1[idx][tied_prev])
+    # voronoi fill at full size: sample rows against numpy
+    cxy = cen[:, :2].astype(np.uint32)
+    crgb = cen[:, 2:].astype(np.uint8)
+    out = ctx.voronoi_fill(cxy, crgb, w, h)
+    ys = rng.integers(0, h, 3)
+    for y in ys:
+        xs = np.arange(w, dtype=np.int64)
+        dd = (cxy[None, :, 0].astype(np.int64) - xs[:, None]) ** 2 + (cxy[None, :, 1].astype(np.int64) - int(y)) ** 2
+        assert np.array_equal(out[y], crgb[dd.argmin(1)])
+    s.close()
+    ctx.device_free(d)
+
+
+def test_c5_integer_stages_8192(ctx):
+    w = h = 8192
+    img = cb.synth_image_host(w, h, 0xC0FFEE + 5, 4096) if False else None
+    rng = np.random.default_rng(1)
+    # smooth-ish random image built cheaply on the host
+    base = rng.integers(0, 256, size=(h // 64, w // 64, 3), dtype=np.uint8)
+    img = np.repeat(np.repeat(base, 64, axis=0), 64, axis=1)
+    img ^= rng.integers(0, 4, size=img.shape, dtype=np.uint8)
+    xy = ctx.hilbert_xy(w, h)
+    lin = xy[:, 1].astype(np.int64) * w + xy[:, 0]
+    assert np.array_equal(np.sort(lin), np.arange(w * h))  # bijection
+    assert np.abs(np.diff(xy.astype(np.int64), axis=0)).sum(axis=1).max() == 1  # true Hilbert curve on 2^n squares
+    d = ctx.delta(img)
+    g = img.reshape(-1, 3)[lin]
+    assert np.array_equal(d[0], g[0].astype(np.int16))
+    assert np.array_equal(d[1:], g[1:].astype(np.int16) - g[:-1].astype(np.int16))
+    assert np.array_equal(ctx.undelta(d, w, h), img)  # encode -> decode round trip (bench.rs:57-59)
+    keys, cnts = ctx.hist_delta(img)
+    assert int(cnts.sum()) == w * h  # checksum of the histogram
+    dk = ((d[:, 0].astype(np.int64) + 255) * 511 + (d[:, 1] + 255)) * 511 + (d[:, 2] + 255)
+    uk, uc = np.unique(dk, return_counts=True)
+    assert np.array_equal(keys, uk.astype(np.uint32)) and np.array_equal(cnts, uc.astype(np.uint64))
+    ck, cc = ctx.hist_rgb(img)
+    assert int(cc.sum()) == w * h

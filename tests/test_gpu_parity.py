@@ -1,0 +1,241 @@
+"""GPU parity tests: every CUDA stage, called through the C ABI (ctypes), against the CPU oracle on the same seeded
+inputs.  Bar: bit-exact (all arithmetic on this path is integer / byte work)."""
+import numpy as np
+import pytest
+
+import oracle as O
+import cniic_b200 as cb
+from cniic_b200 import codecs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cb.Context()
+    yield c
+    c.close()
+
+
+def same_kmeans(g, o):
+    assert g.iterations == o.iterations
+    assert np.array_equal(g.centroids, o.centroids)
+    assert np.array_equal(g.weights, o.weights)
+    assert np.array_equal(g.assign, o.assign)
+    assert g.moved_last == o.moved_last and g.moved_total == o.moved_total
+    assert g.empty_events == o.empty_events
+
+
+# ---- K-means D = 3 (ColorCount, clusterc.rs:68-114) ----
+@pytest.mark.parametrize("w,h,k", [(512, 512, 16), (97, 61, 5), (200, 150, 64), (333, 257, 256), (64, 33, 1), (50, 41, 300)])
+@pytest.mark.parametrize("tie", [cb.TIE_KEEP_CURRENT, cb.TIE_LOWEST_INDEX])
+@pytest.mark.parametrize("max_iters", [1, 4, 0])
+def test_kmeans_rgb_per_pixel(ctx, w, h, k, tie, max_iters):
+    img = cb.synth_image_host(w, h, 0xC0FFEE + k, 24)
+    g = ctx.kmeans_rgb(img, k, max_iters=max_iters, tie=tie)
+    o = O.kmeans_rgb(img, k, mode=O.MODE_EXACT, tie=tie, max_iters=max_iters)
+    same_kmeans(g, o)
+    if max_iters == 0:
+        assert g.converged and g.moved_last == 0
+
+
+@pytest.mark.parametrize("k", [16, 256])
+def test_kmeans_rgb_weighted_unique_colours(ctx, k):  # the reference clusters (colour, count) pairs, clusterc.rs:19-28
+    img = cb.synth_image_host(320, 200, 99, 24)
+    keys, cnts = O.count_freqs_rgb(img)
+    urgb = np.stack([keys >> 16, (keys >> 8) & 255, keys & 255], axis=1).astype(np.uint8)
+    g = ctx.kmeans_rgb(urgb, k, counts=cnts.astype(np.uint32))
+    o = O.kmeans_rgb(urgb, k, counts=cnts.astype(np.uint32), mode=O.MODE_EXACT)
+    same_kmeans(g, o)
+    assert int(g.weights.sum()) == 320 * 200
+
+
+def test_kmeans_rgb_heavy_weights_need_u64(ctx):
+    rgb = np.array([[255, 255, 255], [254, 255, 255], [0, 0, 0], [1, 0, 0], [128, 128, 128], [129, 128, 128]], np.uint8)
+    cnt = np.array([4_000_000_000, 4_000_000_001, 3_999_999_999, 17, 4_294_967_295, 4_294_967_295], np.uint32)
+    g = ctx.kmeans_rgb(rgb, 3, counts=cnt)
+    o = O.kmeans_rgb(rgb, 3, counts=cnt, mode=O.MODE_EXACT)
+    same_kmeans(g, o)
+
+
+def test_kmeans_rgb_empty_clusters_are_repaired_deterministically(ctx):  # kmeans.rs:117-134 stand-in
+    rng = np.random.default_rng(3)
+    palette = rng.integers(0, 256, size=(6, 3), dtype=np.uint8)
+    pts = palette[rng.integers(0, 6, size=5000)]
+    for tie in (cb.TIE_KEEP_CURRENT, cb.TIE_LOWEST_INDEX):
+        g = ctx.kmeans_rgb(pts, 12, max_iters=6, tie=tie, allow_inactive=True)
+        o = O.kmeans_rgb(pts, 12, mode=O.MODE_EXACT, tie=tie, max_iters=6, allow_inactive=True)
+        assert o.empty_events > 0
+        same_kmeans(g, o)
+        assert g.status == o.status  # kmeans.rs:41-57 too-few-active check
+
+
+def test_kmeans_errors(ctx):
+    img = cb.synth_image_host(8, 2, 1, 2)
+    with pytest.raises(cb.CniicError) as e:  # kmeans.rs:67-68
+        ctx.kmeans_rgb(img, 17)
+    assert e.value.code == cb.ERR_TOO_FEW_POINTS
+    with pytest.raises(cb.CniicError) as e:
+        ctx.kmeans_rgb(img, 0)
+    assert e.value.code == cb.ERR_BAD_ARG
+    with pytest.raises(cb.CniicError) as e:
+        ctx.kmeans_xyrgb(img, cb.MAX_K + 1)
+    assert e.value.code == cb.ERR_BAD_ARG
+
+
+# ---- K-means D = 5 (ColorPos, clusterc.rs:148-153,200-248) ----
+@pytest.mark.parametrize("w,h,k", [(64, 48, 16), (257, 131, 64), (300, 200, 256), (1024, 96, 100), (31, 9, 7), (640, 360, 2048)])
+@pytest.mark.parametrize("tie", [cb.TIE_KEEP_CURRENT, cb.TIE_LOWEST_INDEX])
+def test_kmeans_xyrgb(ctx, w, h, k, tie):
+    img = cb.synth_image_host(w, h, 0xC0FFEE + 3, max(4, k // 8))
+    for max_iters in ((1, 3) if k >= 256 else (1, 3, 0)):
+        g = ctx.kmeans_xyrgb(img, k, max_iters=max_iters, tie=tie)
+        o = O.kmeans_xyrgb(img, k, mode=O.MODE_EXACT, tie=tie, max_iters=max_iters)
+        same_kmeans(g, o)
+
+
+def test_kmeans_xyrgb_flat_image_has_exact_ties(ctx):
+    """A constant-colour image makes many pixels equidistant from two centroids: the documented near-tie cases."""
+    img = np.full((40, 64, 3), 77, np.uint8)
+    for tie in (cb.TIE_KEEP_CURRENT, cb.TIE_LOWEST_INDEX):
+        g = ctx.kmeans_xyrgb(img, 8, tie=tie)
+        o = O.kmeans_xyrgb(img, 8, mode=O.MODE_EXACT, tie=tie)
+        same_kmeans(g, o)
+
+
+def test_kmeans_session_reuse(ctx):
+    img = cb.synth_image_host(128, 64, 8, 8)
+    s = cb.KMeansSession(ctx, cb.POINTS_XYRGB, 32, img, 128 * 64, w=128, h_local=64)
+    outs = []
+    for _ in range(2):
+        s.reset()
+        st = s.run(5)
+        cen, wts, asg = s.get()
+        outs.append((cen, wts, asg, st.iterations))
+    s.close()
+    o = O.kmeans_xyrgb(img, 32, max_iters=5)
+    for cen, wts, asg, it in outs:
+        assert it == 5 and np.array_equal(cen, o.centroids) and np.array_equal(asg, o.assign)
+
+
+# ---- cluster-colors pipeline (clusterc.rs:18-52) ----
+@pytest.mark.parametrize("k", [16, 64])
+def test_cluster_colors_pipeline(ctx, k):
+    img = cb.synth_image_host(256, 192, 21, 12)
+    out, cen, st = ctx.cluster_colors(img, k)
+    oout, ocen, oit = O.cluster_colors(img, k)
+    assert st.iterations == oit
+    assert np.array_equal(cen, ocen) and np.array_equal(out, oout)
+
+
+def test_hist_rgb_and_recolor(ctx):
+    img = cb.synth_image_host(300, 100, 4, 9)
+    keys, cnts = ctx.hist_rgb(img)
+    okeys, ocnts = O.count_freqs_rgb(img)
+    assert np.array_equal(keys, okeys) and np.array_equal(cnts, ocnts)
+    asg = (np.arange(len(keys)) % 5).astype(np.uint16)
+    cen = np.arange(15, dtype=np.uint8).reshape(5, 3) * 10
+    out = ctx.recolor_rgb(img, keys, asg, cen)
+    lut = {int(k): cen[a] for k, a in zip(keys, asg)}
+    flat = img.reshape(-1, 3).astype(np.uint32)
+    exp = np.array([lut[int((p[0] << 16) | (p[1] << 8) | p[2])] for p in flat[:2000]], np.uint8)
+    assert np.array_equal(out.reshape(-1, 3)[:2000], exp)
+    # extremes: a single colour, and all-distinct colours
+    k1, c1 = ctx.hist_rgb(np.full((10, 10, 3), 200, np.uint8))
+    assert k1.tolist() == [(200 << 16) | (200 << 8) | 200] and c1.tolist() == [100]
+    k0, c0 = ctx.hist_rgb(np.zeros((0, 3), np.uint8))
+    assert len(k0) == 0
+
+
+# ---- voronoi fill (clusterc.rs:179-186) ----
+@pytest.mark.parametrize("w,h,k", [(64, 64, 1), (200, 130, 17), (513, 97, 300), (640, 360, 2048)])
+def test_voronoi_fill(ctx, w, h, k):
+    rng = np.random.default_rng(k)
+    cxy = np.stack([rng.integers(0, w, k), rng.integers(0, h, k)], axis=1).astype(np.uint32)
+    cxy[k // 2] = cxy[0]  # duplicate centroid: the first one must win (min_by_key returns the first minimum)
+    crgb = rng.integers(0, 256, size=(k, 3), dtype=np.uint8)
+    assert np.array_equal(ctx.voronoi_fill(cxy, crgb, w, h), O.voronoi_fill(cxy, crgb, w, h))
+
+
+def test_voronoi_fill_ties_and_outside_centroids(ctx):
+    cxy = np.array([[10, 10], [30, 10], [10, 30], [30, 30], [500, 500], [20, 20], [20, 20]], np.uint32)
+    crgb = (np.arange(21, dtype=np.uint8).reshape(7, 3) + 1) * 9
+    assert np.array_equal(ctx.voronoi_fill(cxy, crgb, 41, 41), O.voronoi_fill(cxy, crgb, 41, 41))
+    with pytest.raises(cb.CniicError):
+        ctx.voronoi_fill(np.zeros((0, 2), np.uint32), np.zeros((0, 3), np.uint8), 4, 4)  # clusterc.rs:182-184 unwrap
+
+
+# ---- Hilbert / delta / histograms (hilbert.rs:34-43, hilbertc.rs:449-477) ----
+@pytest.mark.parametrize("w,h", [(1, 1), (1, 9), (9, 1), (4, 4), (64, 64), (5, 3), (3, 5), (100, 7), (123, 77), (256, 256), (640, 360)])
+def test_hilbert_delta_stages(ctx, w, h):
+    img = cb.synth_image_host(w, h, 17, 4)
+    assert np.array_equal(ctx.hilbert_xy(w, h), O.hilbert_xy(w, h))
+    assert np.array_equal(ctx.hilbert_gather(img), O.hilbert_gather(img))
+    d = ctx.delta(img)
+    assert np.array_equal(d, O.delta(img))
+    assert np.array_equal(ctx.undelta(d, w, h), img)
+    keys, cnts = ctx.hist_delta(img)
+    okeys, ocnts = O.hist_delta(O.delta(img))
+    assert np.array_equal(keys, okeys) and np.array_equal(cnts, ocnts)
+
+
+def test_hist_delta_extremes(ctx):
+    flat = np.full((64, 64, 3), 9, np.uint8)  # all-equal image: two symbols (first colour, zero diff)
+    keys, cnts = ctx.hist_delta(flat)
+    assert sorted(cnts.tolist()) == [1, 64 * 64 - 1]
+    rng = np.random.default_rng(0)
+    noise = rng.integers(0, 256, size=(128, 128, 3), dtype=np.uint8)
+    keys, cnts = ctx.hist_delta(noise)
+    okeys, ocnts = O.hist_delta(O.delta(noise))
+    assert np.array_equal(keys, okeys) and np.array_equal(cnts, ocnts)
+
+
+def test_sse(ctx):
+    a = cb.synth_image_host(333, 77, 1, 5)
+    b = cb.synth_image_host(333, 77, 2, 5)
+    assert ctx.sse(a, b) == O.sse(a, b)
+    assert ctx.sse(a, a) == 0
+    assert ctx.sse(a, b) / (333 * 77) == pytest.approx(O.mse(a, b), rel=1e-9)  # bench.rs:95-104, tolerance 1e-6 in north_star
+
+
+# ---- whole codecs: byte streams equal the oracle's, decoders invert (codec.rs:14-19, bench.rs:45-59) ----
+@pytest.mark.parametrize("expr,oenc,odec", [
+    ("hufman", lambda im: O.encode_hufman(im), O.decode_hufman),
+    ("delta", lambda im: O.encode_delta(im), O.decode_delta),
+    ("hilbert(rle)", lambda im: O.encode_hilbert_rle(im), O.decode_hilbert_rle),
+    ("voronoi(24)", lambda im: O.encode_voronoi(im, 24), O.decode_voronoi),
+    ("cluster-colors(16)", lambda im: O.encode_cluster_colors(im, 16), O.decode_hufman),
+])
+@pytest.mark.parametrize("w,h", [(96, 64), (57, 31)])
+def test_codec_streams(ctx, expr, oenc, odec, w, h):
+    img = cb.synth_image_host(w, h, 31, 5)
+    if expr == "hilbert(rle)":
+        img = (img // 64) * 64  # give the run-length coder some runs
+    c = codecs.Codec.from_str(ctx, expr)
+    data = c.encode(img)
+    assert data == oenc(img)
+    dec = c.decode(data)
+    assert np.array_equal(dec, odec(data))
+    if c.is_lossless():
+        assert np.array_equal(dec, img)  # bench.rs:57-59
+    else:
+        assert ctx.sse(img, dec) / (w * h) == pytest.approx(O.mse(img, odec(data)), rel=1e-6)
+
+
+def test_codec_decode_rejects_malformed(ctx):
+    img = cb.synth_image_host(32, 16, 5, 3)
+    for expr in ("hufman", "delta", "voronoi(8)", "hilbert(rle)"):
+        c = codecs.Codec.from_str(ctx, expr)
+        data = c.encode(img)
+        assert c.decode(data[:len(data) // 2]) is None  # Codec::decode -> None
+        assert c.decode(data[:5]) is None
+    with pytest.raises(cb.CniicError):
+        ctx.codec_encode("zip(dict)", img)
+
+
+def test_single_colour_image_codecs(ctx):  # huf.rs:139-142 zero-length code
+    img = np.full((8, 8, 3), 50, np.uint8)
+    c = codecs.Hufman(ctx)
+    data = c.encode(img)
+    assert data == O.encode_hufman(img) and len(data) == 8 + 12
+    assert np.array_equal(c.decode(data), img)
