@@ -144,7 +144,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     D = 5 if kind == "xyrgb" else 3
     cores = os.cpu_count() or 1
-    cpu_px = args.cpu_px or (512 * 512 if kind == "rgb" else 256 * 256)
+    cpu_px = args.cpu_px or (1024 * 8192 if kind == "rgb" else 1024 * 2048)  # ~10-20 s of single-thread CPU work
 
     # ------------------------------------------------------------------ reference arm (CPU) -----------------
     if args.impl == "reference":

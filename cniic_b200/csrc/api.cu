@@ -1,6 +1,7 @@
 // api.cu -- context management, error reporting, NCCL (dlopen) plumbing of the cniic_b200 C ABI.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 
@@ -17,6 +18,58 @@ int cniic_set_error(cniic_ctx *ctx, int code, const char *fmt, ...) {
         ctx->err = buf;
     }
     return code;
+}
+
+void *cniic_cache_alloc(cniic_ctx *ctx, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 16) + 255) & ~size_t(255);
+    int best = -1;
+    for (size_t i = 0; i < ctx->cache.size(); i++) {
+        const cniic_ctx::Block &b = ctx->cache[i];
+        if (!b.used && b.bytes >= bytes && b.bytes <= 2 * bytes + (size_t(1) << 20) && (best < 0 || b.bytes < ctx->cache[best].bytes)) best = (int)i;
+    }
+    if (best >= 0) {
+        ctx->cache[best].used = true;
+        return ctx->cache[best].p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        // give cached-but-unused blocks back to the driver and retry once
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        for (size_t i = 0; i < ctx->cache.size();) {
+            if (!ctx->cache[i].used) { cudaFree(ctx->cache[i].p); ctx->cache.erase(ctx->cache.begin() + i); }
+            else i++;
+        }
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    ctx->cache.push_back({p, bytes, true});
+    return p;
+}
+
+void cniic_cache_free(cniic_ctx *ctx, void *p) {
+    if (!p) return;
+    for (cniic_ctx::Block &b : ctx->cache)
+        if (b.p == p) { b.used = false; return; }
+}
+
+void *cniic_pinned_get(cniic_ctx *ctx) {
+    if (!ctx->pinned_free.empty()) {
+        void *p = ctx->pinned_free.back();
+        ctx->pinned_free.pop_back();
+        return p;
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, 256) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void cniic_pinned_put(cniic_ctx *ctx, void *p) {
+    if (p) ctx->pinned_free.push_back(p);
 }
 
 int cniic_launch_bump(cniic_ctx *ctx, uint32_t n) {
@@ -158,6 +211,8 @@ extern "C" void cniic_ctx_destroy(cniic_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cniic_nccl_destroy(ctx);
+    for (cniic_ctx::Block &b : ctx->cache) cudaFree(b.p);
+    for (void *p : ctx->pinned_free) cudaFreeHost(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

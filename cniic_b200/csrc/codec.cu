@@ -16,12 +16,6 @@
 
 namespace {
 
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes < 16 ? 16 : bytes); }
-    template <class T> T *as() { return static_cast<T *>(p); }
-};
 
 // ---- codec expression parsing (clusterc.rs:116-141, 274-297; hilbertc.rs:337-395, 574-582; hufc.rs:51-63) ----
 enum CodecKind { CK_NONE, CK_CLUSTER_COLORS, CK_VORONOI, CK_DELTA, CK_HUFMAN, CK_HILBERT_RLE };
@@ -232,9 +226,9 @@ int encode_hufman_body(cniic_ctx *ctx, const uint8_t *d_rgb, const uint8_t *host
         cudaMemcpyAsync(counts.data(), d_counts, u * 8, cudaMemcpyDeviceToHost, ctx->stream);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "histogram copy failed");
     }
-    if (d_bins) cudaFree(d_bins);
-    if (d_keys) cudaFree(d_keys);
-    if (d_counts) cudaFree(d_counts);
+    cniic_cache_free(ctx, d_bins);
+    cniic_cache_free(ctx, d_keys);
+    cniic_cache_free(ctx, d_counts);
     if (rc != CNIIC_OK) return rc;
     HufTree T;
     if (!huf_build(counts, &T)) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "Huffman code longer than 64 bits");
@@ -289,7 +283,7 @@ extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8
     if (n >= (size_t(1) << 31)) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "image too large");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     Sink s;
-    DevBuf din;
+    DevBuf din(ctx);
     CU_TRY(ctx, din.alloc(n * 3));
     if (n) CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
     switch (sp.kind) {
@@ -300,7 +294,7 @@ extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8
     }
     case CK_CLUSTER_COLORS: {  // clusterc.rs:18-53
         if (sp.arg == 0 || sp.arg > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d", CNIIC_MAX_K);
-        DevBuf dred;
+        DevBuf dred(ctx);
         CU_TRY(ctx, dred.alloc(n * 3));
         ST_TRY(cniic_dev_cluster_colors(ctx, din.as<uint8_t>(), n, sp.arg, ctx->codec_max_iters, CNIIC_TIE_KEEP_CURRENT, dred.as<uint8_t>(), nullptr, nullptr));
         std::vector<uint8_t> red(n * 3);
@@ -340,9 +334,9 @@ extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8
             cudaMemcpyAsync(counts.data(), d_counts, u * 8, cudaMemcpyDeviceToHost, ctx->stream);
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "histogram copy failed");
         }
-        if (d_bins) cudaFree(d_bins);
-        if (d_keys) cudaFree(d_keys);
-        if (d_counts) cudaFree(d_counts);
+        cniic_cache_free(ctx, d_bins);
+        cniic_cache_free(ctx, d_keys);
+        cniic_cache_free(ctx, d_counts);
         ST_TRY(rc);
         HufTree T;
         if (!huf_build(counts, &T)) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "Huffman code longer than 64 bits");
@@ -352,7 +346,7 @@ extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8
             for (int j = 0; j < 3; j++) { s.u8((uint8_t)((uint16_t)d[j] & 0xff)); s.u8((uint8_t)((uint16_t)d[j] >> 8)); }
         });
         // pass 2: the delta stream itself (GPU) -> host bit packing
-        DevBuf dd;
+        DevBuf dd(ctx);
         CU_TRY(ctx, dd.alloc(n * 6));
         ST_TRY(cniic_delta_i16_device(ctx, din.as<uint8_t>(), w, h, dd.as<int16_t>()));
         std::vector<int16_t> diff(n * 3);
@@ -372,7 +366,7 @@ extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8
     case CK_HILBERT_RLE: {  // hilbertc.rs:26-38, 99-196 ; records = u8 count (1..=255) + Rgb slice
         s.u32(w); s.u32(h);
         if (n) {
-            DevBuf dl;
+            DevBuf dl(ctx);
             CU_TRY(ctx, dl.alloc(n * 3));
             ST_TRY(cniic_dev_hilbert_gather(ctx, din.as<uint8_t>(), w, h, dl.as<uint8_t>()));
             std::vector<uint8_t> lin(n * 3);

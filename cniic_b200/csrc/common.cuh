@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/cniic_b200.h"
 
@@ -24,6 +25,27 @@ struct cniic_ctx {
     NcclApi *nccl = nullptr;
     uint32_t codec_max_iters = 0;
     uint32_t launches = 0;  // kernels launched on this ctx (bench.py reports it as gpu_launches)
+    // device scratch cache: blocks are reused across calls (all work is ordered on `stream`, so reuse is safe);
+    // nothing is returned to the driver before cniic_ctx_destroy -- cudaMalloc/cudaFree cost milliseconds per call
+    struct Block { void *p; size_t bytes; bool used; };
+    std::vector<Block> cache;
+    std::vector<void *> pinned_free;  // 256-byte pinned host slots
+};
+
+void *cniic_cache_alloc(cniic_ctx *ctx, size_t bytes);  // nullptr + error set on failure
+void cniic_cache_free(cniic_ctx *ctx, void *p);
+void *cniic_pinned_get(cniic_ctx *ctx);
+void cniic_pinned_put(cniic_ctx *ctx, void *p);
+
+struct DevBuf {  // RAII scratch from the ctx cache
+    cniic_ctx *ctx;
+    void *p = nullptr;
+    explicit DevBuf(cniic_ctx *c) : ctx(c) {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { if (p) cniic_cache_free(ctx, p); }
+    cudaError_t alloc(size_t bytes) { p = cniic_cache_alloc(ctx, bytes); return p ? cudaSuccess : cudaErrorMemoryAllocation; }
+    template <class T> T *as() { return static_cast<T *>(p); }
 };
 
 int cniic_set_error(cniic_ctx *ctx, int code, const char *fmt, ...);

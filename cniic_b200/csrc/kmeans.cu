@@ -681,11 +681,13 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     const uint8_t *d_rgb = desc->rgb;
     const uint32_t *d_wts = desc->weights;
     if (!desc->points_on_device) {
-        KM_TRY(cudaMalloc(&km->own_rgb, std::max<size_t>(16, desc->n_local * 3)));
+        km->own_rgb = static_cast<uint8_t *>(cniic_cache_alloc(ctx, desc->n_local * 3));
+        if (!km->own_rgb) return fail(CNIIC_ERR_CUDA);
         KM_TRY(cudaMemcpyAsync(km->own_rgb, desc->rgb, desc->n_local * 3, cudaMemcpyHostToDevice, ctx->stream));
         d_rgb = km->own_rgb;
         if (desc->weights) {
-            KM_TRY(cudaMalloc(&km->own_wts, std::max<size_t>(16, desc->n_local * 4)));
+            km->own_wts = static_cast<uint32_t *>(cniic_cache_alloc(ctx, desc->n_local * 4));
+            if (!km->own_wts) return fail(CNIIC_ERR_CUDA);
             KM_TRY(cudaMemcpyAsync(km->own_wts, desc->weights, desc->n_local * 4, cudaMemcpyHostToDevice, ctx->stream));
             d_wts = km->own_wts;
         }
@@ -701,9 +703,11 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     const size_t o_cpk = take(KP * 4), o_cxy = take(KP * 4), o_bias = take(KP * 4), o_id = take(KP * 2), o_pos = take(k * 2);
     const size_t o_sums = take((size_t(k) * (D + 1) + 1) * 8), o_cen = take(size_t(k) * D * 4), o_w = take(size_t(k) * 8);
     const size_t o_st = take(sizeof(KmState));
-    KM_TRY(cudaMalloc(&km->pool, off));
+    km->pool = cniic_cache_alloc(ctx, off);
+    if (!km->pool) return fail(CNIIC_ERR_CUDA);
     KM_TRY(cudaMemsetAsync(km->pool, 0, off, ctx->stream));
-    KM_TRY(cudaMallocHost(&km->h_state, sizeof(KmState)));
+    km->h_state = static_cast<KmState *>(cniic_pinned_get(ctx));
+    if (!km->h_state) return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMallocHost failed"));
     char *p = static_cast<char *>(km->pool);
     KmDev &dv = km->dev;
     dv.rgb = d_rgb;
@@ -848,10 +852,10 @@ extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
     if (!km) return;
     cudaSetDevice(km->ctx->device);
     cudaStreamSynchronize(km->ctx->stream);
-    if (km->own_rgb) cudaFree(km->own_rgb);
-    if (km->own_wts) cudaFree(km->own_wts);
-    if (km->pool) cudaFree(km->pool);
-    if (km->h_state) cudaFreeHost(km->h_state);
+    cniic_cache_free(km->ctx, km->own_rgb);
+    cniic_cache_free(km->ctx, km->own_wts);
+    cniic_cache_free(km->ctx, km->pool);
+    cniic_pinned_put(km->ctx, km->h_state);
     if (km->ev0) cudaEventDestroy(km->ev0);
     if (km->ev1) cudaEventDestroy(km->ev1);
     for (cudaEvent_t e : km->pev)

@@ -445,8 +445,8 @@ int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins, size_t nbins
     const size_t nblocks = (nbins + CB - 1) / CB;
     uint32_t *d_bc = nullptr;
     unsigned long long *d_off = nullptr;
-    CU_TRY(ctx, cudaMalloc(&d_bc, nblocks * 4));
-    CU_TRY(ctx, cudaMalloc(&d_off, (nblocks + 1) * 8));
+    if (!(d_bc = static_cast<decltype(d_bc)>(cniic_cache_alloc(ctx, nblocks * 4)))) return CNIIC_ERR_CUDA;
+    if (!(d_off = static_cast<decltype(d_off)>(cniic_cache_alloc(ctx, (nblocks + 1) * 8)))) return CNIIC_ERR_CUDA;
     count_nonzero_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_bins, nbins, d_bc);
     scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(d_bc, nblocks, d_off);
     ctx->launches += 2;
@@ -456,20 +456,20 @@ int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins, size_t nbins
     *n_unique = (size_t)total;
     *d_keys = nullptr;
     *d_counts = nullptr;
-    CU_TRY(ctx, cudaMalloc(d_keys, std::max<size_t>(16, total * 4)));
-    CU_TRY(ctx, cudaMalloc(d_counts, std::max<size_t>(16, total * 8)));
+    if (!(*d_keys = static_cast<std::remove_reference<decltype(*d_keys)>::type>(cniic_cache_alloc(ctx, std::max<size_t>(16, total * 4))))) return CNIIC_ERR_CUDA;
+    if (!(*d_counts = static_cast<std::remove_reference<decltype(*d_counts)>::type>(cniic_cache_alloc(ctx, std::max<size_t>(16, total * 8))))) return CNIIC_ERR_CUDA;
     compact_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_bins, nbins, d_off, *d_keys, *d_counts, total);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_bc);
-    cudaFree(d_off);
+    cniic_cache_free(ctx, d_bc);
+    cniic_cache_free(ctx, d_off);
     return CNIIC_OK;
 }
 
 int cniic_dev_hist_rgb_bins(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t **d_bins) {
     *d_bins = nullptr;
-    CU_TRY(ctx, cudaMalloc(d_bins, (size_t(1) << 24) * 4));
+    if (!(*d_bins = static_cast<std::remove_reference<decltype(*d_bins)>::type>(cniic_cache_alloc(ctx, (size_t(1) << 24) * 4)))) return CNIIC_ERR_CUDA;
     CU_TRY(ctx, cudaMemsetAsync(*d_bins, 0, (size_t(1) << 24) * 4, ctx->stream));
     if (n) {
         hist_rgb_kernel<<<grid_for(ctx, n, 4), 256, 0, ctx->stream>>>(d_rgb, n, *d_bins);
@@ -513,7 +513,7 @@ int cniic_dev_hilbert_gather(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, u
 int cniic_dev_hist_delta_bins(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint32_t **d_bins, size_t *nbins) {
     *nbins = (size_t)511 * 511 * 511;
     *d_bins = nullptr;
-    CU_TRY(ctx, cudaMalloc(d_bins, *nbins * 4));
+    if (!(*d_bins = static_cast<std::remove_reference<decltype(*d_bins)>::type>(cniic_cache_alloc(ctx, *nbins * 4)))) return CNIIC_ERR_CUDA;
     CU_TRY(ctx, cudaMemsetAsync(*d_bins, 0, *nbins * 4, ctx->stream));
     hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins);
     ctx->launches++;
@@ -523,12 +523,6 @@ int cniic_dev_hist_delta_bins(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, 
 
 // ---- C ABI -----------------------------------------------------------------------------------------------------
 
-struct DevBuf {  // RAII device buffer
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(16, bytes)); }
-    template <class T> T *as() { return static_cast<T *>(p); }
-};
 
 extern "C" int cniic_voronoi_fill_device(cniic_ctx *ctx, const uint32_t *d_cxy, const uint8_t *d_crgb, uint32_t k, uint32_t w,
                                          uint32_t h, uint32_t y0, uint32_t h_local, uint8_t *d_out_rgb) {
@@ -556,7 +550,7 @@ extern "C" int cniic_voronoi_fill(cniic_ctx *ctx, const uint32_t *cxy, const uin
             return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "centroid coordinate >= 32768 (u32 wrap-around of the reference is not reproduced)");
     if ((size_t)w * h == 0) return CNIIC_OK;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    DevBuf dxy, drgb, dout;
+    DevBuf dxy(ctx), drgb(ctx), dout(ctx);
     CU_TRY(ctx, dxy.alloc((size_t)k * 8));
     CU_TRY(ctx, drgb.alloc((size_t)k * 3));
     CU_TRY(ctx, dout.alloc((size_t)w * h * 3));
@@ -582,8 +576,8 @@ static int hist_out(cniic_ctx *ctx, uint32_t *d_bins, size_t nbins, uint32_t *ou
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "histogram copy failed");
         }
     }
-    if (d_keys) cudaFree(d_keys);
-    if (d_counts) cudaFree(d_counts);
+    cniic_cache_free(ctx, d_keys);
+    cniic_cache_free(ctx, d_counts);
     return rc;
 }
 
@@ -591,13 +585,13 @@ extern "C" int cniic_hist_rgb(cniic_ctx *ctx, const uint8_t *rgb, size_t n, uint
                               size_t *out_n) {
     if (!ctx || (!rgb && n) || !out_n || (cap && (!out_keys || !out_counts))) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    DevBuf din;
+    DevBuf din(ctx);
     CU_TRY(ctx, din.alloc(n * 3));
     CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
     uint32_t *d_bins = nullptr;
     int rc = cniic_dev_hist_rgb_bins(ctx, din.as<uint8_t>(), n, &d_bins);
     if (rc == CNIIC_OK) rc = hist_out(ctx, d_bins, size_t(1) << 24, out_keys, out_counts, cap, out_n);
-    if (d_bins) cudaFree(d_bins);
+    cniic_cache_free(ctx, d_bins);
     return rc;
 }
 
@@ -607,7 +601,7 @@ extern "C" int cniic_recolor_rgb(cniic_ctx *ctx, const uint8_t *rgb, size_t n, c
     for (size_t i = 0; i < n_unique; i++)
         if (assign[i] >= k || keys[i] >= (1u << 24)) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "assignment / key out of range");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    DevBuf din, dkeys, dasg, dcen, dlut, dout;
+    DevBuf din(ctx), dkeys(ctx), dasg(ctx), dcen(ctx), dlut(ctx), dout(ctx);
     CU_TRY(ctx, din.alloc(n * 3));
     CU_TRY(ctx, dkeys.alloc(n_unique * 4));
     CU_TRY(ctx, dasg.alloc(n_unique * 2));
@@ -634,7 +628,7 @@ int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uin
     size_t u = 0;
     int rc = cniic_dev_hist_rgb_bins(ctx, d_rgb, n, &d_bins);
     if (rc == CNIIC_OK) rc = cniic_dev_dense_compact(ctx, d_bins, size_t(1) << 24, &d_keys, &d_counts, &u);
-    DevBuf upts, uwts;
+    DevBuf upts(ctx), uwts(ctx);
     cniic_kmeans *km = nullptr;
     if (rc == CNIIC_OK && u / k == 0) rc = cniic_set_error(ctx, CNIIC_ERR_TOO_FEW_POINTS, "only %zu distinct colours for k = %u (kmeans.rs:67-68)", u, k);
     if (rc == CNIIC_OK && (upts.alloc(u * 3) != cudaSuccess || uwts.alloc(u * 4) != cudaSuccess)) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc failed");
@@ -657,7 +651,7 @@ int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uin
     if (rc == CNIIC_OK) rc = cniic_kmeans_get(km, cen.data(), wts.data(), nullptr);
     if (rc == CNIIC_OK) {
         // the histogram bins are dead now: reuse them as the colour -> centroid colour lookup table
-        DevBuf dcen;
+        DevBuf dcen(ctx);
         if (dcen.alloc(cen.size() * 4) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc failed");
         if (rc == CNIIC_OK) {
             cudaMemcpyAsync(dcen.p, cen.data(), cen.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
@@ -666,9 +660,9 @@ int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uin
         }
     }
     if (km) cniic_kmeans_close(km);
-    if (d_bins) cudaFree(d_bins);
-    if (d_keys) cudaFree(d_keys);
-    if (d_counts) cudaFree(d_counts);
+    cniic_cache_free(ctx, d_bins);
+    cniic_cache_free(ctx, d_keys);
+    cniic_cache_free(ctx, d_counts);
     if (rc != CNIIC_OK) return rc;
     if (cen_host) *cen_host = cen;
     // kmeans.rs:41-57
@@ -686,7 +680,7 @@ extern "C" int cniic_cluster_colors(cniic_ctx *ctx, const uint8_t *rgb, uint32_t
     if (k == 0 || k > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d", CNIIC_MAX_K);
     const size_t n = (size_t)w * h;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    DevBuf din, dout;
+    DevBuf din(ctx), dout(ctx);
     CU_TRY(ctx, din.alloc(n * 3));
     CU_TRY(ctx, dout.alloc(n * 3));
     CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
@@ -712,7 +706,7 @@ extern "C" int cniic_hilbert_xy(cniic_ctx *ctx, uint32_t w, uint32_t h, uint32_t
     if (n == 0) return CNIIC_OK;
     if (!out_xy) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    DevBuf d;
+    DevBuf d(ctx);
     CU_TRY(ctx, d.alloc(n * 8));
     hilbert_xy_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(w, h, is_pow2_square(w, h), d.as<uint32_t>());
     ctx->launches++;
@@ -729,7 +723,7 @@ extern "C" int cniic_hilbert_gather_rgb(cniic_ctx *ctx, const uint8_t *rgb, uint
     if (n == 0) return CNIIC_OK;
     if (!rgb || !out_rgb) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    DevBuf din, dout;
+    DevBuf din(ctx), dout(ctx);
     CU_TRY(ctx, din.alloc(n * 3));
     CU_TRY(ctx, dout.alloc(n * 3));
     CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
@@ -758,7 +752,7 @@ extern "C" int cniic_delta_i16(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, u
     if (n == 0) return CNIIC_OK;
     if (!rgb || !out) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    DevBuf din, dout;
+    DevBuf din(ctx), dout(ctx);
     CU_TRY(ctx, din.alloc(n * 3));
     CU_TRY(ctx, dout.alloc(n * 6));
     CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
@@ -771,7 +765,7 @@ extern "C" int cniic_delta_i16(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, u
 int cniic_dev_undelta(cniic_ctx *ctx, const int16_t *d_diff, uint32_t w, uint32_t h, uint8_t *d_out) {
     const unsigned long long n = (unsigned long long)w * h;
     const size_t nblocks = (n + 4095) / 4096;
-    DevBuf bs;
+    DevBuf bs(ctx);
     CU_TRY(ctx, bs.alloc(nblocks * 12));
     undelta_partial_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_diff, n, bs.as<int>());
     undelta_scan_blocks_kernel<<<1, 32, 0, ctx->stream>>>(bs.as<int>(), nblocks);
@@ -789,7 +783,7 @@ extern "C" int cniic_undelta_rgb(cniic_ctx *ctx, const int16_t *diff, uint32_t w
     if (n == 0) return CNIIC_OK;
     if (!diff || !out_rgb) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    DevBuf din, dout;
+    DevBuf din(ctx), dout(ctx);
     CU_TRY(ctx, din.alloc(n * 6));
     CU_TRY(ctx, dout.alloc(n * 3));
     CU_TRY(ctx, cudaMemcpyAsync(din.p, diff, n * 6, cudaMemcpyHostToDevice, ctx->stream));
@@ -808,9 +802,9 @@ extern "C" int cniic_hist_delta_device(cniic_ctx *ctx, const uint8_t *d_rgb, uin
     size_t nbins = 0;
     int rc = cniic_dev_hist_delta_bins(ctx, d_rgb, w, h, &d_bins, &nbins);
     if (rc == CNIIC_OK) rc = cniic_dev_dense_compact(ctx, d_bins, nbins, &d_keys, &d_counts, out_n);
-    if (d_bins) cudaFree(d_bins);
-    if (d_keys) cudaFree(d_keys);
-    if (d_counts) cudaFree(d_counts);
+    cniic_cache_free(ctx, d_bins);
+    cniic_cache_free(ctx, d_keys);
+    cniic_cache_free(ctx, d_counts);
     return rc;
 }
 
@@ -823,19 +817,19 @@ extern "C" int cniic_hist_delta(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, 
     if (n == 0) return CNIIC_OK;
     if (!rgb) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    DevBuf din;
+    DevBuf din(ctx);
     CU_TRY(ctx, din.alloc(n * 3));
     CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
     uint32_t *d_bins = nullptr;
     size_t nbins = 0;
     int rc = cniic_dev_hist_delta_bins(ctx, din.as<uint8_t>(), w, h, &d_bins, &nbins);
     if (rc == CNIIC_OK) rc = hist_out(ctx, d_bins, nbins, out_keys, out_counts, cap, out_n);
-    if (d_bins) cudaFree(d_bins);
+    cniic_cache_free(ctx, d_bins);
     return rc;
 }
 
 int cniic_dev_sse(cniic_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, size_t nbytes, uint64_t *out) {
-    DevBuf acc;
+    DevBuf acc(ctx);
     CU_TRY(ctx, acc.alloc(8));
     CU_TRY(ctx, cudaMemsetAsync(acc.p, 0, 8, ctx->stream));
     if (nbytes) {
@@ -851,7 +845,7 @@ int cniic_dev_sse(cniic_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, size_t
 extern "C" int cniic_sse_rgb(cniic_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n_pixels, uint64_t *out_sse) {
     if (!ctx || !out_sse || ((!a || !b) && n_pixels)) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    DevBuf da, db;
+    DevBuf da(ctx), db(ctx);
     CU_TRY(ctx, da.alloc(n_pixels * 3));
     CU_TRY(ctx, db.alloc(n_pixels * 3));
     CU_TRY(ctx, cudaMemcpyAsync(da.p, a, n_pixels * 3, cudaMemcpyHostToDevice, ctx->stream));

@@ -58,16 +58,42 @@ def test_kmeans_rgb_heavy_weights_need_u64(ctx):
     same_kmeans(g, o)
 
 
-def test_kmeans_rgb_empty_clusters_are_repaired_deterministically(ctx):  # kmeans.rs:117-134 stand-in
-    rng = np.random.default_rng(3)
-    palette = rng.integers(0, 256, size=(6, 3), dtype=np.uint8)
-    pts = palette[rng.integers(0, 6, size=5000)]
+def _palette_points(seed):
+    rng = np.random.default_rng(seed)
+    npal, k, n = int(rng.integers(3, 10)), int(rng.integers(4, 16)), int(rng.integers(40, 400))
+    palette = rng.integers(0, 256, size=(npal, 3), dtype=np.uint8)
+    pts = palette[rng.integers(0, npal, size=n)]
+    jit = rng.integers(-3, 4, size=pts.shape)
+    mask = rng.random(n) < 0.3
+    return np.clip(pts.astype(int) + jit * mask[:, None], 0, 255).astype(np.uint8), k
+
+
+@pytest.mark.parametrize("seed", [0, 3, 4, 9, 12, 18, 34, 46, 52, 58])
+def test_kmeans_rgb_empty_clusters_are_repaired_deterministically(ctx, seed):  # kmeans.rs:117-134 stand-in
+    pts, k = _palette_points(seed)
+    events = 0
     for tie in (cb.TIE_KEEP_CURRENT, cb.TIE_LOWEST_INDEX):
-        g = ctx.kmeans_rgb(pts, 12, max_iters=6, tie=tie, allow_inactive=True)
-        o = O.kmeans_rgb(pts, 12, mode=O.MODE_EXACT, tie=tie, max_iters=6, allow_inactive=True)
-        assert o.empty_events > 0
+        g = ctx.kmeans_rgb(pts, k, max_iters=8, tie=tie, allow_inactive=True)
+        o = O.kmeans_rgb(pts, k, mode=O.MODE_EXACT, tie=tie, max_iters=8, allow_inactive=True)
+        events += o.empty_events
         same_kmeans(g, o)
-        assert g.status == o.status  # kmeans.rs:41-57 too-few-active check
+        assert g.status == o.status  # kmeans.rs:41-57 too-few-active check (seed 9 trips it)
+    assert events > 0
+
+
+@pytest.mark.parametrize("seed", [0, 1, 7, 10, 14, 15, 16, 19])
+def test_kmeans_xyrgb_empty_clusters(ctx, seed):  # kmeans.rs:117-134 stand-in on the (x,y,r,g,b) path
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(4, 24)), int(rng.integers(3, 16))
+    k = int(rng.integers(2, max(3, w * h // 2)))
+    img = (rng.integers(0, 3, size=(h, w, 3)) * 100).astype(np.uint8)
+    events = 0
+    for tie in (cb.TIE_KEEP_CURRENT, cb.TIE_LOWEST_INDEX):
+        g = ctx.kmeans_xyrgb(img, k, max_iters=8, tie=tie, allow_inactive=True)
+        o = O.kmeans_xyrgb(img, k, mode=O.MODE_EXACT, tie=tie, max_iters=8, allow_inactive=True)
+        same_kmeans(g, o)
+        events += o.empty_events
+    assert events > 0
 
 
 def test_kmeans_errors(ctx):
