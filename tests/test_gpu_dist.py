@@ -1,0 +1,66 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the row-sharded Lloyd loop with the in-library NCCL all-reduce
+must reproduce the single-GPU result bit for bit."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["CNIIC_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+import cniic_b200 as cb
+from cniic_b200 import dist as cdist
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+ctx = cdist.make_context(lr)
+out = {}
+for kind, w, h, k in ((cb.POINTS_XYRGB, 640, 363, 128), (cb.POINTS_RGB, 512, 301, 64)):
+    full = cb.synth_image_host(w, h, 123, 16)
+    D = 5 if kind == cb.POINTS_XYRGB else 3
+    y0, hl = cdist.row_shard(h, world, rank)
+    local = np.ascontiguousarray(full[y0:y0 + hl])
+    init = cdist.gather_init_centroids(D, local, w, y0 if D == 5 else y0 * w, w * h, k, device=torch.device("cuda", lr))
+    s = cb.KMeansSession(ctx, kind, k, local, w * hl, n_total=w * h, first_index=y0 * w, w=w, h_local=hl, y0=y0)
+    s.reset(init)
+    st = s.run(6)
+    cen, wts, asg = s.get()
+    s.close()
+    out[f"cen{D}"], out[f"wts{D}"], out[f"asg{D}"], out[f"it{D}"] = cen, wts, asg, np.array([st.iterations, st.moved_last])
+np.savez(os.path.join(os.environ["CNIIC_OUT"], f"rank{rank}.npz"), **out)
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_row_sharded_kmeans_matches_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import cniic_b200 as cb
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, CNIIC_ROOT=ROOT, CNIIC_OUT=str(tmp_path))
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                           "127.0.0.1", "--master-port", str(port), str(script)], env=env, timeout=600)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    ctx = cb.Context(0)
+    for kind, w, h, k, D in ((cb.POINTS_XYRGB, 640, 363, 128, 5), (cb.POINTS_RGB, 512, 301, 64, 3)):
+        full = cb.synth_image_host(w, h, 123, 16)
+        g = ctx.kmeans_xyrgb(full, k, max_iters=6) if D == 5 else ctx.kmeans_rgb(full, k, max_iters=6)
+        assert np.array_equal(r0[f"cen{D}"], r1[f"cen{D}"])  # identical on every rank without a broadcast
+        assert np.array_equal(r0[f"cen{D}"], g.centroids)
+        assert np.array_equal(r0[f"wts{D}"], g.weights)
+        assert np.array_equal(np.concatenate([r0[f"asg{D}"], r1[f"asg{D}"]]), g.assign)
+        assert r0[f"it{D}"].tolist() == [g.iterations, g.moved_last]
