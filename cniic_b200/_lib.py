@@ -17,6 +17,7 @@ OK, ERR_BAD_ARG, ERR_TOO_FEW_POINTS, ERR_TOO_FEW_ACTIVE, ERR_CUDA, ERR_NCCL, ERR
     ERR_UNSUPPORTED = range(9)
 TIE_KEEP_CURRENT, TIE_LOWEST_INDEX = 0, 1
 POINTS_RGB, POINTS_XYRGB = 0, 1
+KMEANS_NO_CULL = 1
 MAX_K, MAX_DIM = 4096, 16384
 
 
@@ -29,7 +30,7 @@ class KMeansStats(C.Structure):
 class KMeansDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("k", C.c_uint32), ("tie_rule", C.c_int), ("n_local", C.c_uint64),
                 ("n_total", C.c_uint64), ("first_index", C.c_uint64), ("w", C.c_uint32), ("h_local", C.c_uint32),
-                ("y0", C.c_uint32), ("rgb", C.c_void_p), ("weights", C.c_void_p), ("points_on_device", C.c_int)]
+                ("y0", C.c_uint32), ("rgb", C.c_void_p), ("weights", C.c_void_p), ("points_on_device", C.c_int), ("flags", C.c_int)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -293,7 +293,7 @@ class KMeansSession:
 
     def __init__(self, ctx: Context, kind: int, k: int, rgb, n_local: int, n_total: int | None = None,
                  first_index: int = 0, w: int = 0, h_local: int = 0, y0: int = 0, weights=None,
-                 tie: int = L.TIE_KEEP_CURRENT, on_device: bool = False):
+                 tie: int = L.TIE_KEEP_CURRENT, on_device: bool = False, flags: int = 0):
         self.ctx = ctx
         self.k, self.D = k, (5 if kind == L.POINTS_XYRGB else 3)
         self.n_local = n_local
@@ -315,6 +315,7 @@ class KMeansSession:
                 self._keep.append(wa)
                 d.weights = wa.ctypes.data
         d.points_on_device = 1 if on_device else 0
+        d.flags = flags
         h = C.c_void_p()
         ctx.check(ctx._lib.cniic_kmeans_open(ctx.h, C.byref(d), C.byref(h)))
         self.h = h

@@ -18,6 +18,7 @@
 //   re-scoring the G entries of the winning group.
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -426,6 +427,249 @@ __global__ void __launch_bounds__(THREADS) km_assign_xyrgb(KmDev d) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// D = 5 fused assign + accumulate with EXACT tile culling (default for the voronoi path)
+//   tile = 64 x 32 pixels per CTA; warp = 4 rows, lane = 8 consecutive pixels.
+//   For the tile's position rectangle and colour bounding box:  UB_c = max over the box of |p - c|^2,
+//   LB_c = min over the box.  U = min_c UB_c bounds every pixel's minimum distance, so a centroid with LB_c > U can
+//   neither win nor tie for any pixel of the tile.  Survivors are compacted in table order (parity class, then
+//   index) into a per-tile table, and only those are scanned.  Results are identical to the brute-force kernel.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TW = 64, TH = 32;  // tile size (pixels)
+constexpr int GT = 8;            // group size of the per-tile table
+
+__device__ __forceinline__ uint32_t block_rank256(bool flag, uint32_t *s_warp, uint32_t *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t v = s_warp[i];
+        if (i < warp) before += v;
+        tot += v;
+    }
+    *total = tot;
+    return before + __popc(bal & ((1u << lane) - 1));
+}
+
+__device__ __forceinline__ int sq(int v) { return v * v; }
+
+__global__ void __launch_bounds__(THREADS) km_assign_xyrgb_cull(KmDev d) {
+    if (d.st->done) return;
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t k = d.k;
+    const uint32_t KP = kpad_of(k, G5);
+    const uint32_t KT = kpad_of(k, GT);
+    uint32_t *s_cpk = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *s_cxy = s_cpk + KP;
+    int *s_bias0 = reinterpret_cast<int *>(s_cxy + KP);
+    uint32_t *t_cpk = reinterpret_cast<uint32_t *>(s_bias0 + KP);
+    uint32_t *t_cxy = t_cpk + KT;
+    int *t_bias = reinterpret_cast<int *>(t_cxy + KT);
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(t_bias + KT);  // 6*k u32
+    uint16_t *s_id = reinterpret_cast<uint16_t *>(s_acc + 6 * k);
+    uint16_t *s_pos = s_id + KP;
+    uint16_t *t_id = s_pos + ((k + 7) & ~7u);
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_box[8];  // min r,g,b ; max r,g,b ; U
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_static = d.st->ngroups * G5, n_static0 = d.st->ng0 * G5;
+    for (uint32_t i = tid; i < KP; i += THREADS) {
+        s_cpk[i] = d.t_cpk[i];
+        s_cxy[i] = d.t_cxy[i];
+        s_bias0[i] = d.t_bias[i];
+        s_id[i] = d.t_id[i];
+    }
+    for (uint32_t i = tid; i < k; i += THREADS) s_pos[i] = d.t_pos[i];
+    for (uint32_t i = tid; i < 6 * k; i += THREADS) s_acc[i] = 0u;
+
+    const uint32_t w = d.w, hl = d.h_local;
+    const uint32_t tiles_x = (w + TW - 1) / TW, tiles_y = (hl + TH - 1) / TH;
+    const unsigned long long tiles = (unsigned long long)tiles_x * tiles_y;
+    const bool fast_ok = (w % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.rgb) & 7) == 0);
+    unsigned long long moved = 0;
+    uint32_t since_flush = 0;
+
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t ty = uint32_t(tile / tiles_x), tx = uint32_t(tile % tiles_x);
+        const int x0 = tx * TW, yl0 = ty * TH;
+        const int vw = min(TW, int(w) - x0), vh = min(TH, int(hl) - yl0);
+        const int yg0 = d.y0 + yl0;
+        // ---- this lane's 8 pixels ----
+        const int row = warp * 4 + (lane >> 3), xr0 = (lane & 7) * 8;
+        const int yl = yl0 + row;
+        int nv = 0;
+        if (row < vh && xr0 < vw) nv = min(PX, vw - xr0);
+        const unsigned long long lbase = (unsigned long long)yl * w + x0 + xr0;
+        uint32_t px[PX];
+        if (nv == PX && fast_ok) {
+            const uint2 *p = reinterpret_cast<const uint2 *>(d.rgb + lbase * 3);
+            const uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+            const uint32_t wd[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+            unpack8(wd, px);
+        } else {
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                px[p] = 0;
+                if (p < nv) {
+                    const uint8_t *q = d.rgb + (lbase + p) * 3;
+                    px[p] = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+                }
+            }
+        }
+        // ---- colour bounding box of the tile (bytewise SIMD min/max, then warp + block reduce) ----
+        uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+        for (int p = 0; p < PX; p++)
+            if (p < nv) { mn = __vminu4(mn, px[p]); mx = __vmaxu4(mx, px[p]); }
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = __vmaxu4(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        __syncthreads();  // previous tile is done with s_box / tile table
+        if (tid < 3) { s_box[tid] = 255u; s_box[3 + tid] = 0u; }
+        if (tid == 3) s_box[6] = 0xffffffffu;
+        __syncthreads();
+        if (lane < 3) {
+            atomicMin(&s_box[lane], (mn >> (8 * lane)) & 0xff);
+            atomicMax(&s_box[3 + lane], (mx >> (8 * lane)) & 0xff);
+        }
+        __syncthreads();
+        const int bx0 = x0, bx1 = x0 + vw - 1, by0 = yg0, by1 = yg0 + vh - 1;
+        const int r0 = s_box[0], g0 = s_box[1], b0 = s_box[2], r1 = s_box[3], g1 = s_box[4], b1 = s_box[5];
+        // ---- pass 1: U = min_c UB_c ----
+        uint32_t umin = 0xffffffffu;
+        for (uint32_t e = tid; e < n_static; e += THREADS) {
+            if (s_bias0[e] == DUMMY5) continue;
+            const uint32_t cxy = s_cxy[e], cp = s_cpk[e];
+            const int cx = cxy & 0xffff, cy = cxy >> 16, cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
+            const uint32_t ub = sq(max(abs(cx - bx0), abs(cx - bx1))) + sq(max(abs(cy - by0), abs(cy - by1))) +
+                                sq(max(abs(cr - r0), abs(cr - r1))) + sq(max(abs(cg - g0), abs(cg - g1))) + sq(max(abs(cb - b0), abs(cb - b1)));
+            umin = min(umin, ub);
+        }
+        for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+        if (lane == 0) atomicMin(&s_box[6], umin);
+        __syncthreads();
+        const uint32_t U = s_box[6];
+        // ---- pass 2: compact the survivors of each parity class, in table order, into the tile table ----
+        uint32_t ntile0 = 0, ntile = 0;
+        for (int cls = 0; cls < 2; cls++) {
+            const uint32_t e_begin = cls == 0 ? 0 : n_static0, e_end = cls == 0 ? n_static0 : n_static;
+            uint32_t placed = ntile;
+            for (uint32_t eb = e_begin; eb < e_end; eb += THREADS) {
+                const uint32_t e = eb + tid;
+                bool keep = false;
+                uint32_t cxy = 0, cp = 0;
+                int bias = 0;
+                if (e < e_end && (bias = s_bias0[e]) != DUMMY5) {
+                    cxy = s_cxy[e]; cp = s_cpk[e];
+                    const int cx = cxy & 0xffff, cy = cxy >> 16, cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
+                    const uint32_t lb = sq(max(0, max(bx0 - cx, cx - bx1))) + sq(max(0, max(by0 - cy, cy - by1))) +
+                                        sq(max(0, max(r0 - cr, cr - r1))) + sq(max(0, max(g0 - cg, cg - g1))) + sq(max(0, max(b0 - cb, cb - b1)));
+                    keep = lb <= U;
+                }
+                uint32_t tot;
+                const uint32_t r = block_rank256(keep, s_warp, &tot);
+                if (keep) {
+                    const uint32_t t = placed + r;
+                    t_cpk[t] = cp; t_cxy[t] = cxy; t_id[t] = s_id[e];
+                    t_bias[t] = bias + x0 * int(cxy & 0xffff) + yg0 * int(cxy >> 16);
+                }
+                placed += tot;
+            }
+            const uint32_t padded = (placed + GT - 1) / GT * GT;
+            for (uint32_t t = placed + tid; t < padded; t += THREADS) { t_cpk[t] = 0; t_cxy[t] = 0; t_bias[t] = DUMMY5; t_id[t] = 0; }
+            ntile = padded;
+            if (cls == 0) ntile0 = padded;
+        }
+        __syncthreads();
+        const int ngroups = ntile / GT, ng0 = ntile0 / GT;
+
+        uint32_t pxy[PX];
+#pragma unroll
+        for (int p = 0; p < PX; p++) pxy[p] = uint32_t(xr0 + p) | (uint32_t(row) << 8);
+        int bestkey[PX], bestg[PX];
+#pragma unroll
+        for (int p = 0; p < PX; p++) { bestkey[p] = INT_MIN; bestg[p] = 0; }
+        for (int g = 0; g < ngroups; g++) {
+            const uint4 c0 = reinterpret_cast<const uint4 *>(t_cpk)[2 * g], c1 = reinterpret_cast<const uint4 *>(t_cpk)[2 * g + 1];
+            const uint4 q0 = reinterpret_cast<const uint4 *>(t_cxy)[2 * g], q1 = reinterpret_cast<const uint4 *>(t_cxy)[2 * g + 1];
+            const int4 b0v = reinterpret_cast<const int4 *>(t_bias)[2 * g], b1v = reinterpret_cast<const int4 *>(t_bias)[2 * g + 1];
+            const int par = g >= ng0;
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                int m = max(dp2a_lo_su(q0.x, pxy[p], dp4a_uu(px[p], c0.x, b0v.x)), dp2a_lo_su(q0.y, pxy[p], dp4a_uu(px[p], c0.y, b0v.y)));
+                m = max3i(m, dp2a_lo_su(q0.z, pxy[p], dp4a_uu(px[p], c0.z, b0v.z)), dp2a_lo_su(q0.w, pxy[p], dp4a_uu(px[p], c0.w, b0v.w)));
+                m = max3i(m, dp2a_lo_su(q1.x, pxy[p], dp4a_uu(px[p], c1.x, b1v.x)), dp2a_lo_su(q1.y, pxy[p], dp4a_uu(px[p], c1.y, b1v.y)));
+                m = max3i(m, dp2a_lo_su(q1.z, pxy[p], dp4a_uu(px[p], c1.z, b1v.z)), dp2a_lo_su(q1.w, pxy[p], dp4a_uu(px[p], c1.w, b1v.w)));
+                const int key = 2 * m - par;
+                if (key > bestkey[p]) { bestkey[p] = key; bestg[p] = g; }
+            }
+        }
+
+        int run = -1;
+        uint32_t ax = 0, ar = 0, ag = 0, ab = 0, an = 0;
+        const uint32_t yg = yg0 + row;
+#pragma unroll
+        for (int p = 0; p < PX; p++) {
+            if (p < nv) {
+                const int g = bestg[p];
+                const int par = g >= ng0;
+                int found = 0;
+#pragma unroll
+                for (int j = GT - 1; j >= 0; j--) {
+                    const int e = g * GT + j;
+                    const int sc = dp2a_lo_su(t_cxy[e], pxy[p], dp4a_uu(px[p], t_cpk[e], t_bias[e]));
+                    if (2 * sc - par == bestkey[p]) found = t_id[e];
+                }
+                const uint16_t prev = d.assign[lbase + p];
+                if (d.tie == CNIIC_TIE_KEEP_CURRENT) {
+                    // the current cluster may have been culled; then it is strictly farther than the winner (LB > U)
+                    const int e = s_pos[prev];
+                    const uint32_t cxy = s_cxy[e];
+                    const int bias = s_bias0[e] + x0 * int(cxy & 0xffff) + yg0 * int(cxy >> 16);
+                    const int sc = dp2a_lo_su(cxy, pxy[p], dp4a_uu(px[p], s_cpk[e], bias));
+                    if (2 * sc - (uint32_t(e) >= n_static0) == bestkey[p]) found = prev;
+                }
+                if (found != prev) { moved++; d.assign[lbase + p] = (uint16_t)found; }
+                if (found != run) {
+                    if (run >= 0) {
+                        atomicAdd(&s_acc[6 * run], ax); atomicAdd(&s_acc[6 * run + 1], an * yg);
+                        atomicAdd(&s_acc[6 * run + 2], ar); atomicAdd(&s_acc[6 * run + 3], ag);
+                        atomicAdd(&s_acc[6 * run + 4], ab); atomicAdd(&s_acc[6 * run + 5], an);
+                    }
+                    run = found; ax = ar = ag = ab = an = 0;
+                }
+                ax += x0 + xr0 + p; ar += px[p] & 0xff; ag += (px[p] >> 8) & 0xff; ab += (px[p] >> 16) & 0xff; an += 1;
+            }
+        }
+        if (run >= 0) {
+            atomicAdd(&s_acc[6 * run], ax); atomicAdd(&s_acc[6 * run + 1], an * yg);
+            atomicAdd(&s_acc[6 * run + 2], ar); atomicAdd(&s_acc[6 * run + 3], ag);
+            atomicAdd(&s_acc[6 * run + 4], ab); atomicAdd(&s_acc[6 * run + 5], an);
+        }
+        if (++since_flush == FLUSH_TILES) {
+            __syncthreads();
+            for (uint32_t i = tid; i < 6 * k; i += THREADS) {
+                const uint32_t v = s_acc[i];
+                if (v) { atomicAdd(&d.sums[i], (unsigned long long)v); s_acc[i] = 0; }
+            }
+            since_flush = 0;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < 6 * k; i += THREADS) {
+        const uint32_t v = s_acc[i];
+        if (v) atomicAdd(&d.sums[i], (unsigned long long)v);
+    }
+    for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
+    if (lane == 0 && moved) atomicAdd(&d.sums[6 * k], moved);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // init + finalize (single CTA)
 // ------------------------------------------------------------------------------------------------------------
 
@@ -623,12 +867,14 @@ struct cniic_kmeans {
     static constexpr int PROF = 32;  // assign launches timed per run (CUDA events on the launching stream)
     cudaEvent_t pev[2 * PROF] = {};
     uint32_t launches = 0;
+    bool cull = true;        // D = 5: exact tile culling (CNIIC_KMEANS_NO_CULL in desc.flags selects brute force)
     uint32_t iter_seen = 0;  // state.iter at the end of the previous run (0 after reset)
 };
 
 static int km_launch_assign(cniic_kmeans *km) {
     cniic_ctx *ctx = km->ctx;
-    if (km->D == 5) km_assign_xyrgb<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    if (km->D == 5 && km->cull) km_assign_xyrgb_cull<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    else if (km->D == 5) km_assign_xyrgb<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     else if (km->dev.wts) km_assign_rgb<true><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     else km_assign_rgb<false><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     km->launches++;
@@ -733,7 +979,12 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     dv.st = reinterpret_cast<KmState *>(p + o_st);
 
     // shared memory + persistent grid
-    if (D == 5) {
+    km->cull = !(desc->flags & CNIIC_KMEANS_NO_CULL) && !getenv("CNIIC_NO_CULL");
+    if (D == 5 && km->cull) {
+        const uint32_t KT = kpad_of(k, GT);
+        km->smem = size_t(KP) * 12 + size_t(KT) * 12 + size_t(k) * 24 + KP * 2 + ((k + 7) & ~7u) * 2 + KT * 2 + 16;
+        KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb_cull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+    } else if (D == 5) {
         km->smem = size_t(KP) * 16 + 8 * 192 * 4 + size_t(k) * 24 + KP * 2 + k * 2 + 16;
         KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     } else {
@@ -742,11 +993,13 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
         else KM_TRY(cudaFuncSetAttribute(km_assign_rgb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     }
     int per_sm = 0;
-    if (D == 5) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb, THREADS, km->smem));
+    if (D == 5 && km->cull) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull, THREADS, km->smem));
+    else if (D == 5) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb, THREADS, km->smem));
     else if (d_wts) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb<true>, THREADS, km->smem));
     else KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb<false>, THREADS, km->smem));
     if (per_sm < 1) return fail(cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "k = %u needs %zu bytes of shared memory", k, km->smem));
-    unsigned long long tiles = D == 5 ? (unsigned long long)((desc->w + 255) / 256) * ((desc->h_local + 7) / 8)
+    unsigned long long tiles = D == 5 ? (km->cull ? (unsigned long long)((desc->w + TW - 1) / TW) * ((desc->h_local + TH - 1) / TH)
+                                                  : (unsigned long long)((desc->w + 255) / 256) * ((desc->h_local + 7) / 8))
                                       : (desc->n_local + TILE - 1) / TILE;
     km->grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(tiles, (unsigned long long)per_sm * ctx->sm_count));
     KM_TRY(cudaEventCreate(&km->ev0));

@@ -104,6 +104,7 @@ int cniic_kmeans_xyrgb(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t 
 /* Session form: points stay resident in HBM across calls (what bench.py's device-resident `value` times, and what
  * the row-sharded multi-GPU path uses).                                                                          */
 #define CNIIC_POINTS_RGB 0   /* D = 3, points = packed RGB8 bytes (3 B / point)                                  */
+#define CNIIC_KMEANS_NO_CULL 1 /* XYRGB: scan all k centroids for every pixel (brute force) instead of exact tile culling */
 #define CNIIC_POINTS_XYRGB 1 /* D = 5, points = pixels of a raster image (x, y synthesised from the index)       */
 
 typedef struct {
@@ -118,6 +119,7 @@ typedef struct {
     const uint8_t *rgb;      /* HOST (points_on_device == 0) or DEVICE pointer to 3*n_local bytes                */
     const uint32_t *weights; /* RGB only, nullable; same memory space as rgb                                     */
     int points_on_device;    /* 1: rgb/weights are device pointers that outlive the session (no copy is made)    */
+    int flags;               /* CNIIC_KMEANS_* bits                                                              */
 } cniic_kmeans_desc;
 
 int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, cniic_kmeans **out);

@@ -129,6 +129,19 @@ def test_kmeans_xyrgb_flat_image_has_exact_ties(ctx):
         same_kmeans(g, o)
 
 
+@pytest.mark.parametrize("w,h,k", [(257, 131, 64), (640, 360, 2048), (100, 70, 300)])
+def test_kmeans_xyrgb_brute_force_kernel(ctx, w, h, k):
+    """The non-culled D = 5 kernel (CNIIC_KMEANS_NO_CULL) is kept for roofline measurements; it must agree too."""
+    img = cb.synth_image_host(w, h, 5, max(4, k // 8))
+    s = cb.KMeansSession(ctx, cb.POINTS_XYRGB, k, img, w * h, w=w, h_local=h, flags=cb._lib.KMEANS_NO_CULL)
+    s.reset()
+    st = s.run(3)
+    cen, wts, asg = s.get()
+    s.close()
+    o = O.kmeans_xyrgb(img, k, mode=O.MODE_EXACT, max_iters=3)
+    assert st.iterations == 3 and np.array_equal(cen, o.centroids) and np.array_equal(asg, o.assign) and np.array_equal(wts, o.weights)
+
+
 def test_kmeans_session_reuse(ctx):
     img = cb.synth_image_host(128, 64, 8, 8)
     s = cb.KMeansSession(ctx, cb.POINTS_XYRGB, 32, img, 128 * 64, w=128, h_local=64)

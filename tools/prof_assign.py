@@ -9,7 +9,7 @@ kind, w, h, k, blobs = {"c2": (cb.POINTS_RGB, 4096, 4096, 256, 192), "c3": (cb.P
 ctx = cb.Context(0)
 d = ctx.device_alloc(w * h * 3)
 cb.synth_image_device(ctx, d, w, h, 0xC0FFEE + int(wl[1]), blobs)
-s = cb.KMeansSession(ctx, kind, k, d, w * h, w=w, h_local=h, on_device=True)
+s = cb.KMeansSession(ctx, kind, k, d, w * h, w=w, h_local=h, on_device=True, flags=int(os.environ.get('KM_FLAGS', '0')))
 s.reset()
 st = s.run(iters)
 print(wl, st.iterations, "iters", st.device_ms, "ms", w * h * st.iterations / st.device_ms / 1e3, "Mpx.iter/s; assign avg", st.assign_ms_avg, "ms")
