@@ -227,7 +227,7 @@ def main():
     sampler.start()
     launches0 = sctx.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    assign_ms, iters_run = [], 0
+    assign_ms, iters_run, pairs_per_launch = [], 0, 0.0
     t_wall0 = time.perf_counter()
     for i in range(K):
         flush.fill_(i & 0xff)           # evict the image from L2 between timed steps (untimed)
@@ -237,6 +237,7 @@ def main():
         ev[i][1].record(stream)
         assign_ms.append(st.assign_ms_avg)
         iters_run += st.iterations
+        pairs_per_launch = st.pairs_scored / max(1, st.iterations)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = sctx.launches - launches0
@@ -306,17 +307,32 @@ def main():
     # ---- roofline of the dominant kernel (fused assign+accumulate), measured live with CUDA events ----
     pk = peaks()
     a_ms = float(np.mean(assign_ms))
-    flops_per_launch = (2 * D + 1) * n_local * k            # D FMA + 1 compare per pixel-centroid pair
+    flops_alg = (2 * D + 1) * n_local * k                  # D FMA + 1 compare per pixel-centroid pair, all k centroids
+    flops_exec = (2 * D + 1) * pairs_per_launch             # pairs the kernel actually scored (== N*k unless tile culling is on)
     fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
-    achieved = flops_per_launch / (a_ms * 1e-3) / 1e12
+    achieved = flops_exec / (a_ms * 1e-3) / 1e12
     bytes_per_launch = 3 * n_local                          # RGB read once per iteration (assignments: +2 B r/w not counted)
-    roofline = {"bound": "fp32", "kernel": "km_assign_xyrgb" if D == 5 else "km_assign_rgb", "achieved": achieved,
+    kernel = "km_assign_rgb" if D == 3 else "km_assign_xyrgb_cull"
+    roofline = {"bound": "fp32", "kernel": kernel, "achieved": achieved,
                 "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
                 "peak_source": f"148 SM x 128 FP32 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']} sm_max_mhz); the kernel issues "
                                "IDP.4A/IDP.2A integer dot products, so frac > FFMA-issue ceilings is possible (DESIGN.md)",
-                "launch_ms": a_ms, "algorithmic_flops_per_launch": flops_per_launch,
+                "launch_ms": a_ms, "flops_per_launch_executed": flops_exec, "algorithmic_flops_per_launch": flops_alg,
+                "pairs_scored_frac_of_N_k": pairs_per_launch / (n_local * k),
+                "algorithmic_equiv_tflops": flops_alg / (a_ms * 1e-3) / 1e12,
                 "hbm": {"achieved": bytes_per_launch / (a_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": bytes_per_launch / (a_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "source": pk["source"]}}
+    if D == 5 and independent:
+        # the brute-force kernel (every pixel scores all k centroids) for reference: same results, no culling
+        sb = cb.KMeansSession(sctx, kind_id, k, d_img_s, n_local, w=w, h_local=h_local, on_device=True, flags=cb._lib.KMEANS_NO_CULL)
+        sb.reset()
+        sb.run(1)
+        sb.reset()
+        stb = sb.run(3)
+        sb.close()
+        ab = flops_alg / (stb.assign_ms_avg * 1e-3) / 1e12
+        roofline["brute_force_kernel"] = {"kernel": "km_assign_xyrgb", "launch_ms": stb.assign_ms_avg, "achieved": ab, "frac": ab / fp32_peak,
+                                          "Mpx_iter_per_s": n_local / (stb.assign_ms_avg * 1e-3) / 1e6}
 
     cpu = None
     if not args.no_cpu:
@@ -327,8 +343,9 @@ def main():
     line = {"metric": "Mpixel*iter/s Lloyd K-means", "value": value, "unit": "Mpx*iter/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
-            "config": {"workload": desc + (f", {world} slabs of {w}x{h} (row-sharded {w}x{h_total}, NCCL u64 partial-sum all-reduce)"
-                                           if world > 1 and not independent else ""),
+            "config": {"workload": desc + ((f", {world} slabs of {w}x{h} (row-sharded {w}x{h_total}" if scaling == "weak" else
+                                             f" (rows sharded over {world} GPUs") + ", NCCL u64 partial-sum all-reduce per iteration)"
+                                            if world > 1 and not independent else ""),
                        "k": k, "dims": D, "iters_per_step": ITERS, "pixels": int(px_total),
                        "parallelism": "1 GPU" if world == 1 else (f"{world} independent images" if independent else f"row-sharded x{world}"),
                        "l2": "512 MiB buffer written between timed steps (L2 flush); the image stays L2/HBM resident across the "

@@ -24,7 +24,7 @@ MAX_K, MAX_DIM = 4096, 16384
 class KMeansStats(C.Structure):
     _fields_ = [("iterations", C.c_uint32), ("empty_events", C.c_uint32), ("moved_last", C.c_uint64),
                 ("moved_total", C.c_uint64), ("converged", C.c_uint32), ("gpu_launches", C.c_uint32),
-                ("device_ms", C.c_float), ("assign_ms_avg", C.c_float)]
+                ("device_ms", C.c_float), ("assign_ms_avg", C.c_float), ("pairs_scored", C.c_uint64)]
 
 
 class KMeansDesc(C.Structure):

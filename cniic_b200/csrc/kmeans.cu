@@ -47,6 +47,7 @@ struct KmState {
     uint32_t dist_empty;  // an empty cluster occurred in a multi-GPU run (repair needs the host path)
     uint32_t pad;
     unsigned long long moved_last, moved_total;
+    unsigned long long pairs;  // point-centroid pairs actually scored by the assign kernels since reset
 };
 
 struct KmDev {
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(THREADS) km_assign_rgb(KmDev d) {
     }
     for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
     if ((tid & 31) == 0 && moved) atomicAdd(&d.sums[4 * k], moved);
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(&d.st->pairs, d.n_local * (unsigned long long)k);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -424,6 +426,7 @@ __global__ void __launch_bounds__(THREADS) km_assign_xyrgb(KmDev d) {
     }
     for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
     if (lane == 0 && moved) atomicAdd(&d.sums[6 * k], moved);
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(&d.st->pairs, d.n_local * (unsigned long long)k);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(THREADS) km_assign_xyrgb_cull(KmDev d) {
     const uint32_t tiles_x = (w + TW - 1) / TW, tiles_y = (hl + TH - 1) / TH;
     const unsigned long long tiles = (unsigned long long)tiles_x * tiles_y;
     const bool fast_ok = (w % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.rgb) & 7) == 0);
-    unsigned long long moved = 0;
+    unsigned long long moved = 0, pairs_local = 0;
     uint32_t since_flush = 0;
 
     for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -587,6 +590,7 @@ __global__ void __launch_bounds__(THREADS) km_assign_xyrgb_cull(KmDev d) {
         }
         __syncthreads();
         const int ngroups = ntile / GT, ng0 = ntile0 / GT;
+        if (tid == 0) pairs_local += (unsigned long long)ntile * vw * vh;
 
         uint32_t pxy[PX];
 #pragma unroll
@@ -667,6 +671,7 @@ __global__ void __launch_bounds__(THREADS) km_assign_xyrgb_cull(KmDev d) {
     }
     for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
     if (lane == 0 && moved) atomicAdd(&d.sums[6 * k], moved);
+    if (tid == 0 && pairs_local) atomicAdd(&d.st->pairs, pairs_local);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -834,7 +839,7 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
     if (tid == 0) {
         if (init_mode) {
             d.st->iter = 0; d.st->done = 0; d.st->empty_events = 0; d.st->n_empty_last = 0; d.st->dist_empty = 0;
-            d.st->moved_last = 0; d.st->moved_total = 0;
+            d.st->moved_last = 0; d.st->moved_total = 0; d.st->pairs = 0;
         } else {
             d.st->iter += 1;
             d.st->moved_last = moved;
@@ -1042,7 +1047,7 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
     CU_TRY(ctx, cudaEventRecord(km->ev0, ctx->stream));
     uint32_t issued = 0;
     for (;;) {
-        uint32_t batch = dist ? 1 : 4;
+        uint32_t batch = 4;  // kernels (and the all-reduce) early-exit / are harmless once `done` is set
         if (max_iters) batch = std::min(batch, max_iters - issued);
         for (uint32_t b = 0; b < batch; b++) {
             const bool prof = issued + b < (uint32_t)cniic_kmeans::PROF;
@@ -1081,6 +1086,7 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
             if (cudaEventElapsedTime(&t, km->pev[2 * i], km->pev[2 * i + 1]) == cudaSuccess) acc += t;
         }
         stats->assign_ms_avg = np ? acc / np : 0.f;
+        stats->pairs_scored = s.pairs;
     }
     km->iter_seen = s.iter;
     return CNIIC_OK;

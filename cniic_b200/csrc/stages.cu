@@ -340,6 +340,121 @@ __global__ void hilbert_stream_kernel(const uint8_t *__restrict__ rgb, uint32_t 
     }
 }
 
+// ---- fast path for 2^n x 2^n images (n >= 6): one CTA per 64x64 block = 4096 consecutive curve indices ----------
+// The classic index->(x,y) map builds coordinates from the LOW base-4 digits upward, and every higher level applies
+// the same swap / flip / translate to the partial result.  The 16 indices of one thread (a 4x4 cell) share all digits
+// above the lowest two, so the thread folds levels 2..L-1 once into an affine map  x = ax + sx*u, y = ay + sy*v
+// ((u,v) = the 4x4 pattern, possibly transposed) and applies it to the 16 pattern entries.  The block's pixels are
+// staged in shared memory with coalesced 128-bit row loads; outputs are 128-bit stores of 16 consecutive symbols.
+__constant__ uint8_t HIL4_X[16] = {0, 1, 1, 0, 0, 0, 1, 1, 2, 2, 3, 3, 3, 2, 2, 3};
+__constant__ uint8_t HIL4_Y[16] = {0, 0, 1, 1, 2, 3, 3, 2, 2, 3, 3, 2, 1, 1, 0, 0};
+
+constexpr int HT = 64;            // block side
+constexpr int HT_STRIDE = 208;    // bytes per staged row (192 + pad, multiple of 16)
+
+template <int MODE>
+__global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__restrict__ rgb, uint32_t n, uint8_t *out_rgb,
+                                                           int16_t *out_delta, uint32_t *bins) {
+    __shared__ __align__(16) uint8_t s_px[HT * HT_STRIDE];
+    __shared__ uint32_t s_last[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long B = (unsigned long long)blockIdx.x * 4096;
+    const unsigned long long i0 = B + (unsigned long long)tid * 16;
+    // fold levels 2..L-1 into (ax, sx, ay, sy, swapped)
+    int ax = 0, ay = 0, sx = 1, sy = 1;
+    bool swapped = false;
+    {
+        unsigned long long t = i0 >> 4;
+        for (uint32_t sft = 4; sft < n; sft <<= 1) {
+            const int sl = (int)sft;
+            const uint32_t rx = 1u & (uint32_t)(t >> 1), ry = 1u & ((uint32_t)t ^ rx);
+            if (ry == 0) {
+                if (rx == 1) {
+                    const int nax = sl - 1 - ay, nsx = -sy, nay = sl - 1 - ax, nsy = -sx;
+                    ax = nax; sx = nsx; ay = nay; sy = nsy;
+                } else {
+                    const int tx = ax, tsx = sx;
+                    ax = ay; sx = sy; ay = tx; sy = tsx;
+                }
+                swapped = !swapped;
+            }
+            ax += sl * (int)rx;
+            ay += sl * (int)ry;
+            t >>= 2;
+        }
+    }
+    const int u0 = swapped ? HIL4_Y[0] : HIL4_X[0], v0 = swapped ? HIL4_X[0] : HIL4_Y[0];
+    const int X0 = (ax + sx * u0) & ~(HT - 1), Y0 = (ay + sy * v0) & ~(HT - 1);
+    // stage the 64x64 block: 64 rows x 12 uint4
+    for (int idx = tid; idx < HT * 12; idx += 256) {
+        const int r = idx / 12, c = idx % 12;
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rgb + ((size_t)(Y0 + r) * n + X0) * 3) + c);
+        *reinterpret_cast<uint4 *>(s_px + r * HT_STRIDE + c * 16) = v;
+    }
+    __syncthreads();
+    uint32_t pix[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int u = swapped ? HIL4_Y[j] : HIL4_X[j], v = swapped ? HIL4_X[j] : HIL4_Y[j];
+        const int lx = (ax + sx * u) - X0, ly = (ay + sy * v) - Y0;
+        const uint8_t *q = s_px + ly * HT_STRIDE + lx * 3;
+        pix[j] = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+    }
+    if (MODE == 0) {
+        uint32_t wd[12];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {  // 4 pixels -> 3 words
+            const uint32_t a = pix[4 * q], b = pix[4 * q + 1], c = pix[4 * q + 2], e = pix[4 * q + 3];
+            wd[3 * q] = a | (b << 24);
+            wd[3 * q + 1] = (b >> 8) | (c << 16);
+            wd[3 * q + 2] = (c >> 16) | (e << 8);
+        }
+        uint4 *o = reinterpret_cast<uint4 *>(out_rgb + i0 * 3);
+        o[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        o[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+        o[2] = make_uint4(wd[8], wd[9], wd[10], wd[11]);
+        return;
+    }
+    // predecessor of this thread's first symbol
+    uint32_t prev = __shfl_up_sync(0xffffffffu, pix[15], 1);
+    if (lane == 31) s_last[warp] = pix[15];
+    __syncthreads();
+    if (lane == 0) {
+        if (warp > 0) prev = s_last[warp - 1];
+        else if (B == 0) prev = 0;  // hilbertc.rs:445 START = [0;3]
+        else {
+            uint32_t px, py;
+            hilbert_d2xy_pow2(n, B - 1, &px, &py);
+            const uint8_t *q = rgb + ((size_t)py * n + px) * 3;
+            prev = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+        }
+    }
+    if (MODE == 1) {
+        uint32_t wd[24];  // 48 i16 packed two per word
+        int16_t dl[48];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
+            dl[3 * j] = (int16_t)(int(c & 0xff) - int(p & 0xff));
+            dl[3 * j + 1] = (int16_t)(int((c >> 8) & 0xff) - int((p >> 8) & 0xff));
+            dl[3 * j + 2] = (int16_t)(int((c >> 16) & 0xff) - int((p >> 16) & 0xff));
+        }
+#pragma unroll
+        for (int q = 0; q < 24; q++) wd[q] = uint32_t(uint16_t(dl[2 * q])) | (uint32_t(uint16_t(dl[2 * q + 1])) << 16);
+        uint4 *o = reinterpret_cast<uint4 *>(out_delta + i0 * 3);
+#pragma unroll
+        for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
+            const int d0 = int(c & 0xff) - int(p & 0xff), d1 = int((c >> 8) & 0xff) - int((p >> 8) & 0xff),
+                      d2 = int((c >> 16) & 0xff) - int((p >> 16) & 0xff);
+            warp_hist_add(bins, uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255)), true);
+        }
+    }
+}
+
 // inverse: segmented prefix sum along the curve is sequential per channel; done as a 3-kernel scan over i16 diffs.
 // Values are bounded (reconstructed colours are 0..255) so int32 prefix sums are exact.
 __global__ void __launch_bounds__(256) undelta_partial_kernel(const int16_t *__restrict__ diff, unsigned long long n, int *block_sums) {
@@ -503,7 +618,17 @@ int cniic_dev_keys_to_points(cniic_ctx *ctx, const uint32_t *d_keys, const unsig
     return CNIIC_OK;
 }
 
+static inline bool tile_path(const void *in, const void *out, uint32_t w, uint32_t h) {
+    return w == h && (w & (w - 1)) == 0 && w >= 64 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+}
+
 int cniic_dev_hilbert_gather(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint8_t *d_out) {
+    if (tile_path(d_rgb, d_out, w, h)) {
+        hilbert_tile_kernel<0><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, d_out, nullptr, nullptr);
+        ctx->launches++;
+        CU_TRY(ctx, cudaGetLastError());
+        return CNIIC_OK;
+    }
     hilbert_stream_kernel<0><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), d_out, nullptr, nullptr);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
@@ -515,7 +640,8 @@ int cniic_dev_hist_delta_bins(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, 
     *d_bins = nullptr;
     if (!(*d_bins = static_cast<std::remove_reference<decltype(*d_bins)>::type>(cniic_cache_alloc(ctx, *nbins * 4)))) return CNIIC_ERR_CUDA;
     CU_TRY(ctx, cudaMemsetAsync(*d_bins, 0, *nbins * 4, ctx->stream));
-    hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins);
+    if (tile_path(d_rgb, nullptr, w, h)) hilbert_tile_kernel<2><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, nullptr, nullptr, *d_bins);
+    else hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
@@ -739,7 +865,8 @@ extern "C" int cniic_delta_i16_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint
     if ((size_t)w * h == 0) return CNIIC_OK;
     if (!d_rgb || !d_out) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    hilbert_stream_kernel<1><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, d_out, nullptr);
+    if (tile_path(d_rgb, d_out, w, h)) hilbert_tile_kernel<1><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, nullptr, d_out, nullptr);
+    else hilbert_stream_kernel<1><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, d_out, nullptr);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;

@@ -10,7 +10,7 @@ use std::ffi::{c_char, c_int, c_void, CStr, CString};
 #[derive(Default, Clone, Copy, Debug)]
 pub struct cniic_kmeans_stats {
     pub iterations: u32, pub empty_events: u32, pub moved_last: u64, pub moved_total: u64,
-    pub converged: u32, pub gpu_launches: u32, pub device_ms: f32, pub assign_ms_avg: f32,
+    pub converged: u32, pub gpu_launches: u32, pub device_ms: f32, pub assign_ms_avg: f32, pub pairs_scored: u64,
 }
 
 pub const CNIIC_OK: c_int = 0;
