@@ -64,6 +64,13 @@ struct KmDev {
     int *t_bias;
     uint16_t *t_id;
     uint16_t *t_pos;
+    // per-centroid arrays in id order + per-supertile candidate lists (culled D = 5 path)
+    uint32_t *g_cpk;
+    uint32_t *g_cxy;
+    uint32_t *g_nrm;
+    uint16_t *sc_list;   // [n_super][k] centroid ids, ascending
+    uint32_t *sc_count;  // [n_super]
+    uint32_t super_x, super_y;
     unsigned long long *sums;  // k*(D+1) partial sums + 1 moved counter
     int32_t *cen;              // k*D
     unsigned long long *weights;
@@ -430,15 +437,18 @@ __global__ void __launch_bounds__(THREADS) km_assign_xyrgb(KmDev d) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// D = 5 fused assign + accumulate with EXACT tile culling (default for the voronoi path)
-//   tile = 64 x 32 pixels per CTA; warp = 4 rows, lane = 8 consecutive pixels.
-//   For the tile's position rectangle and colour bounding box:  UB_c = max over the box of |p - c|^2,
-//   LB_c = min over the box.  U = min_c UB_c bounds every pixel's minimum distance, so a centroid with LB_c > U can
-//   neither win nor tie for any pixel of the tile.  Survivors are compacted in table order (parity class, then
-//   index) into a per-tile table, and only those are scanned.  Results are identical to the brute-force kernel.
+// D = 5 fused assign + accumulate with EXACT two-level culling (default for the voronoi path)
+//   For a box of points (position rectangle x colour box): UB_c = max over the box of |p - c|^2, LB_c = min over it.
+//   U = min_c UB_c bounds every point's minimum distance, so a centroid with LB_c > U can neither win nor tie.
+//   level 1  km_supercull : one CTA per 512x256 supertile, position-only bounds (colour box = full cube) -> ascending id list
+//   level 2  km_assign_xyrgb_cull : per 64x32 tile (CTA; warp = 4 rows, lane = 8 pixels) bounds with the tile's colour
+//            bounding box over the supertile's list; survivors (typically ~10 of 2048) are scored directly:
+//            key = 2*(p.c) - |c|^2  (exact integer order of -|p-c|^2), strict ">" in ascending id order = lowest index.
+//   Results are identical to the brute-force kernel.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int TW = 64, TH = 32;  // tile size (pixels)
-constexpr int GT = 8;            // group size of the per-tile table
+constexpr int TW = 64, TH = 32;    // tile
+constexpr int SW = 512, SH = 256;  // supertile = 8 x 8 tiles
+constexpr int TCAP = 256;          // survivors scored per round
 
 __device__ __forceinline__ uint32_t block_rank256(bool flag, uint32_t *s_warp, uint32_t *total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -459,34 +469,54 @@ __device__ __forceinline__ uint32_t block_rank256(bool flag, uint32_t *s_warp, u
 
 __device__ __forceinline__ int sq(int v) { return v * v; }
 
-__global__ void __launch_bounds__(THREADS) km_assign_xyrgb_cull(KmDev d) {
+__global__ void __launch_bounds__(THREADS) km_supercull(KmDev d) {
+    if (d.st->done) return;
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_U;
+    const int tid = threadIdx.x;
+    const uint32_t k = d.k, sup = blockIdx.x;
+    const int x0 = (sup % d.super_x) * SW, yl0 = (sup / d.super_x) * SH;
+    const int x1 = min(x0 + SW, (int)d.w) - 1, y0 = d.y0 + yl0, y1 = d.y0 + min(yl0 + SH, (int)d.h_local) - 1;
+    if (tid == 0) s_U = 0xffffffffu;
+    __syncthreads();
+    uint32_t umin = 0xffffffffu;
+    for (uint32_t c = tid; c < k; c += THREADS) {
+        const uint32_t cxy = d.g_cxy[c];
+        const int cx = cxy & 0xffff, cy = cxy >> 16;
+        umin = min(umin, uint32_t(sq(max(abs(cx - x0), abs(cx - x1))) + sq(max(abs(cy - y0), abs(cy - y1)))));
+    }
+    for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+    if ((tid & 31) == 0) atomicMin(&s_U, umin);
+    __syncthreads();
+    const uint32_t U = s_U + 3u * 255u * 255u;  // colour part of UB for the full colour cube
+    uint16_t *list = d.sc_list + (size_t)sup * k;
+    uint32_t placed = 0;
+    for (uint32_t cb = 0; cb < k; cb += THREADS) {
+        const uint32_t c = cb + tid;
+        bool keep = false;
+        if (c < k) {
+            const uint32_t cxy = d.g_cxy[c];
+            const int cx = cxy & 0xffff, cy = cxy >> 16;
+            keep = uint32_t(sq(max(0, max(x0 - cx, cx - x1))) + sq(max(0, max(y0 - cy, cy - y1)))) <= U;
+        }
+        uint32_t tot;
+        const uint32_t r = block_rank256(keep, s_warp, &tot);
+        if (keep) list[placed + r] = (uint16_t)c;
+        placed += tot;
+    }
+    if (tid == 0) d.sc_count[sup] = placed;
+}
+
+__global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull(KmDev d) {
     if (d.st->done) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
-    const uint32_t KP = kpad_of(k, G5);
-    const uint32_t KT = kpad_of(k, GT);
-    uint32_t *s_cpk = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t *s_cxy = s_cpk + KP;
-    int *s_bias0 = reinterpret_cast<int *>(s_cxy + KP);
-    uint32_t *t_cpk = reinterpret_cast<uint32_t *>(s_bias0 + KP);
-    uint32_t *t_cxy = t_cpk + KT;
-    int *t_bias = reinterpret_cast<int *>(t_cxy + KT);
-    uint32_t *s_acc = reinterpret_cast<uint32_t *>(t_bias + KT);  // 6*k u32
-    uint16_t *s_id = reinterpret_cast<uint16_t *>(s_acc + 6 * k);
-    uint16_t *s_pos = s_id + KP;
-    uint16_t *t_id = s_pos + ((k + 7) & ~7u);
+    uint4 *t_ent = smem_raw;                                              // TCAP x {cpk, cxy, kb, id}
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(t_ent + TCAP);         // 6*k u32
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_box[8];  // min r,g,b ; max r,g,b ; U
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n_static = d.st->ngroups * G5, n_static0 = d.st->ng0 * G5;
-    for (uint32_t i = tid; i < KP; i += THREADS) {
-        s_cpk[i] = d.t_cpk[i];
-        s_cxy[i] = d.t_cxy[i];
-        s_bias0[i] = d.t_bias[i];
-        s_id[i] = d.t_id[i];
-    }
-    for (uint32_t i = tid; i < k; i += THREADS) s_pos[i] = d.t_pos[i];
     for (uint32_t i = tid; i < 6 * k; i += THREADS) s_acc[i] = 0u;
 
     const uint32_t w = d.w, hl = d.h_local;
@@ -532,7 +562,7 @@ __global__ void __launch_bounds__(THREADS) km_assign_xyrgb_cull(KmDev d) {
             mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, o));
             mx = __vmaxu4(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         }
-        __syncthreads();  // previous tile is done with s_box / tile table
+        __syncthreads();  // previous tile is done with s_box / t_ent
         if (tid < 3) { s_box[tid] = 255u; s_box[3 + tid] = 0u; }
         if (tid == 3) s_box[6] = 0xffffffffu;
         __syncthreads();
@@ -543,11 +573,14 @@ __global__ void __launch_bounds__(THREADS) km_assign_xyrgb_cull(KmDev d) {
         __syncthreads();
         const int bx0 = x0, bx1 = x0 + vw - 1, by0 = yg0, by1 = yg0 + vh - 1;
         const int r0 = s_box[0], g0 = s_box[1], b0 = s_box[2], r1 = s_box[3], g1 = s_box[4], b1 = s_box[5];
-        // ---- pass 1: U = min_c UB_c ----
+        const uint32_t sup = (ty / (SH / TH)) * d.super_x + tx / (SW / TW);
+        const uint32_t m = d.sc_count[sup];
+        const uint16_t *list = d.sc_list + (size_t)sup * k;
+        // ---- pass 1: U = min_c UB_c over the supertile's list ----
         uint32_t umin = 0xffffffffu;
-        for (uint32_t e = tid; e < n_static; e += THREADS) {
-            if (s_bias0[e] == DUMMY5) continue;
-            const uint32_t cxy = s_cxy[e], cp = s_cpk[e];
+        for (uint32_t j = tid; j < m; j += THREADS) {
+            const uint32_t id = list[j];
+            const uint32_t cxy = d.g_cxy[id], cp = d.g_cpk[id];
             const int cx = cxy & 0xffff, cy = cxy >> 16, cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
             const uint32_t ub = sq(max(abs(cx - bx0), abs(cx - bx1))) + sq(max(abs(cy - by0), abs(cy - by1))) +
                                 sq(max(abs(cr - r0), abs(cr - r1))) + sq(max(abs(cg - g0), abs(cg - g1))) + sq(max(abs(cb - b0), abs(cb - b1)));
@@ -557,61 +590,41 @@ __global__ void __launch_bounds__(THREADS) km_assign_xyrgb_cull(KmDev d) {
         if (lane == 0) atomicMin(&s_box[6], umin);
         __syncthreads();
         const uint32_t U = s_box[6];
-        // ---- pass 2: compact the survivors of each parity class, in table order, into the tile table ----
-        uint32_t ntile0 = 0, ntile = 0;
-        for (int cls = 0; cls < 2; cls++) {
-            const uint32_t e_begin = cls == 0 ? 0 : n_static0, e_end = cls == 0 ? n_static0 : n_static;
-            uint32_t placed = ntile;
-            for (uint32_t eb = e_begin; eb < e_end; eb += THREADS) {
-                const uint32_t e = eb + tid;
-                bool keep = false;
-                uint32_t cxy = 0, cp = 0;
-                int bias = 0;
-                if (e < e_end && (bias = s_bias0[e]) != DUMMY5) {
-                    cxy = s_cxy[e]; cp = s_cpk[e];
-                    const int cx = cxy & 0xffff, cy = cxy >> 16, cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
-                    const uint32_t lb = sq(max(0, max(bx0 - cx, cx - bx1))) + sq(max(0, max(by0 - cy, cy - by1))) +
-                                        sq(max(0, max(r0 - cr, cr - r1))) + sq(max(0, max(g0 - cg, cg - g1))) + sq(max(0, max(b0 - cb, cb - b1)));
-                    keep = lb <= U;
-                }
-                uint32_t tot;
-                const uint32_t r = block_rank256(keep, s_warp, &tot);
-                if (keep) {
-                    const uint32_t t = placed + r;
-                    t_cpk[t] = cp; t_cxy[t] = cxy; t_id[t] = s_id[e];
-                    t_bias[t] = bias + x0 * int(cxy & 0xffff) + yg0 * int(cxy >> 16);
-                }
-                placed += tot;
-            }
-            const uint32_t padded = (placed + GT - 1) / GT * GT;
-            for (uint32_t t = placed + tid; t < padded; t += THREADS) { t_cpk[t] = 0; t_cxy[t] = 0; t_bias[t] = DUMMY5; t_id[t] = 0; }
-            ntile = padded;
-            if (cls == 0) ntile0 = padded;
-        }
-        __syncthreads();
-        const int ngroups = ntile / GT, ng0 = ntile0 / GT;
-        if (tid == 0) pairs_local += (unsigned long long)ntile * vw * vh;
 
         uint32_t pxy[PX];
 #pragma unroll
         for (int p = 0; p < PX; p++) pxy[p] = uint32_t(xr0 + p) | (uint32_t(row) << 8);
-        int bestkey[PX], bestg[PX];
+        int best[PX], bi[PX];
 #pragma unroll
-        for (int p = 0; p < PX; p++) { bestkey[p] = INT_MIN; bestg[p] = 0; }
-        for (int g = 0; g < ngroups; g++) {
-            const uint4 c0 = reinterpret_cast<const uint4 *>(t_cpk)[2 * g], c1 = reinterpret_cast<const uint4 *>(t_cpk)[2 * g + 1];
-            const uint4 q0 = reinterpret_cast<const uint4 *>(t_cxy)[2 * g], q1 = reinterpret_cast<const uint4 *>(t_cxy)[2 * g + 1];
-            const int4 b0v = reinterpret_cast<const int4 *>(t_bias)[2 * g], b1v = reinterpret_cast<const int4 *>(t_bias)[2 * g + 1];
-            const int par = g >= ng0;
-#pragma unroll
-            for (int p = 0; p < PX; p++) {
-                int m = max(dp2a_lo_su(q0.x, pxy[p], dp4a_uu(px[p], c0.x, b0v.x)), dp2a_lo_su(q0.y, pxy[p], dp4a_uu(px[p], c0.y, b0v.y)));
-                m = max3i(m, dp2a_lo_su(q0.z, pxy[p], dp4a_uu(px[p], c0.z, b0v.z)), dp2a_lo_su(q0.w, pxy[p], dp4a_uu(px[p], c0.w, b0v.w)));
-                m = max3i(m, dp2a_lo_su(q1.x, pxy[p], dp4a_uu(px[p], c1.x, b1v.x)), dp2a_lo_su(q1.y, pxy[p], dp4a_uu(px[p], c1.y, b1v.y)));
-                m = max3i(m, dp2a_lo_su(q1.z, pxy[p], dp4a_uu(px[p], c1.z, b1v.z)), dp2a_lo_su(q1.w, pxy[p], dp4a_uu(px[p], c1.w, b1v.w)));
-                const int key = 2 * m - par;
-                if (key > bestkey[p]) { bestkey[p] = key; bestg[p] = g; }
+        for (int p = 0; p < PX; p++) { best[p] = INT_MIN; bi[p] = 0; }
+        // ---- pass 2 + scoring, TCAP candidates of the list per round (one round in the common case) ----
+        for (uint32_t base = 0; base < m; base += TCAP) {
+            const uint32_t j = base + tid;
+            bool keep = false;
+            uint4 ent = make_uint4(0, 0, 0, 0);
+            if (j < m) {
+                const uint32_t id = list[j];
+                const uint32_t cxy = d.g_cxy[id], cp = d.g_cpk[id];
+                const int cx = cxy & 0xffff, cy = cxy >> 16, cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
+                const uint32_t lb = sq(max(0, max(bx0 - cx, cx - bx1))) + sq(max(0, max(by0 - cy, cy - by1))) +
+                                    sq(max(0, max(r0 - cr, cr - r1))) + sq(max(0, max(g0 - cg, cg - g1))) + sq(max(0, max(b0 - cb, cb - b1)));
+                keep = lb <= U;
+                ent = make_uint4(cp, cxy, uint32_t(2 * (x0 * cx + yg0 * cy) - int(d.g_nrm[id])), id);
             }
+            uint32_t nt;
+            const uint32_t r = block_rank256(keep, s_warp, &nt);
+            if (keep) t_ent[r] = ent;
+            __syncthreads();
+            if (tid == 0) pairs_local += (unsigned long long)nt * vw * vh;
+            for (uint32_t e = 0; e < nt; e++) {
+                const uint4 c = t_ent[e];
+#pragma unroll
+                for (int p = 0; p < PX; p++) {
+                    const int key = 2 * dp2a_lo_su(c.y, pxy[p], dp4a_uu(px[p], c.x, 0)) + int(c.z);
+                    if (key > best[p]) { best[p] = key; bi[p] = int(c.w); }
+                }
+            }
+            if (base + TCAP < m) __syncthreads();  // next round overwrites t_ent
         }
 
         int run = -1;
@@ -620,23 +633,13 @@ __global__ void __launch_bounds__(THREADS) km_assign_xyrgb_cull(KmDev d) {
 #pragma unroll
         for (int p = 0; p < PX; p++) {
             if (p < nv) {
-                const int g = bestg[p];
-                const int par = g >= ng0;
-                int found = 0;
-#pragma unroll
-                for (int j = GT - 1; j >= 0; j--) {
-                    const int e = g * GT + j;
-                    const int sc = dp2a_lo_su(t_cxy[e], pxy[p], dp4a_uu(px[p], t_cpk[e], t_bias[e]));
-                    if (2 * sc - par == bestkey[p]) found = t_id[e];
-                }
+                int found = bi[p];
                 const uint16_t prev = d.assign[lbase + p];
-                if (d.tie == CNIIC_TIE_KEEP_CURRENT) {
+                if (d.tie == CNIIC_TIE_KEEP_CURRENT && found != prev) {
                     // the current cluster may have been culled; then it is strictly farther than the winner (LB > U)
-                    const int e = s_pos[prev];
-                    const uint32_t cxy = s_cxy[e];
-                    const int bias = s_bias0[e] + x0 * int(cxy & 0xffff) + yg0 * int(cxy >> 16);
-                    const int sc = dp2a_lo_su(cxy, pxy[p], dp4a_uu(px[p], s_cpk[e], bias));
-                    if (2 * sc - (uint32_t(e) >= n_static0) == bestkey[p]) found = prev;
+                    const uint32_t cxy = d.g_cxy[prev];
+                    const int kb = 2 * (x0 * int(cxy & 0xffff) + yg0 * int(cxy >> 16)) - int(d.g_nrm[prev]);
+                    if (2 * dp2a_lo_su(cxy, pxy[p], dp4a_uu(px[p], d.g_cpk[prev], 0)) + kb == best[p]) found = prev;
                 }
                 if (found != prev) { moved++; d.assign[lbase + p] = (uint16_t)found; }
                 if (found != run) {
@@ -819,6 +822,7 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
                 d.t_bias[e] = -int(nrm >> 1);
                 d.t_id[e] = uint16_t(c);
                 d.t_pos[c] = uint16_t(e);
+                if (D == 5) { d.g_cpk[c] = d.t_cpk[e]; d.g_cxy[c] = d.t_cxy[e]; d.g_nrm[c] = nrm; }
             }
             placed += tot;
         }
@@ -878,7 +882,11 @@ struct cniic_kmeans {
 
 static int km_launch_assign(cniic_kmeans *km) {
     cniic_ctx *ctx = km->ctx;
-    if (km->D == 5 && km->cull) km_assign_xyrgb_cull<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    if (km->D == 5 && km->cull) {
+        km_supercull<<<km->dev.super_x * km->dev.super_y, THREADS, 0, ctx->stream>>>(km->dev);
+        km->launches++;
+        km_assign_xyrgb_cull<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    }
     else if (km->D == 5) km_assign_xyrgb<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     else if (km->dev.wts) km_assign_rgb<true><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     else km_assign_rgb<false><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
@@ -954,6 +962,9 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     const size_t o_cpk = take(KP * 4), o_cxy = take(KP * 4), o_bias = take(KP * 4), o_id = take(KP * 2), o_pos = take(k * 2);
     const size_t o_sums = take((size_t(k) * (D + 1) + 1) * 8), o_cen = take(size_t(k) * D * 4), o_w = take(size_t(k) * 8);
     const size_t o_st = take(sizeof(KmState));
+    const uint32_t super_x = D == 5 ? (desc->w + SW - 1) / SW : 0, super_y = D == 5 ? (desc->h_local + SH - 1) / SH : 0;
+    const size_t o_gcpk = take(size_t(k) * 4), o_gcxy = take(size_t(k) * 4), o_gnrm = take(size_t(k) * 4);
+    const size_t o_sclist = take(size_t(super_x) * super_y * k * 2), o_sccount = take(size_t(super_x) * super_y * 4 + 4);
     km->pool = cniic_cache_alloc(ctx, off);
     if (!km->pool) return fail(CNIIC_ERR_CUDA);
     KM_TRY(cudaMemsetAsync(km->pool, 0, off, ctx->stream));
@@ -982,12 +993,18 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     dv.cen = reinterpret_cast<int32_t *>(p + o_cen);
     dv.weights = reinterpret_cast<unsigned long long *>(p + o_w);
     dv.st = reinterpret_cast<KmState *>(p + o_st);
+    dv.g_cpk = reinterpret_cast<uint32_t *>(p + o_gcpk);
+    dv.g_cxy = reinterpret_cast<uint32_t *>(p + o_gcxy);
+    dv.g_nrm = reinterpret_cast<uint32_t *>(p + o_gnrm);
+    dv.sc_list = reinterpret_cast<uint16_t *>(p + o_sclist);
+    dv.sc_count = reinterpret_cast<uint32_t *>(p + o_sccount);
+    dv.super_x = super_x;
+    dv.super_y = super_y;
 
     // shared memory + persistent grid
     km->cull = !(desc->flags & CNIIC_KMEANS_NO_CULL) && !getenv("CNIIC_NO_CULL");
     if (D == 5 && km->cull) {
-        const uint32_t KT = kpad_of(k, GT);
-        km->smem = size_t(KP) * 12 + size_t(KT) * 12 + size_t(k) * 24 + KP * 2 + ((k + 7) & ~7u) * 2 + KT * 2 + 16;
+        km->smem = size_t(TCAP) * 16 + size_t(k) * 24 + 16;
         KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb_cull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     } else if (D == 5) {
         km->smem = size_t(KP) * 16 + 8 * 192 * 4 + size_t(k) * 24 + KP * 2 + k * 2 + 16;
