@@ -71,6 +71,10 @@ struct KmDev {
     uint16_t *sc_list;   // [n_super][k] centroid ids, ascending
     uint32_t *sc_count;  // [n_super]
     uint32_t super_x, super_y;
+    // colour-sorted copy of the points (culled D = 3 path): packed r|g<<8|b<<16, original index, weight
+    const uint32_t *pts_sorted;
+    const uint32_t *perm;
+    const uint32_t *wts_sorted;
     unsigned long long *sums;  // k*(D+1) partial sums + 1 moved counter
     int32_t *cen;              // k*D
     unsigned long long *weights;
@@ -78,6 +82,27 @@ struct KmDev {
 };
 
 __host__ __device__ inline uint32_t kpad_of(uint32_t k, int G) { return (k + 2 * (G - 1) + G - 1) / G * G; }
+
+__device__ __forceinline__ int sq(int v) { return v * v; }
+
+// exclusive rank of `flag` among the 256 threads of the block (thread order); *total = number of flags set
+__device__ __forceinline__ uint32_t block_rank256(bool flag, uint32_t *s_warp, uint32_t *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t v = s_warp[i];
+        if (i < warp) before += v;
+        tot += v;
+    }
+    *total = tot;
+    return before + __popc(bal & ((1u << lane) - 1));
+}
+
 
 // ------------------------------------------------------------------------------------------------------------
 // D = 3 fused assign + accumulate
@@ -268,6 +293,269 @@ __global__ void __launch_bounds__(THREADS) km_assign_rgb(KmDev d) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// D = 3 with EXACT culling on a colour-sorted copy of the points (default for the RGB path)
+//   Once per session the points are counting-sorted by a 15-bit Morton code of (r>>3, g>>3, b>>3), so a tile of 2048
+//   consecutive sorted points occupies a small colour box.  Per tile (CTA): U = min_c max-distance^2(c, box) bounds
+//   every point's minimum, only centroids with min-distance^2(c, box) <= U are scored (ascending id, strict ">" =
+//   lowest index; key = 2*(p.c) - |c|^2 is the exact integer order).  Sums are permutation invariant and the
+//   assignment is kept in sorted order (mapped back through `perm` on output), so results equal the brute-force
+//   kernel bit for bit.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SORT_BINS = 32768;
+
+__device__ __forceinline__ uint32_t part1by2_5(uint32_t v) {
+    v &= 0x1f;
+    v = (v | (v << 8)) & 0x100f;
+    v = (v | (v << 4)) & 0x10c3;
+    v = (v | (v << 2)) & 0x1249;
+    return v;
+}
+__device__ __forceinline__ uint32_t colour_bucket(uint32_t r, uint32_t g, uint32_t b) {
+    return (part1by2_5(r >> 3) << 2) | (part1by2_5(g >> 3) << 1) | part1by2_5(b >> 3);
+}
+
+__global__ void __launch_bounds__(256) km_sort_hist(const uint8_t *__restrict__ rgb, unsigned long long n, uint32_t *bins) {
+    // warp-aggregated global atomics (neighbouring pixels usually share a bucket)
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, n_round = (n + 31) / 32 * 32;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < n;
+        const uint32_t key = valid ? colour_bucket(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]) : 0;
+        const uint32_t act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const uint32_t peers = __match_any_sync(act, key);
+            if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&bins[key], (uint32_t)__popc(peers));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) km_sort_scan(uint32_t *bins) {  // exclusive scan of SORT_BINS counters, in place
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < SORT_BINS; base += 1024) {
+        const uint32_t v = bins[base + threadIdx.x];
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        uint32_t before = s_carry;
+        for (int j = 0; j < warp; j++) before += s_w[j];
+        bins[base + threadIdx.x] = before + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + x;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) km_sort_scatter(const uint8_t *__restrict__ rgb, const uint32_t *__restrict__ wts, unsigned long long n,
+                                                       uint32_t *cursor, uint32_t *pts_sorted, uint32_t *perm, uint32_t *wts_sorted) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, n_round = (n + 31) / 32 * 32;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < n;
+        uint32_t r = 0, g = 0, b = 0, key = 0;
+        if (valid) { r = rgb[3 * i]; g = rgb[3 * i + 1]; b = rgb[3 * i + 2]; key = colour_bucket(r, g, b); }
+        const uint32_t act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const uint32_t peers = __match_any_sync(act, key);
+            const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const uint32_t pos = base + __popc(peers & ((1u << lane) - 1));
+            pts_sorted[pos] = r | (g << 8) | (b << 16);
+            perm[pos] = (uint32_t)i;
+            if (wts) wts_sorted[pos] = wts[i];
+        }
+    }
+}
+
+__global__ void km_unsort_assign(const uint16_t *__restrict__ assign_sorted, const uint32_t *__restrict__ perm, unsigned long long n, uint16_t *out) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+        out[perm[i]] = assign_sorted[i];
+}
+
+constexpr int RCAP = 256;  // survivors scored per round
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
+    if (d.st->done) return;
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t k = d.k;
+    uint4 *t_ent = smem_raw;  // RCAP x {cpk, kb, id, -}
+    uint32_t *s_acc32 = reinterpret_cast<uint32_t *>(t_ent + RCAP);
+    unsigned long long *s_acc64 = reinterpret_cast<unsigned long long *>(t_ent + RCAP);
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_box[8];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t i = tid; i < 4 * k; i += THREADS) {
+        if (WEIGHTED) s_acc64[i] = 0ull;
+        else s_acc32[i] = 0u;
+    }
+    const unsigned long long n = d.n_local;
+    const unsigned long long tiles = (n + TILE - 1) / TILE;
+    unsigned long long moved = 0, pairs_local = 0;
+
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const unsigned long long base = tile * TILE + (unsigned long long)tid * PX;
+        int nv = 0;
+        if (base < n) nv = (n - base) >= PX ? PX : int(n - base);
+        uint32_t px[PX];
+        if (nv == PX) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(d.pts_sorted + base)), b = __ldg(reinterpret_cast<const uint4 *>(d.pts_sorted + base) + 1);
+            px[0] = a.x; px[1] = a.y; px[2] = a.z; px[3] = a.w; px[4] = b.x; px[5] = b.y; px[6] = b.z; px[7] = b.w;
+        } else {
+#pragma unroll
+            for (int p = 0; p < PX; p++) px[p] = p < nv ? d.pts_sorted[base + p] : 0u;
+        }
+        uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+        for (int p = 0; p < PX; p++)
+            if (p < nv) { mn = __vminu4(mn, px[p]); mx = __vmaxu4(mx, px[p]); }
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = __vmaxu4(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        __syncthreads();
+        if (tid < 3) { s_box[tid] = 255u; s_box[3 + tid] = 0u; }
+        if (tid == 3) s_box[6] = 0xffffffffu;
+        __syncthreads();
+        if (lane < 3) {
+            atomicMin(&s_box[lane], (mn >> (8 * lane)) & 0xff);
+            atomicMax(&s_box[3 + lane], (mx >> (8 * lane)) & 0xff);
+        }
+        __syncthreads();
+        const int r0 = s_box[0], g0 = s_box[1], b0 = s_box[2], r1 = s_box[3], g1 = s_box[4], b1 = s_box[5];
+        uint32_t umin = 0xffffffffu;
+        for (uint32_t c = tid; c < k; c += THREADS) {
+            const uint32_t cp = d.g_cpk[c];
+            const int cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
+            umin = min(umin, uint32_t(sq(max(abs(cr - r0), abs(cr - r1))) + sq(max(abs(cg - g0), abs(cg - g1))) + sq(max(abs(cb - b0), abs(cb - b1)))));
+        }
+        for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+        if (lane == 0) atomicMin(&s_box[6], umin);
+        __syncthreads();
+        const uint32_t U = s_box[6];
+
+        int best[PX], bi[PX];
+#pragma unroll
+        for (int p = 0; p < PX; p++) { best[p] = INT_MIN; bi[p] = 0; }
+        for (uint32_t cb0 = 0; cb0 < k; cb0 += RCAP) {
+            const uint32_t c = cb0 + tid;
+            bool keep = false;
+            uint4 ent = make_uint4(0, 0, 0, 0);
+            if (c < k) {
+                const uint32_t cp = d.g_cpk[c];
+                const int cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
+                keep = uint32_t(sq(max(0, max(r0 - cr, cr - r1))) + sq(max(0, max(g0 - cg, cg - g1))) + sq(max(0, max(b0 - cb, cb - b1)))) <= U;
+                ent = make_uint4(cp, uint32_t(-int(d.g_nrm[c])), c, 0);
+            }
+            uint32_t nt;
+            const uint32_t r = block_rank256(keep, s_warp, &nt);
+            if (keep) t_ent[r] = ent;
+            __syncthreads();
+            if (tid == 0) pairs_local += (unsigned long long)nt * min((unsigned long long)TILE, n - tile * TILE);
+            for (uint32_t e = 0; e < nt; e++) {
+                const uint4 ce = t_ent[e];
+#pragma unroll
+                for (int p = 0; p < PX; p++) {
+                    const int key = 2 * dp4a_uu(px[p], ce.x, 0) + int(ce.y);
+                    if (key > best[p]) { best[p] = key; bi[p] = int(ce.z); }
+                }
+            }
+            if (cb0 + RCAP < k) __syncthreads();
+        }
+
+        uint16_t prev[PX], idx[PX];
+        if (nv == PX) {
+            const uint4 pv = *reinterpret_cast<const uint4 *>(d.assign + base);
+            prev[0] = pv.x & 0xffff; prev[1] = pv.x >> 16; prev[2] = pv.y & 0xffff; prev[3] = pv.y >> 16;
+            prev[4] = pv.z & 0xffff; prev[5] = pv.z >> 16; prev[6] = pv.w & 0xffff; prev[7] = pv.w >> 16;
+        } else {
+#pragma unroll
+            for (int p = 0; p < PX; p++) prev[p] = p < nv ? d.assign[base + p] : 0;
+        }
+        bool any_moved = false;
+#pragma unroll
+        for (int p = 0; p < PX; p++) {
+            int found = bi[p];
+            if (p < nv && d.tie == CNIIC_TIE_KEEP_CURRENT && found != prev[p]) {
+                // a culled current cluster is strictly farther than the winner (LB > U), so it cannot tie
+                if (2 * dp4a_uu(px[p], d.g_cpk[prev[p]], 0) - int(d.g_nrm[prev[p]]) == best[p]) found = prev[p];
+            }
+            idx[p] = (uint16_t)found;
+            if (p < nv && idx[p] != prev[p]) { moved++; any_moved = true; }
+        }
+        if (any_moved) {
+            if (nv == PX) {
+                uint4 ov;
+                ov.x = idx[0] | (uint32_t(idx[1]) << 16); ov.y = idx[2] | (uint32_t(idx[3]) << 16);
+                ov.z = idx[4] | (uint32_t(idx[5]) << 16); ov.w = idx[6] | (uint32_t(idx[7]) << 16);
+                *reinterpret_cast<uint4 *>(d.assign + base) = ov;
+            } else {
+#pragma unroll
+                for (int p = 0; p < PX; p++)
+                    if (p < nv) d.assign[base + p] = idx[p];
+            }
+        }
+        if (WEIGHTED) {
+            unsigned long long ar = 0, ag = 0, ab = 0, aw = 0;
+            int run = -1;
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                if (p < nv) {
+                    if (idx[p] != run) {
+                        if (run >= 0) {
+                            atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
+                            atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+                        }
+                        run = idx[p]; ar = ag = ab = aw = 0;
+                    }
+                    const unsigned long long wq = d.wts_sorted[base + p];
+                    ar += (px[p] & 0xff) * wq; ag += ((px[p] >> 8) & 0xff) * wq; ab += ((px[p] >> 16) & 0xff) * wq; aw += wq;
+                }
+            }
+            if (run >= 0) {
+                atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
+                atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+            }
+        } else {
+            uint32_t ar = 0, ag = 0, ab = 0, aw = 0;
+            int run = -1;
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                if (p < nv) {
+                    if (idx[p] != run) {
+                        if (run >= 0) {
+                            atomicAdd(&s_acc32[4 * run], ar); atomicAdd(&s_acc32[4 * run + 1], ag);
+                            atomicAdd(&s_acc32[4 * run + 2], ab); atomicAdd(&s_acc32[4 * run + 3], aw);
+                        }
+                        run = idx[p]; ar = ag = ab = aw = 0;
+                    }
+                    ar += px[p] & 0xff; ag += (px[p] >> 8) & 0xff; ab += (px[p] >> 16) & 0xff; aw += 1;
+                }
+            }
+            if (run >= 0) {
+                atomicAdd(&s_acc32[4 * run], ar); atomicAdd(&s_acc32[4 * run + 1], ag);
+                atomicAdd(&s_acc32[4 * run + 2], ab); atomicAdd(&s_acc32[4 * run + 3], aw);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < 4 * k; i += THREADS) {
+        const unsigned long long v = WEIGHTED ? s_acc64[i] : (unsigned long long)s_acc32[i];
+        if (v) atomicAdd(&d.sums[i], v);
+    }
+    for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
+    if (lane == 0 && moved) atomicAdd(&d.sums[4 * k], moved);
+    if (tid == 0 && pairs_local) atomicAdd(&d.st->pairs, pairs_local);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // D = 5 fused assign + accumulate: tile = 256 pixels x 8 rows, warp = one row, lane = 8 consecutive pixels
 // ------------------------------------------------------------------------------------------------------------
 
@@ -449,25 +737,6 @@ __global__ void __launch_bounds__(THREADS) km_assign_xyrgb(KmDev d) {
 constexpr int TW = 64, TH = 32;    // tile
 constexpr int SW = 512, SH = 256;  // supertile = 8 x 8 tiles
 constexpr int TCAP = 256;          // survivors scored per round
-
-__device__ __forceinline__ uint32_t block_rank256(bool flag, uint32_t *s_warp, uint32_t *total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
-    __syncthreads();
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t before = 0, tot = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const uint32_t v = s_warp[i];
-        if (i < warp) before += v;
-        tot += v;
-    }
-    *total = tot;
-    return before + __popc(bal & ((1u << lane) - 1));
-}
-
-__device__ __forceinline__ int sq(int v) { return v * v; }
 
 __global__ void __launch_bounds__(THREADS) km_supercull(KmDev d) {
     if (d.st->done) return;
@@ -698,7 +967,7 @@ __global__ void km_init_assign(KmDev d) {
     const unsigned long long head = N - (unsigned long long)(d.k - 1) * ppc;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < d.n_local;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long gi = d.first_index + i;
+        const unsigned long long gi = d.first_index + (d.perm ? d.perm[i] : i);
         d.assign[i] = gi >= head ? uint16_t((N - 1 - gi) / ppc) : uint16_t(d.k - 1);
     }
 }
@@ -778,6 +1047,26 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
             __syncthreads();
             const uint32_t victim = s_victim;
             uint32_t found = 0;
+            if (d.perm) {
+                // points are stored colour-sorted: select the members with the lowest ORIGINAL indices one at a time
+                long long last = -1;
+                for (; found < nempty; found++) {
+                    uint32_t best = 0xffffffffu;
+                    for (unsigned long long i = tid; i < d.n_local; i += 1024)
+                        if (d.assign[i] == victim) {
+                            const uint32_t o = d.perm[i];
+                            if ((long long)o > last && o < best) best = o;
+                        }
+                    for (int o2 = 16; o2 > 0; o2 >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o2));
+                    __syncthreads();
+                    if ((tid & 31) == 0) s_warp[tid >> 5] = best;
+                    __syncthreads();
+                    for (int i = 0; i < 32; i++) best = min(best, s_warp[i]);
+                    if (best == 0xffffffffu) break;
+                    if (tid == 0) s_found[found] = best;
+                    last = best;
+                }
+            } else
             for (unsigned long long base = 0; base < d.n_local && found < nempty; base += 1024) {
                 const unsigned long long i = base + tid;
                 const bool is = i < d.n_local && d.assign[i] == victim;
@@ -822,7 +1111,8 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
                 d.t_bias[e] = -int(nrm >> 1);
                 d.t_id[e] = uint16_t(c);
                 d.t_pos[c] = uint16_t(e);
-                if (D == 5) { d.g_cpk[c] = d.t_cpk[e]; d.g_cxy[c] = d.t_cxy[e]; d.g_nrm[c] = nrm; }
+                d.g_cpk[c] = d.t_cpk[e]; d.g_nrm[c] = nrm;
+                if (D == 5) d.g_cxy[c] = d.t_cxy[e];
             }
             placed += tot;
         }
@@ -876,7 +1166,9 @@ struct cniic_kmeans {
     static constexpr int PROF = 32;  // assign launches timed per run (CUDA events on the launching stream)
     cudaEvent_t pev[2 * PROF] = {};
     uint32_t launches = 0;
-    bool cull = true;        // D = 5: exact tile culling (CNIIC_KMEANS_NO_CULL in desc.flags selects brute force)
+    uint32_t *d_sorted = nullptr, *d_perm = nullptr, *d_wsorted = nullptr;  // colour-sorted copy (culled D = 3)
+    uint16_t *d_assign_orig = nullptr;  // assignment mapped back to original order (filled on demand)
+    bool cull = true;        // exact culling (CNIIC_KMEANS_NO_CULL in desc.flags selects brute force)
     uint32_t iter_seen = 0;  // state.iter at the end of the previous run (0 after reset)
 };
 
@@ -888,6 +1180,8 @@ static int km_launch_assign(cniic_kmeans *km) {
         km_assign_xyrgb_cull<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     }
     else if (km->D == 5) km_assign_xyrgb<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    else if (km->cull && km->dev.wts) km_assign_rgb_cull<true><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    else if (km->cull) km_assign_rgb_cull<false><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     else if (km->dev.wts) km_assign_rgb<true><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     else km_assign_rgb<false><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     km->launches++;
@@ -1001,14 +1295,38 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     dv.super_x = super_x;
     dv.super_y = super_y;
 
-    // shared memory + persistent grid
     km->cull = !(desc->flags & CNIIC_KMEANS_NO_CULL) && !getenv("CNIIC_NO_CULL");
+    if (D == 3 && km->cull && desc->n_local) {
+        // colour-sorted copy of the points (counting sort by a 15-bit Morton bucket), built once per session
+        const size_t n = desc->n_local;
+        km->d_sorted = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (n + 8) * 4));
+        km->d_perm = static_cast<uint32_t *>(cniic_cache_alloc(ctx, n * 4));
+        if (d_wts) km->d_wsorted = static_cast<uint32_t *>(cniic_cache_alloc(ctx, n * 4));
+        uint32_t *d_bins = static_cast<uint32_t *>(cniic_cache_alloc(ctx, SORT_BINS * 4));
+        if (!km->d_sorted || !km->d_perm || (d_wts && !km->d_wsorted) || !d_bins) return fail(CNIIC_ERR_CUDA);
+        KM_TRY(cudaMemsetAsync(d_bins, 0, SORT_BINS * 4, ctx->stream));
+        const int sgrid = (int)std::max<size_t>(1, std::min<size_t>((n + 1023) / 1024, (size_t)ctx->sm_count * 16));
+        km_sort_hist<<<sgrid, 256, 0, ctx->stream>>>(d_rgb, n, d_bins);
+        km_sort_scan<<<1, 1024, 0, ctx->stream>>>(d_bins);
+        km_sort_scatter<<<sgrid, 256, 0, ctx->stream>>>(d_rgb, d_wts, n, d_bins, km->d_sorted, km->d_perm, km->d_wsorted);
+        km->launches += 3;
+        KM_TRY(cudaGetLastError());
+        cniic_cache_free(ctx, d_bins);  // stream-ordered reuse is safe
+        dv.pts_sorted = km->d_sorted;
+        dv.perm = km->d_perm;
+        dv.wts_sorted = km->d_wsorted;
+    }
+    // shared memory + persistent grid
     if (D == 5 && km->cull) {
         km->smem = size_t(TCAP) * 16 + size_t(k) * 24 + 16;
         KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb_cull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     } else if (D == 5) {
         km->smem = size_t(KP) * 16 + 8 * 192 * 4 + size_t(k) * 24 + KP * 2 + k * 2 + 16;
         KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+    } else if (km->cull) {
+        km->smem = size_t(RCAP) * 16 + size_t(k) * 4 * (d_wts ? 8 : 4) + 16;
+        if (d_wts) KM_TRY(cudaFuncSetAttribute(km_assign_rgb_cull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+        else KM_TRY(cudaFuncSetAttribute(km_assign_rgb_cull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     } else {
         km->smem = size_t(KP) * 8 + KP * 2 + k * 2 + 16 + size_t(k) * 4 * (d_wts ? 8 : 4) + 16;
         if (d_wts) KM_TRY(cudaFuncSetAttribute(km_assign_rgb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
@@ -1017,6 +1335,8 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     int per_sm = 0;
     if (D == 5 && km->cull) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull, THREADS, km->smem));
     else if (D == 5) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb, THREADS, km->smem));
+    else if (km->cull && d_wts) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull<true>, THREADS, km->smem));
+    else if (km->cull) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull<false>, THREADS, km->smem));
     else if (d_wts) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb<true>, THREADS, km->smem));
     else KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb<false>, THREADS, km->smem));
     if (per_sm < 1) return fail(cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "k = %u needs %zu bytes of shared memory", k, km->smem));
@@ -1116,13 +1436,29 @@ extern "C" int cniic_kmeans_get(cniic_kmeans *km, int32_t *out_centroids, uint64
     const uint32_t k = km->desc.k;
     if (out_centroids) CU_TRY(ctx, cudaMemcpyAsync(out_centroids, km->dev.cen, size_t(k) * km->D * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_weight) CU_TRY(ctx, cudaMemcpyAsync(out_weight, km->dev.weights, size_t(k) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_assign && km->desc.n_local)
-        CU_TRY(ctx, cudaMemcpyAsync(out_assign, km->dev.assign, km->desc.n_local * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_assign && km->desc.n_local) {
+        const uint16_t *src = cniic_kmeans_device_assign(km);
+        if (!src) return CNIIC_ERR_CUDA;
+        CU_TRY(ctx, cudaMemcpyAsync(out_assign, src, km->desc.n_local * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CNIIC_OK;
 }
 
-extern "C" const uint16_t *cniic_kmeans_device_assign(cniic_kmeans *km) { return km ? km->dev.assign : nullptr; }
+extern "C" const uint16_t *cniic_kmeans_device_assign(cniic_kmeans *km) {
+    if (!km) return nullptr;
+    if (!km->dev.perm) return km->dev.assign;
+    // the culled RGB path keeps the assignment in colour-sorted order: map it back through the permutation
+    cniic_ctx *ctx = km->ctx;
+    const size_t n = km->desc.n_local;
+    if (!km->d_assign_orig) km->d_assign_orig = static_cast<uint16_t *>(cniic_cache_alloc(ctx, n * 2));
+    if (!km->d_assign_orig) return nullptr;
+    km_unsort_assign<<<(int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16)), 256, 0, ctx->stream>>>(
+        km->dev.assign, km->dev.perm, n, km->d_assign_orig);
+    km->launches++;
+    ctx->launches++;
+    return km->d_assign_orig;
+}
 
 extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
     if (!km) return;
@@ -1131,6 +1467,10 @@ extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
     cniic_cache_free(km->ctx, km->own_rgb);
     cniic_cache_free(km->ctx, km->own_wts);
     cniic_cache_free(km->ctx, km->pool);
+    cniic_cache_free(km->ctx, km->d_sorted);
+    cniic_cache_free(km->ctx, km->d_perm);
+    cniic_cache_free(km->ctx, km->d_wsorted);
+    cniic_cache_free(km->ctx, km->d_assign_orig);
     cniic_pinned_put(km->ctx, km->h_state);
     if (km->ev0) cudaEventDestroy(km->ev0);
     if (km->ev1) cudaEventDestroy(km->ev1);

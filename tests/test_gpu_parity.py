@@ -142,6 +142,22 @@ def test_kmeans_xyrgb_brute_force_kernel(ctx, w, h, k):
     assert st.iterations == 3 and np.array_equal(cen, o.centroids) and np.array_equal(asg, o.assign) and np.array_equal(wts, o.weights)
 
 
+@pytest.mark.parametrize("n,k,weighted", [(5000, 16, False), (70000, 256, False), (33333, 300, True), (2048 * 3 + 5, 64, True)])
+def test_kmeans_rgb_brute_force_kernel(ctx, n, k, weighted):
+    """The non-culled D = 3 kernel (CNIIC_KMEANS_NO_CULL) must agree with the oracle as well."""
+    rng = np.random.default_rng(n)
+    pts = cb.synth_image_host(256, (n + 255) // 256, 77, 9).reshape(-1, 3)[:n]
+    wts = rng.integers(1, 1000, n).astype(np.uint32) if weighted else None
+    s = cb.KMeansSession(ctx, cb.POINTS_RGB, k, pts, n, weights=wts, flags=cb._lib.KMEANS_NO_CULL)
+    s.reset()
+    st = s.run(4)
+    cen, wsum, asg = s.get()
+    s.close()
+    o = O.kmeans_rgb(pts, k, counts=wts, mode=O.MODE_EXACT, max_iters=4)
+    assert st.iterations == o.iterations and np.array_equal(cen, o.centroids) and np.array_equal(asg, o.assign)
+    assert np.array_equal(wsum, o.weights)
+
+
 def test_kmeans_session_reuse(ctx):
     img = cb.synth_image_host(128, 64, 8, 8)
     s = cb.KMeansSession(ctx, cb.POINTS_XYRGB, 32, img, 128 * 64, w=128, h_local=64)
