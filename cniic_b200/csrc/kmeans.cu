@@ -75,6 +75,7 @@ struct KmDev {
     const uint32_t *pts_sorted;
     const uint32_t *perm;
     const uint32_t *wts_sorted;
+    const uint2 *tile_box;  // per 2048-point tile of the sorted copy: {bytewise min, bytewise max} of the packed colours
     unsigned long long *sums;  // k*(D+1) partial sums + 1 moved counter
     int32_t *cen;              // k*D
     unsigned long long *weights;
@@ -314,63 +315,132 @@ __device__ __forceinline__ uint32_t colour_bucket(uint32_t r, uint32_t g, uint32
     return (part1by2_5(r >> 3) << 2) | (part1by2_5(g >> 3) << 1) | part1by2_5(b >> 3);
 }
 
-__global__ void __launch_bounds__(256) km_sort_hist(const uint8_t *__restrict__ rgb, unsigned long long n, uint32_t *bins) {
-    // warp-aggregated global atomics (neighbouring pixels usually share a bucket)
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, n_round = (n + 31) / 32 * 32;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool valid = i < n;
-        const uint32_t key = valid ? colour_bucket(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]) : 0;
-        const uint32_t act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const uint32_t peers = __match_any_sync(act, key);
-            if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&bins[key], (uint32_t)__popc(peers));
-        }
-    }
+// Counting sort in three kernels, no global atomics: every CTA owns a contiguous chunk of the input.
+//   km_sort_hist    : per-CTA histogram in shared memory (32768 bins)            -> hist[cta][bucket]
+//   km_sort_offsets : per bucket, exclusive prefix over the CTAs + bucket start  -> hist[cta][bucket] = first slot
+//   km_sort_scatter : per-CTA cursors in shared memory hand out the slots
+constexpr int SORT_THREADS = 1024;
+
+__device__ __forceinline__ void sort_chunk(unsigned long long n, unsigned long long *lo, unsigned long long *hi) {
+    // chunk boundaries are multiples of 4 points (12 bytes) so that every thread can use aligned 32-bit loads
+    const unsigned long long per = ((n + gridDim.x - 1) / gridDim.x + 3) & ~3ull;
+    *lo = min(n, per * blockIdx.x);
+    *hi = min(n, *lo + per);
 }
 
-__global__ void __launch_bounds__(1024) km_sort_scan(uint32_t *bins) {  // exclusive scan of SORT_BINS counters, in place
-    __shared__ uint32_t s_w[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+__global__ void __launch_bounds__(SORT_THREADS) km_sort_hist(const uint8_t *__restrict__ rgb, unsigned long long n, uint32_t *hist) {
+    extern __shared__ uint32_t s_bins[];
+    for (int i = threadIdx.x; i < SORT_BINS; i += SORT_THREADS) s_bins[i] = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < SORT_BINS; base += 1024) {
-        const uint32_t v = bins[base + threadIdx.x];
-        uint32_t x = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+    unsigned long long lo, hi;
+    sort_chunk(n, &lo, &hi);
+    const bool al = (reinterpret_cast<uintptr_t>(rgb) & 3) == 0;
+    for (unsigned long long i = lo + 4ull * threadIdx.x; i < hi; i += 4ull * SORT_THREADS) {
+        if (al && i + 4 <= hi) {  // 4 points = three aligned words
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(rgb + i * 3);
+            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+            const uint32_t k0 = colour_bucket(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
+            const uint32_t k1 = colour_bucket(w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff);
+            const uint32_t k2 = colour_bucket((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
+            const uint32_t k3 = colour_bucket((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
+            if (k0 == k1 && k1 == k2 && k2 == k3) atomicAdd(&s_bins[k0], 4u);
+            else { atomicAdd(&s_bins[k0], 1u); atomicAdd(&s_bins[k1], 1u); atomicAdd(&s_bins[k2], 1u); atomicAdd(&s_bins[k3], 1u); }
+        } else {
+            for (unsigned long long j = i; j < min(i + 4, hi); j++) atomicAdd(&s_bins[colour_bucket(rgb[3 * j], rgb[3 * j + 1], rgb[3 * j + 2])], 1u);
         }
-        if (lane == 31) s_w[warp] = x;
-        __syncthreads();
-        uint32_t before = s_carry;
-        for (int j = 0; j < warp; j++) before += s_w[j];
-        bins[base + threadIdx.x] = before + x - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = before + x;
-        __syncthreads();
+    }
+    __syncthreads();
+    uint32_t *out = hist + (size_t)blockIdx.x * SORT_BINS;
+    for (int i = threadIdx.x; i < SORT_BINS; i += SORT_THREADS) out[i] = s_bins[i];
+}
+
+// one thread per bucket: totals over CTAs, block scan of the totals (grid = 32 blocks x 1024 buckets, two phases)
+__global__ void __launch_bounds__(1024) km_sort_totals(const uint32_t *__restrict__ hist, int nctas, uint32_t *totals) {
+    const int b = blockIdx.x * 1024 + threadIdx.x;
+    uint32_t t = 0;
+    for (int c = 0; c < nctas; c++) t += hist[(size_t)c * SORT_BINS + b];
+    totals[b] = t;
+}
+
+__global__ void __launch_bounds__(1024) km_sort_scan(uint32_t *totals) {  // exclusive scan of SORT_BINS totals, in place
+    __shared__ uint32_t s_w[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t v[SORT_BINS / 1024], tot = 0;
+#pragma unroll
+    for (int j = 0; j < SORT_BINS / 1024; j++) { v[j] = totals[threadIdx.x * (SORT_BINS / 1024) + j]; tot += v[j]; }
+    uint32_t x = tot;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int j = 0; j < warp; j++) before += s_w[j];
+    uint32_t run = before + x - tot;
+#pragma unroll
+    for (int j = 0; j < SORT_BINS / 1024; j++) { totals[threadIdx.x * (SORT_BINS / 1024) + j] = run; run += v[j]; }
+}
+
+__global__ void __launch_bounds__(1024) km_sort_offsets(uint32_t *hist, int nctas, const uint32_t *__restrict__ starts) {
+    const int b = blockIdx.x * 1024 + threadIdx.x;
+    uint32_t run = starts[b];
+    for (int c = 0; c < nctas; c++) {
+        const uint32_t v = hist[(size_t)c * SORT_BINS + b];
+        hist[(size_t)c * SORT_BINS + b] = run;
+        run += v;
     }
 }
 
-__global__ void __launch_bounds__(256) km_sort_scatter(const uint8_t *__restrict__ rgb, const uint32_t *__restrict__ wts, unsigned long long n,
-                                                       uint32_t *cursor, uint32_t *pts_sorted, uint32_t *perm, uint32_t *wts_sorted) {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, n_round = (n + 31) / 32 * 32;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool valid = i < n;
-        uint32_t r = 0, g = 0, b = 0, key = 0;
-        if (valid) { r = rgb[3 * i]; g = rgb[3 * i + 1]; b = rgb[3 * i + 2]; key = colour_bucket(r, g, b); }
-        const uint32_t act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const uint32_t peers = __match_any_sync(act, key);
-            const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            const uint32_t pos = base + __popc(peers & ((1u << lane) - 1));
-            pts_sorted[pos] = r | (g << 8) | (b << 16);
-            perm[pos] = (uint32_t)i;
-            if (wts) wts_sorted[pos] = wts[i];
+__global__ void __launch_bounds__(SORT_THREADS) km_sort_scatter(const uint8_t *__restrict__ rgb, const uint32_t *__restrict__ wts, unsigned long long n,
+                                                                const uint32_t *__restrict__ hist, uint32_t *pts_sorted, uint32_t *perm,
+                                                                uint32_t *wts_sorted) {
+    extern __shared__ uint32_t s_cur[];
+    const uint32_t *mine = hist + (size_t)blockIdx.x * SORT_BINS;
+    for (int i = threadIdx.x; i < SORT_BINS; i += SORT_THREADS) s_cur[i] = mine[i];
+    __syncthreads();
+    unsigned long long lo, hi;
+    sort_chunk(n, &lo, &hi);
+    const bool al = (reinterpret_cast<uintptr_t>(rgb) & 3) == 0;
+    for (unsigned long long i = lo + 4ull * threadIdx.x; i < hi; i += 4ull * SORT_THREADS) {
+        uint32_t pk[4];
+        int cnt = (int)min((unsigned long long)4, hi - i);
+        if (al && cnt == 4) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(rgb + i * 3);
+            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+            pk[0] = w0 & 0xffffff; pk[1] = (w0 >> 24) | ((w1 & 0xffff) << 8); pk[2] = (w1 >> 16) | ((w2 & 0xff) << 16); pk[3] = w2 >> 8;
+        } else {
+            for (int j = 0; j < 4; j++) {
+                pk[j] = 0;
+                if (j < cnt) { const uint8_t *q = rgb + (i + j) * 3; pk[j] = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16); }
+            }
         }
+        for (int j = 0; j < cnt; j++) {
+            const uint32_t pos = atomicAdd(&s_cur[colour_bucket(pk[j] & 0xff, (pk[j] >> 8) & 0xff, pk[j] >> 16)], 1u);
+            pts_sorted[pos] = pk[j];
+            perm[pos] = (uint32_t)(i + j);
+            if (wts) wts_sorted[pos] = wts[i + j];
+        }
+    }
+}
+
+// bytewise min / max of the packed colours of every 2048-point tile of the sorted copy (static for the whole session)
+__global__ void __launch_bounds__(256) km_tile_boxes(const uint32_t *__restrict__ pts_sorted, unsigned long long n, uint2 *boxes) {
+    __shared__ uint32_t s_mn[8], s_mx[8];
+    const unsigned long long base = (unsigned long long)blockIdx.x * TILE + (unsigned long long)threadIdx.x * PX;
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    for (int p = 0; p < PX; p++)
+        if (base + p < n) { const uint32_t v = pts_sorted[base + p]; mn = __vminu4(mn, v); mx = __vmaxu4(mx, v); }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = __vmaxu4(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) { mn = __vminu4(mn, s_mn[i]); mx = __vmaxu4(mx, s_mx[i]); }
+        mn = __vminu4(mn, s_mn[0]); mx = __vmaxu4(mx, s_mx[0]);
+        boxes[blockIdx.x] = make_uint2(mn, mx);
     }
 }
 
@@ -386,12 +456,14 @@ __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
     if (d.st->done) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
-    uint4 *t_ent = smem_raw;  // RCAP x {cpk, kb, id, -}
-    uint32_t *s_acc32 = reinterpret_cast<uint32_t *>(t_ent + RCAP);
-    unsigned long long *s_acc64 = reinterpret_cast<unsigned long long *>(t_ent + RCAP);
+    uint4 *t_ent = smem_raw;                                   // RCAP x {cpk, -|c|^2, id, -}
+    uint2 *s_cen = reinterpret_cast<uint2 *>(t_ent + RCAP);    // k x {cpk, |c|^2}
+    uint32_t *s_acc32 = reinterpret_cast<uint32_t *>(s_cen + ((k + 1) & ~1u));
+    unsigned long long *s_acc64 = reinterpret_cast<unsigned long long *>(s_cen + ((k + 1) & ~1u));
     __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_box[8];
+    __shared__ uint32_t s_U;
     const int tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t i = tid; i < k; i += THREADS) s_cen[i] = make_uint2(d.g_cpk[i], d.g_nrm[i]);
     for (uint32_t i = tid; i < 4 * k; i += THREADS) {
         if (WEIGHTED) s_acc64[i] = 0ull;
         else s_acc32[i] = 0u;
@@ -412,34 +484,31 @@ __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
 #pragma unroll
             for (int p = 0; p < PX; p++) px[p] = p < nv ? d.pts_sorted[base + p] : 0u;
         }
-        uint32_t mn = 0xffffffffu, mx = 0u;
+        uint16_t prev[PX];
+        if (nv == PX) {
+            const uint4 pv = *reinterpret_cast<const uint4 *>(d.assign + base);
+            prev[0] = pv.x & 0xffff; prev[1] = pv.x >> 16; prev[2] = pv.y & 0xffff; prev[3] = pv.y >> 16;
+            prev[4] = pv.z & 0xffff; prev[5] = pv.z >> 16; prev[6] = pv.w & 0xffff; prev[7] = pv.w >> 16;
+        } else {
 #pragma unroll
-        for (int p = 0; p < PX; p++)
-            if (p < nv) { mn = __vminu4(mn, px[p]); mx = __vmaxu4(mx, px[p]); }
-        for (int o = 16; o > 0; o >>= 1) {
-            mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            mx = __vmaxu4(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            for (int p = 0; p < PX; p++) prev[p] = p < nv ? d.assign[base + p] : 0;
         }
+        const uint2 box = d.tile_box[tile];  // static colour box of this tile
+        const int r0 = box.x & 0xff, g0 = (box.x >> 8) & 0xff, b0 = (box.x >> 16) & 0xff;
+        const int r1 = box.y & 0xff, g1 = (box.y >> 8) & 0xff, b1 = (box.y >> 16) & 0xff;
+        __syncthreads();  // previous tile done with s_U / t_ent (and s_cen is loaded on the first pass)
+        if (tid == 0) s_U = 0xffffffffu;
         __syncthreads();
-        if (tid < 3) { s_box[tid] = 255u; s_box[3 + tid] = 0u; }
-        if (tid == 3) s_box[6] = 0xffffffffu;
-        __syncthreads();
-        if (lane < 3) {
-            atomicMin(&s_box[lane], (mn >> (8 * lane)) & 0xff);
-            atomicMax(&s_box[3 + lane], (mx >> (8 * lane)) & 0xff);
-        }
-        __syncthreads();
-        const int r0 = s_box[0], g0 = s_box[1], b0 = s_box[2], r1 = s_box[3], g1 = s_box[4], b1 = s_box[5];
         uint32_t umin = 0xffffffffu;
         for (uint32_t c = tid; c < k; c += THREADS) {
-            const uint32_t cp = d.g_cpk[c];
+            const uint32_t cp = s_cen[c].x;
             const int cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
             umin = min(umin, uint32_t(sq(max(abs(cr - r0), abs(cr - r1))) + sq(max(abs(cg - g0), abs(cg - g1))) + sq(max(abs(cb - b0), abs(cb - b1)))));
         }
         for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-        if (lane == 0) atomicMin(&s_box[6], umin);
+        if (lane == 0) atomicMin(&s_U, umin);
         __syncthreads();
-        const uint32_t U = s_box[6];
+        const uint32_t U = s_U;
 
         int best[PX], bi[PX];
 #pragma unroll
@@ -449,10 +518,10 @@ __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
             bool keep = false;
             uint4 ent = make_uint4(0, 0, 0, 0);
             if (c < k) {
-                const uint32_t cp = d.g_cpk[c];
-                const int cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
+                const uint2 ce = s_cen[c];
+                const int cr = ce.x & 0xff, cg = (ce.x >> 8) & 0xff, cb = (ce.x >> 16) & 0xff;
                 keep = uint32_t(sq(max(0, max(r0 - cr, cr - r1))) + sq(max(0, max(g0 - cg, cg - g1))) + sq(max(0, max(b0 - cb, cb - b1)))) <= U;
-                ent = make_uint4(cp, uint32_t(-int(d.g_nrm[c])), c, 0);
+                ent = make_uint4(ce.x, uint32_t(-int(ce.y)), c, 0);
             }
             uint32_t nt;
             const uint32_t r = block_rank256(keep, s_warp, &nt);
@@ -470,25 +539,19 @@ __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
             if (cb0 + RCAP < k) __syncthreads();
         }
 
-        uint16_t prev[PX], idx[PX];
-        if (nv == PX) {
-            const uint4 pv = *reinterpret_cast<const uint4 *>(d.assign + base);
-            prev[0] = pv.x & 0xffff; prev[1] = pv.x >> 16; prev[2] = pv.y & 0xffff; prev[3] = pv.y >> 16;
-            prev[4] = pv.z & 0xffff; prev[5] = pv.z >> 16; prev[6] = pv.w & 0xffff; prev[7] = pv.w >> 16;
-        } else {
-#pragma unroll
-            for (int p = 0; p < PX; p++) prev[p] = p < nv ? d.assign[base + p] : 0;
-        }
-        bool any_moved = false;
+        uint16_t idx[PX];
+        bool any_moved = false, uniform = nv == PX;
 #pragma unroll
         for (int p = 0; p < PX; p++) {
             int found = bi[p];
             if (p < nv && d.tie == CNIIC_TIE_KEEP_CURRENT && found != prev[p]) {
                 // a culled current cluster is strictly farther than the winner (LB > U), so it cannot tie
-                if (2 * dp4a_uu(px[p], d.g_cpk[prev[p]], 0) - int(d.g_nrm[prev[p]]) == best[p]) found = prev[p];
+                const uint2 ce = s_cen[prev[p]];
+                if (2 * dp4a_uu(px[p], ce.x, 0) - int(ce.y) == best[p]) found = prev[p];
             }
             idx[p] = (uint16_t)found;
             if (p < nv && idx[p] != prev[p]) { moved++; any_moved = true; }
+            if (p > 0 && idx[p] != idx[0]) uniform = false;
         }
         if (any_moved) {
             if (nv == PX) {
@@ -502,6 +565,7 @@ __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
                     if (p < nv) d.assign[base + p] = idx[p];
             }
         }
+        // ---- accumulate ----
         if (WEIGHTED) {
             unsigned long long ar = 0, ag = 0, ab = 0, aw = 0;
             int run = -1;
@@ -524,24 +588,46 @@ __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
                 atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
             }
         } else {
-            uint32_t ar = 0, ag = 0, ab = 0, aw = 0;
-            int run = -1;
+            // fast paths: the thread's 8 points (and often the whole warp's 256) fall into one cluster, because the
+            // points are colour sorted.  Channel sums come from the idle integer-dot pipe.
+            const int lead = __shfl_sync(0xffffffffu, (int)idx[0], 0);  // unconditional: every lane must reach the shuffle
+            const bool warp_uniform = __all_sync(0xffffffffu, uniform && (int)idx[0] == lead);
+            if (warp_uniform || uniform) {
+                int ar = 0, ag = 0, ab = 0;
 #pragma unroll
-            for (int p = 0; p < PX; p++) {
-                if (p < nv) {
-                    if (idx[p] != run) {
-                        if (run >= 0) {
-                            atomicAdd(&s_acc32[4 * run], ar); atomicAdd(&s_acc32[4 * run + 1], ag);
-                            atomicAdd(&s_acc32[4 * run + 2], ab); atomicAdd(&s_acc32[4 * run + 3], aw);
-                        }
-                        run = idx[p]; ar = ag = ab = aw = 0;
-                    }
-                    ar += px[p] & 0xff; ag += (px[p] >> 8) & 0xff; ab += (px[p] >> 16) & 0xff; aw += 1;
+                for (int p = 0; p < PX; p++) {
+                    ar = dp4a_uu(px[p], 0x00000001u, ar); ag = dp4a_uu(px[p], 0x00000100u, ag); ab = dp4a_uu(px[p], 0x00010000u, ab);
                 }
-            }
-            if (run >= 0) {
-                atomicAdd(&s_acc32[4 * run], ar); atomicAdd(&s_acc32[4 * run + 1], ag);
-                atomicAdd(&s_acc32[4 * run + 2], ab); atomicAdd(&s_acc32[4 * run + 3], aw);
+                if (warp_uniform) {
+                    ar = __reduce_add_sync(0xffffffffu, ar); ag = __reduce_add_sync(0xffffffffu, ag); ab = __reduce_add_sync(0xffffffffu, ab);
+                    if (lane == 0) {
+                        atomicAdd(&s_acc32[4 * idx[0]], (uint32_t)ar); atomicAdd(&s_acc32[4 * idx[0] + 1], (uint32_t)ag);
+                        atomicAdd(&s_acc32[4 * idx[0] + 2], (uint32_t)ab); atomicAdd(&s_acc32[4 * idx[0] + 3], 32u * PX);
+                    }
+                } else {
+                    atomicAdd(&s_acc32[4 * idx[0]], (uint32_t)ar); atomicAdd(&s_acc32[4 * idx[0] + 1], (uint32_t)ag);
+                    atomicAdd(&s_acc32[4 * idx[0] + 2], (uint32_t)ab); atomicAdd(&s_acc32[4 * idx[0] + 3], (uint32_t)PX);
+                }
+            } else {
+                uint32_t ar = 0, ag = 0, ab = 0, aw = 0;
+                int run = -1;
+#pragma unroll
+                for (int p = 0; p < PX; p++) {
+                    if (p < nv) {
+                        if (idx[p] != run) {
+                            if (run >= 0) {
+                                atomicAdd(&s_acc32[4 * run], ar); atomicAdd(&s_acc32[4 * run + 1], ag);
+                                atomicAdd(&s_acc32[4 * run + 2], ab); atomicAdd(&s_acc32[4 * run + 3], aw);
+                            }
+                            run = idx[p]; ar = ag = ab = aw = 0;
+                        }
+                        ar += px[p] & 0xff; ag += (px[p] >> 8) & 0xff; ab += (px[p] >> 16) & 0xff; aw += 1;
+                    }
+                }
+                if (run >= 0) {
+                    atomicAdd(&s_acc32[4 * run], ar); atomicAdd(&s_acc32[4 * run + 1], ag);
+                    atomicAdd(&s_acc32[4 * run + 2], ab); atomicAdd(&s_acc32[4 * run + 3], aw);
+                }
             }
         }
     }
@@ -968,7 +1054,7 @@ __global__ void km_init_assign(KmDev d) {
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < d.n_local;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long gi = d.first_index + (d.perm ? d.perm[i] : i);
-        d.assign[i] = gi >= head ? uint16_t((N - 1 - gi) / ppc) : uint16_t(d.k - 1);
+        d.assign[i] = gi >= head ? uint16_t(uint32_t(N - 1 - gi) / uint32_t(ppc)) : uint16_t(d.k - 1);  // N < 2^31
     }
 }
 
@@ -1166,6 +1252,7 @@ struct cniic_kmeans {
     static constexpr int PROF = 32;  // assign launches timed per run (CUDA events on the launching stream)
     cudaEvent_t pev[2 * PROF] = {};
     uint32_t launches = 0;
+    uint2 *d_boxes = nullptr;
     uint32_t *d_sorted = nullptr, *d_perm = nullptr, *d_wsorted = nullptr;  // colour-sorted copy (culled D = 3)
     uint16_t *d_assign_orig = nullptr;  // assignment mapped back to original order (filled on demand)
     bool cull = true;        // exact culling (CNIIC_KMEANS_NO_CULL in desc.flags selects brute force)
@@ -1302,16 +1389,26 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
         km->d_sorted = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (n + 8) * 4));
         km->d_perm = static_cast<uint32_t *>(cniic_cache_alloc(ctx, n * 4));
         if (d_wts) km->d_wsorted = static_cast<uint32_t *>(cniic_cache_alloc(ctx, n * 4));
-        uint32_t *d_bins = static_cast<uint32_t *>(cniic_cache_alloc(ctx, SORT_BINS * 4));
+        const int nctas = ctx->sm_count;  // one sorting CTA per SM (128 KB of shared memory each)
+        uint32_t *d_bins = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (size_t(nctas) + 1) * SORT_BINS * 4));
         if (!km->d_sorted || !km->d_perm || (d_wts && !km->d_wsorted) || !d_bins) return fail(CNIIC_ERR_CUDA);
-        KM_TRY(cudaMemsetAsync(d_bins, 0, SORT_BINS * 4, ctx->stream));
-        const int sgrid = (int)std::max<size_t>(1, std::min<size_t>((n + 1023) / 1024, (size_t)ctx->sm_count * 16));
-        km_sort_hist<<<sgrid, 256, 0, ctx->stream>>>(d_rgb, n, d_bins);
-        km_sort_scan<<<1, 1024, 0, ctx->stream>>>(d_bins);
-        km_sort_scatter<<<sgrid, 256, 0, ctx->stream>>>(d_rgb, d_wts, n, d_bins, km->d_sorted, km->d_perm, km->d_wsorted);
-        km->launches += 3;
+        const size_t ntiles = (n + TILE - 1) / TILE;
+        km->d_boxes = static_cast<uint2 *>(cniic_cache_alloc(ctx, ntiles * 8));
+        if (!km->d_boxes) return fail(CNIIC_ERR_CUDA);
+        uint32_t *d_tot = d_bins + size_t(nctas) * SORT_BINS;
+        KM_TRY(cudaFuncSetAttribute(km_sort_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_BINS * 4));
+        KM_TRY(cudaFuncSetAttribute(km_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_BINS * 4));
+        km_sort_hist<<<nctas, SORT_THREADS, SORT_BINS * 4, ctx->stream>>>(d_rgb, n, d_bins);
+        km_sort_totals<<<SORT_BINS / 1024, 1024, 0, ctx->stream>>>(d_bins, nctas, d_tot);
+        km_sort_scan<<<1, 1024, 0, ctx->stream>>>(d_tot);
+        km_sort_offsets<<<SORT_BINS / 1024, 1024, 0, ctx->stream>>>(d_bins, nctas, d_tot);
+        km_sort_scatter<<<nctas, SORT_THREADS, SORT_BINS * 4, ctx->stream>>>(d_rgb, d_wts, n, d_bins, km->d_sorted, km->d_perm, km->d_wsorted);
+        km_tile_boxes<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(km->d_sorted, n, km->d_boxes);
+        km->launches += 6;
+        ctx->launches += 6;
         KM_TRY(cudaGetLastError());
         cniic_cache_free(ctx, d_bins);  // stream-ordered reuse is safe
+        dv.tile_box = km->d_boxes;
         dv.pts_sorted = km->d_sorted;
         dv.perm = km->d_perm;
         dv.wts_sorted = km->d_wsorted;
@@ -1324,7 +1421,7 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
         km->smem = size_t(KP) * 16 + 8 * 192 * 4 + size_t(k) * 24 + KP * 2 + k * 2 + 16;
         KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     } else if (km->cull) {
-        km->smem = size_t(RCAP) * 16 + size_t(k) * 4 * (d_wts ? 8 : 4) + 16;
+        km->smem = size_t(RCAP) * 16 + size_t((k + 1) & ~1u) * 8 + size_t(k) * 4 * (d_wts ? 8 : 4) + 16;
         if (d_wts) KM_TRY(cudaFuncSetAttribute(km_assign_rgb_cull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
         else KM_TRY(cudaFuncSetAttribute(km_assign_rgb_cull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     } else {
@@ -1467,6 +1564,7 @@ extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
     cniic_cache_free(km->ctx, km->own_rgb);
     cniic_cache_free(km->ctx, km->own_wts);
     cniic_cache_free(km->ctx, km->pool);
+    cniic_cache_free(km->ctx, km->d_boxes);
     cniic_cache_free(km->ctx, km->d_sorted);
     cniic_cache_free(km->ctx, km->d_perm);
     cniic_cache_free(km->ctx, km->d_wsorted);
