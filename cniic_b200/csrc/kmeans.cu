@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "nccl_dyn.h"
+#include "sort.cuh"
 
 namespace {
 
@@ -295,135 +296,13 @@ __global__ void __launch_bounds__(THREADS) km_assign_rgb(KmDev d) {
 
 // ------------------------------------------------------------------------------------------------------------
 // D = 3 with EXACT culling on a colour-sorted copy of the points (default for the RGB path)
-//   Once per session the points are counting-sorted by a 15-bit Morton code of (r>>3, g>>3, b>>3), so a tile of 2048
-//   consecutive sorted points occupies a small colour box.  Per tile (CTA): U = min_c max-distance^2(c, box) bounds
+//   Once per session the points are sorted by the 24-bit Morton code of (r, g, b) (sort.cu), so a tile of 2048
+//   consecutive sorted points occupies a small colour box and a thread's 8 points usually share one cluster.  Per tile (CTA): U = min_c max-distance^2(c, box) bounds
 //   every point's minimum, only centroids with min-distance^2(c, box) <= U are scored (ascending id, strict ">" =
 //   lowest index; key = 2*(p.c) - |c|^2 is the exact integer order).  Sums are permutation invariant and the
 //   assignment is kept in sorted order (mapped back through `perm` on output), so results equal the brute-force
 //   kernel bit for bit.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int SORT_BINS = 32768;
-
-__device__ __forceinline__ uint32_t part1by2_5(uint32_t v) {
-    v &= 0x1f;
-    v = (v | (v << 8)) & 0x100f;
-    v = (v | (v << 4)) & 0x10c3;
-    v = (v | (v << 2)) & 0x1249;
-    return v;
-}
-__device__ __forceinline__ uint32_t colour_bucket(uint32_t r, uint32_t g, uint32_t b) {
-    return (part1by2_5(r >> 3) << 2) | (part1by2_5(g >> 3) << 1) | part1by2_5(b >> 3);
-}
-
-// Counting sort in three kernels, no global atomics: every CTA owns a contiguous chunk of the input.
-//   km_sort_hist    : per-CTA histogram in shared memory (32768 bins)            -> hist[cta][bucket]
-//   km_sort_offsets : per bucket, exclusive prefix over the CTAs + bucket start  -> hist[cta][bucket] = first slot
-//   km_sort_scatter : per-CTA cursors in shared memory hand out the slots
-constexpr int SORT_THREADS = 1024;
-
-__device__ __forceinline__ void sort_chunk(unsigned long long n, unsigned long long *lo, unsigned long long *hi) {
-    // chunk boundaries are multiples of 4 points (12 bytes) so that every thread can use aligned 32-bit loads
-    const unsigned long long per = ((n + gridDim.x - 1) / gridDim.x + 3) & ~3ull;
-    *lo = min(n, per * blockIdx.x);
-    *hi = min(n, *lo + per);
-}
-
-__global__ void __launch_bounds__(SORT_THREADS) km_sort_hist(const uint8_t *__restrict__ rgb, unsigned long long n, uint32_t *hist) {
-    extern __shared__ uint32_t s_bins[];
-    for (int i = threadIdx.x; i < SORT_BINS; i += SORT_THREADS) s_bins[i] = 0;
-    __syncthreads();
-    unsigned long long lo, hi;
-    sort_chunk(n, &lo, &hi);
-    const bool al = (reinterpret_cast<uintptr_t>(rgb) & 3) == 0;
-    for (unsigned long long i = lo + 4ull * threadIdx.x; i < hi; i += 4ull * SORT_THREADS) {
-        if (al && i + 4 <= hi) {  // 4 points = three aligned words
-            const uint32_t *q = reinterpret_cast<const uint32_t *>(rgb + i * 3);
-            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-            const uint32_t k0 = colour_bucket(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
-            const uint32_t k1 = colour_bucket(w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff);
-            const uint32_t k2 = colour_bucket((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
-            const uint32_t k3 = colour_bucket((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
-            if (k0 == k1 && k1 == k2 && k2 == k3) atomicAdd(&s_bins[k0], 4u);
-            else { atomicAdd(&s_bins[k0], 1u); atomicAdd(&s_bins[k1], 1u); atomicAdd(&s_bins[k2], 1u); atomicAdd(&s_bins[k3], 1u); }
-        } else {
-            for (unsigned long long j = i; j < min(i + 4, hi); j++) atomicAdd(&s_bins[colour_bucket(rgb[3 * j], rgb[3 * j + 1], rgb[3 * j + 2])], 1u);
-        }
-    }
-    __syncthreads();
-    uint32_t *out = hist + (size_t)blockIdx.x * SORT_BINS;
-    for (int i = threadIdx.x; i < SORT_BINS; i += SORT_THREADS) out[i] = s_bins[i];
-}
-
-// one thread per bucket: totals over CTAs, block scan of the totals (grid = 32 blocks x 1024 buckets, two phases)
-__global__ void __launch_bounds__(1024) km_sort_totals(const uint32_t *__restrict__ hist, int nctas, uint32_t *totals) {
-    const int b = blockIdx.x * 1024 + threadIdx.x;
-    uint32_t t = 0;
-    for (int c = 0; c < nctas; c++) t += hist[(size_t)c * SORT_BINS + b];
-    totals[b] = t;
-}
-
-__global__ void __launch_bounds__(1024) km_sort_scan(uint32_t *totals) {  // exclusive scan of SORT_BINS totals, in place
-    __shared__ uint32_t s_w[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t v[SORT_BINS / 1024], tot = 0;
-#pragma unroll
-    for (int j = 0; j < SORT_BINS / 1024; j++) { v[j] = totals[threadIdx.x * (SORT_BINS / 1024) + j]; tot += v[j]; }
-    uint32_t x = tot;
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-    }
-    if (lane == 31) s_w[warp] = x;
-    __syncthreads();
-    uint32_t before = 0;
-    for (int j = 0; j < warp; j++) before += s_w[j];
-    uint32_t run = before + x - tot;
-#pragma unroll
-    for (int j = 0; j < SORT_BINS / 1024; j++) { totals[threadIdx.x * (SORT_BINS / 1024) + j] = run; run += v[j]; }
-}
-
-__global__ void __launch_bounds__(1024) km_sort_offsets(uint32_t *hist, int nctas, const uint32_t *__restrict__ starts) {
-    const int b = blockIdx.x * 1024 + threadIdx.x;
-    uint32_t run = starts[b];
-    for (int c = 0; c < nctas; c++) {
-        const uint32_t v = hist[(size_t)c * SORT_BINS + b];
-        hist[(size_t)c * SORT_BINS + b] = run;
-        run += v;
-    }
-}
-
-__global__ void __launch_bounds__(SORT_THREADS) km_sort_scatter(const uint8_t *__restrict__ rgb, const uint32_t *__restrict__ wts, unsigned long long n,
-                                                                const uint32_t *__restrict__ hist, uint32_t *pts_sorted, uint32_t *perm,
-                                                                uint32_t *wts_sorted) {
-    extern __shared__ uint32_t s_cur[];
-    const uint32_t *mine = hist + (size_t)blockIdx.x * SORT_BINS;
-    for (int i = threadIdx.x; i < SORT_BINS; i += SORT_THREADS) s_cur[i] = mine[i];
-    __syncthreads();
-    unsigned long long lo, hi;
-    sort_chunk(n, &lo, &hi);
-    const bool al = (reinterpret_cast<uintptr_t>(rgb) & 3) == 0;
-    for (unsigned long long i = lo + 4ull * threadIdx.x; i < hi; i += 4ull * SORT_THREADS) {
-        uint32_t pk[4];
-        int cnt = (int)min((unsigned long long)4, hi - i);
-        if (al && cnt == 4) {
-            const uint32_t *q = reinterpret_cast<const uint32_t *>(rgb + i * 3);
-            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-            pk[0] = w0 & 0xffffff; pk[1] = (w0 >> 24) | ((w1 & 0xffff) << 8); pk[2] = (w1 >> 16) | ((w2 & 0xff) << 16); pk[3] = w2 >> 8;
-        } else {
-            for (int j = 0; j < 4; j++) {
-                pk[j] = 0;
-                if (j < cnt) { const uint8_t *q = rgb + (i + j) * 3; pk[j] = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16); }
-            }
-        }
-        for (int j = 0; j < cnt; j++) {
-            const uint32_t pos = atomicAdd(&s_cur[colour_bucket(pk[j] & 0xff, (pk[j] >> 8) & 0xff, pk[j] >> 16)], 1u);
-            pts_sorted[pos] = pk[j];
-            perm[pos] = (uint32_t)(i + j);
-            if (wts) wts_sorted[pos] = wts[i + j];
-        }
-    }
-}
-
 // bytewise min / max of the packed colours of every 2048-point tile of the sorted copy (static for the whole session)
 __global__ void __launch_bounds__(256) km_tile_boxes(const uint32_t *__restrict__ pts_sorted, unsigned long long n, uint2 *boxes) {
     __shared__ uint32_t s_mn[8], s_mx[8];
@@ -521,23 +400,30 @@ __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
                 const uint2 ce = s_cen[c];
                 const int cr = ce.x & 0xff, cg = (ce.x >> 8) & 0xff, cb = (ce.x >> 16) & 0xff;
                 keep = uint32_t(sq(max(0, max(r0 - cr, cr - r1))) + sq(max(0, max(g0 - cg, cg - g1))) + sq(max(0, max(b0 - cb, cb - b1)))) <= U;
-                ent = make_uint4(ce.x, uint32_t(-int(ce.y)), c, 0);
+                // packed score: (2*dot - |c|^2) * 4096 + (4095 - id)  ==  dot * 8192 + ent.y ; max() picks the best key, then the lowest id
+                ent = make_uint4(ce.x, uint32_t(-int(ce.y) * 4096 + 4095 - int(c)), c, 0);
             }
             uint32_t nt;
             const uint32_t r = block_rank256(keep, s_warp, &nt);
             if (keep) t_ent[r] = ent;
             __syncthreads();
             if (tid == 0) pairs_local += (unsigned long long)nt * min((unsigned long long)TILE, n - tile * TILE);
-            for (uint32_t e = 0; e < nt; e++) {
-                const uint4 ce = t_ent[e];
+            uint32_t e = 0;
+            for (; e + 2 <= nt; e += 2) {
+                const uint4 c0 = t_ent[e], c1 = t_ent[e + 1];
 #pragma unroll
-                for (int p = 0; p < PX; p++) {
-                    const int key = 2 * dp4a_uu(px[p], ce.x, 0) + int(ce.y);
-                    if (key > best[p]) { best[p] = key; bi[p] = int(ce.z); }
-                }
+                for (int p = 0; p < PX; p++)
+                    best[p] = max3i(best[p], dp4a_uu(px[p], c0.x, 0) * 8192 + int(c0.y), dp4a_uu(px[p], c1.x, 0) * 8192 + int(c1.y));
+            }
+            if (e < nt) {
+                const uint4 c0 = t_ent[e];
+#pragma unroll
+                for (int p = 0; p < PX; p++) best[p] = max(best[p], dp4a_uu(px[p], c0.x, 0) * 8192 + int(c0.y));
             }
             if (cb0 + RCAP < k) __syncthreads();
         }
+#pragma unroll
+        for (int p = 0; p < PX; p++) { bi[p] = 4095 - (best[p] & 4095); best[p] >>= 12; }  // unpack: id, exact key
 
         uint16_t idx[PX];
         bool any_moved = false, uniform = nv == PX;
@@ -1384,30 +1270,22 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
 
     km->cull = !(desc->flags & CNIIC_KMEANS_NO_CULL) && !getenv("CNIIC_NO_CULL");
     if (D == 3 && km->cull && desc->n_local) {
-        // colour-sorted copy of the points (counting sort by a 15-bit Morton bucket), built once per session
+        // colour-sorted copy of the points (Morton order), built once per session
         const size_t n = desc->n_local;
         km->d_sorted = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (n + 8) * 4));
         km->d_perm = static_cast<uint32_t *>(cniic_cache_alloc(ctx, n * 4));
         if (d_wts) km->d_wsorted = static_cast<uint32_t *>(cniic_cache_alloc(ctx, n * 4));
-        const int nctas = ctx->sm_count;  // one sorting CTA per SM (128 KB of shared memory each)
-        uint32_t *d_bins = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (size_t(nctas) + 1) * SORT_BINS * 4));
-        if (!km->d_sorted || !km->d_perm || (d_wts && !km->d_wsorted) || !d_bins) return fail(CNIIC_ERR_CUDA);
+        if (!km->d_sorted || !km->d_perm || (d_wts && !km->d_wsorted)) return fail(CNIIC_ERR_CUDA);
         const size_t ntiles = (n + TILE - 1) / TILE;
         km->d_boxes = static_cast<uint2 *>(cniic_cache_alloc(ctx, ntiles * 8));
         if (!km->d_boxes) return fail(CNIIC_ERR_CUDA);
-        uint32_t *d_tot = d_bins + size_t(nctas) * SORT_BINS;
-        KM_TRY(cudaFuncSetAttribute(km_sort_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_BINS * 4));
-        KM_TRY(cudaFuncSetAttribute(km_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_BINS * 4));
-        km_sort_hist<<<nctas, SORT_THREADS, SORT_BINS * 4, ctx->stream>>>(d_rgb, n, d_bins);
-        km_sort_totals<<<SORT_BINS / 1024, 1024, 0, ctx->stream>>>(d_bins, nctas, d_tot);
-        km_sort_scan<<<1, 1024, 0, ctx->stream>>>(d_tot);
-        km_sort_offsets<<<SORT_BINS / 1024, 1024, 0, ctx->stream>>>(d_bins, nctas, d_tot);
-        km_sort_scatter<<<nctas, SORT_THREADS, SORT_BINS * 4, ctx->stream>>>(d_rgb, d_wts, n, d_bins, km->d_sorted, km->d_perm, km->d_wsorted);
+        {
+            const int rc = cniic_dev_sort_colours(ctx, d_rgb, d_wts, n, km->d_sorted, km->d_perm, km->d_wsorted, &km->launches);
+            if (rc != CNIIC_OK) return fail(rc);
+        }
         km_tile_boxes<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(km->d_sorted, n, km->d_boxes);
-        km->launches += 6;
-        ctx->launches += 6;
+        km->launches += 1;
         KM_TRY(cudaGetLastError());
-        cniic_cache_free(ctx, d_bins);  // stream-ordered reuse is safe
         dv.tile_box = km->d_boxes;
         dv.pts_sorted = km->d_sorted;
         dv.perm = km->d_perm;

@@ -6,7 +6,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let csrc = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../../cniic_b200/csrc");
     let mut objs = Vec::new();
-    for name in ["api", "kmeans", "stages", "codec", "synth"] {
+    for name in ["api", "kmeans", "sort", "stages", "codec", "synth"] {
         let obj = out.join(format!("{name}.o"));
         let status = Command::new("nvcc")
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
