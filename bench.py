@@ -302,6 +302,11 @@ def main():
                "h2d_bytes_per_step": int(n_local * 3), "d2h_bytes_per_step": int(k * D * 4 + k * 8),
                "api": "cniic_kmeans_open/reset/run/get (row-sharded session, host points)"}
 
+    # the brute-force kernel (every pixel scores all k centroids) for reference: same results, no culling.
+    # Collective in the sharded case, so every rank runs it (before the non-zero ranks leave).
+    one_step(cb._lib.KMEANS_NO_CULL, 1)
+    stb = one_step(cb._lib.KMEANS_NO_CULL, 3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -327,9 +332,6 @@ def main():
                         "`brute_force_kernel` is the same Lloyd step with every pixel scoring all k centroids",
                 "hbm": {"achieved": bytes_per_launch / (a_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": bytes_per_launch / (a_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "source": pk["source"]}}
-    # the brute-force kernel (every pixel scores all k centroids) for reference: same results, no culling
-    one_step(cb._lib.KMEANS_NO_CULL, 1)
-    stb = one_step(cb._lib.KMEANS_NO_CULL, 3)
     ab = flops_alg / (stb.assign_ms_avg * 1e-3) / 1e12
     roofline["brute_force_kernel"] = {"kernel": "km_assign_rgb" if D == 3 else "km_assign_xyrgb", "launch_ms": stb.assign_ms_avg,
                                       "achieved": ab, "frac": ab / fp32_peak, "Mpx_iter_per_s": n_local / (stb.assign_ms_avg * 1e-3) / 1e6}
