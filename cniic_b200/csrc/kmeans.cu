@@ -1137,13 +1137,18 @@ struct cniic_kmeans {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     static constexpr int PROF = 32;  // assign launches timed per run (CUDA events on the launching stream)
     cudaEvent_t pev[2 * PROF] = {};
-    uint32_t launches = 0;
+    uint32_t launches = 0, launches_reported = 0;
     uint2 *d_boxes = nullptr;
     uint32_t *d_sorted = nullptr, *d_perm = nullptr, *d_wsorted = nullptr;  // colour-sorted copy (culled D = 3)
     uint16_t *d_assign_orig = nullptr;  // assignment mapped back to original order (filled on demand)
     bool cull = true;        // exact culling (CNIIC_KMEANS_NO_CULL in desc.flags selects brute force)
     uint32_t iter_seen = 0;  // state.iter at the end of the previous run (0 after reset)
 };
+
+static void km_report_launches(cniic_kmeans *km) {
+    km->ctx->launches += km->launches - km->launches_reported;
+    km->launches_reported = km->launches;
+}
 
 static int km_launch_assign(cniic_kmeans *km) {
     cniic_ctx *ctx = km->ctx;
@@ -1323,6 +1328,7 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     KM_TRY(cudaEventCreate(&km->ev1));
     for (int i = 0; i < 2 * cniic_kmeans::PROF; i++) KM_TRY(cudaEventCreate(&km->pev[i]));
 #undef KM_TRY
+    km_report_launches(km);
     *out = km;
     return CNIIC_OK;
 }
@@ -1346,7 +1352,9 @@ extern "C" int cniic_kmeans_reset(cniic_kmeans *km, const int32_t *host_init_cen
     }
     CU_TRY(ctx, cudaGetLastError());
     km->iter_seen = 0;
-    return km_launch_finalize(km, 1);
+    const int rc_fin = km_launch_finalize(km, 1);
+    km_report_launches(km);
+    return rc_fin;
 }
 
 extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmeans_stats *stats) {
@@ -1380,7 +1388,7 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
     CU_TRY(ctx, cudaEventSynchronize(km->ev1));
     float ms = 0.f;
     CU_TRY(ctx, cudaEventElapsedTime(&ms, km->ev0, km->ev1));
-    ctx->launches += km->launches - launches0;
+    km_report_launches(km);
     const KmState &s = *km->h_state;
     if (stats) {
         stats->iterations = s.iter;
@@ -1431,7 +1439,7 @@ extern "C" const uint16_t *cniic_kmeans_device_assign(cniic_kmeans *km) {
     km_unsort_assign<<<(int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16)), 256, 0, ctx->stream>>>(
         km->dev.assign, km->dev.perm, n, km->d_assign_orig);
     km->launches++;
-    ctx->launches++;
+    km_report_launches(km);
     return km->d_assign_orig;
 }
 
