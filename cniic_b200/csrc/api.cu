@@ -212,6 +212,8 @@ extern "C" void cniic_ctx_destroy(cniic_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cniic_nccl_destroy(ctx);
     for (cniic_ctx::Block &b : ctx->cache) cudaFree(b.p);
+    for (uint32_t *hb : ctx->hist_bins)
+        if (hb) cudaFree(hb);
     for (void *p : ctx->pinned_free) cudaFreeHost(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

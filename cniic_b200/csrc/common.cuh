@@ -30,6 +30,7 @@ struct cniic_ctx {
     struct Block { void *p; size_t bytes; bool used; };
     std::vector<Block> cache;
     std::vector<void *> pinned_free;  // 256-byte pinned host slots
+    uint32_t *hist_bins[2] = {nullptr, nullptr};  // persistent dense histogram bins (+ page flags), all zero between calls
 };
 
 void *cniic_cache_alloc(cniic_ctx *ctx, size_t bytes);  // nullptr + error set on failure

@@ -112,19 +112,24 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ 
 __device__ __forceinline__ uint32_t rgb_key(const uint8_t *p) { return (uint32_t(p[0]) << 16) | (uint32_t(p[1]) << 8) | p[2]; }
 
 // warp-aggregated atomic increment: lanes holding the same key elect a leader that adds the group's population
-__device__ __forceinline__ void warp_hist_add(uint32_t *bins, uint32_t key, bool valid) {
+// `flags` marks the 4096-bin pages that received a count, so compaction and re-zeroing touch only those pages.
+constexpr int PAGE_SHIFT = 12;
+__device__ __forceinline__ void warp_hist_add(uint32_t *bins, uint8_t *flags, uint32_t key, bool valid) {
     const uint32_t act = __ballot_sync(0xffffffffu, valid);
     if (!valid) return;
     const uint32_t peers = __match_any_sync(act, key);
-    if ((__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(&bins[key], (uint32_t)__popc(peers));
+    if ((__ffs(peers) - 1) == (threadIdx.x & 31)) {
+        // first touch of a bin marks its page (one flag store per distinct key instead of one per pixel)
+        if (atomicAdd(&bins[key], (uint32_t)__popc(peers)) == 0) flags[key >> PAGE_SHIFT] = 1;
+    }
 }
 
-__global__ void hist_rgb_kernel(const uint8_t *__restrict__ rgb, size_t n, uint32_t *bins) {
+__global__ void hist_rgb_kernel(const uint8_t *__restrict__ rgb, size_t n, uint32_t *bins, uint8_t *flags) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t n_round = (n + 31) / 32 * 32;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_round; i += stride) {
         const bool valid = i < n;
-        warp_hist_add(bins, valid ? rgb_key(rgb + 3 * i) : 0, valid);
+        warp_hist_add(bins, flags, valid ? rgb_key(rgb + 3 * i) : 0, valid);
     }
 }
 
@@ -188,6 +193,71 @@ __global__ void __launch_bounds__(256) compact_kernel(const uint32_t *__restrict
         if (v && pos + r < cap) { out_keys[pos + r] = (uint32_t)i; out_counts[pos + r] = v; }
         pos += tot;
     }
+}
+
+// ---- paged variant: the bins of the two key spaces live in the context for its whole life and are ALL ZERO between
+// calls; a histogram pass marks the pages it touched, compaction visits only those pages and zeroes them again.
+constexpr int PAGE = 1 << PAGE_SHIFT;
+
+__global__ void __launch_bounds__(1024) list_pages_kernel(const uint8_t *__restrict__ flags, uint32_t npages, uint32_t *list, uint32_t *count) {
+    __shared__ uint32_t s_w[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t placed = 0;
+    for (uint32_t base = 0; base < npages; base += 1024) {
+        const uint32_t pg = base + threadIdx.x;
+        const bool f = pg < npages && flags[pg];
+        const uint32_t bal = __ballot_sync(0xffffffffu, f);
+        __syncthreads();
+        if (lane == 0) s_w[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, tot = 0;
+        for (int i = 0; i < 32; i++) { const uint32_t v = s_w[i]; if (i < warp) before += v; tot += v; }
+        if (f) list[placed + before + __popc(bal & ((1u << lane) - 1))] = pg;
+        placed += tot;
+    }
+    if (threadIdx.x == 0) *count = placed;
+}
+
+__global__ void __launch_bounds__(256) page_count_kernel(const uint32_t *__restrict__ bins, size_t nbins, const uint32_t *__restrict__ list,
+                                                         const uint32_t *__restrict__ count, uint32_t *block_counts) {
+    if (blockIdx.x >= *count) { block_counts[blockIdx.x] = 0; return; }
+    const size_t base = (size_t)list[blockIdx.x] * PAGE;
+    uint32_t c = 0;
+    for (int j = 0; j < PAGE / 256; j++) {
+        const size_t i = base + (size_t)j * 256 + threadIdx.x;
+        if (i < nbins && bins[i]) c++;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    __shared__ uint32_t s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; i++) t += s[i];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) page_compact_kernel(uint32_t *bins, size_t nbins, const uint32_t *__restrict__ list, const uint32_t *__restrict__ count,
+                                                           const unsigned long long *__restrict__ offsets, uint8_t *flags, uint32_t *out_keys,
+                                                           unsigned long long *out_counts, size_t cap) {
+    __shared__ uint32_t s_warp[8];
+    if (blockIdx.x >= *count) return;
+    const uint32_t pg = list[blockIdx.x];
+    const size_t base = (size_t)pg * PAGE;
+    unsigned long long pos = offsets[blockIdx.x];
+    for (int j = 0; j < PAGE / 256; j++) {
+        const size_t i = base + (size_t)j * 256 + threadIdx.x;
+        const uint32_t v = i < nbins ? bins[i] : 0;
+        uint32_t tot;
+        const uint32_t r = block_rank256(v != 0, s_warp, &tot);
+        if (v) {
+            if (pos + r < cap) { out_keys[pos + r] = (uint32_t)i; out_counts[pos + r] = v; }
+            bins[i] = 0;  // restore the all-zero invariant
+        }
+        pos += tot;
+    }
+    if (threadIdx.x == 0) flags[pg] = 0;
 }
 
 // ============================================================================================================
@@ -303,7 +373,7 @@ __global__ void hilbert_xy_kernel(uint32_t w, uint32_t h, bool pow2, uint32_t *o
 // mode 0: gather rgb along the curve; mode 1: delta stream (i16 x 3); mode 2: delta histogram only (fused)
 template <int MODE>
 __global__ void hilbert_stream_kernel(const uint8_t *__restrict__ rgb, uint32_t w, uint32_t h, bool pow2, uint8_t *out_rgb,
-                                      int16_t *out_delta, uint32_t *bins) {
+                                      int16_t *out_delta, uint32_t *bins, uint8_t *flags) {
     const unsigned long long n = (unsigned long long)w * h;
     const unsigned long long n_round = (n + 31) / 32 * 32;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_round;
@@ -334,7 +404,7 @@ __global__ void hilbert_stream_kernel(const uint8_t *__restrict__ rgb, uint32_t 
             if (MODE == 1) {
                 if (valid) { out_delta[3 * i] = d0; out_delta[3 * i + 1] = d1; out_delta[3 * i + 2] = d2; }
             } else {
-                warp_hist_add(bins, valid ? uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255)) : 0, valid);
+                warp_hist_add(bins, flags, valid ? uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255)) : 0, valid);
             }
         }
     }
@@ -349,108 +419,151 @@ __global__ void hilbert_stream_kernel(const uint8_t *__restrict__ rgb, uint32_t 
 __constant__ uint8_t HIL4_X[16] = {0, 1, 1, 0, 0, 0, 1, 1, 2, 2, 3, 3, 3, 2, 2, 3};
 __constant__ uint8_t HIL4_Y[16] = {0, 0, 1, 1, 2, 3, 3, 2, 2, 3, 3, 2, 1, 1, 0, 0};
 
+constexpr int HASH_BITS = 12, HASH_SLOTS = 1 << HASH_BITS;  // block-local symbol table of the fused histogram
 constexpr int HT = 64;            // block side
 constexpr int HT_STRIDE = 208;    // bytes per staged row (192 + pad, multiple of 16)
 
+constexpr int CUBE_R = 15, CUBE_S = 2 * CUBE_R + 1, CUBE_N = CUBE_S * CUBE_S * CUBE_S;  // 31^3 near-zero delta symbols
+constexpr int CUBE_FLUSH_TILES = 12;  // 12 * 4096 symbols < 2^16: the packed u16 counters cannot overflow
+
 template <int MODE>
 __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__restrict__ rgb, uint32_t n, uint8_t *out_rgb,
-                                                           int16_t *out_delta, uint32_t *bins) {
+                                                           int16_t *out_delta, uint32_t *bins, uint8_t *flags) {
+    extern __shared__ uint32_t s_cube[];  // MODE 2 only: CUBE_N packed u16 counters for the near-zero symbols
     __shared__ __align__(16) uint8_t s_px[HT * HT_STRIDE];
     __shared__ uint32_t s_last[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned long long B = (unsigned long long)blockIdx.x * 4096;
-    const unsigned long long i0 = B + (unsigned long long)tid * 16;
-    // fold levels 2..L-1 into (ax, sx, ay, sy, swapped)
-    int ax = 0, ay = 0, sx = 1, sy = 1;
-    bool swapped = false;
-    {
-        unsigned long long t = i0 >> 4;
-        for (uint32_t sft = 4; sft < n; sft <<= 1) {
-            const int sl = (int)sft;
-            const uint32_t rx = 1u & (uint32_t)(t >> 1), ry = 1u & ((uint32_t)t ^ rx);
-            if (ry == 0) {
-                if (rx == 1) {
-                    const int nax = sl - 1 - ay, nsx = -sy, nay = sl - 1 - ax, nsy = -sx;
-                    ax = nax; sx = nsx; ay = nay; sy = nsy;
-                } else {
-                    const int tx = ax, tsx = sx;
-                    ax = ay; sx = sy; ay = tx; sy = tsx;
+    const unsigned long long nblocks = (unsigned long long)n * n / 4096;
+    if (MODE == 2) {
+        for (int i = tid; i < (CUBE_N + 1) / 2; i += 256) s_cube[i] = 0;
+    }
+    int since_flush = 0;
+    for (unsigned long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const unsigned long long B = blk * 4096;
+        const unsigned long long i0 = B + (unsigned long long)tid * 16;
+        // fold levels 2..L-1 into (ax, sx, ay, sy, swapped)
+        int ax = 0, ay = 0, sx = 1, sy = 1;
+        bool swapped = false;
+        {
+            unsigned long long t = i0 >> 4;
+            for (uint32_t sft = 4; sft < n; sft <<= 1) {
+                const int sl = (int)sft;
+                const uint32_t rx = 1u & (uint32_t)(t >> 1), ry = 1u & ((uint32_t)t ^ rx);
+                if (ry == 0) {
+                    if (rx == 1) {
+                        const int nax = sl - 1 - ay, nsx = -sy, nay = sl - 1 - ax, nsy = -sx;
+                        ax = nax; sx = nsx; ay = nay; sy = nsy;
+                    } else {
+                        const int tx = ax, tsx = sx;
+                        ax = ay; sx = sy; ay = tx; sy = tsx;
+                    }
+                    swapped = !swapped;
                 }
-                swapped = !swapped;
+                ax += sl * (int)rx;
+                ay += sl * (int)ry;
+                t >>= 2;
             }
-            ax += sl * (int)rx;
-            ay += sl * (int)ry;
-            t >>= 2;
         }
-    }
-    const int u0 = swapped ? HIL4_Y[0] : HIL4_X[0], v0 = swapped ? HIL4_X[0] : HIL4_Y[0];
-    const int X0 = (ax + sx * u0) & ~(HT - 1), Y0 = (ay + sy * v0) & ~(HT - 1);
-    // stage the 64x64 block: 64 rows x 12 uint4
-    for (int idx = tid; idx < HT * 12; idx += 256) {
-        const int r = idx / 12, c = idx % 12;
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rgb + ((size_t)(Y0 + r) * n + X0) * 3) + c);
-        *reinterpret_cast<uint4 *>(s_px + r * HT_STRIDE + c * 16) = v;
-    }
-    __syncthreads();
-    uint32_t pix[16];
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const int u = swapped ? HIL4_Y[j] : HIL4_X[j], v = swapped ? HIL4_X[j] : HIL4_Y[j];
-        const int lx = (ax + sx * u) - X0, ly = (ay + sy * v) - Y0;
-        const uint8_t *q = s_px + ly * HT_STRIDE + lx * 3;
-        pix[j] = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
-    }
-    if (MODE == 0) {
-        uint32_t wd[12];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {  // 4 pixels -> 3 words
-            const uint32_t a = pix[4 * q], b = pix[4 * q + 1], c = pix[4 * q + 2], e = pix[4 * q + 3];
-            wd[3 * q] = a | (b << 24);
-            wd[3 * q + 1] = (b >> 8) | (c << 16);
-            wd[3 * q + 2] = (c >> 16) | (e << 8);
+        const int u0 = swapped ? HIL4_Y[0] : HIL4_X[0], v0 = swapped ? HIL4_X[0] : HIL4_Y[0];
+        const int X0 = (ax + sx * u0) & ~(HT - 1), Y0 = (ay + sy * v0) & ~(HT - 1);
+        __syncthreads();  // previous block is done with s_px / s_last
+        // stage the 64x64 block: 64 rows x 12 uint4
+        for (int idx = tid; idx < HT * 12; idx += 256) {
+            const int r = idx / 12, c = idx % 12;
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rgb + ((size_t)(Y0 + r) * n + X0) * 3) + c);
+            *reinterpret_cast<uint4 *>(s_px + r * HT_STRIDE + c * 16) = v;
         }
-        uint4 *o = reinterpret_cast<uint4 *>(out_rgb + i0 * 3);
-        o[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-        o[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
-        o[2] = make_uint4(wd[8], wd[9], wd[10], wd[11]);
-        return;
-    }
-    // predecessor of this thread's first symbol
-    uint32_t prev = __shfl_up_sync(0xffffffffu, pix[15], 1);
-    if (lane == 31) s_last[warp] = pix[15];
-    __syncthreads();
-    if (lane == 0) {
-        if (warp > 0) prev = s_last[warp - 1];
-        else if (B == 0) prev = 0;  // hilbertc.rs:445 START = [0;3]
-        else {
-            uint32_t px, py;
-            hilbert_d2xy_pow2(n, B - 1, &px, &py);
-            const uint8_t *q = rgb + ((size_t)py * n + px) * 3;
-            prev = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
-        }
-    }
-    if (MODE == 1) {
-        uint32_t wd[24];  // 48 i16 packed two per word
-        int16_t dl[48];
+        __syncthreads();
+        uint32_t pix[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-            const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
-            dl[3 * j] = (int16_t)(int(c & 0xff) - int(p & 0xff));
-            dl[3 * j + 1] = (int16_t)(int((c >> 8) & 0xff) - int((p >> 8) & 0xff));
-            dl[3 * j + 2] = (int16_t)(int((c >> 16) & 0xff) - int((p >> 16) & 0xff));
+            const int u = swapped ? HIL4_Y[j] : HIL4_X[j], v = swapped ? HIL4_X[j] : HIL4_Y[j];
+            const int lx = (ax + sx * u) - X0, ly = (ay + sy * v) - Y0;
+            const uint8_t *q = s_px + ly * HT_STRIDE + lx * 3;
+            pix[j] = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
         }
+        if (MODE == 0) {
+            uint32_t wd[12];
 #pragma unroll
-        for (int q = 0; q < 24; q++) wd[q] = uint32_t(uint16_t(dl[2 * q])) | (uint32_t(uint16_t(dl[2 * q + 1])) << 16);
-        uint4 *o = reinterpret_cast<uint4 *>(out_delta + i0 * 3);
+            for (int q = 0; q < 4; q++) {  // 4 pixels -> 3 words
+                const uint32_t a = pix[4 * q], b = pix[4 * q + 1], c = pix[4 * q + 2], e = pix[4 * q + 3];
+                wd[3 * q] = a | (b << 24);
+                wd[3 * q + 1] = (b >> 8) | (c << 16);
+                wd[3 * q + 2] = (c >> 16) | (e << 8);
+            }
+            uint4 *o = reinterpret_cast<uint4 *>(out_rgb + i0 * 3);
+            o[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            o[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+            o[2] = make_uint4(wd[8], wd[9], wd[10], wd[11]);
+            continue;
+        }
+        // predecessor of this thread's first symbol
+        uint32_t prev = __shfl_up_sync(0xffffffffu, pix[15], 1);
+        if (lane == 31) s_last[warp] = pix[15];
+        __syncthreads();
+        if (lane == 0) {
+            if (warp > 0) prev = s_last[warp - 1];
+            else if (B == 0) prev = 0;  // hilbertc.rs:445 START = [0;3]
+            else {
+                uint32_t px, py;
+                hilbert_d2xy_pow2(n, B - 1, &px, &py);
+                const uint8_t *q = rgb + ((size_t)py * n + px) * 3;
+                prev = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+            }
+        }
+        if (MODE == 1) {
+            uint32_t wd[24];  // 48 i16 packed two per word
+            int16_t dl[48];
 #pragma unroll
-        for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
-    } else {
+            for (int j = 0; j < 16; j++) {
+                const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
+                dl[3 * j] = (int16_t)(int(c & 0xff) - int(p & 0xff));
+                dl[3 * j + 1] = (int16_t)(int((c >> 8) & 0xff) - int((p >> 8) & 0xff));
+                dl[3 * j + 2] = (int16_t)(int((c >> 16) & 0xff) - int((p >> 16) & 0xff));
+            }
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
-            const int d0 = int(c & 0xff) - int(p & 0xff), d1 = int((c >> 8) & 0xff) - int((p >> 8) & 0xff),
-                      d2 = int((c >> 16) & 0xff) - int((p >> 16) & 0xff);
-            warp_hist_add(bins, uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255)), true);
+            for (int q = 0; q < 24; q++) wd[q] = uint32_t(uint16_t(dl[2 * q])) | (uint32_t(uint16_t(dl[2 * q + 1])) << 16);
+            uint4 *o = reinterpret_cast<uint4 *>(out_delta + i0 * 3);
+#pragma unroll
+            for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
+        } else {
+            // near-zero symbols (|d| <= 15 per channel, the bulk of any natural image) are counted in shared memory
+            // (packed u16 counters, plain ATOMS); the rest goes to the global bins directly
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
+                const int d0 = int(c & 0xff) - int(p & 0xff), d1 = int((c >> 8) & 0xff) - int((p >> 8) & 0xff),
+                          d2 = int((c >> 16) & 0xff) - int((p >> 16) & 0xff);
+                if ((unsigned)(d0 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d1 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d2 + CUBE_R) < (unsigned)CUBE_S) {
+                    const int ci = ((d0 + CUBE_R) * CUBE_S + (d1 + CUBE_R)) * CUBE_S + (d2 + CUBE_R);
+                    atomicAdd(&s_cube[ci >> 1], 1u << (16 * (ci & 1)));
+                } else {
+                    const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                    atomicAdd(&bins[key], 1u);
+                    if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
+                }
+            }
+            if (++since_flush == CUBE_FLUSH_TILES || blk + gridDim.x >= nblocks) {
+                __syncthreads();
+                for (int i = tid; i < (CUBE_N + 1) / 2; i += 256) {
+                    const uint32_t v = s_cube[i];
+                    if (v) {
+                        s_cube[i] = 0;
+#pragma unroll
+                        for (int hlf = 0; hlf < 2; hlf++) {
+                            const uint32_t cnt = (v >> (16 * hlf)) & 0xffff;
+                            if (cnt) {
+                                const int ci = 2 * i + hlf;
+                                const int d2 = ci % CUBE_S - CUBE_R, d1 = (ci / CUBE_S) % CUBE_S - CUBE_R, d0 = ci / (CUBE_S * CUBE_S) - CUBE_R;
+                                const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                                atomicAdd(&bins[key], cnt);
+                                if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
+                            }
+                        }
+                    }
+                }
+                since_flush = 0;
+            }
         }
     }
 }
@@ -556,38 +669,58 @@ inline bool is_pow2_square(uint32_t w, uint32_t h) { return w == h && (w & (w - 
 
 // ---- device-level building blocks (declared in stages.cuh) -----------------------------------------------------
 
-int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins, size_t nbins, uint32_t **d_keys, unsigned long long **d_counts, size_t *n_unique) {
-    const size_t nblocks = (nbins + CB - 1) / CB;
-    uint32_t *d_bc = nullptr;
-    unsigned long long *d_off = nullptr;
-    if (!(d_bc = static_cast<decltype(d_bc)>(cniic_cache_alloc(ctx, nblocks * 4)))) return CNIIC_ERR_CUDA;
-    if (!(d_off = static_cast<decltype(d_off)>(cniic_cache_alloc(ctx, (nblocks + 1) * 8)))) return CNIIC_ERR_CUDA;
-    count_nonzero_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_bins, nbins, d_bc);
-    scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(d_bc, nblocks, d_off);
-    ctx->launches += 2;
-    unsigned long long total = 0;
-    CU_TRY(ctx, cudaMemcpyAsync(&total, d_off + nblocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    *n_unique = (size_t)total;
+// persistent, all-zero-between-calls bins of a key space (kind 0: 2^24 colours, kind 1: 511^3 delta symbols)
+static int hist_space(cniic_ctx *ctx, int kind, uint32_t **bins, uint8_t **flags, size_t *nbins) {
+    *nbins = kind == 0 ? (size_t(1) << 24) : (size_t)511 * 511 * 511;
+    const size_t npages = (*nbins + PAGE - 1) / PAGE;
+    if (!ctx->hist_bins[kind]) {
+        void *p = nullptr;
+        CU_TRY(ctx, cudaMalloc(&p, *nbins * 4 + npages + 16));
+        CU_TRY(ctx, cudaMemsetAsync(p, 0, *nbins * 4 + npages + 16, ctx->stream));
+        ctx->hist_bins[kind] = static_cast<uint32_t *>(p);
+    }
+    *bins = ctx->hist_bins[kind];
+    *flags = reinterpret_cast<uint8_t *>(*bins + *nbins);
+    return CNIIC_OK;
+}
+
+int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins_in, size_t nbins, uint32_t **d_keys, unsigned long long **d_counts, size_t *n_unique) {
+    const int kind = d_bins_in == ctx->hist_bins[0] ? 0 : 1;
+    uint32_t *bins;
+    uint8_t *flags;
+    ST_TRY(hist_space(ctx, kind, &bins, &flags, &nbins));
+    const uint32_t npages = (uint32_t)((nbins + PAGE - 1) / PAGE);
     *d_keys = nullptr;
     *d_counts = nullptr;
-    if (!(*d_keys = static_cast<std::remove_reference<decltype(*d_keys)>::type>(cniic_cache_alloc(ctx, std::max<size_t>(16, total * 4))))) return CNIIC_ERR_CUDA;
-    if (!(*d_counts = static_cast<std::remove_reference<decltype(*d_counts)>::type>(cniic_cache_alloc(ctx, std::max<size_t>(16, total * 8))))) return CNIIC_ERR_CUDA;
-    compact_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_bins, nbins, d_off, *d_keys, *d_counts, total);
+    DevBuf list(ctx), bc(ctx), off(ctx);
+    CU_TRY(ctx, list.alloc((size_t(npages) + 1) * 4));
+    CU_TRY(ctx, bc.alloc(size_t(npages) * 4));
+    CU_TRY(ctx, off.alloc((size_t(npages) + 1) * 8));
+    uint32_t *d_count = list.as<uint32_t>() + npages;
+    list_pages_kernel<<<1, 1024, 0, ctx->stream>>>(flags, npages, list.as<uint32_t>(), d_count);
+    page_count_kernel<<<npages, 256, 0, ctx->stream>>>(bins, nbins, list.as<uint32_t>(), d_count, bc.as<uint32_t>());
+    scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(bc.as<uint32_t>(), npages, off.as<unsigned long long>());
+    ctx->launches += 3;
+    unsigned long long total = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&total, off.as<unsigned long long>() + npages, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_unique = (size_t)total;
+    if (!(*d_keys = static_cast<uint32_t *>(cniic_cache_alloc(ctx, std::max<size_t>(16, total * 4))))) return CNIIC_ERR_CUDA;
+    if (!(*d_counts = static_cast<unsigned long long *>(cniic_cache_alloc(ctx, std::max<size_t>(16, total * 8))))) return CNIIC_ERR_CUDA;
+    page_compact_kernel<<<npages, 256, 0, ctx->stream>>>(bins, nbins, list.as<uint32_t>(), d_count, off.as<unsigned long long>(), flags, *d_keys,
+                                                         *d_counts, total);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cniic_cache_free(ctx, d_bc);
-    cniic_cache_free(ctx, d_off);
     return CNIIC_OK;
 }
 
 int cniic_dev_hist_rgb_bins(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t **d_bins) {
-    *d_bins = nullptr;
-    if (!(*d_bins = static_cast<std::remove_reference<decltype(*d_bins)>::type>(cniic_cache_alloc(ctx, (size_t(1) << 24) * 4)))) return CNIIC_ERR_CUDA;
-    CU_TRY(ctx, cudaMemsetAsync(*d_bins, 0, (size_t(1) << 24) * 4, ctx->stream));
+    uint8_t *flags;
+    size_t nbins;
+    ST_TRY(hist_space(ctx, 0, d_bins, &flags, &nbins));
     if (n) {
-        hist_rgb_kernel<<<grid_for(ctx, n, 4), 256, 0, ctx->stream>>>(d_rgb, n, *d_bins);
+        hist_rgb_kernel<<<grid_for(ctx, n, 4), 256, 0, ctx->stream>>>(d_rgb, n, *d_bins, flags);
         ctx->launches++;
     }
     CU_TRY(ctx, cudaGetLastError());
@@ -624,24 +757,27 @@ static inline bool tile_path(const void *in, const void *out, uint32_t w, uint32
 
 int cniic_dev_hilbert_gather(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint8_t *d_out) {
     if (tile_path(d_rgb, d_out, w, h)) {
-        hilbert_tile_kernel<0><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, d_out, nullptr, nullptr);
+        hilbert_tile_kernel<0><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, d_out, nullptr, nullptr, nullptr);
         ctx->launches++;
         CU_TRY(ctx, cudaGetLastError());
         return CNIIC_OK;
     }
-    hilbert_stream_kernel<0><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), d_out, nullptr, nullptr);
+    hilbert_stream_kernel<0><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), d_out, nullptr, nullptr, nullptr);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
 }
 
 int cniic_dev_hist_delta_bins(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint32_t **d_bins, size_t *nbins) {
-    *nbins = (size_t)511 * 511 * 511;
-    *d_bins = nullptr;
-    if (!(*d_bins = static_cast<std::remove_reference<decltype(*d_bins)>::type>(cniic_cache_alloc(ctx, *nbins * 4)))) return CNIIC_ERR_CUDA;
-    CU_TRY(ctx, cudaMemsetAsync(*d_bins, 0, *nbins * 4, ctx->stream));
-    if (tile_path(d_rgb, nullptr, w, h)) hilbert_tile_kernel<2><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, nullptr, nullptr, *d_bins);
-    else hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins);
+    uint8_t *flags;
+    ST_TRY(hist_space(ctx, 1, d_bins, &flags, nbins));
+    if (tile_path(d_rgb, nullptr, w, h)) {
+        const size_t smem = ((CUBE_N + 1) / 2) * 4;
+        CU_TRY(ctx, cudaFuncSetAttribute(hilbert_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)std::min<size_t>((size_t)w * h / 4096, (size_t)ctx->sm_count * 3);
+        hilbert_tile_kernel<2><<<grid, 256, smem, ctx->stream>>>(d_rgb, w, nullptr, nullptr, *d_bins, flags);
+    }
+    else hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins, flags);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
@@ -776,12 +912,12 @@ int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uin
     std::vector<int32_t> cen(size_t(k) * 3);
     if (rc == CNIIC_OK) rc = cniic_kmeans_get(km, cen.data(), wts.data(), nullptr);
     if (rc == CNIIC_OK) {
-        // the histogram bins are dead now: reuse them as the colour -> centroid colour lookup table
-        DevBuf dcen(ctx);
-        if (dcen.alloc(cen.size() * 4) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc failed");
+        // colour -> centroid colour lookup table (every colour that occurs is written before it is read)
+        DevBuf dcen(ctx), dlut(ctx);
+        if (dcen.alloc(cen.size() * 4) != cudaSuccess || dlut.alloc((size_t(1) << 24) * 4) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc failed");
         if (rc == CNIIC_OK) {
             cudaMemcpyAsync(dcen.p, cen.data(), cen.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
-            rc = cniic_dev_recolor(ctx, d_rgb, n, d_keys, cniic_kmeans_device_assign(km), u, dcen.as<int32_t>(), nullptr, d_bins, d_out);
+            rc = cniic_dev_recolor(ctx, d_rgb, n, d_keys, cniic_kmeans_device_assign(km), u, dcen.as<int32_t>(), nullptr, dlut.as<uint32_t>(), d_out);
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "recolour failed");
         }
     }
@@ -865,8 +1001,8 @@ extern "C" int cniic_delta_i16_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint
     if ((size_t)w * h == 0) return CNIIC_OK;
     if (!d_rgb || !d_out) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    if (tile_path(d_rgb, d_out, w, h)) hilbert_tile_kernel<1><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, nullptr, d_out, nullptr);
-    else hilbert_stream_kernel<1><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, d_out, nullptr);
+    if (tile_path(d_rgb, d_out, w, h)) hilbert_tile_kernel<1><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, nullptr, d_out, nullptr, nullptr);
+    else hilbert_stream_kernel<1><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, d_out, nullptr, nullptr);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
