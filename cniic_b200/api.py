@@ -69,6 +69,17 @@ class Context:
             raise CniicError(rc, "ncclGetUniqueId failed")
         return bytes(buf)
 
+    def p2p_export(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of this rank's exchange region for the peer-memory all-reduce."""
+        buf = (C.c_uint8 * 64)()
+        self.check(self._lib.cniic_ctx_p2p_export(self.h, buf))
+        return bytes(buf)
+
+    def p2p_connect(self, handles: bytes):
+        """handles = world x 64 bytes in rank order (every rank's p2p_export())."""
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self.check(self._lib.cniic_ctx_p2p_connect(self.h, buf))
+
     def close(self):
         if getattr(self, "h", None):
             self._lib.cniic_ctx_destroy(self.h)

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "nccl_dyn.h"
@@ -161,6 +162,47 @@ int cniic_nccl_allgather_bytes(cniic_ctx *ctx, const void *d_send, void *d_recv,
     return CNIIC_OK;
 }
 
+// ---- peer-memory exchange region (CUDA IPC between the per-GPU processes) ---------------------------------------------------
+static const size_t P2P_SUMS_MAX_HOST = CNIIC_MAX_K * 6 + 8;
+static const size_t P2P_REGION_BYTES = 2 * P2P_SUMS_MAX_HOST * 8 + 4096;  // two ping-pong buffers + arrival flags
+
+extern "C" int cniic_ctx_p2p_export(cniic_ctx *ctx, uint8_t out_handle[64]) {
+    if (!ctx || !out_handle) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->p2p_local) {
+        void *p = nullptr;
+        CU_TRY(ctx, cudaMalloc(&p, P2P_REGION_BYTES));
+        CU_TRY(ctx, cudaMemset(p, 0, P2P_REGION_BYTES));
+        ctx->p2p_local = static_cast<unsigned long long *>(p);
+    }
+    cudaIpcMemHandle_t h;
+    CU_TRY(ctx, cudaIpcGetMemHandle(&h, ctx->p2p_local));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out_handle, &h, 64);
+    return CNIIC_OK;
+}
+
+extern "C" int cniic_ctx_p2p_connect(cniic_ctx *ctx, const uint8_t *handles /* world x 64 */) {
+    if (!ctx || !handles || !ctx->p2p_local) return CNIIC_ERR_BAD_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<unsigned long long *> bases(ctx->world);
+    for (int r = 0; r < ctx->world; r++) {
+        if (r == ctx->rank) { bases[r] = ctx->p2p_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * r, 64);
+        void *p = nullptr;
+        CU_TRY(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->p2p_opened.push_back(p);
+        bases[r] = static_cast<unsigned long long *>(p);
+    }
+    void *tab = nullptr;
+    CU_TRY(ctx, cudaMalloc(&tab, sizeof(void *) * ctx->world));
+    CU_TRY(ctx, cudaMemcpy(tab, bases.data(), sizeof(void *) * ctx->world, cudaMemcpyHostToDevice));
+    ctx->p2p_peer_table = static_cast<unsigned long long **>(tab);
+    ctx->p2p_ready = true;
+    return CNIIC_OK;
+}
+
 // ---- context ---------------------------------------------------------------------------------------------------
 extern "C" int cniic_version(void) { return 100; }
 
@@ -214,6 +256,9 @@ extern "C" void cniic_ctx_destroy(cniic_ctx *ctx) {
     for (cniic_ctx::Block &b : ctx->cache) cudaFree(b.p);
     for (uint32_t *hb : ctx->hist_bins)
         if (hb) cudaFree(hb);
+    for (void *p : ctx->p2p_opened) cudaIpcCloseMemHandle(p);
+    if (ctx->p2p_peer_table) cudaFree(ctx->p2p_peer_table);
+    if (ctx->p2p_local) cudaFree(ctx->p2p_local);
     for (void *p : ctx->pinned_free) cudaFreeHost(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -30,6 +30,12 @@ struct cniic_ctx {
     struct Block { void *p; size_t bytes; bool used; };
     std::vector<Block> cache;
     std::vector<void *> pinned_free;  // 256-byte pinned host slots
+    // peer-memory exchange (multi-GPU): my IPC region, the peer-mapped bases of all ranks (device table), sequence number
+    unsigned long long *p2p_local = nullptr;
+    unsigned long long **p2p_peer_table = nullptr;  // device array [world]
+    std::vector<void *> p2p_opened;
+    bool p2p_ready = false;
+    uint32_t p2p_seq = 0;
     uint32_t *hist_bins[2] = {nullptr, nullptr};  // persistent dense histogram bins (+ page flags), all zero between calls
 };
 

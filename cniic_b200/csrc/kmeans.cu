@@ -36,6 +36,7 @@ constexpr int TILE = THREADS * PX;
 constexpr int DUMMY3 = -(1 << 19);  // bias of padding entries, D = 3 (real scores > -97538)
 constexpr int DUMMY5 = -(1 << 29);  // bias of padding entries, D = 5 (real scores > -2.7e8)
 constexpr int GSHIFT = 10;          // D = 3: bits of the group field packed under the key
+constexpr uint32_t P2P_SUMS_MAX = CNIIC_MAX_K * 6 + 8;  // u64 slots per ping-pong buffer of the exchange region
 constexpr int FLUSH_TILES = 64;     // D = 5: flush u32 shared accumulators to global every 64 tiles
 
 struct KmState {
@@ -76,6 +77,13 @@ struct KmDev {
     const uint32_t *pts_sorted;
     const uint32_t *perm;
     const uint32_t *wts_sorted;
+    // peer-memory all-reduce fused into km_finalize (multi-GPU, one process per GPU)
+    int p2p;                                   // 1: sums live in the IPC exchange region, no NCCL call
+    int my_rank;
+    uint32_t seq;                              // global iteration sequence number of this launch
+    unsigned long long *const *peer_base;      // [world] base of every rank's exchange region (peer-mapped)
+    unsigned long long *sums_other;            // my other ping-pong buffer (zeroed here for the next iteration)
+    unsigned long long *sums_red;              // local reduced sums the rest of finalize reads
     const uint2 *tile_box;  // per 2048-point tile of the sorted copy: {bytewise min, bytewise max} of the packed colours
     unsigned long long *sums;  // k*(D+1) partial sums + 1 moved counter
     int32_t *cen;              // k*D
@@ -987,19 +995,47 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
     const int tid = threadIdx.x;
     unsigned long long moved = 0;
 
+    const unsigned long long *rs = d.sums;
+    if (!init_mode && d.p2p) {
+        // ---- all-reduce over peer memory: publish, wait for every rank, sum the partials in rank order ----
+        // The assign kernel of this iteration has completed (stream order), so my partial sums are in my exchange buffer.
+        volatile uint32_t *arrived = reinterpret_cast<volatile uint32_t *>(d.peer_base[d.my_rank] + 2 * P2P_SUMS_MAX);
+        if (tid < d.world) {
+            __threadfence_system();
+            volatile uint32_t *remote = reinterpret_cast<volatile uint32_t *>(d.peer_base[tid] + 2 * P2P_SUMS_MAX);
+            remote[d.my_rank] = d.seq;  // push my arrival into every rank's flag array (NVLink store)
+            unsigned long long spins = 0;
+            while (int(arrived[tid] - d.seq) < 0) {
+                if (++spins > (1ull << 25)) { d.st->dist_empty = 2; break; }  // never hang the GPU: report and carry on
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        const uint32_t len = k * DW + 1;
+        const size_t boff = size_t(d.seq & 1) * P2P_SUMS_MAX;
+        for (uint32_t i = tid; i < len; i += 1024) {
+            unsigned long long acc = 0;
+            for (int r = 0; r < d.world; r++) acc += __ldcv(d.peer_base[r] + boff + i);  // fixed order: deterministic
+            d.sums_red[i] = acc;
+        }
+        // every rank has passed iteration seq-1, so nobody reads my other buffer any more: clear it for iteration seq+1
+        for (uint32_t i = tid; i < P2P_SUMS_MAX; i += 1024) d.sums_other[i] = 0ull;
+        __syncthreads();
+        rs = d.sums_red;
+    }
     if (!init_mode) {
         if (tid == 0) s_nempty = 0;
         __syncthreads();
         for (uint32_t c = tid; c < k; c += 1024) {
-            const unsigned long long wsum = d.sums[c * DW + D];
+            const unsigned long long wsum = rs[c * DW + D];
             d.weights[c] = wsum;
             if (wsum) {
-                for (int j = 0; j < D; j++) d.cen[c * D + j] = int32_t(d.sums[c * DW + j] / wsum);
+                for (int j = 0; j < D; j++) d.cen[c * D + j] = int32_t(rs[c * DW + j] / wsum);
             } else {
                 atomicAdd(&s_nempty, 1u);
             }
         }
-        moved = d.sums[k * DW];
+        moved = rs[k * DW];
         __syncthreads();
         const uint32_t nempty = s_nempty;
         if (nempty && d.world > 1) {
@@ -1101,7 +1137,8 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
             d.st->ngroups = (n0 + G - 1) / G + (placed + G - 1) / G;
         }
     }
-    for (uint32_t i = tid; i < k * DW + 1; i += 1024) d.sums[i] = 0ull;
+    if (!d.p2p)
+        for (uint32_t i = tid; i < k * DW + 1; i += 1024) d.sums[i] = 0ull;
     if (tid == 0) {
         if (init_mode) {
             d.st->iter = 0; d.st->done = 0; d.st->empty_events = 0; d.st->n_empty_last = 0; d.st->dist_empty = 0;
@@ -1234,6 +1271,7 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     const size_t o_cpk = take(KP * 4), o_cxy = take(KP * 4), o_bias = take(KP * 4), o_id = take(KP * 2), o_pos = take(k * 2);
     const size_t o_sums = take((size_t(k) * (D + 1) + 1) * 8), o_cen = take(size_t(k) * D * 4), o_w = take(size_t(k) * 8);
     const size_t o_st = take(sizeof(KmState));
+    const size_t o_red = take((size_t(k) * (D + 1) + 1) * 8);
     const uint32_t super_x = D == 5 ? (desc->w + SW - 1) / SW : 0, super_y = D == 5 ? (desc->h_local + SH - 1) / SH : 0;
     const size_t o_gcpk = take(size_t(k) * 4), o_gcxy = take(size_t(k) * 4), o_gnrm = take(size_t(k) * 4);
     const size_t o_sclist = take(size_t(super_x) * super_y * k * 2), o_sccount = take(size_t(super_x) * super_y * 4 + 4);
@@ -1265,6 +1303,10 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     dv.cen = reinterpret_cast<int32_t *>(p + o_cen);
     dv.weights = reinterpret_cast<unsigned long long *>(p + o_w);
     dv.st = reinterpret_cast<KmState *>(p + o_st);
+    dv.sums_red = reinterpret_cast<unsigned long long *>(p + o_red);
+    dv.p2p = ctx->p2p_ready ? 1 : 0;
+    dv.my_rank = ctx->rank;
+    dv.peer_base = ctx->p2p_peer_table;
     dv.g_cpk = reinterpret_cast<uint32_t *>(p + o_gcpk);
     dv.g_cxy = reinterpret_cast<uint32_t *>(p + o_gcxy);
     dv.g_nrm = reinterpret_cast<uint32_t *>(p + o_gnrm);
@@ -1371,15 +1413,22 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
         if (max_iters) batch = std::min(batch, max_iters - issued);
         for (uint32_t b = 0; b < batch; b++) {
             const bool prof = issued + b < (uint32_t)cniic_kmeans::PROF;
+            if (km->dev.p2p) {  // ping-pong exchange buffers, selected by the global sequence number
+                km->dev.seq = ++ctx->p2p_seq;
+                km->dev.sums = ctx->p2p_local + size_t(km->dev.seq & 1) * P2P_SUMS_MAX;
+                km->dev.sums_other = ctx->p2p_local + size_t((km->dev.seq + 1) & 1) * P2P_SUMS_MAX;
+            }
             if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * (issued + b)], ctx->stream));
             ST_TRY(km_launch_assign(km));
             if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * (issued + b) + 1], ctx->stream));
-            if (dist) ST_TRY(cniic_nccl_allreduce_u64(ctx, km->dev.sums, size_t(km->desc.k) * DW + 1));
+            if (dist && !km->dev.p2p) ST_TRY(cniic_nccl_allreduce_u64(ctx, km->dev.sums, size_t(km->desc.k) * DW + 1));
             ST_TRY(km_launch_finalize(km, 0));
         }
         issued += batch;
         CU_TRY(ctx, cudaMemcpyAsync(km->h_state, km->dev.st, sizeof(KmState), cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (km->h_state->dist_empty == 2)
+            return cniic_set_error(ctx, CNIIC_ERR_NCCL, "peer-memory all-reduce timed out waiting for another rank");
         if (km->h_state->dist_empty)
             return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "empty cluster in a multi-GPU run (repair not implemented for sharded points)");
         if (km->h_state->done || (max_iters && issued >= max_iters)) break;

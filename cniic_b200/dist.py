@@ -75,4 +75,14 @@ def make_context(local_rank: int | None = None):
     if dist.get_backend() == "nccl":
         uid = uid.cuda(dev)
     dist.broadcast(uid, src=0)
-    return Context(dev, rank=rank, world=world, nccl_unique_id=bytes(uid.cpu().numpy().tobytes()))
+    ctx = Context(dev, rank=rank, world=world, nccl_unique_id=bytes(uid.cpu().numpy().tobytes()))
+    if os.environ.get("CNIIC_NO_P2P", "0") != "1":
+        # peer-memory all-reduce: exchange the CUDA IPC handles of the per-rank exchange regions
+        mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda(dev)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        ctx.p2p_connect(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+        dist.barrier()
+    return ctx

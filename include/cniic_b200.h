@@ -70,6 +70,11 @@ int cniic_ctx_create(int device, cniic_ctx **out);
  * (cniic_nccl_unique_id) and distributed by the host (torch.distributed store / MPI / file).                   */
 int cniic_ctx_create_dist(int device, int rank, int world, const uint8_t nccl_unique_id[128], cniic_ctx **out);
 int cniic_nccl_unique_id(uint8_t out_id[128]);
+/* Optional peer-memory all-reduce (replaces the per-iteration NCCL call of the row-sharded Lloyd loop): every rank exports
+ * a CUDA IPC handle of its exchange region, the host gathers the world x 64 bytes, every rank connects.  The finalize kernel
+ * then reads all ranks' partial sums over NVLink and reduces them in rank order.            */
+int cniic_ctx_p2p_export(cniic_ctx *ctx, uint8_t out_handle[64]);
+int cniic_ctx_p2p_connect(cniic_ctx *ctx, const uint8_t *handles /* world x 64 bytes, rank order */);
 void cniic_ctx_destroy(cniic_ctx *ctx);
 const char *cniic_last_error(const cniic_ctx *ctx);
 int cniic_ctx_sync(cniic_ctx *ctx);
