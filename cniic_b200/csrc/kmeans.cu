@@ -1013,10 +1013,23 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
         __syncthreads();
         const uint32_t len = k * DW + 1;
         const size_t boff = size_t(d.seq & 1) * P2P_SUMS_MAX;
-        for (uint32_t i = tid; i < len; i += 1024) {
-            unsigned long long acc = 0;
-            for (int r = 0; r < d.world; r++) acc += __ldcv(d.peer_base[r] + boff + i);  // fixed order: deterministic
-            d.sums_red[i] = acc;
+        // 128-bit loads, four independent chunks in flight per thread and rank (NVLink latency is ~2 us per round trip)
+        const uint32_t len2 = (len + 1) / 2;  // in ulonglong2 units; buffers are padded, so reading one slot past len is safe
+        for (uint32_t i0 = tid; i0 < len2; i0 += 4 * 1024) {
+            ulonglong2 acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) acc[u] = make_ulonglong2(0ull, 0ull);
+            for (int r = 0; r < d.world; r++) {  // fixed rank order: deterministic (and integers anyway)
+                const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(d.peer_base[r] + boff);
+                ulonglong2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = (i0 + u * 1024 < len2) ? __ldcv(src + i0 + u * 1024) : make_ulonglong2(0ull, 0ull);
+#pragma unroll
+                for (int u = 0; u < 4; u++) { acc[u].x += v[u].x; acc[u].y += v[u].y; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i0 + u * 1024 < len2) reinterpret_cast<ulonglong2 *>(d.sums_red)[i0 + u * 1024] = acc[u];
         }
         // every rank has passed iteration seq-1, so nobody reads my other buffer any more: clear it for iteration seq+1
         for (uint32_t i = tid; i < P2P_SUMS_MAX; i += 1024) d.sums_other[i] = 0ull;
@@ -1271,7 +1284,7 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     const size_t o_cpk = take(KP * 4), o_cxy = take(KP * 4), o_bias = take(KP * 4), o_id = take(KP * 2), o_pos = take(k * 2);
     const size_t o_sums = take((size_t(k) * (D + 1) + 1) * 8), o_cen = take(size_t(k) * D * 4), o_w = take(size_t(k) * 8);
     const size_t o_st = take(sizeof(KmState));
-    const size_t o_red = take((size_t(k) * (D + 1) + 1) * 8);
+    const size_t o_red = take((size_t(k) * (D + 1) + 2) * 8);
     const uint32_t super_x = D == 5 ? (desc->w + SW - 1) / SW : 0, super_y = D == 5 ? (desc->h_local + SH - 1) / SH : 0;
     const size_t o_gcpk = take(size_t(k) * 4), o_gcxy = take(size_t(k) * 4), o_gnrm = take(size_t(k) * 4);
     const size_t o_sclist = take(size_t(super_x) * super_y * k * 2), o_sccount = take(size_t(super_x) * super_y * 4 + 4);
