@@ -40,9 +40,9 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("no_p2p", ["0", "1"])
-def test_two_gpu_row_sharded_kmeans_matches_single_gpu(tmp_path, no_p2p):
-    """no_p2p=0: peer-memory all-reduce fused into the finalize kernel (default); 1: ncclAllReduce."""
+@pytest.mark.parametrize("p2p", ["0", "1"])
+def test_two_gpu_row_sharded_kmeans_matches_single_gpu(tmp_path, p2p):
+    """p2p=0: ncclAllReduce between assign and finalize (default); 1: peer-memory all-reduce fused into km_finalize."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -53,7 +53,7 @@ def test_two_gpu_row_sharded_kmeans_matches_single_gpu(tmp_path, no_p2p):
     s.close()
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, CNIIC_ROOT=ROOT, CNIIC_OUT=str(tmp_path), CNIIC_NO_P2P=no_p2p)
+    env = dict(os.environ, CNIIC_ROOT=ROOT, CNIIC_OUT=str(tmp_path), CNIIC_P2P=p2p)
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                            "127.0.0.1", "--master-port", str(port), str(script)], env=env, timeout=120)
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
