@@ -1,0 +1,148 @@
+"""Stage workloads of bench.py (--workload c5 | fill): the HBM-bound integer stages and the voronoi decode fill.
+Same JSON contract as the K-means workloads; metric = Mpix/s.  Single GPU (the stages shard without any collective)."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+
+def run(args, workload, peaks, ClockSampler):
+    import torch
+    import cniic_b200 as cb
+    import oracle as O
+
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    ctx = cb.Context(0)
+    lib = ctx._lib
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    pk = peaks()
+
+    if workload == "c5":
+        w = h = 8192
+        desc = "hilbert-rle / delta pre-Huffman stages (Hilbert index map + delta + histograms) on a 8192x8192 synthetic image"
+        d_img = ctx.device_alloc(w * h * 3)
+        cb.synth_image_device(ctx, d_img, w, h, 0xC0FFEE + 5, 4096)
+        d_delta = ctx.device_alloc(w * h * 6)
+        nuniq = C.c_size_t(0)
+
+        def dev_step():  # one pass of the path: delta stream (huf.rs:38 pass 2 input) + fused symbol histogram (pass 1)
+            ctx.check(lib.cniic_delta_i16_device(ctx.h, C.c_void_p(d_img), C.c_uint32(w), C.c_uint32(h), C.c_void_p(d_delta)))
+            ctx.check(lib.cniic_hist_delta_device(ctx.h, C.c_void_p(d_img), C.c_uint32(w), C.c_uint32(h), C.byref(nuniq)))
+        launches_per_step = None
+        alg_bytes = (3 + 6 + 3) * w * h  # delta: 3 B/px read + 6 B/px written; fused histogram: 3 B/px read
+        kernel, kernel_bytes = "hilbert_tile_kernel<1> (delta)", 9 * w * h
+        pinned = torch.empty((h, w, 3), dtype=torch.uint8).pin_memory()
+        host = pinned.numpy()
+        ctx.d2h(host, d_img)
+        out_host = torch.empty((w * h, 3), dtype=torch.int16).pin_memory().numpy()
+
+        def e2e_step():
+            ctx.check(lib.cniic_delta_i16(ctx.h, host.ctypes.data_as(C.c_void_p), C.c_uint32(w), C.c_uint32(h), out_host.ctypes.data_as(C.c_void_p)))
+        h2d, d2h = w * h * 3, w * h * 6
+        crop = cb.synth_image_host(2048, 2048, 0xC0FFEE + 5, 256)
+
+        def cpu_step():
+            d = O.delta(crop)
+            O.hist_delta(d)
+            return crop.shape[0] * crop.shape[1]
+        cpu_desc = "oracle delta + hist_delta (hilbertc.rs:449-477, utils.rs:4-16) on a 2048x2048 crop, 1 thread"
+
+        def kernel_only():
+            ctx.check(lib.cniic_delta_i16_device(ctx.h, C.c_void_p(d_img), C.c_uint32(w), C.c_uint32(h), C.c_void_p(d_delta)))
+    else:
+        w, h, k = 7680, 4320, 2048
+        desc = "voronoi decode fill (clusterc.rs:179-186) k=2048 on a 7680x4320 image"
+        d_img = ctx.device_alloc(w * h * 3)
+        cb.synth_image_device(ctx, d_img, w, h, 0xC0FFEE + 3, 2048)
+        s = cb.KMeansSession(ctx, cb.POINTS_XYRGB, k, d_img, w * h, w=w, h_local=h, on_device=True)
+        s.reset()
+        s.run(3)
+        cen, _, _ = s.get(want_assign=False)
+        s.close()
+        cxy = np.ascontiguousarray(cen[:, :2].astype(np.uint32))
+        crgb = np.ascontiguousarray(cen[:, 2:].astype(np.uint8))
+        d_cxy, d_crgb, d_out = ctx.device_alloc(cxy.nbytes), ctx.device_alloc(crgb.nbytes), ctx.device_alloc(w * h * 3)
+        ctx.h2d(d_cxy, cxy)
+        ctx.h2d(d_crgb, crgb)
+
+        def dev_step():
+            ctx.check(lib.cniic_voronoi_fill_device(ctx.h, C.c_void_p(d_cxy), C.c_void_p(d_crgb), C.c_uint32(k), C.c_uint32(w), C.c_uint32(h),
+                                                    C.c_uint32(0), C.c_uint32(h), C.c_void_p(d_out)))
+        kernel_only = dev_step
+        alg_bytes = 3 * w * h + 19 * k
+        kernel, kernel_bytes = "fill_kernel", 3 * w * h
+        out_host = torch.empty((h, w, 3), dtype=torch.uint8).pin_memory().numpy()
+
+        def e2e_step():
+            ctx.check(lib.cniic_voronoi_fill(ctx.h, cxy.ctypes.data_as(C.c_void_p), crgb.ctypes.data_as(C.c_void_p), C.c_uint32(k), C.c_uint32(w),
+                                             C.c_uint32(h), out_host.ctypes.data_as(C.c_void_p)))
+        h2d, d2h = 19 * k, w * h * 3
+
+        def cpu_step():
+            O.voronoi_fill(cxy, crgb, w, 24)  # 24 rows of the full-width image against all k centroids
+            return w * 24
+        cpu_desc = "oracle voronoi_fill (clusterc.rs:179-186, brute force over k) on 24 full-width rows, 1 thread"
+
+    for _ in range(W):
+        dev_step()
+    ctx.sync()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = ctx.launches
+    tot = 0.0
+    for i in range(K):
+        flush.fill_(i & 0xff)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        dev_step()
+        b.record(stream)
+        ctx.sync()
+        tot += a.elapsed_time(b)
+    launches = (ctx.launches - l0) // K
+    t_s = time.perf_counter()
+    while time.perf_counter() - t_s < 0.5:  # keep the same load running (untimed) until the clock sampler has its samples
+        dev_step()
+        ctx.sync()
+    clocks = sampler.stop()
+    value = w * h * K / (tot * 1e-3) / 1e6
+    # dominant kernel alone (CUDA events on the launching stream)
+    kt = 0.0
+    for i in range(5):
+        flush.fill_(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        kernel_only()
+        b.record(stream)
+        ctx.sync()
+        kt += a.elapsed_time(b) / 5
+    ach = kernel_bytes / (kt * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "traffic": None, "launch_ms": kt, "algorithmic_bytes_per_launch": kernel_bytes, "peak_source": pk["source"],
+                "step_algorithmic_bytes": alg_bytes, "step_hbm_frac": alg_bytes * K / (tot * 1e-3) / 1e9 / pk["hbm_gbs"]}
+    for _ in range(2):
+        e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    dt = time.perf_counter() - t0
+    e2e = {"value": w * h * K / dt / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+    cpu = None
+    if not args.no_cpu:
+        t0, px = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 10.0:
+            px += cpu_step()
+        dtc = time.perf_counter() - t0
+        cpu = {"value": px / dtc / 1e6, "unit": "Mpix/s", "cores": 1, "kind": "port", "sample": cpu_desc, "seconds": dtc}
+    line = {"metric": "Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": tot / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i16/u32", "data": "synthetic",
+            "config": {"workload": desc, "pixels": w * h, "l2": "512 MiB buffer written between timed steps (L2 flush)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    return 0
