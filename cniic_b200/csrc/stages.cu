@@ -421,7 +421,7 @@ __constant__ uint8_t HIL4_Y[16] = {0, 0, 1, 1, 2, 3, 3, 2, 2, 3, 3, 2, 1, 1, 0, 
 
 constexpr int HASH_BITS = 12, HASH_SLOTS = 1 << HASH_BITS;  // block-local symbol table of the fused histogram
 constexpr int HT = 64;            // block side
-constexpr int HT_STRIDE = 208;    // bytes per staged row (192 + pad, multiple of 16)
+constexpr int HT_STRIDE = 68;     // words per staged row (64 + 4 pad: rows shift by 4 banks, 128-bit aligned)
 
 constexpr int CUBE_R = 15, CUBE_S = 2 * CUBE_R + 1, CUBE_N = CUBE_S * CUBE_S * CUBE_S;  // 31^3 near-zero delta symbols
 constexpr int CUBE_FLUSH_TILES = 12;  // 12 * 4096 symbols < 2^16: the packed u16 counters cannot overflow
@@ -430,8 +430,9 @@ template <int MODE>
 __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__restrict__ rgb, uint32_t n, uint8_t *out_rgb,
                                                            int16_t *out_delta, uint32_t *bins, uint8_t *flags) {
     extern __shared__ uint32_t s_cube[];  // MODE 2 only: CUBE_N packed u16 counters for the near-zero symbols
-    __shared__ __align__(16) uint8_t s_px[HT * HT_STRIDE];
+    __shared__ __align__(16) uint32_t s_px[HT * HT_STRIDE];  // one word per pixel (r | g<<8 | b<<16)
     __shared__ uint32_t s_last[8];
+    __shared__ int s_top[5];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long nblocks = (unsigned long long)n * n / 4096;
     if (MODE == 2) {
@@ -441,21 +442,45 @@ __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__rest
     for (unsigned long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const unsigned long long B = blk * 4096;
         const unsigned long long i0 = B + (unsigned long long)tid * 16;
-        // fold levels 2..L-1 into (ax, sx, ay, sy, swapped)
+        // The block's 4096 indices share every base-4 digit above the lowest six: lane 0 of warp 0 folds those levels
+        // (6..L-1) into one affine map of the 64x64 block, every thread folds only its own levels 2..5.
+        __syncthreads();  // previous block is done with s_px / s_last / s_top
+        if (tid == 0) {
+            int bx = 0, by = 0, tx = 1, ty = 1, sw = 0;
+            unsigned long long t = B >> 12;
+            for (uint32_t sft = HT; sft < n; sft <<= 1) {
+                const int sl = (int)sft;
+                const uint32_t rx = 1u & (uint32_t)(t >> 1), ry = 1u & ((uint32_t)t ^ rx);
+                if (ry == 0) {
+                    if (rx == 1) {
+                        const int nbx = sl - 1 - by, ntx = -ty, nby = sl - 1 - bx, nty = -tx;
+                        bx = nbx; tx = ntx; by = nby; ty = nty;
+                    } else {
+                        const int q = bx, qs = tx;
+                        bx = by; tx = ty; by = q; ty = qs;
+                    }
+                    sw ^= 1;
+                }
+                bx += sl * (int)rx;
+                by += sl * (int)ry;
+                t >>= 2;
+            }
+            s_top[0] = bx; s_top[1] = tx; s_top[2] = by; s_top[3] = ty; s_top[4] = sw;
+        }
         int ax = 0, ay = 0, sx = 1, sy = 1;
         bool swapped = false;
         {
-            unsigned long long t = i0 >> 4;
-            for (uint32_t sft = 4; sft < n; sft <<= 1) {
-                const int sl = (int)sft;
-                const uint32_t rx = 1u & (uint32_t)(t >> 1), ry = 1u & ((uint32_t)t ^ rx);
+            uint32_t t = (uint32_t)(i0 >> 4) & 0xff;  // digits 2..5
+#pragma unroll
+            for (int sl = 4; sl < HT; sl <<= 1) {
+                const uint32_t rx = 1u & (t >> 1), ry = 1u & (t ^ rx);
                 if (ry == 0) {
                     if (rx == 1) {
                         const int nax = sl - 1 - ay, nsx = -sy, nay = sl - 1 - ax, nsy = -sx;
                         ax = nax; sx = nsx; ay = nay; sy = nsy;
                     } else {
-                        const int tx = ax, tsx = sx;
-                        ax = ay; sx = sy; ay = tx; sy = tsx;
+                        const int q = ax, qs = sx;
+                        ax = ay; sx = sy; ay = q; sy = qs;
                     }
                     swapped = !swapped;
                 }
@@ -464,14 +489,29 @@ __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__rest
                 t >>= 2;
             }
         }
+        __syncthreads();
+        {   // compose: (x, y) = top(local(u, v)); x = bx + tx * (sw ? yl : xl), y = by + ty * (sw ? xl : yl)
+            const int bx = s_top[0], tx = s_top[1], by = s_top[2], ty = s_top[3], sw = s_top[4];
+            const int nax = bx + tx * (sw ? ay : ax), nsx = tx * (sw ? sy : sx);
+            const int nay = by + ty * (sw ? ax : ay), nsy = ty * (sw ? sx : sy);
+            ax = nax; sx = nsx; ay = nay; sy = nsy;
+            swapped = swapped != (sw != 0);
+        }
         const int u0 = swapped ? HIL4_Y[0] : HIL4_X[0], v0 = swapped ? HIL4_X[0] : HIL4_Y[0];
         const int X0 = (ax + sx * u0) & ~(HT - 1), Y0 = (ay + sy * v0) & ~(HT - 1);
-        __syncthreads();  // previous block is done with s_px / s_last
-        // stage the 64x64 block: 64 rows x 12 uint4
-        for (int idx = tid; idx < HT * 12; idx += 256) {
-            const int r = idx / 12, c = idx % 12;
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rgb + ((size_t)(Y0 + r) * n + X0) * 3) + c);
-            *reinterpret_cast<uint4 *>(s_px + r * HT_STRIDE + c * 16) = v;
+        // stage the 64x64 block as one 32-bit word per pixel: thread t expands 16 pixels (three 128-bit loads) of row t/4
+        {
+            const int r = tid >> 2, c16 = (tid & 3) * 16;
+            const uint4 *src = reinterpret_cast<const uint4 *>(rgb + ((size_t)(Y0 + r) * n + X0 + c16) * 3);
+            const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+            const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+            uint32_t *dst = s_px + r * HT_STRIDE + c16;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // 3 words -> 4 pixels
+                const uint32_t w0 = wd[3 * q], w1 = wd[3 * q + 1], w2 = wd[3 * q + 2];
+                *reinterpret_cast<uint4 *>(dst + 4 * q) =
+                    make_uint4(w0 & 0xffffff, __byte_perm(w0, w1, 0x4543) & 0xffffff, __byte_perm(w1, w2, 0x4432) & 0xffffff, w2 >> 8);
+            }
         }
         __syncthreads();
         uint32_t pix[16];
@@ -479,8 +519,7 @@ __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__rest
         for (int j = 0; j < 16; j++) {
             const int u = swapped ? HIL4_Y[j] : HIL4_X[j], v = swapped ? HIL4_X[j] : HIL4_Y[j];
             const int lx = (ax + sx * u) - X0, ly = (ay + sy * v) - Y0;
-            const uint8_t *q = s_px + ly * HT_STRIDE + lx * 3;
-            pix[j] = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+            pix[j] = s_px[ly * HT_STRIDE + lx];
         }
         if (MODE == 0) {
             uint32_t wd[12];
@@ -512,17 +551,19 @@ __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__rest
             }
         }
         if (MODE == 1) {
+            // 16-bit SIMD lanes: A = (r, b), G = (g, 0); per-lane wrap-around subtraction gives the i16 differences
             uint32_t wd[24];  // 48 i16 packed two per word
-            int16_t dl[48];
+            uint32_t pa = prev & 0x00ff00ffu, pg = (prev >> 8) & 0xffu;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
-                dl[3 * j] = (int16_t)(int(c & 0xff) - int(p & 0xff));
-                dl[3 * j + 1] = (int16_t)(int((c >> 8) & 0xff) - int((p >> 8) & 0xff));
-                dl[3 * j + 2] = (int16_t)(int((c >> 16) & 0xff) - int((p >> 16) & 0xff));
+            for (int j = 0; j < 16; j += 2) {
+                const uint32_t a0 = pix[j] & 0x00ff00ffu, g0 = (pix[j] >> 8) & 0xffu;
+                const uint32_t a1 = pix[j + 1] & 0x00ff00ffu, g1 = (pix[j + 1] >> 8) & 0xffu;
+                const uint32_t da0 = __vsub2(a0, pa), dg0 = __vsub2(g0, pg), da1 = __vsub2(a1, a0), dg1 = __vsub2(g1, g0);
+                wd[3 * (j / 2)] = __byte_perm(da0, dg0, 0x5410);      // dr0, dg0
+                wd[3 * (j / 2) + 1] = __byte_perm(da0, da1, 0x5432);  // db0, dr1
+                wd[3 * (j / 2) + 2] = __byte_perm(dg1, da1, 0x7610);  // dg1, db1
+                pa = a1; pg = g1;
             }
-#pragma unroll
-            for (int q = 0; q < 24; q++) wd[q] = uint32_t(uint16_t(dl[2 * q])) | (uint32_t(uint16_t(dl[2 * q + 1])) << 16);
             uint4 *o = reinterpret_cast<uint4 *>(out_delta + i0 * 3);
 #pragma unroll
             for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
