@@ -2,8 +2,8 @@
 //   ClusterColors (src/codec/clusterc.rs:14-62), VoronoiCluster (clusterc.rs:143-194), Delta (src/codec/hilbertc.rs:402-439),
 //   Hufman (src/codec/hufc.rs), Hilbert RLE exact (hilbertc.rs:12-96).
 // Wire formats follow src/ser.rs, src/huf.rs and src/bit.rs byte for byte (DESIGN.md "Wire formats").
-// The per-pixel work (K-means, histograms, recolour, Hilbert gather, delta, fill, scatter) runs on the GPU; the Huffman
-// tree (<= #symbols nodes) and the sequential bit packing / run-length pass run on the host.
+// The per-pixel work (K-means, histograms, recolour, Hilbert gather, delta, fill, scatter, Huffman bit packing) runs on the
+// GPU; the Huffman tree (<= #symbols nodes), the decoders' bit-serial trie walk and the run-length pass run on the host.
 #include <cctype>
 #include <cstring>
 #include <queue>
@@ -59,24 +59,10 @@ CodecSpec parse_codec(const char *expr) {
 // ---- byte sink / source (ser.rs: little endian, usize as u64, Rgb as a slice = u64 length + 3 bytes) ----
 struct Sink {
     std::vector<uint8_t> v;
-    uint8_t cur = 0;
-    int nbits = 0;
     void u8(uint8_t b) { v.push_back(b); }
     void u32(uint32_t x) { for (int i = 0; i < 4; i++) v.push_back((uint8_t)(x >> (8 * i))); }
     void u64(uint64_t x) { for (int i = 0; i < 8; i++) v.push_back((uint8_t)(x >> (8 * i))); }
     void rgb(uint32_t key) { u64(3); u8(key >> 16); u8(key >> 8); u8(key); }
-    // bit.rs:209-253 : MSB first, zero padded
-    void bits(uint64_t code, uint32_t len) {
-        while (len) {
-            const uint32_t take = std::min<uint32_t>(len, 8 - nbits);
-            const uint32_t chunk = (uint32_t)((code >> (len - take)) & ((1u << take) - 1));
-            cur = (uint8_t)(cur | (chunk << (8 - nbits - take)));
-            nbits += take;
-            len -= take;
-            if (nbits == 8) { v.push_back(cur); cur = 0; nbits = 0; }
-        }
-    }
-    void flush() { if (nbits) { v.push_back(cur); cur = 0; nbits = 0; } }
 };
 
 struct Source {
@@ -227,20 +213,19 @@ int encode_hufman_body(cniic_ctx *ctx, const uint8_t *d_rgb, const uint8_t *host
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "histogram copy failed");
     }
     cniic_cache_free(ctx, d_bins);
-    cniic_cache_free(ctx, d_keys);
     cniic_cache_free(ctx, d_counts);
-    if (rc != CNIIC_OK) return rc;
     HufTree T;
-    if (!huf_build(counts, &T)) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "Huffman code longer than 64 bits");
-    huf_serialize(T, s, [&](uint32_t sym) { s.rgb(keys[sym]); });
-    std::vector<uint32_t> lut(size_t(1) << 24);
-    for (size_t i = 0; i < u; i++) lut[keys[i]] = (uint32_t)i;
-    for (size_t i = 0; i < n; i++) {  // pass 2: bit packing
-        const uint32_t sym = lut[((uint32_t)host_rgb[3 * i] << 16) | ((uint32_t)host_rgb[3 * i + 1] << 8) | host_rgb[3 * i + 2]];
-        s.bits(T.code[sym], T.len[sym]);
+    if (rc == CNIIC_OK && !huf_build(counts, &T)) rc = cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "Huffman code longer than 64 bits");
+    if (rc == CNIIC_OK) {
+        huf_serialize(T, s, [&](uint32_t sym) { s.rgb(keys[sym]); });
+        // pass 2: bit packing on the GPU (code lookup, scan of the lengths, MSB-first word assembly)
+        std::vector<uint8_t> payload;
+        rc = cniic_dev_huffman_pack(ctx, 0, d_rgb, n, d_keys, u, T.code, T.len, &payload);
+        if (rc == CNIIC_OK) s.v.insert(s.v.end(), payload.begin(), payload.end());
     }
-    s.flush();
-    return CNIIC_OK;
+    cniic_cache_free(ctx, d_keys);
+    (void)host_rgb;
+    return rc;
 }
 
 int decode_hufman_body(cniic_ctx *ctx, Source &src, size_t n, uint8_t *out_rgb) {
@@ -335,32 +320,25 @@ extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "histogram copy failed");
         }
         cniic_cache_free(ctx, d_bins);
-        cniic_cache_free(ctx, d_keys);
         cniic_cache_free(ctx, d_counts);
-        ST_TRY(rc);
         HufTree T;
-        if (!huf_build(counts, &T)) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "Huffman code longer than 64 bits");
-        huf_serialize(T, s, [&](uint32_t sym) {  // ser.rs:188-195 : [i16;3] LE
-            const uint32_t key = keys[sym];
-            const int16_t d[3] = {(int16_t)(int(key / (511 * 511)) - 255), (int16_t)(int((key / 511) % 511) - 255), (int16_t)(int(key % 511) - 255)};
-            for (int j = 0; j < 3; j++) { s.u8((uint8_t)((uint16_t)d[j] & 0xff)); s.u8((uint8_t)((uint16_t)d[j] >> 8)); }
-        });
-        // pass 2: the delta stream itself (GPU) -> host bit packing
+        if (rc == CNIIC_OK && !huf_build(counts, &T)) rc = cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "Huffman code longer than 64 bits");
         DevBuf dd(ctx);
-        CU_TRY(ctx, dd.alloc(n * 6));
-        ST_TRY(cniic_delta_i16_device(ctx, din.as<uint8_t>(), w, h, dd.as<int16_t>()));
-        std::vector<int16_t> diff(n * 3);
-        CU_TRY(ctx, cudaMemcpyAsync(diff.data(), dd.p, n * 6, cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        std::unordered_map<uint32_t, uint32_t> ids;
-        ids.reserve(u * 2);
-        for (size_t i = 0; i < u; i++) ids[keys[i]] = (uint32_t)i;
-        for (size_t i = 0; i < n; i++) {
-            const uint32_t key = uint32_t(((diff[3 * i] + 255) * 511 + (diff[3 * i + 1] + 255)) * 511 + (diff[3 * i + 2] + 255));
-            const uint32_t sym = ids[key];
-            s.bits(T.code[sym], T.len[sym]);
+        if (rc == CNIIC_OK && dd.alloc(n * 6) != cudaSuccess) rc = CNIIC_ERR_CUDA;
+        if (rc == CNIIC_OK) {
+            huf_serialize(T, s, [&](uint32_t sym) {  // ser.rs:188-195 : [i16;3] LE
+                const uint32_t key = keys[sym];
+                const int16_t d[3] = {(int16_t)(int(key / (511 * 511)) - 255), (int16_t)(int((key / 511) % 511) - 255), (int16_t)(int(key % 511) - 255)};
+                for (int j = 0; j < 3; j++) { s.u8((uint8_t)((uint16_t)d[j] & 0xff)); s.u8((uint8_t)((uint16_t)d[j] >> 8)); }
+            });
+            // pass 2: the delta stream itself, then bit packing, both on the GPU
+            rc = cniic_delta_i16_device(ctx, din.as<uint8_t>(), w, h, dd.as<int16_t>());
         }
-        s.flush();
+        std::vector<uint8_t> payload;
+        if (rc == CNIIC_OK) rc = cniic_dev_huffman_pack(ctx, 1, dd.p, n, d_keys, u, T.code, T.len, &payload);
+        cniic_cache_free(ctx, d_keys);
+        ST_TRY(rc);
+        s.v.insert(s.v.end(), payload.begin(), payload.end());
         break;
     }
     case CK_HILBERT_RLE: {  // hilbertc.rs:26-38, 99-196 ; records = u8 count (1..=255) + Rgb slice

@@ -46,7 +46,7 @@ struct KmState {
     uint32_t ngroups;
     uint32_t ng0;
     uint32_t n_empty_last;
-    uint32_t dist_empty;  // an empty cluster occurred in a multi-GPU run (repair needs the host path)
+    uint32_t dist_empty;  // multi-GPU: 1 = an empty cluster halted the loop until the host path repairs it, 2 = peer wait timed out
     uint32_t pad;
     unsigned long long moved_last, moved_total;
     unsigned long long pairs;  // point-centroid pairs actually scored by the assign kernels since reset
@@ -133,7 +133,7 @@ __device__ __forceinline__ void unpack8(const uint32_t w[6], uint32_t px[PX]) {
 
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(THREADS) km_assign_rgb(KmDev d) {
-    if (d.st->done) return;
+    if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
     const uint32_t KP = kpad_of(k, G3);
@@ -340,7 +340,7 @@ constexpr int RCAP = 256;  // survivors scored per round
 
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
-    if (d.st->done) return;
+    if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
     uint4 *t_ent = smem_raw;                                   // RCAP x {cpk, -|c|^2, id, -}
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
 // ------------------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(THREADS) km_assign_xyrgb(KmDev d) {
-    if (d.st->done) return;
+    if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
     const uint32_t KP = kpad_of(k, G5);
@@ -719,7 +719,7 @@ constexpr int SW = 512, SH = 256;  // supertile = 8 x 8 tiles
 constexpr int TCAP = 256;          // survivors scored per round
 
 __global__ void __launch_bounds__(THREADS) km_supercull(KmDev d) {
-    if (d.st->done) return;
+    if (d.st->done || d.st->dist_empty) return;
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_U;
     const int tid = threadIdx.x;
@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(THREADS) km_supercull(KmDev d) {
 }
 
 __global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull(KmDev d) {
-    if (d.st->done) return;
+    if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
     uint4 *t_ent = smem_raw;                                              // TCAP x {cpk, cxy, kb, id}
@@ -986,7 +986,7 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
     constexpr int DW = D + 1;
     constexpr int G = D == 5 ? G5 : G3;
     constexpr int DUMMY = D == 5 ? DUMMY5 : DUMMY3;
-    if (!init_mode && d.st->done) return;
+    if (init_mode == 0 && (d.st->done || d.st->dist_empty)) return;
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_nempty, s_victim, s_m;
     __shared__ uint16_t s_empty[CNIIC_MAX_K];
@@ -995,8 +995,8 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
     const int tid = threadIdx.x;
     unsigned long long moved = 0;
 
-    const unsigned long long *rs = d.sums;
-    if (!init_mode && d.p2p) {
+    const unsigned long long *rs = d.p2p ? d.sums_red : d.sums;
+    if (init_mode == 0 && d.p2p) {
         // ---- all-reduce over peer memory: publish, wait for every rank, sum the partials in rank order ----
         // The assign kernel of this iteration has completed (stream order), so my partial sums are in my exchange buffer.
         volatile uint32_t *arrived = reinterpret_cast<volatile uint32_t *>(d.peer_base[d.my_rank] + 2 * P2P_SUMS_MAX);
@@ -1034,9 +1034,13 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
         // every rank has passed iteration seq-1, so nobody reads my other buffer any more: clear it for iteration seq+1
         for (uint32_t i = tid; i < P2P_SUMS_MAX; i += 1024) d.sums_other[i] = 0ull;
         __syncthreads();
-        rs = d.sums_red;
     }
-    if (!init_mode) {
+    if (init_mode == 2) {  // resume after the host repaired the empty clusters of a sharded run
+        if (tid == 0) s_nempty = d.st->n_empty_last;
+        moved = d.st->moved_last;
+        __syncthreads();
+    }
+    if (init_mode == 0) {
         if (tid == 0) s_nempty = 0;
         __syncthreads();
         for (uint32_t c = tid; c < k; c += 1024) {
@@ -1052,7 +1056,11 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
         __syncthreads();
         const uint32_t nempty = s_nempty;
         if (nempty && d.world > 1) {
-            if (tid == 0) d.st->dist_empty = 1;  // repaired by the host path (cniic_kmeans_run)
+            // sharded points: the members with the lowest global indices live on several ranks.  Halt here (nothing else is
+            // modified; later launches of the batch exit at once); cniic_kmeans_run repairs on the host and resumes.
+            // (`moved` is parked in the state: later all-reduce calls of the batch still run and re-add the sums buffer)
+            if (tid == 0) { d.st->dist_empty = 1; d.st->n_empty_last = nempty; d.st->moved_last = moved; }
+            return;
         } else if (nempty) {
             // deterministic stand-in for kmeans.rs:117-134 (see header): heaviest cluster = victim
             if (tid == 0) {
@@ -1153,7 +1161,7 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
     if (!d.p2p)
         for (uint32_t i = tid; i < k * DW + 1; i += 1024) d.sums[i] = 0ull;
     if (tid == 0) {
-        if (init_mode) {
+        if (init_mode == 1) {
             d.st->iter = 0; d.st->done = 0; d.st->empty_events = 0; d.st->n_empty_last = 0; d.st->dist_empty = 0;
             d.st->moved_last = 0; d.st->moved_total = 0; d.st->pairs = 0;
         } else {
@@ -1163,6 +1171,69 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
             d.st->n_empty_last = s_nempty;
             d.st->empty_events += s_nempty;
             if (moved == 0) d.st->done = 1;
+            d.st->dist_empty = 0;
+        }
+    }
+}
+
+// Multi-GPU empty-cluster repair, step 1: this rank's members of `victim` with the lowest global indices (ascending),
+// at most `need` of them, with their coordinates, plus the rank's member count.  Single CTA; rare path.
+template <int D>
+__global__ void __launch_bounds__(1024) km_repair_scan(KmDev d, uint32_t victim, uint32_t need, unsigned long long *out_idx, int32_t *out_val,
+                                                       unsigned long long *out_count) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_found[CNIIC_MAX_K];
+    const int tid = threadIdx.x;
+    uint32_t found = 0;
+    unsigned long long members = 0;
+    for (unsigned long long i = tid; i < d.n_local; i += 1024) members += d.assign[i] == victim;
+    for (int o = 16; o > 0; o >>= 1) members += __shfl_xor_sync(0xffffffffu, members, o);
+    __shared__ unsigned long long s_m[32];
+    if ((tid & 31) == 0) s_m[tid >> 5] = members;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < 32; i++) t += s_m[i];
+        *out_count = t;
+    }
+    if (d.perm) {
+        long long last = -1;
+        for (; found < need; found++) {
+            uint32_t best = 0xffffffffu;
+            for (unsigned long long i = tid; i < d.n_local; i += 1024)
+                if (d.assign[i] == victim) {
+                    const uint32_t o = d.perm[i];
+                    if ((long long)o > last && o < best) best = o;
+                }
+            for (int o2 = 16; o2 > 0; o2 >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o2));
+            __syncthreads();
+            if ((tid & 31) == 0) s_warp[tid >> 5] = best;
+            __syncthreads();
+            for (int i = 0; i < 32; i++) best = min(best, s_warp[i]);
+            if (best == 0xffffffffu) break;
+            if (tid == 0) s_found[found] = best;
+            last = best;
+        }
+    } else {
+        for (unsigned long long base = 0; base < d.n_local && found < need; base += 1024) {
+            const unsigned long long i = base + tid;
+            const bool is = i < d.n_local && d.assign[i] == victim;
+            uint32_t tot;
+            const uint32_t r = block_rank(is, s_warp, &tot);
+            if (is && found + r < need) s_found[found + r] = uint32_t(i);
+            found += tot;
+        }
+    }
+    __syncthreads();
+    const uint32_t m = min(found, need);
+    for (uint32_t j = tid; j < need; j += 1024) {
+        if (j < m) {
+            int32_t v[D];
+            fetch_point<D>(d, s_found[j], v);
+            out_idx[j] = d.first_index + s_found[j];
+            for (int q = 0; q < D; q++) out_val[j * D + q] = v[q];
+        } else {
+            out_idx[j] = ~0ull;
         }
     }
 }
@@ -1412,6 +1483,57 @@ extern "C" int cniic_kmeans_reset(cniic_kmeans *km, const int32_t *host_init_cen
     return rc_fin;
 }
 
+// Multi-GPU empty-cluster repair (host-coordinated, rare): same deterministic rule as the single-GPU kernel path -- the j-th
+// empty cluster copies the member with the (j mod m)-th lowest GLOBAL point index of the heaviest cluster.
+template <int D>
+static int km_repair_dist(cniic_kmeans *km) {
+    cniic_ctx *ctx = km->ctx;
+    const uint32_t k = km->desc.k;
+    std::vector<uint64_t> wts(k);
+    CU_TRY(ctx, cudaMemcpyAsync(wts.data(), km->dev.weights, size_t(k) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> empties;
+    uint32_t victim = 0;
+    uint64_t bw = 0;
+    for (uint32_t c = 0; c < k; c++) {
+        if (!wts[c]) empties.push_back(c);
+        else if (wts[c] > bw) { bw = wts[c]; victim = c; }
+    }
+    const uint32_t need = (uint32_t)empties.size();
+    const size_t rec = size_t(need) * (8 + 4 * D) + 8;  // per rank: indices, coordinates, member count
+    DevBuf mine(ctx), all(ctx);
+    CU_TRY(ctx, mine.alloc(rec));
+    CU_TRY(ctx, all.alloc(rec * ctx->world));
+    unsigned long long *d_idx = mine.as<unsigned long long>();
+    unsigned long long *d_cnt = d_idx + need;
+    int32_t *d_val = reinterpret_cast<int32_t *>(d_cnt + 1);
+    km_repair_scan<D><<<1, 1024, 0, ctx->stream>>>(km->dev, victim, need, d_idx, d_val, d_cnt);
+    km->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    ST_TRY(cniic_nccl_allgather_bytes(ctx, mine.p, all.p, rec));
+    std::vector<uint8_t> host(rec * ctx->world);
+    CU_TRY(ctx, cudaMemcpyAsync(host.data(), all.p, host.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<std::pair<uint64_t, std::vector<int32_t>>> cand;
+    uint64_t m = 0;
+    for (int r = 0; r < ctx->world; r++) {
+        const uint8_t *base = host.data() + rec * r;
+        const uint64_t *idx = reinterpret_cast<const uint64_t *>(base);
+        m += idx[need];
+        const int32_t *val = reinterpret_cast<const int32_t *>(idx + need + 1);
+        for (uint32_t j = 0; j < need; j++)
+            if (idx[j] != ~0ull) cand.push_back({idx[j], std::vector<int32_t>(val + j * D, val + (j + 1) * D)});
+    }
+    std::sort(cand.begin(), cand.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+    if (m == 0 || cand.empty()) return cniic_set_error(ctx, CNIIC_ERR_CUDA, "empty-cluster repair found no member of the heaviest cluster");
+    for (uint32_t j = 0; j < need; j++) {
+        const std::vector<int32_t> &v = cand[(size_t)(j % m)].second;
+        CU_TRY(ctx, cudaMemcpyAsync(km->dev.cen + size_t(empties[j]) * D, v.data(), D * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the source vectors die with this scope
+    return km_launch_finalize(km, 2);  // rebuild the tables, close the iteration, clear the halt
+}
+
 extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmeans_stats *stats) {
     if (!km) return CNIIC_ERR_BAD_ARG;
     cniic_ctx *ctx = km->ctx;
@@ -1420,31 +1542,37 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
     const int DW = km->D + 1;
     const bool dist = ctx->world > 1;
     CU_TRY(ctx, cudaEventRecord(km->ev0, ctx->stream));
-    uint32_t issued = 0;
+    uint32_t issued = 0;            // assign launches of this call (indexes the profiling events)
+    uint32_t done_iters = 0;        // iterations completed by this call (state.iter - iter_seen)
     for (;;) {
-        uint32_t batch = 4;  // kernels (and the all-reduce) early-exit / are harmless once `done` is set
-        if (max_iters) batch = std::min(batch, max_iters - issued);
+        uint32_t batch = 4;  // kernels (and the all-reduce) early-exit / are harmless once `done` or a halt is set
+        if (max_iters) batch = std::min(batch, max_iters - done_iters);
         for (uint32_t b = 0; b < batch; b++) {
-            const bool prof = issued + b < (uint32_t)cniic_kmeans::PROF;
+            const bool prof = issued < (uint32_t)cniic_kmeans::PROF;
             if (km->dev.p2p) {  // ping-pong exchange buffers, selected by the global sequence number
                 km->dev.seq = ++ctx->p2p_seq;
                 km->dev.sums = ctx->p2p_local + size_t(km->dev.seq & 1) * P2P_SUMS_MAX;
                 km->dev.sums_other = ctx->p2p_local + size_t((km->dev.seq + 1) & 1) * P2P_SUMS_MAX;
             }
-            if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * (issued + b)], ctx->stream));
+            if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * issued], ctx->stream));
             ST_TRY(km_launch_assign(km));
-            if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * (issued + b) + 1], ctx->stream));
+            if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * issued + 1], ctx->stream));
+            issued++;
             if (dist && !km->dev.p2p) ST_TRY(cniic_nccl_allreduce_u64(ctx, km->dev.sums, size_t(km->desc.k) * DW + 1));
             ST_TRY(km_launch_finalize(km, 0));
         }
-        issued += batch;
         CU_TRY(ctx, cudaMemcpyAsync(km->h_state, km->dev.st, sizeof(KmState), cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         if (km->h_state->dist_empty == 2)
             return cniic_set_error(ctx, CNIIC_ERR_NCCL, "peer-memory all-reduce timed out waiting for another rank");
-        if (km->h_state->dist_empty)
-            return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "empty cluster in a multi-GPU run (repair not implemented for sharded points)");
-        if (km->h_state->done || (max_iters && issued >= max_iters)) break;
+        if (km->h_state->dist_empty == 1) {
+            if (km->dev.p2p) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "empty cluster with the peer-memory all-reduce (use the NCCL path)");
+            ST_TRY(km->D == 5 ? km_repair_dist<5>(km) : km_repair_dist<3>(km));
+            CU_TRY(ctx, cudaMemcpyAsync(km->h_state, km->dev.st, sizeof(KmState), cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        done_iters = km->h_state->iter - km->iter_seen;
+        if (km->h_state->done || (max_iters && done_iters >= max_iters)) break;
     }
     CU_TRY(ctx, cudaEventRecord(km->ev1, ctx->stream));
     CU_TRY(ctx, cudaEventSynchronize(km->ev1));

@@ -133,26 +133,6 @@ __global__ void hist_rgb_kernel(const uint8_t *__restrict__ rgb, size_t n, uint3
     }
 }
 
-constexpr int CB = 4096;  // bins per compaction block (256 threads x 16)
-
-__global__ void __launch_bounds__(256) count_nonzero_kernel(const uint32_t *__restrict__ bins, size_t nbins, uint32_t *block_counts) {
-    const size_t base = (size_t)blockIdx.x * CB;
-    uint32_t c = 0;
-    for (int j = 0; j < 16; j++) {
-        const size_t i = base + (size_t)j * 256 + threadIdx.x;
-        if (i < nbins && bins[i]) c++;
-    }
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    __shared__ uint32_t s[8];
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int i = 0; i < 8; i++) t += s[i];
-        block_counts[blockIdx.x] = t;
-    }
-}
-
 // single-block exclusive scan of block_counts (u32 -> u64 offsets); total to offsets[nblocks]
 __global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t *__restrict__ counts, size_t nblocks, unsigned long long *offsets) {
     __shared__ unsigned long long s_warp[32];
@@ -177,22 +157,6 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t *__res
         __syncthreads();
     }
     if (threadIdx.x == 0) offsets[nblocks] = s_carry;
-}
-
-__global__ void __launch_bounds__(256) compact_kernel(const uint32_t *__restrict__ bins, size_t nbins, const unsigned long long *__restrict__ offsets,
-                                                      uint32_t *out_keys, unsigned long long *out_counts, size_t cap) {
-    __shared__ uint32_t s_warp[8];
-    const size_t base = (size_t)blockIdx.x * CB;
-    unsigned long long pos = offsets[blockIdx.x];
-    if (offsets[blockIdx.x + 1] == pos) return;
-    for (int j = 0; j < 16; j++) {
-        const size_t i = base + (size_t)j * 256 + threadIdx.x;
-        const uint32_t v = i < nbins ? bins[i] : 0;
-        uint32_t tot;
-        const uint32_t r = block_rank256(v != 0, s_warp, &tot);
-        if (v && pos + r < cap) { out_keys[pos + r] = (uint32_t)i; out_counts[pos + r] = v; }
-        pos += tot;
-    }
 }
 
 // ---- paged variant: the bins of the two key spaces live in the context for its whole life and are ALL ZERO between
@@ -419,7 +383,6 @@ __global__ void hilbert_stream_kernel(const uint8_t *__restrict__ rgb, uint32_t 
 __constant__ uint8_t HIL4_X[16] = {0, 1, 1, 0, 0, 0, 1, 1, 2, 2, 3, 3, 3, 2, 2, 3};
 __constant__ uint8_t HIL4_Y[16] = {0, 0, 1, 1, 2, 3, 3, 2, 2, 3, 3, 2, 1, 1, 0, 0};
 
-constexpr int HASH_BITS = 12, HASH_SLOTS = 1 << HASH_BITS;  // block-local symbol table of the fused histogram
 constexpr int HT = 64;            // block side
 constexpr int HT_STRIDE = 68;     // words per staged row (64 + 4 pad: rows shift by 4 banks, 128-bit aligned)
 
@@ -697,6 +660,113 @@ __global__ void sse_kernel(const uint8_t *__restrict__ a, const uint8_t *__restr
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+// ============================================================================================================
+// Huffman payload packing on the device (reference src/huf.rs:36-41 + src/bit.rs:209-253: MSB-first, zero padded)
+//   symbol stream -> (code, length) by binary search in the ascending key table -> exclusive scan of the lengths
+//   -> every thread assembles the bits of its 16 symbols in registers and stores whole 32-bit words; only the first and
+//   last word of a thread can be shared with a neighbour and are merged with atomicOr.
+// ============================================================================================================
+template <int SRC>  // 0: packed RGB8 pixels in raster order, 1: i16 x 3 delta symbols
+__device__ __forceinline__ uint32_t pack_key(const void *src, size_t i) {
+    if (SRC == 0) {
+        const uint8_t *p = static_cast<const uint8_t *>(src) + 3 * i;
+        return (uint32_t(p[0]) << 16) | (uint32_t(p[1]) << 8) | p[2];
+    }
+    const int16_t *d = static_cast<const int16_t *>(src) + 3 * i;
+    return uint32_t(((d[0] + 255) * 511 + (d[1] + 255)) * 511 + (d[2] + 255));
+}
+
+__device__ __forceinline__ uint32_t find_symbol(const uint32_t *__restrict__ keys, uint32_t nsym, uint32_t key) {
+    uint32_t lo = 0, hi = nsym;  // keys[lo] <= key < keys[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(keys + mid) <= key) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(256) pack_len_kernel(const void *__restrict__ src, size_t n, const uint32_t *__restrict__ keys, uint32_t nsym,
+                                                       const uint8_t *__restrict__ lens, uint32_t *block_bits) {
+    const size_t base = (size_t)blockIdx.x * 4096 + (size_t)threadIdx.x * 16;
+    uint32_t bits = 0;
+    for (int j = 0; j < 16; j++)
+        if (base + j < n) bits += lens[find_symbol(keys, nsym, pack_key<SRC>(src, base + j))];
+    for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
+    __shared__ uint32_t s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; i++) t += s[i];
+        block_bits[blockIdx.x] = t;
+    }
+}
+
+struct BitEmitter {
+    uint32_t *out;                 // big-endian bit stream viewed as 32-bit words (byte-swapped on store)
+    unsigned long long word;       // index of the word being filled
+    uint32_t acc;                  // bits collected for that word, left aligned
+    int nb;                        // number of valid bits in acc
+    bool shared_first;             // the word being filled may also be written by the previous thread
+    __device__ __forceinline__ void flush_word() {
+        const uint32_t v = __byte_perm(acc, 0, 0x0123);
+        if (shared_first) { if (v) atomicOr(out + word, v); shared_first = false; }
+        else out[word] = v;
+        word++; acc = 0; nb = 0;
+    }
+    __device__ __forceinline__ void put(uint32_t bits, int len) {  // len <= 32, bits right aligned
+        while (len > 0) {
+            const int room = 32 - nb, take = len < room ? len : room;
+            const uint32_t chunk = (take == 32) ? bits : ((bits >> (len - take)) & ((1u << take) - 1u));
+            acc |= (take == 32) ? chunk : (chunk << (room - take));
+            nb += take; len -= take;
+            if (nb == 32) flush_word();
+        }
+    }
+    __device__ __forceinline__ void finish() {  // last, partially filled word: may be shared with the next thread
+        if (nb) { const uint32_t v = __byte_perm(acc, 0, 0x0123); if (v) atomicOr(out + word, v); }
+    }
+};
+
+template <int SRC>
+__global__ void __launch_bounds__(256) pack_write_kernel(const void *__restrict__ src, size_t n, const uint32_t *__restrict__ keys, uint32_t nsym,
+                                                         const uint8_t *__restrict__ lens, const unsigned long long *__restrict__ codes,
+                                                         const unsigned long long *__restrict__ block_off, uint32_t *out) {
+    __shared__ uint32_t s_w[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t base = (size_t)blockIdx.x * 4096 + (size_t)threadIdx.x * 16;
+    uint32_t sym[16];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        sym[j] = 0xffffffffu;
+        if (base + j < n) { sym[j] = find_symbol(keys, nsym, pack_key<SRC>(src, base + j)); mine += lens[sym[j]]; }
+    }
+    uint32_t x = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    unsigned long long p = block_off[blockIdx.x] + (x - mine);
+    for (int j = 0; j < warp; j++) p += s_w[j];
+    if (mine == 0) return;
+    BitEmitter em{out, p >> 5, 0u, int(p & 31), true};
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (sym[j] != 0xffffffffu) {
+            const int len = lens[sym[j]];
+            const unsigned long long code = codes[sym[j]];
+            if (len > 32) { em.put(uint32_t(code >> 32), len - 32); em.put(uint32_t(code), 32); }
+            else if (len > 0) em.put(uint32_t(code), len);
+        }
+    }
+    em.finish();
 }
 
 inline int grid_for(cniic_ctx *ctx, size_t n, int per_thread = 1) {
@@ -1155,4 +1225,39 @@ extern "C" int cniic_sse_rgb(cniic_ctx *ctx, const uint8_t *a, const uint8_t *b,
     CU_TRY(ctx, cudaMemcpyAsync(da.p, a, n_pixels * 3, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(db.p, b, n_pixels * 3, cudaMemcpyHostToDevice, ctx->stream));
     return cniic_dev_sse(ctx, da.as<uint8_t>(), db.as<uint8_t>(), n_pixels * 3, out_sse);
+}
+
+// Huffman payload of a symbol stream, packed on the device.  d_keys: ascending symbol keys (device); codes/lens: per symbol id (host).
+// *out receives the payload bytes (MSB-first, zero padded to a whole byte).
+int cniic_dev_huffman_pack(cniic_ctx *ctx, int src_kind, const void *d_src, size_t n, const uint32_t *d_keys, size_t nsym,
+                           const std::vector<uint64_t> &codes, const std::vector<uint8_t> &lens, std::vector<uint8_t> *out) {
+    out->clear();
+    if (n == 0 || nsym == 0) return CNIIC_OK;
+    const size_t nblocks = (n + 4095) / 4096;
+    DevBuf dl(ctx), dc(ctx), bb(ctx), off(ctx), dout(ctx);
+    CU_TRY(ctx, dl.alloc(nsym));
+    CU_TRY(ctx, dc.alloc(nsym * 8));
+    CU_TRY(ctx, bb.alloc(nblocks * 4));
+    CU_TRY(ctx, off.alloc((nblocks + 1) * 8));
+    CU_TRY(ctx, cudaMemcpyAsync(dl.p, lens.data(), nsym, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(dc.p, codes.data(), nsym * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (src_kind == 0) pack_len_kernel<0><<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_src, n, d_keys, (uint32_t)nsym, dl.as<uint8_t>(), bb.as<uint32_t>());
+    else pack_len_kernel<1><<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_src, n, d_keys, (uint32_t)nsym, dl.as<uint8_t>(), bb.as<uint32_t>());
+    scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(bb.as<uint32_t>(), nblocks, off.as<unsigned long long>());
+    ctx->launches += 2;
+    unsigned long long total_bits = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&total_bits, off.as<unsigned long long>() + nblocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t nbytes = (size_t)((total_bits + 7) / 8), nwords = (nbytes + 3) / 4;
+    if (nbytes == 0) return CNIIC_OK;
+    CU_TRY(ctx, dout.alloc(nwords * 4 + 16));
+    CU_TRY(ctx, cudaMemsetAsync(dout.p, 0, nwords * 4 + 16, ctx->stream));
+    if (src_kind == 0) pack_write_kernel<0><<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_src, n, d_keys, (uint32_t)nsym, dl.as<uint8_t>(), dc.as<unsigned long long>(), off.as<unsigned long long>(), dout.as<uint32_t>());
+    else pack_write_kernel<1><<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_src, n, d_keys, (uint32_t)nsym, dl.as<uint8_t>(), dc.as<unsigned long long>(), off.as<unsigned long long>(), dout.as<uint32_t>());
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    out->resize(nbytes);
+    CU_TRY(ctx, cudaMemcpyAsync(out->data(), dout.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
 }

@@ -15,3 +15,5 @@ int cniic_dev_undelta(cniic_ctx *ctx, const int16_t *d_diff, uint32_t w, uint32_
 int cniic_dev_sse(cniic_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, size_t nbytes, uint64_t *out);
 int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t k, uint32_t max_iters, int tie_rule, uint8_t *d_out,
                              std::vector<int32_t> *cen_host, cniic_kmeans_stats *stats);
+int cniic_dev_huffman_pack(cniic_ctx *ctx, int src_kind, const void *d_src, size_t n, const uint32_t *d_keys, size_t nsym,
+                           const std::vector<uint64_t> &codes, const std::vector<uint8_t> &lens, std::vector<uint8_t> *out);

@@ -35,6 +35,24 @@ for kind, w, h, k in ((cb.POINTS_XYRGB, 640, 363, 128), (cb.POINTS_RGB, 512, 301
     cen, wts, asg = s.get()
     s.close()
     out[f"cen{D}"], out[f"wts{D}"], out[f"asg{D}"], out[f"it{D}"] = cen, wts, asg, np.array([st.iterations, st.moved_last])
+# empty-cluster repair across shards (kmeans.rs:117-134 stand-in): palette point lists that empty clusters
+if os.environ.get("CNIIC_P2P", "0") != "1":
+    for seed in (0, 4, 9):
+        rng = np.random.default_rng(seed)
+        npal, k, n = int(rng.integers(3, 10)), int(rng.integers(4, 16)), int(rng.integers(40, 400))
+        palette = rng.integers(0, 256, size=(npal, 3), dtype=np.uint8)
+        pts = palette[rng.integers(0, npal, size=n)]
+        jit = rng.integers(-3, 4, size=pts.shape); mask = rng.random(n) < 0.3
+        pts = np.clip(pts.astype(int) + jit * mask[:, None], 0, 255).astype(np.uint8)
+        lo, cnt = cdist.row_shard(n, world, rank)
+        local = np.ascontiguousarray(pts[lo:lo + cnt])
+        init = cdist.gather_init_centroids(3, local, 1, lo, n, k, device=torch.device("cuda", lr))
+        s = cb.KMeansSession(ctx, cb.POINTS_RGB, k, local, cnt, n_total=n, first_index=lo, tie=cb.TIE_LOWEST_INDEX)
+        s.reset(init)
+        st = s.run(8)
+        cen, wts, asg = s.get()
+        s.close()
+        out[f"e_cen{seed}"], out[f"e_asg{seed}"], out[f"e_it{seed}"] = cen, asg, np.array([st.iterations, st.empty_events])
 np.savez(os.path.join(os.environ["CNIIC_OUT"], f"rank{rank}.npz"), **out)
 dist.destroy_process_group()
 '''
@@ -66,3 +84,19 @@ def test_two_gpu_row_sharded_kmeans_matches_single_gpu(tmp_path, p2p):
         assert np.array_equal(r0[f"wts{D}"], g.weights)
         assert np.array_equal(np.concatenate([r0[f"asg{D}"], r1[f"asg{D}"]]), g.assign)
         assert r0[f"it{D}"].tolist() == [g.iterations, g.moved_last]
+    if p2p != "1":
+        events = 0
+        for seed in (0, 4, 9):
+            rng = np.random.default_rng(seed)
+            npal, k, n = int(rng.integers(3, 10)), int(rng.integers(4, 16)), int(rng.integers(40, 400))
+            palette = rng.integers(0, 256, size=(npal, 3), dtype=np.uint8)
+            pts = palette[rng.integers(0, npal, size=n)]
+            jit = rng.integers(-3, 4, size=pts.shape)
+            mask = rng.random(n) < 0.3
+            pts = np.clip(pts.astype(int) + jit * mask[:, None], 0, 255).astype(np.uint8)
+            g = ctx.kmeans_rgb(pts, k, max_iters=8, tie=cb.TIE_LOWEST_INDEX, allow_inactive=True)
+            assert np.array_equal(r0[f"e_cen{seed}"], g.centroids) and np.array_equal(r1[f"e_cen{seed}"], g.centroids)
+            assert np.array_equal(np.concatenate([r0[f"e_asg{seed}"], r1[f"e_asg{seed}"]]), g.assign)
+            assert r0[f"e_it{seed}"].tolist() == [g.iterations, g.empty_events]
+            events += g.empty_events
+        assert events > 0

@@ -277,6 +277,18 @@ def test_codec_streams(ctx, expr, oenc, odec, w, h):
         assert ctx.sse(img, dec) / (w * h) == pytest.approx(O.mse(img, odec(data)), rel=1e-6)
 
 
+@pytest.mark.parametrize("expr", ["hufman", "delta"])
+def test_codec_streams_many_symbols(ctx, expr):
+    """Noise image: ~all pixels are distinct symbols (long codes, payload words shared between threads everywhere)."""
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, size=(160, 224, 3), dtype=np.uint8)
+    img[:40] = (img[:40] // 128) * 128  # plus a region with very frequent symbols (short codes)
+    c = codecs.Codec.from_str(ctx, expr)
+    data = c.encode(img)
+    assert data == (O.encode_hufman(img) if expr == "hufman" else O.encode_delta(img))
+    assert np.array_equal(c.decode(data), img)
+
+
 def test_codec_decode_rejects_malformed(ctx):
     img = cb.synth_image_host(32, 16, 5, 3)
     for expr in ("hufman", "delta", "voronoi(8)", "hilbert(rle)"):
