@@ -331,8 +331,14 @@ def main():
     achieved = flops_exec / (a_ms * 1e-3) / 1e12
     bytes_per_launch = 3 * n_local                          # RGB read once per iteration (assignments: +2 B r/w not counted)
     kernel = "km_assign_rgb_cull" if D == 3 else "km_assign_xyrgb_cull"
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp) and world == 1:
+        ent = json.load(open(tp)).get(kernel)
+        if ent and ent.get("workload") == args.workload:
+            traffic = ent["bytes"]  # dram bytes per launch from the committed ncu --set full capture of this kernel/workload
     roofline = {"bound": "fp32", "kernel": kernel, "achieved": achieved,
-                "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": traffic,
                 "peak_source": f"148 SM x 128 FP32 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']} sm_max_mhz); the kernels issue "
                                "IDP.4A/IDP.2A integer dot products, so frac > FFMA-issue ceilings is possible (DESIGN.md)",
                 "launch_ms": a_ms, "flops_per_launch_executed": flops_exec, "algorithmic_flops_per_launch": flops_alg,
