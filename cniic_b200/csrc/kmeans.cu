@@ -718,6 +718,34 @@ constexpr int TW = 64, TH = 32;    // tile
 constexpr int SW = 512, SH = 256;  // supertile = 8 x 8 tiles
 constexpr int TCAP = 256;          // survivors scored per round
 
+// static colour bounding box (bytewise min / max of r|g<<8|b<<16) of every 64x32 tile of the image, once per session
+__global__ void __launch_bounds__(THREADS) km_tile_boxes_xy(const uint8_t *__restrict__ rgb, uint32_t w, uint32_t hl, uint2 *boxes) {
+    __shared__ uint32_t s_mn[8], s_mx[8];
+    const uint32_t tiles_x = (w + TW - 1) / TW;
+    const int x0 = (blockIdx.x % tiles_x) * TW, yl0 = (blockIdx.x / tiles_x) * TH;
+    const int vw = min(TW, int(w) - x0), vh = min(TH, int(hl) - yl0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = warp * 4 + (lane >> 3), xr0 = (lane & 7) * 8;
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    if (row < vh)
+        for (int p = 0; p < PX; p++)
+            if (xr0 + p < vw) {
+                const uint8_t *q = rgb + ((size_t)(yl0 + row) * w + x0 + xr0 + p) * 3;
+                const uint32_t v = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+                mn = __vminu4(mn, v); mx = __vmaxu4(mx, v);
+            }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = __vmaxu4(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 8; i++) { mn = __vminu4(mn, s_mn[i]); mx = __vmaxu4(mx, s_mx[i]); }
+        boxes[blockIdx.x] = make_uint2(mn & 0xffffff, mx & 0xffffff);
+    }
+}
+
 __global__ void __launch_bounds__(THREADS) km_supercull(KmDev d) {
     if (d.st->done || d.st->dist_empty) return;
     __shared__ uint32_t s_warp[8];
@@ -802,26 +830,14 @@ __global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull(KmDev d) {
                 }
             }
         }
-        // ---- colour bounding box of the tile (bytewise SIMD min/max, then warp + block reduce) ----
-        uint32_t mn = 0xffffffffu, mx = 0u;
-#pragma unroll
-        for (int p = 0; p < PX; p++)
-            if (p < nv) { mn = __vminu4(mn, px[p]); mx = __vmaxu4(mx, px[p]); }
-        for (int o = 16; o > 0; o >>= 1) {
-            mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            mx = __vmaxu4(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        }
+        // ---- static colour bounding box of the tile (km_tile_boxes_xy, once per session) ----
+        const uint2 box = d.tile_box[tile];
         __syncthreads();  // previous tile is done with s_box / t_ent
-        if (tid < 3) { s_box[tid] = 255u; s_box[3 + tid] = 0u; }
-        if (tid == 3) s_box[6] = 0xffffffffu;
-        __syncthreads();
-        if (lane < 3) {
-            atomicMin(&s_box[lane], (mn >> (8 * lane)) & 0xff);
-            atomicMax(&s_box[3 + lane], (mx >> (8 * lane)) & 0xff);
-        }
+        if (tid == 0) s_box[6] = 0xffffffffu;
         __syncthreads();
         const int bx0 = x0, bx1 = x0 + vw - 1, by0 = yg0, by1 = yg0 + vh - 1;
-        const int r0 = s_box[0], g0 = s_box[1], b0 = s_box[2], r1 = s_box[3], g1 = s_box[4], b1 = s_box[5];
+        const int r0 = box.x & 0xff, g0 = (box.x >> 8) & 0xff, b0 = (box.x >> 16) & 0xff;
+        const int r1 = box.y & 0xff, g1 = (box.y >> 8) & 0xff, b1 = (box.y >> 16) & 0xff;
         const uint32_t sup = (ty / (SH / TH)) * d.super_x + tx / (SW / TW);
         const uint32_t m = d.sc_count[sup];
         const uint16_t *list = d.sc_list + (size_t)sup * k;
@@ -1421,6 +1437,15 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
         dv.pts_sorted = km->d_sorted;
         dv.perm = km->d_perm;
         dv.wts_sorted = km->d_wsorted;
+    }
+    if (D == 5 && km->cull && desc->n_local) {
+        const size_t ntiles = (size_t)((desc->w + TW - 1) / TW) * ((desc->h_local + TH - 1) / TH);
+        km->d_boxes = static_cast<uint2 *>(cniic_cache_alloc(ctx, ntiles * 8));
+        if (!km->d_boxes) return fail(CNIIC_ERR_CUDA);
+        km_tile_boxes_xy<<<(unsigned)ntiles, THREADS, 0, ctx->stream>>>(d_rgb, desc->w, desc->h_local, km->d_boxes);
+        km->launches++;
+        KM_TRY(cudaGetLastError());
+        dv.tile_box = km->d_boxes;
     }
     // shared memory + persistent grid
     if (D == 5 && km->cull) {
