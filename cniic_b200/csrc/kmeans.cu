@@ -841,8 +841,10 @@ __global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull(KmDev d) {
         const uint32_t sup = (ty / (SH / TH)) * d.super_x + tx / (SW / TW);
         const uint32_t m = d.sc_count[sup];
         const uint16_t *list = d.sc_list + (size_t)sup * k;
-        // ---- pass 1: U = min_c UB_c over the supertile's list ----
+        // ---- pass 1: U = min_c UB_c over the supertile's list (the first 256 candidates stay in registers for pass 2) ----
         uint32_t umin = 0xffffffffu;
+        uint4 ent0 = make_uint4(0, 0, 0, 0);
+        uint32_t lb0 = 0xffffffffu;
         for (uint32_t j = tid; j < m; j += THREADS) {
             const uint32_t id = list[j];
             const uint32_t cxy = d.g_cxy[id], cp = d.g_cpk[id];
@@ -850,6 +852,11 @@ __global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull(KmDev d) {
             const uint32_t ub = sq(max(abs(cx - bx0), abs(cx - bx1))) + sq(max(abs(cy - by0), abs(cy - by1))) +
                                 sq(max(abs(cr - r0), abs(cr - r1))) + sq(max(abs(cg - g0), abs(cg - g1))) + sq(max(abs(cb - b0), abs(cb - b1)));
             umin = min(umin, ub);
+            if (j < THREADS) {
+                lb0 = sq(max(0, max(bx0 - cx, cx - bx1))) + sq(max(0, max(by0 - cy, cy - by1))) +
+                      sq(max(0, max(r0 - cr, cr - r1))) + sq(max(0, max(g0 - cg, cg - g1))) + sq(max(0, max(b0 - cb, cb - b1)));
+                ent0 = make_uint4(cp, cxy, uint32_t(2 * (x0 * cx + yg0 * cy) - int(d.g_nrm[id])), id);
+            }
         }
         for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
         if (lane == 0) atomicMin(&s_box[6], umin);
@@ -866,8 +873,10 @@ __global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull(KmDev d) {
         for (uint32_t base = 0; base < m; base += TCAP) {
             const uint32_t j = base + tid;
             bool keep = false;
-            uint4 ent = make_uint4(0, 0, 0, 0);
-            if (j < m) {
+            uint4 ent = ent0;
+            if (base == 0) {
+                keep = j < m && lb0 <= U;
+            } else if (j < m) {
                 const uint32_t id = list[j];
                 const uint32_t cxy = d.g_cxy[id], cp = d.g_cpk[id];
                 const int cx = cxy & 0xffff, cy = cxy >> 16, cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
