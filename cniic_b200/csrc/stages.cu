@@ -33,8 +33,51 @@ __device__ __forceinline__ uint32_t block_rank256(bool flag, uint32_t *s_warp, u
     return before + __popc(bal & ((1u << lane) - 1));
 }
 
+constexpr int FSW = 512, FSH = 256;  // supertile of the fill pre-pass (8 x 4 tiles)
+
+// level 1: one CTA per 512x256 supertile keeps the centroids that can be nearest to some pixel of it (ascending ids)
+__global__ void __launch_bounds__(256) fill_supercull_kernel(const uint32_t *__restrict__ cxy, uint32_t k, uint32_t w, uint32_t y0, uint32_t h_local,
+                                                             uint32_t super_x, uint16_t *lists, uint32_t *counts) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_U;
+    const int tid = threadIdx.x;
+    const int x0 = (blockIdx.x % super_x) * FSW, yl0 = (blockIdx.x / super_x) * FSH;
+    const int x1 = min(x0 + FSW, (int)w) - 1, gy0 = y0 + yl0, gy1 = y0 + min(yl0 + FSH, (int)h_local) - 1;
+    if (tid == 0) s_U = 0xffffffffu;
+    __syncthreads();
+    uint32_t umin = 0xffffffffu;
+    for (uint32_t c = tid; c < k; c += 256) {
+        const int cx = (int)cxy[2 * c], cy = (int)cxy[2 * c + 1];
+        const uint32_t dx = max(abs(cx - x0), abs(cx - x1)), dy = max(abs(cy - gy0), abs(cy - gy1));
+        umin = min(umin, dx * dx + dy * dy);
+    }
+    for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+    if ((tid & 31) == 0) atomicMin(&s_U, umin);
+    __syncthreads();
+    const uint32_t U = s_U;
+    uint16_t *list = lists + (size_t)blockIdx.x * k;
+    uint32_t placed = 0;
+    for (uint32_t cb = 0; cb < k; cb += 256) {
+        const uint32_t c = cb + tid;
+        bool keep = false;
+        if (c < k) {
+            const int cx = (int)cxy[2 * c], cy = (int)cxy[2 * c + 1];
+            const uint32_t dx = max(0, max(x0 - cx, cx - x1)), dy = max(0, max(gy0 - cy, cy - gy1));
+            keep = dx * dx + dy * dy <= U;
+        }
+        uint32_t tot;
+        const uint32_t r = block_rank256(keep, s_warp, &tot);
+        if (keep) list[placed + r] = (uint16_t)c;
+        placed += tot;
+    }
+    if (tid == 0) counts[blockIdx.x] = placed;
+}
+
+// level 2: 64x64 tile per CTA, bounds over the supertile's list, survivors scored per pixel (first minimum = lowest id)
 __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ cxy, const uint8_t *__restrict__ crgb, uint32_t k,
-                                                   uint32_t w, uint32_t y0, uint32_t h_local, uint8_t *__restrict__ out) {
+                                                   uint32_t w, uint32_t y0, uint32_t h_local, uint32_t super_x,
+                                                   const uint16_t *__restrict__ lists, const uint32_t *__restrict__ counts,
+                                                   uint8_t *__restrict__ out) {
     extern __shared__ uint4 fsm[];
     int2 *s_c = reinterpret_cast<int2 *>(fsm);                 // candidate coordinates
     uint16_t *s_i = reinterpret_cast<uint16_t *>(s_c + k);     // candidate ids
@@ -43,14 +86,19 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ 
     const int tid = threadIdx.x;
     const uint32_t tiles_x = (w + FT - 1) / FT, tiles_y = (h_local + FT - 1) / FT;
     for (uint32_t tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
-        const int x0 = (tile % tiles_x) * FT, yl0 = (tile / tiles_x) * FT;
+        const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+        const int x0 = tx * FT, yl0 = ty * FT;
         const int x1 = min(x0 + FT, (int)w) - 1, yl1 = min(yl0 + FT, (int)h_local) - 1;
         const int gy0 = y0 + yl0, gy1 = y0 + yl1;
+        const uint32_t sup = (ty / (FSH / FT)) * super_x + tx / (FSW / FT);
+        const uint32_t m = counts[sup];
+        const uint16_t *list = lists + (size_t)sup * k;
         __syncthreads();
         if (tid == 0) s_U = 0xffffffffu;
         __syncthreads();
         uint32_t umin = 0xffffffffu;
-        for (uint32_t c = tid; c < k; c += 256) {
+        for (uint32_t j = tid; j < m; j += 256) {
+            const uint32_t c = list[j];
             const int cx = (int)cxy[2 * c], cy = (int)cxy[2 * c + 1];
             const uint32_t dx = max(abs(cx - x0), abs(cx - x1)), dy = max(abs(cy - gy0), abs(cy - gy1));
             umin = min(umin, dx * dx + dy * dy);
@@ -60,11 +108,13 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ 
         __syncthreads();
         const uint32_t U = s_U;
         uint32_t ncand = 0;
-        for (uint32_t cb = 0; cb < k; cb += 256) {
-            const uint32_t c = cb + tid;
+        for (uint32_t jb = 0; jb < m; jb += 256) {
+            const uint32_t j = jb + tid;
             bool keep = false;
             int cx = 0, cy = 0;
-            if (c < k) {
+            uint32_t c = 0;
+            if (j < m) {
+                c = list[j];
                 cx = (int)cxy[2 * c]; cy = (int)cxy[2 * c + 1];
                 const uint32_t dx = max(0, max(x0 - cx, cx - x1)), dy = max(0, max(gy0 - cy, cy - gy1));
                 keep = dx * dx + dy * dy <= U;
@@ -94,13 +144,26 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ 
                     if (dd < bd[p]) { bd[p] = dd; bi[p] = j; }
                 }
             }
-            uint8_t *o = out + ((size_t)yl * w + x0 + seg) * 3;
+            uint32_t col[16];
 #pragma unroll
             for (int p = 0; p < 16; p++) {
-                if (x0 + seg + p <= x1) {
-                    const uint32_t id = s_i[bi[p]];
-                    o[3 * p] = crgb[3 * id]; o[3 * p + 1] = crgb[3 * id + 1]; o[3 * p + 2] = crgb[3 * id + 2];
+                const uint32_t id = s_i[bi[p]];
+                col[p] = uint32_t(crgb[3 * id]) | (uint32_t(crgb[3 * id + 1]) << 8) | (uint32_t(crgb[3 * id + 2]) << 16);
+            }
+            uint8_t *o = out + ((size_t)yl * w + x0 + seg) * 3;
+            if (x0 + seg + 15 <= x1 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {  // 16 pixels = three 128-bit stores
+                uint32_t wd[12];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t a = col[4 * q], b = col[4 * q + 1], c = col[4 * q + 2], e = col[4 * q + 3];
+                    wd[3 * q] = a | (b << 24); wd[3 * q + 1] = (b >> 8) | (c << 16); wd[3 * q + 2] = (c >> 16) | (e << 8);
                 }
+                uint4 *o4 = reinterpret_cast<uint4 *>(o);
+                o4[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]); o4[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]); o4[2] = make_uint4(wd[8], wd[9], wd[10], wd[11]);
+            } else {
+#pragma unroll
+                for (int p = 0; p < 16; p++)
+                    if (x0 + seg + p <= x1) { o[3 * p] = col[p]; o[3 * p + 1] = col[p] >> 8; o[3 * p + 2] = col[p] >> 16; }
             }
         }
     }
@@ -906,9 +969,15 @@ extern "C" int cniic_voronoi_fill_device(cniic_ctx *ctx, const uint32_t *d_cxy, 
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t smem = (size_t)k * 10 + 16;
     CU_TRY(ctx, cudaFuncSetAttribute(fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t super_x = (w + FSW - 1) / FSW, super_y = (h_local + FSH - 1) / FSH;
+    DevBuf lists(ctx), counts(ctx);
+    CU_TRY(ctx, lists.alloc((size_t)super_x * super_y * k * 2));
+    CU_TRY(ctx, counts.alloc((size_t)super_x * super_y * 4));
+    fill_supercull_kernel<<<super_x * super_y, 256, 0, ctx->stream>>>(d_cxy, k, w, y0, h_local, super_x, lists.as<uint16_t>(), counts.as<uint32_t>());
     const size_t tiles = (size_t)((w + FT - 1) / FT) * ((h_local + FT - 1) / FT);
     const int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 8);
-    fill_kernel<<<grid, 256, smem, ctx->stream>>>(d_cxy, d_crgb, k, w, y0, h_local, d_out_rgb);
+    fill_kernel<<<grid, 256, smem, ctx->stream>>>(d_cxy, d_crgb, k, w, y0, h_local, super_x, lists.as<uint16_t>(), counts.as<uint32_t>(), d_out_rgb);
+    ctx->launches++;
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
