@@ -18,6 +18,7 @@ OK, ERR_BAD_ARG, ERR_TOO_FEW_POINTS, ERR_TOO_FEW_ACTIVE, ERR_CUDA, ERR_NCCL, ERR
 TIE_KEEP_CURRENT, TIE_LOWEST_INDEX = 0, 1
 POINTS_RGB, POINTS_XYRGB = 0, 1
 KMEANS_NO_CULL = 1
+KMEANS_FORCE_CULL = 2
 MAX_K, MAX_DIM = 4096, 16384
 
 

@@ -260,6 +260,7 @@ extern "C" void cniic_ctx_destroy(cniic_ctx *ctx) {
     if (ctx->p2p_peer_table) cudaFree(ctx->p2p_peer_table);
     if (ctx->p2p_local) cudaFree(ctx->p2p_local);
     for (void *p : ctx->pinned_free) cudaFreeHost(p);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -30,6 +30,7 @@ struct cniic_ctx {
     struct Block { void *p; size_t bytes; bool used; };
     std::vector<Block> cache;
     std::vector<void *> pinned_free;  // 256-byte pinned host slots
+    std::vector<cudaEvent_t> event_pool;
     // peer-memory exchange (multi-GPU): my IPC region, the peer-mapped bases of all ranks (device table), sequence number
     unsigned long long *p2p_local = nullptr;
     unsigned long long **p2p_peer_table = nullptr;  // device array [world]

@@ -78,6 +78,7 @@ struct KmDev {
     const uint32_t *perm;
     const uint32_t *wts_sorted;
     // peer-memory all-reduce fused into km_finalize (multi-GPU, one process per GPU)
+    int brute;                                 // 1: the brute-force kernels run, so km_finalize must build the parity-class scan table
     int p2p;                                   // 1: sums live in the IPC exchange region, no NCCL call
     int my_rank;
     uint32_t seq;                              // global iteration sequence number of this launch
@@ -1141,9 +1142,21 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
         __syncthreads();
     }
 
+    if (!d.brute) {
+        // culled kernels only need the per-centroid arrays in id order
+        for (uint32_t c = tid; c < k; c += 1024) {
+            int32_t v[D];
+            uint32_t nrm = 0;
+            for (int j = 0; j < D; j++) { v[j] = d.cen[c * D + j]; nrm += uint32_t(v[j] * v[j]); }
+            const int rgb0 = D == 5 ? 2 : 0;
+            d.g_cpk[c] = uint32_t(v[rgb0]) | (uint32_t(v[rgb0 + 1]) << 8) | (uint32_t(v[rgb0 + 2]) << 16);
+            d.g_nrm[c] = nrm;
+            if (D == 5) d.g_cxy[c] = uint32_t(v[0]) | (uint32_t(v[1]) << 16);
+        }
+    }
     // ---- build the scan table: even-|c|^2 class first, then odd, each in ascending id order, padded to G ----
     uint32_t n0 = 0;
-    for (int cls = 0; cls < 2; cls++) {
+    for (int cls = 0; cls < 2 && d.brute; cls++) {
         uint32_t placed = 0;
         const uint32_t start = cls == 0 ? 0 : (n0 + G - 1) / G * G;
         for (uint32_t cb = 0; cb < k; cb += 1024) {
@@ -1425,6 +1438,8 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     dv.super_y = super_y;
 
     km->cull = !(desc->flags & CNIIC_KMEANS_NO_CULL) && !getenv("CNIIC_NO_CULL");
+    // small D = 3 problems: the one-time colour sort costs more than brute-force scoring saves (break-even ~2^27 pairs/iteration)
+    if (D == 3 && (unsigned long long)desc->n_total * k < (1ull << 27) && !(desc->flags & CNIIC_KMEANS_FORCE_CULL)) km->cull = false;
     if (D == 3 && km->cull && desc->n_local) {
         // colour-sorted copy of the points (Morton order), built once per session
         const size_t n = desc->n_local;
@@ -1456,6 +1471,7 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
         KM_TRY(cudaGetLastError());
         dv.tile_box = km->d_boxes;
     }
+    dv.brute = km->cull ? 0 : 1;
     // shared memory + persistent grid
     if (D == 5 && km->cull) {
         km->smem = size_t(TCAP) * 16 + size_t(k) * 24 + 16;
@@ -1484,9 +1500,15 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
                                                   : (unsigned long long)((desc->w + 255) / 256) * ((desc->h_local + 7) / 8))
                                       : (desc->n_local + TILE - 1) / TILE;
     km->grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(tiles, (unsigned long long)per_sm * ctx->sm_count));
-    KM_TRY(cudaEventCreate(&km->ev0));
-    KM_TRY(cudaEventCreate(&km->ev1));
-    for (int i = 0; i < 2 * cniic_kmeans::PROF; i++) KM_TRY(cudaEventCreate(&km->pev[i]));
+    {   // events come from a per-context pool (creating 66 events per session costs ~0.1 ms)
+        auto take_event = [&](cudaEvent_t *e) -> cudaError_t {
+            if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return cudaSuccess; }
+            return cudaEventCreate(e);
+        };
+        KM_TRY(take_event(&km->ev0));
+        KM_TRY(take_event(&km->ev1));
+        for (int i = 0; i < 2 * cniic_kmeans::PROF; i++) KM_TRY(take_event(&km->pev[i]));
+    }
 #undef KM_TRY
     km_report_launches(km);
     *out = km;
@@ -1579,7 +1601,7 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
     uint32_t issued = 0;            // assign launches of this call (indexes the profiling events)
     uint32_t done_iters = 0;        // iterations completed by this call (state.iter - iter_seen)
     for (;;) {
-        uint32_t batch = 4;  // kernels (and the all-reduce) early-exit / are harmless once `done` or a halt is set
+        uint32_t batch = 8;  // kernels (and the all-reduce) early-exit / are harmless once `done` or a halt is set
         if (max_iters) batch = std::min(batch, max_iters - done_iters);
         for (uint32_t b = 0; b < batch; b++) {
             const bool prof = issued < (uint32_t)cniic_kmeans::PROF;
@@ -1680,10 +1702,10 @@ extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
     cniic_cache_free(km->ctx, km->d_wsorted);
     cniic_cache_free(km->ctx, km->d_assign_orig);
     cniic_pinned_put(km->ctx, km->h_state);
-    if (km->ev0) cudaEventDestroy(km->ev0);
-    if (km->ev1) cudaEventDestroy(km->ev1);
+    if (km->ev0) km->ctx->event_pool.push_back(km->ev0);
+    if (km->ev1) km->ctx->event_pool.push_back(km->ev1);
     for (cudaEvent_t e : km->pev)
-        if (e) cudaEventDestroy(e);
+        if (e) km->ctx->event_pool.push_back(e);
     delete km;
 }
 

@@ -110,6 +110,7 @@ int cniic_kmeans_xyrgb(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t 
 /* Session form: points stay resident in HBM across calls (what bench.py's device-resident `value` times, and what
  * the row-sharded multi-GPU path uses).                                                                          */
 #define CNIIC_POINTS_RGB 0   /* D = 3, points = packed RGB8 bytes (3 B / point)                                  */
+#define CNIIC_KMEANS_FORCE_CULL 2 /* RGB: use the colour-sorted culled kernel even for small problems (default: brute force below 2^27 pairs) */
 #define CNIIC_KMEANS_NO_CULL 1 /* XYRGB: scan all k centroids for every pixel (brute force) instead of exact tile culling */
 #define CNIIC_POINTS_XYRGB 1 /* D = 5, points = pixels of a raster image (x, y synthesised from the index)       */
 

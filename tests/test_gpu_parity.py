@@ -77,6 +77,14 @@ def test_kmeans_rgb_empty_clusters_are_repaired_deterministically(ctx, seed):  #
         o = O.kmeans_rgb(pts, k, mode=O.MODE_EXACT, tie=tie, max_iters=8, allow_inactive=True)
         events += o.empty_events
         same_kmeans(g, o)
+        # the same through the colour-sorted culled kernel (its repair path maps through the permutation)
+        s = cb.KMeansSession(ctx, cb.POINTS_RGB, k, pts, len(pts), tie=tie, flags=cb._lib.KMEANS_FORCE_CULL)
+        s.reset()
+        st = s.run(8)
+        cen, wsum, asg = s.get()
+        s.close()
+        assert st.iterations == o.iterations and st.empty_events == o.empty_events
+        assert np.array_equal(cen, o.centroids) and np.array_equal(asg, o.assign) and np.array_equal(wsum, o.weights)
         assert g.status == o.status  # kmeans.rs:41-57 too-few-active check (seed 9 trips it)
     assert events > 0
 
@@ -142,13 +150,14 @@ def test_kmeans_xyrgb_brute_force_kernel(ctx, w, h, k):
     assert st.iterations == 3 and np.array_equal(cen, o.centroids) and np.array_equal(asg, o.assign) and np.array_equal(wts, o.weights)
 
 
+@pytest.mark.parametrize("flag", ["NO_CULL", "FORCE_CULL"])
 @pytest.mark.parametrize("n,k,weighted", [(5000, 16, False), (70000, 256, False), (33333, 300, True), (2048 * 3 + 5, 64, True)])
-def test_kmeans_rgb_brute_force_kernel(ctx, n, k, weighted):
-    """The non-culled D = 3 kernel (CNIIC_KMEANS_NO_CULL) must agree with the oracle as well."""
+def test_kmeans_rgb_both_kernels(ctx, n, k, weighted, flag):
+    """Small D = 3 problems default to the brute-force kernel; both it and the colour-sorted culled kernel must agree with the oracle."""
     rng = np.random.default_rng(n)
     pts = cb.synth_image_host(256, (n + 255) // 256, 77, 9).reshape(-1, 3)[:n]
     wts = rng.integers(1, 1000, n).astype(np.uint32) if weighted else None
-    s = cb.KMeansSession(ctx, cb.POINTS_RGB, k, pts, n, weights=wts, flags=cb._lib.KMEANS_NO_CULL)
+    s = cb.KMeansSession(ctx, cb.POINTS_RGB, k, pts, n, weights=wts, flags=getattr(cb._lib, "KMEANS_" + flag))
     s.reset()
     st = s.run(4)
     cen, wsum, asg = s.get()
