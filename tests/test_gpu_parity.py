@@ -128,6 +128,28 @@ def test_kmeans_xyrgb(ctx, w, h, k, tie):
         same_kmeans(g, o)
 
 
+@pytest.mark.parametrize("w,h,k", [(1, 97, 5), (97, 1, 5), (7, 3, 21), (513, 65, 4096), (1030, 40, 1000)])
+def test_kmeans_xyrgb_degenerate_shapes_and_max_k(ctx, w, h, k):
+    img = cb.synth_image_host(w, h, 3, 9)
+    for tie in (cb.TIE_KEEP_CURRENT, cb.TIE_LOWEST_INDEX):
+        g = ctx.kmeans_xyrgb(img, k, max_iters=3, tie=tie, allow_inactive=True)
+        o = O.kmeans_xyrgb(img, k, mode=O.MODE_EXACT, tie=tie, max_iters=3, allow_inactive=True)
+        same_kmeans(g, o)
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (7, 7), (9, 2), (4096 * 3, 4096), (100003, 1000)])
+def test_kmeans_rgb_degenerate_sizes_and_max_k(ctx, n, k):
+    pts = cb.synth_image_host(251, (n + 250) // 251, 5, 7).reshape(-1, 3)[:n]
+    for flag in ("NO_CULL", "FORCE_CULL"):
+        s = cb.KMeansSession(ctx, cb.POINTS_RGB, k, pts, n, flags=getattr(cb._lib, "KMEANS_" + flag))
+        s.reset()
+        st = s.run(3)
+        cen, wsum, asg = s.get()
+        s.close()
+        o = O.kmeans_rgb(pts, k, mode=O.MODE_EXACT, max_iters=3, allow_inactive=True)
+        assert st.iterations == o.iterations and np.array_equal(cen, o.centroids) and np.array_equal(asg, o.assign)
+
+
 def test_kmeans_xyrgb_flat_image_has_exact_ties(ctx):
     """A constant-colour image makes many pixels equidistant from two centroids: the documented near-tie cases."""
     img = np.full((40, 64, 3), 77, np.uint8)

@@ -1,0 +1,23 @@
+"""compute-sanitizer memcheck target: one small invocation of every kernel family (GPU box helper, not a test)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import cniic_b200 as cb
+from cniic_b200 import codecs
+ctx = cb.Context(0)
+img = cb.synth_image_host(203, 77, 1, 6)
+sq = cb.synth_image_host(128, 128, 2, 6)
+for flag in (cb._lib.KMEANS_NO_CULL, cb._lib.KMEANS_FORCE_CULL):
+    s = cb.KMeansSession(ctx, cb.POINTS_RGB, 37, img, 203 * 77, flags=flag); s.reset(); s.run(3); s.get(); s.close()
+    s = cb.KMeansSession(ctx, cb.POINTS_XYRGB, 300, img, 203 * 77, w=203, h_local=77, flags=flag & 1); s.reset(); s.run(3); s.get(); s.close()
+keys, cnts = ctx.hist_rgb(img)
+s = cb.KMeansSession(ctx, cb.POINTS_RGB, 16, np.stack([keys >> 16, (keys >> 8) & 255, keys & 255], 1).astype(np.uint8), len(keys),
+                     weights=cnts.astype(np.uint32), flags=cb._lib.KMEANS_FORCE_CULL); s.reset(); s.run(3); s.get(); s.close()
+ctx.cluster_colors(img, 16, max_iters=3)
+ctx.voronoi_fill(np.array([[3, 4], [100, 50], [202, 76]], np.uint32), np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]], np.uint8), 203, 77)
+for im in (img, sq):
+    ctx.hilbert_xy(im.shape[1], im.shape[0]); ctx.hilbert_gather(im); d = ctx.delta(im); ctx.undelta(d, im.shape[1], im.shape[0]); ctx.hist_delta(im)
+    for e in ("hufman", "delta", "hilbert(rle)", "voronoi(8)", "cluster-colors(8)"):
+        c = codecs.Codec.from_str(ctx, e, 3); c.decode(c.encode(im))
+ctx.sse(img, img[::-1].copy())
+print("sanitize target done")
