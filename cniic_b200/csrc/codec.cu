@@ -6,7 +6,7 @@
 // GPU; the Huffman tree (<= #symbols nodes), the decoders' bit-serial trie walk and the run-length pass run on the host.
 #include <cctype>
 #include <cstring>
-#include <queue>
+#include <algorithm>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -85,25 +85,34 @@ struct HufTree {
 bool huf_build(const std::vector<uint64_t> &freq, HufTree *T) {
     const size_t n = freq.size();
     if (n == 0) return false;
-    typedef std::pair<std::pair<uint64_t, uint32_t>, int> Item;  // ((freq, seq), node)
-    std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
+    // Two-queue construction.  It reproduces the min-heap ordered by (freq, creation sequence) exactly: leaves are
+    // taken in (freq, symbol id) order, internal nodes are created with non-decreasing freq and increasing sequence
+    // numbers, and on equal freq a leaf (smaller sequence number) precedes any internal node.
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return freq[a] < freq[b]; });
     T->nodes.reserve(2 * n);
     std::vector<uint64_t> nf;
     nf.reserve(2 * n);
     for (size_t i = 0; i < n; i++) {
         T->nodes.push_back({-1, -1, (uint32_t)i});
         nf.push_back(freq[i]);
-        heap.push({{freq[i], (uint32_t)i}, (int)i});
     }
-    while (heap.size() > 1) {
-        const int l = heap.top().second; heap.pop();
-        const int r = heap.top().second; heap.pop();
-        const int id = (int)T->nodes.size();
+    size_t li = 0, ii = n;  // next leaf (index into order), next internal node (node id)
+    auto pop_min = [&]() -> int {
+        const bool has_leaf = li < n, has_int = ii < T->nodes.size();
+        if (has_leaf && (!has_int || nf[order[li]] <= nf[ii])) return (int)order[li++];
+        return (int)ii++;
+    };
+    size_t remaining = n;
+    while (remaining > 1) {
+        const int l = pop_min();
+        const int r = pop_min();
         T->nodes.push_back({l, r, 0});
         nf.push_back(nf[l] + nf[r]);
-        heap.push({{nf[id], (uint32_t)id}, id});
+        remaining--;
     }
-    T->root = heap.top().second;
+    T->root = (n == 1) ? 0 : (int)T->nodes.size() - 1;
     T->code.assign(n, 0);
     T->len.assign(n, 0);
     // iterative DFS assigning codes
@@ -172,18 +181,38 @@ bool huf_deserialize(Source &src, size_t sym_size, DecTrie *T) {
     }
 }
 
-// huf.rs:187-206 trie walk over MSB-first bits; decodes exactly n symbols
+// huf.rs:187-206 trie walk over MSB-first bits; decodes exactly n symbols.  A 12-bit prefix table resolves short codes
+// in one step (entry = node reached after consuming `used` bits; leaves stop early), longer codes continue bit by bit.
 bool huf_decode(Source &src, const DecTrie &T, size_t sym_size, size_t n, uint8_t *out) {
+    constexpr int L = 12;
+    struct Ent { int node; int used; };
+    std::vector<Ent> lut(size_t(1) << L);
+    for (uint32_t pre = 0; pre < (1u << L); pre++) {
+        int nd = 0, used = 0;
+        while (used < L && T.nodes[nd].left >= 0) {
+            nd = ((pre >> (L - 1 - used)) & 1) ? T.nodes[nd].right : T.nodes[nd].left;
+            used++;
+        }
+        lut[pre] = {nd, used};
+    }
     size_t bit = src.pos * 8;
     const size_t end = src.len * 8;
+    auto peek = [&](size_t at) -> uint32_t {  // L bits starting at `at`, zero padded past the end
+        uint32_t v = 0;
+        const size_t byte = at >> 3;
+        for (int i = 0; i < 3; i++) v = (v << 8) | (byte + i < src.len ? src.p[byte + i] : 0);
+        return (v >> (24 - L - (at & 7))) & ((1u << L) - 1);
+    };
     for (size_t i = 0; i < n; i++) {
-        int nd = 0;
+        const Ent e = lut[peek(bit)];
+        if (bit + e.used > end) return false;
+        bit += e.used;
+        int nd = e.node;
         while (T.nodes[nd].left >= 0) {
             if (bit >= end) return false;
             const int b = (src.p[bit >> 3] >> (7 - (bit & 7))) & 1;
             bit++;
             nd = b ? T.nodes[nd].right : T.nodes[nd].left;
-            if (nd < 0) return false;
         }
         memcpy(out + i * sym_size, T.nodes[nd].val, sym_size);
     }
