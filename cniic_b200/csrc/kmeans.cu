@@ -1028,8 +1028,11 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
         volatile uint32_t *arrived = reinterpret_cast<volatile uint32_t *>(d.peer_base[d.my_rank] + 2 * P2P_SUMS_MAX);
         if (tid < d.world) {
             __threadfence_system();
-            volatile uint32_t *remote = reinterpret_cast<volatile uint32_t *>(d.peer_base[tid] + 2 * P2P_SUMS_MAX);
-            remote[d.my_rank] = d.seq;  // push my arrival into every rank's flag array (NVLink store)
+            uint32_t *remote = reinterpret_cast<uint32_t *>(d.peer_base[tid] + 2 * P2P_SUMS_MAX);
+            // push my arrival into every rank's flag array: a system-scope atomic is not a posted write, it completes before
+            // this thread starts to spin (a plain NVLink store could sit in a write buffer while every rank waits)
+            atomicExch_system(remote + d.my_rank, d.seq);
+            __threadfence_system();
             unsigned long long spins = 0;
             while (int(arrived[tid] - d.seq) < 0) {
                 if (++spins > (1ull << 25)) { d.st->dist_empty = 2; break; }  // never hang the GPU: report and carry on
