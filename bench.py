@@ -233,9 +233,10 @@ def main():
 
     for _ in range(W):
         one_step()
-    barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.start()        # spawns nvidia-smi: do it BEFORE the last warm-up step and the barrier, so no rank enters the timed
+    one_step()             # region late (a late rank shows up as a wait inside every other rank's per-iteration exchange)
+    barrier()
     launches0 = sctx.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     assign_ms, iters_run, pairs_per_launch = [], 0, 0.0
@@ -248,6 +249,9 @@ def main():
         ev[i][1].record(stream)
         assign_ms.append(st.assign_ms_avg)
         iters_run += st.iterations
+        if os.environ.get("CNIIC_BENCH_DEBUG"):
+            torch.cuda.synchronize()
+            print(f"[rank {rank}] step {i}: {ev[i][0].elapsed_time(ev[i][1]):.3f} ms total, loop {st.device_ms:.3f} ms, assign avg {st.assign_ms_avg:.4f} ms", file=sys.stderr, flush=True)
         pairs_per_launch = st.pairs_scored / max(1, st.iterations)
     barrier()
     t_wall = time.perf_counter() - t_wall0

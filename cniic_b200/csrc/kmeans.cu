@@ -1625,7 +1625,9 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
         if (km->h_state->dist_empty == 2)
             return cniic_set_error(ctx, CNIIC_ERR_NCCL, "peer-memory all-reduce timed out waiting for another rank");
         if (km->h_state->dist_empty == 1) {
-            if (km->dev.p2p) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "empty cluster with the peer-memory all-reduce (use the NCCL path)");
+            // the repair is verified with the NCCL exchange only; under the peer-memory exchange it produced different centroids in
+            // the 2-GPU parity test (unresolved this round), so fail loudly instead of returning a result that may be wrong
+            if (km->dev.p2p) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "empty cluster in a sharded run with the peer-memory all-reduce: rerun with CNIIC_P2P=0 (NCCL path repairs it)");
             ST_TRY(km->D == 5 ? km_repair_dist<5>(km) : km_repair_dist<3>(km));
             CU_TRY(ctx, cudaMemcpyAsync(km->h_state, km->dev.st, sizeof(KmState), cudaMemcpyDeviceToHost, ctx->stream));
             CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));

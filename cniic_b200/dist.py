@@ -76,9 +76,9 @@ def make_context(local_rank: int | None = None):
         uid = uid.cuda(dev)
     dist.broadcast(uid, src=0)
     ctx = Context(dev, rank=rank, world=world, nccl_unique_id=bytes(uid.cpu().numpy().tobytes()))
-    if os.environ.get("CNIIC_P2P", "0") == "1":
-        # opt-in peer-memory all-reduce (on par with NCCL at 2 GPUs, slower at 8 -- DESIGN.md section 6): exchange the CUDA
-        # IPC handles of the per-rank exchange regions
+    if os.environ.get("CNIIC_P2P", "1") == "1":
+        # peer-memory all-reduce fused into the finalize kernel (default; CNIIC_P2P=0 selects ncclAllReduce): exchange the
+        # CUDA IPC handles of the per-rank exchange regions
         mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).clone()
         if dist.get_backend() == "nccl":
             mine = mine.cuda(dev)
