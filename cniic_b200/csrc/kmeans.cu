@@ -1022,9 +1022,10 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
     unsigned long long moved = 0;
 
     const unsigned long long *rs = d.p2p ? d.sums_red : d.sums;
-    if (init_mode == 0 && d.p2p) {
-        // ---- all-reduce over peer memory: publish, wait for every rank, sum the partials in rank order ----
-        // The assign kernel of this iteration has completed (stream order), so my partial sums are in my exchange buffer.
+    if (init_mode != 2 && d.p2p) {
+        // ---- barrier over peer memory: publish my arrival for sequence number d.seq, wait for every rank ----
+        // (init_mode 0: the assign kernel of this iteration has completed, so my partial sums are in my exchange buffer;
+        //  init_mode 1: every rank has finished all work of the previous session)
         volatile uint32_t *arrived = reinterpret_cast<volatile uint32_t *>(d.peer_base[d.my_rank] + 2 * P2P_SUMS_MAX);
         if (tid < d.world) {
             __threadfence_system();
@@ -1039,6 +1040,18 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
             }
             __threadfence_system();
         }
+        __syncthreads();
+    }
+    if (init_mode != 0 && d.p2p) {
+        // (re)start of a session or resume after a repair: launches that exit early (converged / halted) still advance the
+        // sequence number, so the next iteration may land on either ping-pong buffer -- clear both.  Safe: a barrier (above,
+        // or the repair's all-gather) guarantees that no rank still reads them.
+        unsigned long long *mine = d.peer_base[d.my_rank];
+        for (uint32_t i = tid; i < 2 * P2P_SUMS_MAX; i += 1024) mine[i] = 0ull;
+        __syncthreads();
+    }
+    if (init_mode == 0 && d.p2p) {
+        // ---- all-reduce: sum every rank's partials in rank order ----
         __syncthreads();
         const uint32_t len = k * DW + 1;
         const size_t boff = size_t(d.seq & 1) * P2P_SUMS_MAX;
@@ -1537,6 +1550,7 @@ extern "C" int cniic_kmeans_reset(cniic_kmeans *km, const int32_t *host_init_cen
     }
     CU_TRY(ctx, cudaGetLastError());
     km->iter_seen = 0;
+    if (km->dev.p2p) km->dev.seq = ++ctx->p2p_seq;  // the init pass is a barrier over peer memory (all ranks left the previous session)
     const int rc_fin = km_launch_finalize(km, 1);
     km_report_launches(km);
     return rc_fin;
@@ -1625,9 +1639,6 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
         if (km->h_state->dist_empty == 2)
             return cniic_set_error(ctx, CNIIC_ERR_NCCL, "peer-memory all-reduce timed out waiting for another rank");
         if (km->h_state->dist_empty == 1) {
-            // the repair is verified with the NCCL exchange only; under the peer-memory exchange it produced different centroids in
-            // the 2-GPU parity test (unresolved this round), so fail loudly instead of returning a result that may be wrong
-            if (km->dev.p2p) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "empty cluster in a sharded run with the peer-memory all-reduce: rerun with CNIIC_P2P=0 (NCCL path repairs it)");
             ST_TRY(km->D == 5 ? km_repair_dist<5>(km) : km_repair_dist<3>(km));
             CU_TRY(ctx, cudaMemcpyAsync(km->h_state, km->dev.st, sizeof(KmState), cudaMemcpyDeviceToHost, ctx->stream));
             CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));

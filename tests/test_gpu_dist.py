@@ -36,7 +36,7 @@ for kind, w, h, k in ((cb.POINTS_XYRGB, 640, 363, 128), (cb.POINTS_RGB, 512, 301
     s.close()
     out[f"cen{D}"], out[f"wts{D}"], out[f"asg{D}"], out[f"it{D}"] = cen, wts, asg, np.array([st.iterations, st.moved_last])
 # empty-cluster repair across shards (kmeans.rs:117-134 stand-in): palette point lists that empty clusters
-if os.environ.get("CNIIC_P2P", "1") != "1":  # the repair is supported with the NCCL exchange only
+if True:
     for seed in (0, 4, 9):
         rng = np.random.default_rng(seed)
         npal, k, n = int(rng.integers(3, 10)), int(rng.integers(4, 16)), int(rng.integers(40, 400))
@@ -84,7 +84,7 @@ def test_two_gpu_row_sharded_kmeans_matches_single_gpu(tmp_path, p2p):
         assert np.array_equal(r0[f"wts{D}"], g.weights)
         assert np.array_equal(np.concatenate([r0[f"asg{D}"], r1[f"asg{D}"]]), g.assign)
         assert r0[f"it{D}"].tolist() == [g.iterations, g.moved_last]
-    if p2p != "1":
+    if True:
         events = 0
         for seed in (0, 4, 9):
             rng = np.random.default_rng(seed)
