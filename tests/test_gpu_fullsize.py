@@ -21,11 +21,9 @@ def check_kmeans_properties(pts, cen, wts, asg, k, rng, D):
     assert np.array_equal(cnt.astype(np.uint64), wts)
     # every non-empty centroid is the truncated integer mean of its members (clusterc.rs:81-114 / 215-248)
     for j in range(D):
-        sums = np.bincount(asg, weights=None if False else pts[:, j].astype(np.float64), minlength=k)
+        sums = np.bincount(asg, weights=pts[:, j].astype(np.float64), minlength=k)  # exact: sums < 2^53
         nz = cnt > 0
         assert np.array_equal((sums[nz].astype(np.int64) // cnt[nz]), cen[nz, j])
-    # a sample of points: the assignment is an exact nearest centroid of the PREVIOUS centroids is not observable here,
-    # so check the fixed-point property after convergence instead (done by the caller when converged)
 
 
 def test_c2_cluster_colors_k256_4096(ctx):
@@ -99,7 +97,6 @@ def test_c3_voronoi_k2048_8k(ctx):
 
 def test_c5_integer_stages_8192(ctx):
     w = h = 8192
-    img = cb.synth_image_host(w, h, 0xC0FFEE + 5, 4096) if False else None
     rng = np.random.default_rng(1)
     # smooth-ish random image built cheaply on the host
     base = rng.integers(0, 256, size=(h // 64, w // 64, 3), dtype=np.uint8)
