@@ -1328,8 +1328,10 @@ static void km_report_launches(cniic_kmeans *km) {
 static int km_launch_assign(cniic_kmeans *km) {
     cniic_ctx *ctx = km->ctx;
     if (km->D == 5 && km->cull) {
-        km_supercull<<<km->dev.super_x * km->dev.super_y, THREADS, 0, ctx->stream>>>(km->dev);
-        km->launches++;
+        if (km->dev.super_x * km->dev.super_y) {  // a rank may hold no rows at all
+            km_supercull<<<km->dev.super_x * km->dev.super_y, THREADS, 0, ctx->stream>>>(km->dev);
+            km->launches++;
+        }
         km_assign_xyrgb_cull<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     }
     else if (km->D == 5) km_assign_xyrgb<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
