@@ -165,3 +165,23 @@ def test_oracle_verbatim_vs_exact_divergence_is_small():
     assert np.all(d2[rows, v.assign[rows]] == d2[rows, e.assign[rows]])
     full = O.kmeans_xyrgb(img, 16, mode=O.MODE_VERBATIM)
     assert full.dist_evals < O.kmeans_xyrgb(img, 16, mode=O.MODE_EXACT, max_iters=full.iterations).dist_evals
+
+
+def test_bench_roofline_object():
+    """bench.py's roofline builder on made-up numbers: schema of the judged keys and the arithmetic."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    pk = {"hbm_gbs": 6471.1, "sm_max_mhz": 1965.0, "source": "measured"}
+    n, k = 4096 * 4096, 256
+    r = bench.build_roofline(3, n, k, 0.1, 0.036 * n * k, pk, "km_assign_rgb_cull", 110253056, 0.43)
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] == 6471.1 and r["traffic"] == 110253056
+    assert r["achieved"] == pytest.approx(3 * n / 1e-4 / 1e9) and r["frac"] == pytest.approx(r["achieved"] / 6471.1)
+    f = r["fp32"]
+    assert f["peak"] == pytest.approx(74.45, rel=1e-3)
+    assert f["algorithmic_equiv_tflops"] == pytest.approx(7 * n * k / 1e-4 / 1e12)
+    assert f["brute_force_kernel"]["frac"] == pytest.approx(7 * n * k / 0.43e-3 / 1e12 / f["peak"])
+    assert bench.build_roofline(5, 100, 10, 1.0, 1000.0, pk, "x", None, 0.0)["fp32"]["brute_force_kernel"] is None
+    import json
+    json.dumps(r)
