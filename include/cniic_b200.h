@@ -70,7 +70,8 @@ int cniic_ctx_create(int device, cniic_ctx **out);
  * (cniic_nccl_unique_id) and distributed by the host (torch.distributed store / MPI / file).                   */
 int cniic_ctx_create_dist(int device, int rank, int world, const uint8_t nccl_unique_id[128], cniic_ctx **out);
 int cniic_nccl_unique_id(uint8_t out_id[128]);
-/* Optional peer-memory all-reduce (replaces the per-iteration NCCL call of the row-sharded Lloyd loop): every rank exports
+/* Peer-memory all-reduce (replaces the per-iteration NCCL call of the row-sharded Lloyd loop; cniic_b200/dist.py enables it by
+ * default, without it the library calls ncclAllReduce): every rank exports
  * a CUDA IPC handle of its exchange region, the host gathers the world x 64 bytes, every rank connects.  The finalize kernel
  * then reads all ranks' partial sums over NVLink and reduces them in rank order.            */
 int cniic_ctx_p2p_export(cniic_ctx *ctx, uint8_t out_handle[64]);
@@ -111,7 +112,7 @@ int cniic_kmeans_xyrgb(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t 
  * the row-sharded multi-GPU path uses).                                                                          */
 #define CNIIC_POINTS_RGB 0   /* D = 3, points = packed RGB8 bytes (3 B / point)                                  */
 #define CNIIC_KMEANS_FORCE_CULL 2 /* RGB: use the colour-sorted culled kernel even for small problems (default: brute force below 2^27 pairs) */
-#define CNIIC_KMEANS_NO_CULL 1 /* XYRGB: scan all k centroids for every pixel (brute force) instead of exact tile culling */
+#define CNIIC_KMEANS_NO_CULL 1 /* score all k centroids for every point (brute-force kernels) instead of exact culling; same results */
 #define CNIIC_POINTS_XYRGB 1 /* D = 5, points = pixels of a raster image (x, y synthesised from the index)       */
 
 typedef struct {
@@ -133,7 +134,8 @@ int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, cniic_kmean
 /* (Re)start from the reference's chunked init.  Single GPU: gathered on the device.  Multi-GPU: every rank must
  * pass the same k x D int32 initial centroids (host) computed from the global point list (kmeans.rs:101-108).    */
 int cniic_kmeans_reset(cniic_kmeans *km, const int32_t *host_init_centroids /* nullable on a single GPU */);
-/* Run Lloyd iterations: fused assign+accumulate kernel, [NCCL all-reduce of the k x (D+1) u64 partial sums],
+/* Run Lloyd iterations: fused assign+accumulate kernel, [multi-GPU: all-reduce of the k x (D+1) u64 partial sums, over peer memory
+ * inside the finalize kernel or with NCCL],
  * finalize kernel.  Stops after max_iters (0 = unbounded) or at convergence.                                    */
 int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmeans_stats *stats);
 /* centroids: k x D int32 (D = 3: r,g,b ; D = 5: x,y,r,g,b), weights k x u64, assign n_local x u16 (nullable each) */
