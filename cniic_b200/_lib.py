@@ -51,25 +51,29 @@ def lib() -> C.CDLL:
         if not os.path.exists(SO_PATH):
             raise ImportError(f"{SO_PATH} is missing: build it with `make -C cniic_b200/csrc` "
                               "(__graft_entry__.build()); there is no CPU fallback")
-        L = C.CDLL(SO_PATH)
-        L.cniic_last_error.restype = C.c_char_p
-        L.cniic_ctx_stream.restype = C.c_void_p
-        L.cniic_device_alloc.restype = C.c_void_p
-        L.cniic_device_alloc.argtypes = [C.c_void_p, C.c_size_t]
-        L.cniic_device_free.argtypes = [C.c_void_p, C.c_void_p]
-        L.cniic_device_free.restype = None
-        L.cniic_ctx_destroy.argtypes = [C.c_void_p]
-        L.cniic_ctx_destroy.restype = None
-        L.cniic_kmeans_close.argtypes = [C.c_void_p]
-        L.cniic_kmeans_close.restype = None
-        L.cniic_kmeans_device_assign.restype = C.c_void_p
-        L.cniic_kmeans_device_assign.argtypes = [C.c_void_p]
-        L.cniic_ctx_launches.restype = C.c_uint32
-        L.cniic_ctx_launches.argtypes = [C.c_void_p]
-        L.cniic_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
-        L.cniic_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
-        _lib = L
+        _lib = _declare(C.CDLL(SO_PATH))
     return _lib
+
+
+def _declare(L: C.CDLL) -> C.CDLL:
+    """ctypes signatures of the entry points whose defaults (int in / int out) are wrong."""
+    L.cniic_last_error.restype = C.c_char_p
+    L.cniic_ctx_stream.restype = C.c_void_p
+    L.cniic_device_alloc.restype = C.c_void_p
+    L.cniic_device_alloc.argtypes = [C.c_void_p, C.c_size_t]
+    L.cniic_device_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.cniic_device_free.restype = None
+    L.cniic_ctx_destroy.argtypes = [C.c_void_p]
+    L.cniic_ctx_destroy.restype = None
+    L.cniic_kmeans_close.argtypes = [C.c_void_p]
+    L.cniic_kmeans_close.restype = None
+    L.cniic_kmeans_device_assign.restype = C.c_void_p
+    L.cniic_kmeans_device_assign.argtypes = [C.c_void_p]
+    L.cniic_ctx_launches.restype = C.c_uint32
+    L.cniic_ctx_launches.argtypes = [C.c_void_p]
+    L.cniic_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.cniic_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    return L
 
 
 def declared_symbols() -> list[str]:

@@ -1,0 +1,74 @@
+"""The CUDA kernel sources, compiled for the HOST and run under the fiber emulation of tests/emu/ -- logic tests of the
+real kernels (barriers, warp collectives, shared-memory protocols, index arithmetic) on a machine without a GPU.
+
+TEST INFRASTRUCTURE ONLY.  tests/emu/build_emu.py compiles cniic_b200/csrc/*.cu against a stand-in <cuda_runtime.h>
+into tests/emu/_build/libcniic_emu.so; this module points the ctypes loader at that library for its own duration
+(module-scoped fixture, restored afterwards) and re-runs the bodies of the GPU parity tests against the oracle.
+The product never loads the emulated library and still has no CPU path (tests/test_cpu_host.py checks both); a
+green run here says nothing about performance and does not replace `pytest -m gpu` on a B200.
+
+Sizes: the slow cases (dense 2^24 / 511^3 histogram bins, k = 2048 tables) are skipped unless CNIIC_EMU_FULL=1
+(`CNIIC_EMU_FULL=1 python -m pytest tests/test_emu_kernels.py` takes ~10 minutes).
+"""
+import ctypes
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+import cniic_b200 as cb  # noqa: E402
+from cniic_b200 import _lib as L  # noqa: E402
+
+if sys.platform != "linux":
+    pytest.skip("the emulation needs Linux (mmap'ed fiber stacks, ELF shared object)", allow_module_level=True)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emu_lib():
+    import build_emu
+    so = build_emu.build()
+    saved = L._lib
+    L._lib = L._declare(ctypes.CDLL(so))
+    yield so
+    L._lib = saved
+
+
+@pytest.fixture(scope="module")
+def ctx(emu_lib):
+    c = cb.Context()
+    yield c
+    c.close()
+
+
+def _reexport(module):
+    """Collect the GPU test functions of `module` here, under the emulated context (module-level gpu marks stay behind)."""
+    for name, fn in vars(module).items():
+        if name.startswith("test_") and callable(fn):
+            globals()["test_emu_" + name[5:]] = fn
+
+
+import test_gpu_golden  # noqa: E402
+import test_gpu_parity  # noqa: E402
+
+_reexport(test_gpu_parity)
+_reexport(test_gpu_golden)
+
+
+def test_emu_library_is_the_emulated_one(ctx, emu_lib):
+    assert "tests/emu/_build" in emu_lib.replace(os.sep, "/")
+    assert ctx._lib._name == emu_lib
+    assert cb.Context is not None and L.SO_PATH.endswith("libcniic_b200.so")  # the product path is untouched
+
+
+def test_emu_detects_out_of_bounds_and_deadlocks():
+    """The emulation's own checks fire: run tiny bad kernels in a child process and expect an abort with a diagnosis."""
+    import subprocess
+    import build_emu
+    exe = build_emu.build_selftest()
+    for case, needle in (("oob", "OUT-OF-BOUNDS WRITE"), ("deadlock", "DEADLOCK"), ("divergent", "DIFFERENT collectives"), ("ok", "selftest ok")):
+        r = subprocess.run([exe, case], capture_output=True, text=True, timeout=60)
+        assert needle in (r.stderr + r.stdout), (case, r.stderr, r.stdout)
+        assert (r.returncode == 0) == (case == "ok")
