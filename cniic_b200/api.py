@@ -170,6 +170,25 @@ class Context:
         cen = np.concatenate([cxy[:k].astype(np.int64), crgb[:k].astype(np.int64)], axis=1)
         return self._result(st, cen, wts[:k], asg, rc)
 
+    def kmeans_rgb_batch(self, images, k, max_iters=0, tie=L.TIE_KEEP_CURRENT, want_assign=True, allow_inactive=False):
+        """`count` independent RGB images (per-pixel points), one K-means each, advanced in lock step with one launch per
+        stage for the whole batch (cniic_kmeans_rgb_batch; bench.rs:27 runs one image per worker).  Returns a list of
+        KMeansResult, identical to calling kmeans_rgb on every image."""
+        imgs = [_u8(im).reshape(-1, 3) for im in images]
+        count = len(imgs)
+        ptrs = (C.c_void_p * count)(*[im.ctypes.data for im in imgs])
+        ns = (C.c_size_t * count)(*[len(im) for im in imgs])
+        cen = np.zeros((count, max(k, 1), 3), np.uint8)
+        wts = np.zeros((count, max(k, 1)), np.uint64)
+        asgs = [np.zeros(len(im), np.uint16) for im in imgs] if want_assign else None
+        aptrs = (C.c_void_p * count)(*[a.ctypes.data for a in asgs]) if want_assign else None
+        sts = (L.KMeansStats * count)()
+        rc = self._lib.cniic_kmeans_rgb_batch(self.h, ptrs, ns, C.c_uint32(count), C.c_uint32(k), C.c_uint32(max_iters), tie,
+                                              _ptr(cen), _ptr(wts), aptrs, sts)
+        self.check(rc, (L.ERR_TOO_FEW_ACTIVE,) if allow_inactive else ())
+        return [self._result(sts[i], cen[i, :k].astype(np.int64), wts[i, :k], asgs[i] if want_assign else None, rc)
+                for i in range(count)]
+
     def kmeans_session(self, **kw) -> "KMeansSession":
         return KMeansSession(self, **kw)
 
@@ -357,6 +376,23 @@ class KMeansSession:
             self.close()
         except Exception:
             pass
+
+
+def kmeans_reset_batch(sessions):
+    """cniic_kmeans_reset_batch: chunked init of every session, one launch per stage for the whole batch."""
+    ctx = sessions[0].ctx
+    hs = (C.c_void_p * len(sessions))(*[s.h.value for s in sessions])
+    ctx.check(ctx._lib.cniic_kmeans_reset_batch(hs, C.c_uint32(len(sessions))))
+
+
+def kmeans_run_batch(sessions, max_iters: int = 0):
+    """cniic_kmeans_run_batch: Lloyd iterations of all sessions in lock step.  Returns one KMeansStats per session
+    (device_ms / assign_ms_avg / gpu_launches describe the whole batch)."""
+    ctx = sessions[0].ctx
+    hs = (C.c_void_p * len(sessions))(*[s.h.value for s in sessions])
+    sts = (L.KMeansStats * len(sessions))()
+    ctx.check(ctx._lib.cniic_kmeans_run_batch(hs, C.c_uint32(len(sessions)), C.c_uint32(max_iters), sts))
+    return list(sts)
 
 
 # ---- synthetic images (SURVEY.md 8d): identical on host and device ----

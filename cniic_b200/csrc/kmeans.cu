@@ -133,7 +133,7 @@ __device__ __forceinline__ void unpack8(const uint32_t w[6], uint32_t px[PX]) {
 }
 
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(THREADS) km_assign_rgb(KmDev d) {
+__device__ __forceinline__ void km_assign_rgb_body(const KmDev d) {
     if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
@@ -340,7 +340,7 @@ __global__ void km_unsort_assign(const uint16_t *__restrict__ assign_sorted, con
 constexpr int RCAP = 256;  // survivors scored per round
 
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
+__device__ __forceinline__ void km_assign_rgb_cull_body(const KmDev d) {
     if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) {
 // D = 5 fused assign + accumulate: tile = 256 pixels x 8 rows, warp = one row, lane = 8 consecutive pixels
 // ------------------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(THREADS) km_assign_xyrgb(KmDev d) {
+__device__ __forceinline__ void km_assign_xyrgb_body(const KmDev d) {
     if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(THREADS) km_tile_boxes_xy(const uint8_t *__res
     }
 }
 
-__global__ void __launch_bounds__(THREADS) km_supercull(KmDev d) {
+__device__ __forceinline__ void km_supercull_body(const KmDev d) {
     if (d.st->done || d.st->dist_empty) return;
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_U;
@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(THREADS) km_supercull(KmDev d) {
     if (tid == 0) d.sc_count[sup] = placed;
 }
 
-__global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull(KmDev d) {
+__device__ __forceinline__ void km_assign_xyrgb_cull_body(const KmDev d) {
     if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
@@ -968,7 +968,7 @@ __device__ __forceinline__ void fetch_point(const KmDev &d, unsigned long long l
 }
 
 // kmeans.rs:61-78 init_assignment: cluster i < k-1 owns points [N-(i+1)*ppc, N-i*ppc), cluster k-1 the rest
-__global__ void km_init_assign(KmDev d) {
+__device__ __forceinline__ void km_init_assign_body(const KmDev d) {
     const unsigned long long N = d.n_total, ppc = N / d.k;
     const unsigned long long head = N - (unsigned long long)(d.k - 1) * ppc;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < d.n_local;
@@ -980,7 +980,7 @@ __global__ void km_init_assign(KmDev d) {
 
 // kmeans.rs:101-108 init_centroids (single GPU: gathered straight from the resident points)
 template <int D>
-__global__ void km_init_centroids(KmDev d) {
+__device__ __forceinline__ void km_init_centroids_body(const KmDev d) {
     const unsigned long long N = d.n_total, ppc = N / d.k;
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < d.k; c += gridDim.x * blockDim.x) {
         const unsigned long long gi = c + 1 < d.k ? N - (unsigned long long)(c + 1) * ppc : 0ull;
@@ -1008,7 +1008,7 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *s_warp, uint
 }
 
 template <int D>
-__global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
+__device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode) {
     constexpr int DW = D + 1;
     constexpr int G = D == 5 ? G5 : G3;
     constexpr int DUMMY = D == 5 ? DUMMY5 : DUMMY3;
@@ -1228,6 +1228,39 @@ __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) {
             d.st->dist_empty = 0;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel entry points.  Every stage exists in two forms that share one body:
+//   single : the session descriptor travels by value in the parameter space (one K-means problem per launch);
+//   batch  : blockIdx.y selects one of `count` independent problems from a descriptor array in global memory, so a batch
+//            of small images (bench.rs:27 -- one image per worker; BASELINE config 4) advances one Lloyd iteration per
+//            launch instead of one launch per image.  The bodies only use blockIdx.x / gridDim.x, so they are unaware.
+// ------------------------------------------------------------------------------------------------------------
+template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS) km_assign_rgb(KmDev d) { km_assign_rgb_body<WEIGHTED>(d); }
+template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) { km_assign_rgb_cull_body<WEIGHTED>(d); }
+__global__ void __launch_bounds__(THREADS) km_assign_xyrgb(KmDev d) { km_assign_xyrgb_body(d); }
+__global__ void __launch_bounds__(THREADS) km_supercull(KmDev d) { km_supercull_body(d); }
+__global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull(KmDev d) { km_assign_xyrgb_cull_body(d); }
+__global__ void km_init_assign(KmDev d) { km_init_assign_body(d); }
+template <int D> __global__ void km_init_centroids(KmDev d) { km_init_centroids_body<D>(d); }
+template <int D> __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) { km_finalize_body<D>(d, init_mode); }
+
+template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS) km_assign_rgb_batch(const KmDev *__restrict__ batch) { km_assign_rgb_body<WEIGHTED>(batch[blockIdx.y]); }
+template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull_batch(const KmDev *__restrict__ batch) { km_assign_rgb_cull_body<WEIGHTED>(batch[blockIdx.y]); }
+__global__ void __launch_bounds__(THREADS) km_assign_xyrgb_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_body(batch[blockIdx.y]); }
+__global__ void __launch_bounds__(THREADS) km_supercull_batch(const KmDev *__restrict__ batch) {
+    const KmDev &d = batch[blockIdx.y];
+    if (blockIdx.x >= d.super_x * d.super_y) return;  // the grid is sized for the largest image of the batch
+    km_supercull_body(d);
+}
+__global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_cull_body(batch[blockIdx.y]); }
+__global__ void km_init_assign_batch(const KmDev *__restrict__ batch) { km_init_assign_body(batch[blockIdx.y]); }
+template <int D> __global__ void km_init_centroids_batch(const KmDev *__restrict__ batch) { km_init_centroids_body<D>(batch[blockIdx.y]); }
+template <int D> __global__ void __launch_bounds__(1024) km_finalize_batch(const KmDev *__restrict__ batch, int init_mode) { km_finalize_body<D>(batch[blockIdx.x], init_mode); }
+// the states of a batch, gathered into one array for a single device-to-host copy
+__global__ void km_gather_states(const KmDev *__restrict__ batch, uint32_t count, KmState *out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[i] = *batch[i].st;
 }
 
 // Multi-GPU empty-cluster repair, step 1: this rank's members of `victim` with the lowest global indices (ascending),
@@ -1674,6 +1707,261 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
     }
     km->iter_seen = s.iter;
     return CNIIC_OK;
+}
+
+static int check_active(cniic_ctx *ctx, const uint64_t *weights, uint32_t k, uint64_t n);
+
+// ------------------------------------------------------------------------------------------------------------
+// batch of independent K-means problems advancing in lock step (one launch per stage for the whole batch)
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct BatchPlan {
+    cniic_ctx *ctx = nullptr;
+    int D = 3;
+    bool cull = false, weighted = false;
+    uint32_t k = 0, count = 0;
+    size_t smem = 0;
+    unsigned gx_assign = 1, gx_init = 1, gx_super = 0;
+    KmDev *d_batch = nullptr;  // device copy of the descriptors (ctx cache; blocks are reused in stream order, so freeing early is safe)
+    BatchPlan() = default;
+    BatchPlan(const BatchPlan &) = delete;
+    BatchPlan &operator=(const BatchPlan &) = delete;
+    ~BatchPlan() { if (d_batch) cniic_cache_free(ctx, d_batch); }
+};
+
+// all sessions of a batch must run the same kernel variant with the same launch shape
+int km_batch_plan(cniic_kmeans *const *ss, uint32_t count, BatchPlan *bp) {
+    if (!ss || !count || !ss[0]) return CNIIC_ERR_BAD_ARG;
+    cniic_kmeans *k0 = ss[0];
+    cniic_ctx *ctx = k0->ctx;
+    if (ctx->world > 1) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "batches are independent problems: use a single-GPU context per rank");
+    unsigned long long max_tiles = 1, max_n = 1;
+    uint32_t max_super = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        cniic_kmeans *km = ss[i];
+        if (!km || km->ctx != ctx) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "batch session %u is null or belongs to another context", i);
+        if (km->D != k0->D || km->desc.k != k0->desc.k || km->cull != k0->cull || (km->dev.wts != nullptr) != (k0->dev.wts != nullptr) ||
+            km->smem != k0->smem || km->desc.tie_rule != k0->desc.tie_rule)
+            return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "batch session %u differs from session 0 in kind, k, tie rule, weights or kernel variant", i);
+        if (km->desc.n_local != km->desc.n_total || !km->desc.n_local) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "batch session %u is sharded or empty", i);
+        const cniic_kmeans_desc &ds = km->desc;
+        const unsigned long long tiles = km->D == 5 ? (km->cull ? (unsigned long long)((ds.w + TW - 1) / TW) * ((ds.h_local + TH - 1) / TH)
+                                                                : (unsigned long long)((ds.w + 255) / 256) * ((ds.h_local + 7) / 8))
+                                                    : (ds.n_local + TILE - 1) / TILE;
+        max_tiles = std::max(max_tiles, tiles);
+        max_n = std::max<unsigned long long>(max_n, ds.n_local);
+        max_super = std::max(max_super, km->dev.super_x * km->dev.super_y);
+    }
+    bp->ctx = ctx;
+    bp->D = k0->D;
+    bp->cull = k0->cull;
+    bp->weighted = k0->dev.wts != nullptr;
+    bp->k = k0->desc.k;
+    bp->count = count;
+    bp->smem = k0->smem;
+    // resident CTAs of the single-problem launch (k0->grid was capped by its tile count, so recompute from the occupancy)
+    int per_sm = 0;
+    cudaError_t e;
+    if (bp->D == 5 && bp->cull) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull_batch, THREADS, bp->smem);
+    else if (bp->D == 5) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_batch, THREADS, bp->smem);
+    else if (bp->cull && bp->weighted) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull_batch<true>, THREADS, bp->smem);
+    else if (bp->cull) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull_batch<false>, THREADS, bp->smem);
+    else if (bp->weighted) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_batch<true>, THREADS, bp->smem);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_batch<false>, THREADS, bp->smem);
+    CU_TRY(ctx, e);
+    if (per_sm < 1) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "k = %u needs %zu bytes of shared memory", bp->k, bp->smem);
+    const unsigned long long resident = (unsigned long long)per_sm * ctx->sm_count;
+    bp->gx_assign = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(max_tiles, (resident + count - 1) / count));
+    bp->gx_init = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((max_n + 255) / 256, ((unsigned long long)ctx->sm_count * 8 + count - 1) / count));
+    bp->gx_super = max_super;
+    if (count > 65535) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "at most 65535 problems per batch (gridDim.y)");
+    return CNIIC_OK;
+}
+
+int km_batch_upload(cniic_kmeans *const *ss, BatchPlan *bp) {
+    cniic_ctx *ctx = bp->ctx;
+    std::vector<KmDev> h(bp->count);
+    for (uint32_t i = 0; i < bp->count; i++) h[i] = ss[i]->dev;
+    bp->d_batch = static_cast<KmDev *>(cniic_cache_alloc(ctx, sizeof(KmDev) * bp->count));
+    if (!bp->d_batch) return CNIIC_ERR_CUDA;
+    CU_TRY(ctx, cudaMemcpyAsync(bp->d_batch, h.data(), sizeof(KmDev) * bp->count, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `h` dies with this scope
+    return CNIIC_OK;
+}
+
+int km_batch_set_attributes(const BatchPlan &bp) {
+    cniic_ctx *ctx = bp.ctx;
+    const int sm = (int)bp.smem;
+    if (bp.D == 5 && bp.cull) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_xyrgb_cull_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    else if (bp.D == 5) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_xyrgb_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    else if (bp.cull && bp.weighted) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_rgb_cull_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    else if (bp.cull) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_rgb_cull_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    else if (bp.weighted) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_rgb_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    else CU_TRY(ctx, cudaFuncSetAttribute(km_assign_rgb_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    return CNIIC_OK;
+}
+
+// one Lloyd iteration of the whole batch: [supertile pre-pass] + fused assign/accumulate + finalize; returns kernels launched
+int km_batch_launch_iteration(const BatchPlan &bp, uint32_t *launched) {
+    cniic_ctx *ctx = bp.ctx;
+    const dim3 grid(bp.gx_assign, bp.count);
+    if (bp.D == 5 && bp.cull) {
+        if (bp.gx_super) {
+            km_supercull_batch<<<dim3(bp.gx_super, bp.count), THREADS, 0, ctx->stream>>>(bp.d_batch);
+            (*launched)++;
+        }
+        km_assign_xyrgb_cull_batch<<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
+    }
+    else if (bp.D == 5) km_assign_xyrgb_batch<<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
+    else if (bp.cull && bp.weighted) km_assign_rgb_cull_batch<true><<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
+    else if (bp.cull) km_assign_rgb_cull_batch<false><<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
+    else if (bp.weighted) km_assign_rgb_batch<true><<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
+    else km_assign_rgb_batch<false><<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
+    (*launched)++;
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+int km_batch_launch_finalize(const BatchPlan &bp, int init_mode, uint32_t *launched) {
+    cniic_ctx *ctx = bp.ctx;
+    if (bp.D == 5) km_finalize_batch<5><<<bp.count, 1024, 0, ctx->stream>>>(bp.d_batch, init_mode);
+    else km_finalize_batch<3><<<bp.count, 1024, 0, ctx->stream>>>(bp.d_batch, init_mode);
+    (*launched)++;
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+}  // namespace
+
+extern "C" int cniic_kmeans_reset_batch(cniic_kmeans *const *sessions, uint32_t count) {
+    BatchPlan bp;
+    ST_TRY(km_batch_plan(sessions, count, &bp));
+    cniic_ctx *ctx = bp.ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    ST_TRY(km_batch_upload(sessions, &bp));
+    uint32_t launched = 0;
+    km_init_assign_batch<<<dim3(bp.gx_init, count), 256, 0, ctx->stream>>>(bp.d_batch);
+    if (bp.D == 5) km_init_centroids_batch<5><<<dim3((bp.k + 127) / 128, count), 128, 0, ctx->stream>>>(bp.d_batch);
+    else km_init_centroids_batch<3><<<dim3((bp.k + 127) / 128, count), 128, 0, ctx->stream>>>(bp.d_batch);
+    launched += 2;
+    int rc = cudaGetLastError() == cudaSuccess ? CNIIC_OK : cniic_set_error(ctx, CNIIC_ERR_CUDA, "batch init launch failed");
+    if (rc == CNIIC_OK) rc = km_batch_launch_finalize(bp, 1, &launched);
+    for (uint32_t i = 0; i < count; i++) sessions[i]->iter_seen = 0;
+    ctx->launches += launched;
+    if (rc == CNIIC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "batch init failed");
+    return rc;
+}
+
+extern "C" int cniic_kmeans_run_batch(cniic_kmeans *const *sessions, uint32_t count, uint32_t max_iters, cniic_kmeans_stats *stats) {
+    BatchPlan bp;
+    ST_TRY(km_batch_plan(sessions, count, &bp));
+    cniic_ctx *ctx = bp.ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    ST_TRY(km_batch_set_attributes(bp));
+    ST_TRY(km_batch_upload(sessions, &bp));
+    DevBuf d_states(ctx);
+    CU_TRY(ctx, d_states.alloc(sizeof(KmState) * count));
+    std::vector<KmState> h_states(count);
+    cniic_kmeans *k0 = sessions[0];
+    uint32_t launched = 0, issued = 0;
+    int rc = CNIIC_OK;
+    auto finish = [&](int code) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx->launches += launched;
+        return code;
+    };
+    if (cudaEventRecord(k0->ev0, ctx->stream) != cudaSuccess) return finish(cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaEventRecord failed"));
+    for (;;) {
+        uint32_t batch = 8;  // launches of a converged problem exit at once, so over-issuing is harmless
+        if (max_iters) batch = std::min(batch, max_iters - issued);
+        for (uint32_t b = 0; b < batch && rc == CNIIC_OK; b++) {
+            const bool prof = issued < (uint32_t)cniic_kmeans::PROF;
+            if (prof) cudaEventRecord(k0->pev[2 * issued], ctx->stream);
+            rc = km_batch_launch_iteration(bp, &launched);
+            if (prof) cudaEventRecord(k0->pev[2 * issued + 1], ctx->stream);
+            issued++;
+            if (rc == CNIIC_OK) rc = km_batch_launch_finalize(bp, 0, &launched);
+        }
+        if (rc != CNIIC_OK) return finish(rc);
+        km_gather_states<<<(count + 255) / 256, 256, 0, ctx->stream>>>(bp.d_batch, count, d_states.as<KmState>());
+        launched++;
+        if (cudaMemcpyAsync(h_states.data(), d_states.p, sizeof(KmState) * count, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            return finish(cniic_set_error(ctx, CNIIC_ERR_CUDA, "batch state read-back failed: %s", cudaGetErrorString(cudaGetLastError())));
+        bool all_done = true;
+        for (uint32_t i = 0; i < count; i++) all_done = all_done && h_states[i].done;
+        if (all_done || (max_iters && issued >= max_iters)) break;
+    }
+    cudaEventRecord(k0->ev1, ctx->stream);
+    cudaEventSynchronize(k0->ev1);
+    float ms = 0.f, acc = 0.f;
+    cudaEventElapsedTime(&ms, k0->ev0, k0->ev1);
+    uint32_t ran = 0;  // assign launches in which at least one problem was still active
+    for (uint32_t i = 0; i < count; i++) ran = std::max(ran, h_states[i].iter - sessions[i]->iter_seen);
+    const uint32_t np = std::min<uint32_t>(ran, (uint32_t)cniic_kmeans::PROF);
+    for (uint32_t i = 0; i < np; i++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, k0->pev[2 * i], k0->pev[2 * i + 1]) == cudaSuccess) acc += t;
+    }
+    for (uint32_t i = 0; i < count; i++) {
+        const KmState &st = h_states[i];
+        if (stats) {
+            cniic_kmeans_stats &o = stats[i];
+            o.iterations = st.iter;
+            o.empty_events = st.empty_events;
+            o.moved_last = st.moved_last;
+            o.moved_total = st.moved_total;
+            o.converged = st.done;
+            o.gpu_launches = launched;    // of the whole batch
+            o.device_ms = ms;             // of the whole batch
+            o.assign_ms_avg = np ? acc / np : 0.f;  // one launch = the whole batch
+            o.pairs_scored = st.pairs;
+        }
+        sessions[i]->iter_seen = st.iter;
+    }
+    return finish(CNIIC_OK);
+}
+
+// Host-buffer form: `count` independent RGB images (per-pixel points), one K-means each, advanced together.
+extern "C" int cniic_kmeans_rgb_batch(cniic_ctx *ctx, const uint8_t *const *rgb, const size_t *n, uint32_t count, uint32_t k, uint32_t max_iters,
+                                      int tie_rule, uint8_t *out_centroids, uint64_t *out_weight, uint16_t *const *out_assign,
+                                      cniic_kmeans_stats *stats) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    if (!rgb || !n || !count || !out_centroids) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "null buffer or empty batch");
+    std::vector<cniic_kmeans *> ss(count, nullptr);
+    auto close_all = [&]() {
+        for (cniic_kmeans *km : ss) cniic_kmeans_close(km);
+    };
+    // one kernel variant for the whole batch: culled only if every image is past the break-even (cniic_kmeans_open's rule)
+    bool all_big = true;
+    for (uint32_t i = 0; i < count; i++) all_big = all_big && (unsigned long long)n[i] * k >= (1ull << 27);
+    int rc = CNIIC_OK;
+    for (uint32_t i = 0; i < count && rc == CNIIC_OK; i++) {
+        if (!rgb[i]) { rc = cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "null image %u", i); break; }
+        cniic_kmeans_desc desc{};
+        desc.kind = CNIIC_POINTS_RGB;
+        desc.k = k;
+        desc.tie_rule = tie_rule;
+        desc.n_local = desc.n_total = n[i];
+        desc.rgb = rgb[i];
+        desc.flags = all_big ? CNIIC_KMEANS_FORCE_CULL : CNIIC_KMEANS_NO_CULL;
+        rc = cniic_kmeans_open(ctx, &desc, &ss[i]);
+    }
+    if (rc == CNIIC_OK) rc = cniic_kmeans_reset_batch(ss.data(), count);
+    if (rc == CNIIC_OK) rc = cniic_kmeans_run_batch(ss.data(), count, max_iters, stats);
+    std::vector<int32_t> cen(size_t(k) * 3);
+    std::vector<uint64_t> wts(k);
+    int worst = CNIIC_OK;
+    for (uint32_t i = 0; i < count && rc == CNIIC_OK; i++) {
+        rc = cniic_kmeans_get(ss[i], cen.data(), wts.data(), out_assign ? out_assign[i] : nullptr);
+        if (rc != CNIIC_OK) break;
+        for (size_t j = 0; j < size_t(k) * 3; j++) out_centroids[size_t(i) * k * 3 + j] = (uint8_t)cen[j];
+        if (out_weight) memcpy(out_weight + size_t(i) * k, wts.data(), size_t(k) * 8);
+        if (check_active(ctx, wts.data(), k, n[i]) != CNIIC_OK) worst = CNIIC_ERR_TOO_FEW_ACTIVE;  // kmeans.rs:41-57, outputs still written
+    }
+    close_all();
+    return rc != CNIIC_OK ? rc : worst;
 }
 
 extern "C" int cniic_kmeans_get(cniic_kmeans *km, int32_t *out_centroids, uint64_t *out_weight, uint16_t *out_assign) {

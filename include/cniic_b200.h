@@ -144,6 +144,21 @@ int cniic_kmeans_get(cniic_kmeans *km, int32_t *out_centroids, uint64_t *out_wei
 const uint16_t *cniic_kmeans_device_assign(cniic_kmeans *km);
 void cniic_kmeans_close(cniic_kmeans *km);
 
+/* ---- batches of independent images (bench.rs:15-34: `measure_all` hands one image to each rayon worker) -------------
+ * `count` K-means problems advance in lock step: every stage is ONE launch for the whole batch (blockIdx.y = problem), so
+ * small images fill the GPU and cost one launch per iteration instead of one per image.  Results are those of `count`
+ * separate cniic_kmeans_run calls, bit for bit.  All sessions must belong to one single-GPU ctx and agree in kind, k, tie
+ * rule, weighted-ness and kernel variant (CNIIC_KMEANS_NO_CULL / FORCE_CULL make the variant explicit).
+ * stats (nullable) receives `count` entries; device_ms, assign_ms_avg and gpu_launches describe the whole batch.        */
+int cniic_kmeans_reset_batch(cniic_kmeans *const *sessions, uint32_t count);
+int cniic_kmeans_run_batch(cniic_kmeans *const *sessions, uint32_t count, uint32_t max_iters, cniic_kmeans_stats *stats);
+/* Host-buffer form for RGB images (per-pixel points): rgb[i] = n[i] x 3 bytes.  out_centroids = count x k x 3 bytes,
+ * out_weight = count x k (nullable), out_assign = count pointers to n[i] x u16 (nullable).  Returns
+ * CNIIC_ERR_TOO_FEW_ACTIVE (outputs written) if kmeans.rs:41-57 would panic for any image.                              */
+int cniic_kmeans_rgb_batch(cniic_ctx *ctx, const uint8_t *const *rgb, const size_t *n, uint32_t count, uint32_t k, uint32_t max_iters,
+                           int tie_rule, uint8_t *out_centroids, uint64_t *out_weight, uint16_t *const *out_assign,
+                           cniic_kmeans_stats *stats);
+
 /* ---- cluster-colors stages (clusterc.rs:18-52) ---------------------------------------------------------- */
 /* utils::count_freqs over pixels (utils.rs:4-16 as called at clusterc.rs:21 and huf.rs:30 via hufc.rs:15-16).
  * HashMap order is unspecified in the reference; canonical order here = ascending key r<<16|g<<8|b.

@@ -1,0 +1,21 @@
+"""torch.distributed stand-in for world_size 1 (see torch/__init__.py in this directory)."""
+
+
+class ReduceOp:
+    MAX = "max"
+
+
+def init_process_group(*a, **k):
+    raise RuntimeError("the emulated bench smoke test is single-process")
+
+
+def barrier():
+    pass
+
+
+def all_reduce(t, op=None):
+    pass
+
+
+def destroy_process_group():
+    pass

@@ -35,6 +35,9 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in text and "liboracle" not in text and "cniic_oracle" not in text, f
+                # ... nor the host emulation of tests/emu (test infrastructure), nor any environment switch to another library
+                assert "libcniic_emu" not in text and "tests/emu" not in text and "CNIIC_EMU" not in text, f
+    assert _lib.lib()._name == _lib.SO_PATH  # the loader serves exactly the in-tree CUDA build
 
 
 @pytest.mark.parametrize("expr,name", [

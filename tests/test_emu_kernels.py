@@ -72,3 +72,28 @@ def test_emu_detects_out_of_bounds_and_deadlocks():
         r = subprocess.run([exe, case], capture_output=True, text=True, timeout=60)
         assert needle in (r.stderr + r.stdout), (case, r.stderr, r.stdout)
         assert (r.returncode == 0) == (case == "ok")
+
+
+@pytest.mark.parametrize("workload", ["c2", "c4", "c3"])
+def test_emu_bench_main_runs_and_keeps_the_json_contract(workload):
+    """bench.py's real main() on the emulated kernels (tiny workloads, stand-in torch): control flow + JSON contract."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "run_bench_emu.py"), "--workload", workload, "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["steps"] == 2 and line["warmup"] >= 3 and line["n_gpus"] == 1 and line["value"] > 0
+    assert line["gpu_launches"] > 0 and line["iterations_run"] == 2 * 10
+    rf = line["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and rf["achieved"] > 0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert rf["fp32"]["brute_force_kernel"]["launch_ms"] > 0
+    e = line["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
+    assert "workload" in line["config"]
+    if workload == "c4":
+        assert rf["kernel"].endswith("_batch") and line["config"]["images_per_step_per_gpu"] == 3 and e["api"] == "cniic_kmeans_rgb_batch"

@@ -337,3 +337,54 @@ def test_single_colour_image_codecs(ctx):  # huf.rs:139-142 zero-length code
     data = c.encode(img)
     assert data == O.encode_hufman(img) and len(data) == 8 + 12
     assert np.array_equal(c.decode(data), img)
+
+
+# ---- batches of independent images: one launch per stage for the whole batch (bench.rs:27, BASELINE config 4) ----
+@pytest.mark.parametrize("k,sizes", [(16, [(64, 48), (64, 48), (64, 48)]), (64, [(128, 96), (40, 30), (97, 61), (128, 96), (16, 4)]), (5, [(33, 9)])])
+@pytest.mark.parametrize("max_iters", [3, 0])
+def test_kmeans_rgb_batch_equals_separate_runs(ctx, k, sizes, max_iters):
+    imgs = [cb.synth_image_host(w, h, 100 + i, 6) for i, (w, h) in enumerate(sizes)]
+    res = ctx.kmeans_rgb_batch(imgs, k, max_iters=max_iters)
+    assert len(res) == len(imgs)
+    for im, g in zip(imgs, res):
+        o = O.kmeans_rgb(im, k, mode=O.MODE_EXACT, max_iters=max_iters)  # images converge after different numbers of passes
+        same_kmeans(g, o)
+
+
+@pytest.mark.parametrize("kind,flag", [("rgb", "NO_CULL"), ("rgb", "FORCE_CULL"), ("xyrgb", "NO_CULL"), ("xyrgb", 0)])
+def test_kmeans_session_batch_all_kernel_variants(ctx, kind, flag):
+    """Batched launches of every assign kernel family (brute / culled, D = 3 / D = 5), mixed image sizes, with an
+    empty-cluster repair inside the batch, against one oracle run per image."""
+    rng = np.random.default_rng(5)
+    sizes = [(96, 40), (64, 64), (130, 17), (24, 12)]
+    imgs = [cb.synth_image_host(w, h, 7 + i, 5) for i, (w, h) in enumerate(sizes)]
+    imgs[3] = (rng.integers(0, 3, size=(12, 24, 3)) * 100).astype(np.uint8)  # few colours: empty clusters appear
+    k, fl = 12, (getattr(cb._lib, "KMEANS_" + flag) if flag else 0)
+    ss = []
+    for im in imgs:
+        h, w = im.shape[:2]
+        if kind == "rgb":
+            ss.append(cb.KMeansSession(ctx, cb.POINTS_RGB, k, im, w * h, flags=fl))
+        else:
+            ss.append(cb.KMeansSession(ctx, cb.POINTS_XYRGB, k, im, w * h, w=w, h_local=h, flags=fl))
+    for rounds in range(2):  # a second reset + run on the same sessions gives the same answer
+        cb.kmeans_reset_batch(ss)
+        sts = cb.kmeans_run_batch(ss, 3)
+        sts2 = cb.kmeans_run_batch(ss, 2)  # continue: 3 + 2 iterations in two calls
+        for im, s, st, st2 in zip(imgs, ss, sts, sts2):
+            o = (O.kmeans_rgb if kind == "rgb" else O.kmeans_xyrgb)(im, k, mode=O.MODE_EXACT, max_iters=5, allow_inactive=True)
+            cen, wts, asg = s.get()
+            assert st2.iterations == o.iterations and st.iterations == min(3, o.iterations)
+            assert np.array_equal(cen, o.centroids) and np.array_equal(wts, o.weights) and np.array_equal(asg, o.assign)
+            assert st2.empty_events == o.empty_events and st2.moved_total == o.moved_total
+    for s in ss:
+        s.close()
+
+
+def test_kmeans_batch_rejects_mixed_sessions(ctx):
+    a = cb.KMeansSession(ctx, cb.POINTS_RGB, 4, cb.synth_image_host(16, 8, 1, 3), 128)
+    b = cb.KMeansSession(ctx, cb.POINTS_RGB, 5, cb.synth_image_host(16, 8, 2, 3), 128)
+    with pytest.raises(cb.CniicError) as e:
+        cb.kmeans_reset_batch([a, b])
+    assert e.value.code == cb.ERR_BAD_ARG
+    a.close(); b.close()
