@@ -181,42 +181,18 @@ bool huf_deserialize(Source &src, size_t sym_size, DecTrie *T) {
     }
 }
 
-// huf.rs:187-206 trie walk over MSB-first bits; decodes exactly n symbols.  A 12-bit prefix table resolves short codes
-// in one step (entry = node reached after consuming `used` bits; leaves stop early), longer codes continue bit by bit.
-bool huf_decode(Source &src, const DecTrie &T, size_t sym_size, size_t n, uint8_t *out) {
-    constexpr int L = 12;
-    struct Ent { int node; int used; };
-    std::vector<Ent> lut(size_t(1) << L);
-    for (uint32_t pre = 0; pre < (1u << L); pre++) {
-        int nd = 0, used = 0;
-        while (used < L && T.nodes[nd].left >= 0) {
-            nd = ((pre >> (L - 1 - used)) & 1) ? T.nodes[nd].right : T.nodes[nd].left;
-            used++;
-        }
-        lut[pre] = {nd, used};
+// huf.rs:187-206: the payload after the trie is decoded on the GPU (huffdec.cu: self-synchronising parallel decoder with the
+// sequential decoder's results and error behaviour).  val_off = offset of the symbol bytes inside a leaf's serialised value.
+int huf_decode_device(cniic_ctx *ctx, const Source &src, const DecTrie &T, size_t val_off, int sym_bytes, size_t n, uint8_t *d_out) {
+    const size_t nn = T.nodes.size();
+    std::vector<int32_t> child(2 * nn);
+    std::vector<uint8_t> leaf(8 * nn, 0);
+    for (size_t i = 0; i < nn; i++) {
+        child[2 * i] = T.nodes[i].left;
+        child[2 * i + 1] = T.nodes[i].right;
+        if (T.nodes[i].left < 0) memcpy(&leaf[8 * i], T.nodes[i].val + val_off, (size_t)sym_bytes);
     }
-    size_t bit = src.pos * 8;
-    const size_t end = src.len * 8;
-    auto peek = [&](size_t at) -> uint32_t {  // L bits starting at `at`, zero padded past the end
-        uint32_t v = 0;
-        const size_t byte = at >> 3;
-        for (int i = 0; i < 3; i++) v = (v << 8) | (byte + i < src.len ? src.p[byte + i] : 0);
-        return (v >> (24 - L - (at & 7))) & ((1u << L) - 1);
-    };
-    for (size_t i = 0; i < n; i++) {
-        const Ent e = lut[peek(bit)];
-        if (bit + e.used > end) return false;
-        bit += e.used;
-        int nd = e.node;
-        while (T.nodes[nd].left >= 0) {
-            if (bit >= end) return false;
-            const int b = (src.p[bit >> 3] >> (7 - (bit & 7))) & 1;
-            bit++;
-            nd = b ? T.nodes[nd].right : T.nodes[nd].left;
-        }
-        memcpy(out + i * sym_size, T.nodes[nd].val, sym_size);
-    }
-    return true;
+    return cniic_dev_huffman_decode(ctx, src.p + src.pos, src.len - src.pos, child.data(), leaf.data(), nn, sym_bytes, n, d_out);
 }
 
 int finish(cniic_ctx *ctx, const Sink &s, uint8_t *out, size_t cap, size_t *out_len) {
@@ -263,9 +239,11 @@ int decode_hufman_body(cniic_ctx *ctx, Source &src, size_t n, uint8_t *out_rgb) 
     if (!huf_deserialize(src, 11, &T)) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "bad Huffman trie");
     for (const DecTrie::Node &nd : T.nodes)
         if (nd.left < 0 && (nd.val[0] != 3 || memcmp(nd.val + 1, "\0\0\0\0\0\0\0", 7) != 0)) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "bad Rgb leaf");
-    std::vector<uint8_t> vals(n * 11);
-    if (!huf_decode(src, T, 11, n, vals.data())) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated Huffman payload");
-    for (size_t i = 0; i < n; i++) memcpy(out_rgb + 3 * i, vals.data() + 11 * i + 8, 3);
+    DevBuf d_out(ctx);
+    CU_TRY(ctx, d_out.alloc(n * 3));
+    ST_TRY(huf_decode_device(ctx, src, T, 8, 3, n, d_out.as<uint8_t>()));  // leaf = u64 length (= 3) + the colour bytes
+    CU_TRY(ctx, cudaMemcpyAsync(out_rgb, d_out.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CNIIC_OK;
 }
 
@@ -436,10 +414,16 @@ extern "C" int cniic_codec_decode(cniic_ctx *ctx, const char *codec, const uint8
         if (n == 0) return CNIIC_OK;
         DecTrie T;
         if (!huf_deserialize(src, 6, &T)) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "bad Huffman trie");
-        std::vector<uint8_t> vals(n * 6);
-        if (!huf_decode(src, T, 6, n, vals.data())) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated Huffman payload");
-        // little-endian i16 triples == the in-memory layout cniic_undelta_rgb expects on this (little-endian) host
-        return cniic_undelta_rgb(ctx, reinterpret_cast<const int16_t *>(vals.data()), *w, *h, out_rgb);
+        // symbols = little-endian i16 triples (ser.rs:188-195) == the layout the device un-delta pass reads: the difference
+        // stream never visits the host (decode -> prefix sums along the curve -> scatter, all in HBM)
+        DevBuf d_diff(ctx), d_img(ctx);
+        CU_TRY(ctx, d_diff.alloc(n * 6));
+        CU_TRY(ctx, d_img.alloc(n * 3));
+        ST_TRY(huf_decode_device(ctx, src, T, 0, 6, n, d_diff.as<uint8_t>()));
+        ST_TRY(cniic_dev_undelta(ctx, d_diff.as<int16_t>(), *w, *h, d_img.as<uint8_t>()));
+        CU_TRY(ctx, cudaMemcpyAsync(out_rgb, d_img.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return CNIIC_OK;
     }
     case CK_HILBERT_RLE: {  // hilbertc.rs:55-79, 304-333
         if (n == 0) return CNIIC_OK;

@@ -17,3 +17,9 @@ int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uin
                              std::vector<int32_t> *cen_host, cniic_kmeans_stats *stats);
 int cniic_dev_huffman_pack(cniic_ctx *ctx, int src_kind, const void *d_src, size_t n, const uint32_t *d_keys, size_t nsym,
                            const std::vector<uint64_t> &codes, const std::vector<uint8_t> &lens, std::vector<uint8_t> *out);
+// Parallel Huffman decoding (huffdec.cu; semantics of huf.rs:187-206): `payload` = HOST bytes, MSB-first bit string; trie as
+// child[2*node] / child[2*node+1] (left = bit 0, right = bit 1; left < 0 marks a leaf), leaf_val = 8 bytes per node (the first
+// sym_bytes are the symbol: 3 = colour bytes, 6 = [i16;3] little endian), node 0 = root.  Writes n * sym_bytes bytes to the
+// DEVICE buffer d_out; CNIIC_ERR_DECODE when the payload holds fewer than n complete code words.
+int cniic_dev_huffman_decode(cniic_ctx *ctx, const uint8_t *payload, size_t len, const int32_t *child, const uint8_t *leaf_val, size_t nn,
+                             int sym_bytes, size_t n, uint8_t *d_out);

@@ -109,6 +109,8 @@ struct Machine {
     unsigned n_threads = 0, n_live = 0;
     unsigned bar_count = 0;
     volatile unsigned bar_gen = 0;
+    // __syncthreads_or/and/count: accumulators of the barrier in flight, indexed by the parity of its generation
+    int red_or[2] = {0, 0}, red_nand[2] = {0, 0}, red_cnt[2] = {0, 0};
     std::vector<unsigned char> smem;
     const std::function<void()> *body = nullptr;
     const char *kernel = "";
@@ -129,11 +131,15 @@ void wait_on(const volatile unsigned *p, unsigned val, const char *what) {
     f->wait_ptr = nullptr;
 }
 
+void barrier_completed() {
+    M.bar_count = 0;
+    M.bar_gen = M.bar_gen + 1;
+    const unsigned nxt = M.bar_gen & 1;  // the accumulators of the NEXT barrier (its results were read two barriers ago)
+    M.red_or[nxt] = M.red_nand[nxt] = M.red_cnt[nxt] = 0;
+}
+
 void release_barrier_if_complete() {
-    if (M.bar_count && M.bar_count == M.n_live) {
-        M.bar_count = 0;
-        M.bar_gen = M.bar_gen + 1;
-    }
+    if (M.bar_count && M.bar_count == M.n_live) barrier_completed();
 }
 
 void complete_rendezvous(WarpState &w, Rendezvous &r) {
@@ -185,6 +191,7 @@ void run_cta(const LaunchCfg &cfg, Idx bid) {
     const unsigned T = cfg.block.x * cfg.block.y * cfg.block.z;
     M.n_threads = M.n_live = T;
     M.bar_count = 0;
+    M.red_or[0] = M.red_or[1] = M.red_nand[0] = M.red_nand[1] = M.red_cnt[0] = M.red_cnt[1] = 0;
     M.fibers.assign(T, Fiber());
     M.warps.assign((T + 31) / 32, WarpState());
     memset(M.smem.data(), 0xCD, M.smem.size());
@@ -270,11 +277,19 @@ void cta_barrier() {
     M.bar_count++;
     const unsigned gen = M.bar_gen;
     if (M.bar_count == M.n_live) {
-        M.bar_count = 0;
-        M.bar_gen = gen + 1;
+        barrier_completed();
         return;
     }
     wait_on(&M.bar_gen, gen, "__syncthreads()");
+}
+
+int cta_barrier_reduce(int pred, int op) {
+    const unsigned slot = M.bar_gen & 1;
+    M.red_or[slot] |= pred != 0;
+    M.red_nand[slot] |= pred == 0;
+    M.red_cnt[slot] += pred != 0;
+    cta_barrier();
+    return op == 0 ? M.red_or[slot] : (op == 1 ? !M.red_nand[slot] : M.red_cnt[slot]);
 }
 
 void warp_exchange(unsigned mask, unsigned long long v, int op, WarpVals *out) {

@@ -112,6 +112,7 @@ struct ThreadCtx {
 extern ThreadCtx *g_cur;  // the fiber that is running
 void *dyn_smem();
 void cta_barrier();
+int cta_barrier_reduce(int pred, int op);  // op 0: or, 1: and, 2: count
 // warp rendezvous: every lane named in `mask` (and still alive) deposits `v`; returns the deposited values and who deposited
 struct WarpVals { unsigned long long v[32]; unsigned present; };
 void warp_exchange(unsigned mask, unsigned long long v, int op, WarpVals *out);
@@ -129,6 +130,9 @@ void launch(const LaunchCfg &cfg, const std::function<void()> &body, const char 
 #define gridDim (emu::g_cur->gdim)
 
 static inline void __syncthreads() { emu::cta_barrier(); }
+static inline int __syncthreads_or(int pred) { return emu::cta_barrier_reduce(pred, 0); }
+static inline int __syncthreads_and(int pred) { return emu::cta_barrier_reduce(pred, 1); }
+static inline int __syncthreads_count(int pred) { return emu::cta_barrier_reduce(pred, 2); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::WarpVals w; emu::warp_exchange(mask, 0, 0, &w); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}

@@ -388,3 +388,57 @@ def test_kmeans_batch_rejects_mixed_sessions(ctx):
         cb.kmeans_reset_batch([a, b])
     assert e.value.code == cb.ERR_BAD_ARG
     a.close(); b.close()
+
+
+# ---- parallel Huffman decoder (huffdec.cu) against the sequential walk of huf.rs:187-206 ----
+def _fibonacci_image(depth, seed):
+    """Colour i occurs fib(i) times: the Huffman tree degenerates into a chain, code lengths 1 .. depth-1 bits."""
+    fib = [1, 1]
+    while len(fib) < depth:
+        fib.append(fib[-1] + fib[-2])
+    rng = np.random.default_rng(seed)
+    pal = rng.integers(0, 256, size=(depth, 3), dtype=np.uint8)
+    pal[:, 0] = np.arange(depth)  # distinct colours
+    px = np.repeat(np.arange(depth), fib)
+    rng.shuffle(px)
+    w = 256
+    h = len(px) // w
+    return pal[px[:w * h]].reshape(h, w, 3)
+
+
+@pytest.mark.parametrize("expr", ["hufman", "delta"])
+def test_huffman_decoder_long_codes_over_many_chunks(ctx, expr):
+    """Code words from 1 to 20+ bits, several 64-Kbit chunks: wrong starting guesses must re-synchronise inside CTAs and
+    across them, and the symbol counts must add up to the exact output positions."""
+    img = _fibonacci_image(25, 1)
+    c = codecs.Codec.from_str(ctx, expr)
+    data = c.encode(img)
+    assert data == (O.encode_hufman(img) if expr == "hufman" else O.encode_delta(img))
+    assert len(data) * 8 > 3 * 65536
+    assert np.array_equal(c.decode(data), img)
+
+
+def test_huffman_decoder_two_symbols_one_bit_each(ctx):
+    """256 code words per subsequence: the densest stream there is (every bit position is a valid start)."""
+    rng = np.random.default_rng(2)
+    img = np.where(rng.random((96, 128, 1)) < 0.5, np.uint8(10), np.uint8(200)).repeat(3, axis=2).astype(np.uint8)
+    c = codecs.Hufman(ctx)
+    data = c.encode(img)
+    assert data == O.encode_hufman(img)
+    assert np.array_equal(c.decode(data), img)
+
+
+@pytest.mark.parametrize("expr,odec", [("hufman", O.decode_hufman), ("delta", O.decode_delta)])
+def test_huffman_decoder_truncated_at_every_byte(ctx, expr, odec):
+    """Same verdict as the sequential decoder for every prefix of a stream: None while code words are missing
+    (huf.rs:190-204), the image as soon as all n are complete (trailing padding bits are ignored)."""
+    img = _fibonacci_image(12, 4)[:2, :24]
+    c = codecs.Codec.from_str(ctx, expr)
+    data = c.encode(img)
+    for cut in range(8, len(data) + 1):
+        g, o = c.decode(data[:cut]), odec(data[:cut])
+        assert (g is None) == (o is None), cut
+        if o is not None:
+            assert np.array_equal(g, o), cut
+    # garbage appended after the payload is ignored by both
+    assert np.array_equal(c.decode(data + b"\xff\x00\xaa"), odec(data + b"\xff\x00\xaa"))
