@@ -29,6 +29,10 @@ extern "C" {
         tie_rule: c_int, out_centroids: *mut u8, out_weight: *mut u64, out_assign: *mut u16, stats: *mut cniic_kmeans_stats) -> c_int;
     pub fn cniic_kmeans_xyrgb(ctx: *mut cniic_ctx, rgb: *const u8, w: u32, h: u32, k: u32, max_iters: u32, tie_rule: c_int,
         out_xy: *mut u32, out_rgb: *mut u8, out_weight: *mut u64, out_assign: *mut u16, stats: *mut cniic_kmeans_stats) -> c_int;
+    /// `count` independent images advanced in lock step, one launch per stage for the whole batch (bench.rs:15-34).
+    pub fn cniic_kmeans_rgb_batch(ctx: *mut cniic_ctx, rgb: *const *const u8, n: *const usize, count: u32, k: u32, max_iters: u32,
+                                  tie_rule: c_int, out_centroids: *mut u8, out_weight: *mut u64, out_assign: *const *mut u16,
+                                  stats: *mut cniic_kmeans_stats) -> c_int;
     pub fn cniic_voronoi_fill(ctx: *mut cniic_ctx, cxy: *const u32, crgb: *const u8, k: u32, w: u32, h: u32, out_rgb: *mut u8) -> c_int;
     pub fn cniic_hist_rgb(ctx: *mut cniic_ctx, rgb: *const u8, n: usize, out_keys: *mut u32, out_counts: *mut u64, cap: usize, out_n: *mut usize) -> c_int;
     pub fn cniic_hist_delta(ctx: *mut cniic_ctx, rgb: *const u8, w: u32, h: u32, out_keys: *mut u32, out_counts: *mut u64, cap: usize, out_n: *mut usize) -> c_int;
