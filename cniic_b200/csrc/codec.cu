@@ -354,21 +354,7 @@ extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8
             DevBuf dl(ctx);
             CU_TRY(ctx, dl.alloc(n * 3));
             ST_TRY(cniic_dev_hilbert_gather(ctx, din.as<uint8_t>(), w, h, dl.as<uint8_t>()));
-            std::vector<uint8_t> lin(n * 3);
-            CU_TRY(ctx, cudaMemcpyAsync(lin.data(), dl.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
-            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-            size_t i = 0;
-            while (i < n) {
-                size_t j = i + 1;
-                uint32_t count = 1;
-                while (j < n && memcmp(&lin[3 * j], &lin[3 * i], 3) == 0) {
-                    count++; j++;
-                    if (count == 255) break;
-                }
-                s.u8((uint8_t)count);
-                s.u64(3); s.u8(lin[3 * i]); s.u8(lin[3 * i + 1]); s.u8(lin[3 * i + 2]);
-                i = j;
-            }
+            ST_TRY(cniic_dev_rle_encode(ctx, dl.as<uint8_t>(), n, &s.v));  // segmented scans + record scatter on the GPU
         }
         break;
     }
@@ -427,16 +413,11 @@ extern "C" int cniic_codec_decode(cniic_ctx *ctx, const char *codec, const uint8
     }
     case CK_HILBERT_RLE: {  // hilbertc.rs:55-79, 304-333
         if (n == 0) return CNIIC_OK;
-        std::vector<uint32_t> xy(2 * n);
-        ST_TRY(cniic_hilbert_xy(ctx, *w, *h, xy.data()));
-        size_t i = 0;
-        while (i < n) {
-            uint8_t cnt, c[3];
-            uint64_t l;
-            if (!src.u8(&cnt) || !src.u64(&l) || l != 3 || !src.u8(&c[0]) || !src.u8(&c[1]) || !src.u8(&c[2]))
-                return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated RLE stream");
-            for (uint8_t j = 0; j < cnt && i < n; j++, i++) memcpy(out_rgb + 3 * ((size_t)xy[2 * i + 1] * *w + xy[2 * i]), c, 3);
-        }
+        DevBuf d_img(ctx);
+        CU_TRY(ctx, d_img.alloc(n * 3));
+        ST_TRY(cniic_dev_rle_decode(ctx, src.p + src.pos, src.len - src.pos, *w, *h, d_img.as<uint8_t>()));
+        CU_TRY(ctx, cudaMemcpyAsync(out_rgb, d_img.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         return CNIIC_OK;
     }
     default: return CNIIC_ERR_BAD_ARG;

@@ -837,6 +837,217 @@ inline int grid_for(cniic_ctx *ctx, size_t n, int per_thread = 1) {
     return (int)std::max<size_t>(1, std::min<size_t>(blocks, (size_t)ctx->sm_count * 16));
 }
 
+
+// ============================================================================================================
+// exact run-length coding along the Hilbert stream (reference src/codec/hilbertc.rs:99-196, decoder :304-333)
+//   record = u8 count (1..=255) + Rgb as a serialised slice (u64 length 3 + 3 bytes) = 12 bytes (ser.rs:164-172).
+//   The reference's iterator is greedy: a maximal run of L equal pixels becomes floor(L/255) records of 255 and one of
+//   L mod 255 (if non-zero), cut from the START of the run.  With r = position of a pixel inside its maximal run, pixel j
+//   ends a record iff j is the last pixel, or pixel j+1 differs, or (r+1) mod 255 == 0 -- and that record's count is
+//   r mod 255 + 1.  So records fall out of a segmented scan (run starts) and an ordinary scan (record index).
+// ============================================================================================================
+constexpr int RLE_PX = 16;                 // pixels per thread
+constexpr int RLE_BLOCK = 256 * RLE_PX;    // pixels per CTA
+
+__device__ __forceinline__ uint32_t rle_px(const uint8_t *__restrict__ lin, unsigned long long i) {
+    const uint8_t *p = lin + 3 * i;
+    return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16);
+}
+
+// inclusive scan over the 256 threads of a CTA; MAX: running maximum, else running sum.  Returns the inclusive value,
+// *total = value over the whole CTA.  s_w: 8 words of shared scratch.
+template <bool MAX>
+__device__ __forceinline__ uint32_t block_scan256(uint32_t v, uint32_t *s_w, uint32_t *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = MAX ? max(v, y) : v + y;
+    }
+    __syncthreads();  // s_w may still be read from a previous call
+    if (lane == 31) s_w[warp] = v;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t x = s_w[i];
+        if (i < warp) before = MAX ? max(before, x) : before + x;
+        tot = MAX ? max(tot, x) : tot + x;
+    }
+    *total = tot;
+    return MAX ? max(v, before) : v + before;
+}
+
+// pass 1: per CTA block, (index + 1) of the last run start inside the block (0 = none)
+__global__ void __launch_bounds__(256) rle_heads_kernel(const uint8_t *__restrict__ lin, uint32_t n, uint32_t *blk_last) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t i0 = blockIdx.x * RLE_BLOCK + threadIdx.x * RLE_PX;
+    uint32_t last = 0;
+    if (i0 < n) {
+        uint32_t prev = i0 ? rle_px(lin, i0 - 1) : 0xffffffffu;
+        for (int j = 0; j < RLE_PX && i0 + j < n; j++) {
+            const uint32_t c = rle_px(lin, i0 + j);
+            if (c != prev) last = i0 + j + 1;
+            prev = c;
+        }
+    }
+    uint32_t tot;
+    block_scan256<true>(last, s_w, &tot);
+    if (threadIdx.x == 0) blk_last[blockIdx.x] = tot;
+}
+
+// single-CTA exclusive scan over the per-block values (MAX: running maximum; else sum, with the grand total in out[nb])
+template <bool MAX>
+__global__ void __launch_bounds__(256) rle_scan_blocks_kernel(const uint32_t *__restrict__ in, uint32_t nb, uint32_t *out) {
+    __shared__ uint32_t s_w[8];
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nb; base += 256) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nb ? in[i] : 0u;
+        uint32_t tot;
+        const uint32_t inc = block_scan256<MAX>(v, s_w, &tot);
+        // exclusive value = scan of everything before me
+        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, 1);
+        uint32_t excl;
+        if ((threadIdx.x & 31) != 0) excl = up;
+        else {
+            excl = 0;
+            for (int w = 0; w < int(threadIdx.x >> 5); w++) excl = MAX ? max(excl, s_w[w]) : excl + s_w[w];
+        }
+        if (i < nb) out[i] = MAX ? max(carry, excl) : carry + excl;
+        carry = MAX ? max(carry, tot) : carry + tot;
+    }
+    if (!MAX && threadIdx.x == 0) out[nb] = carry;
+}
+
+// pass 2 (WRITE = false): records per block; pass 3 (WRITE = true): the records themselves
+template <bool WRITE>
+__global__ void __launch_bounds__(256) rle_emit_kernel(const uint8_t *__restrict__ lin, uint32_t n, const uint32_t *__restrict__ blk_carry,
+                                                       uint32_t *blk_nrec, const uint32_t *__restrict__ blk_off, uint32_t *records) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t i0 = blockIdx.x * RLE_BLOCK + threadIdx.x * RLE_PX;
+    uint32_t px[RLE_PX + 2];  // px[0] = predecessor, px[RLE_PX + 1] = successor
+    const int nv = i0 < n ? int(min(uint32_t(RLE_PX), n - i0)) : 0;
+    px[0] = (nv && i0) ? rle_px(lin, i0 - 1) : 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < RLE_PX; j++) px[j + 1] = j < nv ? rle_px(lin, i0 + j) : 0xfffffffeu;
+    px[RLE_PX + 1] = (nv == RLE_PX && i0 + RLE_PX < n) ? rle_px(lin, i0 + RLE_PX) : 0xfffffffdu;
+    uint32_t last = 0;  // (index + 1) of the last run start among my pixels
+#pragma unroll
+    for (int j = 0; j < RLE_PX; j++)
+        if (j < nv && px[j + 1] != px[j]) last = i0 + j + 1;
+    uint32_t tot;
+    const uint32_t inc = block_scan256<true>(last, s_w, &tot);
+    // run start in force at my first pixel: the last start before me in this block, else the carry of the earlier blocks
+    uint32_t up = __shfl_up_sync(0xffffffffu, inc, 1);
+    if ((threadIdx.x & 31) == 0) {
+        up = 0;
+        for (int w = 0; w < int(threadIdx.x >> 5); w++) up = max(up, s_w[w]);
+    }
+    uint32_t start1 = max(up, blk_carry[blockIdx.x]);  // index + 1
+    uint32_t ends = 0, endmask = 0;
+    uint32_t cnt_of[RLE_PX];
+#pragma unroll
+    for (int j = 0; j < RLE_PX; j++) {
+        cnt_of[j] = 0;
+        if (j < nv) {
+            const uint32_t i = i0 + j;
+            if (px[j + 1] != px[j]) start1 = i + 1;
+            const uint32_t r = i - (start1 - 1);
+            const bool is_end = i + 1 == n || px[j + 2] != px[j + 1] || (r + 1) % 255 == 0;
+            if (is_end) { ends++; endmask |= 1u << j; cnt_of[j] = r % 255 + 1; }
+        }
+    }
+    const uint32_t inc_e = block_scan256<false>(ends, s_w, &tot);
+    if (!WRITE) {
+        if (threadIdx.x == 0) blk_nrec[blockIdx.x] = tot;
+        return;
+    }
+    uint32_t idx = blk_off[blockIdx.x] + inc_e - ends;
+#pragma unroll
+    for (int j = 0; j < RLE_PX; j++)
+        if (endmask >> j & 1) {
+            uint32_t *rec = records + 3 * (size_t)idx++;   // count, u64 length = 3 (little endian), r, g, b
+            rec[0] = cnt_of[j] | (3u << 8);
+            rec[1] = 0u;
+            rec[2] = px[j + 1] << 8;
+        }
+}
+
+// ---- decoder: parse the 12-byte records, scan the counts, paint every curve index from its record ----
+__global__ void rle_parse_kernel(const uint8_t *__restrict__ recs, uint32_t nrec, uint32_t *cnt, uint8_t *bad) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrec; r += gridDim.x * blockDim.x) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(recs + 12 * (size_t)r);
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        cnt[r] = w0 & 0xff;
+        bad[r] = ((w0 >> 8) != 3u || w1 != 0u || (w2 & 0xff) != 0u) ? 1 : 0;  // Rgb slice length must be 3 (ser.rs:210-214)
+    }
+}
+
+// per-block sums of the counts (256 records per thread block of 256 threads x 1) and, after the block scan, the starts
+__global__ void __launch_bounds__(256) rle_cnt_blocks_kernel(const uint32_t *__restrict__ cnt, uint32_t nrec, uint32_t *blk_sum) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t r = blockIdx.x * 256 + threadIdx.x;
+    uint32_t tot;
+    block_scan256<false>(r < nrec ? cnt[r] : 0u, s_w, &tot);
+    if (threadIdx.x == 0) blk_sum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256) rle_starts_kernel(const uint32_t *__restrict__ cnt, const uint8_t *__restrict__ bad, uint32_t nrec,
+                                                         const unsigned long long *__restrict__ blk_off, unsigned long long n,
+                                                         unsigned long long *start, uint32_t *err) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t r = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t c = r < nrec ? cnt[r] : 0u;
+    uint32_t tot;
+    const uint32_t inc = block_scan256<false>(c, s_w, &tot);
+    if (r < nrec) {
+        const unsigned long long st = blk_off[blockIdx.x] + (inc - c);
+        start[r] = st;
+        if (st < n && bad[r]) atomicOr(err, 1u);  // the sequential decoder reads record r only while pixels are missing
+    }
+}
+
+// exclusive scan of u32 block sums into u64 offsets, single CTA (totals can pass 2^32 for hostile streams); out[nb] = total
+__global__ void __launch_bounds__(256) rle_scan_u64_kernel(const uint32_t *__restrict__ in, uint32_t nb, unsigned long long *out) {
+    __shared__ unsigned long long s_part[256];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 256) {
+        const uint32_t i = base + threadIdx.x;
+        s_part[threadIdx.x] = i < nb ? in[i] : 0ull;
+        __syncthreads();
+        if (threadIdx.x == 0) {  // 256 additions per batch: negligible next to the passes over the records
+            unsigned long long run = s_carry;
+            for (int j = 0; j < 256; j++) { const unsigned long long v = s_part[j]; s_part[j] = run; run += v; }
+            s_carry = run;
+        }
+        __syncthreads();
+        if (i < nb) out[i] = s_part[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[nb] = s_carry;
+}
+
+__global__ void rle_paint_kernel(const uint8_t *__restrict__ recs, const unsigned long long *__restrict__ start, uint32_t nrec, uint32_t w, uint32_t h,
+                                 bool pow2, uint8_t *out) {
+    const unsigned long long n = (unsigned long long)w * h;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        // last record whose start is <= i (records with count 0 share their start with the next one and are skipped)
+        uint32_t lo = 0, hi = nrec;
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (__ldg(start + mid) <= i) lo = mid;
+            else hi = mid;
+        }
+        const uint8_t *rec = recs + 12 * (size_t)lo + 9;
+        uint32_t x, y;
+        hilbert_d2xy(w, h, pow2, i, &x, &y);
+        uint8_t *o = out + ((size_t)y * w + x) * 3;
+        o[0] = rec[0]; o[1] = rec[1]; o[2] = rec[2];
+    }
+}
+
 inline bool is_pow2_square(uint32_t w, uint32_t h) { return w == h && (w & (w - 1)) == 0; }
 
 }  // namespace
@@ -939,6 +1150,76 @@ int cniic_dev_hilbert_gather(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, u
     hilbert_stream_kernel<0><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), d_out, nullptr, nullptr, nullptr);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
+// hilbertc.rs:26-38 + 99-196: run-length records of the linearised image `d_lin` (n pixels, device) appended to *out
+int cniic_dev_rle_encode(cniic_ctx *ctx, const uint8_t *d_lin, size_t n, std::vector<uint8_t> *out) {
+    if (n == 0) return CNIIC_OK;
+    const uint32_t nb = (uint32_t)((n + RLE_BLOCK - 1) / RLE_BLOCK);
+    DevBuf d_last(ctx), d_carry(ctx), d_nrec(ctx), d_off(ctx), d_rec(ctx);
+    CU_TRY(ctx, d_last.alloc(size_t(nb) * 4));
+    CU_TRY(ctx, d_carry.alloc(size_t(nb) * 4));
+    CU_TRY(ctx, d_nrec.alloc(size_t(nb) * 4));
+    CU_TRY(ctx, d_off.alloc((size_t(nb) + 1) * 4));
+    rle_heads_kernel<<<nb, 256, 0, ctx->stream>>>(d_lin, (uint32_t)n, d_last.as<uint32_t>());
+    rle_scan_blocks_kernel<true><<<1, 256, 0, ctx->stream>>>(d_last.as<uint32_t>(), nb, d_carry.as<uint32_t>());
+    rle_emit_kernel<false><<<nb, 256, 0, ctx->stream>>>(d_lin, (uint32_t)n, d_carry.as<uint32_t>(), d_nrec.as<uint32_t>(), nullptr, nullptr);
+    rle_scan_blocks_kernel<false><<<1, 256, 0, ctx->stream>>>(d_nrec.as<uint32_t>(), nb, d_off.as<uint32_t>());
+    ctx->launches += 4;
+    CU_TRY(ctx, cudaGetLastError());
+    uint32_t nrec = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&nrec, d_off.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, d_rec.alloc(size_t(nrec) * 12));
+    rle_emit_kernel<true><<<nb, 256, 0, ctx->stream>>>(d_lin, (uint32_t)n, d_carry.as<uint32_t>(), nullptr, d_off.as<uint32_t>(), d_rec.as<uint32_t>());
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaGetLastError());
+    const size_t at = out->size();
+    out->resize(at + size_t(nrec) * 12);
+    CU_TRY(ctx, cudaMemcpyAsync(out->data() + at, d_rec.p, size_t(nrec) * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CNIIC_OK;
+}
+
+// hilbertc.rs:55-79 + 304-333: `recs` = HOST bytes behind the dimensions; paints the w x h image d_out (device).
+// CNIIC_ERR_DECODE when the records run out, or a record that is needed is malformed, before all pixels are covered.
+int cniic_dev_rle_decode(cniic_ctx *ctx, const uint8_t *recs, size_t len, uint32_t w, uint32_t h, uint8_t *d_out) {
+    const unsigned long long n = (unsigned long long)w * h;
+    if (n == 0) return CNIIC_OK;
+    const size_t nrec_all = len / 12;  // a trailing partial record can only matter if pixels are still missing: truncated either way
+    if (nrec_all == 0) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated RLE stream");
+    // records behind the first n can never be read (every count that matters is >= 0; n records of count >= 1 suffice only if
+    // all are non-zero, so keep up to 2^31 - 1 and let the scan decide)
+    const uint32_t nrec = (uint32_t)std::min<size_t>(nrec_all, (size_t(1) << 31) - 1);
+    const uint32_t nb = (nrec + 255) / 256;
+    DevBuf d_recs(ctx), d_cnt(ctx), d_bad(ctx), d_bsum(ctx), d_boff(ctx), d_start(ctx), d_err(ctx);
+    CU_TRY(ctx, d_recs.alloc(size_t(nrec) * 12));
+    CU_TRY(ctx, d_cnt.alloc(size_t(nrec) * 4));
+    CU_TRY(ctx, d_bad.alloc(nrec));
+    CU_TRY(ctx, d_bsum.alloc(size_t(nb) * 4));
+    CU_TRY(ctx, d_boff.alloc((size_t(nb) + 1) * 8));
+    CU_TRY(ctx, d_start.alloc(size_t(nrec) * 8));
+    CU_TRY(ctx, d_err.alloc(256));
+    CU_TRY(ctx, cudaMemcpyAsync(d_recs.p, recs, size_t(nrec) * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_err.p, 0, 4, ctx->stream));
+    rle_parse_kernel<<<grid_for(ctx, nrec), 256, 0, ctx->stream>>>(d_recs.as<uint8_t>(), nrec, d_cnt.as<uint32_t>(), d_bad.as<uint8_t>());
+    rle_cnt_blocks_kernel<<<nb, 256, 0, ctx->stream>>>(d_cnt.as<uint32_t>(), nrec, d_bsum.as<uint32_t>());
+    rle_scan_u64_kernel<<<1, 256, 0, ctx->stream>>>(d_bsum.as<uint32_t>(), nb, d_boff.as<unsigned long long>());
+    rle_starts_kernel<<<nb, 256, 0, ctx->stream>>>(d_cnt.as<uint32_t>(), d_bad.as<uint8_t>(), nrec, d_boff.as<unsigned long long>(), n,
+                                                   d_start.as<unsigned long long>(), d_err.as<uint32_t>());
+    ctx->launches += 4;
+    CU_TRY(ctx, cudaGetLastError());
+    unsigned long long total = 0;
+    uint32_t err = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&total, d_boff.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err || total < n) return cniic_set_error(ctx, CNIIC_ERR_DECODE, err ? "bad RLE record" : "truncated RLE stream");
+    rle_paint_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(d_recs.as<uint8_t>(), d_start.as<unsigned long long>(), nrec, w, h, is_pow2_square(w, h), d_out);
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CNIIC_OK;
 }
 

@@ -23,3 +23,6 @@ int cniic_dev_huffman_pack(cniic_ctx *ctx, int src_kind, const void *d_src, size
 // DEVICE buffer d_out; CNIIC_ERR_DECODE when the payload holds fewer than n complete code words.
 int cniic_dev_huffman_decode(cniic_ctx *ctx, const uint8_t *payload, size_t len, const int32_t *child, const uint8_t *leaf_val, size_t nn,
                              int sym_bytes, size_t n, uint8_t *d_out);
+// exact run-length coding along the Hilbert stream (hilbertc.rs:99-196 / 304-333), 12-byte records; see stages.cu
+int cniic_dev_rle_encode(cniic_ctx *ctx, const uint8_t *d_lin, size_t n, std::vector<uint8_t> *out);
+int cniic_dev_rle_decode(cniic_ctx *ctx, const uint8_t *recs, size_t len, uint32_t w, uint32_t h, uint8_t *d_out);

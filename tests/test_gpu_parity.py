@@ -442,3 +442,58 @@ def test_huffman_decoder_truncated_at_every_byte(ctx, expr, odec):
             assert np.array_equal(g, o), cut
     # garbage appended after the payload is ignored by both
     assert np.array_equal(c.decode(data + b"\xff\x00\xaa"), odec(data + b"\xff\x00\xaa"))
+
+
+# ---- exact RLE along the Hilbert stream on the GPU (hilbertc.rs:99-196, 304-333) ----
+@pytest.mark.parametrize("w,h", [(70, 70), (255, 3), (64, 64), (510, 1), (1, 511), (128, 96)])
+def test_rle_long_runs_are_cut_at_255(ctx, w, h):
+    """Runs longer than 255 pixels (and exact multiples of 255) across thread and CTA boundaries of the scan."""
+    rng = np.random.default_rng(w * 1000 + h)
+    c = codecs.Codec.from_str(ctx, "hilbert(rle)")
+    flat = np.full((h, w, 3), 7, np.uint8)  # one run of w*h pixels
+    imgs = [flat]
+    lin_len = w * h
+    # runs of chosen lengths laid out ALONG THE CURVE, so their lengths are exact
+    xy = O.hilbert_xy(w, h)
+    runs, pos = [], 0
+    for L in [255, 1, 256, 510, 3, 254, 4096, 2, 765, 4097]:
+        if pos + L > lin_len:
+            break
+        runs.append((pos, L))
+        pos += L
+    img = np.zeros((h, w, 3), np.uint8)
+    colours = rng.integers(1, 255, size=(len(runs) + 1, 3), dtype=np.uint8)
+    for i, (p0, L) in enumerate(runs):
+        colours[i, 0] = i  # neighbouring runs differ
+        img[xy[p0:p0 + L, 1], xy[p0:p0 + L, 0]] = colours[i]
+    img[xy[pos:, 1], xy[pos:, 0]] = (250, 250, 250)
+    imgs.append(img)
+    for im in imgs:
+        data = c.encode(im)
+        assert data == O.encode_hilbert_rle(im)
+        assert np.array_equal(c.decode(data), im)
+
+
+def test_rle_decoder_verdicts_match_the_sequential_decoder(ctx):
+    c = codecs.Codec.from_str(ctx, "hilbert(rle)")
+    img = (cb.synth_image_host(24, 10, 3, 3) // 128) * 128
+    data = c.encode(img)
+    for cut in range(8, len(data) + 1):  # every prefix: None until the records cover all pixels
+        g, o = c.decode(data[:cut]), O.decode_hilbert_rle(data[:cut])
+        assert (g is None) == (o is None), cut
+        if o is not None:
+            assert np.array_equal(g, o), cut
+    hdr, body = data[:8], data[8:]
+    rec = lambda cnt, rgb, ln=3: bytes([cnt]) + int(ln).to_bytes(8, "little") + bytes(rgb)
+    cases = [
+        hdr + rec(0, (1, 2, 3)) + body,                      # zero-count record: paints nothing
+        hdr + body + rec(9, (1, 2, 3), ln=4),                # malformed record BEHIND the last needed one: never read
+        hdr + rec(5, (1, 2, 3), ln=4) + body,                # malformed record that is needed
+        hdr + body[:12] + rec(200, (9, 9, 9)) + body[12:],   # more pixels than the image holds: the surplus is dropped
+        hdr + rec(255, (4, 5, 6)),                           # exactly one record, 240 pixels needed
+    ]
+    for i, s in enumerate(cases):
+        g, o = c.decode(s), O.decode_hilbert_rle(s)
+        assert (g is None) == (o is None), i
+        if o is not None:
+            assert np.array_equal(g, o), i
