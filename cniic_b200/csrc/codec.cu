@@ -202,8 +202,8 @@ int finish(cniic_ctx *ctx, const Sink &s, uint8_t *out, size_t cap, size_t *out_
     return CNIIC_OK;
 }
 
-// Hufman codec body over a DEVICE-resident image whose host copy is `host_rgb` (hufc.rs:12-17, huf.rs:22-43)
-int encode_hufman_body(cniic_ctx *ctx, const uint8_t *d_rgb, const uint8_t *host_rgb, size_t n, Sink &s) {
+// Hufman codec body over a DEVICE-resident image (hufc.rs:12-17, huf.rs:22-43)
+int encode_hufman_body(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, Sink &s) {
     if (n == 0) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "empty image (huf.rs:95 asserts a non-empty alphabet)");
     uint32_t *d_bins = nullptr, *d_keys = nullptr;
     unsigned long long *d_counts = nullptr;
@@ -224,12 +224,9 @@ int encode_hufman_body(cniic_ctx *ctx, const uint8_t *d_rgb, const uint8_t *host
     if (rc == CNIIC_OK) {
         huf_serialize(T, s, [&](uint32_t sym) { s.rgb(keys[sym]); });
         // pass 2: bit packing on the GPU (code lookup, scan of the lengths, MSB-first word assembly)
-        std::vector<uint8_t> payload;
-        rc = cniic_dev_huffman_pack(ctx, 0, d_rgb, n, d_keys, u, T.code, T.len, &payload);
-        if (rc == CNIIC_OK) s.v.insert(s.v.end(), payload.begin(), payload.end());
+        rc = cniic_dev_huffman_pack(ctx, 0, d_rgb, n, d_keys, u, T.code, T.len, &s.v);
     }
     cniic_cache_free(ctx, d_keys);
-    (void)host_rgb;
     return rc;
 }
 
@@ -281,7 +278,7 @@ extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8
     switch (sp.kind) {
     case CK_HUFMAN: {  // hufc.rs:12-17
         s.u32(w); s.u32(h);
-        ST_TRY(encode_hufman_body(ctx, din.as<uint8_t>(), rgb, n, s));
+        ST_TRY(encode_hufman_body(ctx, din.as<uint8_t>(), n, s));
         break;
     }
     case CK_CLUSTER_COLORS: {  // clusterc.rs:18-53
@@ -289,11 +286,8 @@ extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8
         DevBuf dred(ctx);
         CU_TRY(ctx, dred.alloc(n * 3));
         ST_TRY(cniic_dev_cluster_colors(ctx, din.as<uint8_t>(), n, sp.arg, ctx->codec_max_iters, CNIIC_TIE_KEEP_CURRENT, dred.as<uint8_t>(), nullptr, nullptr));
-        std::vector<uint8_t> red(n * 3);
-        CU_TRY(ctx, cudaMemcpyAsync(red.data(), dred.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         s.u32(w); s.u32(h);
-        ST_TRY(encode_hufman_body(ctx, dred.as<uint8_t>(), red.data(), n, s));
+        ST_TRY(encode_hufman_body(ctx, dred.as<uint8_t>(), n, s));  // the recoloured image never leaves HBM
         break;
     }
     case CK_VORONOI: {  // clusterc.rs:148-166
@@ -341,11 +335,9 @@ extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8
             // pass 2: the delta stream itself, then bit packing, both on the GPU
             rc = cniic_delta_i16_device(ctx, din.as<uint8_t>(), w, h, dd.as<int16_t>());
         }
-        std::vector<uint8_t> payload;
-        if (rc == CNIIC_OK) rc = cniic_dev_huffman_pack(ctx, 1, dd.p, n, d_keys, u, T.code, T.len, &payload);
+        if (rc == CNIIC_OK) rc = cniic_dev_huffman_pack(ctx, 1, dd.p, n, d_keys, u, T.code, T.len, &s.v);
         cniic_cache_free(ctx, d_keys);
         ST_TRY(rc);
-        s.v.insert(s.v.end(), payload.begin(), payload.end());
         break;
     }
     case CK_HILBERT_RLE: {  // hilbertc.rs:26-38, 99-196 ; records = u8 count (1..=255) + Rgb slice

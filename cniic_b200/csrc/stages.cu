@@ -1581,8 +1581,7 @@ extern "C" int cniic_sse_rgb(cniic_ctx *ctx, const uint8_t *a, const uint8_t *b,
 // *out receives the payload bytes (MSB-first, zero padded to a whole byte).
 int cniic_dev_huffman_pack(cniic_ctx *ctx, int src_kind, const void *d_src, size_t n, const uint32_t *d_keys, size_t nsym,
                            const std::vector<uint64_t> &codes, const std::vector<uint8_t> &lens, std::vector<uint8_t> *out) {
-    out->clear();
-    if (n == 0 || nsym == 0) return CNIIC_OK;
+    if (n == 0 || nsym == 0) return CNIIC_OK;  // the payload is APPENDED to *out (the stream under construction)
     const size_t nblocks = (n + 4095) / 4096;
     DevBuf dl(ctx), dc(ctx), bb(ctx), off(ctx), dout(ctx);
     CU_TRY(ctx, dl.alloc(nsym));
@@ -1606,8 +1605,9 @@ int cniic_dev_huffman_pack(cniic_ctx *ctx, int src_kind, const void *d_src, size
     else pack_write_kernel<1><<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_src, n, d_keys, (uint32_t)nsym, dl.as<uint8_t>(), dc.as<unsigned long long>(), off.as<unsigned long long>(), dout.as<uint32_t>());
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
-    out->resize(nbytes);
-    CU_TRY(ctx, cudaMemcpyAsync(out->data(), dout.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t at = out->size();
+    out->resize(at + nbytes);
+    CU_TRY(ctx, cudaMemcpyAsync(out->data() + at, dout.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CNIIC_OK;
 }
