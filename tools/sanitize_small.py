@@ -19,5 +19,21 @@ for im in (img, sq):
     ctx.hilbert_xy(im.shape[1], im.shape[0]); ctx.hilbert_gather(im); d = ctx.delta(im); ctx.undelta(d, im.shape[1], im.shape[0]); ctx.hist_delta(im)
     for e in ("hufman", "delta", "hilbert(rle)", "voronoi(8)", "cluster-colors(8)"):
         c = codecs.Codec.from_str(ctx, e, 3); c.decode(c.encode(im))
+# batch API (every kernel family through its batch entry point) and the fibonacci-coded stream of the parallel Huffman decoder
+for kind, flag in (("rgb", cb._lib.KMEANS_NO_CULL), ("rgb", cb._lib.KMEANS_FORCE_CULL), ("xy", cb._lib.KMEANS_NO_CULL), ("xy", 0)):
+    ims = [cb.synth_image_host(w, h, 9 + w, 4) for w, h in ((96, 40), (64, 64), (130, 17))]
+    ss = [cb.KMeansSession(ctx, cb.POINTS_RGB, 12, im, im.shape[0] * im.shape[1], flags=flag) if kind == "rgb" else
+          cb.KMeansSession(ctx, cb.POINTS_XYRGB, 12, im, im.shape[0] * im.shape[1], w=im.shape[1], h_local=im.shape[0], flags=flag) for im in ims]
+    cb.kmeans_reset_batch(ss); cb.kmeans_run_batch(ss, 3)
+    for s in ss:
+        s.get(); s.close()
+ctx.kmeans_rgb_batch([img, sq, img[:20]], 9, max_iters=3)
+fib = [1, 1]
+while len(fib) < 24:
+    fib.append(fib[-1] + fib[-2])
+px = np.repeat(np.arange(24), fib); np.random.default_rng(0).shuffle(px)
+deep = np.stack([px, px * 3 % 256, px * 7 % 256], 1).astype(np.uint8)[:256 * (len(px) // 256)].reshape(-1, 256, 3)
+for e in ("hufman", "delta", "hilbert(rle)"):
+    c = codecs.Codec.from_str(ctx, e); assert np.array_equal(c.decode(c.encode(deep)), deep)
 ctx.sse(img, img[::-1].copy())
 print("sanitize target done")
