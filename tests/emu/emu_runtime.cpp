@@ -208,9 +208,27 @@ void run_cta(const LaunchCfg &cfg, Idx bid) {
         f.stack = get_stack(t);
         context_make(&f.uc, f.stack, STACK_BYTES, trampoline);
     }
+    // Scheduling order between yield points.  The CUDA model allows any; running the fibers of a CTA in reverse or in a
+    // random order (EMU_SCHED=reverse | random[:seed]) makes a missing __syncthreads() show up as a wrong result with high
+    // probability, because a thread then runs ahead of (or behind) the neighbours a forward sweep would have kept it next to.
+    static int sched_mode = -1;
+    static unsigned long long rng = 0x9E3779B97F4A7C15ull;
+    if (sched_mode < 0) {
+        const char *e = getenv("EMU_SCHED");
+        sched_mode = !e ? 0 : (!strncmp(e, "reverse", 7) ? 1 : (!strncmp(e, "random", 6) ? 2 : 0));
+        if (e && sched_mode == 2 && strchr(e, ':')) rng ^= strtoull(strchr(e, ':') + 1, nullptr, 10) * 0xD1342543DE82EF95ull;
+    }
+    std::vector<unsigned> order(T);
+    for (unsigned t = 0; t < T; t++) order[t] = sched_mode == 1 ? T - 1 - t : t;
     while (M.n_live) {
         bool progress = false;
-        for (unsigned t = 0; t < T; t++) {
+        if (sched_mode == 2)  // a fresh permutation for every sweep
+            for (unsigned t = T - 1; t > 0; t--) {
+                rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                std::swap(order[t], order[rng % (t + 1)]);
+            }
+        for (unsigned oi = 0; oi < T; oi++) {
+            const unsigned t = order[oi];
             Fiber &f = M.fibers[t];
             if (f.done) continue;
             if (f.wait_ptr && *f.wait_ptr == f.wait_val) continue;

@@ -48,6 +48,14 @@ __global__ void k_divergent(int *p) {
     else p[threadIdx.x] = __shfl_xor_sync(0xffffffffu, (int)threadIdx.x, 1);
 }
 
+// a missing barrier that a forward sweep over the threads hides: every thread reads its LEFT neighbour's slot
+__global__ void k_race(int *out) {
+    __shared__ int s_v[64];
+    s_v[threadIdx.x] = (int)threadIdx.x * 3;
+    /* __syncthreads() is missing here */
+    out[threadIdx.x] = threadIdx.x ? s_v[threadIdx.x - 1] : 0;
+}
+
 int main(int argc, char **argv) {
     const char *mode = argc > 1 ? argv[1] : "ok";
     int *d = nullptr;
@@ -60,6 +68,15 @@ int main(int argc, char **argv) {
     }
     if (!strcmp(mode, "deadlock")) { k_deadlock<<<1, 32>>>(d); return 0; }
     if (!strcmp(mode, "divergent")) { k_divergent<<<1, 32>>>(d); return 0; }
+    if (!strcmp(mode, "race")) {  // exit code 0 = the hazard stayed hidden, 3 = it produced a wrong value
+        k_race<<<1, 64>>>(d);
+        int h[64];
+        cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+        for (int i = 1; i < 64; i++)
+            if (h[i] != (i - 1) * 3) { fprintf(stderr, "race exposed at thread %d\n", i); return 3; }
+        printf("race hidden\n");
+        return 0;
+    }
     const int n = 100000;
     std::vector<int> h(n);
     long long want = 0;

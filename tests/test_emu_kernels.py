@@ -72,6 +72,10 @@ def test_emu_detects_out_of_bounds_and_deadlocks():
         r = subprocess.run([exe, case], capture_output=True, text=True, timeout=60)
         assert needle in (r.stderr + r.stdout), (case, r.stderr, r.stdout)
         assert (r.returncode == 0) == (case == "ok")
+    # a missing __syncthreads() that the forward sweep hides is exposed by the other scheduling orders
+    assert subprocess.run([exe, "race"], capture_output=True, env=dict(os.environ, EMU_SCHED="forward")).returncode == 0
+    assert subprocess.run([exe, "race"], capture_output=True, env=dict(os.environ, EMU_SCHED="reverse")).returncode == 3
+    assert subprocess.run([exe, "race"], capture_output=True, env=dict(os.environ, EMU_SCHED="random:1")).returncode == 3
 
 
 @pytest.mark.parametrize("workload", ["c2", "c4", "c3"])
