@@ -70,6 +70,7 @@ struct KmDev {
     uint32_t *g_cpk;
     uint32_t *g_cxy;
     uint32_t *g_nrm;
+    uint4 *g_ent;        // culled D = 5, v2: {colour, position, |c|^2, 0} per centroid in one 128-bit word
     uint16_t *sc_list;   // [n_super][k] centroid ids, ascending
     uint32_t *sc_count;  // [n_super]
     uint32_t super_x, super_y;
@@ -86,6 +87,7 @@ struct KmDev {
     unsigned long long *sums_other;            // my other ping-pong buffer (zeroed here for the next iteration)
     unsigned long long *sums_red;              // local reduced sums the rest of finalize reads
     const uint2 *tile_box;  // per 2048-point tile of the sorted copy: {bytewise min, bytewise max} of the packed colours
+    const uint4 *wseg;      // culled D = 3, v2: per 256-point warp segment {box min, box max, sum r | sum g << 16, sum b | count << 16}
     unsigned long long *sums;  // k*(D+1) partial sums + 1 moved counter
     int32_t *cen;              // k*D
     unsigned long long *weights;
@@ -537,6 +539,279 @@ __device__ __forceinline__ void km_assign_rgb_cull_body(const KmDev d) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// D = 3 culled kernel, second version (default; CNIIC_RGB_CULL_V1=1 selects the first).  Same results bit for bit, fewer
+// instructions per point (the first version is issue bound: profiles/r01_ncu_full_c2_culled_final.txt):
+//   * one pass computes both bounds of a centroid against the tile box (the lower bounds wait in shared memory for U);
+//   * a second, warp-level culling: the static colour box of the warp's own 256 sorted points prunes the tile's survivors
+//     again (same bound argument, on a box inside the tile box), so a point scores ~half as many centroids;
+//   * warp segments whose 256 points all land in one cluster add their PRECOMPUTED channel sums (static per session);
+//   * 32-bit point indices (n < 2^31) and a 32-bit moved counter.
+// ------------------------------------------------------------------------------------------------------------
+// per tile: colour box; per warp segment (256 consecutive sorted points): colour box, channel sums, point count
+__global__ void __launch_bounds__(256) km_tile_boxes2(const uint32_t *__restrict__ pts_sorted, uint32_t n, uint2 *boxes, uint4 *wseg) {
+    __shared__ uint32_t s_mn[8], s_mx[8];
+    const uint32_t base = blockIdx.x * TILE + threadIdx.x * PX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t mn = 0xffffffffu, mx = 0u, cnt = 0;
+    int sr = 0, sg = 0, sb = 0;
+    for (int p = 0; p < PX; p++)
+        if (base + p < n) {
+            const uint32_t v = pts_sorted[base + p];
+            mn = __vminu4(mn, v); mx = __vmaxu4(mx, v);
+            sr += v & 0xff; sg += (v >> 8) & 0xff; sb += (v >> 16) & 0xff; cnt++;
+        }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = __vmaxu4(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        sr += __shfl_xor_sync(0xffffffffu, sr, o); sg += __shfl_xor_sync(0xffffffffu, sg, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) {
+        s_mn[warp] = mn; s_mx[warp] = mx;
+        wseg[blockIdx.x * 8 + warp] = make_uint4(mn & 0xffffffu, mx & 0xffffffu, uint32_t(sr) | (uint32_t(sg) << 16), uint32_t(sb) | (cnt << 16));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) { mn = __vminu4(mn, s_mn[i]); mx = __vmaxu4(mx, s_mx[i]); }
+        boxes[blockIdx.x] = make_uint2(mn, mx);
+    }
+}
+
+template <bool WEIGHTED>
+__device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
+    if (d.st->done || d.st->dist_empty) return;
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t k = d.k;
+    uint4 *t_ent = smem_raw;                                   // RCAP x {cpk, packed bias, id, -}
+    uint2 *s_cen = reinterpret_cast<uint2 *>(t_ent + RCAP);    // k x {cpk, |c|^2}
+    uint32_t *s_lb = reinterpret_cast<uint32_t *>(s_cen + ((k + 1) & ~1u));  // k lower bounds against the current tile box
+    uint32_t *s_acc32 = s_lb + ((k + 3) & ~3u);
+    unsigned long long *s_acc64 = reinterpret_cast<unsigned long long *>(s_lb + ((k + 3) & ~3u));
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_U;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < k; i += THREADS) s_cen[i] = make_uint2(d.g_cpk[i], d.g_nrm[i]);
+    for (uint32_t i = tid; i < 4 * k; i += THREADS) {
+        if (WEIGHTED) s_acc64[i] = 0ull;
+        else s_acc32[i] = 0u;
+    }
+    const uint32_t n = (uint32_t)d.n_local;  // < 2^31 (cniic_kmeans_open)
+    const uint32_t tiles = (n + TILE - 1) / TILE;
+    uint32_t moved = 0;
+    unsigned long long pairs_local = 0;
+
+    for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t base = tile * TILE + uint32_t(tid) * PX;
+        int nv = 0;
+        if (base < n) nv = (n - base) >= PX ? PX : int(n - base);
+        uint32_t px[PX];
+        uint16_t prev[PX];
+        if (nv == PX) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(d.pts_sorted + base)), b = __ldg(reinterpret_cast<const uint4 *>(d.pts_sorted + base) + 1);
+            px[0] = a.x; px[1] = a.y; px[2] = a.z; px[3] = a.w; px[4] = b.x; px[5] = b.y; px[6] = b.z; px[7] = b.w;
+            const uint4 pv = *reinterpret_cast<const uint4 *>(d.assign + base);
+            prev[0] = pv.x & 0xffff; prev[1] = pv.x >> 16; prev[2] = pv.y & 0xffff; prev[3] = pv.y >> 16;
+            prev[4] = pv.z & 0xffff; prev[5] = pv.z >> 16; prev[6] = pv.w & 0xffff; prev[7] = pv.w >> 16;
+        } else {
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                px[p] = p < nv ? d.pts_sorted[base + p] : 0u;
+                prev[p] = p < nv ? d.assign[base + p] : 0;
+            }
+        }
+        const uint2 box = d.tile_box[tile];            // static colour box of this tile
+        const uint4 seg = d.wseg[tile * 8 + warp];     // static box / sums of this warp's 256 points
+        const int r0 = box.x & 0xff, g0 = (box.x >> 8) & 0xff, b0 = (box.x >> 16) & 0xff;
+        const int r1 = box.y & 0xff, g1 = (box.y >> 8) & 0xff, b1 = (box.y >> 16) & 0xff;
+        __syncthreads();  // previous tile done with s_U / t_ent (and s_cen is loaded on the first pass)
+        if (tid == 0) s_U = 0xffffffffu;
+        __syncthreads();
+        // ---- one pass: upper and lower bound of every centroid against the tile box ----
+        uint32_t umin = 0xffffffffu;
+        for (uint32_t c = tid; c < k; c += THREADS) {
+            const uint32_t cp = s_cen[c].x;
+            const int cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
+            const int dr0 = cr - r0, dr1 = cr - r1, dg0 = cg - g0, dg1 = cg - g1, db0 = cb - b0, db1 = cb - b1;
+            umin = min(umin, uint32_t(sq(max(abs(dr0), abs(dr1))) + sq(max(abs(dg0), abs(dg1))) + sq(max(abs(db0), abs(db1)))));
+            s_lb[c] = uint32_t(sq(max(0, max(-dr0, dr1))) + sq(max(0, max(-dg0, dg1))) + sq(max(0, max(-db0, db1))));  // read back by this thread only
+        }
+        for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+        if (lane == 0) atomicMin(&s_U, umin);
+        __syncthreads();
+        const uint32_t U = s_U;
+        // this warp's own box
+        const int wr0 = seg.x & 0xff, wg0 = (seg.x >> 8) & 0xff, wb0 = (seg.x >> 16) & 0xff;
+        const int wr1 = seg.y & 0xff, wg1 = (seg.y >> 8) & 0xff, wb1 = (seg.y >> 16) & 0xff;
+        const uint32_t seg_pts = seg.w >> 16;
+
+        int best[PX], bi[PX];
+#pragma unroll
+        for (int p = 0; p < PX; p++) { best[p] = INT_MIN; bi[p] = 0; }
+        for (uint32_t cb0 = 0; cb0 < k; cb0 += RCAP) {
+            const uint32_t c = cb0 + tid;
+            bool keep = false;
+            uint4 ent = make_uint4(0, 0, 0, 0);
+            if (c < k) {
+                const uint2 ce = s_cen[c];
+                keep = s_lb[c] <= U;
+                // packed score: (2*dot - |c|^2) * 4096 + (4095 - id)  ==  dot * 8192 + ent.y ; max() picks the best key, then the lowest id
+                ent = make_uint4(ce.x, uint32_t(-int(ce.y) * 4096 + 4095 - int(c)), c, 0);
+            }
+            uint32_t nt;
+            const uint32_t r = block_rank256(keep, s_warp, &nt);
+            if (keep) t_ent[r] = ent;
+            __syncthreads();
+            if (nt <= 32) {
+                // ---- warp-level culling of the tile's survivors against the warp's own box (exact, same argument) ----
+                uint32_t ubw = 0xffffffffu, lbw = 0xffffffffu;
+                if (uint32_t(lane) < nt) {
+                    const uint32_t cp = t_ent[lane].x;
+                    const int cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
+                    const int dr0 = cr - wr0, dr1 = cr - wr1, dg0 = cg - wg0, dg1 = cg - wg1, db0 = cb - wb0, db1 = cb - wb1;
+                    ubw = uint32_t(sq(max(abs(dr0), abs(dr1))) + sq(max(abs(dg0), abs(dg1))) + sq(max(abs(db0), abs(db1))));
+                    lbw = uint32_t(sq(max(0, max(-dr0, dr1))) + sq(max(0, max(-dg0, dg1))) + sq(max(0, max(-db0, db1))));
+                }
+                const uint32_t Uw = __reduce_min_sync(0xffffffffu, ubw);
+                uint32_t m = __ballot_sync(0xffffffffu, uint32_t(lane) < nt && lbw <= Uw);
+                if (lane == 0) pairs_local += (unsigned long long)__popc(m) * seg_pts;
+                while (m) {  // warp-uniform loop over the set bits, two survivors per step
+                    const int e0 = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint4 c0 = t_ent[e0];
+                    if (m) {
+                        const int e1 = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint4 c1 = t_ent[e1];
+#pragma unroll
+                        for (int p = 0; p < PX; p++)
+                            best[p] = max3i(best[p], dp4a_uu(px[p], c0.x, 0) * 8192 + int(c0.y), dp4a_uu(px[p], c1.x, 0) * 8192 + int(c1.y));
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < PX; p++) best[p] = max(best[p], dp4a_uu(px[p], c0.x, 0) * 8192 + int(c0.y));
+                    }
+                }
+            } else {
+                if (lane == 0) pairs_local += (unsigned long long)nt * seg_pts;
+                uint32_t e = 0;
+                for (; e + 2 <= nt; e += 2) {
+                    const uint4 c0 = t_ent[e], c1 = t_ent[e + 1];
+#pragma unroll
+                    for (int p = 0; p < PX; p++)
+                        best[p] = max3i(best[p], dp4a_uu(px[p], c0.x, 0) * 8192 + int(c0.y), dp4a_uu(px[p], c1.x, 0) * 8192 + int(c1.y));
+                }
+                if (e < nt) {
+                    const uint4 c0 = t_ent[e];
+#pragma unroll
+                    for (int p = 0; p < PX; p++) best[p] = max(best[p], dp4a_uu(px[p], c0.x, 0) * 8192 + int(c0.y));
+                }
+            }
+            if (cb0 + RCAP < k) __syncthreads();
+        }
+#pragma unroll
+        for (int p = 0; p < PX; p++) { bi[p] = 4095 - (best[p] & 4095); best[p] >>= 12; }  // unpack: id, exact key
+
+        uint16_t idx[PX];
+        bool any_moved = false, uniform = nv == PX;
+#pragma unroll
+        for (int p = 0; p < PX; p++) {
+            int found = bi[p];
+            if (p < nv && d.tie == CNIIC_TIE_KEEP_CURRENT && found != prev[p]) {
+                // a culled current cluster is strictly farther than the winner (LB > U), so it cannot tie
+                const uint2 ce = s_cen[prev[p]];
+                if (2 * dp4a_uu(px[p], ce.x, 0) - int(ce.y) == best[p]) found = prev[p];
+            }
+            idx[p] = (uint16_t)found;
+            if (p < nv && idx[p] != prev[p]) { moved++; any_moved = true; }
+            if (p > 0 && idx[p] != idx[0]) uniform = false;
+        }
+        if (any_moved) {
+            if (nv == PX) {
+                uint4 ov;
+                ov.x = idx[0] | (uint32_t(idx[1]) << 16); ov.y = idx[2] | (uint32_t(idx[3]) << 16);
+                ov.z = idx[4] | (uint32_t(idx[5]) << 16); ov.w = idx[6] | (uint32_t(idx[7]) << 16);
+                *reinterpret_cast<uint4 *>(d.assign + base) = ov;
+            } else {
+#pragma unroll
+                for (int p = 0; p < PX; p++)
+                    if (p < nv) d.assign[base + p] = idx[p];
+            }
+        }
+        // ---- accumulate ----
+        if (WEIGHTED) {
+            unsigned long long ar = 0, ag = 0, ab = 0, aw = 0;
+            int run = -1;
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                if (p < nv) {
+                    if (idx[p] != run) {
+                        if (run >= 0) {
+                            atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
+                            atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+                        }
+                        run = idx[p]; ar = ag = ab = aw = 0;
+                    }
+                    const unsigned long long wq = d.wts_sorted[base + p];
+                    ar += (px[p] & 0xff) * wq; ag += ((px[p] >> 8) & 0xff) * wq; ab += ((px[p] >> 16) & 0xff) * wq; aw += wq;
+                }
+            }
+            if (run >= 0) {
+                atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
+                atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+            }
+        } else {
+            const int lead = __shfl_sync(0xffffffffu, (int)idx[0], 0);  // unconditional: every lane must reach the shuffle
+            const bool warp_uniform = __all_sync(0xffffffffu, uniform && (int)idx[0] == lead);
+            if (warp_uniform) {
+                // all 256 points of the warp's segment land in one cluster: add the segment's precomputed sums
+                if (lane == 0) {
+                    atomicAdd(&s_acc32[4 * lead], seg.z & 0xffffu); atomicAdd(&s_acc32[4 * lead + 1], seg.z >> 16);
+                    atomicAdd(&s_acc32[4 * lead + 2], seg.w & 0xffffu); atomicAdd(&s_acc32[4 * lead + 3], seg.w >> 16);
+                }
+            } else if (uniform) {
+                int ar = 0, ag = 0, ab = 0;
+#pragma unroll
+                for (int p = 0; p < PX; p++) {
+                    ar = dp4a_uu(px[p], 0x00000001u, ar); ag = dp4a_uu(px[p], 0x00000100u, ag); ab = dp4a_uu(px[p], 0x00010000u, ab);
+                }
+                atomicAdd(&s_acc32[4 * idx[0]], (uint32_t)ar); atomicAdd(&s_acc32[4 * idx[0] + 1], (uint32_t)ag);
+                atomicAdd(&s_acc32[4 * idx[0] + 2], (uint32_t)ab); atomicAdd(&s_acc32[4 * idx[0] + 3], (uint32_t)PX);
+            } else {
+                uint32_t ar = 0, ag = 0, ab = 0, aw = 0;
+                int run = -1;
+#pragma unroll
+                for (int p = 0; p < PX; p++) {
+                    if (p < nv) {
+                        if (idx[p] != run) {
+                            if (run >= 0) {
+                                atomicAdd(&s_acc32[4 * run], ar); atomicAdd(&s_acc32[4 * run + 1], ag);
+                                atomicAdd(&s_acc32[4 * run + 2], ab); atomicAdd(&s_acc32[4 * run + 3], aw);
+                            }
+                            run = idx[p]; ar = ag = ab = aw = 0;
+                        }
+                        ar += px[p] & 0xff; ag += (px[p] >> 8) & 0xff; ab += (px[p] >> 16) & 0xff; aw += 1;
+                    }
+                }
+                if (run >= 0) {
+                    atomicAdd(&s_acc32[4 * run], ar); atomicAdd(&s_acc32[4 * run + 1], ag);
+                    atomicAdd(&s_acc32[4 * run + 2], ab); atomicAdd(&s_acc32[4 * run + 3], aw);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < 4 * k; i += THREADS) {
+        const unsigned long long v = WEIGHTED ? s_acc64[i] : (unsigned long long)s_acc32[i];
+        if (v) atomicAdd(&d.sums[i], v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        moved += __shfl_down_sync(0xffffffffu, moved, o);
+        pairs_local += __shfl_down_sync(0xffffffffu, pairs_local, o);
+    }
+    if (lane == 0 && moved) atomicAdd(&d.sums[4 * k], (unsigned long long)moved);
+    if (lane == 0 && pairs_local) atomicAdd(&d.st->pairs, pairs_local);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // D = 5 fused assign + accumulate: tile = 256 pixels x 8 rows, warp = one row, lane = 8 consecutive pixels
 // ------------------------------------------------------------------------------------------------------------
 
@@ -953,6 +1228,266 @@ __device__ __forceinline__ void km_assign_xyrgb_cull_body(const KmDev d) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// D = 5 culled kernel, second version (default; CNIIC_XY_CULL_V1=1 selects the first).  Same culling and scoring; what changed is
+// the 43 % of the instructions the first version spent AFTER the scoring (profiles/r01_ncu_full_c3_culled_final.txt):
+//   * the 8 current cluster ids of a lane arrive in one 128-bit load and leave in one 128-bit store;
+//   * the keep-current check reads the old centroid with one 128-bit load (g_ent) instead of three 32-bit loads;
+//   * a warp whose 4 x 64 pixels all land in one cluster adds closed-form coordinate sums and PRECOMPUTED colour sums (6 shared
+//     atomics per warp instead of per lane); a lane whose 8 pixels agree uses closed forms + integer-dot channel sums.
+// ------------------------------------------------------------------------------------------------------------
+// static per session: colour box of every 64x32 tile, and per warp segment (4 rows x 64 pixels) {sum r, sum g, sum b, pixel count}
+__global__ void __launch_bounds__(THREADS) km_tile_boxes_xy2(const uint8_t *__restrict__ rgb, uint32_t w, uint32_t hl, uint2 *boxes, uint4 *wseg) {
+    __shared__ uint32_t s_mn[8], s_mx[8];
+    const uint32_t tiles_x = (w + TW - 1) / TW;
+    const int x0 = (blockIdx.x % tiles_x) * TW, yl0 = (blockIdx.x / tiles_x) * TH;
+    const int vw = min(TW, int(w) - x0), vh = min(TH, int(hl) - yl0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = warp * 4 + (lane >> 3), xr0 = (lane & 7) * 8;
+    uint32_t mn = 0xffffffffu, mx = 0u, cnt = 0, sr = 0, sg = 0, sb = 0;
+    if (row < vh)
+        for (int p = 0; p < PX; p++)
+            if (xr0 + p < vw) {
+                const uint8_t *q = rgb + ((size_t)(yl0 + row) * w + x0 + xr0 + p) * 3;
+                const uint32_t v = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+                mn = __vminu4(mn, v); mx = __vmaxu4(mx, v);
+                sr += q[0]; sg += q[1]; sb += q[2]; cnt++;
+            }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = __vmaxu4(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        sr += __shfl_xor_sync(0xffffffffu, sr, o); sg += __shfl_xor_sync(0xffffffffu, sg, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; wseg[blockIdx.x * 8 + warp] = make_uint4(sr, sg, sb, cnt); }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 8; i++) { mn = __vminu4(mn, s_mn[i]); mx = __vmaxu4(mx, s_mx[i]); }
+        boxes[blockIdx.x] = make_uint2(mn & 0xffffff, mx & 0xffffff);
+    }
+}
+
+__device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
+    if (d.st->done || d.st->dist_empty) return;
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t k = d.k;
+    uint4 *t_ent = smem_raw;                                              // TCAP x {cpk, cxy, kb, id}
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(t_ent + TCAP);         // 6*k u32
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_box[8];  // min r,g,b ; max r,g,b ; U
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < 6 * k; i += THREADS) s_acc[i] = 0u;
+
+    const uint32_t w = d.w, hl = d.h_local;
+    const uint32_t tiles_x = (w + TW - 1) / TW, tiles_y = (hl + TH - 1) / TH;
+    const unsigned long long tiles = (unsigned long long)tiles_x * tiles_y;
+    const bool fast_ok = (w % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.rgb) & 7) == 0);
+    unsigned long long moved = 0, pairs_local = 0;
+    uint32_t since_flush = 0;
+
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t ty = uint32_t(tile / tiles_x), tx = uint32_t(tile % tiles_x);
+        const int x0 = tx * TW, yl0 = ty * TH;
+        const int vw = min(TW, int(w) - x0), vh = min(TH, int(hl) - yl0);
+        const int yg0 = d.y0 + yl0;
+        // ---- this lane's 8 pixels ----
+        const int row = warp * 4 + (lane >> 3), xr0 = (lane & 7) * 8;
+        const int yl = yl0 + row;
+        int nv = 0;
+        if (row < vh && xr0 < vw) nv = min(PX, vw - xr0);
+        const unsigned long long lbase = (unsigned long long)yl * w + x0 + xr0;
+        uint32_t px[PX];
+        if (nv == PX && fast_ok) {
+            const uint2 *p = reinterpret_cast<const uint2 *>(d.rgb + lbase * 3);
+            const uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+            const uint32_t wd[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+            unpack8(wd, px);
+        } else {
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                px[p] = 0;
+                if (p < nv) {
+                    const uint8_t *q = d.rgb + (lbase + p) * 3;
+                    px[p] = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+                }
+            }
+        }
+        // current cluster of my 8 pixels: one 128-bit load (issued early, consumed after the scoring)
+        uint4 pv = make_uint4(0, 0, 0, 0);
+        if (nv == PX && fast_ok) pv = *reinterpret_cast<const uint4 *>(d.assign + lbase);
+        else {
+            uint32_t t[PX];
+#pragma unroll
+            for (int p = 0; p < PX; p++) t[p] = p < nv ? d.assign[lbase + p] : 0u;
+            pv = make_uint4(t[0] | (t[1] << 16), t[2] | (t[3] << 16), t[4] | (t[5] << 16), t[6] | (t[7] << 16));
+        }
+        // ---- static colour bounding box of the tile and sums of my warp's 4 x 64 pixels (km_tile_boxes_xy2, once per session) ----
+        const uint2 box = d.tile_box[tile];
+        const uint4 seg = d.wseg[tile * 8 + warp];
+        __syncthreads();  // previous tile is done with s_box / t_ent
+        if (tid == 0) s_box[6] = 0xffffffffu;
+        __syncthreads();
+        const int bx0 = x0, bx1 = x0 + vw - 1, by0 = yg0, by1 = yg0 + vh - 1;
+        const int r0 = box.x & 0xff, g0 = (box.x >> 8) & 0xff, b0 = (box.x >> 16) & 0xff;
+        const int r1 = box.y & 0xff, g1 = (box.y >> 8) & 0xff, b1 = (box.y >> 16) & 0xff;
+        const uint32_t sup = (ty / (SH / TH)) * d.super_x + tx / (SW / TW);
+        const uint32_t m = d.sc_count[sup];
+        const uint16_t *list = d.sc_list + (size_t)sup * k;
+        // ---- pass 1: U = min_c UB_c over the supertile's list (the first 256 candidates stay in registers for pass 2) ----
+        uint32_t umin = 0xffffffffu;
+        uint4 ent0 = make_uint4(0, 0, 0, 0);
+        uint32_t lb0 = 0xffffffffu;
+        for (uint32_t j = tid; j < m; j += THREADS) {
+            const uint32_t id = list[j];
+            const uint32_t cxy = d.g_cxy[id], cp = d.g_cpk[id];
+            const int cx = cxy & 0xffff, cy = cxy >> 16, cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
+            const uint32_t ub = sq(max(abs(cx - bx0), abs(cx - bx1))) + sq(max(abs(cy - by0), abs(cy - by1))) +
+                                sq(max(abs(cr - r0), abs(cr - r1))) + sq(max(abs(cg - g0), abs(cg - g1))) + sq(max(abs(cb - b0), abs(cb - b1)));
+            umin = min(umin, ub);
+            if (j < THREADS) {
+                lb0 = sq(max(0, max(bx0 - cx, cx - bx1))) + sq(max(0, max(by0 - cy, cy - by1))) +
+                      sq(max(0, max(r0 - cr, cr - r1))) + sq(max(0, max(g0 - cg, cg - g1))) + sq(max(0, max(b0 - cb, cb - b1)));
+                ent0 = make_uint4(cp, cxy, uint32_t(2 * (x0 * cx + yg0 * cy) - int(d.g_nrm[id])), id);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+        if (lane == 0) atomicMin(&s_box[6], umin);
+        __syncthreads();
+        const uint32_t U = s_box[6];
+
+        uint32_t pxy[PX];
+#pragma unroll
+        for (int p = 0; p < PX; p++) pxy[p] = uint32_t(xr0 + p) | (uint32_t(row) << 8);
+        int best[PX], bi[PX];
+#pragma unroll
+        for (int p = 0; p < PX; p++) { best[p] = INT_MIN; bi[p] = 0; }
+        // ---- pass 2 + scoring, TCAP candidates of the list per round (one round in the common case) ----
+        for (uint32_t base = 0; base < m; base += TCAP) {
+            const uint32_t j = base + tid;
+            bool keep = false;
+            uint4 ent = ent0;
+            if (base == 0) {
+                keep = j < m && lb0 <= U;
+            } else if (j < m) {
+                const uint32_t id = list[j];
+                const uint32_t cxy = d.g_cxy[id], cp = d.g_cpk[id];
+                const int cx = cxy & 0xffff, cy = cxy >> 16, cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
+                const uint32_t lb = sq(max(0, max(bx0 - cx, cx - bx1))) + sq(max(0, max(by0 - cy, cy - by1))) +
+                                    sq(max(0, max(r0 - cr, cr - r1))) + sq(max(0, max(g0 - cg, cg - g1))) + sq(max(0, max(b0 - cb, cb - b1)));
+                keep = lb <= U;
+                ent = make_uint4(cp, cxy, uint32_t(2 * (x0 * cx + yg0 * cy) - int(d.g_nrm[id])), id);
+            }
+            uint32_t nt;
+            const uint32_t r = block_rank256(keep, s_warp, &nt);
+            if (keep) t_ent[r] = ent;
+            __syncthreads();
+            if (tid == 0) pairs_local += (unsigned long long)nt * vw * vh;
+            for (uint32_t e = 0; e < nt; e++) {
+                const uint4 c = t_ent[e];
+#pragma unroll
+                for (int p = 0; p < PX; p++) {
+                    const int key = 2 * dp2a_lo_su(c.y, pxy[p], dp4a_uu(px[p], c.x, 0)) + int(c.z);
+                    if (key > best[p]) { best[p] = key; bi[p] = int(c.w); }
+                }
+            }
+            if (base + TCAP < m) __syncthreads();  // next round overwrites t_ent
+        }
+
+        const uint32_t yg = yg0 + row;
+        const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+        uint32_t idx[PX];
+        bool any_moved = false, uniform = nv == PX;
+#pragma unroll
+        for (int p = 0; p < PX; p++) {
+            const uint32_t prev = (pw[p >> 1] >> (16 * (p & 1))) & 0xffffu;
+            uint32_t found = uint32_t(bi[p]);
+            if (p < nv && d.tie == CNIIC_TIE_KEEP_CURRENT && found != prev) {
+                // the current cluster may have been culled; then it is strictly farther than the winner (LB > U)
+                const uint4 ge = __ldg(d.g_ent + prev);  // {colour, position, |c|^2, -} in one load
+                const int kb = 2 * (x0 * int(ge.y & 0xffff) + yg0 * int(ge.y >> 16)) - int(ge.z);
+                if (2 * dp2a_lo_su(ge.y, pxy[p], dp4a_uu(px[p], ge.x, 0)) + kb == best[p]) found = prev;
+            }
+            if (p >= nv) found = prev;
+            idx[p] = found;
+            if (found != prev) { moved++; any_moved = true; }
+            if (p > 0 && found != idx[0]) uniform = false;
+        }
+        if (any_moved) {
+            if (nv == PX && fast_ok) {
+                *reinterpret_cast<uint4 *>(d.assign + lbase) =
+                    make_uint4(idx[0] | (idx[1] << 16), idx[2] | (idx[3] << 16), idx[4] | (idx[5] << 16), idx[6] | (idx[7] << 16));
+            } else {
+#pragma unroll
+                for (int p = 0; p < PX; p++)
+                    if (p < nv) d.assign[lbase + p] = (uint16_t)idx[p];
+            }
+        }
+        // ---- accumulate: whole warp in one cluster -> precomputed segment sums; my 8 pixels in one cluster -> closed forms +
+        //      integer-dot channel sums; otherwise runs of equal ids ----
+        const int lead = __shfl_sync(0xffffffffu, (int)idx[0], 0);  // unconditional: every lane must reach the shuffle
+        const bool warp_uniform = __all_sync(0xffffffffu, uniform && (int)idx[0] == lead) && seg.w == 256u;
+        if (warp_uniform) {
+            if (lane == 0) {
+                const uint32_t row0 = yg0 + warp * 4;
+                atomicAdd(&s_acc[6 * lead], 4u * (64u * uint32_t(x0) + 2016u));       // 4 rows x sum of x0 .. x0 + 63
+                atomicAdd(&s_acc[6 * lead + 1], 64u * (4u * row0 + 6u));              // 64 columns x sum of the 4 rows
+                atomicAdd(&s_acc[6 * lead + 2], seg.x); atomicAdd(&s_acc[6 * lead + 3], seg.y);
+                atomicAdd(&s_acc[6 * lead + 4], seg.z); atomicAdd(&s_acc[6 * lead + 5], 256u);
+            }
+        } else if (uniform) {
+            int ar = 0, ag = 0, ab = 0;
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                ar = dp4a_uu(px[p], 0x00000001u, ar); ag = dp4a_uu(px[p], 0x00000100u, ag); ab = dp4a_uu(px[p], 0x00010000u, ab);
+            }
+            const uint32_t c = idx[0];
+            atomicAdd(&s_acc[6 * c], 8u * uint32_t(x0 + xr0) + 28u); atomicAdd(&s_acc[6 * c + 1], 8u * yg);
+            atomicAdd(&s_acc[6 * c + 2], (uint32_t)ar); atomicAdd(&s_acc[6 * c + 3], (uint32_t)ag);
+            atomicAdd(&s_acc[6 * c + 4], (uint32_t)ab); atomicAdd(&s_acc[6 * c + 5], 8u);
+        } else {
+            int run = -1;
+            uint32_t ax = 0, ar = 0, ag = 0, ab = 0, an = 0;
+#pragma unroll
+            for (int p = 0; p < PX; p++) {
+                if (p < nv) {
+                    const int found = int(idx[p]);
+                    if (found != run) {
+                        if (run >= 0) {
+                            atomicAdd(&s_acc[6 * run], ax); atomicAdd(&s_acc[6 * run + 1], an * yg);
+                            atomicAdd(&s_acc[6 * run + 2], ar); atomicAdd(&s_acc[6 * run + 3], ag);
+                            atomicAdd(&s_acc[6 * run + 4], ab); atomicAdd(&s_acc[6 * run + 5], an);
+                        }
+                        run = found; ax = ar = ag = ab = an = 0;
+                    }
+                    ax += x0 + xr0 + p; ar += px[p] & 0xff; ag += (px[p] >> 8) & 0xff; ab += (px[p] >> 16) & 0xff; an += 1;
+                }
+            }
+            if (run >= 0) {
+                atomicAdd(&s_acc[6 * run], ax); atomicAdd(&s_acc[6 * run + 1], an * yg);
+                atomicAdd(&s_acc[6 * run + 2], ar); atomicAdd(&s_acc[6 * run + 3], ag);
+                atomicAdd(&s_acc[6 * run + 4], ab); atomicAdd(&s_acc[6 * run + 5], an);
+            }
+        }
+        if (++since_flush == FLUSH_TILES) {
+            __syncthreads();
+            for (uint32_t i = tid; i < 6 * k; i += THREADS) {
+                const uint32_t v = s_acc[i];
+                if (v) { atomicAdd(&d.sums[i], (unsigned long long)v); s_acc[i] = 0; }
+            }
+            since_flush = 0;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < 6 * k; i += THREADS) {
+        const uint32_t v = s_acc[i];
+        if (v) atomicAdd(&d.sums[i], (unsigned long long)v);
+    }
+    for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
+    if (lane == 0 && moved) atomicAdd(&d.sums[6 * k], moved);
+    if (tid == 0 && pairs_local) atomicAdd(&d.st->pairs, pairs_local);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // init + finalize (single CTA)
 // ------------------------------------------------------------------------------------------------------------
 
@@ -1167,7 +1702,10 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode) {
             const int rgb0 = D == 5 ? 2 : 0;
             d.g_cpk[c] = uint32_t(v[rgb0]) | (uint32_t(v[rgb0 + 1]) << 8) | (uint32_t(v[rgb0 + 2]) << 16);
             d.g_nrm[c] = nrm;
-            if (D == 5) d.g_cxy[c] = uint32_t(v[0]) | (uint32_t(v[1]) << 16);
+            if (D == 5) {
+                d.g_cxy[c] = uint32_t(v[0]) | (uint32_t(v[1]) << 16);
+                d.g_ent[c] = make_uint4(d.g_cpk[c], d.g_cxy[c], nrm, 0u);
+            }
         }
     }
     // ---- build the scan table: even-|c|^2 class first, then odd, each in ascending id order, padded to G ----
@@ -1239,15 +1777,18 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode) {
 // ------------------------------------------------------------------------------------------------------------
 template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS) km_assign_rgb(KmDev d) { km_assign_rgb_body<WEIGHTED>(d); }
 template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull(KmDev d) { km_assign_rgb_cull_body<WEIGHTED>(d); }
+template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull2(KmDev d) { km_assign_rgb_cull2_body<WEIGHTED>(d); }
 __global__ void __launch_bounds__(THREADS) km_assign_xyrgb(KmDev d) { km_assign_xyrgb_body(d); }
 __global__ void __launch_bounds__(THREADS) km_supercull(KmDev d) { km_supercull_body(d); }
 __global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull(KmDev d) { km_assign_xyrgb_cull_body(d); }
+__global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull2(KmDev d) { km_assign_xyrgb_cull2_body(d); }
 __global__ void km_init_assign(KmDev d) { km_init_assign_body(d); }
 template <int D> __global__ void km_init_centroids(KmDev d) { km_init_centroids_body<D>(d); }
 template <int D> __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) { km_finalize_body<D>(d, init_mode); }
 
 template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS) km_assign_rgb_batch(const KmDev *__restrict__ batch) { km_assign_rgb_body<WEIGHTED>(batch[blockIdx.y]); }
 template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull_batch(const KmDev *__restrict__ batch) { km_assign_rgb_cull_body<WEIGHTED>(batch[blockIdx.y]); }
+template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull2_batch(const KmDev *__restrict__ batch) { km_assign_rgb_cull2_body<WEIGHTED>(batch[blockIdx.y]); }
 __global__ void __launch_bounds__(THREADS) km_assign_xyrgb_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_body(batch[blockIdx.y]); }
 __global__ void __launch_bounds__(THREADS) km_supercull_batch(const KmDev *__restrict__ batch) {
     const KmDev &d = batch[blockIdx.y];
@@ -1255,6 +1796,7 @@ __global__ void __launch_bounds__(THREADS) km_supercull_batch(const KmDev *__res
     km_supercull_body(d);
 }
 __global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_cull_body(batch[blockIdx.y]); }
+__global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull2_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_cull2_body(batch[blockIdx.y]); }
 __global__ void km_init_assign_batch(const KmDev *__restrict__ batch) { km_init_assign_body(batch[blockIdx.y]); }
 template <int D> __global__ void km_init_centroids_batch(const KmDev *__restrict__ batch) { km_init_centroids_body<D>(batch[blockIdx.y]); }
 template <int D> __global__ void __launch_bounds__(1024) km_finalize_batch(const KmDev *__restrict__ batch, int init_mode) { km_finalize_body<D>(batch[blockIdx.x], init_mode); }
@@ -1347,6 +1889,8 @@ struct cniic_kmeans {
     cudaEvent_t pev[2 * PROF] = {};
     uint32_t launches = 0, launches_reported = 0;
     uint2 *d_boxes = nullptr;
+    uint4 *d_wseg = nullptr;  // culled D = 3, v2: per-warp-segment boxes and sums
+    bool v2 = false;          // culled D = 3: second kernel version (default)
     uint32_t *d_sorted = nullptr, *d_perm = nullptr, *d_wsorted = nullptr;  // colour-sorted copy (culled D = 3)
     uint16_t *d_assign_orig = nullptr;  // assignment mapped back to original order (filled on demand)
     bool cull = true;        // exact culling (CNIIC_KMEANS_NO_CULL in desc.flags selects brute force)
@@ -1365,9 +1909,12 @@ static int km_launch_assign(cniic_kmeans *km) {
             km_supercull<<<km->dev.super_x * km->dev.super_y, THREADS, 0, ctx->stream>>>(km->dev);
             km->launches++;
         }
-        km_assign_xyrgb_cull<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+        if (km->v2) km_assign_xyrgb_cull2<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+        else km_assign_xyrgb_cull<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     }
     else if (km->D == 5) km_assign_xyrgb<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    else if (km->cull && km->v2 && km->dev.wts) km_assign_rgb_cull2<true><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    else if (km->cull && km->v2) km_assign_rgb_cull2<false><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     else if (km->cull && km->dev.wts) km_assign_rgb_cull<true><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     else if (km->cull) km_assign_rgb_cull<false><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
     else if (km->dev.wts) km_assign_rgb<true><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
@@ -1446,7 +1993,7 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     const size_t o_st = take(sizeof(KmState));
     const size_t o_red = take((size_t(k) * (D + 1) + 2) * 8);
     const uint32_t super_x = D == 5 ? (desc->w + SW - 1) / SW : 0, super_y = D == 5 ? (desc->h_local + SH - 1) / SH : 0;
-    const size_t o_gcpk = take(size_t(k) * 4), o_gcxy = take(size_t(k) * 4), o_gnrm = take(size_t(k) * 4);
+    const size_t o_gcpk = take(size_t(k) * 4), o_gcxy = take(size_t(k) * 4), o_gnrm = take(size_t(k) * 4), o_gent = take(size_t(k) * 16);
     const size_t o_sclist = take(size_t(super_x) * super_y * k * 2), o_sccount = take(size_t(super_x) * super_y * 4 + 4);
     km->pool = cniic_cache_alloc(ctx, off);
     if (!km->pool) return fail(CNIIC_ERR_CUDA);
@@ -1483,6 +2030,7 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     dv.g_cpk = reinterpret_cast<uint32_t *>(p + o_gcpk);
     dv.g_cxy = reinterpret_cast<uint32_t *>(p + o_gcxy);
     dv.g_nrm = reinterpret_cast<uint32_t *>(p + o_gnrm);
+    dv.g_ent = reinterpret_cast<uint4 *>(p + o_gent);
     dv.sc_list = reinterpret_cast<uint16_t *>(p + o_sclist);
     dv.sc_count = reinterpret_cast<uint32_t *>(p + o_sccount);
     dv.super_x = super_x;
@@ -1505,7 +2053,15 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
             const int rc = cniic_dev_sort_colours(ctx, d_rgb, d_wts, n, km->d_sorted, km->d_perm, km->d_wsorted, &km->launches);
             if (rc != CNIIC_OK) return fail(rc);
         }
-        km_tile_boxes<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(km->d_sorted, n, km->d_boxes);
+        km->v2 = !getenv("CNIIC_RGB_CULL_V1");
+        if (km->v2) {
+            km->d_wseg = static_cast<uint4 *>(cniic_cache_alloc(ctx, ntiles * 8 * 16));
+            if (!km->d_wseg) return fail(CNIIC_ERR_CUDA);
+            km_tile_boxes2<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(km->d_sorted, (uint32_t)n, km->d_boxes, km->d_wseg);
+            dv.wseg = km->d_wseg;
+        } else {
+            km_tile_boxes<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(km->d_sorted, n, km->d_boxes);
+        }
         km->launches += 1;
         KM_TRY(cudaGetLastError());
         dv.tile_box = km->d_boxes;
@@ -1517,7 +2073,15 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
         const size_t ntiles = (size_t)((desc->w + TW - 1) / TW) * ((desc->h_local + TH - 1) / TH);
         km->d_boxes = static_cast<uint2 *>(cniic_cache_alloc(ctx, ntiles * 8));
         if (!km->d_boxes) return fail(CNIIC_ERR_CUDA);
-        km_tile_boxes_xy<<<(unsigned)ntiles, THREADS, 0, ctx->stream>>>(d_rgb, desc->w, desc->h_local, km->d_boxes);
+        km->v2 = !getenv("CNIIC_XY_CULL_V1");
+        if (km->v2) {
+            km->d_wseg = static_cast<uint4 *>(cniic_cache_alloc(ctx, ntiles * 8 * 16));
+            if (!km->d_wseg) return fail(CNIIC_ERR_CUDA);
+            km_tile_boxes_xy2<<<(unsigned)ntiles, THREADS, 0, ctx->stream>>>(d_rgb, desc->w, desc->h_local, km->d_boxes, km->d_wseg);
+            dv.wseg = km->d_wseg;
+        } else {
+            km_tile_boxes_xy<<<(unsigned)ntiles, THREADS, 0, ctx->stream>>>(d_rgb, desc->w, desc->h_local, km->d_boxes);
+        }
         km->launches++;
         KM_TRY(cudaGetLastError());
         dv.tile_box = km->d_boxes;
@@ -1527,9 +2091,14 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     if (D == 5 && km->cull) {
         km->smem = size_t(TCAP) * 16 + size_t(k) * 24 + 16;
         KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb_cull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+        KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb_cull2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     } else if (D == 5) {
         km->smem = size_t(KP) * 16 + 8 * 192 * 4 + size_t(k) * 24 + KP * 2 + k * 2 + 16;
         KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+    } else if (km->cull && km->v2) {
+        km->smem = size_t(RCAP) * 16 + size_t((k + 1) & ~1u) * 8 + size_t((k + 3) & ~3u) * 4 + size_t(k) * 4 * (d_wts ? 8 : 4) + 16;
+        if (d_wts) KM_TRY(cudaFuncSetAttribute(km_assign_rgb_cull2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+        else KM_TRY(cudaFuncSetAttribute(km_assign_rgb_cull2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     } else if (km->cull) {
         km->smem = size_t(RCAP) * 16 + size_t((k + 1) & ~1u) * 8 + size_t(k) * 4 * (d_wts ? 8 : 4) + 16;
         if (d_wts) KM_TRY(cudaFuncSetAttribute(km_assign_rgb_cull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
@@ -1540,8 +2109,11 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
         else KM_TRY(cudaFuncSetAttribute(km_assign_rgb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     }
     int per_sm = 0;
-    if (D == 5 && km->cull) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull, THREADS, km->smem));
+    if (D == 5 && km->cull && km->v2) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull2, THREADS, km->smem));
+    else if (D == 5 && km->cull) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull, THREADS, km->smem));
     else if (D == 5) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb, THREADS, km->smem));
+    else if (km->cull && km->v2 && d_wts) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull2<true>, THREADS, km->smem));
+    else if (km->cull && km->v2) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull2<false>, THREADS, km->smem));
     else if (km->cull && d_wts) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull<true>, THREADS, km->smem));
     else if (km->cull) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull<false>, THREADS, km->smem));
     else if (d_wts) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb<true>, THREADS, km->smem));
@@ -1719,7 +2291,7 @@ namespace {
 struct BatchPlan {
     cniic_ctx *ctx = nullptr;
     int D = 3;
-    bool cull = false, weighted = false;
+    bool cull = false, weighted = false, v2 = false;
     uint32_t k = 0, count = 0;
     size_t smem = 0;
     unsigned gx_assign = 1, gx_init = 1, gx_super = 0;
@@ -1742,7 +2314,7 @@ int km_batch_plan(cniic_kmeans *const *ss, uint32_t count, BatchPlan *bp) {
         cniic_kmeans *km = ss[i];
         if (!km || km->ctx != ctx) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "batch session %u is null or belongs to another context", i);
         if (km->D != k0->D || km->desc.k != k0->desc.k || km->cull != k0->cull || (km->dev.wts != nullptr) != (k0->dev.wts != nullptr) ||
-            km->smem != k0->smem || km->desc.tie_rule != k0->desc.tie_rule)
+            km->smem != k0->smem || km->desc.tie_rule != k0->desc.tie_rule || km->v2 != k0->v2)
             return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "batch session %u differs from session 0 in kind, k, tie rule, weights or kernel variant", i);
         if (km->desc.n_local != km->desc.n_total || !km->desc.n_local) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "batch session %u is sharded or empty", i);
         const cniic_kmeans_desc &ds = km->desc;
@@ -1757,14 +2329,18 @@ int km_batch_plan(cniic_kmeans *const *ss, uint32_t count, BatchPlan *bp) {
     bp->D = k0->D;
     bp->cull = k0->cull;
     bp->weighted = k0->dev.wts != nullptr;
+    bp->v2 = k0->v2;
     bp->k = k0->desc.k;
     bp->count = count;
     bp->smem = k0->smem;
     // resident CTAs of the single-problem launch (k0->grid was capped by its tile count, so recompute from the occupancy)
     int per_sm = 0;
     cudaError_t e;
-    if (bp->D == 5 && bp->cull) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull_batch, THREADS, bp->smem);
+    if (bp->D == 5 && bp->cull && bp->v2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull2_batch, THREADS, bp->smem);
+    else if (bp->D == 5 && bp->cull) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull_batch, THREADS, bp->smem);
     else if (bp->D == 5) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_batch, THREADS, bp->smem);
+    else if (bp->cull && bp->v2 && bp->weighted) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull2_batch<true>, THREADS, bp->smem);
+    else if (bp->cull && bp->v2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull2_batch<false>, THREADS, bp->smem);
     else if (bp->cull && bp->weighted) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull_batch<true>, THREADS, bp->smem);
     else if (bp->cull) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull_batch<false>, THREADS, bp->smem);
     else if (bp->weighted) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_batch<true>, THREADS, bp->smem);
@@ -1793,8 +2369,11 @@ int km_batch_upload(cniic_kmeans *const *ss, BatchPlan *bp) {
 int km_batch_set_attributes(const BatchPlan &bp) {
     cniic_ctx *ctx = bp.ctx;
     const int sm = (int)bp.smem;
-    if (bp.D == 5 && bp.cull) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_xyrgb_cull_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    if (bp.D == 5 && bp.cull && bp.v2) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_xyrgb_cull2_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    else if (bp.D == 5 && bp.cull) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_xyrgb_cull_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     else if (bp.D == 5) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_xyrgb_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    else if (bp.cull && bp.v2 && bp.weighted) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_rgb_cull2_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    else if (bp.cull && bp.v2) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_rgb_cull2_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     else if (bp.cull && bp.weighted) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_rgb_cull_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     else if (bp.cull) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_rgb_cull_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     else if (bp.weighted) CU_TRY(ctx, cudaFuncSetAttribute(km_assign_rgb_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -1811,9 +2390,12 @@ int km_batch_launch_iteration(const BatchPlan &bp, uint32_t *launched) {
             km_supercull_batch<<<dim3(bp.gx_super, bp.count), THREADS, 0, ctx->stream>>>(bp.d_batch);
             (*launched)++;
         }
-        km_assign_xyrgb_cull_batch<<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
+        if (bp.v2) km_assign_xyrgb_cull2_batch<<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
+        else km_assign_xyrgb_cull_batch<<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
     }
     else if (bp.D == 5) km_assign_xyrgb_batch<<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
+    else if (bp.cull && bp.v2 && bp.weighted) km_assign_rgb_cull2_batch<true><<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
+    else if (bp.cull && bp.v2) km_assign_rgb_cull2_batch<false><<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
     else if (bp.cull && bp.weighted) km_assign_rgb_cull_batch<true><<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
     else if (bp.cull) km_assign_rgb_cull_batch<false><<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
     else if (bp.weighted) km_assign_rgb_batch<true><<<grid, THREADS, bp.smem, ctx->stream>>>(bp.d_batch);
@@ -2003,6 +2585,7 @@ extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
     cniic_cache_free(km->ctx, km->own_wts);
     cniic_cache_free(km->ctx, km->pool);
     cniic_cache_free(km->ctx, km->d_boxes);
+    cniic_cache_free(km->ctx, km->d_wseg);
     cniic_cache_free(km->ctx, km->d_sorted);
     cniic_cache_free(km->ctx, km->d_perm);
     cniic_cache_free(km->ctx, km->d_wsorted);

@@ -189,6 +189,18 @@ template <class T> static inline T __reduce_add_sync(unsigned mask, T v) {
     for (int i = 0; i < 32; i++) if (w.present >> i & 1) r += emu::from_bits<T>(w.v[i]);
     return r;
 }
+template <class T> static inline T __reduce_min_sync(unsigned mask, T v) {
+    emu::WarpVals w; emu::warp_exchange(mask, emu::to_bits(v), 10, &w);
+    T r = v;
+    for (int i = 0; i < 32; i++) if (w.present >> i & 1) r = std::min(r, emu::from_bits<T>(w.v[i]));
+    return r;
+}
+template <class T> static inline T __reduce_max_sync(unsigned mask, T v) {
+    emu::WarpVals w; emu::warp_exchange(mask, emu::to_bits(v), 11, &w);
+    T r = v;
+    for (int i = 0; i < 32; i++) if (w.present >> i & 1) r = std::max(r, emu::from_bits<T>(w.v[i]));
+    return r;
+}
 template <class T> static inline unsigned __match_any_sync(unsigned mask, T v) {
     emu::WarpVals w; emu::warp_exchange(mask, emu::to_bits(v), 9, &w);
     unsigned r = 0;

@@ -497,3 +497,31 @@ def test_rle_decoder_verdicts_match_the_sequential_decoder(ctx):
         assert (g is None) == (o is None), i
         if o is not None:
             assert np.array_equal(g, o), i
+
+
+# ---- first versions of the culled kernels stay selectable (A/B measurements) and agree with the second versions ----
+@pytest.mark.parametrize("var,kind", [("CNIIC_RGB_CULL_V1", "rgb"), ("CNIIC_XY_CULL_V1", "xyrgb")])
+def test_first_kernel_versions_agree(ctx, var, kind, monkeypatch):
+    img = cb.synth_image_host(300, 170, 77, 12)
+    n, k = 300 * 170, 96
+    outs = []
+    for v1 in (False, True):
+        if v1:
+            monkeypatch.setenv(var, "1")
+        else:
+            monkeypatch.delenv(var, raising=False)
+        if kind == "rgb":
+            s = cb.KMeansSession(ctx, cb.POINTS_RGB, k, img, n, flags=cb._lib.KMEANS_FORCE_CULL)
+        else:
+            s = cb.KMeansSession(ctx, cb.POINTS_XYRGB, k, img, n, w=300, h_local=170)
+        s.reset()
+        st = s.run(4)
+        outs.append((s.get(), st.iterations, st.moved_total, st.pairs_scored))
+        s.close()
+    (c0, w0, a0), it0, m0, p0 = outs[0]
+    (c1, w1, a1), it1, m1, p1 = outs[1]
+    assert it0 == it1 and m0 == m1 and np.array_equal(c0, c1) and np.array_equal(w0, w1) and np.array_equal(a0, a1)
+    o = (O.kmeans_rgb if kind == "rgb" else O.kmeans_xyrgb)(img, k, mode=O.MODE_EXACT, max_iters=4)
+    assert np.array_equal(c0, o.centroids) and np.array_equal(a0, o.assign)
+    if kind == "rgb":
+        assert p0 <= p1  # the warp-level culling of the second version never scores more pairs
