@@ -449,13 +449,19 @@ __constant__ uint8_t HIL4_Y[16] = {0, 0, 1, 1, 2, 3, 3, 2, 2, 3, 3, 2, 1, 1, 0, 
 constexpr int HT = 64;            // block side
 constexpr int HT_STRIDE = 68;     // words per staged row (64 + 4 pad: rows shift by 4 banks, 128-bit aligned)
 
-constexpr int CUBE_R = 15, CUBE_S = 2 * CUBE_R + 1, CUBE_N = CUBE_S * CUBE_S * CUBE_S;  // 31^3 near-zero delta symbols
-constexpr int CUBE_FLUSH_TILES = 12;  // 12 * 4096 symbols < 2^16: the packed u16 counters cannot overflow
+// near-zero delta symbols (|d| <= 15: 97 % of the symbols of the noisy benchmark image, more for photographs) are counted in
+// shared memory: 31^3 counters packed two per word = 58 KB (+ 17 KB of staged pixels: 2 CTAs per SM).  A field holds 15 bits of
+// count plus a guard bit: the increment that sets the guard moves 2^15 counts to the global bin and clears the guard again, so
+// a CTA flushes ONCE, at the end of its persistent loop, whatever the image.  (Between that increment and its subtraction at
+// most 4095 other increments of the tile can land -- the thread reaches the tile's next barrier first -- far from the 2^15 that
+// would carry into the neighbouring field.)  The first version flushed every 12 tiles, ~20 M contended global atomics per
+// 8192^2 image, and launched 3 CTAs per SM where only 2 fit (a 1.5-wave tail).
+constexpr int CUBE_R = 15, CUBE_S = 2 * CUBE_R + 1, CUBE_N = CUBE_S * CUBE_S * CUBE_S;
 
 template <int MODE>
 __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__restrict__ rgb, uint32_t n, uint8_t *out_rgb,
                                                            int16_t *out_delta, uint32_t *bins, uint8_t *flags) {
-    extern __shared__ uint32_t s_cube[];  // MODE 2 only: CUBE_N packed u16 counters for the near-zero symbols
+    extern __shared__ uint32_t s_cube[];  // MODE 2 only: CUBE_N 15-bit counters (+ guard bit), two per word
     __shared__ __align__(16) uint32_t s_px[HT * HT_STRIDE];  // one word per pixel (r | g<<8 | b<<16)
     __shared__ uint32_t s_last[8];
     __shared__ int s_top[5];
@@ -464,7 +470,6 @@ __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__rest
     if (MODE == 2) {
         for (int i = tid; i < (CUBE_N + 1) / 2; i += 256) s_cube[i] = 0;
     }
-    int since_flush = 0;
     for (unsigned long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const unsigned long long B = blk * 4096;
         const unsigned long long i0 = B + (unsigned long long)tid * 16;
@@ -594,8 +599,7 @@ __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__rest
 #pragma unroll
             for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
         } else {
-            // near-zero symbols (|d| <= 15 per channel, the bulk of any natural image) are counted in shared memory
-            // (packed u16 counters, plain ATOMS); the rest goes to the global bins directly
+            // near-zero symbols are counted in shared memory (ATOMS), the rest goes to the global bins directly
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
@@ -603,33 +607,31 @@ __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__rest
                           d2 = int((c >> 16) & 0xff) - int((p >> 16) & 0xff);
                 if ((unsigned)(d0 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d1 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d2 + CUBE_R) < (unsigned)CUBE_S) {
                     const int ci = ((d0 + CUBE_R) * CUBE_S + (d1 + CUBE_R)) * CUBE_S + (d2 + CUBE_R);
-                    atomicAdd(&s_cube[ci >> 1], 1u << (16 * (ci & 1)));
+                    const int sh = 16 * (ci & 1);
+                    const uint32_t old = atomicAdd(&s_cube[ci >> 1], 1u << sh);
+                    if (((old >> sh) & 0x7fffu) == 0x7fffu) {  // my increment set the guard bit: 2^15 counts leave the field
+                        atomicSub(&s_cube[ci >> 1], 0x8000u << sh);
+                        const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                        atomicAdd(&bins[key], 32768u);
+                        if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
+                    }
                 } else {
                     const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
                     atomicAdd(&bins[key], 1u);
                     if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
                 }
             }
-            if (++since_flush == CUBE_FLUSH_TILES || blk + gridDim.x >= nblocks) {
-                __syncthreads();
-                for (int i = tid; i < (CUBE_N + 1) / 2; i += 256) {
-                    const uint32_t v = s_cube[i];
-                    if (v) {
-                        s_cube[i] = 0;
-#pragma unroll
-                        for (int hlf = 0; hlf < 2; hlf++) {
-                            const uint32_t cnt = (v >> (16 * hlf)) & 0xffff;
-                            if (cnt) {
-                                const int ci = 2 * i + hlf;
-                                const int d2 = ci % CUBE_S - CUBE_R, d1 = (ci / CUBE_S) % CUBE_S - CUBE_R, d0 = ci / (CUBE_S * CUBE_S) - CUBE_R;
-                                const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
-                                atomicAdd(&bins[key], cnt);
-                                if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
-                            }
-                        }
-                    }
-                }
-                since_flush = 0;
+        }
+    }
+    if (MODE == 2) {  // flush the CTA's near-zero counters into the global bins
+        __syncthreads();
+        for (int ci = tid; ci < CUBE_N; ci += 256) {
+            const uint32_t cnt = (s_cube[ci >> 1] >> (16 * (ci & 1))) & 0xffffu;
+            if (cnt) {
+                const int d2 = ci % CUBE_S - CUBE_R, d1 = (ci / CUBE_S) % CUBE_S - CUBE_R, d0 = ci / (CUBE_S * CUBE_S) - CUBE_R;
+                const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                atomicAdd(&bins[key], cnt);
+                if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
             }
         }
     }
@@ -1227,9 +1229,12 @@ int cniic_dev_hist_delta_bins(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, 
     uint8_t *flags;
     ST_TRY(hist_space(ctx, 1, d_bins, &flags, nbins));
     if (tile_path(d_rgb, nullptr, w, h)) {
-        const size_t smem = ((CUBE_N + 1) / 2) * 4;
+        const size_t smem = size_t((CUBE_N + 1) / 2) * 4;
         CU_TRY(ctx, cudaFuncSetAttribute(hilbert_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned grid = (unsigned)std::min<size_t>((size_t)w * h / 4096, (size_t)ctx->sm_count * 3);
+        int per_sm = 0;
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hilbert_tile_kernel<2>, 256, smem));
+        if (per_sm < 1) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "delta histogram kernel does not fit an SM");
+        const unsigned grid = (unsigned)std::min<size_t>((size_t)w * h / 4096, (size_t)ctx->sm_count * per_sm);  // persistent: one wave
         hilbert_tile_kernel<2><<<grid, 256, smem, ctx->stream>>>(d_rgb, w, nullptr, nullptr, *d_bins, flags);
     }
     else hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins, flags);

@@ -266,6 +266,7 @@ template <class T> static inline void __stcs(T *p, T v) { *p = v; }
 
 // atomics: one fiber runs at a time, so plain read-modify-write is atomic
 template <class T, class U> static inline T atomicAdd(T *p, U v) { const T o = *p; *p = T(o + T(v)); return o; }
+template <class T, class U> static inline T atomicSub(T *p, U v) { const T o = *p; *p = T(o - T(v)); return o; }
 template <class T, class U> static inline T atomicMin(T *p, U v) { const T o = *p; if (T(v) < o) *p = T(v); return o; }
 template <class T, class U> static inline T atomicMax(T *p, U v) { const T o = *p; if (T(v) > o) *p = T(v); return o; }
 template <class T, class U> static inline T atomicOr(T *p, U v) { const T o = *p; *p = T(o | T(v)); return o; }

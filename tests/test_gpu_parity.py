@@ -525,3 +525,15 @@ def test_first_kernel_versions_agree(ctx, var, kind, monkeypatch):
     assert np.array_equal(c0, o.centroids) and np.array_equal(a0, o.assign)
     if kind == "rgb":
         assert p0 <= p1  # the warp-level culling of the second version never scores more pairs
+
+
+def test_hist_delta_counter_spill(ctx):
+    """A flat 512x512 image puts 262 143 identical symbols through a few CTAs: the packed 15-bit shared counters must hand
+    their full 2^15 blocks to the global bins without losing or double counting (and the neighbouring field stays intact)."""
+    img = np.full((512, 512, 3), 40, np.uint8)
+    img[100:140, 7:300] = 41     # some (+1,+1,+1) / (-1,-1,-1) symbols: the neighbour fields of (0,0,0)
+    img[300, 300] = (200, 0, 90)  # and two symbols outside the shared cube
+    keys, cnts = ctx.hist_delta(img)
+    okeys, ocnts = O.hist_delta(O.delta(img))
+    assert np.array_equal(keys, okeys) and np.array_equal(cnts, ocnts)
+    assert int(cnts.sum()) == 512 * 512 and int(cnts.max()) > 200000
