@@ -102,7 +102,8 @@ def build(verbose: bool = False) -> str:
     if os.path.exists(OUT_SO) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
         return OUT_SO
     objs, procs = [], []
-    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-fno-strict-aliasing", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-unused-variable",
+    # -fsanitize=alignment: the GPU faults on a misaligned 64/128-bit access, x86 would not notice -- let UBSan stand in
+    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-fno-strict-aliasing", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-unused-variable",
              "-Wno-sign-compare", "-I", os.path.join(HERE, "shim")]
     gen_dir = os.path.join(OUT_DIR, "gen")
     os.makedirs(gen_dir, exist_ok=True)
@@ -127,7 +128,7 @@ def build(verbose: bool = False) -> str:
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError("emulation build failed")
-    subprocess.check_call(["g++", "-shared", "-o", OUT_SO, *objs, "-ldl"])
+    subprocess.check_call(["g++", "-shared", "-fsanitize=alignment", "-o", OUT_SO, *objs, "-ldl"])
     open(stamp, "w").write(h.hexdigest())
     return OUT_SO
 
@@ -142,7 +143,7 @@ def build_selftest() -> str:
         return exe
     g = os.path.join(OUT_DIR, "gen", "selftest.emu.cpp")
     open(g, "w").write(f'#line 1 "{src}"\n' + transform(open(src).read()))
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-Wall", "-I", os.path.join(HERE, "shim"), g, os.path.join(HERE, "emu_runtime.cpp"), "-o", exe])
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-Wall", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-I", os.path.join(HERE, "shim"), g, os.path.join(HERE, "emu_runtime.cpp"), "-o", exe])
     return exe
 
 

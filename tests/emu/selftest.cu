@@ -56,6 +56,12 @@ __global__ void k_race(int *out) {
     out[threadIdx.x] = threadIdx.x ? s_v[threadIdx.x - 1] : 0;
 }
 
+// a 128-bit load from an address that is only 4-byte aligned: the GPU raises "misaligned address"
+__global__ void k_misaligned(const int *p, int *out) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(p + 1);
+    out[0] = (int)(v.x + v.y + v.z + v.w);
+}
+
 int main(int argc, char **argv) {
     const char *mode = argc > 1 ? argv[1] : "ok";
     int *d = nullptr;
@@ -68,6 +74,7 @@ int main(int argc, char **argv) {
     }
     if (!strcmp(mode, "deadlock")) { k_deadlock<<<1, 32>>>(d); return 0; }
     if (!strcmp(mode, "divergent")) { k_divergent<<<1, 32>>>(d); return 0; }
+    if (!strcmp(mode, "misaligned")) { k_misaligned<<<1, 1>>>(d, d + 32); return 0; }
     if (!strcmp(mode, "race")) {  // exit code 0 = the hazard stayed hidden, 3 = it produced a wrong value
         k_race<<<1, 64>>>(d);
         int h[64];

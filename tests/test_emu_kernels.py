@@ -68,7 +68,8 @@ def test_emu_detects_out_of_bounds_and_deadlocks():
     import subprocess
     import build_emu
     exe = build_emu.build_selftest()
-    for case, needle in (("oob", "OUT-OF-BOUNDS WRITE"), ("deadlock", "DEADLOCK"), ("divergent", "DIFFERENT collectives"), ("ok", "selftest ok")):
+    for case, needle in (("oob", "OUT-OF-BOUNDS WRITE"), ("deadlock", "DEADLOCK"), ("divergent", "DIFFERENT collectives"), ("misaligned", "misaligned address"),
+                         ("ok", "selftest ok")):
         r = subprocess.run([exe, case], capture_output=True, text=True, timeout=60)
         assert needle in (r.stderr + r.stdout), (case, r.stderr, r.stdout)
         assert (r.returncode == 0) == (case == "ok")
