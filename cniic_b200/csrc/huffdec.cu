@@ -14,6 +14,7 @@
 // Work is 2-3 decoding passes over the payload; the output is identical to the sequential decoder, including its error
 // behaviour: the stream is rejected when it holds fewer than n complete code words (huf.rs:190-204 returns None).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -269,7 +270,10 @@ int cniic_dev_huffman_decode(cniic_ctx *ctx, const uint8_t *payload, size_t len,
         uint32_t changed = 0;
         CU_TRY(ctx, cudaMemcpyAsync(&changed, d_changed.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        if (!changed) break;
+        if (!changed) {
+            if (getenv("CNIIC_DEBUG")) fprintf(stderr, "cniic huffdec: %llu chunks, fixpoint after %llu sweeps\n", nchunks, round + 1);
+            break;
+        }
         if (round > nchunks + 1) return cniic_set_error(ctx, CNIIC_ERR_CUDA, "Huffman decoder did not reach its fixpoint");
     }
     hd_chunk_sums_kernel<<<(unsigned)nchunks, HD_THREADS, 0, ctx->stream>>>(a);
