@@ -537,3 +537,35 @@ def test_hist_delta_counter_spill(ctx):
     okeys, ocnts = O.hist_delta(O.delta(img))
     assert np.array_equal(keys, okeys) and np.array_equal(cnts, ocnts)
     assert int(cnts.sum()) == 512 * 512 and int(cnts.max()) > 200000
+
+
+@pytest.mark.parametrize("kind", ["rgb", "xyrgb"])
+def test_kernel_versions_agree_on_a_shard(ctx, kind, monkeypatch):
+    """One rank's view of a row-sharded run (rows 37..96 of a 160-row image, explicit initial centroids, one iteration):
+    both kernel versions must produce the same partial sums -> centroids, weights and assignment for the shard."""
+    w, h, y0, hl, k = 192, 160, 37, 60, 40
+    img = cb.synth_image_host(w, h, 5, 9)
+    shard = np.ascontiguousarray(img[y0:y0 + hl])
+    rng = np.random.default_rng(1)
+    if kind == "rgb":
+        init = rng.integers(0, 256, size=(k, 3)).astype(np.int32)
+        kw = dict(n_total=w * h, first_index=y0 * w, flags=cb._lib.KMEANS_FORCE_CULL)
+        kid = cb.POINTS_RGB
+    else:
+        init = np.concatenate([rng.integers(0, w, (k, 1)), rng.integers(0, h, (k, 1)), rng.integers(0, 256, (k, 3))], axis=1).astype(np.int32)
+        kw = dict(n_total=w * h, first_index=y0 * w, w=w, h_local=hl, y0=y0)
+        kid = cb.POINTS_XYRGB
+    outs = []
+    for var in (None, "CNIIC_RGB_CULL_V1", "CNIIC_XY_CULL_V1"):
+        monkeypatch.delenv("CNIIC_RGB_CULL_V1", raising=False)
+        monkeypatch.delenv("CNIIC_XY_CULL_V1", raising=False)
+        if var:
+            monkeypatch.setenv(var, "1")
+        s = cb.KMeansSession(ctx, kid, k, shard, w * hl, **kw)
+        s.reset(init)
+        st = s.run(1)
+        outs.append(s.get() + (st.moved_last,))
+        s.close()
+    for o in outs[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(outs[0][:3], o[:3])) and outs[0][3] == o[3]
+    assert int(outs[0][1].sum()) == w * hl  # every pixel of the shard is counted exactly once
