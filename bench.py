@@ -381,7 +381,9 @@ def main():
     # ---- roofline of the dominant kernel (fused assign+accumulate), measured live with CUDA events ----
     pk = peaks()
     a_ms = float(np.mean(assign_ms))
-    kernel = "km_assign_rgb_cull" if D == 3 else "km_assign_xyrgb_cull"
+    # second kernel versions are the default; CNIIC_*_CULL_V1=1 selects the first ones for A/B runs
+    kernel = (("km_assign_rgb_cull" if os.environ.get("CNIIC_RGB_CULL_V1") else "km_assign_rgb_cull2") if D == 3 else
+              ("km_assign_xyrgb_cull" if os.environ.get("CNIIC_XY_CULL_V1") else "km_assign_xyrgb_cull2"))
     if not sess_culled:
         kernel = "km_assign_rgb" if D == 3 else "km_assign_xyrgb"
     if B > 1:
