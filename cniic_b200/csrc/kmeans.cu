@@ -88,6 +88,7 @@ struct KmDev {
     unsigned long long *sums_red;              // local reduced sums the rest of finalize reads
     const uint2 *tile_box;  // per 2048-point tile of the sorted copy: {bytewise min, bytewise max} of the packed colours
     const uint4 *wseg;      // culled D = 3, v2: per 256-point warp segment {box min, box max, sum r | sum g << 16, sum b | count << 16}
+    const unsigned long long *wseg64;  // weighted points: per warp segment {sum r*w, sum g*w, sum b*w, sum w}
     unsigned long long *sums;  // k*(D+1) partial sums + 1 moved counter
     int32_t *cen;              // k*D
     unsigned long long *weights;
@@ -97,6 +98,18 @@ struct KmDev {
 __host__ __device__ inline uint32_t kpad_of(uint32_t k, int G) { return (k + 2 * (G - 1) + G - 1) / G * G; }
 
 __device__ __forceinline__ int sq(int v) { return v * v; }
+
+// 64-bit add into a shared-memory accumulator with two native 32-bit atomics.  atomicAdd on a 64-bit shared word compiles to a
+// compare-and-swap loop (ATOMS.CAST.SPIN.64) that retries under contention -- and colour-sorted points make every thread of a
+// warp hit the same cluster.  Low word first; the add that wraps it carries exactly once into the high word, so the final
+// (high, low) pair is the exact sum whatever the interleaving.
+__device__ __forceinline__ void smem_add64(unsigned long long *p, unsigned long long v) {
+    uint32_t *w = reinterpret_cast<uint32_t *>(p);
+    const uint32_t lo = uint32_t(v), hi = uint32_t(v >> 32);
+    const uint32_t old = atomicAdd(w, lo);
+    const uint32_t carry = (old + lo) < old ? 1u : 0u;
+    if (hi | carry) atomicAdd(w + 1, hi + carry);
+}
 
 // exclusive rank of `flag` among the 256 threads of the block (thread order); *total = number of flags set
 __device__ __forceinline__ uint32_t block_rank256(bool flag, uint32_t *s_warp, uint32_t *total) {
@@ -260,8 +273,8 @@ __device__ __forceinline__ void km_assign_rgb_body(const KmDev d) {
                 if (p < nv) {
                     if (idx[p] != run) {
                         if (run >= 0) {
-                            atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
-                            atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+                            smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
+                            smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
                         }
                         run = idx[p]; ar = ag = ab = aw = 0;
                     }
@@ -270,8 +283,8 @@ __device__ __forceinline__ void km_assign_rgb_body(const KmDev d) {
                 }
             }
             if (run >= 0) {
-                atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
-                atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+                smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
+                smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
             }
         } else {
             uint32_t ar = 0, ag = 0, ab = 0, aw = 0;
@@ -471,8 +484,8 @@ __device__ __forceinline__ void km_assign_rgb_cull_body(const KmDev d) {
                 if (p < nv) {
                     if (idx[p] != run) {
                         if (run >= 0) {
-                            atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
-                            atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+                            smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
+                            smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
                         }
                         run = idx[p]; ar = ag = ab = aw = 0;
                     }
@@ -481,8 +494,8 @@ __device__ __forceinline__ void km_assign_rgb_cull_body(const KmDev d) {
                 }
             }
             if (run >= 0) {
-                atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
-                atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+                smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
+                smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
             }
         } else {
             // fast paths: the thread's 8 points (and often the whole warp's 256) fall into one cluster, because the
@@ -548,27 +561,41 @@ __device__ __forceinline__ void km_assign_rgb_cull_body(const KmDev d) {
 //   * 32-bit point indices (n < 2^31) and a 32-bit moved counter.
 // ------------------------------------------------------------------------------------------------------------
 // per tile: colour box; per warp segment (256 consecutive sorted points): colour box, channel sums, point count
-__global__ void __launch_bounds__(256) km_tile_boxes2(const uint32_t *__restrict__ pts_sorted, uint32_t n, uint2 *boxes, uint4 *wseg) {
+__global__ void __launch_bounds__(256) km_tile_boxes2(const uint32_t *__restrict__ pts_sorted, const uint32_t *__restrict__ wts_sorted, uint32_t n,
+                                                      uint2 *boxes, uint4 *wseg, unsigned long long *wseg64) {
     __shared__ uint32_t s_mn[8], s_mx[8];
     const uint32_t base = blockIdx.x * TILE + threadIdx.x * PX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t mn = 0xffffffffu, mx = 0u, cnt = 0;
     int sr = 0, sg = 0, sb = 0;
+    unsigned long long wr = 0, wg = 0, wb = 0, ww = 0;  // weighted sums (weighted sessions only)
     for (int p = 0; p < PX; p++)
         if (base + p < n) {
             const uint32_t v = pts_sorted[base + p];
             mn = __vminu4(mn, v); mx = __vmaxu4(mx, v);
             sr += v & 0xff; sg += (v >> 8) & 0xff; sb += (v >> 16) & 0xff; cnt++;
+            if (wts_sorted) {
+                const unsigned long long wq = wts_sorted[base + p];
+                wr += (v & 0xff) * wq; wg += ((v >> 8) & 0xff) * wq; wb += ((v >> 16) & 0xff) * wq; ww += wq;
+            }
         }
     for (int o = 16; o > 0; o >>= 1) {
         mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = __vmaxu4(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         sr += __shfl_xor_sync(0xffffffffu, sr, o); sg += __shfl_xor_sync(0xffffffffu, sg, o);
         sb += __shfl_xor_sync(0xffffffffu, sb, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (wts_sorted) {
+            wr += __shfl_xor_sync(0xffffffffu, wr, o); wg += __shfl_xor_sync(0xffffffffu, wg, o);
+            wb += __shfl_xor_sync(0xffffffffu, wb, o); ww += __shfl_xor_sync(0xffffffffu, ww, o);
+        }
     }
     if (lane == 0) {
         s_mn[warp] = mn; s_mx[warp] = mx;
         wseg[blockIdx.x * 8 + warp] = make_uint4(mn & 0xffffffu, mx & 0xffffffu, uint32_t(sr) | (uint32_t(sg) << 16), uint32_t(sb) | (cnt << 16));
+        if (wts_sorted) {
+            unsigned long long *o64 = wseg64 + 4 * (size_t)(blockIdx.x * 8 + warp);
+            o64[0] = wr; o64[1] = wg; o64[2] = wb; o64[3] = ww;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -738,15 +765,25 @@ __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
         }
         // ---- accumulate ----
         if (WEIGHTED) {
+            const int lead_w = __shfl_sync(0xffffffffu, (int)idx[0], 0);  // unconditional: every lane must reach the shuffle
+            const bool warp_uniform_w = __all_sync(0xffffffffu, uniform && (int)idx[0] == lead_w);
             unsigned long long ar = 0, ag = 0, ab = 0, aw = 0;
             int run = -1;
+            if (warp_uniform_w) {
+                // all 256 points of the segment land in one cluster: its precomputed weighted sums, four adds per warp
+                if (lane == 0) {
+                    const unsigned long long *ws = d.wseg64 + 4 * (size_t)(tile * 8 + warp);
+                    smem_add64(&s_acc64[4 * lead_w], ws[0]); smem_add64(&s_acc64[4 * lead_w + 1], ws[1]);
+                    smem_add64(&s_acc64[4 * lead_w + 2], ws[2]); smem_add64(&s_acc64[4 * lead_w + 3], ws[3]);
+                }
+            } else
 #pragma unroll
             for (int p = 0; p < PX; p++) {
                 if (p < nv) {
                     if (idx[p] != run) {
                         if (run >= 0) {
-                            atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
-                            atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+                            smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
+                            smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
                         }
                         run = idx[p]; ar = ag = ab = aw = 0;
                     }
@@ -755,8 +792,8 @@ __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
                 }
             }
             if (run >= 0) {
-                atomicAdd(&s_acc64[4 * run], ar); atomicAdd(&s_acc64[4 * run + 1], ag);
-                atomicAdd(&s_acc64[4 * run + 2], ab); atomicAdd(&s_acc64[4 * run + 3], aw);
+                smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
+                smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
             }
         } else {
             const int lead = __shfl_sync(0xffffffffu, (int)idx[0], 0);  // unconditional: every lane must reach the shuffle
@@ -1890,6 +1927,7 @@ struct cniic_kmeans {
     uint32_t launches = 0, launches_reported = 0;
     uint2 *d_boxes = nullptr;
     uint4 *d_wseg = nullptr;  // culled D = 3, v2: per-warp-segment boxes and sums
+    unsigned long long *d_wseg64 = nullptr;  // ... and weighted sums (weighted sessions)
     bool v2 = false;          // culled D = 3: second kernel version (default)
     uint32_t *d_sorted = nullptr, *d_perm = nullptr, *d_wsorted = nullptr;  // colour-sorted copy (culled D = 3)
     uint16_t *d_assign_orig = nullptr;  // assignment mapped back to original order (filled on demand)
@@ -2057,8 +2095,13 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
         if (km->v2) {
             km->d_wseg = static_cast<uint4 *>(cniic_cache_alloc(ctx, ntiles * 8 * 16));
             if (!km->d_wseg) return fail(CNIIC_ERR_CUDA);
-            km_tile_boxes2<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(km->d_sorted, (uint32_t)n, km->d_boxes, km->d_wseg);
+            if (d_wts) {
+                km->d_wseg64 = static_cast<unsigned long long *>(cniic_cache_alloc(ctx, ntiles * 8 * 32));
+                if (!km->d_wseg64) return fail(CNIIC_ERR_CUDA);
+            }
+            km_tile_boxes2<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(km->d_sorted, km->d_wsorted, (uint32_t)n, km->d_boxes, km->d_wseg, km->d_wseg64);
             dv.wseg = km->d_wseg;
+            dv.wseg64 = km->d_wseg64;
         } else {
             km_tile_boxes<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(km->d_sorted, n, km->d_boxes);
         }
@@ -2586,6 +2629,7 @@ extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
     cniic_cache_free(km->ctx, km->pool);
     cniic_cache_free(km->ctx, km->d_boxes);
     cniic_cache_free(km->ctx, km->d_wseg);
+    cniic_cache_free(km->ctx, km->d_wseg64);
     cniic_cache_free(km->ctx, km->d_sorted);
     cniic_cache_free(km->ctx, km->d_perm);
     cniic_cache_free(km->ctx, km->d_wsorted);
