@@ -1823,20 +1823,32 @@ __global__ void km_init_assign(KmDev d) { km_init_assign_body(d); }
 template <int D> __global__ void km_init_centroids(KmDev d) { km_init_centroids_body<D>(d); }
 template <int D> __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) { km_finalize_body<D>(d, init_mode); }
 
-template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS) km_assign_rgb_batch(const KmDev *__restrict__ batch) { km_assign_rgb_body<WEIGHTED>(batch[blockIdx.y]); }
-template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull_batch(const KmDev *__restrict__ batch) { km_assign_rgb_cull_body<WEIGHTED>(batch[blockIdx.y]); }
-template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull2_batch(const KmDev *__restrict__ batch) { km_assign_rgb_cull2_body<WEIGHTED>(batch[blockIdx.y]); }
-__global__ void __launch_bounds__(THREADS) km_assign_xyrgb_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_body(batch[blockIdx.y]); }
+// A descriptor read from memory carries generic pointers: without help the compiler emits address-space checks around every
+// atomic (and a dead shared-memory compare-and-swap path).  Every pointer of a KmDev points to global memory.
+__device__ __forceinline__ KmDev km_load_desc(const KmDev *__restrict__ batch, unsigned i) {
+    const KmDev d = batch[i];
+#define KM_GLOBAL(p) __builtin_assume(__isGlobal(p))
+    KM_GLOBAL(d.rgb); KM_GLOBAL(d.wts); KM_GLOBAL(d.assign); KM_GLOBAL(d.t_cpk); KM_GLOBAL(d.t_cxy); KM_GLOBAL(d.t_bias); KM_GLOBAL(d.t_id);
+    KM_GLOBAL(d.t_pos); KM_GLOBAL(d.g_cpk); KM_GLOBAL(d.g_cxy); KM_GLOBAL(d.g_nrm); KM_GLOBAL(d.g_ent); KM_GLOBAL(d.sc_list); KM_GLOBAL(d.sc_count);
+    KM_GLOBAL(d.pts_sorted); KM_GLOBAL(d.perm); KM_GLOBAL(d.wts_sorted); KM_GLOBAL(d.tile_box); KM_GLOBAL(d.wseg); KM_GLOBAL(d.wseg64);
+    KM_GLOBAL(d.sums); KM_GLOBAL(d.cen); KM_GLOBAL(d.weights); KM_GLOBAL(d.st); KM_GLOBAL(d.sums_red); KM_GLOBAL(d.sums_other);
+#undef KM_GLOBAL
+    return d;
+}
+template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS) km_assign_rgb_batch(const KmDev *__restrict__ batch) { km_assign_rgb_body<WEIGHTED>(km_load_desc(batch, blockIdx.y)); }
+template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull_batch(const KmDev *__restrict__ batch) { km_assign_rgb_cull_body<WEIGHTED>(km_load_desc(batch, blockIdx.y)); }
+template <bool WEIGHTED> __global__ void __launch_bounds__(THREADS, 4) km_assign_rgb_cull2_batch(const KmDev *__restrict__ batch) { km_assign_rgb_cull2_body<WEIGHTED>(km_load_desc(batch, blockIdx.y)); }
+__global__ void __launch_bounds__(THREADS) km_assign_xyrgb_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_body(km_load_desc(batch, blockIdx.y)); }
 __global__ void __launch_bounds__(THREADS) km_supercull_batch(const KmDev *__restrict__ batch) {
-    const KmDev &d = batch[blockIdx.y];
+    const KmDev d = km_load_desc(batch, blockIdx.y);
     if (blockIdx.x >= d.super_x * d.super_y) return;  // the grid is sized for the largest image of the batch
     km_supercull_body(d);
 }
-__global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_cull_body(batch[blockIdx.y]); }
-__global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull2_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_cull2_body(batch[blockIdx.y]); }
-__global__ void km_init_assign_batch(const KmDev *__restrict__ batch) { km_init_assign_body(batch[blockIdx.y]); }
-template <int D> __global__ void km_init_centroids_batch(const KmDev *__restrict__ batch) { km_init_centroids_body<D>(batch[blockIdx.y]); }
-template <int D> __global__ void __launch_bounds__(1024) km_finalize_batch(const KmDev *__restrict__ batch, int init_mode) { km_finalize_body<D>(batch[blockIdx.x], init_mode); }
+__global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_cull_body(km_load_desc(batch, blockIdx.y)); }
+__global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull2_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_cull2_body(km_load_desc(batch, blockIdx.y)); }
+__global__ void km_init_assign_batch(const KmDev *__restrict__ batch) { km_init_assign_body(km_load_desc(batch, blockIdx.y)); }
+template <int D> __global__ void km_init_centroids_batch(const KmDev *__restrict__ batch) { km_init_centroids_body<D>(km_load_desc(batch, blockIdx.y)); }
+template <int D> __global__ void __launch_bounds__(1024) km_finalize_batch(const KmDev *__restrict__ batch, int init_mode) { km_finalize_body<D>(km_load_desc(batch, blockIdx.x), init_mode); }
 // the states of a batch, gathered into one array for a single device-to-host copy
 __global__ void km_gather_states(const KmDev *__restrict__ batch, uint32_t count, KmState *out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[i] = *batch[i].st;

@@ -209,6 +209,10 @@ template <class T> static inline unsigned __match_any_sync(unsigned mask, T v) {
     return r;
 }
 
+// address-space hints of the device compiler: no-ops here
+#define __builtin_assume(x) ((void)0)
+template <class T> static inline bool __isGlobal(const T *) { return true; }
+
 // ---- scalar intrinsics ------------------------------------------------------------------------------------------------
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
