@@ -8,7 +8,8 @@ The product never loads the emulated library and still has no CPU path (tests/te
 green run here says nothing about performance and does not replace `pytest -m gpu` on a B200.
 
 Sizes: the slow cases (dense 2^24 / 511^3 histogram bins, k = 2048 tables) are skipped unless CNIIC_EMU_FULL=1
-(`CNIIC_EMU_FULL=1 python -m pytest tests/test_emu_kernels.py` takes ~10 minutes).
+(`CNIIC_EMU_FULL=1 python -m pytest tests/test_emu_kernels.py` also runs the BASELINE-size cases of test_gpu_fullsize.py and
+takes ~20 minutes).
 """
 import ctypes
 import os
@@ -50,11 +51,13 @@ def _reexport(module):
             globals()["test_emu_" + name[5:]] = fn
 
 
+import test_gpu_fullsize  # noqa: E402
 import test_gpu_golden  # noqa: E402
 import test_gpu_parity  # noqa: E402
 
 _reexport(test_gpu_parity)
 _reexport(test_gpu_golden)
+_reexport(test_gpu_fullsize)  # BASELINE sizes: CNIIC_EMU_FULL=1 only (minutes per case even on the host)
 
 
 def test_emu_library_is_the_emulated_one(ctx, emu_lib):

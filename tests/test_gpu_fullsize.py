@@ -118,3 +118,29 @@ def test_c5_integer_stages_8192(ctx):
     assert np.array_equal(keys, uk.astype(np.uint32)) and np.array_equal(cnts, uc.astype(np.uint64))
     ck, cc = ctx.hist_rgb(img)
     assert int(cc.sum()) == w * h
+
+
+@pytest.mark.parametrize("expr,w,h,blobs", [("delta", 8192, 8192, 4096), ("hufman", 4096, 4096, 192), ("hilbert(rle)", 4096, 4096, 192),
+                                            ("cluster-colors(256)", 4096, 4096, 192)])
+def test_codecs_fullsize_roundtrip(ctx, expr, w, h, blobs):
+    """Whole codecs at BASELINE sizes: the parallel Huffman decoder (thousands of 64-Kbit chunks), the run-length coder and
+    the fused histogram on tens of millions of symbols.  Lossless codecs must return the image (bench.rs:57-59); for
+    cluster-colors the decoded image must be the recoloured one: <= k colours, and decoding is idempotent under re-encoding."""
+    from cniic_b200 import codecs
+    d = ctx.device_alloc(w * h * 3)
+    cb.synth_image_device(ctx, d, w, h, 0xC0FFEE + 7, blobs)
+    img = np.zeros((h, w, 3), np.uint8)
+    ctx.d2h(img, d)
+    ctx.device_free(d)
+    if expr.startswith("hilbert"):
+        img = (img // 32) * 32  # give the run-length coder runs
+    c = codecs.Codec.from_str(ctx, expr, 3)
+    data = c.encode(img)
+    dec = c.decode(data)
+    assert dec is not None and dec.shape == img.shape
+    if c.is_lossless():
+        assert ctx.sse(img, dec) == 0 and np.array_equal(dec[::97], img[::97])
+    else:
+        keys, cnts = ctx.hist_rgb(dec)
+        assert 1 <= len(keys) <= 256 and int(cnts.sum()) == w * h
+        assert c.decode(data[:len(data) - len(data) // 3]) is None  # a truncated payload is rejected, not mis-decoded
