@@ -172,9 +172,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--batch", type=int, default=C4_BATCH, help="images per step per GPU (workload c4)")
     args = ap.parse_args()
-    if args.workload in ("c5", "fill"):  # HBM-bound stage workloads (single GPU, no collective): bench_stages.py
-        if int(os.environ.get("RANK", 0)) != 0 or args.impl == "reference":
-            if args.impl == "reference" and int(os.environ.get("RANK", 0)) == 0:
+    if args.workload in ("c5", "fill"):  # HBM-bound stage workloads (sharded without any collective): bench_stages.py
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", 0)) == 0:
                 print(json.dumps({"impl": "reference", "unavailable": "stage workloads report their CPU leg as cpu_baseline of the default arm"}))
             return 0
         import bench_stages

@@ -269,6 +269,21 @@ class Context:
         self.check(self._lib.cniic_delta_i16(self.h, _ptr(img), C.c_uint32(w), C.c_uint32(h), _ptr(out)))
         return out
 
+    def delta_range_device(self, d_rgb: int, w: int, h: int, i_begin: int, i_end: int, d_out: int):
+        """DiffStream of curve indices [i_begin, i_end) of a device-resident image into a device buffer (one rank's share)."""
+        self.check(self._lib.cniic_delta_i16_range_device(self.h, C.c_void_p(d_rgb), C.c_uint32(w), C.c_uint32(h),
+                                                          C.c_uint64(i_begin), C.c_uint64(i_end), C.c_void_p(d_out)))
+
+    def hist_delta_range_device(self, d_rgb: int, w: int, h: int, i_begin: int, i_end: int):
+        """Partial histogram (keys ascending, counts) of the delta symbols of curve indices [i_begin, i_end)."""
+        cap = max(1, i_end - i_begin)
+        keys = np.zeros(cap, np.uint32)
+        cnts = np.zeros(cap, np.uint64)
+        u = C.c_size_t(0)
+        self.check(self._lib.cniic_hist_delta_range_device(self.h, C.c_void_p(d_rgb), C.c_uint32(w), C.c_uint32(h), C.c_uint64(i_begin),
+                                                           C.c_uint64(i_end), _ptr(keys), _ptr(cnts), C.c_size_t(cap), C.byref(u)))
+        return keys[:u.value].copy(), cnts[:u.value].copy()
+
     def undelta(self, diff, w, h):
         diff = np.ascontiguousarray(diff, dtype=np.int16)
         out = np.zeros((h, w, 3), np.uint8)

@@ -400,10 +400,12 @@ __global__ void hilbert_xy_kernel(uint32_t w, uint32_t h, bool pow2, uint32_t *o
 // mode 0: gather rgb along the curve; mode 1: delta stream (i16 x 3); mode 2: delta histogram only (fused)
 template <int MODE>
 __global__ void hilbert_stream_kernel(const uint8_t *__restrict__ rgb, uint32_t w, uint32_t h, bool pow2, uint8_t *out_rgb,
-                                      int16_t *out_delta, uint32_t *bins, uint8_t *flags) {
-    const unsigned long long n = (unsigned long long)w * h;
-    const unsigned long long n_round = (n + 31) / 32 * 32;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_round;
+                                      int16_t *out_delta, uint32_t *bins, uint8_t *flags, unsigned long long i_begin, unsigned long long i_end) {
+    // curve indices [i_begin, i_end) (a rank's share of the curve; the whole curve for a single GPU); outputs are
+    // written relative to i_begin.  The predecessor of a warp's first index is recomputed, so a range needs no halo.
+    const unsigned long long n = i_end;
+    const unsigned long long n_round = i_begin + (i_end - i_begin + 31) / 32 * 32;
+    for (unsigned long long i = i_begin + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_round;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const bool valid = i < n;
         uint32_t x = 0, y = 0;
@@ -414,7 +416,7 @@ __global__ void hilbert_stream_kernel(const uint8_t *__restrict__ rgb, uint32_t 
             c0 = p[0]; c1 = p[1]; c2 = p[2];
         }
         if (MODE == 0) {
-            if (valid) { out_rgb[3 * i] = c0; out_rgb[3 * i + 1] = c1; out_rgb[3 * i + 2] = c2; }
+            if (valid) { out_rgb[3 * (i - i_begin)] = c0; out_rgb[3 * (i - i_begin) + 1] = c1; out_rgb[3 * (i - i_begin) + 2] = c2; }
         } else {
             // predecessor along the curve: neighbouring lane, or one extra index map for lane 0
             int p0 = __shfl_up_sync(0xffffffffu, c0, 1), p1 = __shfl_up_sync(0xffffffffu, c1, 1), p2 = __shfl_up_sync(0xffffffffu, c2, 1);
@@ -429,7 +431,7 @@ __global__ void hilbert_stream_kernel(const uint8_t *__restrict__ rgb, uint32_t 
             }
             const int d0 = c0 - p0, d1 = c1 - p1, d2 = c2 - p2;
             if (MODE == 1) {
-                if (valid) { out_delta[3 * i] = d0; out_delta[3 * i + 1] = d1; out_delta[3 * i + 2] = d2; }
+                if (valid) { out_delta[3 * (i - i_begin)] = d0; out_delta[3 * (i - i_begin) + 1] = d1; out_delta[3 * (i - i_begin) + 2] = d2; }
             } else {
                 warp_hist_add(bins, flags, valid ? uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255)) : 0, valid);
             }
@@ -460,17 +462,18 @@ constexpr int CUBE_R = 15, CUBE_S = 2 * CUBE_R + 1, CUBE_N = CUBE_S * CUBE_S * C
 
 template <int MODE>
 __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__restrict__ rgb, uint32_t n, uint8_t *out_rgb,
-                                                           int16_t *out_delta, uint32_t *bins, uint8_t *flags) {
+                                                           int16_t *out_delta, uint32_t *bins, uint8_t *flags, unsigned long long blk_begin,
+                                                           unsigned long long blk_end) {
     extern __shared__ uint32_t s_cube[];  // MODE 2 only: CUBE_N 15-bit counters (+ guard bit), two per word
     __shared__ __align__(16) uint32_t s_px[HT * HT_STRIDE];  // one word per pixel (r | g<<8 | b<<16)
     __shared__ uint32_t s_last[8];
     __shared__ int s_top[5];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned long long nblocks = (unsigned long long)n * n / 4096;
+    const unsigned long long nblocks = blk_end;  // 4096-index blocks [blk_begin, blk_end): a rank's share of the curve; outputs relative to it
     if (MODE == 2) {
         for (int i = tid; i < (CUBE_N + 1) / 2; i += 256) s_cube[i] = 0;
     }
-    for (unsigned long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    for (unsigned long long blk = blk_begin + blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const unsigned long long B = blk * 4096;
         const unsigned long long i0 = B + (unsigned long long)tid * 16;
         // The block's 4096 indices share every base-4 digit above the lowest six: lane 0 of warp 0 folds those levels
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__rest
                 wd[3 * q + 1] = (b >> 8) | (c << 16);
                 wd[3 * q + 2] = (c >> 16) | (e << 8);
             }
-            uint4 *o = reinterpret_cast<uint4 *>(out_rgb + i0 * 3);
+            uint4 *o = reinterpret_cast<uint4 *>(out_rgb + (i0 - blk_begin * 4096) * 3);
             o[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
             o[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
             o[2] = make_uint4(wd[8], wd[9], wd[10], wd[11]);
@@ -595,7 +598,7 @@ __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__rest
                 wd[3 * (j / 2) + 2] = __byte_perm(dg1, da1, 0x7610);  // dg1, db1
                 pa = a1; pg = g1;
             }
-            uint4 *o = reinterpret_cast<uint4 *>(out_delta + i0 * 3);
+            uint4 *o = reinterpret_cast<uint4 *>(out_delta + (i0 - blk_begin * 4096) * 3);
 #pragma unroll
             for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
         } else {
@@ -1144,12 +1147,12 @@ static inline bool tile_path(const void *in, const void *out, uint32_t w, uint32
 
 int cniic_dev_hilbert_gather(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint8_t *d_out) {
     if (tile_path(d_rgb, d_out, w, h)) {
-        hilbert_tile_kernel<0><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, d_out, nullptr, nullptr, nullptr);
+        hilbert_tile_kernel<0><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, d_out, nullptr, nullptr, nullptr, 0ull, (unsigned long long)w * h / 4096);
         ctx->launches++;
         CU_TRY(ctx, cudaGetLastError());
         return CNIIC_OK;
     }
-    hilbert_stream_kernel<0><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), d_out, nullptr, nullptr, nullptr);
+    hilbert_stream_kernel<0><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), d_out, nullptr, nullptr, nullptr, 0ull, (unsigned long long)w * h);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
@@ -1226,18 +1229,25 @@ int cniic_dev_rle_decode(cniic_ctx *ctx, const uint8_t *recs, size_t len, uint32
 }
 
 int cniic_dev_hist_delta_bins(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint32_t **d_bins, size_t *nbins) {
+    return cniic_dev_hist_delta_bins_range(ctx, d_rgb, w, h, 0, (unsigned long long)w * h, d_bins, nbins);
+}
+
+// histogram of the delta symbols of curve indices [i0, i1) only (one rank's share; partial histograms add up)
+int cniic_dev_hist_delta_bins_range(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, unsigned long long i0, unsigned long long i1,
+                                    uint32_t **d_bins, size_t *nbins) {
     uint8_t *flags;
     ST_TRY(hist_space(ctx, 1, d_bins, &flags, nbins));
-    if (tile_path(d_rgb, nullptr, w, h)) {
+    if (i0 >= i1) return CNIIC_OK;
+    if (tile_path(d_rgb, nullptr, w, h) && i0 % 4096 == 0 && i1 % 4096 == 0) {
         const size_t smem = size_t((CUBE_N + 1) / 2) * 4;
         CU_TRY(ctx, cudaFuncSetAttribute(hilbert_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hilbert_tile_kernel<2>, 256, smem));
         if (per_sm < 1) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "delta histogram kernel does not fit an SM");
-        const unsigned grid = (unsigned)std::min<size_t>((size_t)w * h / 4096, (size_t)ctx->sm_count * per_sm);  // persistent: one wave
-        hilbert_tile_kernel<2><<<grid, 256, smem, ctx->stream>>>(d_rgb, w, nullptr, nullptr, *d_bins, flags);
+        const unsigned grid = (unsigned)std::min<size_t>((size_t)((i1 - i0) / 4096), (size_t)ctx->sm_count * per_sm);  // persistent: one wave
+        hilbert_tile_kernel<2><<<grid, 256, smem, ctx->stream>>>(d_rgb, w, nullptr, nullptr, *d_bins, flags, i0 / 4096, i1 / 4096);
     }
-    else hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins, flags);
+    else hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)(i1 - i0)), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins, flags, i0, i1);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
@@ -1462,13 +1472,21 @@ extern "C" int cniic_hilbert_gather_rgb(cniic_ctx *ctx, const uint8_t *rgb, uint
 }
 
 extern "C" int cniic_delta_i16_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, int16_t *d_out) {
+    return cniic_delta_i16_range_device(ctx, d_rgb, w, h, 0, (uint64_t)w * h, d_out);
+}
+
+extern "C" int cniic_delta_i16_range_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint64_t i_begin, uint64_t i_end,
+                                            int16_t *d_out) {
     if (!ctx) return CNIIC_ERR_BAD_ARG;
     ST_TRY(check_dims(ctx, w, h));
-    if ((size_t)w * h == 0) return CNIIC_OK;
+    if (i_begin > i_end || i_end > (uint64_t)w * h) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "curve range outside the image");
+    if (i_begin == i_end) return CNIIC_OK;
     if (!d_rgb || !d_out) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    if (tile_path(d_rgb, d_out, w, h)) hilbert_tile_kernel<1><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, nullptr, d_out, nullptr, nullptr);
-    else hilbert_stream_kernel<1><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, d_out, nullptr, nullptr);
+    if (tile_path(d_rgb, d_out, w, h) && i_begin % 4096 == 0 && i_end % 4096 == 0)
+        hilbert_tile_kernel<1><<<(unsigned)((i_end - i_begin) / 4096), 256, 0, ctx->stream>>>(d_rgb, w, nullptr, d_out, nullptr, nullptr, i_begin / 4096, i_end / 4096);
+    else
+        hilbert_stream_kernel<1><<<grid_for(ctx, (size_t)(i_end - i_begin)), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, d_out, nullptr, nullptr, i_begin, i_end);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
@@ -1520,6 +1538,23 @@ extern "C" int cniic_undelta_rgb(cniic_ctx *ctx, const int16_t *diff, uint32_t w
     CU_TRY(ctx, cudaMemcpyAsync(out_rgb, dout.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CNIIC_OK;
+}
+
+// histogram of the delta symbols of curve indices [i_begin, i_end) of a DEVICE-resident image, (key, count) lists to the host:
+// one rank's partial histogram of a curve-sharded run; the ranks' lists are merged by adding counts of equal keys
+extern "C" int cniic_hist_delta_range_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint64_t i_begin, uint64_t i_end,
+                                             uint32_t *out_keys, uint64_t *out_counts, size_t cap, size_t *out_n) {
+    if (!ctx || !d_rgb || !out_n || (cap && (!out_keys || !out_counts))) return CNIIC_ERR_BAD_ARG;
+    ST_TRY(check_dims(ctx, w, h));
+    if (i_begin > i_end || i_end > (uint64_t)w * h) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "curve range outside the image");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    *out_n = 0;
+    uint32_t *d_bins = nullptr;
+    size_t nbins = 0;
+    int rc = cniic_dev_hist_delta_bins_range(ctx, d_rgb, w, h, i_begin, i_end, &d_bins, &nbins);
+    if (rc == CNIIC_OK) rc = hist_out(ctx, d_bins, nbins, out_keys, out_counts, cap, out_n);
+    cniic_cache_free(ctx, d_bins);
+    return rc;
 }
 
 extern "C" int cniic_hist_delta_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, size_t *out_n) {

@@ -7,6 +7,8 @@
 int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins, size_t nbins, uint32_t **d_keys, unsigned long long **d_counts, size_t *n_unique);
 int cniic_dev_hist_rgb_bins(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t **d_bins);
 int cniic_dev_hist_delta_bins(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint32_t **d_bins, size_t *nbins);
+int cniic_dev_hist_delta_bins_range(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, unsigned long long i0, unsigned long long i1,
+                                    uint32_t **d_bins, size_t *nbins);
 int cniic_dev_recolor(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, const uint32_t *d_keys, const uint16_t *d_assign, size_t n_unique,
                       const int32_t *d_cen_i32, const uint8_t *d_cen_u8, uint32_t *d_lut, uint8_t *d_out);
 int cniic_dev_keys_to_points(cniic_ctx *ctx, const uint32_t *d_keys, const unsigned long long *d_counts, size_t n, uint8_t *d_rgb, uint32_t *d_wts);

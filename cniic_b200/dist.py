@@ -18,6 +18,28 @@ def row_shard(h: int, world: int, rank: int) -> tuple[int, int]:
     return y0, y1 - y0
 
 
+def curve_shard(n: int, world: int, rank: int, align: int = 4096) -> tuple[int, int]:
+    """[i_begin, i_end) of the Hilbert-curve indices owned by `rank` (the integer stages shard the CURVE, not
+    the rows).  Boundaries are multiples of `align` (the tile kernels work on 4096-index blocks), the last rank takes the rest."""
+    blocks = (n + align - 1) // align
+    b0 = rank * blocks // world
+    b1 = (rank + 1) * blocks // world
+    return min(n, b0 * align), min(n, b1 * align)
+
+
+def merge_histograms(parts) -> tuple[np.ndarray, np.ndarray]:
+    """Sum of per-rank partial histograms [(keys ascending, counts), ...] -> (keys ascending, counts) (utils.rs:4-16 over the
+    whole stream: count_freqs is additive over any partition of its input)."""
+    keys = np.concatenate([np.asarray(k, dtype=np.uint32) for k, _ in parts]) if parts else np.zeros(0, np.uint32)
+    cnts = np.concatenate([np.asarray(c, dtype=np.uint64) for _, c in parts]) if parts else np.zeros(0, np.uint64)
+    if len(keys) == 0:
+        return keys, cnts
+    uk, inv = np.unique(keys, return_inverse=True)
+    out = np.zeros(len(uk), np.uint64)
+    np.add.at(out, inv, cnts)
+    return uk.astype(np.uint32), out
+
+
 def init_point_indices(n_total: int, k: int) -> np.ndarray:
     """Global point index of each initial centroid: N-(i+1)*ppc for i < k-1, and 0 for i = k-1 (kmeans.rs:61-108)."""
     ppc = n_total // k

@@ -226,6 +226,14 @@ int cniic_voronoi_fill_device(cniic_ctx *ctx, const uint32_t *d_cxy, const uint8
                               uint32_t h, uint32_t y0, uint32_t h_local, uint8_t *d_out_rgb);
 int cniic_delta_i16_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, int16_t *d_out);
 int cniic_hist_delta_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, size_t *out_n);
+/* Curve-sharded forms (GPU g of G owns curve indices [g*N/G, (g+1)*N/G); every rank holds the image).  The
+ * predecessor of a range's first symbol is recomputed from the image, so no halo is exchanged; d_out receives
+ * 3*(i_end-i_begin) values; partial histograms are merged by adding the counts of equal keys.  Ranges aligned to 4096
+ * indices take the tile kernels on 2^n squares.  (hilbert.rs:34-43, hilbertc.rs:445-477, utils.rs:4-16)                 */
+int cniic_delta_i16_range_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint64_t i_begin, uint64_t i_end,
+                                 int16_t *d_out);
+int cniic_hist_delta_range_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint64_t i_begin, uint64_t i_end,
+                                  uint32_t *out_keys, uint64_t *out_counts, size_t cap, size_t *out_n);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ import time
 import numpy as np
 
 uint8 = np.uint8
+int16 = np.int16
 float64 = np.float64
 
 

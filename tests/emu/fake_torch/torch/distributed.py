@@ -6,7 +6,7 @@ class ReduceOp:
 
 
 def init_process_group(*a, **k):
-    raise RuntimeError("the emulated bench smoke test is single-process")
+    pass  # every "rank" of an emulated run is a lone process: collectives are identities (enough to walk the sharded code paths)
 
 
 def barrier():

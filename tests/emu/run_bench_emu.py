@@ -31,8 +31,7 @@ bench.WORKLOADS = {
     "c4": ("rgb", 64, 32, 16, 4, "emulated c4", "weak"),
 }
 bench.C4_BATCH = 3
-if hasattr(bench_stages, "EMU_SHRINK"):
-    bench_stages.EMU_SHRINK()
+bench_stages.SIZES = {"c5": (256, 256, 64), "fill": (192, 96, 64)}
 if "--batch" not in sys.argv:
     sys.argv += ["--batch", "3"]
 if "--cpu-px" not in sys.argv:

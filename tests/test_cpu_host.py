@@ -188,3 +188,16 @@ def test_bench_roofline_object():
     assert bench.build_roofline(5, 100, 10, 1.0, 1000.0, pk, "x", None, 0.0)["fp32"]["brute_force_kernel"] is None
     import json
     json.dumps(r)
+
+
+def test_curve_shard_and_histogram_merge():
+    from cniic_b200 import dist as cdist
+    for n, world in ((8192 * 8192, 8), (100 * 70, 3), (4096, 4), (1, 2), (0, 3)):
+        edges = [cdist.curve_shard(n, world, r) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+        assert all(e[0] % 4096 == 0 for e in edges)
+    if True:
+        k, c = cdist.merge_histograms([(np.array([1, 5, 9], np.uint32), np.array([2, 3, 4], np.uint64)),
+                                       (np.array([0, 5], np.uint32), np.array([7, 10], np.uint64)), (np.zeros(0, np.uint32), np.zeros(0, np.uint64))])
+        assert k.tolist() == [0, 1, 5, 9] and c.tolist() == [7, 2, 13, 4]

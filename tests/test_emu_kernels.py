@@ -82,6 +82,41 @@ def test_emu_detects_out_of_bounds_and_deadlocks():
     assert subprocess.run([exe, "race"], capture_output=True, env=dict(os.environ, EMU_SCHED="random:1")).returncode == 3
 
 
+@pytest.mark.parametrize("workload", ["c5", "fill"])
+def test_emu_bench_stage_workloads_run(workload):
+    """bench_stages.run() (integer stages, voronoi fill) on the emulated kernels: control flow + JSON contract."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "run_bench_emu.py"), "--workload", workload, "--steps", "2", "--warmup", "1", "--no-cpu"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["metric"] == "Mpix/s" and line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] >= 3
+    rf = line["roofline"]
+    assert rf["bound"] == "hbm" and rf["achieved"] > 0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["gpu_launches"] > 0 and "workload" in line["config"]
+
+
+@pytest.mark.parametrize("workload", ["c5", "fill"])
+def test_emu_bench_stage_workloads_sharded_code_path(workload):
+    """The N > 1 branches of the stage benchmarks (curve / row shards) walked by lone processes that pretend to be ranks 0 and 2 of 3
+    (stand-in torch.distributed: collectives are identities): rank 0 prints the line, the others stay silent."""
+    import json
+    import subprocess
+    for rank in (0, 2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK="0", WORLD_SIZE="3")
+        r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "run_bench_emu.py"), "--workload", workload, "--gpus", "3", "--steps", "2",
+                            "--warmup", "1", "--no-cpu"], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        if rank:
+            assert r.stdout.strip() == ""
+        else:
+            line = json.loads(r.stdout.strip().splitlines()[-1])
+            assert line["n_gpus"] == 3 and line["scaling"] == "strong" and "sharded over 3 GPUs" in line["config"]["workload"]
+            assert line["e2e"]["d2h_bytes_per_step"] > 0
+
+
 @pytest.mark.parametrize("workload", ["c2", "c4", "c3"])
 def test_emu_bench_main_runs_and_keeps_the_json_contract(workload):
     """bench.py's real main() on the emulated kernels (tiny workloads, stand-in torch): control flow + JSON contract."""

@@ -569,3 +569,38 @@ def test_kernel_versions_agree_on_a_shard(ctx, kind, monkeypatch):
     for o in outs[1:]:
         assert all(np.array_equal(a, b) for a, b in zip(outs[0][:3], o[:3])) and outs[0][3] == o[3]
     assert int(outs[0][1].sum()) == w * hl  # every pixel of the shard is counted exactly once
+
+
+# ---- curve-sharded integer stages: ranges of the Hilbert curve processed separately add up to the whole ----
+@pytest.mark.parametrize("w,h,world", [(128, 128, 2), (128, 128, 3), (256, 256, 8), (100, 70, 3), (64, 64, 5)])
+def test_curve_sharded_delta_and_histogram(ctx, w, h, world):
+    from cniic_b200 import dist as cdist
+    img = cb.synth_image_host(w, h, 23, 6)
+    n = w * h
+    d_img = ctx.device_alloc(n * 3)
+    ctx.h2d(d_img, img)
+    d_out = ctx.device_alloc(n * 6)
+    parts, covered = [], 0
+    whole = np.zeros((n, 3), np.int16)
+    for r in range(world):
+        i0, i1 = cdist.curve_shard(n, world, r)
+        assert i0 == covered and i1 >= i0
+        covered = i1
+        if i1 > i0:
+            ctx.delta_range_device(d_img, w, h, i0, i1, d_out)  # written relative to i0
+            piece = np.zeros((i1 - i0, 3), np.int16)
+            ctx.d2h(piece, d_out)
+            whole[i0:i1] = piece
+        parts.append(ctx.hist_delta_range_device(d_img, w, h, i0, i1))
+    assert covered == n
+    assert np.array_equal(whole, O.delta(img))
+    keys, cnts = cdist.merge_histograms(parts)
+    okeys, ocnts = O.hist_delta(O.delta(img))
+    assert np.array_equal(keys, okeys) and np.array_equal(cnts, ocnts)
+    # unaligned ranges fall back to the per-index kernel and still agree
+    i0, i1 = 5, min(n, 4096 + 77)
+    ctx.delta_range_device(d_img, w, h, i0, i1, d_out)
+    piece = np.zeros((i1 - i0, 3), np.int16)
+    ctx.d2h(piece, d_out)
+    assert np.array_equal(piece, O.delta(img)[i0:i1])
+    ctx.device_free(d_img); ctx.device_free(d_out)
