@@ -20,4 +20,12 @@ ncu --set full --clock-control none --import-source on -k regex:km_assign_rgb_ba
     python bench.py --workload c4 --steps 1 --warmup 1 --no-cpu > gpurun_out/r2_prof_c4.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"hd_sync_kernel|hd_write_kernel|rle_emit_kernel" -c 6 -o gpurun_out/r2_prof_codecs \
     python tools/bench_codecs.py > gpurun_out/r2_prof_codecs.log 2>&1
+for wl in c5 fill; do
+  python bench.py --workload $wl --steps 10 --warmup 3 > gpurun_out/r2_bench_$wl.json 2> gpurun_out/r2_bench_$wl.err
+done
+# A/B of the kernel versions and of the sort width on the headline workload
+CNIIC_RGB_CULL_V1=1 python bench.py --workload c2 --steps 10 --warmup 3 --no-cpu > gpurun_out/r2_bench_c2_v1.json 2>&1
+CNIIC_SORT_BITS=16 python bench.py --workload c2 --steps 10 --warmup 3 --no-cpu > gpurun_out/r2_bench_c2_sort16.json 2>&1
+CNIIC_XY_CULL_V1=1 python bench.py --workload c3 --steps 10 --warmup 3 --no-cpu > gpurun_out/r2_bench_c3_v1.json 2>&1
 ls -la gpurun_out | tail -30
+# later, on 2 GPUs (gpurun --gpus 2): pytest tests/test_gpu_dist.py; torchrun ... bench.py --gpus 2 for c2, c3, c4, c5, fill

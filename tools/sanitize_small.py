@@ -35,5 +35,10 @@ px = np.repeat(np.arange(24), fib); np.random.default_rng(0).shuffle(px)
 deep = np.stack([px, px * 3 % 256, px * 7 % 256], 1).astype(np.uint8)[:256 * (len(px) // 256)].reshape(-1, 256, 3)
 for e in ("hufman", "delta", "hilbert(rle)"):
     c = codecs.Codec.from_str(ctx, e); assert np.array_equal(c.decode(c.encode(deep)), deep)
+# curve-sharded stages: three ranges of a 128x128 image (aligned -> tile kernels) and one unaligned range
+d_img = ctx.device_alloc(128 * 128 * 3); ctx.h2d(d_img, sq); d_o = ctx.device_alloc(128 * 128 * 6)
+for i0, i1 in ((0, 4096), (4096, 12288), (12288, 16384), (5, 4173)):
+    ctx.delta_range_device(d_img, 128, 128, i0, i1, d_o); ctx.hist_delta_range_device(d_img, 128, 128, i0, i1)
+ctx.device_free(d_img); ctx.device_free(d_o)
 ctx.sse(img, img[::-1].copy())
 print("sanitize target done")
