@@ -89,7 +89,11 @@ def transform(text: str) -> str:
     return rewrite_launches(text)
 
 
-def build(verbose: bool = False) -> str:
+def build(verbose: bool = False, asan: bool | None = None) -> str:
+    """asan (default: environment CNIIC_EMU_ASAN): AddressSanitizer build, loadable only into a process started with
+    LD_PRELOAD=libasan (tests/emu/run_asan.sh); it also catches out-of-bounds READS of device blocks."""
+    if asan is None:
+        asan = bool(os.environ.get("CNIIC_EMU_ASAN"))
     os.makedirs(OUT_DIR, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     deps = srcs + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(CSRC, "*.h"))) + [
@@ -98,14 +102,17 @@ def build(verbose: bool = False) -> str:
     h = hashlib.sha256()
     for p in deps:
         h.update(open(p, "rb").read())
-    stamp = os.path.join(OUT_DIR, "stamp")
-    if os.path.exists(OUT_SO) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
-        return OUT_SO
+    out_so = OUT_SO[:-3] + "_asan.so" if asan else OUT_SO
+    stamp = os.path.join(OUT_DIR, "stamp_asan" if asan else "stamp")
+    if os.path.exists(out_so) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
+        return out_so
     objs, procs = [], []
     # -fsanitize=alignment: the GPU faults on a misaligned 64/128-bit access, x86 would not notice -- let UBSan stand in
     flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-fno-strict-aliasing", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-unused-variable",
              "-Wno-sign-compare", "-I", os.path.join(HERE, "shim")]
-    gen_dir = os.path.join(OUT_DIR, "gen")
+    if asan:
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer", "-DEMU_ASAN"]
+    gen_dir = os.path.join(OUT_DIR, "gen_asan" if asan else "gen")
     os.makedirs(gen_dir, exist_ok=True)
     # headers are transformed too (common.cuh holds the inline asm); they keep their names so the #includes resolve
     for p in glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")):
@@ -128,9 +135,9 @@ def build(verbose: bool = False) -> str:
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError("emulation build failed")
-    subprocess.check_call(["g++", "-shared", "-fsanitize=alignment", "-o", OUT_SO, *objs, "-ldl"])
+    subprocess.check_call(["g++", "-shared", "-fsanitize=alignment", *(["-fsanitize=address"] if asan else []), "-o", out_so, *objs, "-ldl"])
     open(stamp, "w").write(h.hexdigest())
-    return OUT_SO
+    return out_so
 
 
 def build_selftest() -> str:

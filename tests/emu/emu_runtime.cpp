@@ -258,6 +258,26 @@ void check_canary(void *user, const Alloc &a) {
         }
 }
 
+#ifdef EMU_ASAN
+// AddressSanitizer build (tests/emu/run_asan.sh): blocks carry no padding of ours, so ASan's own red zones sit right behind the
+// last byte and catch out-of-bounds READS as well (the GPU may fault on them, or silently read a neighbour's data)
+cudaError_t alloc_common(void **p, size_t bytes, bool host) {
+    void *raw = nullptr;
+    if (posix_memalign(&raw, 256, bytes ? bytes : 1)) return cudaErrorMemoryAllocation;
+    memset(raw, host ? 0x00 : 0xCB, bytes);
+    *p = raw;
+    g_allocs[*p] = Alloc{bytes, host};
+    return cudaSuccess;
+}
+cudaError_t free_common(void *p) {
+    if (!p) return cudaSuccess;
+    g_allocs.erase(p);
+    free(p);
+    return cudaSuccess;
+}
+#define EMU_NO_CANARY 1
+#endif
+#ifndef EMU_NO_CANARY
 cudaError_t alloc_common(void **p, size_t bytes, bool host) {
     unsigned char *raw = nullptr;
     if (posix_memalign(reinterpret_cast<void **>(&raw), 256, bytes + 256 + CANARY)) return cudaErrorMemoryAllocation;
@@ -286,6 +306,7 @@ struct AtExit {
         for (auto &kv : g_allocs) check_canary(kv.first, kv.second);
     }
 } g_at_exit;
+#endif
 
 }  // namespace
 
