@@ -372,7 +372,11 @@ void launch(const LaunchCfg &cfg, const std::function<void()> &body, const char 
     }
     M.body = &body;
     M.kernel = name;
+#ifdef EMU_ASAN
+    M.smem = std::vector<unsigned char>(cfg.smem ? cfg.smem : 1);  // exact size, fresh block: ASan sees the first byte past the dynamic shared memory
+#else
     M.smem.resize(cfg.smem + 64);
+#endif
     for (unsigned z = 0; z < cfg.grid.z; z++)
         for (unsigned y = 0; y < cfg.grid.y; y++)
             for (unsigned x = 0; x < cfg.grid.x; x++) run_cta(cfg, Idx{x, y, z});

@@ -140,3 +140,10 @@ def test_emu_bench_main_runs_and_keeps_the_json_contract(workload):
     assert "workload" in line["config"]
     if workload == "c4":
         assert rf["kernel"].endswith("_batch") and line["config"]["images_per_step_per_gpu"] == 3 and e["api"] == "cniic_kmeans_rgb_batch"
+
+
+def test_emu_graft_entry_smoke_runs(ctx):
+    """__graft_entry__.smoke() (what the driver runs on the GPU box before the bench) walks on the emulated kernels too."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import __graft_entry__ as g
+    g.smoke()
