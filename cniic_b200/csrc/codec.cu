@@ -183,7 +183,8 @@ bool huf_deserialize(Source &src, size_t sym_size, DecTrie *T) {
 
 // huf.rs:187-206: the payload after the trie is decoded on the GPU (huffdec.cu: self-synchronising parallel decoder with the
 // sequential decoder's results and error behaviour).  val_off = offset of the symbol bytes inside a leaf's serialised value.
-int huf_decode_device(cniic_ctx *ctx, const Source &src, const DecTrie &T, size_t val_off, int sym_bytes, size_t n, uint8_t *d_out) {
+int huf_decode_device(cniic_ctx *ctx, const Source &src, const DecTrie &T, size_t val_off, int sym_bytes, size_t n, uint8_t *d_out,
+                      size_t *decoded = nullptr) {
     const size_t nn = T.nodes.size();
     std::vector<int32_t> child(2 * nn);
     std::vector<uint8_t> leaf(8 * nn, 0);
@@ -192,7 +193,7 @@ int huf_decode_device(cniic_ctx *ctx, const Source &src, const DecTrie &T, size_
         child[2 * i + 1] = T.nodes[i].right;
         if (T.nodes[i].left < 0) memcpy(&leaf[8 * i], T.nodes[i].val + val_off, (size_t)sym_bytes);
     }
-    return cniic_dev_huffman_decode(ctx, src.p + src.pos, src.len - src.pos, child.data(), leaf.data(), nn, sym_bytes, n, d_out);
+    return cniic_dev_huffman_decode(ctx, src.p + src.pos, src.len - src.pos, child.data(), leaf.data(), nn, sym_bytes, n, d_out, decoded);
 }
 
 int finish(cniic_ctx *ctx, const Sink &s, uint8_t *out, size_t cap, size_t *out_len) {
@@ -397,8 +398,13 @@ extern "C" int cniic_codec_decode(cniic_ctx *ctx, const char *codec, const uint8
         DevBuf d_diff(ctx), d_img(ctx);
         CU_TRY(ctx, d_diff.alloc(n * 6));
         CU_TRY(ctx, d_img.alloc(n * 3));
-        ST_TRY(huf_decode_device(ctx, src, T, 0, 6, n, d_diff.as<uint8_t>()));
+        // hilbertc.rs:425-428: the colour stream is zipped with the curve over a zero image -- a payload that ends early paints the
+        // pixels it reaches and leaves the rest zero (Hufman::decode, in contrast, returns None: hufc.rs:24-36)
+        size_t got = 0;
+        ST_TRY(huf_decode_device(ctx, src, T, 0, 6, n, d_diff.as<uint8_t>(), &got));
+        if (got < n) CU_TRY(ctx, cudaMemsetAsync(d_diff.as<uint8_t>() + got * 6, 0, (n - got) * 6, ctx->stream));
         ST_TRY(cniic_dev_undelta(ctx, d_diff.as<int16_t>(), *w, *h, d_img.as<uint8_t>()));
+        if (got < n) ST_TRY(cniic_dev_zero_curve_tail(ctx, *w, *h, got, d_img.as<uint8_t>()));
         CU_TRY(ctx, cudaMemcpyAsync(out_rgb, d_img.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         return CNIIC_OK;

@@ -203,7 +203,8 @@ __global__ void hd_fill_kernel(uint8_t *out, unsigned long long n, int sym_bytes
 }  // namespace
 
 int cniic_dev_huffman_decode(cniic_ctx *ctx, const uint8_t *payload, size_t len, const int32_t *child, const uint8_t *leaf_val, size_t nn,
-                             int sym_bytes, size_t n, uint8_t *d_out) {
+                             int sym_bytes, size_t n, uint8_t *d_out, size_t *decoded) {
+    if (decoded) *decoded = n;
     if (n == 0) return CNIIC_OK;
     if (nn == 0 || nn >= (size_t(1) << 28) || (sym_bytes != 3 && sym_bytes != 6)) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "bad Huffman trie");
     uint32_t launched = 0;
@@ -216,7 +217,10 @@ int cniic_dev_huffman_decode(cniic_ctx *ctx, const uint8_t *payload, size_t len,
         return CNIIC_OK;
     }
     const unsigned long long end_bit = (unsigned long long)len * 8;
-    if (end_bit == 0) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated Huffman payload");
+    if (end_bit == 0) {
+        if (decoded) { *decoded = 0; return CNIIC_OK; }
+        return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated Huffman payload");
+    }
     // prefix table (same construction as the sequential decoder's): node reached after <= HD_LUT_BITS bits
     std::vector<uint32_t> lut(size_t(1) << HD_LUT_BITS);
     for (uint32_t pre = 0; pre < (1u << HD_LUT_BITS); pre++) {
@@ -284,7 +288,11 @@ int cniic_dev_huffman_decode(cniic_ctx *ctx, const uint8_t *payload, size_t len,
     CU_TRY(ctx, cudaMemcpyAsync(&total, a.chunk_off + nchunks, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->launches += launched;
-    if (total < n) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated Huffman payload (%llu of %zu symbols)", total, n);
+    if (total < n) {
+        if (!decoded) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated Huffman payload (%llu of %zu symbols)", total, n);
+        *decoded = (size_t)total;  // the caller's consumer is zipped with the symbol iterator and simply stops (hilbertc.rs:425-428)
+        if (total == 0) return CNIIC_OK;
+    }
     hd_write_kernel<<<(unsigned)nchunks, HD_THREADS, 0, ctx->stream>>>(a);
     ctx->launches += 1;
     CU_TRY(ctx, cudaGetLastError());

@@ -1008,7 +1008,9 @@ __global__ void __launch_bounds__(256) rle_starts_kernel(const uint32_t *__restr
     if (r < nrec) {
         const unsigned long long st = blk_off[blockIdx.x] + (inc - c);
         start[r] = st;
-        if (st < n && bad[r]) atomicOr(err, 1u);  // the sequential decoder reads record r only while pixels are missing
+        // the sequential decoder reads record r only while pixels are missing; a record it reads must be well formed and must
+        // not have count 0 (hilbertc.rs:325 assert!(self.count > 0))
+        if (st < n && (bad[r] || c == 0)) atomicOr(err, 1u);
     }
 }
 
@@ -1034,10 +1036,24 @@ __global__ void __launch_bounds__(256) rle_scan_u64_kernel(const uint32_t *__res
     if (threadIdx.x == 0) out[nb] = s_carry;
 }
 
+__global__ void zero_curve_tail_kernel(uint32_t w, uint32_t h, bool pow2, unsigned long long from, uint8_t *out) {
+    const unsigned long long n = (unsigned long long)w * h;
+    for (unsigned long long i = from + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t x, y;
+        hilbert_d2xy(w, h, pow2, i, &x, &y);
+        uint8_t *o = out + ((size_t)y * w + x) * 3;
+        o[0] = 0; o[1] = 0; o[2] = 0;
+    }
+}
+
 __global__ void rle_paint_kernel(const uint8_t *__restrict__ recs, const unsigned long long *__restrict__ start, uint32_t nrec, uint32_t w, uint32_t h,
-                                 bool pow2, uint8_t *out) {
+                                 bool pow2, unsigned long long total, uint8_t *out) {
     const unsigned long long n = (unsigned long long)w * h;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t x, y;
+        hilbert_d2xy(w, h, pow2, i, &x, &y);
+        uint8_t *o = out + ((size_t)y * w + x) * 3;
+        if (i >= total) { o[0] = 0; o[1] = 0; o[2] = 0; continue; }  // the records ran out cleanly: ImageBuffer::new leaves zeros (hilbertc.rs:57)
         // last record whose start is <= i (records with count 0 share their start with the next one and are skipped)
         uint32_t lo = 0, hi = nrec;
         while (hi - lo > 1) {
@@ -1046,9 +1062,6 @@ __global__ void rle_paint_kernel(const uint8_t *__restrict__ recs, const unsigne
             else hi = mid;
         }
         const uint8_t *rec = recs + 12 * (size_t)lo + 9;
-        uint32_t x, y;
-        hilbert_d2xy(w, h, pow2, i, &x, &y);
-        uint8_t *o = out + ((size_t)y * w + x) * 3;
         o[0] = rec[0]; o[1] = rec[1]; o[2] = rec[2];
     }
 }
@@ -1158,6 +1171,15 @@ int cniic_dev_hilbert_gather(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, u
     return CNIIC_OK;
 }
 
+int cniic_dev_zero_curve_tail(cniic_ctx *ctx, uint32_t w, uint32_t h, unsigned long long from, uint8_t *d_img) {
+    const unsigned long long n = (unsigned long long)w * h;
+    if (from >= n) return CNIIC_OK;
+    zero_curve_tail_kernel<<<grid_for(ctx, (size_t)(n - from)), 256, 0, ctx->stream>>>(w, h, is_pow2_square(w, h), from, d_img);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
 // hilbertc.rs:26-38 + 99-196: run-length records of the linearised image `d_lin` (n pixels, device) appended to *out
 int cniic_dev_rle_encode(cniic_ctx *ctx, const uint8_t *d_lin, size_t n, std::vector<uint8_t> *out) {
     if (n == 0) return CNIIC_OK;
@@ -1188,12 +1210,19 @@ int cniic_dev_rle_encode(cniic_ctx *ctx, const uint8_t *d_lin, size_t n, std::ve
 }
 
 // hilbertc.rs:55-79 + 304-333: `recs` = HOST bytes behind the dimensions; paints the w x h image d_out (device).
-// CNIIC_ERR_DECODE when the records run out, or a record that is needed is malformed, before all pixels are covered.
+// Reference semantics: the decoder iterator is zipped with the curve over a zero-initialised image.  If the bytes end exactly at
+// a record boundary the iterator just ends and the remaining pixels STAY ZERO (decode still returns the image); a record that is
+// read but has count 0, or whose colour is truncated / malformed, makes the reference panic -> CNIIC_ERR_DECODE here.
 int cniic_dev_rle_decode(cniic_ctx *ctx, const uint8_t *recs, size_t len, uint32_t w, uint32_t h, uint8_t *d_out) {
     const unsigned long long n = (unsigned long long)w * h;
     if (n == 0) return CNIIC_OK;
-    const size_t nrec_all = len / 12;  // a trailing partial record can only matter if pixels are still missing: truncated either way
-    if (nrec_all == 0) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated RLE stream");
+    const size_t nrec_all = len / 12;
+    const bool ragged = len % 12 != 0;  // bytes of an incomplete record behind the last complete one
+    if (nrec_all == 0) {
+        if (ragged) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated RLE record");
+        CU_TRY(ctx, cudaMemsetAsync(d_out, 0, n * 3, ctx->stream));  // no record at all: the image stays zero
+        return CNIIC_OK;
+    }
     // records behind the first n can never be read (every count that matters is >= 0; n records of count >= 1 suffice only if
     // all are non-zero, so keep up to 2^31 - 1 and let the scan decide)
     const uint32_t nrec = (uint32_t)std::min<size_t>(nrec_all, (size_t(1) << 31) - 1);
@@ -1220,8 +1249,10 @@ int cniic_dev_rle_decode(cniic_ctx *ctx, const uint8_t *recs, size_t len, uint32
     CU_TRY(ctx, cudaMemcpyAsync(&total, d_boff.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (err || total < n) return cniic_set_error(ctx, CNIIC_ERR_DECODE, err ? "bad RLE record" : "truncated RLE stream");
-    rle_paint_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(d_recs.as<uint8_t>(), d_start.as<unsigned long long>(), nrec, w, h, is_pow2_square(w, h), d_out);
+    if (err) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "malformed or zero-count RLE record (the reference panics)");
+    if (total < n && ragged) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "truncated RLE record (the reference panics)");
+    rle_paint_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(d_recs.as<uint8_t>(), d_start.as<unsigned long long>(), nrec, w, h, is_pow2_square(w, h),
+                                                                std::min<unsigned long long>(total, n), d_out);
     ctx->launches += 1;
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));

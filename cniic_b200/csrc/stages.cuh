@@ -22,9 +22,13 @@ int cniic_dev_huffman_pack(cniic_ctx *ctx, int src_kind, const void *d_src, size
 // Parallel Huffman decoding (huffdec.cu; semantics of huf.rs:187-206): `payload` = HOST bytes, MSB-first bit string; trie as
 // child[2*node] / child[2*node+1] (left = bit 0, right = bit 1; left < 0 marks a leaf), leaf_val = 8 bytes per node (the first
 // sym_bytes are the symbol: 3 = colour bytes, 6 = [i16;3] little endian), node 0 = root.  Writes n * sym_bytes bytes to the
-// DEVICE buffer d_out; CNIIC_ERR_DECODE when the payload holds fewer than n complete code words.
+// DEVICE buffer d_out.  decoded == nullptr: CNIIC_ERR_DECODE when the payload holds fewer than n complete code words (hufc.rs:19-40
+// returns None); decoded != nullptr: the first *decoded <= n symbols are written and the call succeeds (hilbertc.rs:417-431 zips the
+// symbol iterator with the curve, a short payload just ends it).
 int cniic_dev_huffman_decode(cniic_ctx *ctx, const uint8_t *payload, size_t len, const int32_t *child, const uint8_t *leaf_val, size_t nn,
-                             int sym_bytes, size_t n, uint8_t *d_out);
+                             int sym_bytes, size_t n, uint8_t *d_out, size_t *decoded);
+// zero the pixels of curve indices [from, w*h) of a device image (pixels a short stream never reached: ImageBuffer::new is all zero)
+int cniic_dev_zero_curve_tail(cniic_ctx *ctx, uint32_t w, uint32_t h, unsigned long long from, uint8_t *d_img);
 // exact run-length coding along the Hilbert stream (hilbertc.rs:99-196 / 304-333), 12-byte records; see stages.cu
 int cniic_dev_rle_encode(cniic_ctx *ctx, const uint8_t *d_lin, size_t n, std::vector<uint8_t> *out);
 int cniic_dev_rle_decode(cniic_ctx *ctx, const uint8_t *recs, size_t len, uint32_t w, uint32_t h, uint8_t *d_out);

@@ -203,7 +203,13 @@ int cniic_sse_rgb(cniic_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n_p
  * encode: returns CNIIC_ERR_BUFFER_TOO_SMALL with *out_len = required size when cap is too small.               */
 int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8_t *rgb, uint32_t w, uint32_t h, uint8_t *out,
                        size_t cap, size_t *out_len);
-/* decode: *w,*h receive the dimensions; out_rgb must hold cap_pixels pixels (call with out_rgb NULL to query dims). */
+/* decode: *w,*h receive the dimensions; out_rgb must hold cap_pixels pixels (call with out_rgb NULL to query dims).
+ * Short or damaged streams follow the reference decoder of each codec: hufman / cluster-colors return CNIIC_ERR_DECODE
+ * when code words are missing (hufc.rs:24-36 -> None); delta and hilbert(rle) zip their symbol iterator with the curve
+ * over a zero image (hilbertc.rs:55-79, 417-431), so a payload that simply ENDS (for RLE: at a record boundary) gives the
+ * pixels it reached, zeros elsewhere, and CNIIC_OK; wherever the reference would panic (bad trie: .unwrap(); RLE record
+ * with count 0 or a truncated colour: assert! / .unwrap()) the call returns CNIIC_ERR_DECODE -- nothing unwinds across
+ * the FFI.  Bytes behind the last needed symbol are ignored, as in the reference.                                       */
 int cniic_codec_decode(cniic_ctx *ctx, const char *codec, const uint8_t *data, size_t len, uint32_t *w, uint32_t *h,
                        uint8_t *out_rgb, size_t cap_pixels);
 /* Codec::name() (clusterc.rs:59-61,191-193; hilbertc.rs:433-435): writes a NUL-terminated name                  */

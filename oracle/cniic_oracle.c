@@ -1134,19 +1134,29 @@ static int32_t deser_trie(rdr *r, dtrie *T, size_t sym_size) { /* huf.rs:330-350
 }
 
 /* decode nsyms symbols (huf.rs:187-206 trie walk over MSB-first bits); returns 0 ok */
-static int huf_decode_n(rdr *r, size_t sym_size, size_t nsyms, uint8_t *out_vals) {
+static int huf_decode_n_partial(rdr *r, size_t sym_size, size_t nsyms, uint8_t *out_vals, size_t *decoded) {
     dtrie T = {NULL, 0, 0};
     int32_t root = deser_trie(r, &T, sym_size);
     if (root < 0) {
         free(T.nodes);
         return 1;
     }
+    if (sym_size == 11) /* ser.rs:210-214: Rgb = a serialised slice that must hold exactly 3 elements (vec.try_into().ok()?); the
+                           trie is deserialised as a whole (huf.rs:330-350), so ANY leaf with another length fails the decode */
+        for (size_t i = 0; i < T.nn; i++)
+            if (T.nodes[i].left < 0 && (T.nodes[i].val[0] != 3 || T.nodes[i].val[1] | T.nodes[i].val[2] | T.nodes[i].val[3] |
+                                                                      T.nodes[i].val[4] | T.nodes[i].val[5] | T.nodes[i].val[6] | T.nodes[i].val[7])) {
+                free(T.nodes);
+                return 1;
+            }
     size_t bitpos = r->pos * 8, bitend = r->len * 8;
+    if (decoded) *decoded = nsyms;
     for (size_t i = 0; i < nsyms; i++) {
         int32_t nd = root;
         while (T.nodes[nd].left >= 0) {
             if (bitpos >= bitend) {
                 free(T.nodes);
+                if (decoded) { *decoded = i; return 0; } /* the symbol iterator just ends (huf.rs lookup -> None) */
                 return 2;
             }
             int bit = (r->buf[bitpos >> 3] >> (7 - (bitpos & 7))) & 1;
@@ -1157,6 +1167,10 @@ static int huf_decode_n(rdr *r, size_t sym_size, size_t nsyms, uint8_t *out_vals
     }
     free(T.nodes);
     return 0;
+}
+
+static int huf_decode_n(rdr *r, size_t sym_size, size_t nsyms, uint8_t *out_vals) {
+    return huf_decode_n_partial(r, sym_size, nsyms, out_vals, NULL);
 }
 
 int oracle_decode_hufman(const uint8_t *buf, size_t len, uint32_t *w, uint32_t *h, uint8_t *out_rgb, size_t cap_px) {
@@ -1225,13 +1239,23 @@ int oracle_decode_delta(const uint8_t *buf, size_t len, uint32_t *w, uint32_t *h
     size_t n = (size_t)*w * *h;
     if (n > cap_px) return 3;
     if (n == 0) return 0;
-    uint8_t *vals = (uint8_t *)malloc(n * 6);
-    int rc = huf_decode_n(&r, 6, n, vals);
+    /* hilbertc.rs:417-431: decode_all(reader).unwrap() -- a bad trie panics (reported as failure); the colour stream is then
+       ZIPPED with the curve over a zero-initialised image, so a payload that ends early leaves the remaining pixels ZERO and
+       decode still returns Some(img). */
+    uint8_t *vals = (uint8_t *)calloc(n, 6);
+    size_t got = 0;
+    int rc = huf_decode_n_partial(&r, 6, n, vals, &got);
     if (rc == 0) {
         int16_t *diff = (int16_t *)malloc(n * 3 * sizeof(int16_t));
         for (size_t i = 0; i < 3 * n; i++) diff[i] = (int16_t)((uint16_t)vals[2 * i] | ((uint16_t)vals[2 * i + 1] << 8));
         oracle_undelta(diff, *w, *h, out_rgb);
         free(diff);
+        if (got < n) {
+            uint32_t *xy = (uint32_t *)malloc(n * 2 * sizeof(uint32_t));
+            oracle_hilbert_xy(*w, *h, xy);
+            for (size_t i = got; i < n; i++) memset(out_rgb + 3 * ((size_t)xy[2 * i + 1] * *w + xy[2 * i]), 0, 3);
+            free(xy);
+        }
     }
     free(vals);
     return rc;
@@ -1329,10 +1353,17 @@ int oracle_decode_hilbert_rle(const uint8_t *buf, size_t len, uint32_t *w, uint3
     oracle_hilbert_xy(*w, *h, xy);
     size_t i = 0;
     int rc = 0;
+    /* hilbertc.rs:55-79 + 322-333: the image starts all zero (ImageBuffer::new); the RleDecoder iterator is zipped with the curve.
+       - the byte stream ends exactly where a record would start: the iterator ends, zip stops, the rest of the image STAYS ZERO
+         and decode still returns Some(img)  (RepCount::deserialize(..)? -> None ends the iterator, not the decode);
+       - a record with count 0: assert!(self.count > 0) panics;  a truncated / malformed colour: .unwrap() panics.
+       Panics are reported as failures here (rc 2), like the C ABI does (no unwinding across FFI). */
+    memset(out_rgb, 0, n * 3);
     while (i < n) {
         uint8_t cnt, c[3];
         uint64_t l;
-        if (!rd_byte(&r, &cnt) || !rd_u64(&r, &l) || l != 3 || !rd_byte(&r, &c[0]) || !rd_byte(&r, &c[1]) || !rd_byte(&r, &c[2])) {
+        if (!rd_byte(&r, &cnt)) break; /* clean end of the stream: partial image */
+        if (cnt == 0 || !rd_u64(&r, &l) || l != 3 || !rd_byte(&r, &c[0]) || !rd_byte(&r, &c[1]) || !rd_byte(&r, &c[2])) {
             rc = 2;
             break;
         }

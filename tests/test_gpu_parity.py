@@ -604,3 +604,36 @@ def test_curve_sharded_delta_and_histogram(ctx, w, h, world):
     ctx.d2h(piece, d_out)
     assert np.array_equal(piece, O.delta(img)[i0:i1])
     ctx.device_free(d_img); ctx.device_free(d_out)
+
+
+def test_truncated_streams_follow_the_reference_decoders(ctx):
+    """What the reference does with a short stream differs per codec (SURVEY 8b error behaviour): Hufman::decode returns None
+    (hufc.rs:24-36); Delta and Hilbert-RLE zip their symbol iterator with the curve over a zero image, so a payload that just
+    ENDS yields the pixels it reached and zeros elsewhere (hilbertc.rs:55-79, 417-431); a record cut in the middle / a bad trie
+    panics there -> None here."""
+    img = cb.synth_image_host(40, 24, 9, 4)
+    n = 40 * 24
+    xy = O.hilbert_xy(40, 24)
+    # delta: cut the payload (the trie is intact: it ends where the first payload byte starts; cut a few bytes off the end)
+    c = codecs.Codec.from_str(ctx, "delta")
+    data = c.encode(img)
+    cut = data[:len(data) - 40]
+    g, o = c.decode(cut), O.decode_delta(cut)
+    assert g is not None and np.array_equal(g, o)
+    lin = g[xy[:, 1], xy[:, 0]]
+    reached = int(np.argmax(np.any(lin != img[xy[:, 1], xy[:, 0]], axis=1)))  # first curve index that differs from the original
+    assert 0 < reached < n and not lin[reached:].any()                         # ... from there on everything is zero
+    # hufman: the same cut is a failure
+    h = codecs.Codec.from_str(ctx, "hufman")
+    hd = h.encode(img)
+    assert h.decode(hd[:len(hd) - 40]) is None and O.decode_hufman(hd[:len(hd) - 40]) is None
+    # hilbert-rle: whole records missing -> zeros behind the last run; half a record -> failure
+    r = codecs.Codec.from_str(ctx, "hilbert(rle)")
+    flat = (img // 128) * 128
+    rd = r.encode(flat)
+    whole = rd[:8 + 12 * ((len(rd) - 8) // 12 // 2)]
+    g, o = r.decode(whole), O.decode_hilbert_rle(whole)
+    assert g is not None and np.array_equal(g, o) and not g[xy[-1, 1], xy[-1, 0]].any()
+    assert r.decode(whole + rd[len(whole):len(whole) + 5]) is None and O.decode_hilbert_rle(whole + rd[len(whole):len(whole) + 5]) is None
+    zero_count = rd[:8] + bytes([0]) + rd[9:]
+    assert r.decode(zero_count) is None and O.decode_hilbert_rle(zero_count) is None  # assert!(self.count > 0)
