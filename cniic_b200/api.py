@@ -189,6 +189,25 @@ class Context:
         return [self._result(sts[i], cen[i, :k].astype(np.int64), wts[i, :k], asgs[i] if want_assign else None, rc)
                 for i in range(count)]
 
+    def kmeans_xyrgb_batch(self, images, k, max_iters=0, tie=L.TIE_KEEP_CURRENT, want_assign=True, allow_inactive=False):
+        """The batch form for ColorPos points (cniic_kmeans_xyrgb_batch): images of any sizes, results as kmeans_xyrgb per image."""
+        imgs = [_u8(im) for im in images]
+        count = len(imgs)
+        ptrs = (C.c_void_p * count)(*[im.ctypes.data for im in imgs])
+        ws = (C.c_uint32 * count)(*[im.shape[1] for im in imgs])
+        hs = (C.c_uint32 * count)(*[im.shape[0] for im in imgs])
+        cxy = np.zeros((count, max(k, 1), 2), np.uint32)
+        crgb = np.zeros((count, max(k, 1), 3), np.uint8)
+        wts = np.zeros((count, max(k, 1)), np.uint64)
+        asgs = [np.zeros(im.shape[0] * im.shape[1], np.uint16) for im in imgs] if want_assign else None
+        aptrs = (C.c_void_p * count)(*[a.ctypes.data for a in asgs]) if want_assign else None
+        sts = (L.KMeansStats * count)()
+        rc = self._lib.cniic_kmeans_xyrgb_batch(self.h, ptrs, ws, hs, C.c_uint32(count), C.c_uint32(k), C.c_uint32(max_iters), tie,
+                                                _ptr(cxy), _ptr(crgb), _ptr(wts), aptrs, sts)
+        self.check(rc, (L.ERR_TOO_FEW_ACTIVE,) if allow_inactive else ())
+        return [self._result(sts[i], np.concatenate([cxy[i, :k].astype(np.int64), crgb[i, :k].astype(np.int64)], axis=1), wts[i, :k],
+                             asgs[i] if want_assign else None, rc) for i in range(count)]
+
     def kmeans_session(self, **kw) -> "KMeansSession":
         return KMeansSession(self, **kw)
 

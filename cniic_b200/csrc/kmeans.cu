@@ -2601,6 +2601,46 @@ extern "C" int cniic_kmeans_rgb_batch(cniic_ctx *ctx, const uint8_t *const *rgb,
     return rc != CNIIC_OK ? rc : worst;
 }
 
+// The same for (x, y, r, g, b) points: `count` images rgb[i] of w[i] x h[i] pixels (voronoi encodes of a batch, bench.rs:27).
+extern "C" int cniic_kmeans_xyrgb_batch(cniic_ctx *ctx, const uint8_t *const *rgb, const uint32_t *w, const uint32_t *h, uint32_t count, uint32_t k,
+                                        uint32_t max_iters, int tie_rule, uint32_t *out_xy, uint8_t *out_rgb, uint64_t *out_weight,
+                                        uint16_t *const *out_assign, cniic_kmeans_stats *stats) {
+    if (!ctx) return CNIIC_ERR_BAD_ARG;
+    if (!rgb || !w || !h || !count || !out_xy || !out_rgb) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "null buffer or empty batch");
+    std::vector<cniic_kmeans *> ss(count, nullptr);
+    int rc = CNIIC_OK;
+    for (uint32_t i = 0; i < count && rc == CNIIC_OK; i++) {
+        if (!rgb[i]) { rc = cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "null image %u", i); break; }
+        cniic_kmeans_desc desc{};
+        desc.kind = CNIIC_POINTS_XYRGB;
+        desc.k = k;
+        desc.tie_rule = tie_rule;
+        desc.n_local = desc.n_total = (uint64_t)w[i] * h[i];
+        desc.w = w[i];
+        desc.h_local = h[i];
+        desc.rgb = rgb[i];
+        rc = cniic_kmeans_open(ctx, &desc, &ss[i]);
+    }
+    if (rc == CNIIC_OK) rc = cniic_kmeans_reset_batch(ss.data(), count);
+    if (rc == CNIIC_OK) rc = cniic_kmeans_run_batch(ss.data(), count, max_iters, stats);
+    std::vector<int32_t> cen(size_t(k) * 5);
+    std::vector<uint64_t> wts(k);
+    int worst = CNIIC_OK;
+    for (uint32_t i = 0; i < count && rc == CNIIC_OK; i++) {
+        rc = cniic_kmeans_get(ss[i], cen.data(), wts.data(), out_assign ? out_assign[i] : nullptr);
+        if (rc != CNIIC_OK) break;
+        for (uint32_t c = 0; c < k; c++) {
+            out_xy[(size_t(i) * k + c) * 2] = (uint32_t)cen[5 * c];
+            out_xy[(size_t(i) * k + c) * 2 + 1] = (uint32_t)cen[5 * c + 1];
+            for (int j = 0; j < 3; j++) out_rgb[(size_t(i) * k + c) * 3 + j] = (uint8_t)cen[5 * c + 2 + j];
+        }
+        if (out_weight) memcpy(out_weight + size_t(i) * k, wts.data(), size_t(k) * 8);
+        if (check_active(ctx, wts.data(), k, (uint64_t)w[i] * h[i]) != CNIIC_OK) worst = CNIIC_ERR_TOO_FEW_ACTIVE;
+    }
+    for (cniic_kmeans *km : ss) cniic_kmeans_close(km);
+    return rc != CNIIC_OK ? rc : worst;
+}
+
 extern "C" int cniic_kmeans_get(cniic_kmeans *km, int32_t *out_centroids, uint64_t *out_weight, uint16_t *out_assign) {
     if (!km) return CNIIC_ERR_BAD_ARG;
     cniic_ctx *ctx = km->ctx;

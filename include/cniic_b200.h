@@ -158,6 +158,10 @@ int cniic_kmeans_run_batch(cniic_kmeans *const *sessions, uint32_t count, uint32
 int cniic_kmeans_rgb_batch(cniic_ctx *ctx, const uint8_t *const *rgb, const size_t *n, uint32_t count, uint32_t k, uint32_t max_iters,
                            int tie_rule, uint8_t *out_centroids, uint64_t *out_weight, uint16_t *const *out_assign,
                            cniic_kmeans_stats *stats);
+/* ColorPos points: rgb[i] = image of w[i] x h[i] pixels; out_xy = count x k x {u32 x, u32 y}, out_rgb = count x k x 3 bytes. */
+int cniic_kmeans_xyrgb_batch(cniic_ctx *ctx, const uint8_t *const *rgb, const uint32_t *w, const uint32_t *h, uint32_t count, uint32_t k,
+                             uint32_t max_iters, int tie_rule, uint32_t *out_xy, uint8_t *out_rgb, uint64_t *out_weight,
+                             uint16_t *const *out_assign, cniic_kmeans_stats *stats);
 
 /* ---- cluster-colors stages (clusterc.rs:18-52) ---------------------------------------------------------- */
 /* utils::count_freqs over pixels (utils.rs:4-16 as called at clusterc.rs:21 and huf.rs:30 via hufc.rs:15-16).

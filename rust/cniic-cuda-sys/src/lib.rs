@@ -33,6 +33,12 @@ extern "C" {
     pub fn cniic_kmeans_rgb_batch(ctx: *mut cniic_ctx, rgb: *const *const u8, n: *const usize, count: u32, k: u32, max_iters: u32,
                                   tie_rule: c_int, out_centroids: *mut u8, out_weight: *mut u64, out_assign: *const *mut u16,
                                   stats: *mut cniic_kmeans_stats) -> c_int;
+    pub fn cniic_kmeans_xyrgb_batch(ctx: *mut cniic_ctx, rgb: *const *const u8, w: *const u32, h: *const u32, count: u32, k: u32, max_iters: u32,
+                                    tie_rule: c_int, out_xy: *mut u32, out_rgb: *mut u8, out_weight: *mut u64, out_assign: *const *mut u16,
+                                    stats: *mut cniic_kmeans_stats) -> c_int;
+    pub fn cniic_delta_i16_range_device(ctx: *mut cniic_ctx, d_rgb: *const u8, w: u32, h: u32, i_begin: u64, i_end: u64, d_out: *mut i16) -> c_int;
+    pub fn cniic_hist_delta_range_device(ctx: *mut cniic_ctx, d_rgb: *const u8, w: u32, h: u32, i_begin: u64, i_end: u64, out_keys: *mut u32,
+                                         out_counts: *mut u64, cap: usize, out_n: *mut usize) -> c_int;
     pub fn cniic_voronoi_fill(ctx: *mut cniic_ctx, cxy: *const u32, crgb: *const u8, k: u32, w: u32, h: u32, out_rgb: *mut u8) -> c_int;
     pub fn cniic_hist_rgb(ctx: *mut cniic_ctx, rgb: *const u8, n: usize, out_keys: *mut u32, out_counts: *mut u64, cap: usize, out_n: *mut usize) -> c_int;
     pub fn cniic_hist_delta(ctx: *mut cniic_ctx, rgb: *const u8, w: u32, h: u32, out_keys: *mut u32, out_counts: *mut u64, cap: usize, out_n: *mut usize) -> c_int;

@@ -637,3 +637,10 @@ def test_truncated_streams_follow_the_reference_decoders(ctx):
     assert r.decode(whole + rd[len(whole):len(whole) + 5]) is None and O.decode_hilbert_rle(whole + rd[len(whole):len(whole) + 5]) is None
     zero_count = rd[:8] + bytes([0]) + rd[9:]
     assert r.decode(zero_count) is None and O.decode_hilbert_rle(zero_count) is None  # assert!(self.count > 0)
+
+
+def test_kmeans_xyrgb_batch_equals_separate_runs(ctx):
+    imgs = [cb.synth_image_host(w, h, 40 + i, 5) for i, (w, h) in enumerate([(96, 40), (64, 64), (130, 17), (24, 12)])]
+    for max_iters in (3, 0):
+        for im, g in zip(imgs, ctx.kmeans_xyrgb_batch(imgs, 10, max_iters=max_iters)):
+            same_kmeans(g, O.kmeans_xyrgb(im, 10, mode=O.MODE_EXACT, max_iters=max_iters))
