@@ -739,10 +739,16 @@ __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
 
         uint16_t idx[PX];
         bool any_moved = false, uniform = nv == PX;
+        // the keep-current check costs ~13 instructions per point whether or not it changes anything; after the first iterations
+        // about half of the warps have no point at all whose winner differs from its current cluster and skip it
+        bool differs = false;
+#pragma unroll
+        for (int p = 0; p < PX; p++) differs |= p < nv && bi[p] != int(prev[p]);
+        const bool check_ties = d.tie == CNIIC_TIE_KEEP_CURRENT && __any_sync(0xffffffffu, differs);
 #pragma unroll
         for (int p = 0; p < PX; p++) {
             int found = bi[p];
-            if (p < nv && d.tie == CNIIC_TIE_KEEP_CURRENT && found != prev[p]) {
+            if (check_ties && p < nv && found != prev[p]) {
                 // a culled current cluster is strictly farther than the winner (LB > U), so it cannot tie
                 const uint2 ce = s_cen[prev[p]];
                 if (2 * dp4a_uu(px[p], ce.x, 0) - int(ce.y) == best[p]) found = prev[p];
