@@ -614,8 +614,8 @@ __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
     uint32_t *s_lb = reinterpret_cast<uint32_t *>(s_cen + ((k + 1) & ~1u));  // k lower bounds against the current tile box
     uint32_t *s_acc32 = s_lb + ((k + 3) & ~3u);
     unsigned long long *s_acc64 = reinterpret_cast<unsigned long long *>(s_lb + ((k + 3) & ~3u));
-    __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_U;
+    __shared__ uint32_t s_nt;  // survivors of the current round
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t i = tid; i < k; i += THREADS) s_cen[i] = make_uint2(d.g_cpk[i], d.g_nrm[i]);
     for (uint32_t i = tid; i < 4 * k; i += THREADS) {
@@ -650,8 +650,8 @@ __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
         const uint4 seg = d.wseg[tile * 8 + warp];     // static box / sums of this warp's 256 points
         const int r0 = box.x & 0xff, g0 = (box.x >> 8) & 0xff, b0 = (box.x >> 16) & 0xff;
         const int r1 = box.y & 0xff, g1 = (box.y >> 8) & 0xff, b1 = (box.y >> 16) & 0xff;
-        __syncthreads();  // previous tile done with s_U / t_ent (and s_cen is loaded on the first pass)
-        if (tid == 0) s_U = 0xffffffffu;
+        __syncthreads();  // previous tile done with s_U / s_nt / t_ent (and s_cen is loaded on the first pass)
+        if (tid == 0) { s_U = 0xffffffffu; s_nt = 0u; }
         __syncthreads();
         // ---- one pass: upper and lower bound of every centroid against the tile box ----
         uint32_t umin = 0xffffffffu;
@@ -684,10 +684,15 @@ __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
                 // packed score: (2*dot - |c|^2) * 4096 + (4095 - id)  ==  dot * 8192 + ent.y ; max() picks the best key, then the lowest id
                 ent = make_uint4(ce.x, uint32_t(-int(ce.y) * 4096 + 4095 - int(c)), c, 0);
             }
-            uint32_t nt;
-            const uint32_t r = block_rank256(keep, s_warp, &nt);
-            if (keep) t_ent[r] = ent;
+            // unordered compaction (the packed score carries the id, so the order of the survivors is irrelevant here): one
+            // shared atomic per warp reserves its slots -- no block-wide prefix, one barrier instead of three
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            uint32_t slot0 = 0;
+            if (lane == 0 && bal) slot0 = atomicAdd(&s_nt, (uint32_t)__popc(bal));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+            if (keep) t_ent[slot0 + __popc(bal & ((1u << lane) - 1))] = ent;
             __syncthreads();
+            const uint32_t nt = s_nt;
             if (nt <= 32) {
                 // ---- warp-level culling of the tile's survivors against the warp's own box (exact, same argument) ----
                 uint32_t ubw = 0xffffffffu, lbw = 0xffffffffu;
@@ -732,7 +737,11 @@ __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
                     for (int p = 0; p < PX; p++) best[p] = max(best[p], dp4a_uu(px[p], c0.x, 0) * 8192 + int(c0.y));
                 }
             }
-            if (cb0 + RCAP < k) __syncthreads();
+            if (cb0 + RCAP < k) {  // next round overwrites t_ent and restarts the count
+                __syncthreads();
+                if (tid == 0) s_nt = 0u;
+                __syncthreads();
+            }
         }
 #pragma unroll
         for (int p = 0; p < PX; p++) { bi[p] = 4095 - (best[p] & 4095); best[p] >>= 12; }  // unpack: id, exact key
