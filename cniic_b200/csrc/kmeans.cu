@@ -1391,7 +1391,8 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
         uint32_t lb0 = 0xffffffffu;
         for (uint32_t j = tid; j < m; j += THREADS) {
             const uint32_t id = list[j];
-            const uint32_t cxy = d.g_cxy[id], cp = d.g_cpk[id];
+            const uint4 ge = __ldg(d.g_ent + id);  // {colour, position, |c|^2, -}: one 128-bit load per candidate
+            const uint32_t cxy = ge.y, cp = ge.x;
             const int cx = cxy & 0xffff, cy = cxy >> 16, cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
             const uint32_t ub = sq(max(abs(cx - bx0), abs(cx - bx1))) + sq(max(abs(cy - by0), abs(cy - by1))) +
                                 sq(max(abs(cr - r0), abs(cr - r1))) + sq(max(abs(cg - g0), abs(cg - g1))) + sq(max(abs(cb - b0), abs(cb - b1)));
@@ -1399,7 +1400,7 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
             if (j < THREADS) {
                 lb0 = sq(max(0, max(bx0 - cx, cx - bx1))) + sq(max(0, max(by0 - cy, cy - by1))) +
                       sq(max(0, max(r0 - cr, cr - r1))) + sq(max(0, max(g0 - cg, cg - g1))) + sq(max(0, max(b0 - cb, cb - b1)));
-                ent0 = make_uint4(cp, cxy, uint32_t(2 * (x0 * cx + yg0 * cy) - int(d.g_nrm[id])), id);
+                ent0 = make_uint4(cp, cxy, uint32_t(2 * (x0 * cx + yg0 * cy) - int(ge.z)), id);
             }
         }
         for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
@@ -1422,12 +1423,13 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
                 keep = j < m && lb0 <= U;
             } else if (j < m) {
                 const uint32_t id = list[j];
-                const uint32_t cxy = d.g_cxy[id], cp = d.g_cpk[id];
+                const uint4 ge = __ldg(d.g_ent + id);
+                const uint32_t cxy = ge.y, cp = ge.x;
                 const int cx = cxy & 0xffff, cy = cxy >> 16, cr = cp & 0xff, cg = (cp >> 8) & 0xff, cb = (cp >> 16) & 0xff;
                 const uint32_t lb = sq(max(0, max(bx0 - cx, cx - bx1))) + sq(max(0, max(by0 - cy, cy - by1))) +
                                     sq(max(0, max(r0 - cr, cr - r1))) + sq(max(0, max(g0 - cg, cg - g1))) + sq(max(0, max(b0 - cb, cb - b1)));
                 keep = lb <= U;
-                ent = make_uint4(cp, cxy, uint32_t(2 * (x0 * cx + yg0 * cy) - int(d.g_nrm[id])), id);
+                ent = make_uint4(cp, cxy, uint32_t(2 * (x0 * cx + yg0 * cy) - int(ge.z)), id);
             }
             uint32_t nt;
             const uint32_t r = block_rank256(keep, s_warp, &nt);
