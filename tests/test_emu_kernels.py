@@ -147,3 +147,4 @@ def test_emu_graft_entry_smoke_runs(ctx):
     sys.path.insert(0, os.path.dirname(HERE))
     import __graft_entry__ as g
     g.smoke()
+    g.smoke_extras()

@@ -38,3 +38,11 @@ def test_gpu_matches_committed_golden_fixtures():
     crgb = np.array([[1, 2, 3], [40, 50, 60], [200, 100, 0], [9, 9, 9]], np.uint8)
     assert np.array_equal(ctx.voronoi_fill(cxy, crgb, 24, 18), gold["fill"])
     ctx.close()
+
+
+def test_graft_entry_smoke_and_extras():
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    import __graft_entry__ as g
+    g.smoke()
+    g.smoke_extras()
