@@ -389,11 +389,11 @@ def main():
     if B > 1:
         kernel += "_batch"
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp) and world == 1:
-        ent = json.load(open(tp)).get(kernel)
-        if ent and ent.get("workload") == args.workload:
-            traffic = ent["bytes"]  # dram bytes per launch from the committed ncu --set full capture of this kernel/workload
+    for tp in (os.path.join(ROOT, "profiles", "r02_traffic.json"), os.path.join(ROOT, "profiles", "r01_traffic.json")):
+        if os.path.exists(tp) and world == 1 and traffic is None:
+            ent = json.load(open(tp)).get(kernel)
+            if ent and ent.get("workload") == args.workload:
+                traffic = ent["bytes"]  # dram bytes per launch from the committed ncu --set full capture of this kernel/workload
     roofline = build_roofline(D, n_local * B, k, a_ms, pairs_per_launch, pk, kernel, traffic, stb.assign_ms_avg, culled=sess_culled)  # one launch = B images
 
     cpu = None

@@ -306,7 +306,10 @@ class Context:
     def undelta(self, diff, w, h):
         diff = np.ascontiguousarray(diff, dtype=np.int16)
         out = np.zeros((h, w, 3), np.uint8)
-        self.check(self._lib.cniic_undelta_rgb(self.h, _ptr(diff), C.c_uint32(w), C.c_uint32(h), _ptr(out)))
+        rc = self._lib.cniic_undelta_rgb(self.h, _ptr(diff), C.c_uint32(w), C.c_uint32(h), _ptr(out))
+        if rc == L.ERR_DECODE:
+            return None  # a reconstructed channel left 0..255: FromDiff's try_into().unwrap() panics (hilbertc.rs:503-506)
+        self.check(rc)
         return out
 
     def sse(self, a, b) -> int:
@@ -322,15 +325,16 @@ class Context:
         h, w = img.shape[:2]
         need = C.c_size_t(0)
         cap = 1 << 16
-        while True:
+        out = np.zeros(cap, np.uint8)
+        rc = self._lib.cniic_codec_encode(self.h, codec.encode(), _ptr(img), C.c_uint32(w), C.c_uint32(h), _ptr(out),
+                                          C.c_size_t(cap), C.byref(need))
+        if rc == L.ERR_BUFFER_TOO_SMALL and need.value > cap:
+            # the finished stream waits in the ctx: fetch it (no second encoding pass)
+            cap = need.value
             out = np.zeros(cap, np.uint8)
-            rc = self._lib.cniic_codec_encode(self.h, codec.encode(), _ptr(img), C.c_uint32(w), C.c_uint32(h), _ptr(out),
-                                              C.c_size_t(cap), C.byref(need))
-            if rc == L.ERR_BUFFER_TOO_SMALL and need.value > cap:
-                cap = need.value
-                continue
-            self.check(rc)
-            return out[:need.value].tobytes()
+            rc = self._lib.cniic_codec_encode_fetch(self.h, _ptr(out), C.c_size_t(cap), C.byref(need))
+        self.check(rc)
+        return out[:need.value].tobytes()
 
     def codec_decode(self, codec: str, data: bytes):
         """Returns the decoded (h, w, 3) image or None (Codec::decode -> Option<Img>)."""

@@ -196,9 +196,14 @@ int huf_decode_device(cniic_ctx *ctx, const Source &src, const DecTrie &T, size_
     return cniic_dev_huffman_decode(ctx, src.p + src.pos, src.len - src.pos, child.data(), leaf.data(), nn, sym_bytes, n, d_out, decoded);
 }
 
-int finish(cniic_ctx *ctx, const Sink &s, uint8_t *out, size_t cap, size_t *out_len) {
+int finish(cniic_ctx *ctx, Sink &s, uint8_t *out, size_t cap, size_t *out_len) {
     *out_len = s.v.size();
-    if (s.v.size() > cap || (!out && !s.v.empty())) return cniic_set_error(ctx, CNIIC_ERR_BUFFER_TOO_SMALL, "need %zu bytes", s.v.size());
+    if (s.v.size() > cap || (!out && !s.v.empty())) {
+        // keep the finished stream: the caller fetches it with cniic_codec_encode_fetch instead of encoding a second time
+        ctx->pending_stream.swap(s.v);
+        ctx->has_pending_stream = true;
+        return cniic_set_error(ctx, CNIIC_ERR_BUFFER_TOO_SMALL, "need %zu bytes", *out_len);
+    }
     if (!s.v.empty()) memcpy(out, s.v.data(), s.v.size());
     return CNIIC_OK;
 }
@@ -263,9 +268,22 @@ extern "C" int cniic_codec_name(const char *codec, char *out, size_t cap) {
     return CNIIC_OK;
 }
 
+extern "C" int cniic_codec_encode_fetch(cniic_ctx *ctx, uint8_t *out, size_t cap, size_t *out_len) {
+    if (!ctx || !out_len) return CNIIC_ERR_BAD_ARG;
+    if (!ctx->has_pending_stream) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "no encoded stream is pending on this context");
+    *out_len = ctx->pending_stream.size();
+    if (*out_len > cap || (!out && *out_len)) return cniic_set_error(ctx, CNIIC_ERR_BUFFER_TOO_SMALL, "need %zu bytes", *out_len);
+    if (*out_len) memcpy(out, ctx->pending_stream.data(), *out_len);
+    std::vector<uint8_t>().swap(ctx->pending_stream);
+    ctx->has_pending_stream = false;
+    return CNIIC_OK;
+}
+
 extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8_t *rgb, uint32_t w, uint32_t h, uint8_t *out,
                                   size_t cap, size_t *out_len) {
     if (!ctx || !out_len) return CNIIC_ERR_BAD_ARG;
+    ctx->has_pending_stream = false;
+    ctx->pending_stream.clear();
     const CodecSpec sp = parse_codec(codec);
     if (sp.kind == CK_NONE) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "unknown codec expression '%s'", codec ? codec : "(null)");
     const size_t n = (size_t)w * h;

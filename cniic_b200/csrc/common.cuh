@@ -37,6 +37,8 @@ struct cniic_ctx {
     std::vector<void *> p2p_opened;
     bool p2p_ready = false;
     uint32_t p2p_seq = 0;
+    std::vector<uint8_t> pending_stream;  // cniic_codec_encode result that did not fit the caller's buffer (cniic_codec_encode_fetch)
+    bool has_pending_stream = false;
     uint32_t *hist_bins[2] = {nullptr, nullptr};  // persistent dense histogram bins (+ page flags), all zero between calls
 };
 

@@ -641,71 +641,76 @@ __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__rest
 }
 
 // inverse: segmented prefix sum along the curve is sequential per channel; done as a 3-kernel scan over i16 diffs.
-// Values are bounded (reconstructed colours are 0..255) so int32 prefix sums are exact.
-__global__ void __launch_bounds__(256) undelta_partial_kernel(const int16_t *__restrict__ diff, unsigned long long n, int *block_sums) {
+// Arithmetic is modulo 2^32 (unsigned): FromDiff (hilbertc.rs:482-509) panics at the FIRST reconstructed channel outside 0..255
+// (`try_into().unwrap()`), every prefix before that one is in 0..255, so the wrapped value at the first offender equals the true
+// value and is detected whatever a damaged stream does afterwards (err_flag -> CNIIC_ERR_DECODE).
+__global__ void __launch_bounds__(256) undelta_partial_kernel(const int16_t *__restrict__ diff, unsigned long long n, uint32_t *block_sums) {
     const unsigned long long base = (unsigned long long)blockIdx.x * 4096;
-    int s0 = 0, s1 = 0, s2 = 0;
+    uint32_t s0 = 0, s1 = 0, s2 = 0;
     for (int j = 0; j < 16; j++) {
         const unsigned long long i = base + (unsigned long long)j * 256 + threadIdx.x;
-        if (i < n) { s0 += diff[3 * i]; s1 += diff[3 * i + 1]; s2 += diff[3 * i + 2]; }
+        if (i < n) { s0 += uint32_t(int(diff[3 * i])); s1 += uint32_t(int(diff[3 * i + 1])); s2 += uint32_t(int(diff[3 * i + 2])); }
     }
     for (int o = 16; o > 0; o >>= 1) {
         s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    __shared__ int s[8][3];
+    __shared__ uint32_t s[8][3];
     if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5][0] = s0; s[threadIdx.x >> 5][1] = s1; s[threadIdx.x >> 5][2] = s2; }
     __syncthreads();
     if (threadIdx.x < 3) {
-        int t = 0;
+        uint32_t t = 0;
         for (int i = 0; i < 8; i++) t += s[i][threadIdx.x];
         block_sums[3 * blockIdx.x + threadIdx.x] = t;
     }
 }
 
-__global__ void undelta_scan_blocks_kernel(int *block_sums, size_t nblocks) {
+__global__ void undelta_scan_blocks_kernel(uint32_t *block_sums, size_t nblocks) {
     // one thread per channel: nblocks <= N/4096 (16K for 8192^2) -- sequential is fine
     if (threadIdx.x < 3) {
-        int run = 0;
+        uint32_t run = 0;
         for (size_t b = 0; b < nblocks; b++) {
-            const int v = block_sums[3 * b + threadIdx.x];
+            const uint32_t v = block_sums[3 * b + threadIdx.x];
             block_sums[3 * b + threadIdx.x] = run;
             run += v;
         }
     }
 }
 
-__global__ void __launch_bounds__(256) undelta_apply_kernel(const int16_t *__restrict__ diff, unsigned long long n, const int *__restrict__ block_sums,
-                                                            uint32_t w, uint32_t h, bool pow2, uint8_t *out) {
+__global__ void __launch_bounds__(256) undelta_apply_kernel(const int16_t *__restrict__ diff, unsigned long long n, const uint32_t *__restrict__ block_sums,
+                                                            uint32_t w, uint32_t h, bool pow2, uint8_t *out, uint32_t *err_flag) {
     // each thread owns 16 consecutive stream positions of the 4096-position block
     const unsigned long long base = (unsigned long long)blockIdx.x * 4096 + (unsigned long long)threadIdx.x * 16;
-    int l0 = 0, l1 = 0, l2 = 0;
+    uint32_t l0 = 0, l1 = 0, l2 = 0;
     for (int j = 0; j < 16; j++) {
         const unsigned long long i = base + j;
-        if (i < n) { l0 += diff[3 * i]; l1 += diff[3 * i + 1]; l2 += diff[3 * i + 2]; }
+        if (i < n) { l0 += uint32_t(int(diff[3 * i])); l1 += uint32_t(int(diff[3 * i + 1])); l2 += uint32_t(int(diff[3 * i + 2])); }
     }
     // exclusive scan of the per-thread sums across the block
-    __shared__ int s_w[8][3];
+    __shared__ uint32_t s_w[8][3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int x0 = l0, x1 = l1, x2 = l2;
+    uint32_t x0 = l0, x1 = l1, x2 = l2;
     for (int o = 1; o < 32; o <<= 1) {
-        const int y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o), y2 = __shfl_up_sync(0xffffffffu, x2, o);
+        const uint32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o), y2 = __shfl_up_sync(0xffffffffu, x2, o);
         if (lane >= o) { x0 += y0; x1 += y1; x2 += y2; }
     }
     if (lane == 31) { s_w[warp][0] = x0; s_w[warp][1] = x1; s_w[warp][2] = x2; }
     __syncthreads();
-    int b0 = block_sums[3 * blockIdx.x], b1 = block_sums[3 * blockIdx.x + 1], b2 = block_sums[3 * blockIdx.x + 2];
+    uint32_t b0 = block_sums[3 * blockIdx.x], b1 = block_sums[3 * blockIdx.x + 1], b2 = block_sums[3 * blockIdx.x + 2];
     for (int j = 0; j < warp; j++) { b0 += s_w[j][0]; b1 += s_w[j][1]; b2 += s_w[j][2]; }
-    int r0 = b0 + x0 - l0, r1 = b1 + x1 - l1, r2 = b2 + x2 - l2;
+    uint32_t r0 = b0 + x0 - l0, r1 = b1 + x1 - l1, r2 = b2 + x2 - l2;
+    bool bad = false;
     for (int j = 0; j < 16; j++) {
         const unsigned long long i = base + j;
         if (i < n) {
-            r0 += diff[3 * i]; r1 += diff[3 * i + 1]; r2 += diff[3 * i + 2];
+            r0 += uint32_t(int(diff[3 * i])); r1 += uint32_t(int(diff[3 * i + 1])); r2 += uint32_t(int(diff[3 * i + 2]));
+            bad |= (r0 | r1 | r2) > 255u;  // hilbertc.rs:503-506: Rgb<u8>::try_from(SignedColor).unwrap()
             uint32_t x, y;
             hilbert_d2xy(w, h, pow2, i, &x, &y);
             uint8_t *p = out + ((size_t)y * w + x) * 3;
             p[0] = (uint8_t)r0; p[1] = (uint8_t)r1; p[2] = (uint8_t)r2;
         }
     }
+    if (bad) *err_flag = 1u;
 }
 
 // ============================================================================================================
@@ -1544,13 +1549,19 @@ int cniic_dev_undelta(cniic_ctx *ctx, const int16_t *d_diff, uint32_t w, uint32_
     const unsigned long long n = (unsigned long long)w * h;
     const size_t nblocks = (n + 4095) / 4096;
     DevBuf bs(ctx);
-    CU_TRY(ctx, bs.alloc(nblocks * 12));
-    undelta_partial_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_diff, n, bs.as<int>());
-    undelta_scan_blocks_kernel<<<1, 32, 0, ctx->stream>>>(bs.as<int>(), nblocks);
-    undelta_apply_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_diff, n, bs.as<int>(), w, h, is_pow2_square(w, h), d_out);
+    CU_TRY(ctx, bs.alloc(nblocks * 12 + 4));
+    uint32_t *d_err = bs.as<uint32_t>() + nblocks * 3;
+    CU_TRY(ctx, cudaMemsetAsync(d_err, 0, 4, ctx->stream));
+    undelta_partial_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_diff, n, bs.as<uint32_t>());
+    undelta_scan_blocks_kernel<<<1, 32, 0, ctx->stream>>>(bs.as<uint32_t>(), nblocks);
+    undelta_apply_kernel<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_diff, n, bs.as<uint32_t>(), w, h, is_pow2_square(w, h), d_out, d_err);
     ctx->launches += 3;
     CU_TRY(ctx, cudaGetLastError());
+    uint32_t bad = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&bad, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // FromDiff (hilbertc.rs:497-507) unwraps the conversion to Rgb<u8>: the reference panics on such a stream
+    if (bad) return cniic_set_error(ctx, CNIIC_ERR_DECODE, "delta stream reconstructs a colour channel outside 0..255");
     return CNIIC_OK;
 }
 

@@ -207,6 +207,9 @@ int cniic_sse_rgb(cniic_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n_p
  * encode: returns CNIIC_ERR_BUFFER_TOO_SMALL with *out_len = required size when cap is too small.               */
 int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8_t *rgb, uint32_t w, uint32_t h, uint8_t *out,
                        size_t cap, size_t *out_len);
+/* After cniic_codec_encode returned CNIIC_ERR_BUFFER_TOO_SMALL the finished stream stays in the ctx: this call copies it out
+ * (no second H2D / K-means / packing pass) and releases it.  CNIIC_ERR_BAD_ARG if no stream is pending on this ctx.    */
+int cniic_codec_encode_fetch(cniic_ctx *ctx, uint8_t *out, size_t cap, size_t *out_len);
 /* decode: *w,*h receive the dimensions; out_rgb must hold cap_pixels pixels (call with out_rgb NULL to query dims).
  * Short or damaged streams follow the reference decoder of each codec: hufman / cluster-colors return CNIIC_ERR_DECODE
  * when code words are missing (hufc.rs:24-36 -> None); delta and hilbert(rle) zip their symbol iterator with the curve

@@ -226,7 +226,8 @@ def delta(img):
 def undelta(diff, w, h):
     diff = np.ascontiguousarray(diff, dtype=np.int16)
     out = np.zeros((h, w, 3), np.uint8)
-    lib().oracle_undelta(_p(diff), C.c_uint32(w), C.c_uint32(h), _p(out))
+    if lib().oracle_undelta(_p(diff), C.c_uint32(w), C.c_uint32(h), _p(out)):
+        return None  # FromDiff's try_into().unwrap() panics (hilbertc.rs:503-506)
     return out
 
 

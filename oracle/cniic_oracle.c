@@ -753,20 +753,25 @@ void oracle_delta(const uint8_t *rgb, uint32_t w, uint32_t h, int16_t *out) {
     free(lin);
 }
 
-/* hilbertc.rs:482-509 + 417-431 */
-void oracle_undelta(const int16_t *diff, uint32_t w, uint32_t h, uint8_t *out_rgb) {
+/* hilbertc.rs:482-509 + 417-431.  FromDiff::next does `new_signed.try_into().unwrap()` (hilbertc.rs:503-506, conversion
+   525-535: i16 -> u8 per channel): the reference PANICS at the first reconstructed channel outside 0..255.  Returns 1 then
+   (the i16 addition itself wraps in a release build, hilbertc.rs:549-558; the first offender is reached before any wrap). */
+int oracle_undelta(const int16_t *diff, uint32_t w, uint32_t h, uint8_t *out_rgb) {
     size_t n = (size_t)w * h;
     uint32_t *xy = (uint32_t *)malloc((n ? n : 1) * 2 * sizeof(uint32_t));
     oracle_hilbert_xy(w, h, xy);
     int16_t last[3] = {0, 0, 0};
-    for (size_t i = 0; i < n; i++) {
+    int panicked = 0;
+    for (size_t i = 0; i < n && !panicked; i++) {
         uint8_t *px = out_rgb + 3 * ((size_t)xy[2 * i + 1] * w + xy[2 * i]);
         for (int j = 0; j < 3; j++) {
-            last[j] = (int16_t)(last[j] + diff[3 * i + j]);
+            last[j] = (int16_t)((uint16_t)last[j] + (uint16_t)diff[3 * i + j]);
+            if (last[j] < 0 || last[j] > 255) panicked = 1;
             px[j] = (uint8_t)last[j];
         }
     }
     free(xy);
+    return panicked;
 }
 
 static inline uint32_t delta_key(const int16_t *d) {
@@ -1248,9 +1253,9 @@ int oracle_decode_delta(const uint8_t *buf, size_t len, uint32_t *w, uint32_t *h
     if (rc == 0) {
         int16_t *diff = (int16_t *)malloc(n * 3 * sizeof(int16_t));
         for (size_t i = 0; i < 3 * n; i++) diff[i] = (int16_t)((uint16_t)vals[2 * i] | ((uint16_t)vals[2 * i + 1] << 8));
-        oracle_undelta(diff, *w, *h, out_rgb);
+        if (oracle_undelta(diff, *w, *h, out_rgb)) rc = 2; /* FromDiff unwrap panics (symbols behind `got` are zero: no effect) */
         free(diff);
-        if (got < n) {
+        if (rc == 0 && got < n) {
             uint32_t *xy = (uint32_t *)malloc(n * 2 * sizeof(uint32_t));
             oracle_hilbert_xy(*w, *h, xy);
             for (size_t i = got; i < n; i++) memset(out_rgb + 3 * ((size_t)xy[2 * i + 1] * *w + xy[2 * i]), 0, 3);

@@ -101,7 +101,7 @@ void oracle_hilbert_d2xy(uint32_t w, uint32_t h, uint64_t d, uint32_t *x, uint32
 /* hilbertc.rs:449-477 DiffStream over hilbert::linearize(img): out = w*h x 3 i16. */
 void oracle_delta(const uint8_t *rgb, uint32_t w, uint32_t h, int16_t *out);
 /* hilbertc.rs:482-509 FromDiff + scatter (Delta::decode 417-431). */
-void oracle_undelta(const int16_t *diff, uint32_t w, uint32_t h, uint8_t *out_rgb);
+int oracle_undelta(const int16_t *diff, uint32_t w, uint32_t h, uint8_t *out_rgb); /* 1 = the reference would panic (channel outside 0..255) */
 /* hilbert.rs:34-38 linearize (gather along the curve). out = w*h x 3. */
 void oracle_hilbert_gather(const uint8_t *rgb, uint32_t w, uint32_t h, uint8_t *out);
 
