@@ -1,10 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the cniic_b200 hot path (BASELINE.json metric: Mpixel*iterations/s of Lloyd K-means).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1|c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1|c4|c5|fill] [--impl ours|reference]
 
+Default (no --workload): the north-star sharded configuration C3 -- voronoi k=2048 on ONE 7680x4320 image, rows sharded over the
+N GPUs, STRONG scaling -- is the headline line at every N, and C2 (cluster-colors k=256, 4096x4096 per GPU) rides in the same
+JSON line as `secondary`.
 A "step" = one pass of the hot path over one batch of synthetic input = kmeans::cluster with max_iters = ITERS
-(chunked init + ITERS fused assign/accumulate/finalize iterations) on the workload's image.
+(chunked init + ITERS fused assign/accumulate/update iterations) on the workload's image.
   value  : whole-job throughput, points resident in HBM when the timed region starts (CUDA events, max over ranks)
   e2e    : same metric through the host-buffer C-ABI call (cniic_kmeans_rgb / cniic_kmeans_xyrgb): pinned host image
            -> H2D -> kernels -> centroids/weights D2H, all inside the timed region
@@ -93,24 +96,49 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_leg(kind, w, h, k, blobs, seed, budget_px, threads):
-    """Times the CPU restatement of the reference's kmeans.rs (oracle, VERBATIM mode = neighbour-list pruning) on a
-    bounded sample of the workload: `threads` independent crops, one per host thread, like bench.rs:27 (rayon, one
-    image per worker).  Returns (Mpx*iter/s aggregate, description, seconds)."""
+def workload_image(name, w, h, blobs, seed_off=0, y0=0, rows=None):
+    """Rows [y0, y0 + rows) of the workload's synthetic image, built by the numpy restatement of the generator (oracle/synth.py)
+    so that the CPU legs never load the product library."""
+    from oracle import synth
+    return synth.synth_image(w, rows if rows else h, SEED + int(name[1]) + seed_off, blobs, y0=y0, h_total=h)
+
+
+def cpu_sample_plan(name):
+    """Bounded CPU sample of a workload: (band rows, k of the sample, description).  C3: a horizontal band of the SAME image with k
+    scaled so that points-per-cluster stays N/k = 16200; RGB workloads: a band of the image with the full k (colour space has no
+    spatial scale)."""
+    kind, w, h, k, blobs, _, _ = WORKLOADS[name]
+    if kind == "xyrgb":
+        rows = max(8, h // 32)
+        ks = max(1, round(k * rows / h))
+        return rows, ks, f"band of {rows} rows of the {w}x{h} workload image, k={ks} (same points per cluster as k={k} on the whole image)"
+    rows = min(h, max(8, (1 << 21) // w))
+    return rows, min(k, w * rows), f"band of {rows} rows of the {w}x{h} workload image, k={min(k, w * rows)}"
+
+
+def cpu_reference_leg(name, threads, seed_off=0, whole_image=False):
+    """Times the CPU restatement of the reference's path (oracle VERBATIM mode = kmeans.rs incl. neighbour-list pruning; for the
+    cluster-colors workloads through count_freqs + weighted points, clusterc.rs:19-28) on a bounded sample: `threads` bands, one
+    per host thread, like bench.rs:27 (rayon, one image per worker).  Returns (Mpx*iter/s aggregate, description, seconds)."""
     import oracle as O
-    import cniic_b200 as cb
-    side_w = min(w, 1024)
-    side_h = max(8, min(h, budget_px // side_w))
-    crops = [cb.synth_image_host(side_w, side_h, seed + 1000 * i, max(1, blobs * side_w * side_h // (w * h)), 0, side_h)
-             for i in range(threads)]
-    kk = min(k, side_w * side_h)
+    kind, w, h, k, blobs, _, _ = WORKLOADS[name]
+    if whole_image:
+        rows, ks, what = h, k, f"the whole {w}x{h} workload image, k={k}"
+    else:
+        rows, ks, what = cpu_sample_plan(name)
+    nb = max(1, h // rows)
+    bands = [workload_image(name, w, h, blobs, seed_off, y0=((i * 7 + seed_off) % nb) * rows, rows=rows) for i in range(threads)]
     iters_done = [0] * threads
+    uniq = [0] * threads
 
     def work(i):
         if kind == "rgb":
-            r = O.kmeans_rgb(crops[i], kk, mode=O.MODE_VERBATIM, max_iters=ITERS, allow_inactive=True)
+            keys, cnts = O.count_freqs_rgb(bands[i])                       # utils.rs:4-16 at clusterc.rs:21
+            cols = np.stack([(keys >> 16) & 255, (keys >> 8) & 255, keys & 255], axis=1).astype(np.uint8)
+            uniq[i] = len(keys)
+            r = O.kmeans_rgb(cols, min(ks, len(keys)), counts=cnts.astype(np.uint32), mode=O.MODE_VERBATIM, max_iters=ITERS, allow_inactive=True)
         else:
-            r = O.kmeans_xyrgb(crops[i], kk, mode=O.MODE_VERBATIM, max_iters=ITERS, allow_inactive=True)
+            r = O.kmeans_xyrgb(bands[i], ks, mode=O.MODE_VERBATIM, max_iters=ITERS, allow_inactive=True)
         iters_done[i] = r.iterations
 
     O.lib()
@@ -121,10 +149,11 @@ def cpu_reference_leg(kind, w, h, k, blobs, seed, budget_px, threads):
     for t in ths:
         t.join()
     dt = time.perf_counter() - t0
-    px_iter = sum(side_w * side_h * it for it in iters_done)
-    desc = (f"{threads} independent {side_w}x{side_h} crops of the workload image generator, k={kk}, {ITERS} Lloyd iterations each, "
-            f"one crop per host thread (bench.rs:27 image-level parallelism); oracle VERBATIM mode = C restatement of kmeans.rs "
-            f"incl. neighbour-list pruning, not the Rust binary")
+    px_iter = sum(w * rows * it for it in iters_done)
+    desc = (f"{threads} x ({what}), {ITERS} Lloyd iterations each, one band per host thread (bench.rs:27 image-level parallelism); "
+            f"oracle VERBATIM mode = C restatement of kmeans.rs incl. neighbour-list pruning"
+            + (f" over the unique colours with counts (clusterc.rs:19-28; {int(np.mean(uniq))} unique colours per band on average, "
+               f"count_freqs inside the timed region)" if kind == "rgb" else "") + ", not the Rust binary")
     return px_iter / dt / 1e6, desc, dt
 
 
@@ -161,67 +190,21 @@ def build_roofline(D, n_local, k, a_ms, pairs_per_launch, pk, kernel, traffic, b
     }
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5", "fill"])
-    ap.add_argument("--cpu-px", type=int, default=0, help="pixels per CPU-baseline crop (0 = default for the workload)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--batch", type=int, default=C4_BATCH, help="images per step per GPU (workload c4)")
-    args = ap.parse_args()
-    if args.workload in ("c5", "fill"):  # HBM-bound stage workloads (sharded without any collective): bench_stages.py
-        if args.impl == "reference":
-            if int(os.environ.get("RANK", 0)) == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "stage workloads report their CPU leg as cpu_baseline of the default arm"}))
-            return 0
-        import bench_stages
-        return bench_stages.run(args, args.workload, peaks, ClockSampler)
-    W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    K = max(args.steps, 1)
-    kind, w, h, k, blobs, desc, scaling = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    D = 5 if kind == "xyrgb" else 3
-    cores = os.cpu_count() or 1
-    cpu_px = args.cpu_px or (1024 * 8192 if kind == "rgb" else 1024 * 2048)  # ~10-20 s of single-thread CPU work
-
-    # ------------------------------------------------------------------ reference arm (CPU) -----------------
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        threads = max(1, min(cores, 32))
-        vals, descr = [], ""
-        for i in range(W + K):
-            v, descr, dt = cpu_reference_leg(kind, w, h, k, blobs, SEED + i, cpu_px, threads)
-            if i >= W:
-                vals.append((v, dt))
-        value = float(np.mean([v for v, _ in vals]))
-        ms = float(np.mean([dt for _, dt in vals]) * 1e3)
-        line = {"impl": "reference", "metric": "Mpixel*iter/s Lloyd K-means", "value": value, "unit": "Mpx*iter/s",
-                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc, "k": k, "iters_per_step": ITERS, "sample": descr},
-                "cpu_baseline": {"value": value, "unit": "Mpx*iter/s", "cores": threads, "kind": "port", "sample": descr},
-                "e2e": {"value": value, "unit": "Mpx*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
-        return 0
-
-    # ------------------------------------------------------------------ our arm (GPU) -----------------------
+def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
+    """Our arm for one K-means workload; returns the JSON line as a dict on every rank (rank 0 prints).  `ctxs` caches the
+    library contexts (plain / distributed) so that the primary and the secondary workload share one NCCL communicator."""
     import torch
     import torch.distributed as dist
     import cniic_b200 as cb
     from cniic_b200 import dist as cdist
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    independent = world == 1 or args.workload == "c4"   # no data-path collective: plain per-GPU context
-    ctx = cb.Context(local_rank) if independent else cdist.make_context(local_rank)
+    kind, w, h, k, blobs, desc, scaling = WORKLOADS[name]
+    D = 5 if kind == "xyrgb" else 3
+    independent = world == 1 or name == "c4"   # no data-path collective: plain per-GPU context
+    key = "plain" if independent else "dist"
+    if key not in ctxs:
+        ctxs[key] = cb.Context(local_rank) if independent else cdist.make_context(local_rank)
+    ctx = ctxs[key]
     sctx = ctx
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
@@ -234,10 +217,10 @@ def main():
         h_total = h
         y0, h_local = cdist.row_shard(h, world, rank)
     n_local, n_total = w * h_local, w * h_total
-    B = max(1, args.batch) if args.workload == "c4" else 1   # images per step per GPU
+    B = max(1, args.batch) if name == "c4" else 1   # images per step per GPU
     d_img = ctx.device_alloc(n_local * 3 * B)
     for b in range(B):  # c4: B different images back to back; every rank gets its own
-        cb.synth_image_device(ctx, d_img + b * n_local * 3, w, h_local, SEED + int(args.workload[1]) + (rank * B + b if independent else 0),
+        cb.synth_image_device(ctx, d_img + b * n_local * 3, w, h_local, SEED + int(name[1]) + (rank * B + b if independent else 0),
                               blobs, y0=y0, h_total=h_total)
     ctx.sync()
     d_img_s = d_img
@@ -252,7 +235,9 @@ def main():
         ctx.d2h(host_local, d_img)
         init = cdist.gather_init_centroids(D, host_local, w, y0 if D == 5 else first, n_total, k, device=torch.device("cuda", local_rank))
 
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    flush = ctxs.get("flush")
+    if flush is None:
+        flush = ctxs["flush"] = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():
         torch.cuda.synchronize()
@@ -261,7 +246,7 @@ def main():
         torch.cuda.synchronize()
 
     def one_step(flags=0, iters=ITERS):
-        # a step = the whole kmeans::cluster call on HBM-resident points: session set-up (incl. the one-time colour sort of
+        # a step = the whole kmeans::cluster call on HBM-resident points: session set-up (incl. the one-time colour ordering of
         # the culled RGB path), chunked init, ITERS Lloyd iterations
         if B > 1:  # batch of independent images: same work per image, one launch per stage for the whole batch
             ss = [cb.KMeansSession(sctx, kind_id, k, d_img_s + b * n_local * 3, n_local, flags=flags, **skw) for b in range(B)]
@@ -287,16 +272,20 @@ def main():
     barrier()
     launches0 = sctx.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    assign_ms, iters_run, pairs_per_launch = [], 0, 0.0
+    assign_ms, loop_ms, iters_run, pairs_per_launch = [], [], 0, 0.0
     sess_culled = D == 5 or n_total * k >= (1 << 27)  # mirrors cniic_kmeans_open: small RGB problems run the brute-force kernel
     t_wall0 = time.perf_counter()
     for i in range(K):
         flush.fill_(i & 0xff)           # evict the image from L2 between timed steps (untimed)
-        torch.cuda.synchronize()
+        if world > 1:
+            barrier()                   # every rank enters every timed step together (a late rank is waited for inside the exchange)
+        else:
+            torch.cuda.synchronize()
         ev[i][0].record(stream)
         st = one_step()
         ev[i][1].record(stream)
         assign_ms.append(st.assign_ms_avg)
+        loop_ms.append(st.device_ms)
         iters_run += st.iterations
         if os.environ.get("CNIIC_BENCH_DEBUG"):
             torch.cuda.synchronize()
@@ -330,20 +319,8 @@ def main():
             if kind == "rgb":
                 return sctx.kmeans_rgb(host_img, k, max_iters=ITERS, want_assign=False)
             return sctx.kmeans_xyrgb(host_img, k, max_iters=ITERS, want_assign=False)
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            r = e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_local * B * world * ITERS * K / float(tt.item()) / 1e6, "unit": "Mpx*iter/s",
-               "h2d_bytes_per_step": int(n_local * 3 * B), "d2h_bytes_per_step": int((k * 3 * 4 + k * 8 + 64) * B),
-               "api": "cniic_kmeans_rgb_batch" if B > 1 else ("cniic_kmeans_rgb" if kind == "rgb" else "cniic_kmeans_xyrgb")}
+        api_name = "cniic_kmeans_rgb_batch" if B > 1 else ("cniic_kmeans_rgb" if kind == "rgb" else "cniic_kmeans_xyrgb")
+        d2h_bytes = int((k * 3 * 4 + k * 8 + 64) * B)
     else:
         # sharded session: per step the shard is re-uploaded from pinned host memory and centroids/weights read back
         def e2e_step():
@@ -354,29 +331,29 @@ def main():
             out = s2.get(want_assign=False)
             s2.close()
             return out
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        api_name = "cniic_kmeans_open/reset/run/get (row-sharded session, host points)"
+        d2h_bytes = int(k * D * 4 + k * 8)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_total * ITERS * K / float(tt.item()) / 1e6, "unit": "Mpx*iter/s",
-               "h2d_bytes_per_step": int(n_local * 3), "d2h_bytes_per_step": int(k * D * 4 + k * 8),
-               "api": "cniic_kmeans_open/reset/run/get (row-sharded session, host points)"}
+    e2e = {"value": px_total * ITERS * K / float(tt.item()) / 1e6, "unit": "Mpx*iter/s",
+           "h2d_bytes_per_step": int(n_local * 3 * B), "d2h_bytes_per_step": d2h_bytes, "api": api_name}
 
     # the brute-force kernel (every pixel scores all k centroids) for reference: same results, no culling.
-    # Collective in the sharded case, so every rank runs it (before the non-zero ranks leave).
+    # Collective in the sharded case, so every rank runs it.
     one_step(cb._lib.KMEANS_NO_CULL, 1)
     stb = one_step(cb._lib.KMEANS_NO_CULL, 3)
-
+    ctx.device_free(d_img)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        return None
 
     # ---- roofline of the dominant kernel (fused assign+accumulate), measured live with CUDA events ----
     pk = peaks()
@@ -392,39 +369,127 @@ def main():
     for tp in (os.path.join(ROOT, "profiles", "r02_traffic.json"), os.path.join(ROOT, "profiles", "r01_traffic.json")):
         if os.path.exists(tp) and world == 1 and traffic is None:
             ent = json.load(open(tp)).get(kernel)
-            if ent and ent.get("workload") == args.workload:
+            if ent and ent.get("workload") == name:
                 traffic = ent["bytes"]  # dram bytes per launch from the committed ncu --set full capture of this kernel/workload
     roofline = build_roofline(D, n_local * B, k, a_ms, pairs_per_launch, pk, kernel, traffic, stb.assign_ms_avg, culled=sess_culled)  # one launch = B images
 
     cpu = None
-    if not args.no_cpu:
-        threads = 1
-        # bounded sample: whole crops until >= 10 s of single-thread CPU work have been timed
-        tot_px_iter, tot_dt, ncrops, descr = 0.0, 0.0, 0, ""
-        while tot_dt < 10.0 and ncrops < 8:
-            v, descr, dt = cpu_reference_leg(kind, w, h, k, blobs, SEED + 17 * ncrops, cpu_px, threads)
-            tot_px_iter += v * dt
-            tot_dt += dt
-            ncrops += 1
-        cpu = {"value": tot_px_iter / tot_dt, "unit": "Mpx*iter/s", "cores": threads, "kind": "port",
-               "sample": f"{ncrops} x ({descr})", "seconds": tot_dt}
+    if do_cpu:
+        # bounded sample, one host thread (the reference's K-means is single-threaded): bands until >= 10 s of CPU work are timed
+        tot_px_iter, tot_dt, nb, descr = 0.0, 0.0, 0, ""
+        while tot_dt < 10.0 and nb < 8:
+            v, descr, dt_ = cpu_reference_leg(name, 1, seed_off=nb)
+            tot_px_iter += v * dt_
+            tot_dt += dt_
+            nb += 1
+        cpu = {"value": tot_px_iter / tot_dt, "unit": "Mpx*iter/s", "cores": 1, "kind": "port",
+               "sample": f"{nb} x ({descr})", "seconds": tot_dt}
 
-    exchange = ("peer-memory all-reduce over NVLink fused into km_finalize" if os.environ.get("CNIIC_P2P", "1") == "1"
+    exchange = ("partial sums pushed over NVLink peer memory inside the multi-CTA update kernel" if os.environ.get("CNIIC_P2P", "1") == "1"
                 else "ncclAllReduce")
-    line = {"metric": "Mpixel*iter/s Lloyd K-means", "value": value, "unit": "Mpx*iter/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic",
+    step_ms = total_ms / K
+    return {"metric": "Mpixel*iter/s Lloyd K-means", "value": value, "unit": "Mpx*iter/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": scaling if world > 1 or name != "c3" else "strong",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": desc + ((f", {world} slabs of {w}x{h} (row-sharded {w}x{h_total}" if scaling == "weak" else
                                              f" (rows sharded over {world} GPUs") + ", u64 partial sums exchanged per iteration: " + exchange + ")"
                                             if world > 1 and not independent else ""),
-                       "k": k, "dims": D, "iters_per_step": ITERS, "pixels": int(px_total), "images_per_step_per_gpu": B,
+                       "name": name, "k": k, "dims": D, "iters_per_step": ITERS, "pixels": int(px_total), "images_per_step_per_gpu": B,
                        "parallelism": "1 GPU" if world == 1 else (f"{world} GPUs, independent batches of images" if independent else f"row-sharded x{world}"),
                        "l2": "512 MiB buffer written between timed steps (L2 flush); the image stays L2/HBM resident across the "
                              "iterations of one step, as the algorithm iterates over it"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches // K), "clocks": clocks,
+            "breakdown": {"assign_kernel_ms_avg": a_ms, "iteration_loop_ms_per_step": float(np.mean(loop_ms)),
+                          "session_setup_and_readback_ms_per_step": step_ms - float(np.mean(loop_ms)),
+                          "per_iteration_overhead_ms": (float(np.mean(loop_ms)) - ITERS * a_ms) / ITERS,
+                          "note": "rank 0's own CUDA events; overhead = update kernel + exchange + launch gaps per Lloyd iteration"},
             "iterations_run": iters_run, "wall_s": t_wall}
-    print(json.dumps(line), flush=True)
+
+
+def reference_arm(args, name, K, W):
+    """--impl reference: the reference's own CPU path for the workload (oracle port; the Rust crate cannot be built here), with all
+    the host threads it can use, on bounded samples.  Loads nothing of the product: images come from oracle/synth.py."""
+    kind, w, h, k, blobs, desc, scaling = WORKLOADS[name]
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 32))
+    vals, descr = [], ""
+    for i in range(W + K):
+        v, descr, dt = cpu_reference_leg(name, threads, seed_off=i)
+        if i >= W:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    single, sdesc, sdt = cpu_reference_leg(name, 1, seed_off=0)  # what kmeans.rs does for ONE image: one thread
+    line = {"impl": "reference", "metric": "Mpixel*iter/s Lloyd K-means", "value": value, "unit": "Mpx*iter/s",
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if name == "c3" else scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "name": name, "k": k, "iters_per_step": ITERS, "sample": descr},
+            "cpu_baseline": {"value": value, "unit": "Mpx*iter/s", "cores": threads, "kind": "port", "sample": descr},
+            "single_image_single_thread": {"value": single, "unit": "Mpx*iter/s", "cores": 1, "sample": sdesc, "seconds": sdt,
+                                           "note": "the reference clusters one image on one thread (kmeans.rs has no parallelism); the "
+                                                   "headline value above is one band per host thread (bench.rs:27)"},
+            "e2e": {"value": value, "unit": "Mpx*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["c5", "fill"],
+                    help="default: c3 (north-star sharded configuration, strong scaling) with c2 as `secondary` in the same line")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="default run: skip the secondary C2 object")
+    ap.add_argument("--batch", type=int, default=C4_BATCH, help="images per step per GPU (workload c4)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.workload in ("c5", "fill"):  # HBM-bound stage workloads (sharded without any collective): bench_stages.py
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "stage workloads report their CPU leg as cpu_baseline of the default arm"}))
+            return 0
+        import bench_stages
+        return bench_stages.run(args, args.workload, peaks, ClockSampler)
+    primary = args.workload or "c3"
+    with_secondary = args.workload is None and not args.no_secondary
+    W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    K = max(args.steps, 1)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        line = reference_arm(args, primary, K, W)
+        if with_secondary:
+            sec = reference_arm(args, "c2", 1, 0)
+            # the reference's real C2 path at the SAME config: one 4096x4096 image, unique colours with counts, one thread
+            v, d, dt = cpu_reference_leg("c2", 1, whole_image=True)
+            sec["same_config_single_image"] = {"value": v, "unit": "Mpx*iter/s", "cores": 1, "sample": d, "seconds": dt}
+            line["secondary"] = {kk: sec[kk] for kk in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "cpu_baseline",
+                                                        "single_image_single_thread", "same_config_single_image")}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
     if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctxs = {}
+    line = gpu_arm(args, primary, K, W, rank, world, local_rank, ctxs, do_cpu=not args.no_cpu)
+    if with_secondary:
+        sec = gpu_arm(args, "c2", max(3, min(K, 5)), 3, rank, world, local_rank, ctxs, do_cpu=False)
+        if rank == 0:
+            line["secondary"] = {kk: sec[kk] for kk in ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "config",
+                                                        "roofline", "e2e", "gpu_launches", "breakdown", "clocks")}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

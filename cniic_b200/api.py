@@ -268,6 +268,24 @@ class Context:
                                                 C.c_uint32(h), _ptr(out)))
         return out
 
+    def voronoi_fill_rows(self, cxy, crgb, w, h, y0, h_local):
+        """Rows [y0, y0 + h_local) of the fill: one rank's share of a row-sharded decode (no collective)."""
+        cxy = np.ascontiguousarray(cxy, dtype=np.uint32).reshape(-1, 2)
+        crgb = _u8(crgb).reshape(-1, 3)
+        out = np.zeros((h_local, w, 3), np.uint8)
+        d_cxy, d_crgb, d_out = self.device_alloc(cxy.nbytes), self.device_alloc(crgb.nbytes), self.device_alloc(max(16, out.nbytes))
+        try:
+            self.h2d(d_cxy, cxy)
+            self.h2d(d_crgb, crgb)
+            self.check(self._lib.cniic_voronoi_fill_device(self.h, C.c_void_p(d_cxy), C.c_void_p(d_crgb), C.c_uint32(len(cxy)), C.c_uint32(w),
+                                                           C.c_uint32(h), C.c_uint32(y0), C.c_uint32(h_local), C.c_void_p(d_out)))
+            if out.nbytes:
+                self.d2h(out, d_out)
+        finally:
+            for p in (d_cxy, d_crgb, d_out):
+                self.device_free(p)
+        return out
+
     # ---- hilbert::iter / linearize (hilbert.rs:34-43), DiffStream (hilbertc.rs:449-477) ----
     def hilbert_xy(self, w, h):
         out = np.zeros((w * h, 2), np.uint32)

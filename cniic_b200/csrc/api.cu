@@ -163,16 +163,18 @@ int cniic_nccl_allgather_bytes(cniic_ctx *ctx, const void *d_send, void *d_recv,
 }
 
 // ---- peer-memory exchange region (CUDA IPC between the per-GPU processes) ---------------------------------------------------
+// layout (kmeans.cu: p2p_flags_off / p2p_xcount_off): recv[2 parities][world source ranks][P2P_SUMS_MAX u64] | u32 flags[world][64] |
+// u32 exchange counter.  3.1 MB for 8 ranks.
 static const size_t P2P_SUMS_MAX_HOST = CNIIC_MAX_K * 6 + 8;
-static const size_t P2P_REGION_BYTES = 2 * P2P_SUMS_MAX_HOST * 8 + 4096;  // two ping-pong buffers + arrival flags
+static size_t p2p_region_bytes(int world) { return 2 * size_t(world) * P2P_SUMS_MAX_HOST * 8 + size_t(world) * 64 * 4 + 256; }
 
 extern "C" int cniic_ctx_p2p_export(cniic_ctx *ctx, uint8_t out_handle[64]) {
     if (!ctx || !out_handle) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (!ctx->p2p_local) {
         void *p = nullptr;
-        CU_TRY(ctx, cudaMalloc(&p, P2P_REGION_BYTES));
-        CU_TRY(ctx, cudaMemset(p, 0, P2P_REGION_BYTES));
+        CU_TRY(ctx, cudaMalloc(&p, p2p_region_bytes(ctx->world)));
+        CU_TRY(ctx, cudaMemset(p, 0, p2p_region_bytes(ctx->world)));
         ctx->p2p_local = static_cast<unsigned long long *>(p);
     }
     cudaIpcMemHandle_t h;

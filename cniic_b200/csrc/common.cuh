@@ -31,12 +31,11 @@ struct cniic_ctx {
     std::vector<Block> cache;
     std::vector<void *> pinned_free;  // 256-byte pinned host slots
     std::vector<cudaEvent_t> event_pool;
-    // peer-memory exchange (multi-GPU): my IPC region, the peer-mapped bases of all ranks (device table), sequence number
+    // peer-memory exchange (multi-GPU): my IPC region (receive areas, flags, exchange counter), the peer-mapped bases of all ranks (device table)
     unsigned long long *p2p_local = nullptr;
     unsigned long long **p2p_peer_table = nullptr;  // device array [world]
     std::vector<void *> p2p_opened;
     bool p2p_ready = false;
-    uint32_t p2p_seq = 0;
     std::vector<uint8_t> pending_stream;  // cniic_codec_encode result that did not fit the caller's buffer (cniic_codec_encode_fetch)
     bool has_pending_stream = false;
     uint32_t *hist_bins[2] = {nullptr, nullptr};  // persistent dense histogram bins (+ page flags), all zero between calls

@@ -36,7 +36,7 @@ constexpr int TILE = THREADS * PX;
 constexpr int DUMMY3 = -(1 << 19);  // bias of padding entries, D = 3 (real scores > -97538)
 constexpr int DUMMY5 = -(1 << 29);  // bias of padding entries, D = 5 (real scores > -2.7e8)
 constexpr int GSHIFT = 10;          // D = 3: bits of the group field packed under the key
-constexpr uint32_t P2P_SUMS_MAX = CNIIC_MAX_K * 6 + 8;  // u64 slots per ping-pong buffer of the exchange region
+constexpr uint32_t P2P_SUMS_MAX = CNIIC_MAX_K * 6 + 8;  // u64 slots per (parity, source rank) receive area of the exchange region
 constexpr int FLUSH_TILES = 64;     // D = 5: flush u32 shared accumulators to global every 64 tiles
 
 struct KmState {
@@ -50,6 +50,9 @@ struct KmState {
     uint32_t pad;
     unsigned long long moved_last, moved_total;
     unsigned long long pairs;  // point-centroid pairs actually scored by the assign kernels since reset
+    // multi-CTA update kernel: reduced `moved` counter of the iteration, empty clusters counted by the slices, arrival ticket
+    unsigned long long moved_red;
+    uint32_t nempty_acc, ticket;
 };
 
 struct KmDev {
@@ -78,14 +81,11 @@ struct KmDev {
     const uint32_t *pts_sorted;
     const uint32_t *perm;
     const uint32_t *wts_sorted;
-    // peer-memory all-reduce fused into km_finalize (multi-GPU, one process per GPU)
+    // peer-memory exchange fused into the update kernel (multi-GPU, one process per GPU)
     int brute;                                 // 1: the brute-force kernels run, so km_finalize must build the parity-class scan table
     int p2p;                                   // 1: sums live in the IPC exchange region, no NCCL call
     int my_rank;
-    uint32_t seq;                              // global iteration sequence number of this launch
     unsigned long long *const *peer_base;      // [world] base of every rank's exchange region (peer-mapped)
-    unsigned long long *sums_other;            // my other ping-pong buffer (zeroed here for the next iteration)
-    unsigned long long *sums_red;              // local reduced sums the rest of finalize reads
     const uint2 *tile_box;  // per 2048-point tile of the sorted copy: {bytewise min, bytewise max} of the packed colours
     const uint4 *wseg;      // culled D = 3, v2: per 256-point warp segment {box min, box max, sum r | sum g << 16, sum b | count << 16}
     const unsigned long long *wseg64;  // weighted points: per warp segment {sum r*w, sum g*w, sum b*w, sum w}
@@ -1542,7 +1542,7 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// init + finalize (single CTA)
+// init + update (kmeans.rs:61-143)
 // ------------------------------------------------------------------------------------------------------------
 
 template <int D>
@@ -1596,74 +1596,161 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *s_warp, uint
     return before + __popc(bal & ((1u << lane) - 1));
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// update step (kmeans.rs:110-143) = exchange + integer means + table rebuild, one launch per Lloyd iteration.
+//
+// init_mode 0 (an iteration) runs on `ncta` = ceil(k / UPD_SLICE) CTAs.  CTA j owns the clusters of slice j:
+//   1. multi-GPU (peer memory): it PUSHES its slice of this rank's partial sums into every rank's receive
+//      area recv[parity][my_rank] (plain 128-bit stores over NVLink, then a system fence and one flag per destination rank), spins
+//      on the flags the other ranks set for slice j in its own memory, and adds the `world` received copies in rank order --
+//      one one-way NVLink trip instead of the flag round trip + remote loads a pulled all-reduce needs, and every slice is
+//      exchanged by its own CTA concurrently.  `parity` alternates with the number of exchanges this context has really made
+//      (xcount, kept on the device: launches that exit early because the run converged do not advance it), so a rank that is one
+//      iteration ahead writes the other half; it cannot be two ahead because its next exchange needs this rank's next push.
+//   2. it divides (truncating u64 means), writes weights / centroids / the per-centroid arrays of its slice, zeroes its slice of
+//      the local partial sums for the next iteration and counts empty clusters.
+// The CTA that finishes last (ticket) closes the iteration: empty-cluster repair (rare), brute-force scan table if that kernel
+// runs, state.  init_mode 1 (session start) and 2 (resume after the host repaired empty clusters of a sharded run) run on one CTA.
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t UPD_SLICE = 256;     // clusters per CTA slice of the update kernel
+constexpr uint32_t UPD_FLAGS_MAX = 64;  // flag slots per source rank (>= CNIIC_MAX_K / UPD_SLICE)
+
+__host__ __device__ inline uint32_t upd_ctas_of(uint32_t k) { return (k + UPD_SLICE - 1) / UPD_SLICE; }
+
+// exchange region of one rank (u64 units): recv[2][world][P2P_SUMS_MAX] | flags: u32[world][UPD_FLAGS_MAX] | xcount u32
+__host__ __device__ inline size_t p2p_flags_off(int world) { return size_t(2) * world * P2P_SUMS_MAX; }
+__host__ __device__ inline size_t p2p_xcount_off(int world) { return p2p_flags_off(world) + size_t(world) * UPD_FLAGS_MAX / 2; }
+
 template <int D>
-__device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode) {
+__device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode, const uint32_t cta, const uint32_t ncta) {
     constexpr int DW = D + 1;
     constexpr int G = D == 5 ? G5 : G3;
     constexpr int DUMMY = D == 5 ? DUMMY5 : DUMMY3;
     if (init_mode == 0 && (d.st->done || d.st->dist_empty)) return;
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_nempty, s_victim, s_m;
+    __shared__ uint32_t s_nempty, s_victim, s_m, s_last, s_timeout;
     __shared__ uint16_t s_empty[CNIIC_MAX_K];
     __shared__ uint32_t s_found[CNIIC_MAX_K];
+    __shared__ ulonglong2 s_red[UPD_SLICE * DW / 2];
     const uint32_t k = d.k;
     const int tid = threadIdx.x;
     unsigned long long moved = 0;
+    const int rgb0 = D == 5 ? 2 : 0;
 
-    const unsigned long long *rs = d.p2p ? d.sums_red : d.sums;
-    if (init_mode != 2 && d.p2p) {
-        // ---- barrier over peer memory: publish my arrival for sequence number d.seq, wait for every rank ----
-        // (init_mode 0: the assign kernel of this iteration has completed, so my partial sums are in my exchange buffer;
-        //  init_mode 1: every rank has finished all work of the previous session)
-        volatile uint32_t *arrived = reinterpret_cast<volatile uint32_t *>(d.peer_base[d.my_rank] + 2 * P2P_SUMS_MAX);
-        if (tid < d.world) {
-            __threadfence_system();
-            uint32_t *remote = reinterpret_cast<uint32_t *>(d.peer_base[tid] + 2 * P2P_SUMS_MAX);
-            // push my arrival into every rank's flag array: a system-scope atomic is not a posted write, it completes before
-            // this thread starts to spin (a plain NVLink store could sit in a write buffer while every rank waits)
-            atomicExch_system(remote + d.my_rank, d.seq);
-            __threadfence_system();
-            unsigned long long spins = 0;
-            while (int(arrived[tid] - d.seq) < 0) {
-                if (++spins > (1ull << 25)) { d.st->dist_empty = 2; break; }  // never hang the GPU: report and carry on
+    if (init_mode == 0) {
+        const bool xch = d.p2p && d.world > 1;
+        uint32_t seq = 0;
+        unsigned long long *my_base = nullptr;
+        if (xch) {
+            my_base = d.peer_base[d.my_rank];
+            seq = *reinterpret_cast<volatile uint32_t *>(my_base + p2p_xcount_off(d.world)) + 1u;  // bumped by the closing CTA only
+        }
+        const size_t par_off = size_t(seq & 1u) * d.world * P2P_SUMS_MAX;
+        if (tid == 0) { s_nempty = 0; s_timeout = 0; }
+        const uint32_t nslices = upd_ctas_of(k);
+        const bool owns_moved = cta == (nslices - 1) % ncta;  // the CTA of the last slice also carries the `moved` counter
+        if (xch) {
+            // ---- push my slices of this rank's partial sums to every rank (including myself), then one flag per destination ----
+            for (uint32_t sl = cta; sl < nslices; sl += ncta) {
+                const uint32_t c0 = sl * UPD_SLICE, ncl = min(UPD_SLICE, k - c0);
+                const uint32_t nchunk = ncl * DW / 2;  // DW is even: whole 128-bit chunks, 16-byte aligned (c0 * DW * 8)
+                ulonglong2 *mine = reinterpret_cast<ulonglong2 *>(d.sums + size_t(c0) * DW);
+                for (uint32_t i = tid; i < nchunk; i += 1024) {
+                    const ulonglong2 v = mine[i];
+                    mine[i] = make_ulonglong2(0ull, 0ull);  // ready for the next iteration's accumulation
+                    for (int r = 0; r < d.world; r++)
+                        reinterpret_cast<ulonglong2 *>(d.peer_base[r] + par_off + size_t(d.my_rank) * P2P_SUMS_MAX + size_t(c0) * DW)[i] = v;
+                }
             }
-            __threadfence_system();
+            if (owns_moved && tid == 0) {
+                const unsigned long long v = d.sums[size_t(k) * DW];
+                d.sums[size_t(k) * DW] = 0ull;
+                for (int r = 0; r < d.world; r++) (d.peer_base[r] + par_off + size_t(d.my_rank) * P2P_SUMS_MAX)[size_t(k) * DW] = v;
+            }
+            __threadfence_system();  // my stores are performed at every destination before ...
+            __syncthreads();
+            if (tid < d.world) {     // ... the flag that announces them (monotonic exchange number; a fire-and-forget reduction)
+                uint32_t *remote = reinterpret_cast<uint32_t *>(d.peer_base[tid] + p2p_flags_off(d.world)) + size_t(d.my_rank) * UPD_FLAGS_MAX + cta;
+                atomicMax_system(remote, seq);
+                volatile uint32_t *arrived = reinterpret_cast<volatile uint32_t *>(my_base + p2p_flags_off(d.world)) + size_t(tid) * UPD_FLAGS_MAX + cta;
+                const long long t0 = clock64();
+                while (int(*arrived - seq) < 0) {
+                    if (clock64() - t0 > (4ll << 30)) { s_timeout = 1; break; }  // ~2 s: never hang the GPU, report and carry on
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+            if (s_timeout && tid == 0) d.st->dist_empty = 2;
+        }
+        // ---- reduce (rank order), divide, per-centroid arrays of my slices ----
+        for (uint32_t sl = cta; sl < nslices; sl += ncta) {
+            const uint32_t c0 = sl * UPD_SLICE, ncl = min(UPD_SLICE, k - c0);
+            const uint32_t nchunk = ncl * DW / 2;
+            __syncthreads();  // s_red of the previous slice has been consumed
+            if (xch) {
+                for (uint32_t i = tid; i < nchunk; i += 1024) {
+                    ulonglong2 acc = make_ulonglong2(0ull, 0ull);
+                    for (int r = 0; r < d.world; r++) {
+                        const ulonglong2 v = __ldcv(reinterpret_cast<const ulonglong2 *>(my_base + par_off + size_t(r) * P2P_SUMS_MAX + size_t(c0) * DW) + i);
+                        acc.x += v.x; acc.y += v.y;
+                    }
+                    s_red[i] = acc;
+                }
+            } else {
+                ulonglong2 *mine = reinterpret_cast<ulonglong2 *>(d.sums + size_t(c0) * DW);
+                for (uint32_t i = tid; i < nchunk; i += 1024) { s_red[i] = mine[i]; mine[i] = make_ulonglong2(0ull, 0ull); }
+            }
+            __syncthreads();
+            const unsigned long long *rs = reinterpret_cast<const unsigned long long *>(s_red);
+            for (uint32_t j = tid; j < ncl; j += 1024) {
+                const uint32_t c = c0 + j;
+                const unsigned long long wsum = rs[j * DW + D];
+                d.weights[c] = wsum;
+                if (wsum) {
+                    int32_t v[D];
+                    uint32_t nrm = 0;
+                    for (int q = 0; q < D; q++) { v[q] = int32_t(rs[j * DW + q] / wsum); d.cen[c * D + q] = v[q]; nrm += uint32_t(v[q] * v[q]); }
+                    if (!d.brute) {  // culled kernels only need the per-centroid arrays in id order
+                        const uint32_t cpk = uint32_t(v[rgb0]) | (uint32_t(v[rgb0 + 1]) << 8) | (uint32_t(v[rgb0 + 2]) << 16);
+                        d.g_cpk[c] = cpk;
+                        d.g_nrm[c] = nrm;
+                        if (D == 5) {
+                            const uint32_t cxy = uint32_t(v[0]) | (uint32_t(v[1]) << 16);
+                            d.g_cxy[c] = cxy;
+                            d.g_ent[c] = make_uint4(cpk, cxy, nrm, 0u);
+                        }
+                    }
+                } else {
+                    atomicAdd(&s_nempty, 1u);
+                }
+            }
+        }
+        if (owns_moved && tid == 0) {
+            unsigned long long m = 0;
+            if (xch) {
+                for (int r = 0; r < d.world; r++) m += __ldcv(my_base + par_off + size_t(r) * P2P_SUMS_MAX + size_t(k) * DW);
+            } else {
+                m = d.sums[size_t(k) * DW];
+                d.sums[size_t(k) * DW] = 0ull;
+            }
+            d.st->moved_red = m;
+        }
+        // ---- the CTA that finishes last closes the iteration ----
+        __syncthreads();
+        if (tid == 0) {
+            if (s_nempty) atomicAdd(&d.st->nempty_acc, s_nempty);
+            __threadfence();
+            s_last = atomicAdd(&d.st->ticket, 1u) == ncta - 1 ? 1u : 0u;
         }
         __syncthreads();
-    }
-    if (init_mode != 0 && d.p2p) {
-        // (re)start of a session or resume after a repair: launches that exit early (converged / halted) still advance the
-        // sequence number, so the next iteration may land on either ping-pong buffer -- clear both.  Safe: a barrier (above,
-        // or the repair's all-gather) guarantees that no rank still reads them.
-        unsigned long long *mine = d.peer_base[d.my_rank];
-        for (uint32_t i = tid; i < 2 * P2P_SUMS_MAX; i += 1024) mine[i] = 0ull;
-        __syncthreads();
-    }
-    if (init_mode == 0 && d.p2p) {
-        // ---- all-reduce: sum every rank's partials in rank order ----
-        __syncthreads();
-        const uint32_t len = k * DW + 1;
-        const size_t boff = size_t(d.seq & 1) * P2P_SUMS_MAX;
-        // 128-bit loads, four independent chunks in flight per thread and rank (NVLink latency is ~2 us per round trip)
-        const uint32_t len2 = (len + 1) / 2;  // in ulonglong2 units; buffers are padded, so reading one slot past len is safe
-        for (uint32_t i0 = tid; i0 < len2; i0 += 4 * 1024) {
-            ulonglong2 acc[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) acc[u] = make_ulonglong2(0ull, 0ull);
-            for (int r = 0; r < d.world; r++) {  // fixed rank order: deterministic (and integers anyway)
-                const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(d.peer_base[r] + boff);
-                ulonglong2 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = (i0 + u * 1024 < len2) ? __ldcv(src + i0 + u * 1024) : make_ulonglong2(0ull, 0ull);
-#pragma unroll
-                for (int u = 0; u < 4; u++) { acc[u].x += v[u].x; acc[u].y += v[u].y; }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (i0 + u * 1024 < len2) reinterpret_cast<ulonglong2 *>(d.sums_red)[i0 + u * 1024] = acc[u];
+        if (!s_last) return;
+        __threadfence();
+        if (tid == 0) {
+            s_nempty = *reinterpret_cast<volatile uint32_t *>(&d.st->nempty_acc);
+            d.st->nempty_acc = 0; d.st->ticket = 0;
+            if (xch) *reinterpret_cast<volatile uint32_t *>(my_base + p2p_xcount_off(d.world)) = seq;  // one more exchange done
         }
-        // every rank has passed iteration seq-1, so nobody reads my other buffer any more: clear it for iteration seq+1
-        for (uint32_t i = tid; i < P2P_SUMS_MAX; i += 1024) d.sums_other[i] = 0ull;
+        moved = *reinterpret_cast<volatile unsigned long long *>(&d.st->moved_red);
         __syncthreads();
     }
     if (init_mode == 2) {  // resume after the host repaired the empty clusters of a sharded run
@@ -1671,34 +1758,23 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode) {
         moved = d.st->moved_last;
         __syncthreads();
     }
+    if (init_mode == 1 && tid == 0) s_nempty = 0;
+    bool rebuild_all = init_mode != 0;  // per-centroid arrays of ALL clusters (the slices above only cover an ordinary iteration)
     if (init_mode == 0) {
-        if (tid == 0) s_nempty = 0;
-        __syncthreads();
-        for (uint32_t c = tid; c < k; c += 1024) {
-            const unsigned long long wsum = rs[c * DW + D];
-            d.weights[c] = wsum;
-            if (wsum) {
-                for (int j = 0; j < D; j++) d.cen[c * D + j] = int32_t(rs[c * DW + j] / wsum);
-            } else {
-                atomicAdd(&s_nempty, 1u);
-            }
-        }
-        moved = rs[k * DW];
-        __syncthreads();
         const uint32_t nempty = s_nempty;
         if (nempty && d.world > 1) {
-            // sharded points: the members with the lowest global indices live on several ranks.  Halt here (nothing else is
-            // modified; later launches of the batch exit at once); cniic_kmeans_run repairs on the host and resumes.
-            // (`moved` is parked in the state: later all-reduce calls of the batch still run and re-add the sums buffer)
+            // sharded points: the members with the lowest global indices live on several ranks.  Halt here (later launches of
+            // the batch exit at once); cniic_kmeans_run repairs on the host and resumes with init_mode 2.
             if (tid == 0) { d.st->dist_empty = 1; d.st->n_empty_last = nempty; d.st->moved_last = moved; }
             return;
         } else if (nempty) {
+            rebuild_all = true;
             // deterministic stand-in for kmeans.rs:117-134 (see header): heaviest cluster = victim
             if (tid == 0) {
                 uint32_t ne = 0, victim = 0;
                 unsigned long long bw = 0;
                 for (uint32_t c = 0; c < k; c++) {
-                    const unsigned long long wsum = d.weights[c];
+                    const unsigned long long wsum = __ldcg(&d.weights[c]);
                     if (!wsum) s_empty[ne++] = uint16_t(c);
                     else if (wsum > bw) { bw = wsum; victim = c; }
                 }
@@ -1747,13 +1823,11 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode) {
         __syncthreads();
     }
 
-    if (!d.brute) {
-        // culled kernels only need the per-centroid arrays in id order
+    if (!d.brute && rebuild_all) {
         for (uint32_t c = tid; c < k; c += 1024) {
             int32_t v[D];
             uint32_t nrm = 0;
-            for (int j = 0; j < D; j++) { v[j] = d.cen[c * D + j]; nrm += uint32_t(v[j] * v[j]); }
-            const int rgb0 = D == 5 ? 2 : 0;
+            for (int j = 0; j < D; j++) { v[j] = __ldcg(&d.cen[c * D + j]); nrm += uint32_t(v[j] * v[j]); }
             d.g_cpk[c] = uint32_t(v[rgb0]) | (uint32_t(v[rgb0 + 1]) << 8) | (uint32_t(v[rgb0 + 2]) << 16);
             d.g_nrm[c] = nrm;
             if (D == 5) {
@@ -1773,14 +1847,13 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode) {
             uint32_t nrm = 0;
             bool flag = false;
             if (c < k) {
-                for (int j = 0; j < D; j++) { v[j] = d.cen[c * D + j]; nrm += uint32_t(v[j] * v[j]); }
+                for (int j = 0; j < D; j++) { v[j] = __ldcg(&d.cen[c * D + j]); nrm += uint32_t(v[j] * v[j]); }
                 flag = int(nrm & 1) == cls;
             }
             uint32_t tot;
             const uint32_t r = block_rank(flag, s_warp, &tot);
             if (flag) {
                 const uint32_t e = start + placed + r;
-                const int rgb0 = D == 5 ? 2 : 0;
                 d.t_cpk[e] = uint32_t(v[rgb0]) | (uint32_t(v[rgb0 + 1]) << 8) | (uint32_t(v[rgb0 + 2]) << 16);
                 if (D == 5) d.t_cxy[e] = uint32_t(v[0]) | (uint32_t(v[1]) << 16);
                 d.t_bias[e] = -int(nrm >> 1);
@@ -1804,12 +1877,13 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode) {
             d.st->ngroups = (n0 + G - 1) / G + (placed + G - 1) / G;
         }
     }
-    if (!d.p2p)
+    if (init_mode == 1)  // the partial sums of a fresh session start from zero (an iteration leaves them zeroed)
         for (uint32_t i = tid; i < k * DW + 1; i += 1024) d.sums[i] = 0ull;
     if (tid == 0) {
         if (init_mode == 1) {
             d.st->iter = 0; d.st->done = 0; d.st->empty_events = 0; d.st->n_empty_last = 0; d.st->dist_empty = 0;
             d.st->moved_last = 0; d.st->moved_total = 0; d.st->pairs = 0;
+            d.st->ticket = 0; d.st->nempty_acc = 0; d.st->moved_red = 0;
         } else {
             d.st->iter += 1;
             d.st->moved_last = moved;
@@ -1817,7 +1891,7 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode) {
             d.st->n_empty_last = s_nempty;
             d.st->empty_events += s_nempty;
             if (moved == 0) d.st->done = 1;
-            d.st->dist_empty = 0;
+            if (d.st->dist_empty != 2) d.st->dist_empty = 0;
         }
     }
 }
@@ -1838,7 +1912,7 @@ __global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull(KmDev d) { km
 __global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull2(KmDev d) { km_assign_xyrgb_cull2_body(d); }
 __global__ void km_init_assign(KmDev d) { km_init_assign_body(d); }
 template <int D> __global__ void km_init_centroids(KmDev d) { km_init_centroids_body<D>(d); }
-template <int D> __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) { km_finalize_body<D>(d, init_mode); }
+template <int D> __global__ void __launch_bounds__(1024) km_finalize(KmDev d, int init_mode) { km_finalize_body<D>(d, init_mode, blockIdx.x, gridDim.x); }
 
 // A descriptor read from memory carries generic pointers: without help the compiler emits address-space checks around every
 // atomic (and a dead shared-memory compare-and-swap path).  Every pointer of a KmDev points to global memory.
@@ -1848,7 +1922,7 @@ __device__ __forceinline__ KmDev km_load_desc(const KmDev *__restrict__ batch, u
     KM_GLOBAL(d.rgb); KM_GLOBAL(d.wts); KM_GLOBAL(d.assign); KM_GLOBAL(d.t_cpk); KM_GLOBAL(d.t_cxy); KM_GLOBAL(d.t_bias); KM_GLOBAL(d.t_id);
     KM_GLOBAL(d.t_pos); KM_GLOBAL(d.g_cpk); KM_GLOBAL(d.g_cxy); KM_GLOBAL(d.g_nrm); KM_GLOBAL(d.g_ent); KM_GLOBAL(d.sc_list); KM_GLOBAL(d.sc_count);
     KM_GLOBAL(d.pts_sorted); KM_GLOBAL(d.perm); KM_GLOBAL(d.wts_sorted); KM_GLOBAL(d.tile_box); KM_GLOBAL(d.wseg); KM_GLOBAL(d.wseg64);
-    KM_GLOBAL(d.sums); KM_GLOBAL(d.cen); KM_GLOBAL(d.weights); KM_GLOBAL(d.st); KM_GLOBAL(d.sums_red); KM_GLOBAL(d.sums_other);
+    KM_GLOBAL(d.sums); KM_GLOBAL(d.cen); KM_GLOBAL(d.weights); KM_GLOBAL(d.st);
 #undef KM_GLOBAL
     return d;
 }
@@ -1865,7 +1939,7 @@ __global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull_batch(const K
 __global__ void __launch_bounds__(THREADS, 3) km_assign_xyrgb_cull2_batch(const KmDev *__restrict__ batch) { km_assign_xyrgb_cull2_body(km_load_desc(batch, blockIdx.y)); }
 __global__ void km_init_assign_batch(const KmDev *__restrict__ batch) { km_init_assign_body(km_load_desc(batch, blockIdx.y)); }
 template <int D> __global__ void km_init_centroids_batch(const KmDev *__restrict__ batch) { km_init_centroids_body<D>(km_load_desc(batch, blockIdx.y)); }
-template <int D> __global__ void __launch_bounds__(1024) km_finalize_batch(const KmDev *__restrict__ batch, int init_mode) { km_finalize_body<D>(km_load_desc(batch, blockIdx.x), init_mode); }
+template <int D> __global__ void __launch_bounds__(1024) km_finalize_batch(const KmDev *__restrict__ batch, int init_mode) { km_finalize_body<D>(km_load_desc(batch, blockIdx.x), init_mode, 0u, 1u); }
 // the states of a batch, gathered into one array for a single device-to-host copy
 __global__ void km_gather_states(const KmDev *__restrict__ batch, uint32_t count, KmState *out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[i] = *batch[i].st;
@@ -1993,8 +2067,9 @@ static int km_launch_assign(cniic_kmeans *km) {
 
 static int km_launch_finalize(cniic_kmeans *km, int init_mode) {
     cniic_ctx *ctx = km->ctx;
-    if (km->D == 5) km_finalize<5><<<1, 1024, 0, ctx->stream>>>(km->dev, init_mode);
-    else km_finalize<3><<<1, 1024, 0, ctx->stream>>>(km->dev, init_mode);
+    const unsigned ncta = init_mode == 0 ? upd_ctas_of(km->desc.k) : 1u;  // an iteration: one CTA per 256-cluster slice
+    if (km->D == 5) km_finalize<5><<<ncta, 1024, 0, ctx->stream>>>(km->dev, init_mode);
+    else km_finalize<3><<<ncta, 1024, 0, ctx->stream>>>(km->dev, init_mode);
     km->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
@@ -2058,7 +2133,6 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     const size_t o_cpk = take(KP * 4), o_cxy = take(KP * 4), o_bias = take(KP * 4), o_id = take(KP * 2), o_pos = take(k * 2);
     const size_t o_sums = take((size_t(k) * (D + 1) + 1) * 8), o_cen = take(size_t(k) * D * 4), o_w = take(size_t(k) * 8);
     const size_t o_st = take(sizeof(KmState));
-    const size_t o_red = take((size_t(k) * (D + 1) + 2) * 8);
     const uint32_t super_x = D == 5 ? (desc->w + SW - 1) / SW : 0, super_y = D == 5 ? (desc->h_local + SH - 1) / SH : 0;
     const size_t o_gcpk = take(size_t(k) * 4), o_gcxy = take(size_t(k) * 4), o_gnrm = take(size_t(k) * 4), o_gent = take(size_t(k) * 16);
     const size_t o_sclist = take(size_t(super_x) * super_y * k * 2), o_sccount = take(size_t(super_x) * super_y * 4 + 4);
@@ -2090,7 +2164,6 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     dv.cen = reinterpret_cast<int32_t *>(p + o_cen);
     dv.weights = reinterpret_cast<unsigned long long *>(p + o_w);
     dv.st = reinterpret_cast<KmState *>(p + o_st);
-    dv.sums_red = reinterpret_cast<unsigned long long *>(p + o_red);
     dv.p2p = ctx->p2p_ready ? 1 : 0;
     dv.my_rank = ctx->rank;
     dv.peer_base = ctx->p2p_peer_table;
@@ -2229,7 +2302,6 @@ extern "C" int cniic_kmeans_reset(cniic_kmeans *km, const int32_t *host_init_cen
     }
     CU_TRY(ctx, cudaGetLastError());
     km->iter_seen = 0;
-    if (km->dev.p2p) km->dev.seq = ++ctx->p2p_seq;  // the init pass is a barrier over peer memory (all ranks left the previous session)
     const int rc_fin = km_launch_finalize(km, 1);
     km_report_launches(km);
     return rc_fin;
@@ -2296,37 +2368,37 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
     CU_TRY(ctx, cudaEventRecord(km->ev0, ctx->stream));
     uint32_t issued = 0;            // assign launches of this call (indexes the profiling events)
     uint32_t done_iters = 0;        // iterations completed by this call (state.iter - iter_seen)
+    // assign launches timed with CUDA events (cniic_kmeans_stats.assign_ms_avg): every one of the first PROF on a single GPU; only
+    // the first two of a sharded run, where an event between two 30 us kernels is a measurable share of the iteration
+    const uint32_t prof_limit = dist ? 2u : (uint32_t)cniic_kmeans::PROF;
+    uint32_t timed = 0;
     for (;;) {
-        uint32_t batch = 8;  // kernels (and the all-reduce) early-exit / are harmless once `done` or a halt is set
-        if (max_iters) batch = std::min(batch, max_iters - done_iters);
+        // kernels (and the all-reduce) exit at once when `done` or a halt is set, so a whole batch is enqueued without looking at
+        // the state: all of max_iters when it is given (ONE host synchronisation per run), else batches of 8
+        uint32_t batch = max_iters ? std::min<uint32_t>(64u, max_iters - done_iters) : 8u;
         for (uint32_t b = 0; b < batch; b++) {
-            const bool prof = issued < (uint32_t)cniic_kmeans::PROF;
-            if (km->dev.p2p) {  // ping-pong exchange buffers, selected by the global sequence number
-                km->dev.seq = ++ctx->p2p_seq;
-                km->dev.sums = ctx->p2p_local + size_t(km->dev.seq & 1) * P2P_SUMS_MAX;
-                km->dev.sums_other = ctx->p2p_local + size_t((km->dev.seq + 1) & 1) * P2P_SUMS_MAX;
-            }
+            const bool prof = issued < prof_limit;
             if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * issued], ctx->stream));
             ST_TRY(km_launch_assign(km));
-            if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * issued + 1], ctx->stream));
+            if (prof) { CU_TRY(ctx, cudaEventRecord(km->pev[2 * issued + 1], ctx->stream)); timed = issued + 1; }
             issued++;
             if (dist && !km->dev.p2p) ST_TRY(cniic_nccl_allreduce_u64(ctx, km->dev.sums, size_t(km->desc.k) * DW + 1));
             ST_TRY(km_launch_finalize(km, 0));
         }
+        CU_TRY(ctx, cudaEventRecord(km->ev1, ctx->stream));  // complete once the stream has been synchronised below
         CU_TRY(ctx, cudaMemcpyAsync(km->h_state, km->dev.st, sizeof(KmState), cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         if (km->h_state->dist_empty == 2)
-            return cniic_set_error(ctx, CNIIC_ERR_NCCL, "peer-memory all-reduce timed out waiting for another rank");
+            return cniic_set_error(ctx, CNIIC_ERR_NCCL, "peer-memory exchange timed out waiting for another rank");
         if (km->h_state->dist_empty == 1) {
             ST_TRY(km->D == 5 ? km_repair_dist<5>(km) : km_repair_dist<3>(km));
+            CU_TRY(ctx, cudaEventRecord(km->ev1, ctx->stream));
             CU_TRY(ctx, cudaMemcpyAsync(km->h_state, km->dev.st, sizeof(KmState), cudaMemcpyDeviceToHost, ctx->stream));
             CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         }
         done_iters = km->h_state->iter - km->iter_seen;
         if (km->h_state->done || (max_iters && done_iters >= max_iters)) break;
     }
-    CU_TRY(ctx, cudaEventRecord(km->ev1, ctx->stream));
-    CU_TRY(ctx, cudaEventSynchronize(km->ev1));
     float ms = 0.f;
     CU_TRY(ctx, cudaEventElapsedTime(&ms, km->ev0, km->ev1));
     km_report_launches(km);
@@ -2340,7 +2412,7 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
         stats->gpu_launches = km->launches - launches0;
         stats->device_ms = ms;
         // average duration of the fused assign+accumulate kernel over the launches that actually ran
-        const uint32_t np = std::min<uint32_t>(s.iter - km->iter_seen, (uint32_t)cniic_kmeans::PROF);
+        const uint32_t np = std::min<uint32_t>(s.iter - km->iter_seen, timed);
         float acc = 0.f;
         for (uint32_t i = 0; i < np; i++) {
             float t = 0.f;

@@ -34,6 +34,4 @@ bench.C4_BATCH = 3
 bench_stages.SIZES = {"c5": (256, 256, 64), "fill": (192, 96, 64)}
 if "--batch" not in sys.argv:
     sys.argv += ["--batch", "3"]
-if "--cpu-px" not in sys.argv:
-    sys.argv += ["--cpu-px", "4096"]
 sys.exit(bench.main())

@@ -263,8 +263,10 @@ static inline int emu_ptx_dp4a_u32_u32(unsigned a, unsigned b, int c) { return (
 static inline int emu_ptx_dp2a_lo_s32_u32(unsigned a, unsigned b, int c) {  // c + a.s16[0]*b.u8[0] + a.s16[1]*b.u8[1]
     return c + int(int16_t(a & 0xffff)) * int(b & 0xff) + int(int16_t(a >> 16)) * int((b >> 8) & 0xff);
 }
+static inline long long clock64() { static long long t = 0; return ++t; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 template <class T> static inline T __ldcv(const T *p) { return *p; }
+template <class T> static inline T __ldcg(const T *p) { return *p; }
 template <class T> static inline T __ldcs(const T *p) { return *p; }
 template <class T> static inline void __stcs(T *p, T v) { *p = v; }
 
@@ -277,6 +279,7 @@ template <class T, class U> static inline T atomicOr(T *p, U v) { const T o = *p
 template <class T, class U> static inline T atomicAnd(T *p, U v) { const T o = *p; *p = T(o & T(v)); return o; }
 template <class T, class U> static inline T atomicExch(T *p, U v) { const T o = *p; *p = T(v); return o; }
 template <class T, class U> static inline T atomicExch_system(T *p, U v) { return atomicExch(p, v); }
+template <class T, class U> static inline T atomicMax_system(T *p, U v) { return atomicMax(p, v); }
 template <class T, class U> static inline T atomicCAS(T *p, U cmp, U v) { const T o = *p; if (o == T(cmp)) *p = T(v); return o; }
 
 // CUDA's integer min / max overloads (mixed signedness promotes to unsigned, like the device headers)

@@ -117,13 +117,14 @@ def test_emu_bench_stage_workloads_sharded_code_path(workload):
             assert line["e2e"]["d2h_bytes_per_step"] > 0
 
 
-@pytest.mark.parametrize("workload", ["c2", "c4", "c3"])
+@pytest.mark.parametrize("workload", ["c2", "c4", "c3", None])
 def test_emu_bench_main_runs_and_keeps_the_json_contract(workload):
-    """bench.py's real main() on the emulated kernels (tiny workloads, stand-in torch): control flow + JSON contract."""
+    """bench.py's real main() on the emulated kernels (tiny workloads, stand-in torch): control flow + JSON contract.
+    workload None = the default run: C3 (north-star sharded configuration) as the line, C2 as its `secondary` object."""
     import json
     import subprocess
-    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "run_bench_emu.py"), "--workload", workload, "--steps", "2", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "run_bench_emu.py")] + (["--workload", workload] if workload else []) +
+                       ["--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
@@ -138,6 +139,12 @@ def test_emu_bench_main_runs_and_keeps_the_json_contract(workload):
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
     assert "workload" in line["config"]
+    assert line["config"]["name"] == (workload or "c3") and "per_iteration_overhead_ms" in line["breakdown"]
+    if workload is None:
+        sec = line["secondary"]
+        assert line["scaling"] == "strong" and sec["config"]["name"] == "c2" and sec["value"] > 0 and sec["e2e"]["value"] > 0
+    else:
+        assert "secondary" not in line
     if workload == "c4":
         assert rf["kernel"].endswith("_batch") and line["config"]["images_per_step_per_gpu"] == 3 and e["api"] == "cniic_kmeans_rgb_batch"
 
