@@ -200,7 +200,8 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
 
     kind, w, h, k, blobs, desc, scaling = WORKLOADS[name]
     D = 5 if kind == "xyrgb" else 3
-    independent = world == 1 or name == "c4"   # no data-path collective: plain per-GPU context
+    independent = world == 1 or name in ("c4", "c2")   # one image (batch) per GPU, no data-path collective: plain per-GPU context
+    unique = name == "c2"   # cluster-colors at full size: K-means over the unique colours with counts, as the reference does (clusterc.rs:19-28)
     key = "plain" if independent else "dist"
     if key not in ctxs:
         ctxs[key] = cb.Context(local_rank) if independent else cdist.make_context(local_rank)
@@ -245,9 +246,16 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
             dist.barrier()
         torch.cuda.synchronize()
 
+    n_unique = [0]
+
     def one_step(flags=0, iters=ITERS):
         # a step = the whole kmeans::cluster call on HBM-resident points: session set-up (incl. the one-time colour ordering of
         # the culled RGB path), chunked init, ITERS Lloyd iterations
+        if unique and not flags:
+            # C2: count_freqs (Morton-binned histogram + ordered compaction = deduplicated, colour-sorted weighted points) and
+            # kmeans::cluster over them, the front half of ClusterColors::encode without the recolour pass
+            _, n_unique[0], st = sctx.cluster_colors_device(d_img_s, n_local, k, max_iters=iters)
+            return st
         if B > 1:  # batch of independent images: same work per image, one launch per stage for the whole batch
             ss = [cb.KMeansSession(sctx, kind_id, k, d_img_s + b * n_local * 3, n_local, flags=flags, **skw) for b in range(B)]
             cb.kmeans_reset_batch(ss)
@@ -273,7 +281,7 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
     launches0 = sctx.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     assign_ms, loop_ms, iters_run, pairs_per_launch = [], [], 0, 0.0
-    sess_culled = D == 5 or n_total * k >= (1 << 27)  # mirrors cniic_kmeans_open: small RGB problems run the brute-force kernel
+    sess_culled = unique or D == 5 or n_total * k >= (1 << 27)  # mirrors cniic_kmeans_open: small RGB problems run the brute-force kernel
     t_wall0 = time.perf_counter()
     for i in range(K):
         flush.fill_(i & 0xff)           # evict the image from L2 between timed steps (untimed)
@@ -316,10 +324,13 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
         def e2e_step():
             if B > 1:
                 return sctx.kmeans_rgb_batch(host_imgs, k, max_iters=ITERS, want_assign=False)
+            if unique:
+                return sctx.cluster_colors(host_img, k, max_iters=ITERS, want_image=False)
             if kind == "rgb":
                 return sctx.kmeans_rgb(host_img, k, max_iters=ITERS, want_assign=False)
             return sctx.kmeans_xyrgb(host_img, k, max_iters=ITERS, want_assign=False)
-        api_name = "cniic_kmeans_rgb_batch" if B > 1 else ("cniic_kmeans_rgb" if kind == "rgb" else "cniic_kmeans_xyrgb")
+        api_name = ("cniic_kmeans_rgb_batch" if B > 1 else "cniic_cluster_colors (out_rgb = NULL)" if unique else
+                    "cniic_kmeans_rgb" if kind == "rgb" else "cniic_kmeans_xyrgb")
         d2h_bytes = int((k * 3 * 4 + k * 8 + 64) * B)
     else:
         # sharded session: per step the shard is re-uploaded from pinned host memory and centroids/weights read back
@@ -363,6 +374,8 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
               ("km_assign_xyrgb_cull" if os.environ.get("CNIIC_XY_CULL_V1") else "km_assign_xyrgb_cull2"))
     if not sess_culled:
         kernel = "km_assign_rgb" if D == 3 else "km_assign_xyrgb"
+    if unique:
+        kernel = "km_assign_rgb_cull2<true>"  # weighted points
     if B > 1:
         kernel += "_batch"
     traffic = None
@@ -385,6 +398,15 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
         cpu = {"value": tot_px_iter / tot_dt, "unit": "Mpx*iter/s", "cores": 1, "kind": "port",
                "sample": f"{nb} x ({descr})", "seconds": tot_dt}
 
+    if unique:
+        u = n_unique[0]
+        roofline["unique_colour_view"] = {
+            "unique_colours": u, "fraction_of_pixels": u / max(1, n_local),
+            "Mcolour_iter_per_s": u * ITERS * K / (total_ms * 1e-3) / 1e6,
+            "algorithmic_bytes_per_launch": 10 * u, "achieved": 10 * u / (a_ms * 1e-3) / 1e9, "unit": "GB/s",
+            "note": "the reference clusters unique colours with counts (clusterc.rs:19-28), so does this step: one launch reads 4 B colour "
+                    "+ 4 B count + 2 B current cluster per unique colour; `achieved`/`frac` above keep the contract's 3 B per PIXEL the "
+                    "launch accounts for (SURVEY 8d)"}
     exchange = ("partial sums pushed over NVLink peer memory inside the multi-CTA update kernel" if os.environ.get("CNIIC_P2P", "1") == "1"
                 else "ncclAllReduce")
     step_ms = total_ms / K

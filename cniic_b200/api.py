@@ -248,16 +248,25 @@ class Context:
                                                C.c_size_t(len(keys)), _ptr(cen), C.c_uint32(len(cen)), _ptr(out)))
         return out.reshape(rgb.shape)
 
-    def cluster_colors(self, img, k, max_iters=0, tie=L.TIE_KEEP_CURRENT):
-        """Front half of ClusterColors::encode (clusterc.rs:19-47): returns (recoloured image, centroids, stats)."""
+    def cluster_colors(self, img, k, max_iters=0, tie=L.TIE_KEEP_CURRENT, want_image=True):
+        """Front half of ClusterColors::encode (clusterc.rs:19-47): returns (recoloured image or None, centroids, stats)."""
         img = _u8(img)
         h, w = img.shape[:2]
-        out = np.zeros_like(img)
+        out = np.zeros_like(img) if want_image else None
         cen = np.zeros((max(k, 1), 3), np.uint8)
         st = L.KMeansStats()
         self.check(self._lib.cniic_cluster_colors(self.h, _ptr(img), C.c_uint32(w), C.c_uint32(h), C.c_uint32(k),
                                                   C.c_uint32(max_iters), tie, _ptr(out), _ptr(cen), C.byref(st)))
         return out, cen[:k], st
+
+    def cluster_colors_device(self, d_rgb: int, n_pixels: int, k: int, max_iters=0, tie=L.TIE_KEEP_CURRENT, d_out: int | None = None):
+        """cniic_cluster_colors on an image resident in HBM: returns (centroids (k, 3) int32, number of unique colours, stats)."""
+        cen = np.zeros((max(k, 1), 3), np.int32)
+        st = L.KMeansStats()
+        nu = C.c_size_t(0)
+        self.check(self._lib.cniic_cluster_colors_device(self.h, C.c_void_p(d_rgb), C.c_size_t(n_pixels), C.c_uint32(k), C.c_uint32(max_iters), tie,
+                                                         C.c_void_p(d_out) if d_out else None, _ptr(cen), C.byref(nu), C.byref(st)))
+        return cen[:k], int(nu.value), st
 
     # ---- voronoi decode fill (clusterc.rs:179-186) ----
     def voronoi_fill(self, cxy, crgb, w, h):

@@ -304,7 +304,7 @@ extern "C" int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8
         if (sp.arg == 0 || sp.arg > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d", CNIIC_MAX_K);
         DevBuf dred(ctx);
         CU_TRY(ctx, dred.alloc(n * 3));
-        ST_TRY(cniic_dev_cluster_colors(ctx, din.as<uint8_t>(), n, sp.arg, ctx->codec_max_iters, CNIIC_TIE_KEEP_CURRENT, dred.as<uint8_t>(), nullptr, nullptr));
+        ST_TRY(cniic_dev_cluster_colors(ctx, din.as<uint8_t>(), n, sp.arg, ctx->codec_max_iters, CNIIC_TIE_KEEP_CURRENT, dred.as<uint8_t>(), nullptr, nullptr, nullptr));
         s.u32(w); s.u32(h);
         ST_TRY(encode_hufman_body(ctx, dred.as<uint8_t>(), n, s));  // the recoloured image never leaves HBM
         break;

@@ -86,6 +86,29 @@ __device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c) {
     asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// ---- programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may become resident while its predecessor in
+// the stream still runs; pdl_wait() (griddepcontrol.wait) returns once that predecessor has completed and its writes are visible,
+// so it must precede the first access to anything an earlier kernel wrote; pdl_trigger() lets the NEXT kernel of the stream
+// start the same way.  Removes the launch gap between the three short dependent kernels of a Lloyd iteration. ----
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {grid, block, smem, stream, at, 1u};  // {gridDim, blockDim, dynamicSmemBytes, stream, attrs, numAttrs}
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ int max3i(int a, int b, int c) { return max(a, max(b, c)); }  // VIMNMX3
 
 static inline uint32_t round_up_u32(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }

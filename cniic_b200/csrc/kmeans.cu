@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "nccl_dyn.h"
 #include "sort.cuh"
+#include "stages.cuh"
 
 namespace {
 
@@ -86,6 +87,9 @@ struct KmDev {
     int p2p;                                   // 1: sums live in the IPC exchange region, no NCCL call
     int my_rank;
     unsigned long long *const *peer_base;      // [world] base of every rank's exchange region (peer-mapped)
+    // points handed over as deduplicated, Morton-sorted unique colours (stages.cu: cniic_dev_unique_colours): the point with canonical
+    // index j is the j-th set bit of the key bitmap; rgb == nullptr
+    const uint32_t *ubits, *uprefix;
     const uint2 *tile_box;  // per 2048-point tile of the sorted copy: {bytewise min, bytewise max} of the packed colours
     const uint4 *wseg;      // culled D = 3, v2: per 256-point warp segment {box min, box max, sum r | sum g << 16, sum b | count << 16}
     const unsigned long long *wseg64;  // weighted points: per warp segment {sum r*w, sum g*w, sum b*w, sum w}
@@ -149,6 +153,8 @@ __device__ __forceinline__ void unpack8(const uint32_t w[6], uint32_t px[PX]) {
 
 template <bool WEIGHTED>
 __device__ __forceinline__ void km_assign_rgb_body(const KmDev d) {
+    pdl_wait();     // everything an earlier kernel of the stream wrote is visible from here on
+    pdl_trigger();  // the next kernel may become resident now (it waits the same way)
     if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
@@ -329,6 +335,8 @@ __device__ __forceinline__ void km_assign_rgb_body(const KmDev d) {
 // ------------------------------------------------------------------------------------------------------------
 // bytewise min / max of the packed colours of every 2048-point tile of the sorted copy (static for the whole session)
 __global__ void __launch_bounds__(256) km_tile_boxes(const uint32_t *__restrict__ pts_sorted, unsigned long long n, uint2 *boxes) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ uint32_t s_mn[8], s_mx[8];
     const unsigned long long base = (unsigned long long)blockIdx.x * TILE + (unsigned long long)threadIdx.x * PX;
     uint32_t mn = 0xffffffffu, mx = 0u;
@@ -356,6 +364,8 @@ constexpr int RCAP = 256;  // survivors scored per round
 
 template <bool WEIGHTED>
 __device__ __forceinline__ void km_assign_rgb_cull_body(const KmDev d) {
+    pdl_wait();     // everything an earlier kernel of the stream wrote is visible from here on
+    pdl_trigger();  // the next kernel may become resident now (it waits the same way)
     if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
@@ -563,6 +573,8 @@ __device__ __forceinline__ void km_assign_rgb_cull_body(const KmDev d) {
 // per tile: colour box; per warp segment (256 consecutive sorted points): colour box, channel sums, point count
 __global__ void __launch_bounds__(256) km_tile_boxes2(const uint32_t *__restrict__ pts_sorted, const uint32_t *__restrict__ wts_sorted, uint32_t n,
                                                       uint2 *boxes, uint4 *wseg, unsigned long long *wseg64) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ uint32_t s_mn[8], s_mx[8];
     const uint32_t base = blockIdx.x * TILE + threadIdx.x * PX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -606,6 +618,8 @@ __global__ void __launch_bounds__(256) km_tile_boxes2(const uint32_t *__restrict
 
 template <bool WEIGHTED>
 __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
+    pdl_wait();     // everything an earlier kernel of the stream wrote is visible from here on
+    pdl_trigger();  // the next kernel may become resident now (it waits the same way)
     if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
@@ -868,6 +882,8 @@ __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
 // ------------------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void km_assign_xyrgb_body(const KmDev d) {
+    pdl_wait();     // everything an earlier kernel of the stream wrote is visible from here on
+    pdl_trigger();  // the next kernel may become resident now (it waits the same way)
     if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
@@ -1048,6 +1064,8 @@ constexpr int TCAP = 256;          // survivors scored per round
 
 // static colour bounding box (bytewise min / max of r|g<<8|b<<16) of every 64x32 tile of the image, once per session
 __global__ void __launch_bounds__(THREADS) km_tile_boxes_xy(const uint8_t *__restrict__ rgb, uint32_t w, uint32_t hl, uint2 *boxes) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ uint32_t s_mn[8], s_mx[8];
     const uint32_t tiles_x = (w + TW - 1) / TW;
     const int x0 = (blockIdx.x % tiles_x) * TW, yl0 = (blockIdx.x / tiles_x) * TH;
@@ -1075,6 +1093,8 @@ __global__ void __launch_bounds__(THREADS) km_tile_boxes_xy(const uint8_t *__res
 }
 
 __device__ __forceinline__ void km_supercull_body(const KmDev d) {
+    pdl_wait();     // everything an earlier kernel of the stream wrote is visible from here on
+    pdl_trigger();  // the next kernel may become resident now (it waits the same way)
     if (d.st->done || d.st->dist_empty) return;
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_U;
@@ -1113,6 +1133,8 @@ __device__ __forceinline__ void km_supercull_body(const KmDev d) {
 }
 
 __device__ __forceinline__ void km_assign_xyrgb_cull_body(const KmDev d) {
+    pdl_wait();     // everything an earlier kernel of the stream wrote is visible from here on
+    pdl_trigger();  // the next kernel may become resident now (it waits the same way)
     if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
@@ -1289,6 +1311,8 @@ __device__ __forceinline__ void km_assign_xyrgb_cull_body(const KmDev d) {
 // ------------------------------------------------------------------------------------------------------------
 // static per session: colour box of every 64x32 tile, and per warp segment (4 rows x 64 pixels) {sum r, sum g, sum b, pixel count}
 __global__ void __launch_bounds__(THREADS) km_tile_boxes_xy2(const uint8_t *__restrict__ rgb, uint32_t w, uint32_t hl, uint2 *boxes, uint4 *wseg) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ uint32_t s_mn[8], s_mx[8];
     const uint32_t tiles_x = (w + TW - 1) / TW;
     const int x0 = (blockIdx.x % tiles_x) * TW, yl0 = (blockIdx.x / tiles_x) * TH;
@@ -1319,6 +1343,8 @@ __global__ void __launch_bounds__(THREADS) km_tile_boxes_xy2(const uint8_t *__re
 }
 
 __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
+    pdl_wait();     // everything an earlier kernel of the stream wrote is visible from here on
+    pdl_trigger();  // the next kernel may become resident now (it waits the same way)
     if (d.st->done || d.st->dist_empty) return;
     extern __shared__ uint4 smem_raw[];
     const uint32_t k = d.k;
@@ -1551,6 +1577,19 @@ __device__ __forceinline__ void fetch_point(const KmDev &d, unsigned long long l
         out[0] = int32_t(local_i % d.w);
         out[1] = int32_t(d.y0 + local_i / d.w);
         out[2] = d.rgb[3 * local_i]; out[3] = d.rgb[3 * local_i + 1]; out[4] = d.rgb[3 * local_i + 2];
+    } else if (d.ubits) {
+        // unique-colour session: select the local_i-th set bit of the key bitmap (last word whose exclusive prefix is <= local_i)
+        const uint32_t j = (uint32_t)local_i;
+        uint32_t lo = 0, hi = 1u << 19;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (d.uprefix[mid] <= j) lo = mid;
+            else hi = mid;
+        }
+        uint32_t bits = d.ubits[lo];
+        for (uint32_t skip = j - d.uprefix[lo]; skip; skip--) bits &= bits - 1;
+        const uint32_t key = (lo << 5) | uint32_t(__ffs(bits) - 1);
+        out[0] = int32_t(key >> 16); out[1] = int32_t((key >> 8) & 0xff); out[2] = int32_t(key & 0xff);
     } else {
         out[0] = d.rgb[3 * local_i]; out[1] = d.rgb[3 * local_i + 1]; out[2] = d.rgb[3 * local_i + 2];
     }
@@ -1558,6 +1597,8 @@ __device__ __forceinline__ void fetch_point(const KmDev &d, unsigned long long l
 
 // kmeans.rs:61-78 init_assignment: cluster i < k-1 owns points [N-(i+1)*ppc, N-i*ppc), cluster k-1 the rest
 __device__ __forceinline__ void km_init_assign_body(const KmDev d) {
+    pdl_wait();     // everything an earlier kernel of the stream wrote is visible from here on
+    pdl_trigger();  // the next kernel may become resident now (it waits the same way)
     const unsigned long long N = d.n_total, ppc = N / d.k;
     const unsigned long long head = N - (unsigned long long)(d.k - 1) * ppc;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < d.n_local;
@@ -1570,6 +1611,8 @@ __device__ __forceinline__ void km_init_assign_body(const KmDev d) {
 // kmeans.rs:101-108 init_centroids (single GPU: gathered straight from the resident points)
 template <int D>
 __device__ __forceinline__ void km_init_centroids_body(const KmDev d) {
+    pdl_wait();     // everything an earlier kernel of the stream wrote is visible from here on
+    pdl_trigger();  // the next kernel may become resident now (it waits the same way)
     const unsigned long long N = d.n_total, ppc = N / d.k;
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < d.k; c += gridDim.x * blockDim.x) {
         const unsigned long long gi = c + 1 < d.k ? N - (unsigned long long)(c + 1) * ppc : 0ull;
@@ -1623,6 +1666,8 @@ __host__ __device__ inline size_t p2p_xcount_off(int world) { return p2p_flags_o
 
 template <int D>
 __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode, const uint32_t cta, const uint32_t ncta) {
+    pdl_wait();     // everything an earlier kernel of the stream wrote is visible from here on
+    pdl_trigger();  // the next kernel may become resident now (it waits the same way)
     constexpr int DW = D + 1;
     constexpr int G = D == 5 ? G5 : G3;
     constexpr int DUMMY = D == 5 ? DUMMY5 : DUMMY3;
@@ -2033,10 +2078,19 @@ struct cniic_kmeans {
     unsigned long long *d_wseg64 = nullptr;  // ... and weighted sums (weighted sessions)
     bool v2 = false;          // culled D = 3: second kernel version (default)
     uint32_t *d_sorted = nullptr, *d_perm = nullptr, *d_wsorted = nullptr;  // colour-sorted copy (culled D = 3)
+    uint32_t *d_ubits = nullptr, *d_uprefix = nullptr;  // unique-colour session: key bitmap + word prefix (owned)
     uint16_t *d_assign_orig = nullptr;  // assignment mapped back to original order (filled on demand)
     bool cull = true;        // exact culling (CNIIC_KMEANS_NO_CULL in desc.flags selects brute force)
     uint32_t iter_seen = 0;  // state.iter at the end of the previous run (0 after reset)
 };
+
+// Launches of the Lloyd path go through programmatic dependent launch (common.cuh); CNIIC_NO_PDL=1 keeps plain stream order (A/B).
+static const bool g_pdl = !getenv("CNIIC_NO_PDL");
+#define KM_LAUNCH(kern, grid, block, smem, ...)                                                            \
+    do {                                                                                                   \
+        if (g_pdl) (void)launch_pdl(kern, dim3(grid), dim3(block), smem, ctx->stream, __VA_ARGS__);        \
+        else kern<<<grid, block, smem, ctx->stream>>>(__VA_ARGS__);                                        \
+    } while (0)
 
 static void km_report_launches(cniic_kmeans *km) {
     km->ctx->launches += km->launches - km->launches_reported;
@@ -2046,20 +2100,20 @@ static void km_report_launches(cniic_kmeans *km) {
 static int km_launch_assign(cniic_kmeans *km) {
     cniic_ctx *ctx = km->ctx;
     if (km->D == 5 && km->cull) {
-        if (km->dev.super_x * km->dev.super_y) {  // a rank may hold no rows at all
-            km_supercull<<<km->dev.super_x * km->dev.super_y, THREADS, 0, ctx->stream>>>(km->dev);
+        if (km->dev.super_x && km->dev.super_y) {  // a rank may hold no rows at all
+            KM_LAUNCH(km_supercull, km->dev.super_x * km->dev.super_y, THREADS, 0, km->dev);
             km->launches++;
         }
-        if (km->v2) km_assign_xyrgb_cull2<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
-        else km_assign_xyrgb_cull<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+        if (km->v2) KM_LAUNCH(km_assign_xyrgb_cull2, km->grid, THREADS, km->smem, km->dev);
+        else KM_LAUNCH(km_assign_xyrgb_cull, km->grid, THREADS, km->smem, km->dev);
     }
-    else if (km->D == 5) km_assign_xyrgb<<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
-    else if (km->cull && km->v2 && km->dev.wts) km_assign_rgb_cull2<true><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
-    else if (km->cull && km->v2) km_assign_rgb_cull2<false><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
-    else if (km->cull && km->dev.wts) km_assign_rgb_cull<true><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
-    else if (km->cull) km_assign_rgb_cull<false><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
-    else if (km->dev.wts) km_assign_rgb<true><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
-    else km_assign_rgb<false><<<km->grid, THREADS, km->smem, ctx->stream>>>(km->dev);
+    else if (km->D == 5) KM_LAUNCH(km_assign_xyrgb, km->grid, THREADS, km->smem, km->dev);
+    else if (km->cull && km->v2 && km->dev.wts) KM_LAUNCH(km_assign_rgb_cull2<true>, km->grid, THREADS, km->smem, km->dev);
+    else if (km->cull && km->v2) KM_LAUNCH(km_assign_rgb_cull2<false>, km->grid, THREADS, km->smem, km->dev);
+    else if (km->cull && km->dev.wts) KM_LAUNCH(km_assign_rgb_cull<true>, km->grid, THREADS, km->smem, km->dev);
+    else if (km->cull) KM_LAUNCH(km_assign_rgb_cull<false>, km->grid, THREADS, km->smem, km->dev);
+    else if (km->dev.wts) KM_LAUNCH(km_assign_rgb<true>, km->grid, THREADS, km->smem, km->dev);
+    else KM_LAUNCH(km_assign_rgb<false>, km->grid, THREADS, km->smem, km->dev);
     km->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
@@ -2068,19 +2122,19 @@ static int km_launch_assign(cniic_kmeans *km) {
 static int km_launch_finalize(cniic_kmeans *km, int init_mode) {
     cniic_ctx *ctx = km->ctx;
     const unsigned ncta = init_mode == 0 ? upd_ctas_of(km->desc.k) : 1u;  // an iteration: one CTA per 256-cluster slice
-    if (km->D == 5) km_finalize<5><<<ncta, 1024, 0, ctx->stream>>>(km->dev, init_mode);
-    else km_finalize<3><<<ncta, 1024, 0, ctx->stream>>>(km->dev, init_mode);
+    if (km->D == 5) KM_LAUNCH(km_finalize<5>, ncta, 1024, 0, km->dev, init_mode);
+    else KM_LAUNCH(km_finalize<3>, ncta, 1024, 0, km->dev, init_mode);
     km->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
 }
 
-extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, cniic_kmeans **out) {
+static int km_open_impl(cniic_ctx *ctx, const cniic_kmeans_desc *desc, UniqueColours *uc, cniic_kmeans **out) {
     if (!ctx || !desc || !out) return CNIIC_ERR_BAD_ARG;
     *out = nullptr;
     if (desc->k == 0 || desc->k > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d", CNIIC_MAX_K);
     if (desc->kind != CNIIC_POINTS_RGB && desc->kind != CNIIC_POINTS_XYRGB) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "bad point kind");
-    if (!desc->rgb && desc->n_local) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "null points");
+    if (!desc->rgb && desc->n_local && !uc) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "null points");
     if (desc->n_total / desc->k == 0) return cniic_set_error(ctx, CNIIC_ERR_TOO_FEW_POINTS, "fewer points (%llu) than clusters (%u)", (unsigned long long)desc->n_total, desc->k);
     if (desc->n_total >= (1ull << 31)) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "at most 2^31-1 points");
     const int D = desc->kind == CNIIC_POINTS_XYRGB ? 5 : 3;
@@ -2109,8 +2163,8 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
             return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)));   \
     } while (0)
     const uint8_t *d_rgb = desc->rgb;
-    const uint32_t *d_wts = desc->weights;
-    if (!desc->points_on_device) {
+    const uint32_t *d_wts = uc ? uc->d_wts : desc->weights;  // (a unique-colour session is weighted; only the sorted weights exist)
+    if (!desc->points_on_device && !uc) {
         km->own_rgb = static_cast<uint8_t *>(cniic_cache_alloc(ctx, desc->n_local * 3));
         if (!km->own_rgb) return fail(CNIIC_ERR_CUDA);
         KM_TRY(cudaMemcpyAsync(km->own_rgb, desc->rgb, desc->n_local * 3, cudaMemcpyHostToDevice, ctx->stream));
@@ -2179,17 +2233,24 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     km->cull = !(desc->flags & CNIIC_KMEANS_NO_CULL) && !getenv("CNIIC_NO_CULL");
     // small D = 3 problems: the one-time colour sort costs more than brute-force scoring saves (break-even ~2^27 pairs/iteration)
     if (D == 3 && (unsigned long long)desc->n_total * k < (1ull << 27) && !(desc->flags & CNIIC_KMEANS_FORCE_CULL)) km->cull = false;
+    if (uc) km->cull = true;  // the points only exist in colour-sorted form
     if (D == 3 && km->cull && desc->n_local) {
-        // colour-sorted copy of the points (Morton order), built once per session
+        // colour-sorted copy of the points (Morton order), built once per session -- or handed over ready-made by the unique-colour
+        // front end, whose Morton-indexed histogram bins compact straight into it (no sort)
         const size_t n = desc->n_local;
-        km->d_sorted = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (n + 8) * 4));
-        km->d_perm = static_cast<uint32_t *>(cniic_cache_alloc(ctx, n * 4));
-        if (d_wts) km->d_wsorted = static_cast<uint32_t *>(cniic_cache_alloc(ctx, n * 4));
-        if (!km->d_sorted || !km->d_perm || (d_wts && !km->d_wsorted)) return fail(CNIIC_ERR_CUDA);
         const size_t ntiles = (n + TILE - 1) / TILE;
         km->d_boxes = static_cast<uint2 *>(cniic_cache_alloc(ctx, ntiles * 8));
         if (!km->d_boxes) return fail(CNIIC_ERR_CUDA);
-        {
+        if (uc) {  // take ownership
+            km->d_sorted = uc->d_pts; km->d_perm = uc->d_perm; km->d_wsorted = uc->d_wts; km->d_ubits = uc->d_keybits; km->d_uprefix = uc->d_word_prefix;
+            *uc = UniqueColours();
+            dv.ubits = km->d_ubits;
+            dv.uprefix = km->d_uprefix;
+        } else {
+            km->d_sorted = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (n + 8) * 4));
+            km->d_perm = static_cast<uint32_t *>(cniic_cache_alloc(ctx, n * 4));
+            if (d_wts) km->d_wsorted = static_cast<uint32_t *>(cniic_cache_alloc(ctx, n * 4));
+            if (!km->d_sorted || !km->d_perm || (d_wts && !km->d_wsorted)) return fail(CNIIC_ERR_CUDA);
             const int rc = cniic_dev_sort_colours(ctx, d_rgb, d_wts, n, km->d_sorted, km->d_perm, km->d_wsorted, &km->launches);
             if (rc != CNIIC_OK) return fail(rc);
         }
@@ -2201,11 +2262,11 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
                 km->d_wseg64 = static_cast<unsigned long long *>(cniic_cache_alloc(ctx, ntiles * 8 * 32));
                 if (!km->d_wseg64) return fail(CNIIC_ERR_CUDA);
             }
-            km_tile_boxes2<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(km->d_sorted, km->d_wsorted, (uint32_t)n, km->d_boxes, km->d_wseg, km->d_wseg64);
+            KM_LAUNCH(km_tile_boxes2, (unsigned)ntiles, 256, 0, km->d_sorted, km->d_wsorted, (uint32_t)n, km->d_boxes, km->d_wseg, km->d_wseg64);
             dv.wseg = km->d_wseg;
             dv.wseg64 = km->d_wseg64;
         } else {
-            km_tile_boxes<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(km->d_sorted, n, km->d_boxes);
+            KM_LAUNCH(km_tile_boxes, (unsigned)ntiles, 256, 0, km->d_sorted, (unsigned long long)n, km->d_boxes);
         }
         km->launches += 1;
         KM_TRY(cudaGetLastError());
@@ -2222,10 +2283,10 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
         if (km->v2) {
             km->d_wseg = static_cast<uint4 *>(cniic_cache_alloc(ctx, ntiles * 8 * 16));
             if (!km->d_wseg) return fail(CNIIC_ERR_CUDA);
-            km_tile_boxes_xy2<<<(unsigned)ntiles, THREADS, 0, ctx->stream>>>(d_rgb, desc->w, desc->h_local, km->d_boxes, km->d_wseg);
+            KM_LAUNCH(km_tile_boxes_xy2, (unsigned)ntiles, THREADS, 0, d_rgb, desc->w, desc->h_local, km->d_boxes, km->d_wseg);
             dv.wseg = km->d_wseg;
         } else {
-            km_tile_boxes_xy<<<(unsigned)ntiles, THREADS, 0, ctx->stream>>>(d_rgb, desc->w, desc->h_local, km->d_boxes);
+            KM_LAUNCH(km_tile_boxes_xy, (unsigned)ntiles, THREADS, 0, d_rgb, desc->w, desc->h_local, km->d_boxes);
         }
         km->launches++;
         KM_TRY(cudaGetLastError());
@@ -2283,12 +2344,32 @@ extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, 
     return CNIIC_OK;
 }
 
+extern "C" int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, cniic_kmeans **out) { return km_open_impl(ctx, desc, nullptr, out); }
+
+// ColorCount points straight from the unique-colour front end (clusterc.rs:19-28): the session takes over the arrays of `uc`.
+int cniic_kmeans_open_unique(cniic_ctx *ctx, UniqueColours *uc, uint32_t k, int tie_rule, cniic_kmeans **out) {
+    if (!uc || !uc->d_pts) return CNIIC_ERR_BAD_ARG;
+    cniic_kmeans_desc desc{};
+    desc.kind = CNIIC_POINTS_RGB;
+    desc.k = k;
+    desc.tie_rule = tie_rule;
+    desc.n_local = desc.n_total = uc->u;
+    desc.points_on_device = 1;
+    return km_open_impl(ctx, &desc, uc, out);
+}
+
+// colour-sorted view of a culled D = 3 session: packed colours and their current cluster ids, both in sorted order
+void cniic_kmeans_sorted_view(cniic_kmeans *km, const uint32_t **pts_sorted, const uint16_t **assign_sorted) {
+    *pts_sorted = km->dev.pts_sorted;
+    *assign_sorted = km->dev.assign;
+}
+
 extern "C" int cniic_kmeans_reset(cniic_kmeans *km, const int32_t *host_init_centroids) {
     if (!km) return CNIIC_ERR_BAD_ARG;
     cniic_ctx *ctx = km->ctx;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (km->desc.n_local) {
-        km_init_assign<<<std::max(1, std::min(ctx->sm_count * 8, int((km->desc.n_local + 255) / 256))), 256, 0, ctx->stream>>>(km->dev);
+        KM_LAUNCH(km_init_assign, std::max(1, std::min(ctx->sm_count * 8, int((km->desc.n_local + 255) / 256))), 256, 0, km->dev);
         km->launches++;
     }
     if (host_init_centroids) {
@@ -2296,8 +2377,8 @@ extern "C" int cniic_kmeans_reset(cniic_kmeans *km, const int32_t *host_init_cen
     } else {
         if (ctx->world > 1 || km->desc.n_local != km->desc.n_total)
             return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "a sharded session needs explicit initial centroids");
-        if (km->D == 5) km_init_centroids<5><<<(km->desc.k + 127) / 128, 128, 0, ctx->stream>>>(km->dev);
-        else km_init_centroids<3><<<(km->desc.k + 127) / 128, 128, 0, ctx->stream>>>(km->dev);
+        if (km->D == 5) KM_LAUNCH(km_init_centroids<5>, (km->desc.k + 127) / 128, 128, 0, km->dev);
+        else KM_LAUNCH(km_init_centroids<3>, (km->desc.k + 127) / 128, 128, 0, km->dev);
         km->launches++;
     }
     CU_TRY(ctx, cudaGetLastError());
@@ -2775,6 +2856,8 @@ extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
     cniic_cache_free(km->ctx, km->d_perm);
     cniic_cache_free(km->ctx, km->d_wsorted);
     cniic_cache_free(km->ctx, km->d_assign_orig);
+    cniic_cache_free(km->ctx, km->d_ubits);
+    cniic_cache_free(km->ctx, km->d_uprefix);
     cniic_pinned_put(km->ctx, km->h_state);
     if (km->ev0) km->ctx->event_pool.push_back(km->ev0);
     if (km->ev1) km->ctx->event_pool.push_back(km->ev1);

@@ -290,6 +290,140 @@ __global__ void __launch_bounds__(256) page_compact_kernel(uint32_t *bins, size_
 // ============================================================================================================
 // cluster-colors helpers (reference src/codec/clusterc.rs:19-47)
 // ============================================================================================================
+
+// ---- unique colours WITH the order the culled D = 3 K-means wants, without a sort (clusterc.rs:19-28, utils.rs:4-16) -----------
+// count_freqs turns the pixels into (colour, count) points.  The dense bins are indexed by the 24-bit MORTON code of (r, g, b), so
+// the ordered compaction of the bins IS the deduplicated, weighted, Morton-sorted point list the culled kernel scans:
+// no radix sort and, on photo-like images, about half as many points as pixels.  The reference's HashMap order is random (SURVEY
+// F5); the canonical order of the unique colours stays ascending key = r<<16 | g<<8 | b (header, oracle): a bitmap over the key space
+// marks the colours present, and a prefix popcount over it gives each colour its canonical index (`perm`) -- the chunked init
+// (kmeans.rs:61-108) and the empty-cluster rule are defined on that index.
+__device__ __forceinline__ uint32_t spread3(uint32_t x) {  // 8 bits -> every third bit
+    x &= 0xff;
+    x = (x ^ (x << 16)) & 0xff0000ffu;
+    x = (x ^ (x << 8)) & 0x0300f00fu;
+    x = (x ^ (x << 4)) & 0x030c30c3u;
+    x = (x ^ (x << 2)) & 0x09249249u;
+    return x;
+}
+__device__ __forceinline__ uint32_t gather3(uint32_t x) {
+    x &= 0x09249249u;
+    x = (x ^ (x >> 2)) & 0x030c30c3u;
+    x = (x ^ (x >> 4)) & 0x0300f00fu;
+    x = (x ^ (x >> 8)) & 0xff0000ffu;
+    x = (x ^ (x >> 16)) & 0x3ffu;
+    return x;
+}
+// same bit order as the former colour sort: r on the highest bit of every triple
+__device__ __forceinline__ uint32_t morton_rgb(uint32_t r, uint32_t g, uint32_t b) { return (spread3(r) << 2) | (spread3(g) << 1) | spread3(b); }
+
+constexpr uint32_t KEYBITS_WORDS = 1u << 19;  // 2^24 keys / 32
+
+__global__ void __launch_bounds__(256) dedup_hist_kernel(const uint8_t *__restrict__ rgb, size_t n, uint32_t *bins, uint8_t *flags, uint32_t *keybits) {
+    const bool al = (reinterpret_cast<uintptr_t>(rgb) & 3) == 0;
+    const size_t quads = n / 4;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < quads; q += (size_t)gridDim.x * blockDim.x) {
+        uint32_t pk[4];  // r | g << 8 | b << 16
+        if (al) {        // 4 pixels = three aligned words
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(rgb + q * 12);
+            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+            pk[0] = w0 & 0xffffff; pk[1] = (w0 >> 24) | ((w1 & 0xffff) << 8); pk[2] = (w1 >> 16) | ((w2 & 0xff) << 16); pk[3] = w2 >> 8;
+        } else {
+            for (int j = 0; j < 4; j++) { const uint8_t *p = rgb + (q * 4 + j) * 3; pk[j] = uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16); }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j > 0 && pk[j] == pk[j - 1]) continue;  // runs of equal neighbours (flat areas) cost one atomic
+            uint32_t cnt = 1;
+            for (int t = j + 1; t < 4 && pk[t] == pk[j]; t++) cnt++;
+            const uint32_t r = pk[j] & 0xff, g = (pk[j] >> 8) & 0xff, b = pk[j] >> 16;
+            const uint32_t m = morton_rgb(r, g, b);
+            if (atomicAdd(&bins[m], cnt) == 0) {  // first pixel of this colour: mark its bin page and its key
+                flags[m >> PAGE_SHIFT] = 1;
+                const uint32_t key = (r << 16) | (g << 8) | b;
+                atomicOr(&keybits[key >> 5], 1u << (key & 31));
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n - quads * 4) {
+        const uint8_t *p = rgb + (quads * 4 + threadIdx.x) * 3;
+        const uint32_t m = morton_rgb(p[0], p[1], p[2]);
+        if (atomicAdd(&bins[m], 1u) == 0) {
+            flags[m >> PAGE_SHIFT] = 1;
+            const uint32_t key = (uint32_t(p[0]) << 16) | (uint32_t(p[1]) << 8) | p[2];
+            atomicOr(&keybits[key >> 5], 1u << (key & 31));
+        }
+    }
+}
+
+// colours present per 4096-key page of the bitmap (128 words), then (after a scan of the page counts) the exclusive prefix of
+// every word: canonical index of key = word_prefix[key >> 5] + popc(bits below key in its word)
+__global__ void __launch_bounds__(128) keybits_page_count_kernel(const uint32_t *__restrict__ keybits, uint32_t *page_counts) {
+    uint32_t c = __popc(keybits[blockIdx.x * 128 + threadIdx.x]);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    __shared__ uint32_t s[4];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) page_counts[blockIdx.x] = s[0] + s[1] + s[2] + s[3];
+}
+
+__global__ void __launch_bounds__(128) keybits_word_prefix_kernel(const uint32_t *__restrict__ keybits, const unsigned long long *__restrict__ page_off,
+                                                                  uint32_t *word_prefix) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t v = __popc(keybits[blockIdx.x * 128 + threadIdx.x]);
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __shared__ uint32_t s[4];
+    if (lane == 31) s[warp] = x;
+    __syncthreads();
+    uint32_t before = (uint32_t)page_off[blockIdx.x];
+    for (int j = 0; j < warp; j++) before += s[j];
+    word_prefix[blockIdx.x * 128 + threadIdx.x] = before + x - v;
+}
+
+// ordered compaction of the Morton-indexed bins: packed colour r | g<<8 | b<<16 (the layout the K-means kernels read), count,
+// canonical index; the bins go back to all-zero
+__global__ void __launch_bounds__(256) dedup_compact_kernel(uint32_t *bins, const uint32_t *__restrict__ list, const uint32_t *__restrict__ count,
+                                                            const unsigned long long *__restrict__ offsets, uint8_t *flags,
+                                                            const uint32_t *__restrict__ keybits, const uint32_t *__restrict__ word_prefix,
+                                                            uint32_t *out_pts, uint32_t *out_wts, uint32_t *out_perm) {
+    __shared__ uint32_t s_warp[8];
+    if (blockIdx.x >= *count) return;
+    const uint32_t pg = list[blockIdx.x];
+    const size_t base = (size_t)pg * PAGE;
+    unsigned long long pos = offsets[blockIdx.x];
+    for (int j = 0; j < PAGE / 256; j++) {
+        const size_t i = base + (size_t)j * 256 + threadIdx.x;
+        const uint32_t v = bins[i];
+        uint32_t tot;
+        const uint32_t rk = block_rank256(v != 0, s_warp, &tot);
+        if (v) {
+            const uint32_t m = (uint32_t)i;
+            const uint32_t r = gather3(m >> 2), g = gather3(m >> 1), b = gather3(m);
+            const uint32_t key = (r << 16) | (g << 8) | b;
+            out_pts[pos + rk] = r | (g << 8) | (b << 16);
+            out_wts[pos + rk] = v;  // clusterc.rs:23 "count as u32"
+            out_perm[pos + rk] = __ldg(word_prefix + (key >> 5)) + __popc(__ldg(keybits + (key >> 5)) & ((1u << (key & 31)) - 1u));
+            bins[i] = 0;  // restore the all-zero invariant
+        }
+        pos += tot;
+    }
+    if (threadIdx.x == 0) flags[pg] = 0;
+}
+
+// lut[key] = centroid colour (packed r | g<<8 | b<<16) straight from the sorted point list and its assignment
+__global__ void build_lut_sorted_kernel(const uint32_t *__restrict__ pts_sorted, const uint16_t *__restrict__ assign_sorted, size_t n,
+                                        const int32_t *__restrict__ cen, uint32_t *lut) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t v = pts_sorted[i];
+        const int32_t *c = cen + 3 * assign_sorted[i];
+        lut[((v & 0xff) << 16) | (v & 0xff00) | (v >> 16)] = uint32_t(c[0]) | (uint32_t(c[1]) << 8) | (uint32_t(c[2]) << 16);
+    }
+}
+
 __global__ void keys_to_points_kernel(const uint32_t *__restrict__ keys, const unsigned long long *__restrict__ counts, size_t n,
                                       uint8_t *rgb, uint32_t *wts) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -1123,6 +1257,66 @@ int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins_in, size_t nb
     return CNIIC_OK;
 }
 
+void cniic_unique_colours_free(cniic_ctx *ctx, UniqueColours *uc) {
+    cniic_cache_free(ctx, uc->d_pts);
+    cniic_cache_free(ctx, uc->d_wts);
+    cniic_cache_free(ctx, uc->d_perm);
+    cniic_cache_free(ctx, uc->d_keybits);
+    cniic_cache_free(ctx, uc->d_word_prefix);
+    *uc = UniqueColours();
+}
+
+// count_freqs over the pixels (utils.rs:4-16 at clusterc.rs:21) with the result already in the form the culled D = 3 K-means scans:
+// see dedup_hist_kernel.  One host synchronisation (the number of unique colours sizes the outputs and the K-means grid).
+int cniic_dev_unique_colours(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, UniqueColours *out) {
+    *out = UniqueColours();
+    uint32_t *bins;
+    uint8_t *flags;
+    size_t nbins;
+    ST_TRY(hist_space(ctx, 0, &bins, &flags, &nbins));  // the 2^24 colour bins, indexed by Morton code for this pass
+    const uint32_t npages = (uint32_t)(nbins / PAGE), kpages = KEYBITS_WORDS / 128;
+    UniqueColours uc;
+    auto fail = [&](int code) {
+        cniic_unique_colours_free(ctx, &uc);
+        return code;
+    };
+    uc.d_keybits = static_cast<uint32_t *>(cniic_cache_alloc(ctx, KEYBITS_WORDS * 4));
+    uc.d_word_prefix = static_cast<uint32_t *>(cniic_cache_alloc(ctx, KEYBITS_WORDS * 4));
+    if (!uc.d_keybits || !uc.d_word_prefix) return fail(CNIIC_ERR_CUDA);
+    DevBuf list(ctx), bc(ctx), off(ctx), kc(ctx), koff(ctx);
+    if (list.alloc((size_t(npages) + 1) * 4) != cudaSuccess || bc.alloc(size_t(npages) * 4) != cudaSuccess || off.alloc((size_t(npages) + 1) * 8) != cudaSuccess ||
+        kc.alloc(size_t(kpages) * 4) != cudaSuccess || koff.alloc((size_t(kpages) + 1) * 8) != cudaSuccess)
+        return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc failed"));
+    uint32_t *d_count = list.as<uint32_t>() + npages;
+    if (cudaMemsetAsync(uc.d_keybits, 0, KEYBITS_WORDS * 4, ctx->stream) != cudaSuccess) return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "memset failed"));
+    if (n) {
+        dedup_hist_kernel<<<grid_for(ctx, n / 4 + 1, 2), 256, 0, ctx->stream>>>(d_rgb, n, bins, flags, uc.d_keybits);
+        ctx->launches++;
+    }
+    list_pages_kernel<<<1, 1024, 0, ctx->stream>>>(flags, npages, list.as<uint32_t>(), d_count);
+    page_count_kernel<<<npages, 256, 0, ctx->stream>>>(bins, nbins, list.as<uint32_t>(), d_count, bc.as<uint32_t>());
+    scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(bc.as<uint32_t>(), npages, off.as<unsigned long long>());
+    keybits_page_count_kernel<<<kpages, 128, 0, ctx->stream>>>(uc.d_keybits, kc.as<uint32_t>());
+    scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(kc.as<uint32_t>(), kpages, koff.as<unsigned long long>());
+    keybits_word_prefix_kernel<<<kpages, 128, 0, ctx->stream>>>(uc.d_keybits, koff.as<unsigned long long>(), uc.d_word_prefix);
+    ctx->launches += 6;
+    unsigned long long total = 0;
+    if (cudaMemcpyAsync(&total, off.as<unsigned long long>() + npages, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "unique-colour count failed: %s", cudaGetErrorString(cudaGetLastError())));
+    uc.u = (size_t)total;
+    uc.d_pts = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (uc.u + 8) * 4));
+    uc.d_wts = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (uc.u + 8) * 4));
+    uc.d_perm = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (uc.u + 8) * 4));
+    if (!uc.d_pts || !uc.d_wts || !uc.d_perm) return fail(CNIIC_ERR_CUDA);
+    dedup_compact_kernel<<<npages, 256, 0, ctx->stream>>>(bins, list.as<uint32_t>(), d_count, off.as<unsigned long long>(), flags, uc.d_keybits,
+                                                          uc.d_word_prefix, uc.d_pts, uc.d_wts, uc.d_perm);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "unique-colour compaction failed"));
+    *out = uc;
+    return CNIIC_OK;
+}
+
 int cniic_dev_hist_rgb_bins(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t **d_bins) {
     uint8_t *flags;
     size_t nbins;
@@ -1396,47 +1590,43 @@ extern "C" int cniic_recolor_rgb(cniic_ctx *ctx, const uint8_t *rgb, size_t n, c
 
 // device-resident cluster-colors front half; d_out may alias nothing; returns centroids (k x 3 i32 on host)
 int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t k, uint32_t max_iters, int tie_rule, uint8_t *d_out,
-                             std::vector<int32_t> *cen_host, cniic_kmeans_stats *stats) {
-    uint32_t *d_bins = nullptr, *d_keys = nullptr;
-    unsigned long long *d_counts = nullptr;
-    size_t u = 0;
-    int rc = cniic_dev_hist_rgb_bins(ctx, d_rgb, n, &d_bins);
-    if (rc == CNIIC_OK) rc = cniic_dev_dense_compact(ctx, d_bins, size_t(1) << 24, &d_keys, &d_counts, &u);
-    DevBuf upts(ctx), uwts(ctx);
+                             std::vector<int32_t> *cen_host, cniic_kmeans_stats *stats, size_t *n_unique) {
+    // clusterc.rs:19-47: count_freqs -> kmeans::cluster over (colour, count) points -> recolour.  The unique colours leave the
+    // histogram already deduplicated and Morton-sorted (cniic_dev_unique_colours), which is what the culled K-means kernel scans.
+    UniqueColours uc;
+    int rc = cniic_dev_unique_colours(ctx, d_rgb, n, &uc);
+    const size_t u = uc.u;
+    if (n_unique) *n_unique = u;
     cniic_kmeans *km = nullptr;
     if (rc == CNIIC_OK && u / k == 0) rc = cniic_set_error(ctx, CNIIC_ERR_TOO_FEW_POINTS, "only %zu distinct colours for k = %u (kmeans.rs:67-68)", u, k);
-    if (rc == CNIIC_OK && (upts.alloc(u * 3) != cudaSuccess || uwts.alloc(u * 4) != cudaSuccess)) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc failed");
-    if (rc == CNIIC_OK) rc = cniic_dev_keys_to_points(ctx, d_keys, d_counts, u, upts.as<uint8_t>(), uwts.as<uint32_t>());
-    if (rc == CNIIC_OK) {
-        cniic_kmeans_desc desc{};
-        desc.kind = CNIIC_POINTS_RGB;
-        desc.k = k;
-        desc.tie_rule = tie_rule;
-        desc.n_local = desc.n_total = u;
-        desc.rgb = upts.as<uint8_t>();
-        desc.weights = uwts.as<uint32_t>();
-        desc.points_on_device = 1;
-        rc = cniic_kmeans_open(ctx, &desc, &km);
-    }
+    if (rc == CNIIC_OK) rc = cniic_kmeans_open_unique(ctx, &uc, k, tie_rule, &km);
+    cniic_unique_colours_free(ctx, &uc);  // (whatever the session did not take over)
     if (rc == CNIIC_OK) rc = cniic_kmeans_reset(km, nullptr);
     if (rc == CNIIC_OK) rc = cniic_kmeans_run(km, max_iters, stats);
     std::vector<uint64_t> wts(k);
     std::vector<int32_t> cen(size_t(k) * 3);
     if (rc == CNIIC_OK) rc = cniic_kmeans_get(km, cen.data(), wts.data(), nullptr);
-    if (rc == CNIIC_OK) {
+    if (rc == CNIIC_OK && d_out) {
         // colour -> centroid colour lookup table (every colour that occurs is written before it is read)
         DevBuf dcen(ctx), dlut(ctx);
         if (dcen.alloc(cen.size() * 4) != cudaSuccess || dlut.alloc((size_t(1) << 24) * 4) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc failed");
         if (rc == CNIIC_OK) {
             cudaMemcpyAsync(dcen.p, cen.data(), cen.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
-            rc = cniic_dev_recolor(ctx, d_rgb, n, d_keys, cniic_kmeans_device_assign(km), u, dcen.as<int32_t>(), nullptr, dlut.as<uint32_t>(), d_out);
+            const uint32_t *pts_sorted;
+            const uint16_t *assign_sorted;
+            cniic_kmeans_sorted_view(km, &pts_sorted, &assign_sorted);
+            if (u) {
+                build_lut_sorted_kernel<<<grid_for(ctx, u), 256, 0, ctx->stream>>>(pts_sorted, assign_sorted, u, dcen.as<int32_t>(), dlut.as<uint32_t>());
+                ctx->launches++;
+            }
+            if (n) {
+                recolor_kernel<<<grid_for(ctx, n, 4), 256, 0, ctx->stream>>>(d_rgb, n, dlut.as<uint32_t>(), d_out);
+                ctx->launches++;
+            }
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "recolour failed");
         }
     }
     if (km) cniic_kmeans_close(km);
-    cniic_cache_free(ctx, d_bins);
-    cniic_cache_free(ctx, d_keys);
-    cniic_cache_free(ctx, d_counts);
     if (rc != CNIIC_OK) return rc;
     if (cen_host) *cen_host = cen;
     // kmeans.rs:41-57
@@ -1448,21 +1638,36 @@ int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uin
     return CNIIC_OK;
 }
 
+// device-resident form (bench.py's C2 `value`): image in HBM, recoloured image (nullable) to HBM, centroids to the host
+extern "C" int cniic_cluster_colors_device(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n_pixels, uint32_t k, uint32_t max_iters, int tie_rule,
+                                           uint8_t *d_out_rgb, int32_t *out_centroids, size_t *out_n_unique, cniic_kmeans_stats *stats) {
+    if (!ctx || !d_rgb) return CNIIC_ERR_BAD_ARG;
+    if (k == 0 || k > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d", CNIIC_MAX_K);
+    if (n_pixels >= (size_t(1) << 31)) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "image too large");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<int32_t> cen;
+    const int rc = cniic_dev_cluster_colors(ctx, d_rgb, n_pixels, k, max_iters, tie_rule, d_out_rgb, &cen, stats, out_n_unique);
+    if ((rc == CNIIC_OK || rc == CNIIC_ERR_TOO_FEW_ACTIVE) && out_centroids && !cen.empty()) memcpy(out_centroids, cen.data(), cen.size() * 4);
+    return rc;
+}
+
 extern "C" int cniic_cluster_colors(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, uint32_t k, uint32_t max_iters,
                                     int tie_rule, uint8_t *out_rgb, uint8_t *out_centroids, cniic_kmeans_stats *stats) {
-    if (!ctx || !rgb || !out_rgb) return CNIIC_ERR_BAD_ARG;
+    if (!ctx || !rgb) return CNIIC_ERR_BAD_ARG;
     if (k == 0 || k > CNIIC_MAX_K) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "k must be in 1..%d", CNIIC_MAX_K);
     const size_t n = (size_t)w * h;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     DevBuf din(ctx), dout(ctx);
     CU_TRY(ctx, din.alloc(n * 3));
-    CU_TRY(ctx, dout.alloc(n * 3));
+    if (out_rgb) CU_TRY(ctx, dout.alloc(n * 3));
     CU_TRY(ctx, cudaMemcpyAsync(din.p, rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<int32_t> cen;
-    const int rc = cniic_dev_cluster_colors(ctx, din.as<uint8_t>(), n, k, max_iters, tie_rule, dout.as<uint8_t>(), &cen, stats);
+    const int rc = cniic_dev_cluster_colors(ctx, din.as<uint8_t>(), n, k, max_iters, tie_rule, out_rgb ? dout.as<uint8_t>() : nullptr, &cen, stats, nullptr);
     if (rc != CNIIC_OK && rc != CNIIC_ERR_TOO_FEW_ACTIVE) return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(out_rgb, dout.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_rgb) {
+        CU_TRY(ctx, cudaMemcpyAsync(out_rgb, dout.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     if (out_centroids)
         for (size_t i = 0; i < cen.size(); i++) out_centroids[i] = (uint8_t)cen[i];
     return rc;

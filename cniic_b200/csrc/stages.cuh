@@ -4,6 +4,19 @@
 
 #include "common.cuh"
 
+// Unique colours of an image as weighted points, deduplicated AND Morton-sorted by one histogram + ordered compaction (stages.cu):
+// d_pts = packed r | g<<8 | b<<16, d_wts = pixel count (clusterc.rs:23), d_perm = canonical index (ascending key r<<16|g<<8|b) of
+// every sorted point; d_keybits / d_word_prefix = presence bitmap over the key space and its per-word exclusive prefix.
+struct UniqueColours {
+    uint32_t *d_pts = nullptr, *d_wts = nullptr, *d_perm = nullptr, *d_keybits = nullptr, *d_word_prefix = nullptr;
+    size_t u = 0;
+};
+int cniic_dev_unique_colours(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, UniqueColours *out);
+void cniic_unique_colours_free(cniic_ctx *ctx, UniqueColours *uc);
+struct cniic_kmeans;
+int cniic_kmeans_open_unique(cniic_ctx *ctx, UniqueColours *uc, uint32_t k, int tie_rule, cniic_kmeans **out);  // takes over uc's arrays
+void cniic_kmeans_sorted_view(cniic_kmeans *km, const uint32_t **pts_sorted, const uint16_t **assign_sorted);
+
 int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins, size_t nbins, uint32_t **d_keys, unsigned long long **d_counts, size_t *n_unique);
 int cniic_dev_hist_rgb_bins(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t **d_bins);
 int cniic_dev_hist_delta_bins(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint32_t **d_bins, size_t *nbins);
@@ -15,8 +28,8 @@ int cniic_dev_keys_to_points(cniic_ctx *ctx, const uint32_t *d_keys, const unsig
 int cniic_dev_hilbert_gather(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint8_t *d_out);
 int cniic_dev_undelta(cniic_ctx *ctx, const int16_t *d_diff, uint32_t w, uint32_t h, uint8_t *d_out);
 int cniic_dev_sse(cniic_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, size_t nbytes, uint64_t *out);
-int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t k, uint32_t max_iters, int tie_rule, uint8_t *d_out,
-                             std::vector<int32_t> *cen_host, cniic_kmeans_stats *stats);
+int cniic_dev_cluster_colors(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t k, uint32_t max_iters, int tie_rule, uint8_t *d_out /* nullable */,
+                             std::vector<int32_t> *cen_host, cniic_kmeans_stats *stats, size_t *n_unique /* nullable */);
 int cniic_dev_huffman_pack(cniic_ctx *ctx, int src_kind, const void *d_src, size_t n, const uint32_t *d_keys, size_t nsym,
                            const std::vector<uint64_t> &codes, const std::vector<uint8_t> &lens, std::vector<uint8_t> *out);
 // Parallel Huffman decoding (huffdec.cu; semantics of huf.rs:187-206): `payload` = HOST bytes, MSB-first bit string; trie as

@@ -174,9 +174,10 @@ int cniic_hist_rgb(cniic_ctx *ctx, const uint8_t *rgb, size_t n, uint32_t *out_k
  * keys/assign describe the clustered unique colours (ascending keys), centroids = k x 3.                          */
 int cniic_recolor_rgb(cniic_ctx *ctx, const uint8_t *rgb, size_t n, const uint32_t *keys, const uint16_t *assign,
                       size_t n_unique, const uint8_t *centroids, uint32_t k, uint8_t *out_rgb);
-/* Whole front half of ClusterColors::encode: unique colours -> weighted K-means -> recolour (clusterc.rs:19-47). */
+/* Whole front half of ClusterColors::encode: unique colours -> weighted K-means -> recolour (clusterc.rs:19-47).  The unique
+ * colours enter K-means in the canonical order above (ascending key); out_rgb == NULL skips the recolour pass and its copy.   */
 int cniic_cluster_colors(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, uint32_t k, uint32_t max_iters,
-                         int tie_rule, uint8_t *out_rgb, uint8_t *out_centroids /* 3k, nullable */,
+                         int tie_rule, uint8_t *out_rgb /* nullable */, uint8_t *out_centroids /* 3k, nullable */,
                          cniic_kmeans_stats *stats);
 
 /* ---- voronoi decode fill (clusterc.rs:179-186) ------------------------------------------------------------
@@ -235,6 +236,10 @@ void cniic_device_free(cniic_ctx *ctx, void *p);
 int cniic_memcpy_h2d(cniic_ctx *ctx, void *d, const void *h, size_t bytes);
 int cniic_memcpy_d2h(cniic_ctx *ctx, void *h, const void *d, size_t bytes);
 /* device-pointer forms of the per-pixel stages (same semantics as the host forms above) */
+/* cniic_cluster_colors on an image resident in HBM: d_out_rgb (nullable) receives the recoloured image in HBM, out_centroids
+ * (host, nullable) k x 3 int32, *out_n_unique (nullable) the number of distinct colours K-means iterated over.            */
+int cniic_cluster_colors_device(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n_pixels, uint32_t k, uint32_t max_iters, int tie_rule,
+                                uint8_t *d_out_rgb, int32_t *out_centroids, size_t *out_n_unique, cniic_kmeans_stats *stats);
 int cniic_voronoi_fill_device(cniic_ctx *ctx, const uint32_t *d_cxy, const uint8_t *d_crgb, uint32_t k, uint32_t w,
                               uint32_t h, uint32_t y0, uint32_t h_local, uint8_t *d_out_rgb);
 int cniic_delta_i16_device(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, int16_t *d_out);

@@ -5,6 +5,7 @@ The kernel sources are used as they are; three purely syntactic rewrites make th
   1. `kernel<<<grid, block, smem, stream>>>(args);`  ->  `emu::launch(emu::LaunchCfg(grid, block, smem, stream), [&]{ kernel(args); }, "kernel");`
   2. `extern __shared__ T name[];`                   ->  `T *name = reinterpret_cast<T *>(emu::dyn_smem());`
   3. `asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));`  ->  `d = emu_ptx_dp4a_u32_u32(a, b, c);`
+     (`asm volatile("griddepcontrol.wait;" ::: "memory");` and `...launch_dependents...` -> nothing: launches are sequential here)
 Output: tests/emu/_build/libcniic_emu.so (git-ignored).  Loaded only by tests/test_emu_kernels.py -- never by cniic_b200.
 """
 from __future__ import annotations
@@ -78,11 +79,14 @@ def rewrite_launches(text: str) -> str:
 
 
 ASM_RE = re.compile(r'asm\s*(?:volatile)?\s*\(\s*"([a-z0-9_.]+)\s+%0,\s*%1,\s*%2,\s*%3;"\s*:\s*"=r"\((\w+)\)\s*:\s*"r"\((\w+)\),\s*"r"\((\w+)\),\s*"r"\((\w+)\)\s*\)\s*;')
+# programmatic-dependent-launch control instructions have no effect when launches run one after another
+NOOP_ASM_RE = re.compile(r'asm\s*(?:volatile)?\s*\(\s*"griddepcontrol\.(?:wait|launch_dependents);"\s*:::\s*"memory"\s*\)\s*;')
 SHARED_RE = re.compile(r"extern\s+__shared__\s+([\w:<> ]+?)\s+(\w+)\s*\[\s*\]\s*;")
 
 
 def transform(text: str) -> str:
     text = ASM_RE.sub(lambda m: f"{m.group(2)} = emu_ptx_{m.group(1).replace('.', '_')}({m.group(3)}, {m.group(4)}, {m.group(5)});", text)
+    text = NOOP_ASM_RE.sub(";", text)
     text = SHARED_RE.sub(lambda m: f"{m.group(1)} *{m.group(2)} = reinterpret_cast<{m.group(1)} *>(emu::dyn_smem());", text)
     if "asm" in re.sub(r"//.*", "", text) and re.search(r"\basm\s*(volatile)?\s*\(", text):
         raise ValueError("an inline asm statement was not rewritten: extend ASM_RE / the shim")

@@ -124,6 +124,16 @@ struct LaunchCfg {
 void launch(const LaunchCfg &cfg, const std::function<void()> &body, const char *name);
 }  // namespace emu
 
+// cudaLaunchKernelEx with launch attributes (programmatic dependent launch): the emulation runs launches one after another
+enum cudaLaunchAttributeID { cudaLaunchAttributeProgrammaticStreamSerialization = 4 };
+struct cudaLaunchAttributeValue { int programmaticStreamSerializationAllowed; };
+struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
+struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes; cudaStream_t stream; cudaLaunchAttribute *attrs; unsigned numAttrs; };
+template <class... KA, class... A> static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t *c, void (*k)(KA...), A &&...a) {
+    emu::launch(emu::LaunchCfg(c->gridDim, c->blockDim, c->dynamicSmemBytes, c->stream), [&]() { k(KA(a)...); }, "cudaLaunchKernelEx");
+    return cudaSuccess;
+}
+
 #define threadIdx (emu::g_cur->tid)
 #define blockIdx (emu::g_cur->bid)
 #define blockDim (emu::g_cur->bdim)

@@ -214,6 +214,39 @@ def test_cluster_colors_pipeline(ctx, k):
     assert np.array_equal(cen, ocen) and np.array_equal(out, oout)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 5, 8, 13])
+def test_cluster_colors_unique_colour_path_edge_cases(ctx, seed):
+    """The unique colours reach K-means deduplicated and Morton-sorted straight out of the histogram (no sort); the canonical order
+    (init chunks, empty-cluster rule: kmeans.rs:61-108, 117-134 stand-in) stays ascending r<<16|g<<8|b.  Palette images with few
+    colours, heavy counts, k close to the number of colours, odd sizes (unaligned 4-pixel groups), flat runs."""
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(3, 90)), int(rng.integers(3, 70))
+    npal = int(rng.integers(2, 40))
+    palette = rng.integers(0, 256, size=(npal, 3), dtype=np.uint8)
+    if seed % 2:  # clustered palette: many near-duplicates -> empty clusters
+        palette = np.clip(palette[rng.integers(0, max(1, npal // 4), npal)].astype(int) + rng.integers(-2, 3, (npal, 3)), 0, 255).astype(np.uint8)
+    img = palette[rng.integers(0, npal, size=(h, w))]
+    img[: h // 3] = palette[0]  # a flat area: runs of equal neighbours
+    u = len(np.unique(img.reshape(-1, 3), axis=0))
+    for k in sorted({1, max(1, u // 2), u}):
+        for max_iters in (1, 0):
+            oout, ocen, oit = O.cluster_colors(img, k, max_iters=max_iters)
+            out, cen, st = ctx.cluster_colors(img, k, max_iters=max_iters)
+            assert st.iterations == oit, (k, max_iters)
+            assert np.array_equal(cen, ocen) and np.array_equal(out, oout), (k, max_iters)
+    with pytest.raises(cb.CniicError) as e:  # kmeans.rs:67-68: fewer points (unique colours) than clusters
+        ctx.cluster_colors(img, u + 1)
+    assert e.value.code == cb.ERR_TOO_FEW_POINTS
+    # device-resident form + the centroid-only host form agree with the full one
+    d = ctx.device_alloc(img.nbytes)
+    ctx.h2d(d, img)
+    cen_d, nu, st = ctx.cluster_colors_device(d, w * h, max(1, u // 2), max_iters=3)
+    ctx.device_free(d)
+    _, ocen3, _ = O.cluster_colors(img, max(1, u // 2), max_iters=3)
+    none_img, cen_h, _ = ctx.cluster_colors(img, max(1, u // 2), max_iters=3, want_image=False)
+    assert nu == u and none_img is None and np.array_equal(cen_d, ocen3) and np.array_equal(cen_h, ocen3)
+
+
 def test_hist_rgb_and_recolor(ctx):
     img = cb.synth_image_host(300, 100, 4, 9)
     keys, cnts = ctx.hist_rgb(img)
