@@ -87,9 +87,6 @@ struct KmDev {
     int p2p;                                   // 1: sums live in the IPC exchange region, no NCCL call
     int my_rank;
     unsigned long long *const *peer_base;      // [world] base of every rank's exchange region (peer-mapped)
-    // points handed over as deduplicated, Morton-sorted unique colours (stages.cu: cniic_dev_unique_colours): the point with canonical
-    // index j is the j-th set bit of the key bitmap; rgb == nullptr
-    const uint32_t *ubits, *uprefix;
     const uint2 *tile_box;  // per 2048-point tile of the sorted copy: {bytewise min, bytewise max} of the packed colours
     const uint4 *wseg;      // culled D = 3, v2: per 256-point warp segment {box min, box max, sum r | sum g << 16, sum b | count << 16}
     const unsigned long long *wseg64;  // weighted points: per warp segment {sum r*w, sum g*w, sum b*w, sum w}
@@ -578,7 +575,7 @@ __global__ void __launch_bounds__(256) km_tile_boxes2(const uint32_t *__restrict
     __shared__ uint32_t s_mn[8], s_mx[8];
     const uint32_t base = blockIdx.x * TILE + threadIdx.x * PX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t mn = 0xffffffffu, mx = 0u, cnt = 0;
+    uint32_t mn = 0xffffffffu, mx = 0u, cnt = 0, wmax = 0;
     int sr = 0, sg = 0, sb = 0;
     unsigned long long wr = 0, wg = 0, wb = 0, ww = 0;  // weighted sums (weighted sessions only)
     for (int p = 0; p < PX; p++)
@@ -588,9 +585,11 @@ __global__ void __launch_bounds__(256) km_tile_boxes2(const uint32_t *__restrict
             sr += v & 0xff; sg += (v >> 8) & 0xff; sb += (v >> 16) & 0xff; cnt++;
             if (wts_sorted) {
                 const unsigned long long wq = wts_sorted[base + p];
+                wmax = max(wmax, (uint32_t)wq);
                 wr += (v & 0xff) * wq; wg += ((v >> 8) & 0xff) * wq; wb += ((v >> 16) & 0xff) * wq; ww += wq;
             }
         }
+    wmax = __reduce_max_sync(0xffffffffu, wmax);
     for (int o = 16; o > 0; o >>= 1) {
         mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = __vmaxu4(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -603,7 +602,9 @@ __global__ void __launch_bounds__(256) km_tile_boxes2(const uint32_t *__restrict
     }
     if (lane == 0) {
         s_mn[warp] = mn; s_mx[warp] = mx;
-        wseg[blockIdx.x * 8 + warp] = make_uint4(mn & 0xffffffu, mx & 0xffffffu, uint32_t(sr) | (uint32_t(sg) << 16), uint32_t(sb) | (cnt << 16));
+        // bit 31: some weight of the segment needs more than 16 bits (the kernel then accumulates in 64-bit arithmetic)
+        wseg[blockIdx.x * 8 + warp] = make_uint4(mn & 0xffffffu, mx & 0xffffffu, uint32_t(sr) | (uint32_t(sg) << 16),
+                                                 uint32_t(sb) | (cnt << 16) | (wmax >= 65536u ? 0x80000000u : 0u));
         if (wts_sorted) {
             unsigned long long *o64 = wseg64 + 4 * (size_t)(blockIdx.x * 8 + warp);
             o64[0] = wr; o64[1] = wg; o64[2] = wb; o64[3] = ww;
@@ -683,7 +684,7 @@ __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
         // this warp's own box
         const int wr0 = seg.x & 0xff, wg0 = (seg.x >> 8) & 0xff, wb0 = (seg.x >> 16) & 0xff;
         const int wr1 = seg.y & 0xff, wg1 = (seg.y >> 8) & 0xff, wb1 = (seg.y >> 16) & 0xff;
-        const uint32_t seg_pts = seg.w >> 16;
+        const uint32_t seg_pts = (seg.w >> 16) & 0x1ffu;
 
         int best[PX], bi[PX];
 #pragma unroll
@@ -796,7 +797,6 @@ __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
         if (WEIGHTED) {
             const int lead_w = __shfl_sync(0xffffffffu, (int)idx[0], 0);  // unconditional: every lane must reach the shuffle
             const bool warp_uniform_w = __all_sync(0xffffffffu, uniform && (int)idx[0] == lead_w);
-            unsigned long long ar = 0, ag = 0, ab = 0, aw = 0;
             int run = -1;
             if (warp_uniform_w) {
                 // all 256 points of the segment land in one cluster: its precomputed weighted sums, four adds per warp
@@ -805,24 +805,64 @@ __device__ __forceinline__ void km_assign_rgb_cull2_body(const KmDev d) {
                     smem_add64(&s_acc64[4 * lead_w], ws[0]); smem_add64(&s_acc64[4 * lead_w + 1], ws[1]);
                     smem_add64(&s_acc64[4 * lead_w + 2], ws[2]); smem_add64(&s_acc64[4 * lead_w + 3], ws[3]);
                 }
-            } else
+            } else if (!(seg.w >> 31)) {
+                // every weight of the segment fits 16 bits (pixel counts of unique colours almost always do): a lane's sums stay
+                // below 8 * 255 * 2^16 < 2^32, so 32-bit arithmetic is exact and only the shared accumulator is 64 bits wide
+                uint32_t wq[PX];
+                if (nv == PX) {
+                    const uint4 wa = __ldg(reinterpret_cast<const uint4 *>(d.wts_sorted + base)), wb = __ldg(reinterpret_cast<const uint4 *>(d.wts_sorted + base) + 1);
+                    wq[0] = wa.x; wq[1] = wa.y; wq[2] = wa.z; wq[3] = wa.w; wq[4] = wb.x; wq[5] = wb.y; wq[6] = wb.z; wq[7] = wb.w;
+                } else {
 #pragma unroll
-            for (int p = 0; p < PX; p++) {
-                if (p < nv) {
-                    if (idx[p] != run) {
-                        if (run >= 0) {
-                            smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
-                            smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
-                        }
-                        run = idx[p]; ar = ag = ab = aw = 0;
-                    }
-                    const unsigned long long wq = d.wts_sorted[base + p];
-                    ar += (px[p] & 0xff) * wq; ag += ((px[p] >> 8) & 0xff) * wq; ab += ((px[p] >> 16) & 0xff) * wq; aw += wq;
+                    for (int p = 0; p < PX; p++) wq[p] = p < nv ? d.wts_sorted[base + p] : 0u;
                 }
-            }
-            if (run >= 0) {
-                smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
-                smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
+                uint32_t ar = 0, ag = 0, ab = 0, aw = 0;
+                if (uniform) {  // my 8 points land in one cluster
+#pragma unroll
+                    for (int p = 0; p < PX; p++) {
+                        ar += (px[p] & 0xff) * wq[p]; ag += ((px[p] >> 8) & 0xff) * wq[p]; ab += (px[p] >> 16) * wq[p]; aw += wq[p];
+                    }
+                    smem_add64(&s_acc64[4 * idx[0]], ar); smem_add64(&s_acc64[4 * idx[0] + 1], ag);
+                    smem_add64(&s_acc64[4 * idx[0] + 2], ab); smem_add64(&s_acc64[4 * idx[0] + 3], aw);
+                } else {
+#pragma unroll
+                    for (int p = 0; p < PX; p++) {
+                        if (p < nv) {
+                            if (idx[p] != run) {
+                                if (run >= 0) {
+                                    smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
+                                    smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
+                                }
+                                run = idx[p]; ar = ag = ab = aw = 0;
+                            }
+                            ar += (px[p] & 0xff) * wq[p]; ag += ((px[p] >> 8) & 0xff) * wq[p]; ab += (px[p] >> 16) * wq[p]; aw += wq[p];
+                        }
+                    }
+                    if (run >= 0) {
+                        smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
+                        smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
+                    }
+                }
+            } else {
+                unsigned long long ar = 0, ag = 0, ab = 0, aw = 0;
+#pragma unroll
+                for (int p = 0; p < PX; p++) {
+                    if (p < nv) {
+                        if (idx[p] != run) {
+                            if (run >= 0) {
+                                smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
+                                smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
+                            }
+                            run = idx[p]; ar = ag = ab = aw = 0;
+                        }
+                        const unsigned long long wq = d.wts_sorted[base + p];
+                        ar += (px[p] & 0xff) * wq; ag += ((px[p] >> 8) & 0xff) * wq; ab += ((px[p] >> 16) & 0xff) * wq; aw += wq;
+                    }
+                }
+                if (run >= 0) {
+                    smem_add64(&s_acc64[4 * run], ar); smem_add64(&s_acc64[4 * run + 1], ag);
+                    smem_add64(&s_acc64[4 * run + 2], ab); smem_add64(&s_acc64[4 * run + 3], aw);
+                }
             }
         } else {
             const int lead = __shfl_sync(0xffffffffu, (int)idx[0], 0);  // unconditional: every lane must reach the shuffle
@@ -1350,8 +1390,9 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
     const uint32_t k = d.k;
     uint4 *t_ent = smem_raw;                                              // TCAP x {cpk, cxy, kb, id}
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(t_ent + TCAP);         // 6*k u32
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_acc + 6 * k);       // level-1 candidates of the current supertile (ascending ids)
     __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_box[8];  // min r,g,b ; max r,g,b ; U
+    __shared__ uint32_t s_box[8];  // [6] = U of the tile, [7] = U of the supertile
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t i = tid; i < 6 * k; i += THREADS) s_acc[i] = 0u;
@@ -1363,8 +1404,62 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
     unsigned long long moved = 0, pairs_local = 0;
     uint32_t since_flush = 0;
 
-    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const uint32_t ty = uint32_t(tile / tiles_x), tx = uint32_t(tile % tiles_x);
+    // Tiles are enumerated SUPERTILE BY SUPERTILE (8 x 8 tiles) and every CTA owns a contiguous range of that order, so it meets
+    // one or two supertiles per launch and computes their level-1 candidate lists itself (position-only bounds over all k
+    // centroids, ~2 us per list): the former km_supercull launch -- a whole kernel of latency per Lloyd iteration, which is what
+    // limits a row-sharded run -- is gone.
+    constexpr uint32_t STX = SW / TW, STY = SH / TH;
+    const unsigned long long per_cta = (tiles + gridDim.x - 1) / gridDim.x;
+    const unsigned long long t_begin = blockIdx.x * per_cta, t_end = min(tiles, t_begin + per_cta);
+    uint32_t cur_sup = 0xffffffffu, m = 0;
+    for (unsigned long long tile_seq = t_begin; tile_seq < t_end; tile_seq++) {
+        uint32_t tx, ty, sup;
+        {
+            const uint32_t row_tiles = tiles_x * STY;                       // tiles of a full row of supertiles
+            const uint32_t sy = uint32_t(tile_seq / row_tiles);
+            const uint32_t rem = uint32_t(tile_seq - (unsigned long long)sy * row_tiles);
+            const uint32_t rows_in = min(STY, tiles_y - sy * STY);
+            const uint32_t sx = rem / (STX * rows_in);
+            const uint32_t rem2 = rem - sx * STX * rows_in;
+            const uint32_t cols_in = min(STX, tiles_x - sx * STX);
+            tx = sx * STX + rem2 % cols_in;
+            ty = sy * STY + rem2 / cols_in;
+            sup = sy * d.super_x + sx;
+        }
+        const unsigned long long tile = (unsigned long long)ty * tiles_x + tx;  // raster index (static per-tile tables)
+        if (sup != cur_sup) {
+            __syncthreads();  // the previous tile is done with s_list / s_box
+            const int sx0 = (sup % d.super_x) * SW, syl0 = (sup / d.super_x) * SH;
+            const int sx1 = min(sx0 + SW, (int)w) - 1, sy0 = d.y0 + syl0, sy1 = d.y0 + min(syl0 + SH, (int)hl) - 1;
+            if (tid == 0) s_box[7] = 0xffffffffu;
+            __syncthreads();
+            uint32_t um = 0xffffffffu;
+            for (uint32_t c = tid; c < k; c += THREADS) {
+                const uint32_t cxy = d.g_cxy[c];
+                const int cx = cxy & 0xffff, cy = cxy >> 16;
+                um = min(um, uint32_t(sq(max(abs(cx - sx0), abs(cx - sx1))) + sq(max(abs(cy - sy0), abs(cy - sy1)))));
+            }
+            for (int o = 16; o > 0; o >>= 1) um = min(um, __shfl_xor_sync(0xffffffffu, um, o));
+            if (lane == 0) atomicMin(&s_box[7], um);
+            __syncthreads();
+            const uint32_t US = s_box[7] + 3u * 255u * 255u;  // colour part of UB for the full colour cube
+            uint32_t placed = 0;
+            for (uint32_t cb = 0; cb < k; cb += THREADS) {
+                const uint32_t c = cb + tid;
+                bool keep = false;
+                if (c < k) {
+                    const uint32_t cxy = d.g_cxy[c];
+                    const int cx = cxy & 0xffff, cy = cxy >> 16;
+                    keep = uint32_t(sq(max(0, max(sx0 - cx, cx - sx1))) + sq(max(0, max(sy0 - cy, cy - sy1)))) <= US;
+                }
+                uint32_t tot;
+                const uint32_t r = block_rank256(keep, s_warp, &tot);
+                if (keep) s_list[placed + r] = (uint16_t)c;
+                placed += tot;
+            }
+            m = placed;
+            cur_sup = sup;
+        }
         const int x0 = tx * TW, yl0 = ty * TH;
         const int vw = min(TW, int(w) - x0), vh = min(TH, int(hl) - yl0);
         const int yg0 = d.y0 + yl0;
@@ -1408,9 +1503,7 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
         const int bx0 = x0, bx1 = x0 + vw - 1, by0 = yg0, by1 = yg0 + vh - 1;
         const int r0 = box.x & 0xff, g0 = (box.x >> 8) & 0xff, b0 = (box.x >> 16) & 0xff;
         const int r1 = box.y & 0xff, g1 = (box.y >> 8) & 0xff, b1 = (box.y >> 16) & 0xff;
-        const uint32_t sup = (ty / (SH / TH)) * d.super_x + tx / (SW / TW);
-        const uint32_t m = d.sc_count[sup];
-        const uint16_t *list = d.sc_list + (size_t)sup * k;
+        const uint16_t *list = s_list;
         // ---- pass 1: U = min_c UB_c over the supertile's list (the first 256 candidates stay in registers for pass 2) ----
         uint32_t umin = 0xffffffffu;
         uint4 ent0 = make_uint4(0, 0, 0, 0);
@@ -1577,19 +1670,11 @@ __device__ __forceinline__ void fetch_point(const KmDev &d, unsigned long long l
         out[0] = int32_t(local_i % d.w);
         out[1] = int32_t(d.y0 + local_i / d.w);
         out[2] = d.rgb[3 * local_i]; out[3] = d.rgb[3 * local_i + 1]; out[4] = d.rgb[3 * local_i + 2];
-    } else if (d.ubits) {
-        // unique-colour session: select the local_i-th set bit of the key bitmap (last word whose exclusive prefix is <= local_i)
-        const uint32_t j = (uint32_t)local_i;
-        uint32_t lo = 0, hi = 1u << 19;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (d.uprefix[mid] <= j) lo = mid;
-            else hi = mid;
-        }
-        uint32_t bits = d.ubits[lo];
-        for (uint32_t skip = j - d.uprefix[lo]; skip; skip--) bits &= bits - 1;
-        const uint32_t key = (lo << 5) | uint32_t(__ffs(bits) - 1);
-        out[0] = int32_t(key >> 16); out[1] = int32_t((key >> 8) & 0xff); out[2] = int32_t(key & 0xff);
+    } else if (!d.rgb) {
+        // unique-colour session (stages.cu: cniic_dev_unique_colours): the points only exist as the Morton-sorted list, which is
+        // also their canonical order
+        const uint32_t v = d.pts_sorted[local_i];
+        out[0] = int32_t(v & 0xff); out[1] = int32_t((v >> 8) & 0xff); out[2] = int32_t(v >> 16);
     } else {
         out[0] = d.rgb[3 * local_i]; out[1] = d.rgb[3 * local_i + 1]; out[2] = d.rgb[3 * local_i + 2];
     }
@@ -2078,7 +2163,6 @@ struct cniic_kmeans {
     unsigned long long *d_wseg64 = nullptr;  // ... and weighted sums (weighted sessions)
     bool v2 = false;          // culled D = 3: second kernel version (default)
     uint32_t *d_sorted = nullptr, *d_perm = nullptr, *d_wsorted = nullptr;  // colour-sorted copy (culled D = 3)
-    uint32_t *d_ubits = nullptr, *d_uprefix = nullptr;  // unique-colour session: key bitmap + word prefix (owned)
     uint16_t *d_assign_orig = nullptr;  // assignment mapped back to original order (filled on demand)
     bool cull = true;        // exact culling (CNIIC_KMEANS_NO_CULL in desc.flags selects brute force)
     uint32_t iter_seen = 0;  // state.iter at the end of the previous run (0 after reset)
@@ -2100,7 +2184,7 @@ static void km_report_launches(cniic_kmeans *km) {
 static int km_launch_assign(cniic_kmeans *km) {
     cniic_ctx *ctx = km->ctx;
     if (km->D == 5 && km->cull) {
-        if (km->dev.super_x && km->dev.super_y) {  // a rank may hold no rows at all
+        if (!km->v2 && km->dev.super_x && km->dev.super_y) {  // first kernel version: level-1 lists from their own launch
             KM_LAUNCH(km_supercull, km->dev.super_x * km->dev.super_y, THREADS, 0, km->dev);
             km->launches++;
         }
@@ -2242,10 +2326,8 @@ static int km_open_impl(cniic_ctx *ctx, const cniic_kmeans_desc *desc, UniqueCol
         km->d_boxes = static_cast<uint2 *>(cniic_cache_alloc(ctx, ntiles * 8));
         if (!km->d_boxes) return fail(CNIIC_ERR_CUDA);
         if (uc) {  // take ownership
-            km->d_sorted = uc->d_pts; km->d_perm = uc->d_perm; km->d_wsorted = uc->d_wts; km->d_ubits = uc->d_keybits; km->d_uprefix = uc->d_word_prefix;
+            km->d_sorted = uc->d_pts; km->d_wsorted = uc->d_wts;  // (no permutation: sorted order = canonical order)
             *uc = UniqueColours();
-            dv.ubits = km->d_ubits;
-            dv.uprefix = km->d_uprefix;
         } else {
             km->d_sorted = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (n + 8) * 4));
             km->d_perm = static_cast<uint32_t *>(cniic_cache_alloc(ctx, n * 4));
@@ -2295,7 +2377,7 @@ static int km_open_impl(cniic_ctx *ctx, const cniic_kmeans_desc *desc, UniqueCol
     dv.brute = km->cull ? 0 : 1;
     // shared memory + persistent grid
     if (D == 5 && km->cull) {
-        km->smem = size_t(TCAP) * 16 + size_t(k) * 24 + 16;
+        km->smem = size_t(TCAP) * 16 + size_t(k) * 24 + size_t((k + 7) & ~7u) * 2 + 16;  // survivors, accumulators, level-1 list (v2)
         KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb_cull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
         KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb_cull2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     } else if (D == 5) {
@@ -2611,7 +2693,7 @@ int km_batch_launch_iteration(const BatchPlan &bp, uint32_t *launched) {
     cniic_ctx *ctx = bp.ctx;
     const dim3 grid(bp.gx_assign, bp.count);
     if (bp.D == 5 && bp.cull) {
-        if (bp.gx_super) {
+        if (bp.gx_super && !bp.v2) {  // (the second kernel version computes the level-1 lists itself)
             km_supercull_batch<<<dim3(bp.gx_super, bp.count), THREADS, 0, ctx->stream>>>(bp.d_batch);
             (*launched)++;
         }
@@ -2856,8 +2938,6 @@ extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
     cniic_cache_free(km->ctx, km->d_perm);
     cniic_cache_free(km->ctx, km->d_wsorted);
     cniic_cache_free(km->ctx, km->d_assign_orig);
-    cniic_cache_free(km->ctx, km->d_ubits);
-    cniic_cache_free(km->ctx, km->d_uprefix);
     cniic_pinned_put(km->ctx, km->h_state);
     if (km->ev0) km->ctx->event_pool.push_back(km->ev0);
     if (km->ev1) km->ctx->event_pool.push_back(km->ev1);

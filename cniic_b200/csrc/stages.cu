@@ -73,17 +73,21 @@ __global__ void __launch_bounds__(256) fill_supercull_kernel(const uint32_t *__r
     if (tid == 0) counts[blockIdx.x] = placed;
 }
 
-// level 2: 64x64 tile per CTA, bounds over the supertile's list, survivors scored per pixel (first minimum = lowest id)
+// level 2 + 3: 64x64 tile per CTA, bounds over the supertile's list (level 2, candidates compacted in id order into shared memory),
+// then every WARP bounds the tile's candidates again against its own 64x8 strip (level 3: same argument on a box inside the tile
+// box -- U_w = min_c maxdist^2(c, strip) bounds every pixel's minimum, a centroid with mindist^2(c, strip) > U_w can neither win nor
+// tie) and scores only those, broadcast by shuffle in ascending id order: strict "<" keeps the FIRST minimum = lowest id
+// (Iterator::min_by_key, clusterc.rs:182-184).  ~5 centroids per pixel instead of ~20 after level 2 alone.
 __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ cxy, const uint8_t *__restrict__ crgb, uint32_t k,
                                                    uint32_t w, uint32_t y0, uint32_t h_local, uint32_t super_x,
                                                    const uint16_t *__restrict__ lists, const uint32_t *__restrict__ counts,
                                                    uint8_t *__restrict__ out) {
     extern __shared__ uint4 fsm[];
     int2 *s_c = reinterpret_cast<int2 *>(fsm);                 // candidate coordinates
-    uint16_t *s_i = reinterpret_cast<uint16_t *>(s_c + k);     // candidate ids
+    uint32_t *s_col = reinterpret_cast<uint32_t *>(s_c + k);   // candidate colours, packed r | g<<8 | b<<16
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_U;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_x = (w + FT - 1) / FT, tiles_y = (h_local + FT - 1) / FT;
     for (uint32_t tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
         const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ 
             umin = min(umin, dx * dx + dy * dy);
         }
         for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-        if ((tid & 31) == 0) atomicMin(&s_U, umin);
+        if (lane == 0) atomicMin(&s_U, umin);
         __syncthreads();
         const uint32_t U = s_U;
         uint32_t ncand = 0;
@@ -121,50 +125,70 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ 
             }
             uint32_t tot;
             const uint32_t r = block_rank256(keep, s_warp, &tot);
-            if (keep) { s_c[ncand + r] = make_int2(cx, cy); s_i[ncand + r] = (uint16_t)c; }
+            if (keep) {
+                s_c[ncand + r] = make_int2(cx, cy);
+                s_col[ncand + r] = uint32_t(crgb[3 * c]) | (uint32_t(crgb[3 * c + 1]) << 8) | (uint32_t(crgb[3 * c + 2]) << 16);
+            }
             ncand += tot;
         }
         __syncthreads();
-        // thread -> one row of the tile, 16 consecutive pixels
-        const int row = tid >> 2, seg = (tid & 3) * 16;
-        const int yl = yl0 + row, gy = y0 + yl;
-        if (yl <= yl1) {
-            uint32_t bd[16];
-            uint32_t bi[16];
+        // warp -> a 64 x 8 strip of the tile; lane -> one row of it, 16 consecutive pixels
+        const int wy0 = gy0 + warp * 8, wy1 = min(wy0 + 7, gy1);
+        if (wy0 > gy1) continue;  // (warp-uniform; the strip lies below the image / shard)
+        uint32_t uw = 0xffffffffu;
+        for (uint32_t j = lane; j < ncand; j += 32) {
+            const int2 c = s_c[j];
+            const uint32_t dx = max(abs(c.x - x0), abs(c.x - x1)), dy = max(abs(c.y - wy0), abs(c.y - wy1));
+            uw = min(uw, dx * dx + dy * dy);
+        }
+        uw = __reduce_min_sync(0xffffffffu, uw);
+        const int row = lane >> 2, seg = (lane & 3) * 16;
+        const int gy = wy0 + row, xs = x0 + seg;
+        uint32_t bd[16], bc[16];
 #pragma unroll
-            for (int p = 0; p < 16; p++) { bd[p] = 0xffffffffu; bi[p] = 0; }
-            for (uint32_t j = 0; j < ncand; j++) {
-                const int2 c = s_c[j];
-                const int dy = c.y - gy;
+        for (int p = 0; p < 16; p++) { bd[p] = 0xffffffffu; bc[p] = 0; }
+        for (uint32_t jb = 0; jb < ncand; jb += 32) {
+            const uint32_t j = jb + lane;
+            int2 c = make_int2(0, 0);
+            uint32_t col = 0;
+            bool keep = false;
+            if (j < ncand) {
+                c = s_c[j];
+                col = s_col[j];
+                const uint32_t dx = max(0, max(x0 - c.x, c.x - x1)), dy = max(0, max(wy0 - c.y, c.y - wy1));
+                keep = dx * dx + dy * dy <= uw;
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            while (mask) {  // warp-uniform, ascending ids
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int ccx = __shfl_sync(0xffffffffu, c.x, src), ccy = __shfl_sync(0xffffffffu, c.y, src);
+                const uint32_t ccol = __shfl_sync(0xffffffffu, col, src);
+                const int dy = ccy - gy;
                 const uint32_t dy2 = dy * dy;
 #pragma unroll
                 for (int p = 0; p < 16; p++) {
-                    const int dx = c.x - (x0 + seg + p);
+                    const int dx = ccx - (xs + p);
                     const uint32_t dd = dx * dx + dy2;
-                    if (dd < bd[p]) { bd[p] = dd; bi[p] = j; }
+                    if (dd < bd[p]) { bd[p] = dd; bc[p] = ccol; }
                 }
             }
-            uint32_t col[16];
+        }
+        if (gy > gy1) continue;
+        uint8_t *o = out + ((size_t)(gy - (int)y0) * w + xs) * 3;
+        if (xs + 15 <= x1 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {  // 16 pixels = three 128-bit stores
+            uint32_t wd[12];
 #pragma unroll
-            for (int p = 0; p < 16; p++) {
-                const uint32_t id = s_i[bi[p]];
-                col[p] = uint32_t(crgb[3 * id]) | (uint32_t(crgb[3 * id + 1]) << 8) | (uint32_t(crgb[3 * id + 2]) << 16);
+            for (int q = 0; q < 4; q++) {
+                const uint32_t a = bc[4 * q], b = bc[4 * q + 1], c = bc[4 * q + 2], e = bc[4 * q + 3];
+                wd[3 * q] = a | (b << 24); wd[3 * q + 1] = (b >> 8) | (c << 16); wd[3 * q + 2] = (c >> 16) | (e << 8);
             }
-            uint8_t *o = out + ((size_t)yl * w + x0 + seg) * 3;
-            if (x0 + seg + 15 <= x1 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {  // 16 pixels = three 128-bit stores
-                uint32_t wd[12];
+            uint4 *o4 = reinterpret_cast<uint4 *>(o);
+            o4[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]); o4[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]); o4[2] = make_uint4(wd[8], wd[9], wd[10], wd[11]);
+        } else {
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t a = col[4 * q], b = col[4 * q + 1], c = col[4 * q + 2], e = col[4 * q + 3];
-                    wd[3 * q] = a | (b << 24); wd[3 * q + 1] = (b >> 8) | (c << 16); wd[3 * q + 2] = (c >> 16) | (e << 8);
-                }
-                uint4 *o4 = reinterpret_cast<uint4 *>(o);
-                o4[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]); o4[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]); o4[2] = make_uint4(wd[8], wd[9], wd[10], wd[11]);
-            } else {
-#pragma unroll
-                for (int p = 0; p < 16; p++)
-                    if (x0 + seg + p <= x1) { o[3 * p] = col[p]; o[3 * p + 1] = col[p] >> 8; o[3 * p + 2] = col[p] >> 16; }
-            }
+            for (int p = 0; p < 16; p++)
+                if (xs + p <= x1) { o[3 * p] = bc[p]; o[3 * p + 1] = bc[p] >> 8; o[3 * p + 2] = bc[p] >> 16; }
         }
     }
 }
@@ -291,13 +315,13 @@ __global__ void __launch_bounds__(256) page_compact_kernel(uint32_t *bins, size_
 // cluster-colors helpers (reference src/codec/clusterc.rs:19-47)
 // ============================================================================================================
 
-// ---- unique colours WITH the order the culled D = 3 K-means wants, without a sort (clusterc.rs:19-28, utils.rs:4-16) -----------
+// ---- unique colours in the order the culled D = 3 K-means wants, without a sort (clusterc.rs:19-28, utils.rs:4-16) ------------
 // count_freqs turns the pixels into (colour, count) points.  The dense bins are indexed by the 24-bit MORTON code of (r, g, b), so
 // the ordered compaction of the bins IS the deduplicated, weighted, Morton-sorted point list the culled kernel scans:
-// no radix sort and, on photo-like images, about half as many points as pixels.  The reference's HashMap order is random (SURVEY
-// F5); the canonical order of the unique colours stays ascending key = r<<16 | g<<8 | b (header, oracle): a bitmap over the key space
-// marks the colours present, and a prefix popcount over it gives each colour its canonical index (`perm`) -- the chunked init
-// (kmeans.rs:61-108) and the empty-cluster rule are defined on that index.
+// no radix sort and, on photo-like images, a fraction of the pixels as points.  The reference's HashMap order is random (SURVEY
+// F5); the canonical order of the unique colours of cluster-colors is DEFINED as this one -- ascending Morton code, r on the most
+// significant bit of every triple (header, oracle_cluster_colors) -- so the list needs no permutation at all: the chunked init
+// (kmeans.rs:61-108) and the empty-cluster rule index it directly.
 __device__ __forceinline__ uint32_t spread3(uint32_t x) {  // 8 bits -> every third bit
     x &= 0xff;
     x = (x ^ (x << 16)) & 0xff0000ffu;
@@ -314,12 +338,10 @@ __device__ __forceinline__ uint32_t gather3(uint32_t x) {
     x = (x ^ (x >> 16)) & 0x3ffu;
     return x;
 }
-// same bit order as the former colour sort: r on the highest bit of every triple
 __device__ __forceinline__ uint32_t morton_rgb(uint32_t r, uint32_t g, uint32_t b) { return (spread3(r) << 2) | (spread3(g) << 1) | spread3(b); }
 
-constexpr uint32_t KEYBITS_WORDS = 1u << 19;  // 2^24 keys / 32
-
-__global__ void __launch_bounds__(256) dedup_hist_kernel(const uint8_t *__restrict__ rgb, size_t n, uint32_t *bins, uint8_t *flags, uint32_t *keybits) {
+// one fire-and-forget reduction (RED.ADD) per pixel, or per run of equal neighbours; nothing is read back
+__global__ void __launch_bounds__(256) dedup_hist_kernel(const uint8_t *__restrict__ rgb, size_t n, uint32_t *bins) {
     const bool al = (reinterpret_cast<uintptr_t>(rgb) & 3) == 0;
     const size_t quads = n / 4;
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < quads; q += (size_t)gridDim.x * blockDim.x) {
@@ -333,85 +355,74 @@ __global__ void __launch_bounds__(256) dedup_hist_kernel(const uint8_t *__restri
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (j > 0 && pk[j] == pk[j - 1]) continue;  // runs of equal neighbours (flat areas) cost one atomic
+            if (j > 0 && pk[j] == pk[j - 1]) continue;  // a run of equal neighbours (flat areas) costs one reduction
             uint32_t cnt = 1;
             for (int t = j + 1; t < 4 && pk[t] == pk[j]; t++) cnt++;
-            const uint32_t r = pk[j] & 0xff, g = (pk[j] >> 8) & 0xff, b = pk[j] >> 16;
-            const uint32_t m = morton_rgb(r, g, b);
-            if (atomicAdd(&bins[m], cnt) == 0) {  // first pixel of this colour: mark its bin page and its key
-                flags[m >> PAGE_SHIFT] = 1;
-                const uint32_t key = (r << 16) | (g << 8) | b;
-                atomicOr(&keybits[key >> 5], 1u << (key & 31));
-            }
+            atomicAdd(&bins[morton_rgb(pk[j] & 0xff, (pk[j] >> 8) & 0xff, pk[j] >> 16)], cnt);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < n - quads * 4) {
         const uint8_t *p = rgb + (quads * 4 + threadIdx.x) * 3;
-        const uint32_t m = morton_rgb(p[0], p[1], p[2]);
-        if (atomicAdd(&bins[m], 1u) == 0) {
-            flags[m >> PAGE_SHIFT] = 1;
-            const uint32_t key = (uint32_t(p[0]) << 16) | (uint32_t(p[1]) << 8) | p[2];
-            atomicOr(&keybits[key >> 5], 1u << (key & 31));
-        }
+        atomicAdd(&bins[morton_rgb(p[0], p[1], p[2])], 1u);
     }
 }
 
-// colours present per 4096-key page of the bitmap (128 words), then (after a scan of the page counts) the exclusive prefix of
-// every word: canonical index of key = word_prefix[key >> 5] + popc(bits below key in its word)
-__global__ void __launch_bounds__(128) keybits_page_count_kernel(const uint32_t *__restrict__ keybits, uint32_t *page_counts) {
-    uint32_t c = __popc(keybits[blockIdx.x * 128 + threadIdx.x]);
+// non-empty bins per 4096-bin page (every page is visited: a photo-like image touches nearly all of them)
+__global__ void __launch_bounds__(256) dedup_count_kernel(const uint32_t *__restrict__ bins, uint32_t *page_counts) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(bins + (size_t)blockIdx.x * PAGE) + threadIdx.x * 4;
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint4 v = p[j];
+        c += (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
+    }
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    __shared__ uint32_t s[4];
+    __shared__ uint32_t s[8];
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
     __syncthreads();
-    if (threadIdx.x == 0) page_counts[blockIdx.x] = s[0] + s[1] + s[2] + s[3];
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; i++) t += s[i];
+        page_counts[blockIdx.x] = t;
+    }
 }
 
-__global__ void __launch_bounds__(128) keybits_word_prefix_kernel(const uint32_t *__restrict__ keybits, const unsigned long long *__restrict__ page_off,
-                                                                  uint32_t *word_prefix) {
+// ordered compaction: thread t owns 16 consecutive bins of the page; packed colour r | g<<8 | b<<16 (the layout the K-means
+// kernels read) and count; the bins go back to all-zero
+__global__ void __launch_bounds__(256) dedup_compact_kernel(uint32_t *bins, const unsigned long long *__restrict__ offsets, uint32_t *out_pts, uint32_t *out_wts) {
+    __shared__ uint32_t s_warp[8];
+    uint4 *p = reinterpret_cast<uint4 *>(bins + (size_t)blockIdx.x * PAGE) + threadIdx.x * 4;
+    uint32_t v[16];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const uint4 q = p[j]; v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w; }
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) c += v[j] != 0;
+    // exclusive prefix of the per-thread counts over the block (thread order = bin order)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t v = __popc(keybits[blockIdx.x * 128 + threadIdx.x]);
-    uint32_t x = v;
+    uint32_t x = c;
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
     }
-    __shared__ uint32_t s[4];
-    if (lane == 31) s[warp] = x;
+    if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    uint32_t before = (uint32_t)page_off[blockIdx.x];
-    for (int j = 0; j < warp; j++) before += s[j];
-    word_prefix[blockIdx.x * 128 + threadIdx.x] = before + x - v;
-}
-
-// ordered compaction of the Morton-indexed bins: packed colour r | g<<8 | b<<16 (the layout the K-means kernels read), count,
-// canonical index; the bins go back to all-zero
-__global__ void __launch_bounds__(256) dedup_compact_kernel(uint32_t *bins, const uint32_t *__restrict__ list, const uint32_t *__restrict__ count,
-                                                            const unsigned long long *__restrict__ offsets, uint8_t *flags,
-                                                            const uint32_t *__restrict__ keybits, const uint32_t *__restrict__ word_prefix,
-                                                            uint32_t *out_pts, uint32_t *out_wts, uint32_t *out_perm) {
-    __shared__ uint32_t s_warp[8];
-    if (blockIdx.x >= *count) return;
-    const uint32_t pg = list[blockIdx.x];
-    const size_t base = (size_t)pg * PAGE;
-    unsigned long long pos = offsets[blockIdx.x];
-    for (int j = 0; j < PAGE / 256; j++) {
-        const size_t i = base + (size_t)j * 256 + threadIdx.x;
-        const uint32_t v = bins[i];
-        uint32_t tot;
-        const uint32_t rk = block_rank256(v != 0, s_warp, &tot);
-        if (v) {
-            const uint32_t m = (uint32_t)i;
-            const uint32_t r = gather3(m >> 2), g = gather3(m >> 1), b = gather3(m);
-            const uint32_t key = (r << 16) | (g << 8) | b;
-            out_pts[pos + rk] = r | (g << 8) | (b << 16);
-            out_wts[pos + rk] = v;  // clusterc.rs:23 "count as u32"
-            out_perm[pos + rk] = __ldg(word_prefix + (key >> 5)) + __popc(__ldg(keybits + (key >> 5)) & ((1u << (key & 31)) - 1u));
-            bins[i] = 0;  // restore the all-zero invariant
-        }
-        pos += tot;
+    uint32_t before = x - c;
+    for (int j = 0; j < warp; j++) before += s_warp[j];
+    if (c) {
+        unsigned long long pos = offsets[blockIdx.x] + before;
+        const uint32_t m0 = blockIdx.x * PAGE + threadIdx.x * 16;
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if (v[j]) {
+                const uint32_t m = m0 + j;
+                out_pts[pos] = gather3(m >> 2) | (gather3(m >> 1) << 8) | (gather3(m) << 16);
+                out_wts[pos] = v[j];  // clusterc.rs:23 "count as u32"
+                pos++;
+            }
+#pragma unroll
+        for (int j = 0; j < 4; j++) p[j] = make_uint4(0u, 0u, 0u, 0u);  // restore the all-zero invariant
     }
-    if (threadIdx.x == 0) flags[pg] = 0;
 }
 
 // lut[key] = centroid colour (packed r | g<<8 | b<<16) straight from the sorted point list and its assignment
@@ -1260,9 +1271,6 @@ int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins_in, size_t nb
 void cniic_unique_colours_free(cniic_ctx *ctx, UniqueColours *uc) {
     cniic_cache_free(ctx, uc->d_pts);
     cniic_cache_free(ctx, uc->d_wts);
-    cniic_cache_free(ctx, uc->d_perm);
-    cniic_cache_free(ctx, uc->d_keybits);
-    cniic_cache_free(ctx, uc->d_word_prefix);
     *uc = UniqueColours();
 }
 
@@ -1274,45 +1282,28 @@ int cniic_dev_unique_colours(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, Uni
     uint8_t *flags;
     size_t nbins;
     ST_TRY(hist_space(ctx, 0, &bins, &flags, &nbins));  // the 2^24 colour bins, indexed by Morton code for this pass
-    const uint32_t npages = (uint32_t)(nbins / PAGE), kpages = KEYBITS_WORDS / 128;
-    UniqueColours uc;
-    auto fail = [&](int code) {
-        cniic_unique_colours_free(ctx, &uc);
-        return code;
-    };
-    uc.d_keybits = static_cast<uint32_t *>(cniic_cache_alloc(ctx, KEYBITS_WORDS * 4));
-    uc.d_word_prefix = static_cast<uint32_t *>(cniic_cache_alloc(ctx, KEYBITS_WORDS * 4));
-    if (!uc.d_keybits || !uc.d_word_prefix) return fail(CNIIC_ERR_CUDA);
-    DevBuf list(ctx), bc(ctx), off(ctx), kc(ctx), koff(ctx);
-    if (list.alloc((size_t(npages) + 1) * 4) != cudaSuccess || bc.alloc(size_t(npages) * 4) != cudaSuccess || off.alloc((size_t(npages) + 1) * 8) != cudaSuccess ||
-        kc.alloc(size_t(kpages) * 4) != cudaSuccess || koff.alloc((size_t(kpages) + 1) * 8) != cudaSuccess)
-        return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc failed"));
-    uint32_t *d_count = list.as<uint32_t>() + npages;
-    if (cudaMemsetAsync(uc.d_keybits, 0, KEYBITS_WORDS * 4, ctx->stream) != cudaSuccess) return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "memset failed"));
+    const uint32_t npages = (uint32_t)(nbins / PAGE);
+    DevBuf bc(ctx), off(ctx);
+    if (bc.alloc(size_t(npages) * 4) != cudaSuccess || off.alloc((size_t(npages) + 1) * 8) != cudaSuccess)
+        return cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMalloc failed");
     if (n) {
-        dedup_hist_kernel<<<grid_for(ctx, n / 4 + 1, 2), 256, 0, ctx->stream>>>(d_rgb, n, bins, flags, uc.d_keybits);
+        dedup_hist_kernel<<<grid_for(ctx, n / 4 + 1, 2), 256, 0, ctx->stream>>>(d_rgb, n, bins);
         ctx->launches++;
     }
-    list_pages_kernel<<<1, 1024, 0, ctx->stream>>>(flags, npages, list.as<uint32_t>(), d_count);
-    page_count_kernel<<<npages, 256, 0, ctx->stream>>>(bins, nbins, list.as<uint32_t>(), d_count, bc.as<uint32_t>());
+    dedup_count_kernel<<<npages, 256, 0, ctx->stream>>>(bins, bc.as<uint32_t>());
     scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(bc.as<uint32_t>(), npages, off.as<unsigned long long>());
-    keybits_page_count_kernel<<<kpages, 128, 0, ctx->stream>>>(uc.d_keybits, kc.as<uint32_t>());
-    scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(kc.as<uint32_t>(), kpages, koff.as<unsigned long long>());
-    keybits_word_prefix_kernel<<<kpages, 128, 0, ctx->stream>>>(uc.d_keybits, koff.as<unsigned long long>(), uc.d_word_prefix);
-    ctx->launches += 6;
+    ctx->launches += 2;
     unsigned long long total = 0;
-    if (cudaMemcpyAsync(&total, off.as<unsigned long long>() + npages, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-        return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "unique-colour count failed: %s", cudaGetErrorString(cudaGetLastError())));
+    CU_TRY(ctx, cudaMemcpyAsync(&total, off.as<unsigned long long>() + npages, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    UniqueColours uc;
     uc.u = (size_t)total;
     uc.d_pts = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (uc.u + 8) * 4));
     uc.d_wts = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (uc.u + 8) * 4));
-    uc.d_perm = static_cast<uint32_t *>(cniic_cache_alloc(ctx, (uc.u + 8) * 4));
-    if (!uc.d_pts || !uc.d_wts || !uc.d_perm) return fail(CNIIC_ERR_CUDA);
-    dedup_compact_kernel<<<npages, 256, 0, ctx->stream>>>(bins, list.as<uint32_t>(), d_count, off.as<unsigned long long>(), flags, uc.d_keybits,
-                                                          uc.d_word_prefix, uc.d_pts, uc.d_wts, uc.d_perm);
+    if (!uc.d_pts || !uc.d_wts) { cniic_unique_colours_free(ctx, &uc); return CNIIC_ERR_CUDA; }
+    dedup_compact_kernel<<<npages, 256, 0, ctx->stream>>>(bins, off.as<unsigned long long>(), uc.d_pts, uc.d_wts);
     ctx->launches++;
-    if (cudaGetLastError() != cudaSuccess) return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "unique-colour compaction failed"));
+    if (cudaGetLastError() != cudaSuccess) { cniic_unique_colours_free(ctx, &uc); return cniic_set_error(ctx, CNIIC_ERR_CUDA, "unique-colour compaction failed"); }
     *out = uc;
     return CNIIC_OK;
 }
@@ -1493,7 +1484,7 @@ extern "C" int cniic_voronoi_fill_device(cniic_ctx *ctx, const uint32_t *d_cxy, 
     if (w == 0 || h_local == 0) return CNIIC_OK;
     if (w > CNIIC_MAX_DIM || h > CNIIC_MAX_DIM || (uint64_t)y0 + h_local > h) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "bad image dimensions");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t smem = (size_t)k * 10 + 16;
+    const size_t smem = (size_t)k * 12 + 16;
     CU_TRY(ctx, cudaFuncSetAttribute(fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t super_x = (w + FSW - 1) / FSW, super_y = (h_local + FSH - 1) / FSH;
     DevBuf lists(ctx), counts(ctx);

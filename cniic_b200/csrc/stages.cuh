@@ -5,10 +5,10 @@
 #include "common.cuh"
 
 // Unique colours of an image as weighted points, deduplicated AND Morton-sorted by one histogram + ordered compaction (stages.cu):
-// d_pts = packed r | g<<8 | b<<16, d_wts = pixel count (clusterc.rs:23), d_perm = canonical index (ascending key r<<16|g<<8|b) of
-// every sorted point; d_keybits / d_word_prefix = presence bitmap over the key space and its per-word exclusive prefix.
+// d_pts = packed r | g<<8 | b<<16, d_wts = pixel count (clusterc.rs:23).  Ascending Morton code (r on the top bit of each triple) is
+// also the canonical order of the unique colours of cluster-colors (header, oracle), so the list carries no permutation.
 struct UniqueColours {
-    uint32_t *d_pts = nullptr, *d_wts = nullptr, *d_perm = nullptr, *d_keybits = nullptr, *d_word_prefix = nullptr;
+    uint32_t *d_pts = nullptr, *d_wts = nullptr;
     size_t u = 0;
 };
 int cniic_dev_unique_colours(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, UniqueColours *out);

@@ -174,8 +174,11 @@ int cniic_hist_rgb(cniic_ctx *ctx, const uint8_t *rgb, size_t n, uint32_t *out_k
  * keys/assign describe the clustered unique colours (ascending keys), centroids = k x 3.                          */
 int cniic_recolor_rgb(cniic_ctx *ctx, const uint8_t *rgb, size_t n, const uint32_t *keys, const uint16_t *assign,
                       size_t n_unique, const uint8_t *centroids, uint32_t k, uint8_t *out_rgb);
-/* Whole front half of ClusterColors::encode: unique colours -> weighted K-means -> recolour (clusterc.rs:19-47).  The unique
- * colours enter K-means in the canonical order above (ascending key); out_rgb == NULL skips the recolour pass and its copy.   */
+/* Whole front half of ClusterColors::encode: unique colours -> weighted K-means -> recolour (clusterc.rs:19-47).  The reference
+ * feeds K-means the unique colours in HashMap order (random, clusterc.rs:21-27); the deterministic stand-in here and in the oracle is
+ * ASCENDING MORTON CODE of (r, g, b), r on the most significant bit of every bit triple -- the order the Morton-indexed histogram
+ * bins compact into, so the deduplicated point list needs neither a sort nor a permutation.  The chunked init (kmeans.rs:61-108)
+ * and the empty-cluster rule index that list.  out_rgb == NULL skips the recolour pass and its copy.                           */
 int cniic_cluster_colors(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, uint32_t k, uint32_t max_iters,
                          int tie_rule, uint8_t *out_rgb /* nullable */, uint8_t *out_centroids /* 3k, nullable */,
                          cniic_kmeans_stats *stats);

@@ -575,6 +575,24 @@ size_t oracle_count_freqs_rgb(const uint8_t *rgb, size_t n, uint32_t *out_keys, 
 }
 
 /* clusterc.rs:18-52 */
+/* 8 bits -> every third bit; Morton code of a colour with r on the most significant bit of every triple */
+static uint32_t spread3(uint32_t x) {
+    uint32_t r = 0;
+    for (int i = 0; i < 8; i++) r |= ((x >> i) & 1u) << (3 * i);
+    return r;
+}
+static uint32_t morton_of_key(uint32_t key) { return (spread3(key >> 16) << 2) | (spread3((key >> 8) & 0xff) << 1) | spread3(key & 0xff); }
+
+typedef struct { uint32_t morton, key; uint64_t count; } ucol_t;
+static int cmp_ucol(const void *a, const void *b) {
+    uint32_t x = ((const ucol_t *)a)->morton, y = ((const ucol_t *)b)->morton;
+    return (x > y) - (x < y);
+}
+
+/* clusterc.rs:18-53.  The reference's point list is `HashMap::into_iter()` order (clusterc.rs:21-27: random); the
+   deterministic stand-in is ASCENDING MORTON CODE of (r, g, b), r on the most significant bit of every bit triple: an order with
+   colour-space locality at every scale, which is also the order the GPU path scans (its histogram bins are Morton-indexed, so
+   their compaction is this list).  The chunked init (kmeans.rs:61-108) and the empty-cluster rule index this list. */
 int oracle_cluster_colors(const uint8_t *rgb, uint32_t w, uint32_t h, size_t k, int mode, int tie_rule, uint32_t max_iters,
                           uint8_t *out_rgb, uint8_t *out_centroids, oracle_kmeans_stats *stats) {
     size_t n = (size_t)w * h;
@@ -582,14 +600,19 @@ int oracle_cluster_colors(const uint8_t *rgb, uint32_t w, uint32_t h, size_t k, 
     uint32_t *keys = (uint32_t *)malloc((cap ? cap : 1) * sizeof(uint32_t));
     uint64_t *cnt64 = (uint64_t *)malloc((cap ? cap : 1) * sizeof(uint64_t));
     size_t u = oracle_count_freqs_rgb(rgb, n, keys, cnt64);
+    ucol_t *uc = (ucol_t *)malloc((u ? u : 1) * sizeof(ucol_t));
+    for (size_t i = 0; i < u; i++) { uc[i].morton = morton_of_key(keys[i]); uc[i].key = keys[i]; uc[i].count = cnt64[i]; }
+    qsort(uc, u, sizeof(ucol_t), cmp_ucol);
     uint8_t *urgb = (uint8_t *)malloc(3 * (u ? u : 1));
     uint32_t *cnt = (uint32_t *)malloc((u ? u : 1) * sizeof(uint32_t));
     for (size_t i = 0; i < u; i++) {
+        keys[i] = uc[i].key;
         urgb[3 * i] = (uint8_t)(keys[i] >> 16);
         urgb[3 * i + 1] = (uint8_t)(keys[i] >> 8);
         urgb[3 * i + 2] = (uint8_t)keys[i];
-        cnt[i] = (uint32_t)cnt64[i]; /* clusterc.rs:23 "count as u32" */
+        cnt[i] = (uint32_t)uc[i].count; /* clusterc.rs:23 "count as u32" */
     }
+    free(uc);
     uint8_t *cen = (uint8_t *)malloc(3 * (k ? k : 1));
     uint32_t *asg = (uint32_t *)malloc((u ? u : 1) * sizeof(uint32_t));
     int rc = oracle_kmeans_rgb(urgb, cnt, u, k, mode, tie_rule, max_iters, cen, NULL, asg, stats);

@@ -20,11 +20,18 @@ from collections import defaultdict
 def main():
     rep, obj, frag = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
-    page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    # NCU_FILTER (optional), e.g. "-k regex:km_assign_rgb_cull2 -s 1": selects ONE launch of a report that holds several
+    page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "-c", "1"] + os.environ.get("NCU_FILTER", "").split(),
+                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(page)))
     hdr = rows[1]
     i_s, i_i = hdr.index("# Samples"), hdr.index("Instructions Executed")
-    prof = [(r[1].strip(), int(r[i_s]), int(r[i_i])) for r in rows[2:] if len(r) > i_i]
+    body = rows[2:]
+    for j, r in enumerate(body):  # a report with several launches repeats the two header rows: keep the first launch
+        if r and r[0] == "Kernel Name":
+            body = body[:j]
+            break
+    prof = [(r[1].strip(), int(r[i_s]), int(r[i_i])) for r in body if len(r) > i_i]
     with tempfile.TemporaryDirectory() as td:
         subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=td, stdout=subprocess.DEVNULL)
         cubin = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
