@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "stages.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -33,111 +34,119 @@ __device__ __forceinline__ uint32_t block_rank256(bool flag, uint32_t *s_warp, u
     return before + __popc(bal & ((1u << lane) - 1));
 }
 
-constexpr int FSW = 512, FSH = 256;  // supertile of the fill pre-pass (8 x 4 tiles)
+constexpr int FSW = 512, FSH = 256;  // supertile (8 x 4 tiles): level 1 of the culling
 
-// level 1: one CTA per 512x256 supertile keeps the centroids that can be nearest to some pixel of it (ascending ids)
-__global__ void __launch_bounds__(256) fill_supercull_kernel(const uint32_t *__restrict__ cxy, uint32_t k, uint32_t w, uint32_t y0, uint32_t h_local,
-                                                             uint32_t super_x, uint16_t *lists, uint32_t *counts) {
-    __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_U;
-    const int tid = threadIdx.x;
-    const int x0 = (blockIdx.x % super_x) * FSW, yl0 = (blockIdx.x / super_x) * FSH;
-    const int x1 = min(x0 + FSW, (int)w) - 1, gy0 = y0 + yl0, gy1 = y0 + min(yl0 + FSH, (int)h_local) - 1;
-    if (tid == 0) s_U = 0xffffffffu;
-    __syncthreads();
-    uint32_t umin = 0xffffffffu;
-    for (uint32_t c = tid; c < k; c += 256) {
-        const int cx = (int)cxy[2 * c], cy = (int)cxy[2 * c + 1];
-        const uint32_t dx = max(abs(cx - x0), abs(cx - x1)), dy = max(abs(cy - gy0), abs(cy - gy1));
-        umin = min(umin, dx * dx + dy * dy);
-    }
-    for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-    if ((tid & 31) == 0) atomicMin(&s_U, umin);
-    __syncthreads();
-    const uint32_t U = s_U;
-    uint16_t *list = lists + (size_t)blockIdx.x * k;
-    uint32_t placed = 0;
-    for (uint32_t cb = 0; cb < k; cb += 256) {
-        const uint32_t c = cb + tid;
-        bool keep = false;
-        if (c < k) {
-            const int cx = (int)cxy[2 * c], cy = (int)cxy[2 * c + 1];
-            const uint32_t dx = max(0, max(x0 - cx, cx - x1)), dy = max(0, max(gy0 - cy, cy - gy1));
-            keep = dx * dx + dy * dy <= U;
-        }
-        uint32_t tot;
-        const uint32_t r = block_rank256(keep, s_warp, &tot);
-        if (keep) list[placed + r] = (uint16_t)c;
-        placed += tot;
-    }
-    if (tid == 0) counts[blockIdx.x] = placed;
-}
-
-// level 2 + 3: 64x64 tile per CTA, bounds over the supertile's list (level 2, candidates compacted in id order into shared memory),
-// then every WARP bounds the tile's candidates again against its own 64x8 strip (level 3: same argument on a box inside the tile
-// box -- U_w = min_c maxdist^2(c, strip) bounds every pixel's minimum, a centroid with mindist^2(c, strip) > U_w can neither win nor
-// tie) and scores only those, broadcast by shuffle in ascending id order: strict "<" keeps the FIRST minimum = lowest id
-// (Iterator::min_by_key, clusterc.rs:182-184).  ~5 centroids per pixel instead of ~20 after level 2 alone.
+// Three levels of the same exact argument (U = min_c maxdist^2(c, box) bounds every pixel's minimum over the box, so a centroid with
+// mindist^2(c, box) > U can neither win nor tie), each compacting IN ID ORDER so that strict "<" keeps the FIRST minimum = lowest id
+// (Iterator::min_by_key, clusterc.rs:182-184):
+//   level 1  512x256 supertile, over all k centroids, once per supertile a CTA enters (tiles are enumerated supertile by supertile
+//            and a CTA owns a contiguous range: one or two supertiles) -> coordinates + colours of ~20 centroids in shared memory;
+//   level 2  64x64 tile, over the supertile's list (shared memory to shared memory: no dependent global loads per tile -- the first
+//            version chased list -> coordinates -> colours through global memory for every tile and was latency bound at 70 us);
+//   level 3  64x8 strip of a warp, over the tile's list, survivors broadcast by shuffle and scored: ~5 centroids per pixel.
 __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ cxy, const uint8_t *__restrict__ crgb, uint32_t k,
-                                                   uint32_t w, uint32_t y0, uint32_t h_local, uint32_t super_x,
-                                                   const uint16_t *__restrict__ lists, const uint32_t *__restrict__ counts,
-                                                   uint8_t *__restrict__ out) {
+                                                   uint32_t w, uint32_t y0, uint32_t h_local, uint8_t *__restrict__ out) {
     extern __shared__ uint4 fsm[];
-    int2 *s_c = reinterpret_cast<int2 *>(fsm);                 // candidate coordinates
-    uint32_t *s_col = reinterpret_cast<uint32_t *>(s_c + k);   // candidate colours, packed r | g<<8 | b<<16
+    int2 *s_sc = reinterpret_cast<int2 *>(fsm);                      // level-1 survivors: coordinates
+    uint32_t *s_scol = reinterpret_cast<uint32_t *>(s_sc + k);       // ... colours, packed r | g<<8 | b<<16
+    uint16_t *s_ti = reinterpret_cast<uint16_t *>(s_scol + k);       // level-2 survivors: positions in the level-1 list
     __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_U;
+    __shared__ uint32_t s_U[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_x = (w + FT - 1) / FT, tiles_y = (h_local + FT - 1) / FT;
-    for (uint32_t tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
-        const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+    const uint32_t super_x = (w + FSW - 1) / FSW;
+    constexpr uint32_t STX = FSW / FT, STY = FSH / FT;
+    const uint32_t tiles = tiles_x * tiles_y;
+    const uint32_t per_cta = (tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t t_begin = blockIdx.x * per_cta, t_end = min(tiles, t_begin + per_cta);
+    uint32_t cur_sup = 0xffffffffu, ms = 0;
+    for (uint32_t tile_seq = t_begin; tile_seq < t_end; tile_seq++) {
+        uint32_t tx, ty, sup;
+        {   // supertile-major enumeration of the tiles
+            const uint32_t row_tiles = tiles_x * STY;
+            const uint32_t sy = tile_seq / row_tiles, rem = tile_seq - sy * row_tiles;
+            const uint32_t rows_in = min(STY, tiles_y - sy * STY);
+            const uint32_t sx = rem / (STX * rows_in), rem2 = rem - sx * STX * rows_in;
+            const uint32_t cols_in = min(STX, tiles_x - sx * STX);
+            tx = sx * STX + rem2 % cols_in;
+            ty = sy * STY + rem2 / cols_in;
+            sup = sy * super_x + sx;
+        }
+        if (sup != cur_sup) {  // ---- level 1 ----
+            __syncthreads();   // the previous tile is done with the lists
+            const int sx0 = (sup % super_x) * FSW, syl0 = (sup / super_x) * FSH;
+            const int sx1 = min(sx0 + FSW, (int)w) - 1, sy0 = y0 + syl0, sy1 = y0 + min(syl0 + FSH, (int)h_local) - 1;
+            if (tid == 0) s_U[0] = 0xffffffffu;
+            __syncthreads();
+            uint32_t um = 0xffffffffu;
+            for (uint32_t c = tid; c < k; c += 256) {
+                const int cx = (int)__ldg(cxy + 2 * c), cy = (int)__ldg(cxy + 2 * c + 1);
+                const uint32_t dx = max(abs(cx - sx0), abs(cx - sx1)), dy = max(abs(cy - sy0), abs(cy - sy1));
+                um = min(um, dx * dx + dy * dy);
+            }
+            for (int o = 16; o > 0; o >>= 1) um = min(um, __shfl_xor_sync(0xffffffffu, um, o));
+            if (lane == 0) atomicMin(&s_U[0], um);
+            __syncthreads();
+            const uint32_t US = s_U[0];
+            uint32_t placed = 0;
+            for (uint32_t cb = 0; cb < k; cb += 256) {
+                const uint32_t c = cb + tid;
+                bool keep = false;
+                int cx = 0, cy = 0;
+                if (c < k) {
+                    cx = (int)__ldg(cxy + 2 * c); cy = (int)__ldg(cxy + 2 * c + 1);
+                    const uint32_t dx = max(0, max(sx0 - cx, cx - sx1)), dy = max(0, max(sy0 - cy, cy - sy1));
+                    keep = dx * dx + dy * dy <= US;
+                }
+                uint32_t tot;
+                const uint32_t r = block_rank256(keep, s_warp, &tot);
+                if (keep) {
+                    s_sc[placed + r] = make_int2(cx, cy);
+                    s_scol[placed + r] = uint32_t(crgb[3 * c]) | (uint32_t(crgb[3 * c + 1]) << 8) | (uint32_t(crgb[3 * c + 2]) << 16);
+                }
+                placed += tot;
+            }
+            ms = placed;
+            cur_sup = sup;
+        }
         const int x0 = tx * FT, yl0 = ty * FT;
         const int x1 = min(x0 + FT, (int)w) - 1, yl1 = min(yl0 + FT, (int)h_local) - 1;
         const int gy0 = y0 + yl0, gy1 = y0 + yl1;
-        const uint32_t sup = (ty / (FSH / FT)) * super_x + tx / (FSW / FT);
-        const uint32_t m = counts[sup];
-        const uint16_t *list = lists + (size_t)sup * k;
-        __syncthreads();
-        if (tid == 0) s_U = 0xffffffffu;
+        // ---- level 2 ----
+        __syncthreads();  // level-1 lists complete / the previous tile is done with s_ti
+        if (tid == 0) s_U[1] = 0xffffffffu;
         __syncthreads();
         uint32_t umin = 0xffffffffu;
-        for (uint32_t j = tid; j < m; j += 256) {
-            const uint32_t c = list[j];
-            const int cx = (int)cxy[2 * c], cy = (int)cxy[2 * c + 1];
-            const uint32_t dx = max(abs(cx - x0), abs(cx - x1)), dy = max(abs(cy - gy0), abs(cy - gy1));
+        for (uint32_t j = tid; j < ms; j += 256) {
+            const int2 c = s_sc[j];
+            const uint32_t dx = max(abs(c.x - x0), abs(c.x - x1)), dy = max(abs(c.y - gy0), abs(c.y - gy1));
             umin = min(umin, dx * dx + dy * dy);
         }
         for (int o = 16; o > 0; o >>= 1) umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-        if (lane == 0) atomicMin(&s_U, umin);
+        if (lane == 0) atomicMin(&s_U[1], umin);
         __syncthreads();
-        const uint32_t U = s_U;
+        const uint32_t U = s_U[1];
         uint32_t ncand = 0;
-        for (uint32_t jb = 0; jb < m; jb += 256) {
+        for (uint32_t jb = 0; jb < ms; jb += 256) {
             const uint32_t j = jb + tid;
             bool keep = false;
-            int cx = 0, cy = 0;
-            uint32_t c = 0;
-            if (j < m) {
-                c = list[j];
-                cx = (int)cxy[2 * c]; cy = (int)cxy[2 * c + 1];
-                const uint32_t dx = max(0, max(x0 - cx, cx - x1)), dy = max(0, max(gy0 - cy, cy - gy1));
+            if (j < ms) {
+                const int2 c = s_sc[j];
+                const uint32_t dx = max(0, max(x0 - c.x, c.x - x1)), dy = max(0, max(gy0 - c.y, c.y - gy1));
                 keep = dx * dx + dy * dy <= U;
             }
             uint32_t tot;
             const uint32_t r = block_rank256(keep, s_warp, &tot);
-            if (keep) {
-                s_c[ncand + r] = make_int2(cx, cy);
-                s_col[ncand + r] = uint32_t(crgb[3 * c]) | (uint32_t(crgb[3 * c + 1]) << 8) | (uint32_t(crgb[3 * c + 2]) << 16);
-            }
+            if (keep) s_ti[ncand + r] = (uint16_t)j;
             ncand += tot;
         }
         __syncthreads();
-        // warp -> a 64 x 8 strip of the tile; lane -> one row of it, 16 consecutive pixels
+        // ---- level 3: warp -> a 64 x 8 strip of the tile; lane -> one row of it, 16 consecutive pixels ----
         const int wy0 = gy0 + warp * 8, wy1 = min(wy0 + 7, gy1);
         if (wy0 > gy1) continue;  // (warp-uniform; the strip lies below the image / shard)
         uint32_t uw = 0xffffffffu;
         for (uint32_t j = lane; j < ncand; j += 32) {
-            const int2 c = s_c[j];
+            const int2 c = s_sc[s_ti[j]];
             const uint32_t dx = max(abs(c.x - x0), abs(c.x - x1)), dy = max(abs(c.y - wy0), abs(c.y - wy1));
             uw = min(uw, dx * dx + dy * dy);
         }
@@ -153,8 +162,9 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ 
             uint32_t col = 0;
             bool keep = false;
             if (j < ncand) {
-                c = s_c[j];
-                col = s_col[j];
+                const uint32_t e = s_ti[j];
+                c = s_sc[e];
+                col = s_scol[e];
                 const uint32_t dx = max(0, max(x0 - c.x, c.x - x1)), dy = max(0, max(wy0 - c.y, c.y - wy1));
                 keep = dx * dx + dy * dy <= uw;
             }
@@ -785,6 +795,210 @@ __global__ void __launch_bounds__(256) hilbert_tile_kernel(const uint8_t *__rest
     }
 }
 
+// ---- the same three stages with the tile brought in by the Tensor Memory Accelerator (default) -------------------------------------
+// One elected thread issues cp.async.bulk.tensor.2d for the 64 x 64 pixel block (box = 192 bytes x 64 rows of a 2-D tensor map over
+// the packed-RGB image) into one of two shared-memory stages and arms its mbarrier with the 12 288 bytes to come; the CTA is
+// persistent, so the tile of block i+1 is in flight while block i is expanded, gathered along the curve, differenced and stored:
+// the 64 row segments at a 3*w-byte stride -- what made the plain-load version latency bound (profiles/r02_ncu_full_c5.txt: 43 % of
+// HBM, top stalls barrier + long scoreboard) -- are one asynchronous request that no warp waits for.
+constexpr uint32_t HT_TILE_BYTES = HT * HT * 3;  // 12 288
+
+template <int MODE>
+__global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ rgb, uint32_t n,
+                                                               uint8_t *out_rgb, int16_t *out_delta, uint32_t *bins, uint8_t *flags,
+                                                               unsigned long long blk_begin, unsigned long long blk_end) {
+    extern __shared__ uint4 s_dyn4[];  // two raw tile stages (packed RGB rows of 192 bytes), then (MODE 2) the counter cube
+    uint8_t *s_raw = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(s_dyn4) + 127) & ~uintptr_t(127));  // TMA destination: 128-byte aligned
+    uint32_t *s_cube = reinterpret_cast<uint32_t *>(s_raw + 2 * HT_TILE_BYTES);
+    __shared__ __align__(16) uint32_t s_px[HT * HT_STRIDE];  // one word per pixel (r | g<<8 | b<<16)
+    __shared__ uint32_t s_last[8];
+    __shared__ int s_top[2][5];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long nblocks = blk_end;
+    if (MODE == 2) {
+        for (int i = tid; i < (CUBE_N + 1) / 2; i += 256) s_cube[i] = 0;
+    }
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    // this thread's 16 indices (a 4x4 cell) share the base-4 digits 2..5 = its thread id: fold those levels once, for every block
+    int lax = 0, lay = 0, lsx = 1, lsy = 1;
+    bool lswapped = false;
+    {
+        uint32_t t = (uint32_t)tid;
+#pragma unroll
+        for (int sl = 4; sl < HT; sl <<= 1) {
+            const uint32_t rx = 1u & (t >> 1), ry = 1u & (t ^ rx);
+            if (ry == 0) {
+                if (rx == 1) {
+                    const int nax = sl - 1 - lay, nsx = -lsy, nay = sl - 1 - lax, nsy = -lsx;
+                    lax = nax; lsx = nsx; lay = nay; lsy = nsy;
+                } else {
+                    const int q = lax, qs = lsx;
+                    lax = lay; lsx = lsy; lay = q; lsy = qs;
+                }
+                lswapped = !lswapped;
+            }
+            lax += sl * (int)rx;
+            lay += sl * (int)ry;
+            t >>= 2;
+        }
+    }
+    __syncthreads();
+    // thread 0: fold the levels above the block (6..L-1) into an affine map of the 64x64 block, request the block's pixels
+    auto issue = [&](unsigned long long blk, int stage) {
+        int bx = 0, by = 0, tx = 1, ty = 1, sw = 0;
+        unsigned long long t = blk;
+        for (uint32_t sft = HT; sft < n; sft <<= 1) {
+            const int sl = (int)sft;
+            const uint32_t rx = 1u & (uint32_t)(t >> 1), ry = 1u & ((uint32_t)t ^ rx);
+            if (ry == 0) {
+                if (rx == 1) {
+                    const int nbx = sl - 1 - by, ntx = -ty, nby = sl - 1 - bx, nty = -tx;
+                    bx = nbx; tx = ntx; by = nby; ty = nty;
+                } else {
+                    const int q = bx, qs = tx;
+                    bx = by; tx = ty; by = q; ty = qs;
+                }
+                sw ^= 1;
+            }
+            bx += sl * (int)rx;
+            by += sl * (int)ry;
+            t >>= 2;
+        }
+        s_top[stage][0] = bx; s_top[stage][1] = tx; s_top[stage][2] = by; s_top[stage][3] = ty; s_top[stage][4] = sw;
+        mbar_arrive_expect_tx(&s_bar[stage], HT_TILE_BYTES);
+        tma_load_2d(s_raw + (size_t)stage * HT_TILE_BYTES, &tmap, (bx & ~(HT - 1)) * 3, by & ~(HT - 1), &s_bar[stage]);
+    };
+    const unsigned long long first = blk_begin + blockIdx.x;
+    if (tid == 0 && first < nblocks) issue(first, 0);
+    uint32_t it = 0;
+    for (unsigned long long blk = first; blk < nblocks; blk += gridDim.x, it++) {
+        const int stage = it & 1;
+        const unsigned long long B = blk * 4096;
+        const unsigned long long i0 = B + (unsigned long long)tid * 16;
+        // the other stage was consumed before the barrier that ended the previous iteration's expansion: refill it now
+        if (tid == 0 && blk + gridDim.x < nblocks) issue(blk + gridDim.x, stage ^ 1);
+        mbar_wait(&s_bar[stage], (it >> 1) & 1);
+        int ax, ay, sx, sy;
+        bool swapped;
+        {   // compose: (x, y) = top(local(u, v)); x = bx + tx * (sw ? yl : xl), y = by + ty * (sw ? xl : yl)
+            const int bx = s_top[stage][0], tx = s_top[stage][1], by = s_top[stage][2], ty = s_top[stage][3], sw = s_top[stage][4];
+            ax = bx + tx * (sw ? lay : lax); sx = tx * (sw ? lsy : lsx);
+            ay = by + ty * (sw ? lax : lay); sy = ty * (sw ? lsx : lsy);
+            swapped = lswapped != (sw != 0);
+        }
+        const int X0 = ax & ~(HT - 1), Y0 = ay & ~(HT - 1);  // (every coordinate of the block shares the bits above the low six)
+        {   // expand the landed tile to one 32-bit word per pixel: thread t takes 16 pixels (three 128-bit words) of row t/4
+            const int r = tid >> 2, c16 = (tid & 3) * 16;
+            const uint4 *src = reinterpret_cast<const uint4 *>(s_raw + (size_t)stage * HT_TILE_BYTES + r * (HT * 3) + c16 * 3);
+            const uint4 a = src[0], b = src[1], c = src[2];
+            const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+            uint32_t *dst = s_px + r * HT_STRIDE + c16;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // 3 words -> 4 pixels
+                const uint32_t w0 = wd[3 * q], w1 = wd[3 * q + 1], w2 = wd[3 * q + 2];
+                *reinterpret_cast<uint4 *>(dst + 4 * q) =
+                    make_uint4(w0 & 0xffffff, __byte_perm(w0, w1, 0x4543) & 0xffffff, __byte_perm(w1, w2, 0x4432) & 0xffffff, w2 >> 8);
+            }
+        }
+        __syncthreads();  // s_px complete; the raw stage is free again
+        uint32_t pix[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int u = swapped ? HIL4_Y[j] : HIL4_X[j], v = swapped ? HIL4_X[j] : HIL4_Y[j];
+            const int lx = (ax + sx * u) - X0, ly = (ay + sy * v) - Y0;
+            pix[j] = s_px[ly * HT_STRIDE + lx];
+        }
+        if (MODE == 0) {
+            uint32_t wd[12];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // 4 pixels -> 3 words
+                const uint32_t a = pix[4 * q], b = pix[4 * q + 1], c = pix[4 * q + 2], e = pix[4 * q + 3];
+                wd[3 * q] = a | (b << 24);
+                wd[3 * q + 1] = (b >> 8) | (c << 16);
+                wd[3 * q + 2] = (c >> 16) | (e << 8);
+            }
+            uint4 *o = reinterpret_cast<uint4 *>(out_rgb + (i0 - blk_begin * 4096) * 3);
+            o[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            o[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+            o[2] = make_uint4(wd[8], wd[9], wd[10], wd[11]);
+            __syncthreads();  // before the next block's expansion overwrites s_px
+            continue;
+        }
+        // predecessor of this thread's first symbol
+        uint32_t prev = __shfl_up_sync(0xffffffffu, pix[15], 1);
+        if (lane == 31) s_last[warp] = pix[15];
+        __syncthreads();  // s_last complete; every thread has gathered its pixels, so s_px may be overwritten after this point
+        if (lane == 0) {
+            if (warp > 0) prev = s_last[warp - 1];
+            else if (B == 0) prev = 0;  // hilbertc.rs:445 START = [0;3]
+            else {
+                uint32_t px, py;
+                hilbert_d2xy_pow2(n, B - 1, &px, &py);
+                const uint8_t *q = rgb + ((size_t)py * n + px) * 3;
+                prev = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+            }
+        }
+        if (MODE == 1) {
+            // 16-bit SIMD lanes: A = (r, b), G = (g, 0); per-lane wrap-around subtraction gives the i16 differences
+            uint32_t wd[24];  // 48 i16 packed two per word
+            uint32_t pa = prev & 0x00ff00ffu, pg = (prev >> 8) & 0xffu;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const uint32_t a0 = pix[j] & 0x00ff00ffu, g0 = (pix[j] >> 8) & 0xffu;
+                const uint32_t a1 = pix[j + 1] & 0x00ff00ffu, g1 = (pix[j + 1] >> 8) & 0xffu;
+                const uint32_t da0 = __vsub2(a0, pa), dg0 = __vsub2(g0, pg), da1 = __vsub2(a1, a0), dg1 = __vsub2(g1, g0);
+                wd[3 * (j / 2)] = __byte_perm(da0, dg0, 0x5410);      // dr0, dg0
+                wd[3 * (j / 2) + 1] = __byte_perm(da0, da1, 0x5432);  // db0, dr1
+                wd[3 * (j / 2) + 2] = __byte_perm(dg1, da1, 0x7610);  // dg1, db1
+                pa = a1; pg = g1;
+            }
+            uint4 *o = reinterpret_cast<uint4 *>(out_delta + (i0 - blk_begin * 4096) * 3);
+#pragma unroll
+            for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
+        } else {
+            // near-zero symbols are counted in shared memory (ATOMS), the rest goes to the global bins directly
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
+                const int d0 = int(c & 0xff) - int(p & 0xff), d1 = int((c >> 8) & 0xff) - int((p >> 8) & 0xff),
+                          d2 = int((c >> 16) & 0xff) - int((p >> 16) & 0xff);
+                if ((unsigned)(d0 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d1 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d2 + CUBE_R) < (unsigned)CUBE_S) {
+                    const int ci = ((d0 + CUBE_R) * CUBE_S + (d1 + CUBE_R)) * CUBE_S + (d2 + CUBE_R);
+                    const int sh = 16 * (ci & 1);
+                    const uint32_t old = atomicAdd(&s_cube[ci >> 1], 1u << sh);
+                    if (((old >> sh) & 0x7fffu) == 0x7fffu) {  // my increment set the guard bit: 2^15 counts leave the field
+                        atomicSub(&s_cube[ci >> 1], 0x8000u << sh);
+                        const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                        atomicAdd(&bins[key], 32768u);
+                        if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
+                    }
+                } else {
+                    const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                    atomicAdd(&bins[key], 1u);
+                    if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
+                }
+            }
+        }
+    }
+    if (MODE == 2) {  // flush the CTA's near-zero counters into the global bins
+        __syncthreads();
+        for (int ci = tid; ci < CUBE_N; ci += 256) {
+            const uint32_t cnt = (s_cube[ci >> 1] >> (16 * (ci & 1))) & 0xffffu;
+            if (cnt) {
+                const int d2 = ci % CUBE_S - CUBE_R, d1 = (ci / CUBE_S) % CUBE_S - CUBE_R, d0 = ci / (CUBE_S * CUBE_S) - CUBE_R;
+                const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                atomicAdd(&bins[key], cnt);
+                if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
+            }
+        }
+    }
+}
+
 // inverse: segmented prefix sum along the curve is sequential per channel; done as a 3-kernel scan over i16 diffs.
 // Arithmetic is modulo 2^32 (unsigned): FromDiff (hilbertc.rs:482-509) panics at the FIRST reconstructed channel outside 0..255
 // (`try_into().unwrap()`), every prefix before that one is in 0..255, so the wrapped value at the first offender equals the true
@@ -1344,16 +1558,48 @@ int cniic_dev_keys_to_points(cniic_ctx *ctx, const uint32_t *d_keys, const unsig
     return CNIIC_OK;
 }
 
+// 2^n squares: the three tile stages, fed by TMA (default) or by plain loads (CNIIC_STAGES_NO_TMA=1, kept for A/B measurements)
+template <int MODE>
+static int launch_tile_stage(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t n, uint8_t *out_rgb, int16_t *out_delta, uint32_t *bins, uint8_t *flags,
+                             unsigned long long blk_begin, unsigned long long blk_end) {
+    static const bool no_tma = getenv("CNIIC_STAGES_NO_TMA") != nullptr;
+    const size_t cube = MODE == 2 ? size_t((CUBE_N + 1) / 2) * 4 : 0;
+    const unsigned long long nblk = blk_end - blk_begin;
+    if (no_tma) {
+        if (MODE == 2) {
+            CU_TRY(ctx, cudaFuncSetAttribute(hilbert_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cube));
+            int per_sm = 0;
+            CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hilbert_tile_kernel<MODE>, 256, cube));
+            if (per_sm < 1) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "delta histogram kernel does not fit an SM");
+            const unsigned grid = (unsigned)std::min<size_t>((size_t)nblk, (size_t)ctx->sm_count * per_sm);  // persistent: one wave
+            hilbert_tile_kernel<MODE><<<grid, 256, cube, ctx->stream>>>(d_rgb, n, out_rgb, out_delta, bins, flags, blk_begin, blk_end);
+        } else {
+            hilbert_tile_kernel<MODE><<<(unsigned)nblk, 256, 0, ctx->stream>>>(d_rgb, n, out_rgb, out_delta, bins, flags, blk_begin, blk_end);
+        }
+    } else {
+        CUtensorMap tmap;
+        if (!tma_encode_2d_u8(&tmap, d_rgb, (uint64_t)n * 3, n, (uint64_t)n * 3, HT * 3, HT))
+            return cniic_set_error(ctx, CNIIC_ERR_CUDA, "cuTensorMapEncodeTiled failed for a %u x %u image", n, n);
+        const size_t smem = 2 * size_t(HT_TILE_BYTES) + 128 + cube;  // two tile stages (+ alignment slack) + the counter cube
+        CU_TRY(ctx, cudaFuncSetAttribute(hilbert_tile_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hilbert_tile_tma_kernel<MODE>, 256, smem));
+        if (per_sm < 1) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "tile stage kernel does not fit an SM");
+        const unsigned grid = (unsigned)std::min<size_t>((size_t)nblk, (size_t)ctx->sm_count * per_sm);  // persistent: one wave
+        hilbert_tile_tma_kernel<MODE><<<grid, 256, smem, ctx->stream>>>(tmap, d_rgb, n, out_rgb, out_delta, bins, flags, blk_begin, blk_end);
+    }
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return CNIIC_OK;
+}
+
 static inline bool tile_path(const void *in, const void *out, uint32_t w, uint32_t h) {
     return w == h && (w & (w - 1)) == 0 && w >= 64 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
 }
 
 int cniic_dev_hilbert_gather(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, uint8_t *d_out) {
     if (tile_path(d_rgb, d_out, w, h)) {
-        hilbert_tile_kernel<0><<<(unsigned)((size_t)w * h / 4096), 256, 0, ctx->stream>>>(d_rgb, w, d_out, nullptr, nullptr, nullptr, 0ull, (unsigned long long)w * h / 4096);
-        ctx->launches++;
-        CU_TRY(ctx, cudaGetLastError());
-        return CNIIC_OK;
+        return launch_tile_stage<0>(ctx, d_rgb, w, d_out, nullptr, nullptr, nullptr, 0ull, (unsigned long long)w * h / 4096);
     }
     hilbert_stream_kernel<0><<<grid_for(ctx, (size_t)w * h), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), d_out, nullptr, nullptr, nullptr, 0ull, (unsigned long long)w * h);
     ctx->launches++;
@@ -1459,15 +1705,8 @@ int cniic_dev_hist_delta_bins_range(cniic_ctx *ctx, const uint8_t *d_rgb, uint32
     uint8_t *flags;
     ST_TRY(hist_space(ctx, 1, d_bins, &flags, nbins));
     if (i0 >= i1) return CNIIC_OK;
-    if (tile_path(d_rgb, nullptr, w, h) && i0 % 4096 == 0 && i1 % 4096 == 0) {
-        const size_t smem = size_t((CUBE_N + 1) / 2) * 4;
-        CU_TRY(ctx, cudaFuncSetAttribute(hilbert_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hilbert_tile_kernel<2>, 256, smem));
-        if (per_sm < 1) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "delta histogram kernel does not fit an SM");
-        const unsigned grid = (unsigned)std::min<size_t>((size_t)((i1 - i0) / 4096), (size_t)ctx->sm_count * per_sm);  // persistent: one wave
-        hilbert_tile_kernel<2><<<grid, 256, smem, ctx->stream>>>(d_rgb, w, nullptr, nullptr, *d_bins, flags, i0 / 4096, i1 / 4096);
-    }
+    if (tile_path(d_rgb, nullptr, w, h) && i0 % 4096 == 0 && i1 % 4096 == 0)
+        return launch_tile_stage<2>(ctx, d_rgb, w, nullptr, nullptr, *d_bins, flags, i0 / 4096, i1 / 4096);
     else hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)(i1 - i0)), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins, flags, i0, i1);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
@@ -1484,17 +1723,14 @@ extern "C" int cniic_voronoi_fill_device(cniic_ctx *ctx, const uint32_t *d_cxy, 
     if (w == 0 || h_local == 0) return CNIIC_OK;
     if (w > CNIIC_MAX_DIM || h > CNIIC_MAX_DIM || (uint64_t)y0 + h_local > h) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "bad image dimensions");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t smem = (size_t)k * 12 + 16;
+    const size_t smem = (size_t)k * 14 + 32;  // level-1 coordinates + colours, level-2 index list
     CU_TRY(ctx, cudaFuncSetAttribute(fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t super_x = (w + FSW - 1) / FSW, super_y = (h_local + FSH - 1) / FSH;
-    DevBuf lists(ctx), counts(ctx);
-    CU_TRY(ctx, lists.alloc((size_t)super_x * super_y * k * 2));
-    CU_TRY(ctx, counts.alloc((size_t)super_x * super_y * 4));
-    fill_supercull_kernel<<<super_x * super_y, 256, 0, ctx->stream>>>(d_cxy, k, w, y0, h_local, super_x, lists.as<uint16_t>(), counts.as<uint32_t>());
+    int per_sm = 0;
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel, 256, smem));
+    if (per_sm < 1) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "fill kernel does not fit an SM");
     const size_t tiles = (size_t)((w + FT - 1) / FT) * ((h_local + FT - 1) / FT);
-    const int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 8);
-    fill_kernel<<<grid, 256, smem, ctx->stream>>>(d_cxy, d_crgb, k, w, y0, h_local, super_x, lists.as<uint16_t>(), counts.as<uint32_t>(), d_out_rgb);
-    ctx->launches++;
+    const int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * per_sm);
+    fill_kernel<<<grid, 256, smem, ctx->stream>>>(d_cxy, d_crgb, k, w, y0, h_local, d_out_rgb);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return CNIIC_OK;
@@ -1716,7 +1952,7 @@ extern "C" int cniic_delta_i16_range_device(cniic_ctx *ctx, const uint8_t *d_rgb
     if (!d_rgb || !d_out) return CNIIC_ERR_BAD_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (tile_path(d_rgb, d_out, w, h) && i_begin % 4096 == 0 && i_end % 4096 == 0)
-        hilbert_tile_kernel<1><<<(unsigned)((i_end - i_begin) / 4096), 256, 0, ctx->stream>>>(d_rgb, w, nullptr, d_out, nullptr, nullptr, i_begin / 4096, i_end / 4096);
+        return launch_tile_stage<1>(ctx, d_rgb, w, nullptr, d_out, nullptr, nullptr, i_begin / 4096, i_end / 4096);
     else
         hilbert_stream_kernel<1><<<grid_for(ctx, (size_t)(i_end - i_begin)), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, d_out, nullptr, nullptr, i_begin, i_end);
     ctx->launches++;

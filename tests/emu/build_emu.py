@@ -84,7 +84,13 @@ NOOP_ASM_RE = re.compile(r'asm\s*(?:volatile)?\s*\(\s*"griddepcontrol\.(?:wait|l
 SHARED_RE = re.compile(r"extern\s+__shared__\s+([\w:<> ]+?)\s+(\w+)\s*\[\s*\]\s*;")
 
 
+# `#ifdef __CUDACC__ ... #endif  // __CUDACC__` blocks hold code only nvcc can compile (TMA / mbarrier inline PTX in tma.cuh); the shim
+# provides host stand-ins of the same names with the same semantics (box copy with zero fill, phase-parity barrier)
+CUDACC_ONLY_RE = re.compile(r"#ifdef __CUDACC__\n.*?#endif  // __CUDACC__\n", re.S)
+
+
 def transform(text: str) -> str:
+    text = CUDACC_ONLY_RE.sub("", text)
     text = ASM_RE.sub(lambda m: f"{m.group(2)} = emu_ptx_{m.group(1).replace('.', '_')}({m.group(3)}, {m.group(4)}, {m.group(5)});", text)
     text = NOOP_ASM_RE.sub(";", text)
     text = SHARED_RE.sub(lambda m: f"{m.group(1)} *{m.group(2)} = reinterpret_cast<{m.group(1)} *>(emu::dyn_smem());", text)

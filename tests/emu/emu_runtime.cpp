@@ -310,6 +310,9 @@ struct AtExit {
 
 }  // namespace
 
+// a fiber waits until *p != val, yielding to the other threads of its CTA (used by the shim's mbarrier stand-in)
+void spin_while_equal(const volatile unsigned *p, unsigned val, const char *what) { wait_on(p, val, what); }
+
 void *dyn_smem() { return M.smem.data(); }
 
 void cta_barrier() {

@@ -122,6 +122,7 @@ struct LaunchCfg {
     LaunchCfg(dim3 g, dim3 b, size_t s = 0, cudaStream_t = nullptr) : grid(g), block(b), smem(s) {}
 };
 void launch(const LaunchCfg &cfg, const std::function<void()> &body, const char *name);
+void spin_while_equal(const volatile unsigned *p, unsigned val, const char *what);
 }  // namespace emu
 
 // cudaLaunchKernelEx with launch attributes (programmatic dependent launch): the emulation runs launches one after another
@@ -132,6 +133,35 @@ struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes; cud
 template <class... KA, class... A> static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t *c, void (*k)(KA...), A &&...a) {
     emu::launch(emu::LaunchCfg(c->gridDim, c->blockDim, c->dynamicSmemBytes, c->stream), [&]() { k(KA(a)...); }, "cudaLaunchKernelEx");
     return cudaSuccess;
+}
+
+// ---- stand-ins of cniic_b200/csrc/tma.cuh (tensor-map tile loads completing on an mbarrier): the copy is performed at once by
+// the issuing thread; the barrier word holds the parity of the phase in progress (bit 0) ----
+#define __grid_constant__
+struct CUtensorMap { const unsigned char *base; unsigned long long inner_bytes, rows, row_stride; unsigned box_inner, box_rows; unsigned long long pad[11]; };
+static inline bool tma_encode_2d_u8(CUtensorMap *m, const void *base, unsigned long long inner_bytes, unsigned long long rows,
+                                    unsigned long long row_stride_bytes, unsigned box_inner, unsigned box_rows) {
+    if (row_stride_bytes % 16 || box_inner % 16 || box_inner > 256 || box_rows > 256 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    m->base = static_cast<const unsigned char *>(base); m->inner_bytes = inner_bytes; m->rows = rows; m->row_stride = row_stride_bytes;
+    m->box_inner = box_inner; m->box_rows = box_rows;
+    return true;
+}
+static inline void mbar_init(unsigned long long *bar, unsigned) { *bar = 0; }
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(unsigned long long *, unsigned) {}
+static inline void mbar_wait(unsigned long long *bar, unsigned parity) {
+    emu::spin_while_equal(reinterpret_cast<const volatile unsigned *>(bar), parity, "mbar_wait (TMA tile not delivered)");
+}
+static inline void tma_load_2d(void *dst, const CUtensorMap *m, int c_inner, int c_row, unsigned long long *bar) {
+    if (reinterpret_cast<uintptr_t>(dst) & 127) { fprintf(stderr, "emu: TMA destination not 128-byte aligned\n"); abort(); }
+    unsigned char *d = static_cast<unsigned char *>(dst);
+    for (unsigned r = 0; r < m->box_rows; r++)
+        for (unsigned b = 0; b < m->box_inner; b++) {
+            const long long y = (long long)c_row + r, x = (long long)c_inner + b;
+            d[(size_t)r * m->box_inner + b] = (y >= 0 && (unsigned long long)y < m->rows && x >= 0 && (unsigned long long)x < m->inner_bytes)
+                                                  ? m->base[(size_t)y * m->row_stride + x] : 0;
+        }
+    *bar ^= 1ull;  // the phase completes
 }
 
 #define threadIdx (emu::g_cur->tid)
