@@ -51,6 +51,64 @@ def test_c2_cluster_colors_k256_4096(ctx):
     ctx.device_free(d)
 
 
+def _session_result(ctx, kind, k, d, n, iters, flags=0, **kw):
+    s = cb.KMeansSession(ctx, kind, k, d, n, on_device=True, flags=flags, **kw)
+    s.reset()
+    st = s.run(iters)
+    cen, wts, asg = s.get()
+    s.close()
+    return cen, wts, asg, st
+
+
+def test_c2_culled_kernels_equal_brute_force_at_full_size(ctx):
+    """at the headline size the culled assignment must be THE nearest centroid, not merely self-consistent.  The
+    default (colour-sorted, exactly culled, second kernel version) and the brute-force kernel (every pixel scores all 256 centroids)
+    must agree bit for bit after 3 iterations -- centroids, weights, every one of the 16.7 M assignments, moved counts -- and a
+    numpy int64 argmin over a sample of pixels must agree with both."""
+    w = h = 4096
+    k = 256
+    d = ctx.device_alloc(w * h * 3)
+    cb.synth_image_device(ctx, d, w, h, 0xC0FFEE + 2, 192)
+    cen, wts, asg, st = _session_result(ctx, cb.POINTS_RGB, k, d, w * h, 3)
+    cen_b, wts_b, asg_b, st_b = _session_result(ctx, cb.POINTS_RGB, k, d, w * h, 3, flags=cb._lib.KMEANS_NO_CULL)
+    assert np.array_equal(cen, cen_b) and np.array_equal(wts, wts_b) and np.array_equal(asg, asg_b)
+    assert (st.moved_last, st.moved_total, st.iterations) == (st_b.moved_last, st_b.moved_total, st_b.iterations)
+    assert st.pairs_scored < st_b.pairs_scored // 10  # the culled run really culled
+    # nearest-centroid sample against numpy: centroids after 2 iterations, assignment of the 3rd pass
+    cen2, _, asg2, _ = _session_result(ctx, cb.POINTS_RGB, k, d, w * h, 2)
+    host = np.zeros((h, w, 3), np.uint8)
+    ctx.d2h(host, d)
+    pts = host.reshape(-1, 3)
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, w * h, 20000)
+    d2 = ((pts[idx].astype(np.int64)[:, None, :] - cen2[None].astype(np.int64)) ** 2).sum(-1)
+    best = d2.min(1)
+    assert np.array_equal(d2[np.arange(len(idx)), asg[idx]], best)  # a minimiser ...
+    tied_prev = d2[np.arange(len(idx)), asg2[idx]] == best
+    assert np.array_equal(asg[idx][tied_prev], asg2[idx][tied_prev])  # ... the current cluster if it ties (kmeans.rs:350-378) ...
+    moved = ~tied_prev
+    assert np.array_equal(asg[idx][moved], d2[moved].argmin(1))  # ... else the lowest index
+    # the unique-colour path (what cluster-colors runs, clusterc.rs:19-28): same checks on its own point list
+    cen_u, nu, st_u = ctx.cluster_colors_device(d, w * h, k, max_iters=3)
+    assert nu == len(np.unique(pts.view(np.dtype((np.void, 3))))) and st_u.iterations == 3
+    ctx.device_free(d)
+
+
+def test_c3_culled_kernels_equal_brute_force_at_full_size(ctx):
+    """The same for the north-star configuration: voronoi k=2048 on 7680x4320, default (three-level culling inside the assign
+    kernel) against the brute-force kernel, 2 iterations (the brute-force pass takes ~10 ms each)."""
+    w, h, k = 7680, 4320, 2048
+    d = ctx.device_alloc(w * h * 3)
+    cb.synth_image_device(ctx, d, w, h, 0xC0FFEE + 3, 2048)
+    kw = dict(w=w, h_local=h)
+    cen, wts, asg, st = _session_result(ctx, cb.POINTS_XYRGB, k, d, w * h, 2, **kw)
+    cen_b, wts_b, asg_b, st_b = _session_result(ctx, cb.POINTS_XYRGB, k, d, w * h, 2, flags=cb._lib.KMEANS_NO_CULL, **kw)
+    assert np.array_equal(cen, cen_b) and np.array_equal(wts, wts_b) and np.array_equal(asg, asg_b)
+    assert (st.moved_last, st.moved_total) == (st_b.moved_last, st_b.moved_total)
+    assert st.pairs_scored < st_b.pairs_scored // 100
+    ctx.device_free(d)
+
+
 def test_c3_voronoi_k2048_8k(ctx):
     w, h, k = 7680, 4320, 2048
     d = ctx.device_alloc(w * h * 3)
