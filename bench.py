@@ -52,17 +52,21 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  ONE poller per job: rank 0 samples
+    every GPU of the run (`gpus` = their indices); eight pollers at 100 ms each measurably disturb 30 us kernels."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpus):
+        self.rows, self.proc = [], None
+        self.gpus = [gpus] if isinstance(gpus, int) else list(gpus)
 
     def start(self):
+        if not self.gpus:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-i", ",".join(str(g) for g in self.gpus)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -73,6 +77,8 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if not self.gpus:
+            return None
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -93,7 +99,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "gpus_sampled": len(self.gpus)}
 
 
 def workload_image(name, w, h, blobs, seed_off=0, y0=0, rows=None):
@@ -274,7 +280,7 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
 
     for _ in range(W):
         one_step()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(list(range(world)) if rank == 0 else [])  # rank 0 polls all GPUs of the job (one process per GPU, one node)
     sampler.start()        # spawns nvidia-smi: do it BEFORE the last warm-up step and the barrier, so no rank enters the timed
     one_step()             # region late (a late rank shows up as a wait inside every other rank's per-iteration exchange)
     barrier()

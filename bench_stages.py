@@ -133,7 +133,7 @@ def run(args, workload, peaks, ClockSampler):
     for _ in range(W):
         dev_step()
     ctx.sync()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(list(range(world)) if rank == 0 else [])  # one poller per job (rank 0, all GPUs)
     sampler.start()
     dev_step()
     barrier()  # all ranks enter the timed region together

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -231,6 +232,10 @@ static int ctx_create_common(int device, cniic_ctx **out) {
         delete ctx;
         return CNIIC_ERR_CUDA;
     }
+    if (getenv("CNIIC_TLOG")) {
+        if (cudaMalloc(&ctx->tlog, 64 * 8 * 8) == cudaSuccess) cudaMemset(ctx->tlog, 0, 64 * 8 * 8);
+        else ctx->tlog = nullptr;
+    }
     *out = ctx;
     return CNIIC_OK;
 }
@@ -261,6 +266,7 @@ extern "C" void cniic_ctx_destroy(cniic_ctx *ctx) {
     for (void *p : ctx->p2p_opened) cudaIpcCloseMemHandle(p);
     if (ctx->p2p_peer_table) cudaFree(ctx->p2p_peer_table);
     if (ctx->p2p_local) cudaFree(ctx->p2p_local);
+    if (ctx->tlog) cudaFree(ctx->tlog);
     for (void *p : ctx->pinned_free) cudaFreeHost(p);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

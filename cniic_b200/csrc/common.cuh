@@ -36,6 +36,7 @@ struct cniic_ctx {
     unsigned long long **p2p_peer_table = nullptr;  // device array [world]
     std::vector<void *> p2p_opened;
     bool p2p_ready = false;
+    unsigned long long *tlog = nullptr;  // CNIIC_TLOG=1: device timeline buffer of the Lloyd loop (64 iterations x 8 timestamps)
     std::vector<uint8_t> pending_stream;  // cniic_codec_encode result that did not fit the caller's buffer (cniic_codec_encode_fetch)
     bool has_pending_stream = false;
     uint32_t *hist_bins[2] = {nullptr, nullptr};  // persistent dense histogram bins (+ page flags), all zero between calls

@@ -90,11 +90,21 @@ struct KmDev {
     const uint2 *tile_box;  // per 2048-point tile of the sorted copy: {bytewise min, bytewise max} of the packed colours
     const uint4 *wseg;      // culled D = 3, v2: per 256-point warp segment {box min, box max, sum r | sum g << 16, sum b | count << 16}
     const unsigned long long *wseg64;  // weighted points: per warp segment {sum r*w, sum g*w, sum b*w, sum w}
+    unsigned long long *tlog;  // CNIIC_TLOG=1: device timeline of the Lloyd loop (globaltimer ns), 8 slots per iteration; else nullptr
+    uint32_t tlog_slot;
     unsigned long long *sums;  // k*(D+1) partial sums + 1 moved counter
     int32_t *cen;              // k*D
     unsigned long long *weights;
     KmState *st;
 };
+
+__device__ __forceinline__ unsigned long long km_now() {
+    unsigned long long t = 0;
+#if defined(__CUDA_ARCH__)
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+#endif
+    return t;
+}
 
 __host__ __device__ inline uint32_t kpad_of(uint32_t k, int G) { return (k + 2 * (G - 1) + G - 1) / G * G; }
 
@@ -1395,6 +1405,7 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
     __shared__ uint32_t s_box[8];  // [6] = U of the tile, [7] = U of the supertile
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (d.tlog && tid == 0 && blockIdx.x == 0) d.tlog[d.tlog_slot] = km_now();
     for (uint32_t i = tid; i < 6 * k; i += THREADS) s_acc[i] = 0u;
 
     const uint32_t w = d.w, hl = d.h_local;
@@ -1658,6 +1669,7 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
     for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
     if (lane == 0 && moved) atomicAdd(&d.sums[6 * k], moved);
     if (tid == 0 && pairs_local) atomicAdd(&d.st->pairs, pairs_local);
+    if (d.tlog && tid == 0) atomicMax(&d.tlog[d.tlog_slot + 1], km_now());  // the last CTA to finish
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1777,6 +1789,7 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode, c
         }
         const size_t par_off = size_t(seq & 1u) * d.world * P2P_SUMS_MAX;
         if (tid == 0) { s_nempty = 0; s_timeout = 0; }
+        if (d.tlog && tid == 0 && cta == 0) d.tlog[d.tlog_slot + 2] = km_now();
         const uint32_t nslices = upd_ctas_of(k);
         const bool owns_moved = cta == (nslices - 1) % ncta;  // the CTA of the last slice also carries the `moved` counter
         if (xch) {
@@ -1799,6 +1812,7 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode, c
             }
             __threadfence_system();  // my stores are performed at every destination before ...
             __syncthreads();
+            if (d.tlog && tid == 0 && cta == 0) d.tlog[d.tlog_slot + 3] = km_now();
             if (tid < d.world) {     // ... the flag that announces them (monotonic exchange number; a fire-and-forget reduction)
                 uint32_t *remote = reinterpret_cast<uint32_t *>(d.peer_base[tid] + p2p_flags_off(d.world)) + size_t(d.my_rank) * UPD_FLAGS_MAX + cta;
                 atomicMax_system(remote, seq);
@@ -1810,6 +1824,7 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode, c
                 __threadfence_system();
             }
             __syncthreads();
+            if (d.tlog && tid == 0 && cta == 0) d.tlog[d.tlog_slot + 4] = km_now();
             if (s_timeout && tid == 0) d.st->dist_empty = 2;
         }
         // ---- reduce (rank order), divide, per-centroid arrays of my slices ----
@@ -2022,6 +2037,7 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode, c
             d.st->empty_events += s_nempty;
             if (moved == 0) d.st->done = 1;
             if (d.st->dist_empty != 2) d.st->dist_empty = 0;
+            if (d.tlog && init_mode == 0) d.tlog[d.tlog_slot + 5] = km_now();
         }
     }
 }
@@ -2540,6 +2556,8 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
         // the state: all of max_iters when it is given (ONE host synchronisation per run), else batches of 8
         uint32_t batch = max_iters ? std::min<uint32_t>(64u, max_iters - done_iters) : 8u;
         for (uint32_t b = 0; b < batch; b++) {
+            km->dev.tlog = ctx->tlog;
+            km->dev.tlog_slot = std::min<uint32_t>(issued, 63u) * 8;
             const bool prof = issued < prof_limit;
             if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * issued], ctx->stream));
             ST_TRY(km_launch_assign(km));
@@ -2561,6 +2579,20 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
         }
         done_iters = km->h_state->iter - km->iter_seen;
         if (km->h_state->done || (max_iters && done_iters >= max_iters)) break;
+    }
+    if (ctx->tlog) {  // CNIIC_TLOG=1: one line per iteration, microseconds on this GPU's globaltimer
+        std::vector<unsigned long long> t(64 * 8);
+        CU_TRY(ctx, cudaMemcpy(t.data(), ctx->tlog, t.size() * 8, cudaMemcpyDeviceToHost));
+        CU_TRY(ctx, cudaMemset(ctx->tlog, 0, t.size() * 8));
+        const uint32_t ni = std::min<uint32_t>(issued, 64u);
+        for (uint32_t i = 0; i < ni; i++) {
+            const unsigned long long *e = &t[i * 8];
+            if (!e[0] || !e[5]) continue;
+            auto us = [](unsigned long long a, unsigned long long b) { return b > a ? double(b - a) * 1e-3 : 0.0; };
+            fprintf(stderr, "[tlog rank %d] it %2u: assign %6.1f | gap %5.1f | update: push+fence %5.1f, wait %5.1f, reduce+close %5.1f | to next assign %5.1f | period %6.1f us\n",
+                    ctx->rank, i, us(e[0], e[1]), us(e[1], e[2]), us(e[2], e[3] ? e[3] : e[2]), us(e[3] ? e[3] : e[2], e[4] ? e[4] : (e[3] ? e[3] : e[2])),
+                    us(e[4] ? e[4] : e[2], e[5]), i + 1 < ni && t[(i + 1) * 8] ? us(e[5], t[(i + 1) * 8]) : 0.0, i + 1 < ni && t[(i + 1) * 8] ? us(e[0], t[(i + 1) * 8]) : 0.0);
+        }
     }
     float ms = 0.f;
     CU_TRY(ctx, cudaEventElapsedTime(&ms, km->ev0, km->ev1));

@@ -81,6 +81,7 @@ def rewrite_launches(text: str) -> str:
 ASM_RE = re.compile(r'asm\s*(?:volatile)?\s*\(\s*"([a-z0-9_.]+)\s+%0,\s*%1,\s*%2,\s*%3;"\s*:\s*"=r"\((\w+)\)\s*:\s*"r"\((\w+)\),\s*"r"\((\w+)\),\s*"r"\((\w+)\)\s*\)\s*;')
 # programmatic-dependent-launch control instructions have no effect when launches run one after another
 NOOP_ASM_RE = re.compile(r'asm\s*(?:volatile)?\s*\(\s*"griddepcontrol\.(?:wait|launch_dependents);"\s*:::\s*"memory"\s*\)\s*;')
+TIMER_ASM_RE = re.compile(r'asm\s*volatile\s*\(\s*"mov\.u64 %0, %%globaltimer;"\s*:\s*"=l"\((\w+)\)\s*\)\s*;')  # timeline instrumentation: no clock here
 SHARED_RE = re.compile(r"extern\s+__shared__\s+([\w:<> ]+?)\s+(\w+)\s*\[\s*\]\s*;")
 
 
@@ -93,6 +94,7 @@ def transform(text: str) -> str:
     text = CUDACC_ONLY_RE.sub("", text)
     text = ASM_RE.sub(lambda m: f"{m.group(2)} = emu_ptx_{m.group(1).replace('.', '_')}({m.group(3)}, {m.group(4)}, {m.group(5)});", text)
     text = NOOP_ASM_RE.sub(";", text)
+    text = TIMER_ASM_RE.sub(lambda m: f"{m.group(1)} = 0;", text)
     text = SHARED_RE.sub(lambda m: f"{m.group(1)} *{m.group(2)} = reinterpret_cast<{m.group(1)} *>(emu::dyn_smem());", text)
     if "asm" in re.sub(r"//.*", "", text) and re.search(r"\basm\s*(volatile)?\s*\(", text):
         raise ValueError("an inline asm statement was not rewritten: extend ASM_RE / the shim")
