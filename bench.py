@@ -252,6 +252,17 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def aligned_start():
+        """barrier + synchronize, then every rank leaves at the same instant of the node's monotonic clock: ranks drop out of an NCCL
+        barrier tens of microseconds apart, which a 0.5 ms step whose first exchange waits for the last rank would count as work."""
+        barrier()
+        if world > 1:
+            t = torch.tensor([time.monotonic_ns() + 400_000], dtype=torch.int64, device="cuda")
+            dist.broadcast(t, src=0)
+            t_go = int(t.item())
+            while time.monotonic_ns() < t_go:
+                pass
+
     n_unique = [0]
 
     def one_step(flags=0, iters=ITERS):
@@ -292,7 +303,7 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
     for i in range(K):
         flush.fill_(i & 0xff)           # evict the image from L2 between timed steps (untimed)
         if world > 1:
-            barrier()                   # every rank enters every timed step together (a late rank is waited for inside the exchange)
+            aligned_start()             # every rank enters every timed step together (a late rank is waited for inside the exchange)
         else:
             torch.cuda.synchronize()
         ev[i][0].record(stream)

@@ -74,6 +74,21 @@ void cniic_pinned_put(cniic_ctx *ctx, void *p) {
     if (p) ctx->pinned_free.push_back(p);
 }
 
+void *cniic_pinned_big_get(cniic_ctx *ctx) {
+    if (!ctx->pinned_big_free.empty()) {
+        void *p = ctx->pinned_big_free.back();
+        ctx->pinned_big_free.pop_back();
+        return p;
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, size_t(CNIIC_MAX_K) * 5 * 4) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void cniic_pinned_big_put(cniic_ctx *ctx, void *p) {
+    if (p) ctx->pinned_big_free.push_back(p);
+}
+
 int cniic_launch_bump(cniic_ctx *ctx, uint32_t n) {
     ctx->launches += n;
     return CNIIC_OK;
@@ -164,10 +179,10 @@ int cniic_nccl_allgather_bytes(cniic_ctx *ctx, const void *d_send, void *d_recv,
 }
 
 // ---- peer-memory exchange region (CUDA IPC between the per-GPU processes) ---------------------------------------------------
-// layout (kmeans.cu: p2p_flags_off / p2p_xcount_off): recv[2 parities][world source ranks][P2P_SUMS_MAX u64] | u32 flags[world][64] |
-// u32 exchange counter.  3.1 MB for 8 ranks.
+// layout (kmeans.cu: p2p_xcount_off): recv[2 parities][world source ranks][P2P_SUMS_MAX cells of 16 bytes] | u32 exchange counter.
+// 6.3 MB for 8 ranks.
 static const size_t P2P_SUMS_MAX_HOST = CNIIC_MAX_K * 6 + 8;
-static size_t p2p_region_bytes(int world) { return 2 * size_t(world) * P2P_SUMS_MAX_HOST * 8 + size_t(world) * 64 * 4 + 256; }
+static size_t p2p_region_bytes(int world) { return 4 * size_t(world) * P2P_SUMS_MAX_HOST * 8 + 256; }
 
 extern "C" int cniic_ctx_p2p_export(cniic_ctx *ctx, uint8_t out_handle[64]) {
     if (!ctx || !out_handle) return CNIIC_ERR_BAD_ARG;
@@ -268,6 +283,7 @@ extern "C" void cniic_ctx_destroy(cniic_ctx *ctx) {
     if (ctx->p2p_local) cudaFree(ctx->p2p_local);
     if (ctx->tlog) cudaFree(ctx->tlog);
     for (void *p : ctx->pinned_free) cudaFreeHost(p);
+    for (void *p : ctx->pinned_big_free) cudaFreeHost(p);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

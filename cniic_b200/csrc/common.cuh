@@ -30,6 +30,7 @@ struct cniic_ctx {
     struct Block { void *p; size_t bytes; bool used; };
     std::vector<Block> cache;
     std::vector<void *> pinned_free;  // 256-byte pinned host slots
+    std::vector<void *> pinned_big_free;  // CNIIC_MAX_K * 5 * 4-byte pinned host staging buffers (initial centroids of sharded sessions)
     std::vector<cudaEvent_t> event_pool;
     // peer-memory exchange (multi-GPU): my IPC region (receive areas, flags, exchange counter), the peer-mapped bases of all ranks (device table)
     unsigned long long *p2p_local = nullptr;
@@ -46,6 +47,8 @@ void *cniic_cache_alloc(cniic_ctx *ctx, size_t bytes);  // nullptr + error set o
 void cniic_cache_free(cniic_ctx *ctx, void *p);
 void *cniic_pinned_get(cniic_ctx *ctx);
 void cniic_pinned_put(cniic_ctx *ctx, void *p);
+void *cniic_pinned_big_get(cniic_ctx *ctx);  // CNIIC_MAX_K * 5 * 4 bytes
+void cniic_pinned_big_put(cniic_ctx *ctx, void *p);
 
 struct DevBuf {  // RAII scratch from the ctx cache
     cniic_ctx *ctx;

@@ -1454,19 +1454,35 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
             if (lane == 0) atomicMin(&s_box[7], um);
             __syncthreads();
             const uint32_t US = s_box[7] + 3u * 255u * 255u;  // colour part of UB for the full colour cube
-            uint32_t placed = 0;
-            for (uint32_t cb = 0; cb < k; cb += THREADS) {
-                const uint32_t c = cb + tid;
-                bool keep = false;
-                if (c < k) {
-                    const uint32_t cxy = d.g_cxy[c];
-                    const int cx = cxy & 0xffff, cy = cxy >> 16;
-                    keep = uint32_t(sq(max(0, max(sx0 - cx, cx - sx1))) + sq(max(0, max(sy0 - cy, cy - sy1)))) <= US;
-                }
-                uint32_t tot;
-                const uint32_t r = block_rank256(keep, s_warp, &tot);
-                if (keep) s_list[placed + r] = (uint16_t)c;
-                placed += tot;
+            // ordered compaction with ONE block-wide prefix: thread t tests the consecutive ids [t * per, (t + 1) * per), so thread
+            // order = id order and the kept ids of a thread go out in one piece
+            const uint32_t per = (k + THREADS - 1) / THREADS, c_lo = min(k, uint32_t(tid) * per), c_hi = min(k, c_lo + per);
+            uint32_t keep_mask = 0;  // per <= CNIIC_MAX_K / 256 = 16 bits
+            for (uint32_t c = c_lo; c < c_hi; c++) {
+                const uint32_t cxy = d.g_cxy[c];
+                const int cx = cxy & 0xffff, cy = cxy >> 16;
+                if (uint32_t(sq(max(0, max(sx0 - cx, cx - sx1))) + sq(max(0, max(sy0 - cy, cy - sy1)))) <= US) keep_mask |= 1u << (c - c_lo);
+            }
+            const uint32_t mine_n = __popc(keep_mask);
+            uint32_t incl = mine_n;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            __syncthreads();  // s_warp is free (a previous use has been read)
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            uint32_t pos = incl - mine_n, placed = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t v = s_warp[i];
+                if (i < warp) pos += v;
+                placed += v;
+            }
+            while (keep_mask) {
+                const uint32_t b = __ffs(keep_mask) - 1;
+                keep_mask &= keep_mask - 1;
+                s_list[pos++] = (uint16_t)(c_lo + b);
             }
             m = placed;
             cur_sup = sup;
@@ -1753,13 +1769,11 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *s_warp, uint
 // runs, state.  init_mode 1 (session start) and 2 (resume after the host repaired empty clusters of a sharded run) run on one CTA.
 // ------------------------------------------------------------------------------------------------------------
 constexpr uint32_t UPD_SLICE = 256;     // clusters per CTA slice of the update kernel
-constexpr uint32_t UPD_FLAGS_MAX = 64;  // flag slots per source rank (>= CNIIC_MAX_K / UPD_SLICE)
 
 __host__ __device__ inline uint32_t upd_ctas_of(uint32_t k) { return (k + UPD_SLICE - 1) / UPD_SLICE; }
 
-// exchange region of one rank (u64 units): recv[2][world][P2P_SUMS_MAX] | flags: u32[world][UPD_FLAGS_MAX] | xcount u32
-__host__ __device__ inline size_t p2p_flags_off(int world) { return size_t(2) * world * P2P_SUMS_MAX; }
-__host__ __device__ inline size_t p2p_xcount_off(int world) { return p2p_flags_off(world) + size_t(world) * UPD_FLAGS_MAX / 2; }
+// exchange region of one rank (u64 units): recv[2 parities][world][P2P_SUMS_MAX cells of 2 words] | xcount u32
+__host__ __device__ inline size_t p2p_xcount_off(int world) { return size_t(4) * world * P2P_SUMS_MAX; }
 
 template <int D>
 __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode, const uint32_t cta, const uint32_t ncta) {
@@ -1773,7 +1787,7 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode, c
     __shared__ uint32_t s_nempty, s_victim, s_m, s_last, s_timeout;
     __shared__ uint16_t s_empty[CNIIC_MAX_K];
     __shared__ uint32_t s_found[CNIIC_MAX_K];
-    __shared__ ulonglong2 s_red[UPD_SLICE * DW / 2];
+    __shared__ ulonglong2 s_red[UPD_SLICE * DW / 2 + 1];  // reduced values of one slice (+ the moved counter)
     const uint32_t k = d.k;
     const int tid = threadIdx.x;
     unsigned long long moved = 0;
@@ -1787,74 +1801,68 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode, c
             my_base = d.peer_base[d.my_rank];
             seq = *reinterpret_cast<volatile uint32_t *>(my_base + p2p_xcount_off(d.world)) + 1u;  // bumped by the closing CTA only
         }
-        const size_t par_off = size_t(seq & 1u) * d.world * P2P_SUMS_MAX;
+        // receive area of (parity, source rank): one 16-byte cell per u64 value = {low half | tag << 32, high half | tag << 32}
+        const size_t par_off = size_t(seq & 1u) * d.world * (2 * size_t(P2P_SUMS_MAX));
         if (tid == 0) { s_nempty = 0; s_timeout = 0; }
         if (d.tlog && tid == 0 && cta == 0) d.tlog[d.tlog_slot + 2] = km_now();
         const uint32_t nslices = upd_ctas_of(k);
-        const bool owns_moved = cta == (nslices - 1) % ncta;  // the CTA of the last slice also carries the `moved` counter
+        const unsigned long long tag = (unsigned long long)seq << 32;
         if (xch) {
-            // ---- push my slices of this rank's partial sums to every rank (including myself), then one flag per destination ----
+            // ---- push: every value of my slices goes to every rank (myself included) as a self-validating cell.  Each 8-byte
+            // word carries the exchange number beside 32 bits of payload (the scheme of NCCL's LL protocol), and aligned 8-byte
+            // accesses are single-copy atomic: the receiver needs neither a fence nor a flag -- a word whose tag equals `seq`
+            // holds this exchange's data, whichever way the 16 bytes travelled.  One one-way NVLink trip per iteration. ----
             for (uint32_t sl = cta; sl < nslices; sl += ncta) {
                 const uint32_t c0 = sl * UPD_SLICE, ncl = min(UPD_SLICE, k - c0);
-                const uint32_t nchunk = ncl * DW / 2;  // DW is even: whole 128-bit chunks, 16-byte aligned (c0 * DW * 8)
-                ulonglong2 *mine = reinterpret_cast<ulonglong2 *>(d.sums + size_t(c0) * DW);
-                for (uint32_t i = tid; i < nchunk; i += 1024) {
-                    const ulonglong2 v = mine[i];
-                    mine[i] = make_ulonglong2(0ull, 0ull);  // ready for the next iteration's accumulation
+                const uint32_t nval = ncl * DW + ((sl == nslices - 1) ? 1u : 0u);  // (+ the moved counter, which follows the last cluster)
+                unsigned long long *mine = d.sums + size_t(c0) * DW;
+                for (uint32_t i = tid; i < nval; i += 1024) {
+                    const unsigned long long v = mine[i];
+                    mine[i] = 0ull;  // ready for the next iteration's accumulation
+                    const ulonglong2 cell = make_ulonglong2((v & 0xffffffffull) | tag, (v >> 32) | tag);
                     for (int r = 0; r < d.world; r++)
-                        reinterpret_cast<ulonglong2 *>(d.peer_base[r] + par_off + size_t(d.my_rank) * P2P_SUMS_MAX + size_t(c0) * DW)[i] = v;
+                        reinterpret_cast<ulonglong2 *>(d.peer_base[r] + par_off + size_t(d.my_rank) * (2 * size_t(P2P_SUMS_MAX)))[size_t(c0) * DW + i] = cell;
                 }
             }
-            if (owns_moved && tid == 0) {
-                const unsigned long long v = d.sums[size_t(k) * DW];
-                d.sums[size_t(k) * DW] = 0ull;
-                for (int r = 0; r < d.world; r++) (d.peer_base[r] + par_off + size_t(d.my_rank) * P2P_SUMS_MAX)[size_t(k) * DW] = v;
-            }
-            __threadfence_system();  // my stores are performed at every destination before ...
-            __syncthreads();
             if (d.tlog && tid == 0 && cta == 0) d.tlog[d.tlog_slot + 3] = km_now();
-            if (tid < d.world) {     // ... the flag that announces them (monotonic exchange number; a fire-and-forget reduction)
-                uint32_t *remote = reinterpret_cast<uint32_t *>(d.peer_base[tid] + p2p_flags_off(d.world)) + size_t(d.my_rank) * UPD_FLAGS_MAX + cta;
-                atomicMax_system(remote, seq);
-                volatile uint32_t *arrived = reinterpret_cast<volatile uint32_t *>(my_base + p2p_flags_off(d.world)) + size_t(tid) * UPD_FLAGS_MAX + cta;
+        }
+        // ---- reduce (rank order), divide, per-centroid arrays of my slices ----
+        unsigned long long *s_val = reinterpret_cast<unsigned long long *>(s_red);
+        for (uint32_t sl = cta; sl < nslices; sl += ncta) {
+            const uint32_t c0 = sl * UPD_SLICE, ncl = min(UPD_SLICE, k - c0);
+            const bool last_slice = sl == nslices - 1;
+            const uint32_t nval = ncl * DW + (last_slice ? 1u : 0u);
+            __syncthreads();  // s_val of the previous slice has been consumed
+            if (xch) {
                 const long long t0 = clock64();
-                while (int(*arrived - seq) < 0) {
-                    if (clock64() - t0 > (4ll << 30)) { s_timeout = 1; break; }  // ~2 s: never hang the GPU, report and carry on
+                for (uint32_t i = tid; i < nval; i += 1024) {
+                    unsigned long long acc = 0;
+                    for (int r = 0; r < d.world; r++) {
+                        const volatile unsigned long long *cell = my_base + par_off + size_t(r) * (2 * size_t(P2P_SUMS_MAX)) + 2 * (size_t(c0) * DW + i);
+                        unsigned long long lo, hi;
+                        for (;;) {  // poll until both words of the cell carry this exchange's tag
+                            lo = cell[0]; hi = cell[1];
+                            if ((lo >> 32) == seq && (hi >> 32) == seq) break;
+                            if (clock64() - t0 > (4ll << 30)) { s_timeout = 1; break; }  // ~2 s: never hang the GPU, report and carry on
+                        }
+                        acc += (lo & 0xffffffffull) | (hi << 32);
+                    }
+                    s_val[i] = acc;
                 }
-                __threadfence_system();
+            } else {
+                unsigned long long *mine = d.sums + size_t(c0) * DW;
+                for (uint32_t i = tid; i < nval; i += 1024) { s_val[i] = mine[i]; mine[i] = 0ull; }
             }
             __syncthreads();
             if (d.tlog && tid == 0 && cta == 0) d.tlog[d.tlog_slot + 4] = km_now();
-            if (s_timeout && tid == 0) d.st->dist_empty = 2;
-        }
-        // ---- reduce (rank order), divide, per-centroid arrays of my slices ----
-        for (uint32_t sl = cta; sl < nslices; sl += ncta) {
-            const uint32_t c0 = sl * UPD_SLICE, ncl = min(UPD_SLICE, k - c0);
-            const uint32_t nchunk = ncl * DW / 2;
-            __syncthreads();  // s_red of the previous slice has been consumed
-            if (xch) {
-                for (uint32_t i = tid; i < nchunk; i += 1024) {
-                    ulonglong2 acc = make_ulonglong2(0ull, 0ull);
-                    for (int r = 0; r < d.world; r++) {
-                        const ulonglong2 v = __ldcv(reinterpret_cast<const ulonglong2 *>(my_base + par_off + size_t(r) * P2P_SUMS_MAX + size_t(c0) * DW) + i);
-                        acc.x += v.x; acc.y += v.y;
-                    }
-                    s_red[i] = acc;
-                }
-            } else {
-                ulonglong2 *mine = reinterpret_cast<ulonglong2 *>(d.sums + size_t(c0) * DW);
-                for (uint32_t i = tid; i < nchunk; i += 1024) { s_red[i] = mine[i]; mine[i] = make_ulonglong2(0ull, 0ull); }
-            }
-            __syncthreads();
-            const unsigned long long *rs = reinterpret_cast<const unsigned long long *>(s_red);
             for (uint32_t j = tid; j < ncl; j += 1024) {
                 const uint32_t c = c0 + j;
-                const unsigned long long wsum = rs[j * DW + D];
+                const unsigned long long wsum = s_val[j * DW + D];
                 d.weights[c] = wsum;
                 if (wsum) {
                     int32_t v[D];
                     uint32_t nrm = 0;
-                    for (int q = 0; q < D; q++) { v[q] = int32_t(rs[j * DW + q] / wsum); d.cen[c * D + q] = v[q]; nrm += uint32_t(v[q] * v[q]); }
+                    for (int q = 0; q < D; q++) { v[q] = int32_t(s_val[j * DW + q] / wsum); d.cen[c * D + q] = v[q]; nrm += uint32_t(v[q] * v[q]); }
                     if (!d.brute) {  // culled kernels only need the per-centroid arrays in id order
                         const uint32_t cpk = uint32_t(v[rgb0]) | (uint32_t(v[rgb0 + 1]) << 8) | (uint32_t(v[rgb0 + 2]) << 16);
                         d.g_cpk[c] = cpk;
@@ -1869,17 +1877,9 @@ __device__ __forceinline__ void km_finalize_body(const KmDev d, int init_mode, c
                     atomicAdd(&s_nempty, 1u);
                 }
             }
+            if (last_slice && tid == 0) d.st->moved_red = s_val[ncl * DW];
         }
-        if (owns_moved && tid == 0) {
-            unsigned long long m = 0;
-            if (xch) {
-                for (int r = 0; r < d.world; r++) m += __ldcv(my_base + par_off + size_t(r) * P2P_SUMS_MAX + size_t(k) * DW);
-            } else {
-                m = d.sums[size_t(k) * DW];
-                d.sums[size_t(k) * DW] = 0ull;
-            }
-            d.st->moved_red = m;
-        }
+        if (xch && s_timeout && tid == 0) d.st->dist_empty = 2;
         // ---- the CTA that finishes last closes the iteration ----
         __syncthreads();
         if (tid == 0) {
@@ -2168,6 +2168,8 @@ struct cniic_kmeans {
     uint32_t *own_wts = nullptr;
     void *pool = nullptr;  // one allocation for table + sums + centroids + state
     KmState *h_state = nullptr;  // pinned
+    void *h_init = nullptr;      // pinned staging of the caller's initial centroids (a pageable source would block the host in the copy)
+    bool h_init_in_flight = false;  // a copy out of h_init has been enqueued and the stream not synchronised since
     size_t smem = 0;
     int grid = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -2471,7 +2473,12 @@ extern "C" int cniic_kmeans_reset(cniic_kmeans *km, const int32_t *host_init_cen
         km->launches++;
     }
     if (host_init_centroids) {
-        CU_TRY(ctx, cudaMemcpyAsync(km->dev.cen, host_init_centroids, size_t(km->desc.k) * km->D * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!km->h_init) km->h_init = cniic_pinned_big_get(ctx);
+        if (!km->h_init) return cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMallocHost failed");
+        if (km->h_init_in_flight) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // two resets in a row: let the earlier copy finish
+        km->h_init_in_flight = true;
+        memcpy(km->h_init, host_init_centroids, size_t(km->desc.k) * km->D * 4);
+        CU_TRY(ctx, cudaMemcpyAsync(km->dev.cen, km->h_init, size_t(km->desc.k) * km->D * 4, cudaMemcpyHostToDevice, ctx->stream));
     } else {
         if (ctx->world > 1 || km->desc.n_local != km->desc.n_total)
             return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "a sharded session needs explicit initial centroids");
@@ -2569,6 +2576,7 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
         CU_TRY(ctx, cudaEventRecord(km->ev1, ctx->stream));  // complete once the stream has been synchronised below
         CU_TRY(ctx, cudaMemcpyAsync(km->h_state, km->dev.st, sizeof(KmState), cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        km->h_init_in_flight = false;
         if (km->h_state->dist_empty == 2)
             return cniic_set_error(ctx, CNIIC_ERR_NCCL, "peer-memory exchange timed out waiting for another rank");
         if (km->h_state->dist_empty == 1) {
@@ -2971,6 +2979,7 @@ extern "C" void cniic_kmeans_close(cniic_kmeans *km) {
     cniic_cache_free(km->ctx, km->d_wsorted);
     cniic_cache_free(km->ctx, km->d_assign_orig);
     cniic_pinned_put(km->ctx, km->h_state);
+    cniic_pinned_big_put(km->ctx, km->h_init);
     if (km->ev0) km->ctx->event_pool.push_back(km->ev0);
     if (km->ev1) km->ctx->event_pool.push_back(km->ev1);
     for (cudaEvent_t e : km->pev)
