@@ -44,7 +44,7 @@ constexpr int FSW = 512, FSH = 256;  // supertile (8 x 4 tiles): level 1 of the 
 //   level 2  64x64 tile, over the supertile's list (shared memory to shared memory: no dependent global loads per tile -- the first
 //            version chased list -> coordinates -> colours through global memory for every tile and was latency bound at 70 us);
 //   level 3  64x8 strip of a warp, over the tile's list, survivors broadcast by shuffle and scored: ~5 centroids per pixel.
-__global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ cxy, const uint8_t *__restrict__ crgb, uint32_t k,
+__global__ void __launch_bounds__(256, 4) fill_kernel(const uint32_t *__restrict__ cxy, const uint8_t *__restrict__ crgb, uint32_t k,
                                                    uint32_t w, uint32_t y0, uint32_t h_local, uint8_t *__restrict__ out) {
     extern __shared__ uint4 fsm[];
     int2 *s_sc = reinterpret_cast<int2 *>(fsm);                      // level-1 survivors: coordinates
@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ 
     uint16_t *s_ti = reinterpret_cast<uint16_t *>(s_scol + k);       // level-2 survivors: positions in the level-1 list
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_U[2];
+    __shared__ uint32_t s_wcol[8][64];  // per warp: colours of its level-3 survivors by slot
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_x = (w + FT - 1) / FT, tiles_y = (h_local + FT - 1) / FT;
     const uint32_t super_x = (w + FSW - 1) / FSW;
@@ -153,10 +154,18 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ 
         uw = __reduce_min_sync(0xffffffffu, uw);
         const int row = lane >> 2, seg = (lane & 3) * 16;
         const int gy = wy0 + row, xs = x0 + seg;
-        uint32_t bd[16], bc[16];
+        uint32_t bc[16];
+        // Fast path (any realistic image): the strip's bound uw < 2^25 means every survivor lies within 5 793 + 65 pixels of every
+        // pixel of the strip, so d^2 < 2^26 and `d^2 * 64 + slot` fits 32 bits: the running minimum of that key IS the first
+        // minimum (slots are handed out in ascending id order), three instructions per pixel and centroid (IADD, IMAD, VIMNMX)
+        // instead of five and half the registers.  More than 64 survivors or a huge bound take the compare/select loop below.
+        uint32_t *w_col = s_wcol[warp];
+        bool packed_ok = uw < (1u << 25);
+        uint32_t key[16];
 #pragma unroll
-        for (int p = 0; p < 16; p++) { bd[p] = 0xffffffffu; bc[p] = 0; }
-        for (uint32_t jb = 0; jb < ncand; jb += 32) {
+        for (int p = 0; p < 16; p++) key[p] = 0xffffffffu;
+        uint32_t nslot = 0;
+        for (uint32_t jb = 0; jb < ncand && packed_ok; jb += 32) {
             const uint32_t j = jb + lane;
             int2 c = make_int2(0, 0);
             uint32_t col = 0;
@@ -169,21 +178,61 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t *__restrict__ 
                 keep = dx * dx + dy * dy <= uw;
             }
             uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            if (nslot + __popc(mask) > 64u) { packed_ok = false; break; }
+            if (keep) w_col[nslot + __popc(mask & ((1u << lane) - 1))] = col;
             while (mask) {  // warp-uniform, ascending ids
                 const int src = __ffs(mask) - 1;
                 mask &= mask - 1;
                 const int ccx = __shfl_sync(0xffffffffu, c.x, src), ccy = __shfl_sync(0xffffffffu, c.y, src);
-                const uint32_t ccol = __shfl_sync(0xffffffffu, col, src);
                 const int dy = ccy - gy;
-                const uint32_t dy2 = dy * dy;
+                const uint32_t base = uint32_t(dy * dy) * 64u + nslot;
+                const int c8 = (ccx - xs) * 8;
 #pragma unroll
                 for (int p = 0; p < 16; p++) {
-                    const int dx = ccx - (xs + p);
-                    const uint32_t dd = dx * dx + dy2;
-                    if (dd < bd[p]) { bd[p] = dd; bc[p] = ccol; }
+                    const int d8 = c8 - 8 * p;
+                    key[p] = min(key[p], uint32_t(d8 * d8) + base);
+                }
+                nslot++;
+            }
+        }
+        if (packed_ok) {
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < 16; p++) bc[p] = w_col[key[p] & 63u];
+        } else {
+            uint32_t bd[16];
+#pragma unroll
+            for (int p = 0; p < 16; p++) { bd[p] = 0xffffffffu; bc[p] = 0; }
+            for (uint32_t jb = 0; jb < ncand; jb += 32) {
+                const uint32_t j = jb + lane;
+                int2 c = make_int2(0, 0);
+                uint32_t col = 0;
+                bool keep = false;
+                if (j < ncand) {
+                    const uint32_t e = s_ti[j];
+                    c = s_sc[e];
+                    col = s_scol[e];
+                    const uint32_t dx = max(0, max(x0 - c.x, c.x - x1)), dy = max(0, max(wy0 - c.y, c.y - wy1));
+                    keep = dx * dx + dy * dy <= uw;
+                }
+                uint32_t mask = __ballot_sync(0xffffffffu, keep);
+                while (mask) {  // warp-uniform, ascending ids
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int ccx = __shfl_sync(0xffffffffu, c.x, src), ccy = __shfl_sync(0xffffffffu, c.y, src);
+                    const uint32_t ccol = __shfl_sync(0xffffffffu, col, src);
+                    const int dy = ccy - gy;
+                    const uint32_t dy2 = dy * dy;
+#pragma unroll
+                    for (int p = 0; p < 16; p++) {
+                        const int dx = ccx - (xs + p);
+                        const uint32_t dd = dx * dx + dy2;
+                        if (dd < bd[p]) { bd[p] = dd; bc[p] = ccol; }
+                    }
                 }
             }
         }
+        __syncwarp();  // (w_col is rewritten by the next tile)
         if (gy > gy1) continue;
         uint8_t *o = out + ((size_t)(gy - (int)y0) * w + xs) * 3;
         if (xs + 15 <= x1 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {  // 16 pixels = three 128-bit stores
