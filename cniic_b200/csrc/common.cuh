@@ -104,6 +104,12 @@ __device__ __forceinline__ void pdl_trigger() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
+// start fetching a line into L1 without holding a destination register (the later load then hits L1)
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
     cudaLaunchAttribute at[1];

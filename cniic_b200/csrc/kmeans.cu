@@ -1403,16 +1403,18 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
     uint16_t *s_list = reinterpret_cast<uint16_t *>(s_acc + 6 * k);       // level-1 candidates of the current supertile (ascending ids)
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_box[8];  // [6] = U of the tile, [7] = U of the supertile
+    __shared__ unsigned long long s_pairs;  // pairs scored by this CTA (kept out of the registers: the kernel sits at its 80-register cap)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (d.tlog && tid == 0 && blockIdx.x == 0) d.tlog[d.tlog_slot] = km_now();
     for (uint32_t i = tid; i < 6 * k; i += THREADS) s_acc[i] = 0u;
+    if (tid == 0) s_pairs = 0ull;
 
     const uint32_t w = d.w, hl = d.h_local;
     const uint32_t tiles_x = (w + TW - 1) / TW, tiles_y = (hl + TH - 1) / TH;
-    const unsigned long long tiles = (unsigned long long)tiles_x * tiles_y;
+    const uint32_t tiles = tiles_x * tiles_y;  // < 2^32: images are at most 16384 x 16384
     const bool fast_ok = (w % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.rgb) & 7) == 0);
-    unsigned long long moved = 0, pairs_local = 0;
+    uint32_t moved = 0;  // per thread: at most 8 points per tile
     uint32_t since_flush = 0;
 
     // Tiles are enumerated SUPERTILE BY SUPERTILE (8 x 8 tiles) and every CTA owns a contiguous range of that order, so it meets
@@ -1420,15 +1422,15 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
     // centroids, ~2 us per list): the former km_supercull launch -- a whole kernel of latency per Lloyd iteration, which is what
     // limits a row-sharded run -- is gone.
     constexpr uint32_t STX = SW / TW, STY = SH / TH;
-    const unsigned long long per_cta = (tiles + gridDim.x - 1) / gridDim.x;
-    const unsigned long long t_begin = blockIdx.x * per_cta, t_end = min(tiles, t_begin + per_cta);
+    const uint32_t per_cta = (tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t t_begin = min(tiles, blockIdx.x * per_cta), t_end = min(tiles, t_begin + per_cta);
     uint32_t cur_sup = 0xffffffffu, m = 0;
-    for (unsigned long long tile_seq = t_begin; tile_seq < t_end; tile_seq++) {
+    for (uint32_t tile_seq = t_begin; tile_seq < t_end; tile_seq++) {
         uint32_t tx, ty, sup;
         {
             const uint32_t row_tiles = tiles_x * STY;                       // tiles of a full row of supertiles
-            const uint32_t sy = uint32_t(tile_seq / row_tiles);
-            const uint32_t rem = uint32_t(tile_seq - (unsigned long long)sy * row_tiles);
+            const uint32_t sy = tile_seq / row_tiles;
+            const uint32_t rem = tile_seq - sy * row_tiles;
             const uint32_t rows_in = min(STY, tiles_y - sy * STY);
             const uint32_t sx = rem / (STX * rows_in);
             const uint32_t rem2 = rem - sx * STX * rows_in;
@@ -1437,7 +1439,7 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
             ty = sy * STY + rem2 / cols_in;
             sup = sy * d.super_x + sx;
         }
-        const unsigned long long tile = (unsigned long long)ty * tiles_x + tx;  // raster index (static per-tile tables)
+        const uint32_t tile = ty * tiles_x + tx;  // raster index (static per-tile tables)
         if (sup != cur_sup) {
             __syncthreads();  // the previous tile is done with s_list / s_box
             const int sx0 = (sup % d.super_x) * SW, syl0 = (sup / d.super_x) * SH;
@@ -1512,18 +1514,9 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
                 }
             }
         }
-        // current cluster of my 8 pixels: one 128-bit load (issued early, consumed after the scoring)
-        uint4 pv = make_uint4(0, 0, 0, 0);
-        if (nv == PX && fast_ok) pv = *reinterpret_cast<const uint4 *>(d.assign + lbase);
-        else {
-            uint32_t t[PX];
-#pragma unroll
-            for (int p = 0; p < PX; p++) t[p] = p < nv ? d.assign[lbase + p] : 0u;
-            pv = make_uint4(t[0] | (t[1] << 16), t[2] | (t[3] << 16), t[4] | (t[5] << 16), t[6] | (t[7] << 16));
-        }
+        prefetch_l1(d.assign + lbase);  // the current cluster ids of my 8 pixels are read after the scoring loop
         // ---- static colour bounding box of the tile and sums of my warp's 4 x 64 pixels (km_tile_boxes_xy2, once per session) ----
         const uint2 box = d.tile_box[tile];
-        const uint4 seg = d.wseg[tile * 8 + warp];
         __syncthreads();  // previous tile is done with s_box / t_ent
         if (tid == 0) s_box[6] = 0xffffffffu;
         __syncthreads();
@@ -1581,7 +1574,7 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
             const uint32_t r = block_rank256(keep, s_warp, &nt);
             if (keep) t_ent[r] = ent;
             __syncthreads();
-            if (tid == 0) pairs_local += (unsigned long long)nt * vw * vh;
+            if (tid == 0) s_pairs += (unsigned long long)nt * vw * vh;
             for (uint32_t e = 0; e < nt; e++) {
                 const uint4 c = t_ent[e];
 #pragma unroll
@@ -1593,6 +1586,15 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
             if (base + TCAP < m) __syncthreads();  // next round overwrites t_ent
         }
 
+        // current cluster of my 8 pixels: one 128-bit load (after the scoring loop: its four registers would otherwise spill there)
+        uint4 pv = make_uint4(0, 0, 0, 0);
+        if (nv == PX && fast_ok) pv = *reinterpret_cast<const uint4 *>(d.assign + lbase);
+        else {
+            uint32_t t[PX];
+#pragma unroll
+            for (int p = 0; p < PX; p++) t[p] = p < nv ? d.assign[lbase + p] : 0u;
+            pv = make_uint4(t[0] | (t[1] << 16), t[2] | (t[3] << 16), t[4] | (t[5] << 16), t[6] | (t[7] << 16));
+        }
         const uint32_t yg = yg0 + row;
         const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
         uint32_t idx[PX];
@@ -1625,6 +1627,7 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
         // ---- accumulate: whole warp in one cluster -> precomputed segment sums; my 8 pixels in one cluster -> closed forms +
         //      integer-dot channel sums; otherwise runs of equal ids ----
         const int lead = __shfl_sync(0xffffffffu, (int)idx[0], 0);  // unconditional: every lane must reach the shuffle
+        const uint4 seg = d.wseg[tile * 8 + warp];  // (loaded here, not before the scoring loop: the kernel sits at its register cap)
         const bool warp_uniform = __all_sync(0xffffffffu, uniform && (int)idx[0] == lead) && seg.w == 256u;
         if (warp_uniform) {
             if (lane == 0) {
@@ -1683,8 +1686,8 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
         if (v) atomicAdd(&d.sums[i], (unsigned long long)v);
     }
     for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
-    if (lane == 0 && moved) atomicAdd(&d.sums[6 * k], moved);
-    if (tid == 0 && pairs_local) atomicAdd(&d.st->pairs, pairs_local);
+    if (lane == 0 && moved) atomicAdd(&d.sums[6 * k], (unsigned long long)moved);
+    if (tid == 0 && s_pairs) atomicAdd(&d.st->pairs, s_pairs);
     if (d.tlog && tid == 0) atomicMax(&d.tlog[d.tlog_slot + 1], km_now());  // the last CTA to finish
 }
 
@@ -2291,10 +2294,14 @@ static int km_open_impl(cniic_ctx *ctx, const cniic_kmeans_desc *desc, UniqueCol
     const size_t o_st = take(sizeof(KmState));
     const uint32_t super_x = D == 5 ? (desc->w + SW - 1) / SW : 0, super_y = D == 5 ? (desc->h_local + SH - 1) / SH : 0;
     const size_t o_gcpk = take(size_t(k) * 4), o_gcxy = take(size_t(k) * 4), o_gnrm = take(size_t(k) * 4), o_gent = take(size_t(k) * 16);
-    const size_t o_sclist = take(size_t(super_x) * super_y * k * 2), o_sccount = take(size_t(super_x) * super_y * 4 + 4);
+    // (per-supertile level-1 lists in global memory: only the first kernel version of the culled D = 5 path uses them)
+    const bool lists_in_global = D == 5 && getenv("CNIIC_XY_CULL_V1") != nullptr;
+    const size_t o_sclist = take(lists_in_global ? size_t(super_x) * super_y * k * 2 : 16), o_sccount = take(size_t(super_x) * super_y * 4 + 4);
     km->pool = cniic_cache_alloc(ctx, off);
     if (!km->pool) return fail(CNIIC_ERR_CUDA);
-    KM_TRY(cudaMemsetAsync(km->pool, 0, off, ctx->stream));
+    // everything behind the assignment array starts from zero; the array itself (2 bytes per point: megabytes) is written in full by
+    // km_init_assign before anything reads it (cniic_kmeans_reset)
+    KM_TRY(cudaMemsetAsync(static_cast<char *>(km->pool) + o_cpk, 0, off - o_cpk, ctx->stream));
     km->h_state = static_cast<KmState *>(cniic_pinned_get(ctx));
     if (!km->h_state) return fail(cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaMallocHost failed"));
     char *p = static_cast<char *>(km->pool);

@@ -859,7 +859,10 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
     extern __shared__ uint4 s_dyn4[];  // two raw tile stages (packed RGB rows of 192 bytes), then (MODE 2) the counter cube
     uint8_t *s_raw = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(s_dyn4) + 127) & ~uintptr_t(127));  // TMA destination: 128-byte aligned
     uint32_t *s_cube = reinterpret_cast<uint32_t *>(s_raw + 2 * HT_TILE_BYTES);
-    __shared__ __align__(16) uint32_t s_px[2][HT * HT_STRIDE];  // one word per pixel (r | g<<8 | b<<16), one buffer per stage
+    // one word per pixel (r | g<<8 | b<<16); one buffer per stage, except for the histogram stage, whose 58 KB counter cube would
+    // leave room for a single CTA per SM: there the buffer is shared and a second barrier per block protects it
+    constexpr int NPX = MODE == 2 ? 1 : 2;
+    __shared__ __align__(16) uint32_t s_px[NPX][HT * HT_STRIDE];
     __shared__ uint32_t s_prev[2];  // colour of the curve's last pixel before the block (it lies in another tile)
     __shared__ int s_top[2][5];
     __shared__ __align__(8) unsigned long long s_bar[2];
@@ -987,7 +990,7 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
             const uint4 *src = reinterpret_cast<const uint4 *>(s_raw + (size_t)stage * HT_TILE_BYTES + r * (HT * 3) + c16 * 3);
             const uint4 a = src[0], b = src[1], c = src[2];
             const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-            uint32_t *dst = s_px[stage] + r * HT_STRIDE + c16;
+            uint32_t *dst = s_px[stage % NPX] + r * HT_STRIDE + c16;
 #pragma unroll
             for (int q = 0; q < 4; q++) {  // 3 words -> 4 pixels
                 const uint32_t w0 = wd[3 * q], w1 = wd[3 * q + 1], w2 = wd[3 * q + 2];
@@ -1003,7 +1006,7 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
         for (int j = 0; j < 16; j++) {
             const int u = swapped ? HIL4_Y[j] : HIL4_X[j], v = swapped ? HIL4_X[j] : HIL4_Y[j];
             const int lx = (ax + sx * u) - X0, ly = (ay + sy * v) - Y0;
-            pix[j] = s_px[stage][ly * HT_STRIDE + lx];
+            pix[j] = s_px[stage % NPX][ly * HT_STRIDE + lx];
         }
         if (MODE == 0) {
             uint32_t wd[12];
@@ -1024,7 +1027,7 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
         uint32_t prev = prev0;
         if (tid > 0) {
             const int gx = bx + tx * (sw ? qy : qx), gy = by + ty * (sw ? qx : qy);
-            prev = s_px[stage][(gy - Y0) * HT_STRIDE + (gx - X0)];
+            prev = s_px[stage % NPX][(gy - Y0) * HT_STRIDE + (gx - X0)];
         }
         if (MODE == 1) {
             // 16-bit SIMD lanes: A = (r, b), G = (g, 0); per-lane wrap-around subtraction gives the i16 differences
@@ -1044,24 +1047,34 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
 #pragma unroll
             for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
         } else {
-            // near-zero symbols are counted in shared memory (ATOMS), the rest goes to the global bins directly
+            if (NPX == 1) __syncthreads();  // every thread has gathered its pixels: the shared pixel buffer may be refilled
+            // near-zero symbols are counted in shared memory (ATOMS), the rest goes to the global bins directly.  16-bit SIMD lanes
+            // A = (r, b), G = g as in the delta stage; one compare tells whether r and b differences lie inside the cube
+            uint32_t pa = prev & 0x00ff00ffu;
+            int pg = int((prev >> 8) & 0xffu);
 #pragma unroll
             for (int j = 0; j < 16; j++) {
-                const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
-                const int d0 = int(c & 0xff) - int(p & 0xff), d1 = int((c >> 8) & 0xff) - int((p >> 8) & 0xff),
-                          d2 = int((c >> 16) & 0xff) - int((p >> 16) & 0xff);
-                if ((unsigned)(d0 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d1 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d2 + CUBE_R) < (unsigned)CUBE_S) {
-                    const int ci = ((d0 + CUBE_R) * CUBE_S + (d1 + CUBE_R)) * CUBE_S + (d2 + CUBE_R);
+                const uint32_t ca = pix[j] & 0x00ff00ffu;
+                const int cg = int((pix[j] >> 8) & 0xffu);
+                const uint32_t da = __vsub2(ca, pa);                      // (dr, db) as wrapped i16 lanes
+                const int dg = cg - pg;
+                pa = ca; pg = cg;
+                const uint32_t ta = __vadd2(da, 0x00010001u * CUBE_R);    // (dr + R, db + R): in the cube iff each lane < S (unsigned)
+                const uint32_t tg = uint32_t(dg + CUBE_R);
+                if (__vcmpltu2(ta, 0x00010001u * CUBE_S) == 0xffffffffu && tg < (uint32_t)CUBE_S) {
+                    const uint32_t ci = ((ta & 0xffffu) * CUBE_S + tg) * CUBE_S + (ta >> 16);
                     const int sh = 16 * (ci & 1);
                     const uint32_t old = atomicAdd(&s_cube[ci >> 1], 1u << sh);
                     if (((old >> sh) & 0x7fffu) == 0x7fffu) {  // my increment set the guard bit: 2^15 counts leave the field
                         atomicSub(&s_cube[ci >> 1], 0x8000u << sh);
-                        const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                        const int d0 = int(ta & 0xffffu) - CUBE_R, d2 = int(ta >> 16) - CUBE_R;
+                        const uint32_t key = uint32_t(((d0 + 255) * 511 + (dg + 255)) * 511 + (d2 + 255));
                         atomicAdd(&bins[key], 32768u);
                         if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
                     }
                 } else {
-                    const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                    const int d0 = int(short(da & 0xffffu)), d2 = int(short(da >> 16));
+                    const uint32_t key = uint32_t(((d0 + 255) * 511 + (dg + 255)) * 511 + (d2 + 255));
                     atomicAdd(&bins[key], 1u);
                     if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
                 }

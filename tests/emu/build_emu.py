@@ -80,7 +80,7 @@ def rewrite_launches(text: str) -> str:
 
 ASM_RE = re.compile(r'asm\s*(?:volatile)?\s*\(\s*"([a-z0-9_.]+)\s+%0,\s*%1,\s*%2,\s*%3;"\s*:\s*"=r"\((\w+)\)\s*:\s*"r"\((\w+)\),\s*"r"\((\w+)\),\s*"r"\((\w+)\)\s*\)\s*;')
 # programmatic-dependent-launch control instructions have no effect when launches run one after another
-NOOP_ASM_RE = re.compile(r'asm\s*(?:volatile)?\s*\(\s*"griddepcontrol\.(?:wait|launch_dependents);"\s*:::\s*"memory"\s*\)\s*;')
+NOOP_ASM_RE = re.compile(r'asm\s*(?:volatile)?\s*\(\s*"(?:griddepcontrol\.(?:wait|launch_dependents);"\s*:::\s*"memory"|prefetch\.global\.L1 \[%0\];"\s*::\s*"l"\(\w+\))\s*\)\s*;')
 TIMER_ASM_RE = re.compile(r'asm\s*volatile\s*\(\s*"mov\.u64 %0, %%globaltimer;"\s*:\s*"=l"\((\w+)\)\s*\)\s*;')  # timeline instrumentation: no clock here
 SHARED_RE = re.compile(r"extern\s+__shared__\s+([\w:<> ]+?)\s+(\w+)\s*\[\s*\]\s*;")
 

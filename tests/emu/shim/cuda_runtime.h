@@ -289,6 +289,7 @@ static inline unsigned __vabsdiffu4(unsigned a, unsigned b) {
     return r;
 }
 static inline unsigned __vsub2(unsigned a, unsigned b) { return ((a - b) & 0xffffu) | (((a >> 16) - (b >> 16)) << 16); }
+static inline unsigned __vcmpltu2(unsigned a, unsigned b) { return ((a & 0xffffu) < (b & 0xffffu) ? 0xffffu : 0u) | ((a >> 16) < (b >> 16) ? 0xffff0000u : 0u); }
 static inline unsigned __vadd2(unsigned a, unsigned b) { return ((a + b) & 0xffffu) | (((a >> 16) + (b >> 16)) << 16); }
 static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
     for (int i = 0; i < 4; i++) c += ((a >> 8 * i) & 0xff) * ((b >> 8 * i) & 0xff);
