@@ -1424,7 +1424,7 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
     constexpr uint32_t STX = SW / TW, STY = SH / TH;
     const uint32_t per_cta = (tiles + gridDim.x - 1) / gridDim.x;
     const uint32_t t_begin = min(tiles, blockIdx.x * per_cta), t_end = min(tiles, t_begin + per_cta);
-    uint32_t cur_sup = 0xffffffffu, m = 0;
+    uint32_t cur_sup = 0xffffffffu;  // (the length of its list lives in s_box[5]: the kernel sits at its 80-register cap)
     for (uint32_t tile_seq = t_begin; tile_seq < t_end; tile_seq++) {
         uint32_t tx, ty, sup;
         {
@@ -1486,7 +1486,7 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
                 keep_mask &= keep_mask - 1;
                 s_list[pos++] = (uint16_t)(c_lo + b);
             }
-            m = placed;
+            if (tid == 0) s_box[5] = placed;
             cur_sup = sup;
         }
         const int x0 = tx * TW, yl0 = ty * TH;
@@ -1514,7 +1514,15 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
                 }
             }
         }
-        prefetch_l1(d.assign + lbase);  // the current cluster ids of my 8 pixels are read after the scoring loop
+        // current cluster of my 8 pixels: one 128-bit load (issued early, consumed after the scoring)
+        uint4 pv = make_uint4(0, 0, 0, 0);
+        if (nv == PX && fast_ok) pv = *reinterpret_cast<const uint4 *>(d.assign + lbase);
+        else {
+            uint32_t t[PX];
+#pragma unroll
+            for (int p = 0; p < PX; p++) t[p] = p < nv ? d.assign[lbase + p] : 0u;
+            pv = make_uint4(t[0] | (t[1] << 16), t[2] | (t[3] << 16), t[4] | (t[5] << 16), t[6] | (t[7] << 16));
+        }
         // ---- static colour bounding box of the tile and sums of my warp's 4 x 64 pixels (km_tile_boxes_xy2, once per session) ----
         const uint2 box = d.tile_box[tile];
         __syncthreads();  // previous tile is done with s_box / t_ent
@@ -1524,6 +1532,7 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
         const int r0 = box.x & 0xff, g0 = (box.x >> 8) & 0xff, b0 = (box.x >> 16) & 0xff;
         const int r1 = box.y & 0xff, g1 = (box.y >> 8) & 0xff, b1 = (box.y >> 16) & 0xff;
         const uint16_t *list = s_list;
+        const uint32_t m = s_box[5];  // (written before the two barriers above)
         // ---- pass 1: U = min_c UB_c over the supertile's list (the first 256 candidates stay in registers for pass 2) ----
         uint32_t umin = 0xffffffffu;
         uint4 ent0 = make_uint4(0, 0, 0, 0);
@@ -1586,15 +1595,6 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
             if (base + TCAP < m) __syncthreads();  // next round overwrites t_ent
         }
 
-        // current cluster of my 8 pixels: one 128-bit load (after the scoring loop: its four registers would otherwise spill there)
-        uint4 pv = make_uint4(0, 0, 0, 0);
-        if (nv == PX && fast_ok) pv = *reinterpret_cast<const uint4 *>(d.assign + lbase);
-        else {
-            uint32_t t[PX];
-#pragma unroll
-            for (int p = 0; p < PX; p++) t[p] = p < nv ? d.assign[lbase + p] : 0u;
-            pv = make_uint4(t[0] | (t[1] << 16), t[2] | (t[3] << 16), t[4] | (t[5] << 16), t[6] | (t[7] << 16));
-        }
         const uint32_t yg = yg0 + row;
         const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
         uint32_t idx[PX];
@@ -2561,9 +2561,11 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
     CU_TRY(ctx, cudaEventRecord(km->ev0, ctx->stream));
     uint32_t issued = 0;            // assign launches of this call (indexes the profiling events)
     uint32_t done_iters = 0;        // iterations completed by this call (state.iter - iter_seen)
-    // assign launches timed with CUDA events (cniic_kmeans_stats.assign_ms_avg): every one of the first PROF on a single GPU; only
-    // the first two of a sharded run, where an event between two 30 us kernels is a measurable share of the iteration
-    const uint32_t prof_limit = dist ? 2u : (uint32_t)cniic_kmeans::PROF;
+    // assign launches timed with CUDA events (cniic_kmeans_stats.assign_ms_avg).  An event between two kernels costs more than it
+    // looks: the next kernel cannot be launched ahead (programmatic dependent launch) across it -- ~6 us of gap per event on the
+    // device timeline (profiles/r02_timeline_c3_n8.txt, iterations 0 and 1).  So the launches are SAMPLED: every third one on a
+    // single GPU, iterations 2, 7, 12 ... of a sharded run (30 us kernels).
+    const uint32_t prof_every = dist ? 5u : 3u, prof_phase = dist ? 2u : 0u;
     uint32_t timed = 0;
     for (;;) {
         // kernels (and the all-reduce) exit at once when `done` or a halt is set, so a whole batch is enqueued without looking at
@@ -2572,10 +2574,10 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
         for (uint32_t b = 0; b < batch; b++) {
             km->dev.tlog = ctx->tlog;
             km->dev.tlog_slot = std::min<uint32_t>(issued, 63u) * 8;
-            const bool prof = issued < prof_limit;
-            if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * issued], ctx->stream));
+            const bool prof = issued % prof_every == prof_phase && timed < (uint32_t)cniic_kmeans::PROF;
+            if (prof) CU_TRY(ctx, cudaEventRecord(km->pev[2 * timed], ctx->stream));
             ST_TRY(km_launch_assign(km));
-            if (prof) { CU_TRY(ctx, cudaEventRecord(km->pev[2 * issued + 1], ctx->stream)); timed = issued + 1; }
+            if (prof) { CU_TRY(ctx, cudaEventRecord(km->pev[2 * timed + 1], ctx->stream)); timed++; }
             issued++;
             if (dist && !km->dev.p2p) ST_TRY(cniic_nccl_allreduce_u64(ctx, km->dev.sums, size_t(km->desc.k) * DW + 1));
             ST_TRY(km_launch_finalize(km, 0));
@@ -2621,8 +2623,11 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
         stats->converged = s.done;
         stats->gpu_launches = km->launches - launches0;
         stats->device_ms = ms;
-        // average duration of the fused assign+accumulate kernel over the launches that actually ran
-        const uint32_t np = std::min<uint32_t>(s.iter - km->iter_seen, timed);
+        // average duration of the fused assign+accumulate kernel over the sampled launches that actually ran (launches issued
+        // after convergence exit at once and would drag the mean down)
+        const uint32_t ran = s.iter - km->iter_seen;
+        uint32_t np = 0;
+        for (uint32_t i = prof_phase; i < ran && np < timed; i += prof_every) np++;
         float acc = 0.f;
         for (uint32_t i = 0; i < np; i++) {
             float t = 0.f;

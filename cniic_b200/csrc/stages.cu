@@ -859,9 +859,9 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
     extern __shared__ uint4 s_dyn4[];  // two raw tile stages (packed RGB rows of 192 bytes), then (MODE 2) the counter cube
     uint8_t *s_raw = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(s_dyn4) + 127) & ~uintptr_t(127));  // TMA destination: 128-byte aligned
     uint32_t *s_cube = reinterpret_cast<uint32_t *>(s_raw + 2 * HT_TILE_BYTES);
-    // one word per pixel (r | g<<8 | b<<16); one buffer per stage, except for the histogram stage, whose 58 KB counter cube would
-    // leave room for a single CTA per SM: there the buffer is shared and a second barrier per block protects it
-    constexpr int NPX = MODE == 2 ? 1 : 2;
+    // one word per pixel (r | g<<8 | b<<16).  ONE buffer: a second one (which would save the block's second barrier) costs a
+    // resident CTA per SM (59 KB instead of 42 KB), measured slower: 0.185 ms against 0.163 ms for the delta stage at 8192^2
+    constexpr int NPX = 1;
     __shared__ __align__(16) uint32_t s_px[NPX][HT * HT_STRIDE];
     __shared__ uint32_t s_prev[2];  // colour of the curve's last pixel before the block (it lies in another tile)
     __shared__ int s_top[2][5];
@@ -998,8 +998,8 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
                     make_uint4(w0 & 0xffffff, __byte_perm(w0, w1, 0x4543) & 0xffffff, __byte_perm(w1, w2, 0x4432) & 0xffffff, w2 >> 8);
             }
         }
-        // the one barrier of the block: s_px[stage] is complete (and s_prev[stage], s_top[stage] were written an iteration ago); the
-        // raw stage is free again, and s_px[stage ^ 1] -- which the next block expands into -- was last read before this point
+        // first barrier of the block: the pixel buffer is complete (s_prev[stage], s_top[stage] were written an iteration ago and
+        // read above); the raw stage is free again
         __syncthreads();
         uint32_t pix[16];
 #pragma unroll
@@ -1021,6 +1021,7 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
             o[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
             o[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
             o[2] = make_uint4(wd[8], wd[9], wd[10], wd[11]);
+            if (NPX == 1) __syncthreads();  // before the next block's expansion overwrites the pixel buffer
             continue;
         }
         // predecessor of this thread's first symbol: thread tid-1's last pixel, read from the tile at its precomputed position
@@ -1029,6 +1030,7 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
             const int gx = bx + tx * (sw ? qy : qx), gy = by + ty * (sw ? qx : qy);
             prev = s_px[stage % NPX][(gy - Y0) * HT_STRIDE + (gx - X0)];
         }
+        if (NPX == 1) __syncthreads();  // every thread has gathered its pixels: the pixel buffer may be refilled (second and last barrier)
         if (MODE == 1) {
             // 16-bit SIMD lanes: A = (r, b), G = (g, 0); per-lane wrap-around subtraction gives the i16 differences
             uint32_t wd[24];  // 48 i16 packed two per word
@@ -1047,7 +1049,6 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
 #pragma unroll
             for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
         } else {
-            if (NPX == 1) __syncthreads();  // every thread has gathered its pixels: the shared pixel buffer may be refilled
             // near-zero symbols are counted in shared memory (ATOMS), the rest goes to the global bins directly.  16-bit SIMD lanes
             // A = (r, b), G = g as in the delta stage; one compare tells whether r and b differences lie inside the cube
             uint32_t pa = prev & 0x00ff00ffu;

@@ -58,7 +58,7 @@ typedef struct {
     uint32_t converged;    /* 1 if the last pass moved nothing (kmeans.rs:25 loop exit)                          */
     uint32_t gpu_launches; /* kernels launched by this run                                                      */
     float device_ms;       /* CUDA-event time of the iteration loop (kernels + collective), H2D/D2H excluded    */
-    float assign_ms_avg;   /* mean CUDA-event duration of the fused assign+accumulate kernel (first 32 launches) */
+    float assign_ms_avg;   /* mean CUDA-event duration of the fused assign+accumulate kernel (sampled launches)       */
     uint64_t pairs_scored; /* point-centroid pairs actually scored since the last reset (N*k per iteration without culling) */
 } cniic_kmeans_stats;
 
