@@ -64,7 +64,7 @@ def run(args, workload, peaks, ClockSampler):
                 ctx.hist_delta_range_device(d_img, w, h, i0, i1)
         launches_per_step = None
         alg_bytes = (3 + 6 + 3) * w * h  # delta: 3 B/px read + 6 B/px written; fused histogram: 3 B/px read
-        kernel, kernel_bytes = "hilbert_tile_kernel<1> (delta)", 9 * (i1 - i0)
+        kernel, kernel_bytes = "hilbert_tile_tma_kernel<1> (delta)", 9 * (i1 - i0)
         pinned = torch.empty((h, w, 3), dtype=torch.uint8).pin_memory()
         host = pinned.numpy()
         ctx.d2h(host, d_img)
@@ -169,8 +169,14 @@ def run(args, workload, peaks, ClockSampler):
         ctx.sync()
         kt += a.elapsed_time(b) / 5
     ach = kernel_bytes / (kt * 1e-3) / 1e9
+    traffic = None  # dram bytes per launch of the committed ncu --set full capture of this kernel at this size (single GPU)
+    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")
+    if world == 1 and os.path.exists(tp) and not os.environ.get("CNIIC_STAGES_NO_TMA"):
+        ent = json.load(open(tp)).get(kernel)
+        if ent and ent.get("workload") == workload:
+            traffic = ent["bytes"]
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                "traffic": None, "launch_ms": kt, "algorithmic_bytes_per_launch": kernel_bytes, "peak_source": pk["source"],
+                "traffic": traffic, "launch_ms": kt, "algorithmic_bytes_per_launch": kernel_bytes, "peak_source": pk["source"],
                 "step_algorithmic_bytes": alg_bytes, "step_hbm_frac": alg_bytes * K / (tot * 1e-3) / 1e9 / pk["hbm_gbs"]}
     for _ in range(2):
         e2e_step()

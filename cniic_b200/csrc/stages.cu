@@ -859,11 +859,8 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
     extern __shared__ uint4 s_dyn4[];  // two raw tile stages (packed RGB rows of 192 bytes), then (MODE 2) the counter cube
     uint8_t *s_raw = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(s_dyn4) + 127) & ~uintptr_t(127));  // TMA destination: 128-byte aligned
     uint32_t *s_cube = reinterpret_cast<uint32_t *>(s_raw + 2 * HT_TILE_BYTES);
-    // one word per pixel (r | g<<8 | b<<16).  ONE buffer: a second one (which would save the block's second barrier) costs a
-    // resident CTA per SM (59 KB instead of 42 KB), measured slower: 0.185 ms against 0.163 ms for the delta stage at 8192^2
-    constexpr int NPX = 1;
-    __shared__ __align__(16) uint32_t s_px[NPX][HT * HT_STRIDE];
-    __shared__ uint32_t s_prev[2];  // colour of the curve's last pixel before the block (it lies in another tile)
+    __shared__ __align__(16) uint32_t s_px[HT * HT_STRIDE];  // one word per pixel (r | g<<8 | b<<16)
+    __shared__ uint32_t s_last[8];
     __shared__ int s_top[2][5];
     __shared__ __align__(8) unsigned long long s_bar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -899,33 +896,6 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
             t >>= 2;
         }
     }
-    // the symbol before a thread's first one is the LAST pixel of thread tid-1's cell: its block-local position is computed here, once
-    // (same fold with tid-1's digits), so no thread waits for another one's registers -- the block needs ONE barrier, not three
-    int qx = 0, qy = 0;
-    if (tid > 0) {
-        int pax = 0, pay = 0, psx = 1, psy = 1;
-        bool pswapped = false;
-        uint32_t t = (uint32_t)(tid - 1);
-#pragma unroll
-        for (int sl = 4; sl < HT; sl <<= 1) {
-            const uint32_t rx = 1u & (t >> 1), ry = 1u & (t ^ rx);
-            if (ry == 0) {
-                if (rx == 1) {
-                    const int nax = sl - 1 - pay, nsx = -psy, nay = sl - 1 - pax, nsy = -psx;
-                    pax = nax; psx = nsx; pay = nay; psy = nsy;
-                } else {
-                    const int q = pax, qs = psx;
-                    pax = pay; psx = psy; pay = q; psy = qs;
-                }
-                pswapped = !pswapped;
-            }
-            pax += sl * (int)rx;
-            pay += sl * (int)ry;
-            t >>= 2;
-        }
-        qx = pax + psx * (pswapped ? HIL4_Y[15] : HIL4_X[15]);
-        qy = pay + psy * (pswapped ? HIL4_X[15] : HIL4_Y[15]);
-    }
     __syncthreads();
     // thread 0: fold the levels above the block (6..L-1) into an affine map of the 64x64 block, request the block's pixels
     auto issue = [&](unsigned long long blk, int stage) {
@@ -952,21 +922,8 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
         mbar_arrive_expect_tx(&s_bar[stage], HT_TILE_BYTES);
         tma_load_2d(s_raw + (size_t)stage * HT_TILE_BYTES, &tmap, (bx & ~(HT - 1)) * 3, by & ~(HT - 1), &s_bar[stage]);
     };
-    // thread 32: colour of the pixel before a block (one dependent global load), fetched one block ahead like the tile itself
-    auto fetch_prev = [&](unsigned long long blk, int stage) {
-        uint32_t v = 0;  // hilbertc.rs:445 START = [0;3]
-        if (blk > 0) {
-            uint32_t px, py;
-            hilbert_d2xy_pow2(n, blk * 4096 - 1, &px, &py);
-            const uint8_t *q = rgb + ((size_t)py * n + px) * 3;
-            v = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
-        }
-        s_prev[stage] = v;
-    };
     const unsigned long long first = blk_begin + blockIdx.x;
     if (tid == 0 && first < nblocks) issue(first, 0);
-    if (MODE != 0 && tid == 32 && first < nblocks) fetch_prev(first, 0);
-    __syncthreads();  // s_prev[0] (later ones are ordered by the per-block barrier; s_top travels with the mbarrier)
     uint32_t it = 0;
     for (unsigned long long blk = first; blk < nblocks; blk += gridDim.x, it++) {
         const int stage = it & 1;
@@ -974,23 +931,22 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
         const unsigned long long i0 = B + (unsigned long long)tid * 16;
         // the other stage was consumed before the barrier that ended the previous iteration's expansion: refill it now
         if (tid == 0 && blk + gridDim.x < nblocks) issue(blk + gridDim.x, stage ^ 1);
-        if (MODE != 0 && tid == 32 && blk + gridDim.x < nblocks) fetch_prev(blk + gridDim.x, stage ^ 1);
         mbar_wait(&s_bar[stage], (it >> 1) & 1);
-        // everything thread 0 / thread 32 wrote for this stage an iteration ago is read HERE, before the block's barrier: after it
-        // those threads may already be refilling the other stage's slots for the block after the next
-        const int bx = s_top[stage][0], tx = s_top[stage][1], by = s_top[stage][2], ty = s_top[stage][3], sw = s_top[stage][4];
-        const uint32_t prev0 = s_prev[stage];
-        // compose: (x, y) = top(local(u, v)); x = bx + tx * (sw ? yl : xl), y = by + ty * (sw ? xl : yl)
-        const int ax = bx + tx * (sw ? lay : lax), sx = tx * (sw ? lsy : lsx);
-        const int ay = by + ty * (sw ? lax : lay), sy = ty * (sw ? lsx : lsy);
-        const bool swapped = lswapped != (sw != 0);
+        int ax, ay, sx, sy;
+        bool swapped;
+        {   // compose: (x, y) = top(local(u, v)); x = bx + tx * (sw ? yl : xl), y = by + ty * (sw ? xl : yl)
+            const int bx = s_top[stage][0], tx = s_top[stage][1], by = s_top[stage][2], ty = s_top[stage][3], sw = s_top[stage][4];
+            ax = bx + tx * (sw ? lay : lax); sx = tx * (sw ? lsy : lsx);
+            ay = by + ty * (sw ? lax : lay); sy = ty * (sw ? lsx : lsy);
+            swapped = lswapped != (sw != 0);
+        }
         const int X0 = ax & ~(HT - 1), Y0 = ay & ~(HT - 1);  // (every coordinate of the block shares the bits above the low six)
         {   // expand the landed tile to one 32-bit word per pixel: thread t takes 16 pixels (three 128-bit words) of row t/4
             const int r = tid >> 2, c16 = (tid & 3) * 16;
             const uint4 *src = reinterpret_cast<const uint4 *>(s_raw + (size_t)stage * HT_TILE_BYTES + r * (HT * 3) + c16 * 3);
             const uint4 a = src[0], b = src[1], c = src[2];
             const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-            uint32_t *dst = s_px[stage % NPX] + r * HT_STRIDE + c16;
+            uint32_t *dst = s_px + r * HT_STRIDE + c16;
 #pragma unroll
             for (int q = 0; q < 4; q++) {  // 3 words -> 4 pixels
                 const uint32_t w0 = wd[3 * q], w1 = wd[3 * q + 1], w2 = wd[3 * q + 2];
@@ -998,15 +954,13 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
                     make_uint4(w0 & 0xffffff, __byte_perm(w0, w1, 0x4543) & 0xffffff, __byte_perm(w1, w2, 0x4432) & 0xffffff, w2 >> 8);
             }
         }
-        // first barrier of the block: the pixel buffer is complete (s_prev[stage], s_top[stage] were written an iteration ago and
-        // read above); the raw stage is free again
-        __syncthreads();
+        __syncthreads();  // s_px complete; the raw stage is free again
         uint32_t pix[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             const int u = swapped ? HIL4_Y[j] : HIL4_X[j], v = swapped ? HIL4_X[j] : HIL4_Y[j];
             const int lx = (ax + sx * u) - X0, ly = (ay + sy * v) - Y0;
-            pix[j] = s_px[stage % NPX][ly * HT_STRIDE + lx];
+            pix[j] = s_px[ly * HT_STRIDE + lx];
         }
         if (MODE == 0) {
             uint32_t wd[12];
@@ -1021,16 +975,23 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
             o[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
             o[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
             o[2] = make_uint4(wd[8], wd[9], wd[10], wd[11]);
-            if (NPX == 1) __syncthreads();  // before the next block's expansion overwrites the pixel buffer
+            __syncthreads();  // before the next block's expansion overwrites s_px
             continue;
         }
-        // predecessor of this thread's first symbol: thread tid-1's last pixel, read from the tile at its precomputed position
-        uint32_t prev = prev0;
-        if (tid > 0) {
-            const int gx = bx + tx * (sw ? qy : qx), gy = by + ty * (sw ? qx : qy);
-            prev = s_px[stage % NPX][(gy - Y0) * HT_STRIDE + (gx - X0)];
+        // predecessor of this thread's first symbol
+        uint32_t prev = __shfl_up_sync(0xffffffffu, pix[15], 1);
+        if (lane == 31) s_last[warp] = pix[15];
+        __syncthreads();  // s_last complete; every thread has gathered its pixels, so s_px may be overwritten after this point
+        if (lane == 0) {
+            if (warp > 0) prev = s_last[warp - 1];
+            else if (B == 0) prev = 0;  // hilbertc.rs:445 START = [0;3]
+            else {
+                uint32_t px, py;
+                hilbert_d2xy_pow2(n, B - 1, &px, &py);
+                const uint8_t *q = rgb + ((size_t)py * n + px) * 3;
+                prev = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+            }
         }
-        if (NPX == 1) __syncthreads();  // every thread has gathered its pixels: the pixel buffer may be refilled (second and last barrier)
         if (MODE == 1) {
             // 16-bit SIMD lanes: A = (r, b), G = (g, 0); per-lane wrap-around subtraction gives the i16 differences
             uint32_t wd[24];  // 48 i16 packed two per word
@@ -1049,33 +1010,24 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
 #pragma unroll
             for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
         } else {
-            // near-zero symbols are counted in shared memory (ATOMS), the rest goes to the global bins directly.  16-bit SIMD lanes
-            // A = (r, b), G = g as in the delta stage; one compare tells whether r and b differences lie inside the cube
-            uint32_t pa = prev & 0x00ff00ffu;
-            int pg = int((prev >> 8) & 0xffu);
+            // near-zero symbols are counted in shared memory (ATOMS), the rest goes to the global bins directly
 #pragma unroll
             for (int j = 0; j < 16; j++) {
-                const uint32_t ca = pix[j] & 0x00ff00ffu;
-                const int cg = int((pix[j] >> 8) & 0xffu);
-                const uint32_t da = __vsub2(ca, pa);                      // (dr, db) as wrapped i16 lanes
-                const int dg = cg - pg;
-                pa = ca; pg = cg;
-                const uint32_t ta = __vadd2(da, 0x00010001u * CUBE_R);    // (dr + R, db + R): in the cube iff each lane < S (unsigned)
-                const uint32_t tg = uint32_t(dg + CUBE_R);
-                if (__vcmpltu2(ta, 0x00010001u * CUBE_S) == 0xffffffffu && tg < (uint32_t)CUBE_S) {
-                    const uint32_t ci = ((ta & 0xffffu) * CUBE_S + tg) * CUBE_S + (ta >> 16);
+                const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
+                const int d0 = int(c & 0xff) - int(p & 0xff), d1 = int((c >> 8) & 0xff) - int((p >> 8) & 0xff),
+                          d2 = int((c >> 16) & 0xff) - int((p >> 16) & 0xff);
+                if ((unsigned)(d0 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d1 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d2 + CUBE_R) < (unsigned)CUBE_S) {
+                    const int ci = ((d0 + CUBE_R) * CUBE_S + (d1 + CUBE_R)) * CUBE_S + (d2 + CUBE_R);
                     const int sh = 16 * (ci & 1);
                     const uint32_t old = atomicAdd(&s_cube[ci >> 1], 1u << sh);
                     if (((old >> sh) & 0x7fffu) == 0x7fffu) {  // my increment set the guard bit: 2^15 counts leave the field
                         atomicSub(&s_cube[ci >> 1], 0x8000u << sh);
-                        const int d0 = int(ta & 0xffffu) - CUBE_R, d2 = int(ta >> 16) - CUBE_R;
-                        const uint32_t key = uint32_t(((d0 + 255) * 511 + (dg + 255)) * 511 + (d2 + 255));
+                        const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
                         atomicAdd(&bins[key], 32768u);
                         if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
                     }
                 } else {
-                    const int d0 = int(short(da & 0xffffu)), d2 = int(short(da >> 16));
-                    const uint32_t key = uint32_t(((d0 + 255) * 511 + (dg + 255)) * 511 + (d2 + 255));
+                    const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
                     atomicAdd(&bins[key], 1u);
                     if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
                 }
