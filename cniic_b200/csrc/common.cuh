@@ -37,6 +37,8 @@ struct cniic_ctx {
     unsigned long long **p2p_peer_table = nullptr;  // device array [world]
     std::vector<void *> p2p_opened;
     bool p2p_ready = false;
+    size_t xy_cull_smem = 0;  // dynamic shared memory the culled D = 5 kernels were last configured for on this context, and their
+    int xy_cull_per_sm = 0;   // resident CTAs per SM at that size (cached: a session would otherwise repeat three driver calls)
     unsigned long long *tlog = nullptr;  // CNIIC_TLOG=1: device timeline buffer of the Lloyd loop (64 iterations x 8 timestamps)
     std::vector<uint8_t> pending_stream;  // cniic_codec_encode result that did not fit the caller's buffer (cniic_codec_encode_fetch)
     bool has_pending_stream = false;

@@ -20,6 +20,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -2403,8 +2404,18 @@ static int km_open_impl(cniic_ctx *ctx, const cniic_kmeans_desc *desc, UniqueCol
     // shared memory + persistent grid
     if (D == 5 && km->cull) {
         km->smem = size_t(TCAP) * 16 + size_t(k) * 24 + size_t((k + 7) & ~7u) * 2 + 16;  // survivors, accumulators, level-1 list (v2)
-        KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb_cull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
-        KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb_cull2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+        {   // the attribute belongs to the function, not to a context: only ever RAISE it (sessions with different k may be alive on
+            // other contexts / threads), and skip the two driver calls when it is already large enough
+            static std::mutex mu;
+            static size_t raised_to[16] = {};  // per device
+            std::lock_guard<std::mutex> lock(mu);
+            size_t &cur = raised_to[ctx->device & 15];
+            if (km->smem > cur) {
+                KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb_cull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+                KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb_cull2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
+                cur = km->smem;
+            }
+        }
     } else if (D == 5) {
         km->smem = size_t(KP) * 16 + 8 * 192 * 4 + size_t(k) * 24 + KP * 2 + k * 2 + 16;
         KM_TRY(cudaFuncSetAttribute(km_assign_xyrgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
@@ -2422,7 +2433,12 @@ static int km_open_impl(cniic_ctx *ctx, const cniic_kmeans_desc *desc, UniqueCol
         else KM_TRY(cudaFuncSetAttribute(km_assign_rgb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km->smem));
     }
     int per_sm = 0;
-    if (D == 5 && km->cull && km->v2) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull2, THREADS, km->smem));
+    if (D == 5 && km->cull && km->v2 && ctx->xy_cull_smem == km->smem && ctx->xy_cull_per_sm > 0) per_sm = ctx->xy_cull_per_sm;
+    else if (D == 5 && km->cull && km->v2) {
+        KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull2, THREADS, km->smem));
+        ctx->xy_cull_smem = km->smem;
+        ctx->xy_cull_per_sm = per_sm;
+    }
     else if (D == 5 && km->cull) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb_cull, THREADS, km->smem));
     else if (D == 5) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_xyrgb, THREADS, km->smem));
     else if (km->cull && km->v2 && d_wts) KM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_assign_rgb_cull2<true>, THREADS, km->smem));
@@ -2564,8 +2580,8 @@ extern "C" int cniic_kmeans_run(cniic_kmeans *km, uint32_t max_iters, cniic_kmea
     // assign launches timed with CUDA events (cniic_kmeans_stats.assign_ms_avg).  An event between two kernels costs more than it
     // looks: the next kernel cannot be launched ahead (programmatic dependent launch) across it -- ~6 us of gap per event on the
     // device timeline (profiles/r02_timeline_c3_n8.txt, iterations 0 and 1).  So the launches are SAMPLED: every third one on a
-    // single GPU, iterations 2, 7, 12 ... of a sharded run (30 us kernels).
-    const uint32_t prof_every = dist ? 5u : 3u, prof_phase = dist ? 2u : 0u;
+    // single GPU, iterations 2, 10, 18 ... of a sharded run (30 us kernels).
+    const uint32_t prof_every = dist ? 8u : 3u, prof_phase = dist ? 2u : 0u;
     uint32_t timed = 0;
     for (;;) {
         // kernels (and the all-reduce) exit at once when `done` or a halt is set, so a whole batch is enqueued without looking at
@@ -2708,6 +2724,9 @@ int km_batch_plan(cniic_kmeans *const *ss, uint32_t count, BatchPlan *bp) {
     if (per_sm < 1) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "k = %u needs %zu bytes of shared memory", bp->k, bp->smem);
     const unsigned long long resident = (unsigned long long)per_sm * ctx->sm_count;
     bp->gx_assign = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(max_tiles, (resident + count - 1) / count));
+    // the unweighted D = 3 kernels accumulate channel sums in 32-bit shared counters per CTA (255 x points < 2^32): never let one CTA
+    // own more than 4096 tiles = 8.4 M points of a problem, however many problems share the resident grid
+    bp->gx_assign = (unsigned)std::max<unsigned long long>(bp->gx_assign, std::min<unsigned long long>(max_tiles, (max_tiles + 4095) / 4096));
     bp->gx_init = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((max_n + 255) / 256, ((unsigned long long)ctx->sm_count * 8 + count - 1) / count));
     bp->gx_super = max_super;
     if (count > 65535) return cniic_set_error(ctx, CNIIC_ERR_BAD_ARG, "at most 65535 problems per batch (gridDim.y)");
