@@ -70,10 +70,11 @@ int cniic_ctx_create(int device, cniic_ctx **out);
  * (cniic_nccl_unique_id) and distributed by the host (torch.distributed store / MPI / file).                   */
 int cniic_ctx_create_dist(int device, int rank, int world, const uint8_t nccl_unique_id[128], cniic_ctx **out);
 int cniic_nccl_unique_id(uint8_t out_id[128]);
-/* Peer-memory all-reduce (replaces the per-iteration NCCL call of the row-sharded Lloyd loop; cniic_b200/dist.py enables it by
- * default, without it the library calls ncclAllReduce): every rank exports
- * a CUDA IPC handle of its exchange region, the host gathers the world x 64 bytes, every rank connects.  The finalize kernel
- * then reads all ranks' partial sums over NVLink and reduces them in rank order.            */
+/* Peer-memory exchange (replaces the per-iteration NCCL call of the row-sharded Lloyd loop; cniic_b200/dist.py enables it by
+ * default, without it the library calls ncclAllReduce): every rank exports a CUDA IPC handle of its exchange region, the host
+ * gathers the world x 64 bytes, every rank connects.  The update kernel of every rank then PUSHES its partial sums into all
+ * ranks' receive areas over NVLink as self-validating 16-byte cells and adds what it received in rank order (DESIGN.md
+ * section 6).  Call both on every rank, in the same order, before the first session.                                     */
 int cniic_ctx_p2p_export(cniic_ctx *ctx, uint8_t out_handle[64]);
 int cniic_ctx_p2p_connect(cniic_ctx *ctx, const uint8_t *handles /* world x 64 bytes, rank order */);
 void cniic_ctx_destroy(cniic_ctx *ctx);
@@ -190,7 +191,10 @@ int cniic_voronoi_fill(cniic_ctx *ctx, const uint32_t *cxy, const uint8_t *crgb,
 
 /* ---- Hilbert / delta / histograms (hilbert.rs:34-43, hilbertc.rs:402-477, utils.rs:4-16) ------------------
  * The curve of the reference comes from the un-vendored crate zhang_hilbert 0.1.1 (PARITY UNPINNED);
- * this library and the oracle implement the same generalized Hilbert scan (classic Hilbert curve on 2^n squares). */
+ * this library and the oracle implement the same generalized Hilbert scan (classic Hilbert curve on 2^n squares), which is
+ * NOT known to equal Zhang's block scan.  Everything built on the curve -- cniic_hilbert_xy, the delta stream, the "delta" and
+ * "hilbert(rle)" codecs -- is therefore self-consistent (encode -> decode round-trips) but not guaranteed to interchange
+ * with the reference's CPU codecs until tools/pin_hilbert.sh has compared the two curves on a box with cargo.                */
 int cniic_hilbert_xy(cniic_ctx *ctx, uint32_t w, uint32_t h, uint32_t *out_xy /* 2*w*h */);
 int cniic_hilbert_gather_rgb(cniic_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, uint8_t *out_rgb /* 3*w*h */);
 /* DiffStream: out[i] = rgb(H(i)) - rgb(H(i-1)) per channel as i16, rgb(H(-1)) = 0.                               */
@@ -206,8 +210,9 @@ int cniic_sse_rgb(cniic_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n_p
 
 /* ---- whole codecs (codec.rs:14-19 Codec::encode / Codec::decode) -------------------------------------------
  * codec = the reference's own expression strings: "cluster-colors(N)", "voronoi(N)", "delta", "hufman",
- * "hilbert(rle)".  Streams follow ser.rs / huf.rs / bit.rs byte for byte (wire formats), with the
- * deterministic Huffman tie rule: leaves enter in ascending symbol order, heap ordered by (freq, creation seq).
+ * "hilbert(rle)".  Containers, tries and payloads follow ser.rs / huf.rs / bit.rs byte for byte (wire formats), with
+ * the deterministic Huffman tie rule: leaves enter in ascending symbol order, heap ordered by (freq, creation seq).  The ORDER
+ * of the symbols of "delta" and "hilbert(rle)" is the Hilbert order of this library (see the caveat above).
  * encode: returns CNIIC_ERR_BUFFER_TOO_SMALL with *out_len = required size when cap is too small.               */
 int cniic_codec_encode(cniic_ctx *ctx, const char *codec, const uint8_t *rgb, uint32_t w, uint32_t h, uint8_t *out,
                        size_t cap, size_t *out_len);

@@ -254,3 +254,30 @@ def test_rust_build_compiles_every_cu_file():
     assert "impl Codec for Gpu" in gpuc and "impl FromStr for Gpu" in gpuc
     for used in re.findall(r"\b(cniic_[a-z0-9_]+)\(", lib):
         assert used in _lib.declared_symbols(), used
+
+
+def test_oracle_side_image_generator_equals_the_library_generator():
+    """oracle/synth.py (numpy) exists so that bench.py's CPU legs never load the product; it must produce the very bytes of
+    cniic_synth_image_host, shards included."""
+    from oracle import synth
+    for (w, h, seed, nb, y0, ht) in [(96, 64, 42, 12, 0, None), (96, 24, 42, 12, 40, 64), (513, 37, 0xC0FFEE + 2, 192, 0, None),
+                                     (7680, 6, 0xC0FFEE + 3, 2048, 1000, 4320), (33, 7, 5, 0, 0, None), (8, 8, 1, 1000, 0, None)]:
+        assert np.array_equal(synth.synth_image(w, h, seed, nb, y0, ht), cb.synth_image_host(w, h, seed, nb, y0, ht)), (w, h, seed)
+
+
+def test_reference_arm_does_not_touch_the_product():
+    """`bench.py --impl reference` imported cniic_b200 (and so mapped the product .so) just to build its image."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    cpu_side = {"reference_arm", "cpu_reference_leg", "workload_image", "cpu_sample_plan"}
+    seen = set()
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in cpu_side:
+            seen.add(node.name)
+            src = ast.dump(node)
+            assert "cniic_b200" not in src and "'cb'" not in src, node.name
+    assert seen == cpu_side
+    # ... and nothing at module level imports it either (the GPU arm imports it inside gpu_arm / main)
+    for node in tree.body:
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            assert "cniic_b200" not in ast.dump(node)
