@@ -1429,15 +1429,19 @@ __device__ __forceinline__ void km_assign_xyrgb_cull2_body(const KmDev d) {
     for (uint32_t tile_seq = t_begin; tile_seq < t_end; tile_seq++) {
         uint32_t tx, ty, sup;
         {
+            // (a runtime integer division costs ~25 instructions and every thread decodes every tile: 7 % of the kernel's
+            // instructions went here in profiles/r02_ncu_full_final_c3.txt -- full supertiles, all but the last row / column, shift)
+            static_assert(STX == 8 && STY == 8, "the decode below shifts by 3 and 6");
             const uint32_t row_tiles = tiles_x * STY;                       // tiles of a full row of supertiles
             const uint32_t sy = tile_seq / row_tiles;
             const uint32_t rem = tile_seq - sy * row_tiles;
             const uint32_t rows_in = min(STY, tiles_y - sy * STY);
-            const uint32_t sx = rem / (STX * rows_in);
+            const uint32_t sx = rows_in == STY ? rem >> 6 : rem / (STX * rows_in);
             const uint32_t rem2 = rem - sx * STX * rows_in;
             const uint32_t cols_in = min(STX, tiles_x - sx * STX);
-            tx = sx * STX + rem2 % cols_in;
-            ty = sy * STY + rem2 / cols_in;
+            const uint32_t ly = cols_in == STX ? rem2 >> 3 : rem2 / cols_in;
+            tx = sx * STX + (rem2 - ly * cols_in);
+            ty = sy * STY + ly;
             sup = sy * d.super_x + sx;
         }
         const uint32_t tile = ty * tiles_x + tx;  // raster index (static per-tile tables)

@@ -64,13 +64,15 @@ __global__ void __launch_bounds__(256, 4) fill_kernel(const uint32_t *__restrict
     for (uint32_t tile_seq = t_begin; tile_seq < t_end; tile_seq++) {
         uint32_t tx, ty, sup;
         {   // supertile-major enumeration of the tiles
+            static_assert(STX == 8 && STY == 4, "the decode below shifts by 3 and 5");  // (runtime divisions only in edge supertiles)
             const uint32_t row_tiles = tiles_x * STY;
             const uint32_t sy = tile_seq / row_tiles, rem = tile_seq - sy * row_tiles;
             const uint32_t rows_in = min(STY, tiles_y - sy * STY);
-            const uint32_t sx = rem / (STX * rows_in), rem2 = rem - sx * STX * rows_in;
+            const uint32_t sx = rows_in == STY ? rem >> 5 : rem / (STX * rows_in), rem2 = rem - sx * STX * rows_in;
             const uint32_t cols_in = min(STX, tiles_x - sx * STX);
-            tx = sx * STX + rem2 % cols_in;
-            ty = sy * STY + rem2 / cols_in;
+            const uint32_t ly = cols_in == STX ? rem2 >> 3 : rem2 / cols_in;
+            tx = sx * STX + (rem2 - ly * cols_in);
+            ty = sy * STY + ly;
             sup = sy * super_x + sx;
         }
         if (sup != cur_sup) {  // ---- level 1 ----

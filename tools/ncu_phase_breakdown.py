@@ -21,16 +21,18 @@ def main():
     rep, obj, frag = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
     # NCU_FILTER (optional), e.g. "-k regex:km_assign_rgb_cull2 -s 1": selects ONE launch of a report that holds several
-    page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "-c", "1"] + os.environ.get("NCU_FILTER", "").split(),
+    page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"] + os.environ.get("NCU_FILTER", "").split(),
                           capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(page)))
     hdr = rows[1]
     i_s, i_i = hdr.index("# Samples"), hdr.index("Instructions Executed")
-    body = rows[2:]
-    for j, r in enumerate(body):  # a report with several launches repeats the two header rows: keep the first launch
-        if r and r[0] == "Kernel Name":
-            body = body[:j]
-            break
+    # a report with several launches repeats the two header rows per launch: take the first launch whose kernel name contains
+    # NCU_KERNEL (default: the first launch)
+    want = os.environ.get("NCU_KERNEL", "")
+    starts = [j for j, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    pick = next((j for j in starts if want in " ".join(rows[j][1:])), starts[0])
+    nxt = next((j for j in starts if j > pick), len(rows))
+    body = rows[pick + 2:nxt]
     prof = [(r[1].strip(), int(r[i_s]), int(r[i_i])) for r in body if len(r) > i_i]
     with tempfile.TemporaryDirectory() as td:
         subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=td, stdout=subprocess.DEVNULL)
