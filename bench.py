@@ -283,11 +283,9 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
             st.iterations = max(x.iterations for x in sts)
             st.pairs_scored = sum(x.pairs_scored for x in sts)
             return st
-        sess = cb.KMeansSession(sctx, kind_id, k, d_img_s, n_local, flags=flags, **skw)
-        sess.reset(init)
-        st = sess.run(iters)
-        sess.close()
-        return st
+        # one C call = kmeans::cluster on this rank's points (open + reset + run + close; nothing is read back inside `value`)
+        return cb.kmeans_cluster(sctx, kind_id, k, d_img_s, n_local, max_iters=iters, init_centroids=init, flags=flags,
+                                 want_centroids=False, **skw)[3]
 
     for _ in range(W):
         one_step()
@@ -352,14 +350,9 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
     else:
         # sharded session: per step the shard is re-uploaded from pinned host memory and centroids/weights read back
         def e2e_step():
-            s2 = cb.KMeansSession(sctx, kind_id, k, host_img, n_local, n_total=n_total, first_index=y0 * w, w=w, h_local=h_local,
-                                  y0=y0, on_device=False)
-            s2.reset(init)
-            s2.run(ITERS)
-            out = s2.get(want_assign=False)
-            s2.close()
-            return out
-        api_name = "cniic_kmeans_open/reset/run/get (row-sharded session, host points)"
+            return cb.kmeans_cluster(sctx, kind_id, k, host_img, n_local, max_iters=ITERS, init_centroids=init, n_total=n_total,
+                                     first_index=y0 * w, w=w, h_local=h_local, y0=y0, on_device=False, want_centroids=True)
+        api_name = "cniic_kmeans_cluster (row-sharded, host points in, centroids + weights out)"
         d2h_bytes = int(k * D * 4 + k * 8)
     for _ in range(2):
         e2e_step()

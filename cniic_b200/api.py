@@ -443,6 +443,34 @@ class KMeansSession:
             pass
 
 
+def kmeans_cluster(ctx: Context, kind: int, k: int, rgb, n_local: int, max_iters: int = 0, init_centroids=None, n_total: int | None = None,
+                   first_index: int = 0, w: int = 0, h_local: int = 0, y0: int = 0, tie: int = L.TIE_KEEP_CURRENT, on_device: bool = False,
+                   flags: int = 0, want_centroids: bool = True, want_assign: bool = False):
+    """cniic_kmeans_cluster: kmeans::cluster on the described points in one C call (open + reset + run + get + close).
+    Returns (centroids (k, D) int64 or None, weights or None, assign or None, stats)."""
+    D = 5 if kind == L.POINTS_XYRGB else 3
+    d = L.KMeansDesc()
+    d.kind, d.k, d.tie_rule = kind, k, tie
+    d.n_local = n_local
+    d.n_total = n_local if n_total is None else n_total
+    d.first_index, d.w, d.h_local, d.y0 = first_index, w, h_local, y0
+    keep = None
+    if on_device:
+        d.rgb = int(rgb)
+    else:
+        keep = _u8(rgb)
+        d.rgb = keep.ctypes.data
+    d.points_on_device = 1 if on_device else 0
+    d.flags = flags
+    ic = None if init_centroids is None else np.ascontiguousarray(init_centroids, dtype=np.int32)
+    cen = np.zeros((k, D), np.int32) if want_centroids else None
+    wts = np.zeros(k, np.uint64) if want_centroids else None
+    asg = np.zeros(n_local, np.uint16) if want_assign else None
+    st = L.KMeansStats()
+    ctx.check(ctx._lib.cniic_kmeans_cluster(ctx.h, C.byref(d), _ptr(ic), C.c_uint32(max_iters), _ptr(cen), _ptr(wts), _ptr(asg), C.byref(st)))
+    return (None if cen is None else cen.astype(np.int64)), wts, asg, st
+
+
 def kmeans_reset_batch(sessions):
     """cniic_kmeans_reset_batch: chunked init of every session, one launch per stage for the whole batch."""
     ctx = sessions[0].ctx

@@ -3049,6 +3049,20 @@ static int km_oneshot(cniic_ctx *ctx, const cniic_kmeans_desc &desc, uint32_t ma
     return check_active(ctx, wts.data(), desc.k, desc.n_total);
 }
 
+// kmeans::cluster (kmeans.rs:21-39) on the points `desc` describes, in ONE call: open + reset + run + get + close.  This is the
+// call a Rust binding makes per image (or per shard of a row-sharded image: every rank passes the same initial centroids); four
+// separate calls cost a binding four FFI crossings and, on a 0.7 ms sharded step, measurable host time between them.
+extern "C" int cniic_kmeans_cluster(cniic_ctx *ctx, const cniic_kmeans_desc *desc, const int32_t *host_init_centroids, uint32_t max_iters,
+                                    int32_t *out_centroids, uint64_t *out_weight, uint16_t *out_assign, cniic_kmeans_stats *stats) {
+    cniic_kmeans *km = nullptr;
+    ST_TRY(cniic_kmeans_open(ctx, desc, &km));
+    int rc = cniic_kmeans_reset(km, host_init_centroids);
+    if (rc == CNIIC_OK) rc = cniic_kmeans_run(km, max_iters, stats);
+    if (rc == CNIIC_OK && (out_centroids || out_weight || out_assign)) rc = cniic_kmeans_get(km, out_centroids, out_weight, out_assign);
+    cniic_kmeans_close(km);
+    return rc;
+}
+
 extern "C" int cniic_kmeans_rgb(cniic_ctx *ctx, const uint8_t *rgb, const uint32_t *counts, size_t n, uint32_t k, uint32_t max_iters,
                                 int tie_rule, uint8_t *out_centroids, uint64_t *out_weight, uint16_t *out_assign,
                                 cniic_kmeans_stats *stats) {

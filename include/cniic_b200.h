@@ -131,6 +131,11 @@ typedef struct {
     int flags;               /* CNIIC_KMEANS_* bits                                                              */
 } cniic_kmeans_desc;
 
+/* kmeans::cluster (kmeans.rs:21-39) on the points of `desc` in one call = open + reset(host_init_centroids) + run(max_iters) +
+ * get (outputs nullable: k x D int32 centroids, k x u64 weights, n_local x u16 assignment) + close.  Single GPU or one rank of a
+ * row-sharded image (then collective: every rank calls it with the same initial centroids).                              */
+int cniic_kmeans_cluster(cniic_ctx *ctx, const cniic_kmeans_desc *desc, const int32_t *host_init_centroids, uint32_t max_iters,
+                         int32_t *out_centroids, uint64_t *out_weight, uint16_t *out_assign, cniic_kmeans_stats *stats);
 int cniic_kmeans_open(cniic_ctx *ctx, const cniic_kmeans_desc *desc, cniic_kmeans **out);
 /* (Re)start from the reference's chunked init.  Single GPU: gathered on the device.  Multi-GPU: every rank must
  * pass the same k x D int32 initial centroids (host) computed from the global point list (kmeans.rs:101-108).    */

@@ -677,3 +677,16 @@ def test_kmeans_xyrgb_batch_equals_separate_runs(ctx):
     for max_iters in (3, 0):
         for im, g in zip(imgs, ctx.kmeans_xyrgb_batch(imgs, 10, max_iters=max_iters)):
             same_kmeans(g, O.kmeans_xyrgb(im, 10, mode=O.MODE_EXACT, max_iters=max_iters))
+
+
+@pytest.mark.parametrize("kind,w,h,k", [("xyrgb", 200, 150, 64), ("rgb", 160, 120, 16)])
+def test_kmeans_cluster_one_call_equals_the_session_calls(ctx, kind, w, h, k):
+    """cniic_kmeans_cluster = open + reset + run + get + close in one FFI crossing: same answers as the oracle / the session API."""
+    img = cb.synth_image_host(w, h, 17, 12)
+    kid = cb.POINTS_XYRGB if kind == "xyrgb" else cb.POINTS_RGB
+    o = O.kmeans_xyrgb(img, k, max_iters=4) if kind == "xyrgb" else O.kmeans_rgb(img, k, max_iters=4)
+    cen, wts, asg, st = cb.kmeans_cluster(ctx, kid, k, img, w * h, max_iters=4, w=w, h_local=h, want_assign=True)
+    assert st.iterations == o.iterations and np.array_equal(cen, o.centroids) and np.array_equal(asg, o.assign)
+    assert np.array_equal(wts, np.bincount(o.assign, minlength=k).astype(np.uint64))
+    none_cen, none_w, none_a, st2 = cb.kmeans_cluster(ctx, kid, k, img, w * h, max_iters=4, w=w, h_local=h, want_centroids=False)
+    assert none_cen is None and none_a is None and st2.moved_total == st.moved_total
