@@ -15,7 +15,8 @@ def pytest_configure(config):
 # emulated-kernel cases that take more than ~5 s on the host (tests/test_emu_kernels.py); run them with CNIIC_EMU_FULL=1
 EMU_SLOW = ("many_symbols", "333-257-256", "640-360-2048", "unique_colours[256]", "hist_delta_extremes", "513-65-4096", "100003-1000",
             "0-512-512-16", "1024-96-100", "pipeline[64]", "k256_4096", "k2048_8k", "stages_8192", "codecs_fullsize",
-            "sharded_code_path[c5]", "stage_workloads_run[c5]", "histogram[256-256-8]", "histogram[64-64-5]", "at_full_size")
+            "sharded_code_path[c5]", "stage_workloads_run[c5]", "histogram[256-256-8]", "histogram[64-64-5]", "at_full_size",
+            "edge_cases[2]", "edge_cases[3]", "edge_cases[8]", "edge_cases[13]", "json_contract[c2]")
 
 
 def pytest_collection_modifyitems(config, items):
