@@ -1012,25 +1012,36 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
 #pragma unroll
             for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
         } else {
-            // near-zero symbols are counted in shared memory (ATOMS), the rest goes to the global bins directly
+            // near-zero symbols are counted in shared memory (ATOMS), the rest goes to the global bins directly.  The 16 shared
+            // atomics of a thread are ISSUED back to back and their return values (the guard-bit check) examined afterwards: checking
+            // each one right behind its atomic made every warp wait out the atomic's latency 16 times per block, with 16 warps per SM
+            uint32_t old_v[16], slot[16];  // slot = cube index (bit 31 set: outside the cube, already counted globally)
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 const uint32_t c = pix[j], p = j ? pix[j - 1] : prev;
                 const int d0 = int(c & 0xff) - int(p & 0xff), d1 = int((c >> 8) & 0xff) - int((p >> 8) & 0xff),
                           d2 = int((c >> 16) & 0xff) - int((p >> 16) & 0xff);
+                old_v[j] = 0;
                 if ((unsigned)(d0 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d1 + CUBE_R) < (unsigned)CUBE_S && (unsigned)(d2 + CUBE_R) < (unsigned)CUBE_S) {
-                    const int ci = ((d0 + CUBE_R) * CUBE_S + (d1 + CUBE_R)) * CUBE_S + (d2 + CUBE_R);
-                    const int sh = 16 * (ci & 1);
-                    const uint32_t old = atomicAdd(&s_cube[ci >> 1], 1u << sh);
-                    if (((old >> sh) & 0x7fffu) == 0x7fffu) {  // my increment set the guard bit: 2^15 counts leave the field
-                        atomicSub(&s_cube[ci >> 1], 0x8000u << sh);
-                        const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
-                        atomicAdd(&bins[key], 32768u);
-                        if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
-                    }
+                    const uint32_t ci = uint32_t(((d0 + CUBE_R) * CUBE_S + (d1 + CUBE_R)) * CUBE_S + (d2 + CUBE_R));
+                    slot[j] = ci;
+                    old_v[j] = atomicAdd(&s_cube[ci >> 1], 1u << (16 * (ci & 1)));
                 } else {
+                    slot[j] = 0x80000000u;
                     const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
                     atomicAdd(&bins[key], 1u);
+                    if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t ci = slot[j];
+                const int sh = 16 * (ci & 1);
+                if (!(ci >> 31) && ((old_v[j] >> sh) & 0x7fffu) == 0x7fffu) {  // my increment set the guard bit: 2^15 counts leave the field
+                    atomicSub(&s_cube[ci >> 1], 0x8000u << sh);
+                    const int d2 = int(ci % CUBE_S) - CUBE_R, d1 = int((ci / CUBE_S) % CUBE_S) - CUBE_R, d0 = int(ci / (CUBE_S * CUBE_S)) - CUBE_R;
+                    const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                    atomicAdd(&bins[key], 32768u);
                     if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
                 }
             }
