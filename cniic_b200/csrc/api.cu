@@ -5,6 +5,8 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -224,6 +226,61 @@ extern "C" int cniic_ctx_p2p_connect(cniic_ctx *ctx, const uint8_t *handles /* w
 // ---- context ---------------------------------------------------------------------------------------------------
 extern "C" int cniic_version(void) { return 100; }
 
+// ---- device-wide histogram bins (declared in common.cuh) ---------------------------------------------------------------
+constexpr size_t BINS_PAGE = 4096;  // bins per page flag (stages.cu: PAGE)
+struct DeviceBins {
+    std::mutex lease[2];                      // held by the context that is counting into / compacting key space `kind`
+    uint32_t *p[2] = {nullptr, nullptr};      // bins, then one flag byte per page
+    cudaEvent_t clean_ev[2] = {nullptr, nullptr};  // recorded by the last holder behind the work that left the bins zero
+    int contexts = 0;
+};
+static std::mutex g_bins_mu;
+static std::map<int, DeviceBins> g_bins;  // by device ordinal (map nodes do not move)
+
+static size_t bins_count(int kind) { return kind == 0 ? (size_t(1) << 24) : (size_t)511 * 511 * 511; }
+static size_t bins_bytes(int kind) { return bins_count(kind) * 4 + (bins_count(kind) + BINS_PAGE - 1) / BINS_PAGE + 16; }
+
+int cniic_bins_acquire(cniic_ctx *ctx, int kind, uint32_t **bins, uint8_t **flags, size_t *nbins) {
+    DeviceBins *db = ctx->dev_bins;
+    if (!ctx->bins_held[kind]) {
+        db->lease[kind].lock();
+        cudaError_t e = cudaSuccess;
+        if (!db->p[kind]) {  // first use on this device: allocate, clear on my stream (later holders wait for my release event)
+            void *p = nullptr;
+            e = cudaMalloc(&p, bins_bytes(kind));
+            if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, bins_bytes(kind), ctx->stream);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&db->clean_ev[kind], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(db->clean_ev[kind], ctx->stream);
+            if (e != cudaSuccess) {
+                if (p) cudaFree(p);
+                if (db->clean_ev[kind]) { cudaEventDestroy(db->clean_ev[kind]); db->clean_ev[kind] = nullptr; }
+                db->lease[kind].unlock();
+                return cniic_set_error(ctx, CNIIC_ERR_CUDA, "histogram bins (%zu MB): %s", bins_bytes(kind) >> 20, cudaGetErrorString(e));
+            }
+            db->p[kind] = static_cast<uint32_t *>(p);
+        } else if ((e = cudaStreamWaitEvent(ctx->stream, db->clean_ev[kind], 0)) != cudaSuccess) {
+            db->lease[kind].unlock();
+            return cniic_set_error(ctx, CNIIC_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+        }
+        ctx->bins_held[kind] = true;
+    }
+    *bins = db->p[kind];
+    *nbins = bins_count(kind);
+    *flags = reinterpret_cast<uint8_t *>(*bins + *nbins);
+    return CNIIC_OK;
+}
+
+void cniic_bins_release(cniic_ctx *ctx, int kind, bool clean) {
+    if (!ctx->bins_held[kind]) return;
+    DeviceBins *db = ctx->dev_bins;
+    if (!clean) cudaMemsetAsync(db->p[kind], 0, bins_bytes(kind), ctx->stream);
+    cudaEventRecord(db->clean_ev[kind], ctx->stream);
+    ctx->bins_held[kind] = false;
+    db->lease[kind].unlock();
+}
+
+const uint32_t *cniic_bins_peek(const cniic_ctx *ctx, int kind) { return ctx->dev_bins ? ctx->dev_bins->p[kind] : nullptr; }
+
 static int ctx_create_common(int device, cniic_ctx **out) {
     if (!out) return CNIIC_ERR_BAD_ARG;
     *out = nullptr;
@@ -251,6 +308,11 @@ static int ctx_create_common(int device, cniic_ctx **out) {
         if (cudaMalloc(&ctx->tlog, 64 * 8 * 8) == cudaSuccess) cudaMemset(ctx->tlog, 0, 64 * 8 * 8);
         else ctx->tlog = nullptr;
     }
+    {
+        std::lock_guard<std::mutex> g(g_bins_mu);
+        ctx->dev_bins = &g_bins[device];
+        ctx->dev_bins->contexts++;
+    }
     *out = ctx;
     return CNIIC_OK;
 }
@@ -273,11 +335,20 @@ extern "C" int cniic_ctx_create_dist(int device, int rank, int world, const uint
 extern "C" void cniic_ctx_destroy(cniic_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (int kind = 0; kind < 2; kind++) cniic_bins_release(ctx, kind, false);  // (only held here if a call was abandoned half way)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cniic_nccl_destroy(ctx);
     for (cniic_ctx::Block &b : ctx->cache) cudaFree(b.p);
-    for (uint32_t *hb : ctx->hist_bins)
-        if (hb) cudaFree(hb);
+    if (ctx->dev_bins) {  // the last context on the device takes the bins with it
+        std::lock_guard<std::mutex> g(g_bins_mu);
+        if (--ctx->dev_bins->contexts == 0)
+            for (int kind = 0; kind < 2; kind++) {
+                if (ctx->dev_bins->p[kind]) cudaFree(ctx->dev_bins->p[kind]);
+                if (ctx->dev_bins->clean_ev[kind]) cudaEventDestroy(ctx->dev_bins->clean_ev[kind]);
+                ctx->dev_bins->p[kind] = nullptr;
+                ctx->dev_bins->clean_ev[kind] = nullptr;
+            }
+    }
     for (void *p : ctx->p2p_opened) cudaIpcCloseMemHandle(p);
     if (ctx->p2p_peer_table) cudaFree(ctx->p2p_peer_table);
     if (ctx->p2p_local) cudaFree(ctx->p2p_local);

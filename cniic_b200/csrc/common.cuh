@@ -42,8 +42,21 @@ struct cniic_ctx {
     unsigned long long *tlog = nullptr;  // CNIIC_TLOG=1: device timeline buffer of the Lloyd loop (64 iterations x 8 timestamps)
     std::vector<uint8_t> pending_stream;  // cniic_codec_encode result that did not fit the caller's buffer (cniic_codec_encode_fetch)
     bool has_pending_stream = false;
-    uint32_t *hist_bins[2] = {nullptr, nullptr};  // persistent dense histogram bins (+ page flags), all zero between calls
+    // dense histogram bins (+ page flags): ONE set per device, shared by every context on it and borrowed for the span of a
+    // counting pass + its compaction (cniic_bins_acquire / cniic_bins_release in api.cu); all zero whenever nobody holds them
+    struct DeviceBins *dev_bins = nullptr;
+    bool bins_held[2] = {false, false};
 };
+
+// The two key spaces (kind 0: 2^24 colours, kind 1: 511^3 delta symbols) cost 64 MB and 534 MB.  A process that follows the
+// reference's threading (bench.rs:27: one codec call per rayon worker, one context per worker) would hold them once per worker if
+// they were a context's own; they belong to the device instead.  acquire: blocks until no other context on the device is using
+// the key space, makes this context's stream wait for the work that left the bins zero, and returns them (idempotent while
+// held).  release: `clean` says the work queued on ctx->stream so far zeroes them again (the compaction kernels do); otherwise --
+// an error between counting and compaction -- they are cleared here.  Both are called on the thread that runs the C-ABI call.
+int cniic_bins_acquire(cniic_ctx *ctx, int kind, uint32_t **bins, uint8_t **flags, size_t *nbins);
+void cniic_bins_release(cniic_ctx *ctx, int kind, bool clean);
+const uint32_t *cniic_bins_peek(const cniic_ctx *ctx, int kind);  // the device's bins of that kind if they exist (no lease), else nullptr
 
 void *cniic_cache_alloc(cniic_ctx *ctx, size_t bytes);  // nullptr + error set on failure
 void cniic_cache_free(cniic_ctx *ctx, void *p);

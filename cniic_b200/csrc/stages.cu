@@ -858,8 +858,10 @@ template <int MODE>
 __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ rgb, uint32_t n,
                                                                uint8_t *out_rgb, int16_t *out_delta, uint32_t *bins, uint8_t *flags,
                                                                unsigned long long blk_begin, unsigned long long blk_end) {
-    extern __shared__ uint4 s_dyn4[];  // two raw tile stages (packed RGB rows of 192 bytes), then (MODE 2) the counter cube
-    uint8_t *s_raw = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(s_dyn4) + 127) & ~uintptr_t(127));  // TMA destination: 128-byte aligned
+    // two raw tile stages (packed RGB rows of 192 bytes; TMA destinations: 128-byte aligned), then (MODE 2) the counter cube.  The
+    // alignment is asked of the declaration -- aligning the pointer by hand made it a generic address, and every tile load and
+    // counter update a generic LD / ATOM instead of LDS / ATOMS
+    extern __shared__ __align__(128) uint8_t s_raw[];
     uint32_t *s_cube = reinterpret_cast<uint32_t *>(s_raw + 2 * HT_TILE_BYTES);
     __shared__ __align__(16) uint32_t s_px[HT * HT_STRIDE];  // one word per pixel (r | g<<8 | b<<16)
     __shared__ uint32_t s_last[8];
@@ -1053,6 +1055,260 @@ __global__ void __launch_bounds__(256) hilbert_tile_tma_kernel(const __grid_cons
             const uint32_t cnt = (s_cube[ci >> 1] >> (16 * (ci & 1))) & 0xffffu;
             if (cnt) {
                 const int d2 = ci % CUBE_S - CUBE_R, d1 = (ci / CUBE_S) % CUBE_S - CUBE_R, d0 = ci / (CUBE_S * CUBE_S) - CUBE_R;
+                const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                atomicAdd(&bins[key], cnt);
+                if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
+            }
+        }
+    }
+}
+
+// ---- second version of the TMA tile stages: no expansion pass, no CTA barrier ------------------------------------------------------
+// A thread's 16 curve indices are one 4 x 4 pixel cell of the block, i.e. four 12-byte row segments of the landed tile: it reads them
+// as 12 words straight from the raw stage, unpacks the 16 pixels in registers, and brings them into curve order with two
+// conditional register permutations -- on the Hilbert curve a cell is the base motif either as it is, rotated by 180 degrees
+// (negative step), transposed (swapped axes), or both; sx == sy always (the fold below only ever transposes or anti-transposes).
+// What the first version spent on the word-per-pixel copy of the tile (3 LDS.128 + 4 STS.128 + 16 scattered LDS per thread, 16.6 KB
+// of shared memory, two CTA barriers per block -- its top stall, profiles/r02_ncu_full_c5_tma.txt) is gone: the predecessor of a
+// warp's first symbol is read from the raw tile too (its position in the block is a per-thread constant), and the stages are handed
+// back through a second pair of mbarriers (256 arrivals) that only the refilling thread waits on, so warps drift freely.
+// A 15-bit counter of the shared-memory cube reached 2^15 (its guard bit is set by the increment that got there): move 2^15 counts
+// of that symbol to the global bins.  Out of line on purpose -- it runs once per 32 768 equal symbols, and sixteen inlined copies of
+// its divisions made up a third of the kernel's code.
+template <int CR>
+__device__ __noinline__ void cube_spill(uint32_t *s_cube, uint32_t ci, uint32_t *bins, uint8_t *flags) {
+    constexpr int CS = 2 * CR + 1;
+    atomicSub(&s_cube[ci >> 1], 0x8000u << (16 * (ci & 1)));
+    const int d2 = int(ci % CS) - CR, d1 = int((ci / CS) % CS) - CR, d0 = int(ci / (CS * CS)) - CR;
+    const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+    atomicAdd(&bins[key], 32768u);
+    flags[key >> PAGE_SHIFT] = 1;
+}
+
+template <int MODE, int NB, int CR>  // CR: radius of the shared-memory counter cube (MODE 2)
+__global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ rgb,
+                                                                                   uint32_t n, uint8_t *out_rgb, int16_t *out_delta, uint32_t *bins,
+                                                                                   uint8_t *flags, unsigned long long blk_begin, unsigned long long blk_end) {
+    // two raw tile stages (packed RGB rows of 192 bytes; TMA destinations: 128-byte aligned), then (MODE 2) the counter cube.  The
+    // alignment is asked of the declaration -- aligning the pointer by hand made it a generic address, and every tile load and
+    // counter update a generic LD / ATOM instead of LDS / ATOMS
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    uint32_t *s_cube = reinterpret_cast<uint32_t *>(s_raw + 2 * HT_TILE_BYTES);
+    __shared__ int s_top[2][4];  // per stage: block origin (bx, by), step sign, swapped axes
+    __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
+    constexpr int CS = 2 * CR + 1, CN = CS * CS * CS;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned long long nblocks = blk_end;
+    if (MODE == 2) {
+        for (int i = tid; i < (CN + 1) / 2; i += 256) s_cube[i] = 0;
+    }
+    if (tid == 0) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        mbar_init(&s_empty[0], 256);
+        mbar_init(&s_empty[1], 256);
+        mbar_fence_init();
+    }
+    // base-4 digits 2..5 of a cell's first index = the cell number: fold those levels once, for every block
+    auto fold_cell = [](uint32_t t, int &cx, int &cy, int &cs, bool &csw) {
+        cx = 0; cy = 0; cs = 1; csw = false;
+#pragma unroll
+        for (int sl = 4; sl < HT; sl <<= 1) {
+            const uint32_t rx = 1u & (t >> 1), ry = 1u & (t ^ rx);
+            if (ry == 0) {
+                if (rx == 1) {
+                    const int nx = sl - 1 - cy, ny = sl - 1 - cx;
+                    cx = nx; cy = ny; cs = -cs;
+                } else {
+                    const int q = cx;
+                    cx = cy; cy = q;
+                }
+                csw = !csw;
+            }
+            cx += sl * (int)rx;
+            cy += sl * (int)ry;
+            t >>= 2;
+        }
+    };
+    int lax, lay, ls, plx = 0, ply = 0;
+    bool lswapped;
+    fold_cell((uint32_t)tid, lax, lay, ls, lswapped);
+    if (lane == 0 && tid > 0) {  // where the LAST pixel of the previous cell lies (digit 15 of the motif is (3, 0))
+        int qx, qy, qs;
+        bool qsw;
+        fold_cell((uint32_t)tid - 1, qx, qy, qs, qsw);
+        plx = qx + qs * (qsw ? 0 : 3);
+        ply = qy + qs * (qsw ? 3 : 0);
+    }
+    __syncthreads();
+    // thread 0: fold the levels above the block (6..L-1) into an affine map of the 64x64 block, request the block's pixels
+    auto issue = [&](unsigned long long blk, int stage) {
+        int bx = 0, by = 0, ts = 1, sw = 0;
+        unsigned long long t = blk;
+        for (uint32_t sft = HT; sft < n; sft <<= 1) {
+            const int sl = (int)sft;
+            const uint32_t rx = 1u & (uint32_t)(t >> 1), ry = 1u & ((uint32_t)t ^ rx);
+            if (ry == 0) {
+                if (rx == 1) {
+                    const int nbx = sl - 1 - by, nby = sl - 1 - bx;
+                    bx = nbx; by = nby; ts = -ts;
+                } else {
+                    const int q = bx;
+                    bx = by; by = q;
+                }
+                sw ^= 1;
+            }
+            bx += sl * (int)rx;
+            by += sl * (int)ry;
+            t >>= 2;
+        }
+        s_top[stage][0] = bx; s_top[stage][1] = by; s_top[stage][2] = ts; s_top[stage][3] = sw;
+        mbar_arrive_expect_tx(&s_full[stage], HT_TILE_BYTES);
+        tma_load_2d(s_raw + (size_t)stage * HT_TILE_BYTES, &tmap, (bx & ~(HT - 1)) * 3, by & ~(HT - 1), &s_full[stage]);
+    };
+    const unsigned long long first = blk_begin + blockIdx.x;
+    if (tid == 0 && first < nblocks) issue(first, 0);
+    uint32_t it = 0;
+    for (unsigned long long blk = first; blk < nblocks; blk += gridDim.x, it++) {
+        const int stage = it & 1;
+        const unsigned long long B = blk * 4096;
+        const unsigned long long i0 = B + (unsigned long long)tid * 16;
+        uint32_t prev = 0;
+        if (MODE != 0 && tid == 0 && B != 0) {  // the block's first symbol follows the last pixel of the previous block: global, asked for early
+            uint32_t px, py;
+            hilbert_d2xy_pow2(n, B - 1, &px, &py);
+            const uint8_t *q = rgb + ((size_t)py * n + px) * 3;
+            prev = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+        }
+        mbar_wait(&s_full[stage], (it >> 1) & 1);
+        const uint8_t *tile = s_raw + (size_t)stage * HT_TILE_BYTES;
+        const int bx = s_top[stage][0], by = s_top[stage][1], ts = s_top[stage][2], sw = s_top[stage][3];
+        // compose: (x, y) = top(local(u, v)); x = bx + ts * (sw ? yl : xl), y = by + ts * (sw ? xl : yl)
+        const int ax = bx + ts * (sw ? lay : lax), ay = by + ts * (sw ? lax : lay);
+        const bool neg = ts * ls < 0, swapped = lswapped != (sw != 0);
+        const int mx = (neg ? ax - 3 : ax) & (HT - 1), my = (neg ? ay - 3 : ay) & (HT - 1);  // the cell's low corner inside the block
+        uint32_t p[16];
+        {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(tile + my * (HT * 3) + mx * 3);
+#pragma unroll
+            for (int v = 0; v < 4; v++) {  // 3 words -> 4 pixels (r | g<<8 | b<<16)
+                const uint32_t w0 = src[v * (HT * 3 / 4)], w1 = src[v * (HT * 3 / 4) + 1], w2 = src[v * (HT * 3 / 4) + 2];
+                p[4 * v] = w0 & 0xffffff;
+                p[4 * v + 1] = __byte_perm(w0, w1, 0x4543) & 0xffffff;
+                p[4 * v + 2] = __byte_perm(w1, w2, 0x4432) & 0xffffff;
+                p[4 * v + 3] = w2 >> 8;
+            }
+        }
+        if (MODE != 0 && lane == 0 && tid > 0) {
+            const int qx = (bx + ts * (sw ? ply : plx)) & (HT - 1), qy = (by + ts * (sw ? plx : ply)) & (HT - 1);
+            const uint8_t *q = tile + qy * (HT * 3) + qx * 3;
+            prev = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+        }
+        mbar_arrive(&s_empty[stage]);  // this thread is done with the stage
+        if (tid == 0 && blk + gridDim.x < nblocks) {  // refill the other stage once everybody has left it (block it - 1)
+            if (it > 0) mbar_wait(&s_empty[stage ^ 1], ((it - 1) >> 1) & 1);
+            issue(blk + gridDim.x, stage ^ 1);
+        }
+        // bring the cell into curve order: rotate by 180 degrees (negative step), then transpose (swapped axes), then the base motif
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t a = p[i], b = p[15 - i];
+            p[i] = neg ? b : a;
+            p[15 - i] = neg ? a : b;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = a + 1; b < 4; b++) {
+                const uint32_t u = p[4 * a + b], v = p[4 * b + a];
+                p[4 * a + b] = swapped ? v : u;
+                p[4 * b + a] = swapped ? u : v;
+            }
+        constexpr int ORD[16] = {0, 1, 5, 4, 8, 12, 13, 9, 10, 14, 15, 11, 7, 6, 2, 3};  // 4 * HIL4_Y[j] + HIL4_X[j]
+        uint32_t pix[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) pix[j] = p[ORD[j]];
+        if (MODE == 0) {
+            uint32_t wd[12];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // 4 pixels -> 3 words
+                const uint32_t a = pix[4 * q], b = pix[4 * q + 1], c = pix[4 * q + 2], e = pix[4 * q + 3];
+                wd[3 * q] = a | (b << 24);
+                wd[3 * q + 1] = (b >> 8) | (c << 16);
+                wd[3 * q + 2] = (c >> 16) | (e << 8);
+            }
+            uint4 *o = reinterpret_cast<uint4 *>(out_rgb + (i0 - blk_begin * 4096) * 3);
+            o[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            o[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+            o[2] = make_uint4(wd[8], wd[9], wd[10], wd[11]);
+            continue;
+        }
+        {   // predecessor of this thread's first symbol: the neighbour lane's last pixel (lane 0 read it from the tile / from global)
+            const uint32_t up = __shfl_up_sync(0xffffffffu, pix[15], 1);
+            if (lane != 0) prev = up;
+        }
+        if (MODE == 1) {
+            // 16-bit SIMD lanes: A = (r, b), G = (g, 0); per-lane wrap-around subtraction gives the i16 differences
+            uint32_t wd[24];  // 48 i16 packed two per word
+            uint32_t pa = prev & 0x00ff00ffu, pg = (prev >> 8) & 0xffu;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const uint32_t a0 = pix[j] & 0x00ff00ffu, g0 = (pix[j] >> 8) & 0xffu;
+                const uint32_t a1 = pix[j + 1] & 0x00ff00ffu, g1 = (pix[j + 1] >> 8) & 0xffu;
+                const uint32_t da0 = __vsub2(a0, pa), dg0 = __vsub2(g0, pg), da1 = __vsub2(a1, a0), dg1 = __vsub2(g1, g0);
+                wd[3 * (j / 2)] = __byte_perm(da0, dg0, 0x5410);      // dr0, dg0
+                wd[3 * (j / 2) + 1] = __byte_perm(da0, da1, 0x5432);  // db0, dr1
+                wd[3 * (j / 2) + 2] = __byte_perm(dg1, da1, 0x7610);  // dg1, db1
+                pa = a1; pg = g1;
+            }
+            uint4 *o = reinterpret_cast<uint4 *>(out_delta + (i0 - blk_begin * 4096) * 3);
+#pragma unroll
+            for (int q = 0; q < 6; q++) o[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
+        } else {
+            // near-zero symbols are counted in shared memory (ATOMS), the rest goes to the global bins directly; the shared atomics
+            // are issued back to back, their return values (the guard-bit check) examined afterwards.  Per symbol: one VABSDIFF4 and
+            // three logic operations decide whether all three |differences| are <= CR; the cube index is linear in the channels,
+            // ((d0 + CR) * CS + (d1 + CR)) * CS + (d2 + CR) = (A(c) - A(p)) * CS + (b(c) - b(p)) + K with A(x) = CS * r + g (one
+            // IDP.4A per pixel), so no channel is extracted on the common path.
+            constexpr uint32_t SPLAT_LIM = (127u - CR) * 0x01010101u;
+            constexpr int K_CUBE = (CR * CS + CR) * CS + CR;
+            uint32_t old_v[16], slot[16];  // slot = cube index (bit 31 set: outside the cube, already counted globally)
+            int pa = dp4a_uu(prev, uint32_t(CS) | (1u << 8), 0), pb = int(prev >> 16);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t c = pix[j], q = j ? pix[j - 1] : prev;
+                const int ca = dp4a_uu(c, uint32_t(CS) | (1u << 8), 0), cb = int(c >> 16);
+                const uint32_t ad = __vabsdiffu4(c, q);  // |difference| per channel
+                old_v[j] = 0;
+                if (((((ad & 0x7f7f7f7fu) + SPLAT_LIM) | ad) & 0x80808080u) == 0) {  // no channel differs by more than CR
+                    const uint32_t ci = uint32_t((ca - pa) * CS + (cb - pb + K_CUBE));
+                    slot[j] = ci;
+                    old_v[j] = atomicAdd(&s_cube[ci >> 1], 1u << (16 * (ci & 1)));
+                } else {
+                    slot[j] = 0x80000000u;
+                    const int d0 = int(c & 0xff) - int(q & 0xff), d1 = int((c >> 8) & 0xff) - int((q >> 8) & 0xff),
+                              d2 = int((c >> 16) & 0xff) - int((q >> 16) & 0xff);
+                    const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                    atomicAdd(&bins[key], 1u);
+                    flags[key >> PAGE_SHIFT] = 1;  // (a plain store: testing the flag first put a dependent global load on this path)
+                }
+                pa = ca; pb = cb;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t ci = slot[j];
+                const int sh = 16 * (ci & 1);
+                if (!(ci >> 31) && ((old_v[j] >> sh) & 0x7fffu) == 0x7fffu)  // my increment set the guard bit: 2^15 counts leave the field
+                    cube_spill<CR>(s_cube, ci, bins, flags);
+            }
+        }
+    }
+    if (MODE == 2) {  // flush the CTA's near-zero counters into the global bins
+        __syncthreads();
+        for (int ci = tid; ci < CN; ci += 256) {
+            const uint32_t cnt = (s_cube[ci >> 1] >> (16 * (ci & 1))) & 0xffffu;
+            if (cnt) {
+                const int d2 = ci % CS - CR, d1 = (ci / CS) % CS - CR, d0 = ci / (CS * CS) - CR;
                 const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
                 atomicAdd(&bins[key], cnt);
                 if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
@@ -1498,25 +1754,17 @@ inline bool is_pow2_square(uint32_t w, uint32_t h) { return w == h && (w & (w - 
 
 // ---- device-level building blocks (declared in stages.cuh) -----------------------------------------------------
 
-// persistent, all-zero-between-calls bins of a key space (kind 0: 2^24 colours, kind 1: 511^3 delta symbols)
+// the device's bins of a key space (kind 0: 2^24 colours, kind 1: 511^3 delta symbols), borrowed until the compaction that
+// follows the counting pass has zeroed them again (common.cuh: cniic_bins_acquire / cniic_bins_release)
 static int hist_space(cniic_ctx *ctx, int kind, uint32_t **bins, uint8_t **flags, size_t *nbins) {
-    *nbins = kind == 0 ? (size_t(1) << 24) : (size_t)511 * 511 * 511;
-    const size_t npages = (*nbins + PAGE - 1) / PAGE;
-    if (!ctx->hist_bins[kind]) {
-        void *p = nullptr;
-        CU_TRY(ctx, cudaMalloc(&p, *nbins * 4 + npages + 16));
-        CU_TRY(ctx, cudaMemsetAsync(p, 0, *nbins * 4 + npages + 16, ctx->stream));
-        ctx->hist_bins[kind] = static_cast<uint32_t *>(p);
-    }
-    *bins = ctx->hist_bins[kind];
-    *flags = reinterpret_cast<uint8_t *>(*bins + *nbins);
-    return CNIIC_OK;
+    static_assert(PAGE == 4096, "api.cu sizes the page flags with the same constant");
+    return cniic_bins_acquire(ctx, kind, bins, flags, nbins);
 }
 
-int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins_in, size_t nbins, uint32_t **d_keys, unsigned long long **d_counts, size_t *n_unique) {
-    const int kind = d_bins_in == ctx->hist_bins[0] ? 0 : 1;
+static int dense_compact_body(cniic_ctx *ctx, int kind, uint32_t **d_keys, unsigned long long **d_counts, size_t *n_unique) {
     uint32_t *bins;
     uint8_t *flags;
+    size_t nbins;
     ST_TRY(hist_space(ctx, kind, &bins, &flags, &nbins));
     const uint32_t npages = (uint32_t)((nbins + PAGE - 1) / PAGE);
     *d_keys = nullptr;
@@ -1544,6 +1792,16 @@ int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins_in, size_t nb
     return CNIIC_OK;
 }
 
+// (key, count) lists of the non-empty bins of the key space `d_bins_in` belongs to, ascending; leaves the bins zero and hands
+// them back to the device (the lease was taken by the counting pass)
+int cniic_dev_dense_compact(cniic_ctx *ctx, const uint32_t *d_bins_in, size_t nbins, uint32_t **d_keys, unsigned long long **d_counts, size_t *n_unique) {
+    (void)nbins;
+    const int kind = d_bins_in == cniic_bins_peek(ctx, 0) ? 0 : 1;
+    const int rc = dense_compact_body(ctx, kind, d_keys, d_counts, n_unique);
+    cniic_bins_release(ctx, kind, rc == CNIIC_OK);
+    return rc;
+}
+
 void cniic_unique_colours_free(cniic_ctx *ctx, UniqueColours *uc) {
     cniic_cache_free(ctx, uc->d_pts);
     cniic_cache_free(ctx, uc->d_wts);
@@ -1552,7 +1810,7 @@ void cniic_unique_colours_free(cniic_ctx *ctx, UniqueColours *uc) {
 
 // count_freqs over the pixels (utils.rs:4-16 at clusterc.rs:21) with the result already in the form the culled D = 3 K-means scans:
 // see dedup_hist_kernel.  One host synchronisation (the number of unique colours sizes the outputs and the K-means grid).
-int cniic_dev_unique_colours(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, UniqueColours *out) {
+static int unique_colours_body(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, UniqueColours *out) {
     *out = UniqueColours();
     uint32_t *bins;
     uint8_t *flags;
@@ -1584,6 +1842,12 @@ int cniic_dev_unique_colours(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, Uni
     return CNIIC_OK;
 }
 
+int cniic_dev_unique_colours(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, UniqueColours *out) {
+    const int rc = unique_colours_body(ctx, d_rgb, n, out);
+    cniic_bins_release(ctx, 0, rc == CNIIC_OK);  // the compaction kernel queued above zeroes the bins as it reads them
+    return rc;
+}
+
 int cniic_dev_hist_rgb_bins(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint32_t **d_bins) {
     uint8_t *flags;
     size_t nbins;
@@ -1592,8 +1856,11 @@ int cniic_dev_hist_rgb_bins(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, uint
         hist_rgb_kernel<<<grid_for(ctx, n, 4), 256, 0, ctx->stream>>>(d_rgb, n, *d_bins, flags);
         ctx->launches++;
     }
-    CU_TRY(ctx, cudaGetLastError());
-    return CNIIC_OK;
+    if (cudaGetLastError() != cudaSuccess) {
+        cniic_bins_release(ctx, 0, false);
+        return cniic_set_error(ctx, CNIIC_ERR_CUDA, "colour histogram launch failed");
+    }
+    return CNIIC_OK;  // the lease ends in cniic_dev_dense_compact
 }
 
 int cniic_dev_recolor(cniic_ctx *ctx, const uint8_t *d_rgb, size_t n, const uint32_t *d_keys, const uint16_t *d_assign, size_t n_unique,
@@ -1625,9 +1892,10 @@ template <int MODE>
 static int launch_tile_stage(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t n, uint8_t *out_rgb, int16_t *out_delta, uint32_t *bins, uint8_t *flags,
                              unsigned long long blk_begin, unsigned long long blk_end) {
     static const bool no_tma = getenv("CNIIC_STAGES_NO_TMA") != nullptr;
-    const size_t cube = MODE == 2 ? size_t((CUBE_N + 1) / 2) * 4 : 0;
+    const size_t cube_v1 = MODE == 2 ? size_t((CUBE_N + 1) / 2) * 4 : 0;
     const unsigned long long nblk = blk_end - blk_begin;
     if (no_tma) {
+        const size_t cube = cube_v1;
         if (MODE == 2) {
             CU_TRY(ctx, cudaFuncSetAttribute(hilbert_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cube));
             int per_sm = 0;
@@ -1642,13 +1910,23 @@ static int launch_tile_stage(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t n, u
         CUtensorMap tmap;
         if (!tma_encode_2d_u8(&tmap, d_rgb, (uint64_t)n * 3, n, (uint64_t)n * 3, HT * 3, HT))
             return cniic_set_error(ctx, CNIIC_ERR_CUDA, "cuTensorMapEncodeTiled failed for a %u x %u image", n, n);
-        const size_t smem = 2 * size_t(HT_TILE_BYTES) + 128 + cube;  // two tile stages (+ alignment slack) + the counter cube
-        CU_TRY(ctx, cudaFuncSetAttribute(hilbert_tile_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static const bool tile_v1 = getenv("CNIIC_TILE_V1") != nullptr;  // first TMA version (word-per-pixel copy of the tile), for A/B runs
+        // counter cube of the histogram stage: |d| <= 14 per channel (48.8 KB, 3 CTAs/SM) by default; CNIIC_HIST_CUBE_R=15 -> 59.6 KB, 2 CTAs/SM
+        static const int cube_r = getenv("CNIIC_HIST_CUBE_R") ? atoi(getenv("CNIIC_HIST_CUBE_R")) : 14;
+        void (*kern)(const CUtensorMap, const uint8_t *, uint32_t, uint8_t *, int16_t *, uint32_t *, uint8_t *, unsigned long long, unsigned long long);
+        size_t cube = 0;
+        if (tile_v1) { kern = hilbert_tile_tma_kernel<MODE>; cube = cube_v1; }
+        else if constexpr (MODE != 2) kern = hilbert_tile_tma2_kernel<MODE, 6, CUBE_R>;  // 40 registers: six CTAs (48 warps) per SM
+        else if (cube_r == 15) { kern = hilbert_tile_tma2_kernel<2, 2, CUBE_R>; cube = cube_v1; }
+        else { kern = hilbert_tile_tma2_kernel<2, 3, 14>; cube = size_t((29 * 29 * 29 + 1) / 2) * 4; }
+        const size_t smem = 2 * size_t(HT_TILE_BYTES) + cube;  // two tile stages + the counter cube
+        CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int per_sm = 0;
-        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hilbert_tile_tma_kernel<MODE>, 256, smem));
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
         if (per_sm < 1) return cniic_set_error(ctx, CNIIC_ERR_UNSUPPORTED, "tile stage kernel does not fit an SM");
         const unsigned grid = (unsigned)std::min<size_t>((size_t)nblk, (size_t)ctx->sm_count * per_sm);  // persistent: one wave
-        hilbert_tile_tma_kernel<MODE><<<grid, 256, smem, ctx->stream>>>(tmap, d_rgb, n, out_rgb, out_delta, bins, flags, blk_begin, blk_end);
+        kern<<<grid, 256, smem, ctx->stream>>>(tmap, d_rgb, n, out_rgb, out_delta, bins, flags, blk_begin, blk_end);
     }
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
@@ -1765,14 +2043,18 @@ int cniic_dev_hist_delta_bins(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, 
 int cniic_dev_hist_delta_bins_range(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h, unsigned long long i0, unsigned long long i1,
                                     uint32_t **d_bins, size_t *nbins) {
     uint8_t *flags;
-    ST_TRY(hist_space(ctx, 1, d_bins, &flags, nbins));
+    ST_TRY(hist_space(ctx, 1, d_bins, &flags, nbins));  // the lease ends in cniic_dev_dense_compact
     if (i0 >= i1) return CNIIC_OK;
-    if (tile_path(d_rgb, nullptr, w, h) && i0 % 4096 == 0 && i1 % 4096 == 0)
-        return launch_tile_stage<2>(ctx, d_rgb, w, nullptr, nullptr, *d_bins, flags, i0 / 4096, i1 / 4096);
-    else hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)(i1 - i0)), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins, flags, i0, i1);
-    ctx->launches++;
-    CU_TRY(ctx, cudaGetLastError());
-    return CNIIC_OK;
+    int rc = CNIIC_OK;
+    if (tile_path(d_rgb, nullptr, w, h) && i0 % 4096 == 0 && i1 % 4096 == 0) {
+        rc = launch_tile_stage<2>(ctx, d_rgb, w, nullptr, nullptr, *d_bins, flags, i0 / 4096, i1 / 4096);
+    } else {
+        hilbert_stream_kernel<2><<<grid_for(ctx, (size_t)(i1 - i0)), 256, 0, ctx->stream>>>(d_rgb, w, h, is_pow2_square(w, h), nullptr, nullptr, *d_bins, flags, i0, i1);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = cniic_set_error(ctx, CNIIC_ERR_CUDA, "delta histogram launch failed");
+    }
+    if (rc != CNIIC_OK) cniic_bins_release(ctx, 1, false);
+    return rc;
 }
 
 // ---- C ABI -----------------------------------------------------------------------------------------------------

@@ -82,7 +82,7 @@ ASM_RE = re.compile(r'asm\s*(?:volatile)?\s*\(\s*"([a-z0-9_.]+)\s+%0,\s*%1,\s*%2
 # programmatic-dependent-launch control instructions have no effect when launches run one after another
 NOOP_ASM_RE = re.compile(r'asm\s*(?:volatile)?\s*\(\s*"(?:griddepcontrol\.(?:wait|launch_dependents);"\s*:::\s*"memory"|prefetch\.global\.L1 \[%0\];"\s*::\s*"l"\(\w+\))\s*\)\s*;')
 TIMER_ASM_RE = re.compile(r'asm\s*volatile\s*\(\s*"mov\.u64 %0, %%globaltimer;"\s*:\s*"=l"\((\w+)\)\s*\)\s*;')  # timeline instrumentation: no clock here
-SHARED_RE = re.compile(r"extern\s+__shared__\s+([\w:<> ]+?)\s+(\w+)\s*\[\s*\]\s*;")
+SHARED_RE = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w:<> ]+?)\s+(\w+)\s*\[\s*\]\s*;")
 
 
 # `#ifdef __CUDACC__ ... #endif  // __CUDACC__` blocks hold code only nvcc can compile (TMA / mbarrier inline PTX in tma.cuh); the shim

@@ -313,7 +313,8 @@ struct AtExit {
 // a fiber waits until *p != val, yielding to the other threads of its CTA (used by the shim's mbarrier stand-in)
 void spin_while_equal(const volatile unsigned *p, unsigned val, const char *what) { wait_on(p, val, what); }
 
-void *dyn_smem() { return M.smem.data(); }
+// 128-byte aligned (kernels may declare `extern __shared__ __align__(128)`: TMA destinations)
+void *dyn_smem() { return reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(M.smem.data()) + 127) & ~uintptr_t(127)); }
 
 void cta_barrier() {
     M.bar_count++;
@@ -376,9 +377,9 @@ void launch(const LaunchCfg &cfg, const std::function<void()> &body, const char 
     M.body = &body;
     M.kernel = name;
 #ifdef EMU_ASAN
-    M.smem = std::vector<unsigned char>(cfg.smem ? cfg.smem : 1);  // exact size, fresh block: ASan sees the first byte past the dynamic shared memory
+    M.smem = std::vector<unsigned char>(cfg.smem + 127);  // fresh block (+ alignment slack): ASan sees accesses past the dynamic shared memory
 #else
-    M.smem.resize(cfg.smem + 64);
+    M.smem.resize(cfg.smem + 64 + 127);
 #endif
     for (unsigned z = 0; z < cfg.grid.z; z++)
         for (unsigned y = 0; y < cfg.grid.y; y++)
@@ -410,6 +411,8 @@ cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event{0.0}; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }  // kernels run synchronously here
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t_ms = now_ms(); return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

@@ -26,6 +26,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __constant__ static const
@@ -58,7 +59,8 @@ typedef struct emu_stream *cudaStream_t;
 typedef struct emu_event *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaIpcMemLazyEnablePeerAccess = 1 };
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+enum { cudaSharedmemCarveoutMaxShared = 100 };
 struct cudaIpcMemHandle_t { char reserved[64]; };
 struct cudaDeviceProp {
     char name[256];
@@ -81,6 +83,9 @@ cudaError_t cudaStreamDestroy(cudaStream_t s);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaEventCreate(cudaEvent_t *e);
+enum { cudaEventDisableTiming = 2 };
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned flags);
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags = 0);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = nullptr);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);
@@ -146,7 +151,13 @@ static inline bool tma_encode_2d_u8(CUtensorMap *m, const void *base, unsigned l
     m->box_inner = box_inner; m->box_rows = box_rows;
     return true;
 }
-static inline void mbar_init(unsigned long long *bar, unsigned) { *bar = 0; }
+// bits 48..63: arrivals a phase needs, bits 32..47: arrivals so far (plain arrivals only; a TMA phase completes in tma_load_2d)
+static inline void mbar_init(unsigned long long *bar, unsigned arrivals) { *bar = (unsigned long long)arrivals << 48; }
+static inline void mbar_arrive(unsigned long long *bar) {
+    const unsigned long long need = *bar >> 48, got = ((*bar >> 32) & 0xffffull) + 1;
+    if (got == need) *bar = (need << 48) | ((*bar & 1ull) ^ 1ull);
+    else *bar = (need << 48) | (got << 32) | (*bar & 1ull);
+}
 static inline void mbar_fence_init() {}
 static inline void mbar_arrive_expect_tx(unsigned long long *, unsigned) {}
 static inline void mbar_wait(unsigned long long *bar, unsigned parity) {

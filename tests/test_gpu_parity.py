@@ -690,3 +690,56 @@ def test_kmeans_cluster_one_call_equals_the_session_calls(ctx, kind, w, h, k):
     assert np.array_equal(wts, np.bincount(o.assign, minlength=k).astype(np.uint64))
     none_cen, none_w, none_a, st2 = cb.kmeans_cluster(ctx, kid, k, img, w * h, max_iters=4, w=w, h_local=h, want_centroids=False)
     assert none_cen is None and none_a is None and st2.moved_total == st.moved_total
+
+
+def test_histogram_bins_belong_to_the_device_not_the_context(ctx):
+    """the 2^24-colour and 511^3-delta key spaces are allocated once per device and lent to whichever context
+    is counting (bench.rs:27 runs one codec call per rayon worker, so a process holds one context per worker).  Contexts used
+    in turn and -- on a real GPU -- from concurrent threads must all get the oracle's histograms, and a second context must
+    not cost a second 534 MB key space."""
+    import threading
+    emulated = "tests/emu/_build" in str(ctx._lib._name).replace("\\", "/")
+    rng = np.random.default_rng(77)
+    imgs = [rng.integers(0, 256, (32, 32, 3), dtype=np.uint8) // d * d for d in (1, 16, 64)]
+    want = [(O.count_freqs_rgb(im.reshape(-1, 3)), O.hist_delta(O.delta(im))) for im in imgs]
+
+    def check(c, i):
+        k, n = c.hist_rgb(imgs[i].reshape(-1, 3))
+        assert np.array_equal(k, want[i][0][0]) and np.array_equal(n, want[i][0][1])
+        k, n = c.hist_delta(imgs[i])
+        assert np.array_equal(k, want[i][1][0]) and np.array_equal(n, want[i][1][1])
+        _, cen, _ = c.cluster_colors(imgs[i], 4, max_iters=2)  # the Morton-binned pass borrows the colour bins too
+        assert np.array_equal(cen, O.cluster_colors(imgs[i], 4, max_iters=2)[1])
+
+    check(ctx, 0)  # both key spaces exist on the device from here on
+    free_before = None
+    if not emulated:
+        import torch
+        torch.cuda.synchronize()
+        free_before = torch.cuda.mem_get_info()[0]
+    others = [cb.Context() for _ in range(3)]
+    try:
+        for rep in range(2):
+            for j, c in enumerate(others + [ctx]):
+                check(c, (j + rep) % 3)
+        if free_before is not None:
+            import torch
+            assert free_before - torch.cuda.mem_get_info()[0] < (200 << 20)  # three more contexts, no second copy of the key spaces
+            errors = []
+
+            def worker(c, j):
+                try:
+                    for rep in range(6):
+                        check(c, (j + rep) % 3)
+                except BaseException as e:  # noqa: BLE001 -- reported on the main thread
+                    errors.append(e)
+            ts = [threading.Thread(target=worker, args=(c, j)) for j, c in enumerate(others)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            assert not errors, errors
+    finally:
+        for c in others:
+            c.close()
+    check(ctx, 1)  # the bins outlive the contexts that came and went
