@@ -336,21 +336,21 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
     host_imgs = [host_img[b * h_local:(b + 1) * h_local] for b in range(B)]
     e2e = None
     if independent:
-        def e2e_step():
+        def e2e_step(c=sctx):
             if B > 1:
-                return sctx.kmeans_rgb_batch(host_imgs, k, max_iters=ITERS, want_assign=False)
+                return c.kmeans_rgb_batch(host_imgs, k, max_iters=ITERS, want_assign=False)
             if unique:
-                return sctx.cluster_colors(host_img, k, max_iters=ITERS, want_image=False)
+                return c.cluster_colors(host_img, k, max_iters=ITERS, want_image=False)
             if kind == "rgb":
-                return sctx.kmeans_rgb(host_img, k, max_iters=ITERS, want_assign=False)
-            return sctx.kmeans_xyrgb(host_img, k, max_iters=ITERS, want_assign=False)
+                return c.kmeans_rgb(host_img, k, max_iters=ITERS, want_assign=False)
+            return c.kmeans_xyrgb(host_img, k, max_iters=ITERS, want_assign=False)
         api_name = ("cniic_kmeans_rgb_batch" if B > 1 else "cniic_cluster_colors (out_rgb = NULL)" if unique else
                     "cniic_kmeans_rgb" if kind == "rgb" else "cniic_kmeans_xyrgb")
         d2h_bytes = int((k * 3 * 4 + k * 8 + 64) * B)
     else:
         # sharded session: per step the shard is re-uploaded from pinned host memory and centroids/weights read back
-        def e2e_step():
-            return cb.kmeans_cluster(sctx, kind_id, k, host_img, n_local, max_iters=ITERS, init_centroids=init, n_total=n_total,
+        def e2e_step(c=sctx):
+            return cb.kmeans_cluster(c, kind_id, k, host_img, n_local, max_iters=ITERS, init_centroids=init, n_total=n_total,
                                      first_index=y0 * w, w=w, h_local=h_local, y0=y0, on_device=False, want_centroids=True)
         api_name = "cniic_kmeans_cluster (row-sharded, host points in, centroids + weights out)"
         d2h_bytes = int(k * D * 4 + k * 8)
@@ -366,7 +366,40 @@ def gpu_arm(args, name, K, W, rank, world, local_rank, ctxs, do_cpu):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e = {"value": px_total * ITERS * K / float(tt.item()) / 1e6, "unit": "Mpx*iter/s",
-           "h2d_bytes_per_step": int(n_local * 3 * B), "d2h_bytes_per_step": d2h_bytes, "api": api_name}
+           "h2d_bytes_per_step": int(n_local * 3 * B), "d2h_bytes_per_step": d2h_bytes, "api": api_name, "callers": 1}
+    if world == 1:
+        # The same calls from TWO host threads, one context each -- how the reference's harness drives a codec (bench.rs:27:
+        # par_iter over the images): one caller's upload overlaps the other's kernels.  Every call still carries its own
+        # host->device and device->host copies; `value` above stays the single-caller figure.
+        try:
+            import threading
+            ctx2 = cb.Context(local_rank)
+            e2e_step(ctx2)
+            torch.cuda.synchronize()
+            share = [K - K // 2, K // 2]
+            errs = []
+
+            def caller(c, n_calls):
+                try:
+                    for _ in range(n_calls):
+                        e2e_step(c)
+                except BaseException as e:  # noqa: BLE001 -- re-raised below
+                    errs.append(e)
+            ths = [threading.Thread(target=caller, args=(c, n_calls)) for c, n_calls in zip((sctx, ctx2), share) if n_calls]
+            t0 = time.perf_counter()
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            torch.cuda.synchronize()
+            dt2 = time.perf_counter() - t0
+            ctx2.close()
+            if errs:
+                raise errs[0]
+            e2e["two_callers"] = {"value": px_total * ITERS * K / dt2 / 1e6, "callers": len(ths), "calls": K,
+                                  "note": "one context per host thread, as bench.rs:27 runs codec calls; copies of one call overlap kernels of the other"}
+        except Exception as e:  # the single-caller figure stands on its own
+            e2e["two_callers"] = {"error": repr(e)[:200]}
 
     # the brute-force kernel (every pixel scores all k centroids) for reference: same results, no culling.
     # Collective in the sharded case, so every rank runs it.

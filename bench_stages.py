@@ -200,6 +200,25 @@ def run(args, workload, peaks, ClockSampler):
     if second_ms is not None:  # c5: the fused histogram call (tile kernel + page compaction) beside the delta kernel
         roofline["histogram_call_ms"] = second_ms
         roofline["histogram_call_hbm_frac"] = 3 * (i1 - i0) / (second_ms * 1e-3) / 1e9 / pk["hbm_gbs"]
+        # calibration: the delta kernel writes two bytes for each byte it reads, and `peak` is a COPY bandwidth (one read per write).
+        # A plain streaming pass with the kernel's mix (torch u8 -> i16 cast of as many elements, contiguous both sides) shows what
+        # the memory system delivers for it; reported beside the roofline, never as its denominator.
+        src = torch.empty(3 * (i1 - i0), dtype=torch.uint8, device="cuda")
+        dst = torch.empty(3 * (i1 - i0), dtype=torch.int16, device="cuda")
+        dst.copy_(src)
+        mix_ms = 0.0
+        for i in range(5):
+            flush.fill_(i)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dst.copy_(src)
+            b.record()
+            torch.cuda.synchronize()
+            mix_ms += a.elapsed_time(b) / 5
+        roofline["same_mix_streaming_pass"] = {"what": "torch u8->i16 cast, 1 B read : 2 B written, contiguous", "ms": mix_ms,
+                                               "gbs": kernel_bytes / (mix_ms * 1e-3) / 1e9, "kernel_vs_this": mix_ms / kt}
+        del src, dst
     for _ in range(2):
         e2e_step()
     barrier()

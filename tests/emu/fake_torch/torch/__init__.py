@@ -19,6 +19,10 @@ class _Tensor:
         self.arr.fill(v)
         return self
 
+    def copy_(self, other):
+        self.arr[...] = other.arr.astype(self.arr.dtype)
+        return self
+
     def pin_memory(self):
         return self
 
