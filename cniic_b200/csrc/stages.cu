@@ -1085,7 +1085,7 @@ __device__ __noinline__ void cube_spill(uint32_t *s_cube, uint32_t ci, uint32_t 
     if (!flags[key >> PAGE_SHIFT]) flags[key >> PAGE_SHIFT] = 1;
 }
 
-template <int MODE, int NB, int CR>  // CR: radius of the shared-memory counter cube (MODE 2)
+template <int MODE, int NB, int CR, int NS>  // CR: radius of the shared-memory counter cube (MODE 2); NS: tile stages
 __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ rgb,
                                                                                    uint32_t n, uint8_t *out_rgb, int16_t *out_delta, uint32_t *bins,
                                                                                    uint8_t *flags, unsigned long long blk_begin, unsigned long long blk_end) {
@@ -1093,14 +1093,14 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
     // alignment is asked of the declaration -- aligning the pointer by hand made it a generic address, and every tile load and
     // counter update a generic LD / ATOM instead of LDS / ATOMS
     extern __shared__ __align__(128) uint8_t s_raw[];
-    uint32_t *s_cube = reinterpret_cast<uint32_t *>(s_raw + 2 * HT_TILE_BYTES);
-    __shared__ int s_top[2][4];  // per stage: block origin (bx, by), step sign, swapped axes
+    uint32_t *s_cube = reinterpret_cast<uint32_t *>(s_raw + NS * HT_TILE_BYTES);
+    __shared__ int s_top[NS][4];  // per stage: block origin (bx, by), step sign, swapped axes
     // MODE 2: which pages of the global bins this CTA touched, one bit per 8 pages (511^3 / 4096 / 8 < 4096 bits).  The page flags
     // tell the compaction where to look; marking them from the counting path cost either a dependent global load per far symbol
     // (test, then set) or -- as plain stores -- millions of writes to a few hot lines (0.75 -> 1.1 ms for the whole call).  Bits
     // are set here with ATOMS.OR (no return value, nothing to wait for) and written out once, when the CTA is done.
     __shared__ uint32_t s_dirty[128];
-    __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
+    __shared__ __align__(8) unsigned long long s_full[NS], s_empty[NS];
     constexpr int CS = 2 * CR + 1, CN = CS * CS * CS;
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned long long nblocks = blk_end;
@@ -1109,10 +1109,10 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
         if (tid < 128) s_dirty[tid] = 0;
     }
     if (tid == 0) {
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
-        mbar_init(&s_empty[0], 256);
-        mbar_init(&s_empty[1], 256);
+        for (int i = 0; i < NS; i++) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], 256);
+        }
         mbar_fence_init();
     }
     // base-4 digits 2..5 of a cell's first index = the cell number: fold those levels once, for every block
@@ -1172,11 +1172,20 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
         mbar_arrive_expect_tx(&s_full[stage], HT_TILE_BYTES);
         tma_load_2d(s_raw + (size_t)stage * HT_TILE_BYTES, &tmap, (bx & ~(HT - 1)) * 3, by & ~(HT - 1), &s_full[stage]);
     };
+    // NS - 1 blocks are requested ahead of the one being worked on.  (With a single block ahead, requested only once the current one
+    // had landed, a quarter of all warp samples sat in the mbarrier wait below: profiles/r02_ncu_full_c5_tma2_two_stages.txt.)
     const unsigned long long first = blk_begin + blockIdx.x;
-    if (tid == 0 && first < nblocks) issue(first, 0);
+    if (tid == 0)
+        for (int i = 0; i < NS - 1; i++)
+            if (first + (unsigned long long)i * gridDim.x < nblocks) issue(first + (unsigned long long)i * gridDim.x, i);
     uint32_t it = 0;
+    int stage = 0, pstage = NS - 1;  // stage of block `it`; stage of block it - 1 = the one block it + NS - 1 goes to
+    uint32_t phase = 0, pphase = 0;  // parities of those stages' current uses
     for (unsigned long long blk = first; blk < nblocks; blk += gridDim.x, it++) {
-        const int stage = it & 1;
+        if (tid == 0 && blk + (unsigned long long)(NS - 1) * gridDim.x < nblocks) {  // refill the stage block it - 1 was read from
+            if (it > 0) mbar_wait(&s_empty[pstage], pphase);  // ... once every thread has left it
+            issue(blk + (unsigned long long)(NS - 1) * gridDim.x, pstage);
+        }
         const unsigned long long B = blk * 4096;
         const unsigned long long i0 = B + (unsigned long long)tid * 16;
         uint32_t prev = 0;
@@ -1186,7 +1195,7 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
             const uint8_t *q = rgb + ((size_t)py * n + px) * 3;
             prev = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
         }
-        mbar_wait(&s_full[stage], (it >> 1) & 1);
+        mbar_wait(&s_full[stage], phase);
         const uint8_t *tile = s_raw + (size_t)stage * HT_TILE_BYTES;
         const int bx = s_top[stage][0], by = s_top[stage][1], ts = s_top[stage][2], sw = s_top[stage][3];
         // compose: (x, y) = top(local(u, v)); x = bx + ts * (sw ? yl : xl), y = by + ts * (sw ? xl : yl)
@@ -1211,10 +1220,8 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
             prev = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
         }
         mbar_arrive(&s_empty[stage]);  // this thread is done with the stage
-        if (tid == 0 && blk + gridDim.x < nblocks) {  // refill the other stage once everybody has left it (block it - 1)
-            if (it > 0) mbar_wait(&s_empty[stage ^ 1], ((it - 1) >> 1) & 1);
-            issue(blk + gridDim.x, stage ^ 1);
-        }
+        pstage = stage; pphase = phase;
+        if (++stage == NS) { stage = 0; phase ^= 1; }
         // bring the cell into curve order: rotate by 180 degrees (negative step), then transpose (swapped axes), then the base motif
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -1927,11 +1934,12 @@ static int launch_tile_stage(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t n, u
         static const int cube_r = getenv("CNIIC_HIST_CUBE_R") ? atoi(getenv("CNIIC_HIST_CUBE_R")) : 14;
         void (*kern)(const CUtensorMap, const uint8_t *, uint32_t, uint8_t *, int16_t *, uint32_t *, uint8_t *, unsigned long long, unsigned long long);
         size_t cube = 0;
+        int stages = 2;
         if (tile_v1) { kern = hilbert_tile_tma_kernel<MODE>; cube = cube_v1; }
-        else if constexpr (MODE != 2) kern = hilbert_tile_tma2_kernel<MODE, 6, CUBE_R>;  // 40 registers: six CTAs (48 warps) per SM
-        else if (cube_r == 15) { kern = hilbert_tile_tma2_kernel<2, 2, CUBE_R>; cube = cube_v1; }
-        else { kern = hilbert_tile_tma2_kernel<2, 3, 14>; cube = size_t((29 * 29 * 29 + 1) / 2) * 4; }
-        const size_t smem = 2 * size_t(HT_TILE_BYTES) + cube;  // two tile stages + the counter cube
+        else if constexpr (MODE != 2) { kern = hilbert_tile_tma2_kernel<MODE, 6, CUBE_R, 3>; stages = 3; }  // 40 registers, 36 KB: six CTAs (48 warps) per SM
+        else if (cube_r == 15) { kern = hilbert_tile_tma2_kernel<2, 2, CUBE_R, 2>; cube = cube_v1; }
+        else { kern = hilbert_tile_tma2_kernel<2, 3, 14, 2>; cube = size_t((29 * 29 * 29 + 1) / 2) * 4; }
+        const size_t smem = stages * size_t(HT_TILE_BYTES) + cube;  // the tile stages + the counter cube
         CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int per_sm = 0;
