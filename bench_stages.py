@@ -64,7 +64,8 @@ def run(args, workload, peaks, ClockSampler):
                 ctx.hist_delta_range_device(d_img, w, h, i0, i1)
         launches_per_step = None
         alg_bytes = (3 + 6 + 3) * w * h  # delta: 3 B/px read + 6 B/px written; fused histogram: 3 B/px read
-        kernel, kernel_bytes = "hilbert_tile_tma_kernel<1> (delta)", 9 * (i1 - i0)
+        kernel = "hilbert_tile_tma_kernel<1> (delta)" if os.environ.get("CNIIC_TILE_V1") else "hilbert_tile_tma2_kernel<1> (delta)"
+        kernel_bytes = 9 * (i1 - i0)
         pinned = torch.empty((h, w, 3), dtype=torch.uint8).pin_memory()
         host = pinned.numpy()
         ctx.d2h(host, d_img)

@@ -1172,8 +1172,7 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
         mbar_arrive_expect_tx(&s_full[stage], HT_TILE_BYTES);
         tma_load_2d(s_raw + (size_t)stage * HT_TILE_BYTES, &tmap, (bx & ~(HT - 1)) * 3, by & ~(HT - 1), &s_full[stage]);
     };
-    // NS - 1 blocks are requested ahead of the one being worked on.  (With a single block ahead, requested only once the current one
-    // had landed, a quarter of all warp samples sat in the mbarrier wait below: profiles/r02_ncu_full_c5_tma2_two_stages.txt.)
+    // NS - 1 blocks are requested ahead of the one being worked on, each as soon as every thread has left the stage it goes to
     const unsigned long long first = blk_begin + blockIdx.x;
     if (tid == 0)
         for (int i = 0; i < NS - 1; i++)
@@ -1936,7 +1935,9 @@ static int launch_tile_stage(cniic_ctx *ctx, const uint8_t *d_rgb, uint32_t n, u
         size_t cube = 0;
         int stages = 2;
         if (tile_v1) { kern = hilbert_tile_tma_kernel<MODE>; cube = cube_v1; }
-        else if constexpr (MODE != 2) { kern = hilbert_tile_tma2_kernel<MODE, 6, CUBE_R, 3>; stages = 3; }  // 40 registers, 36 KB: six CTAs (48 warps) per SM
+        // 40 registers, two 12 KB stages: six CTAs (48 warps) per SM.  A third stage (two blocks requested ahead) measured SLOWER,
+        // 0.169 against 0.157 ms at 8192^2: it costs the sixth CTA, and the resident warps are what hides this kernel's latencies
+        else if constexpr (MODE != 2) { kern = hilbert_tile_tma2_kernel<MODE, 6, CUBE_R, 2>; }
         else if (cube_r == 15) { kern = hilbert_tile_tma2_kernel<2, 2, CUBE_R, 2>; cube = cube_v1; }
         else { kern = hilbert_tile_tma2_kernel<2, 3, 14, 2>; cube = size_t((29 * 29 * 29 + 1) / 2) * 4; }
         const size_t smem = stages * size_t(HT_TILE_BYTES) + cube;  // the tile stages + the counter cube
