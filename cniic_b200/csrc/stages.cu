@@ -1101,6 +1101,7 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
     // are set here with ATOMS.OR (no return value, nothing to wait for) and written out once, when the CTA is done.
     __shared__ uint32_t s_dirty[128];
     __shared__ __align__(8) unsigned long long s_full[NS], s_empty[NS];
+    __shared__ uint32_t s_prev[NS];  // per stage: the pixel in front of the block's first one (the last pixel of the previous block)
     constexpr int CS = 2 * CR + 1, CN = CS * CS * CS;
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned long long nblocks = blk_end;
@@ -1110,7 +1111,7 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
     }
     if (tid == 0) {
         for (int i = 0; i < NS; i++) {
-            mbar_init(&s_full[i], 1);
+            mbar_init(&s_full[i], MODE == 0 ? 1 : 2);  // the tile's bytes (+ one arrival), and the arrival that publishes s_prev
             mbar_init(&s_empty[i], 256);
         }
         mbar_fence_init();
@@ -1147,7 +1148,11 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
         ply = qy + qs * (qsw ? 3 : 0);
     }
     __syncthreads();
-    // thread 0: fold the levels above the block (6..L-1) into an affine map of the 64x64 block, request the block's pixels
+    // One thread per block: fold the levels above the block (6..L-1) into an affine map of the 64x64 block, request the block's
+    // pixels, fetch the pixel in front of its first one.  That is ~250 dependent instructions and a global load -- a fifth of what a
+    // warp spends on a block -- and a block is only done when its slowest warp is, so the duty ROTATES over the eight warps
+    // (with thread 0 doing all of it, the other warps spent 22 % of the kernel's issue slots polling the tile barrier:
+    // profiles/r02_ncu_full_c5_tma2.txt).
     auto issue = [&](unsigned long long blk, int stage) {
         int bx = 0, by = 0, ts = 1, sw = 0;
         unsigned long long t = blk;
@@ -1171,6 +1176,17 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
         s_top[stage][0] = bx; s_top[stage][1] = by; s_top[stage][2] = ts; s_top[stage][3] = sw;
         mbar_arrive_expect_tx(&s_full[stage], HT_TILE_BYTES);
         tma_load_2d(s_raw + (size_t)stage * HT_TILE_BYTES, &tmap, (bx & ~(HT - 1)) * 3, by & ~(HT - 1), &s_full[stage]);
+        if (MODE != 0) {
+            uint32_t pv = 0;  // hilbertc.rs:445 START = [0;3] in front of the very first pixel
+            if (blk != 0) {
+                uint32_t px, py;
+                hilbert_d2xy_pow2(n, blk * 4096 - 1, &px, &py);
+                const uint8_t *q = rgb + ((size_t)py * n + px) * 3;
+                pv = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
+            }
+            s_prev[stage] = pv;
+            mbar_arrive(&s_full[stage]);  // (release: s_prev and s_top are visible to whoever sees the phase complete)
+        }
     };
     // NS - 1 blocks are requested ahead of the one being worked on, each as soon as every thread has left the stage it goes to
     const unsigned long long first = blk_begin + blockIdx.x;
@@ -1181,20 +1197,14 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
     int stage = 0, pstage = NS - 1;  // stage of block `it`; stage of block it - 1 = the one block it + NS - 1 goes to
     uint32_t phase = 0, pphase = 0;  // parities of those stages' current uses
     for (unsigned long long blk = first; blk < nblocks; blk += gridDim.x, it++) {
-        if (tid == 0 && blk + (unsigned long long)(NS - 1) * gridDim.x < nblocks) {  // refill the stage block it - 1 was read from
+        if (tid == int(it & 7) * 32 && blk + (unsigned long long)(NS - 1) * gridDim.x < nblocks) {  // refill the stage block it - 1 was read from
             if (it > 0) mbar_wait(&s_empty[pstage], pphase);  // ... once every thread has left it
             issue(blk + (unsigned long long)(NS - 1) * gridDim.x, pstage);
         }
         const unsigned long long B = blk * 4096;
         const unsigned long long i0 = B + (unsigned long long)tid * 16;
-        uint32_t prev = 0;
-        if (MODE != 0 && tid == 0 && B != 0) {  // the block's first symbol follows the last pixel of the previous block: global, asked for early
-            uint32_t px, py;
-            hilbert_d2xy_pow2(n, B - 1, &px, &py);
-            const uint8_t *q = rgb + ((size_t)py * n + px) * 3;
-            prev = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16);
-        }
         mbar_wait(&s_full[stage], phase);
+        uint32_t prev = MODE != 0 && tid == 0 ? s_prev[stage] : 0u;
         const uint8_t *tile = s_raw + (size_t)stage * HT_TILE_BYTES;
         const int bx = s_top[stage][0], by = s_top[stage][1], ts = s_top[stage][2], sw = s_top[stage][3];
         // compose: (x, y) = top(local(u, v)); x = bx + ts * (sw ? yl : xl), y = by + ts * (sw ? xl : yl)

@@ -151,17 +151,20 @@ static inline bool tma_encode_2d_u8(CUtensorMap *m, const void *base, unsigned l
     m->box_inner = box_inner; m->box_rows = box_rows;
     return true;
 }
-// bits 48..63: arrivals a phase needs, bits 32..47: arrivals so far (plain arrivals only; a TMA phase completes in tma_load_2d)
+// bit 0: parity of the phase in progress; bits 32..46: arrivals so far; bit 47: bytes announced (expect_tx) and not yet delivered;
+// bits 48..63: arrivals a phase needs.  A phase completes when all arrivals are in and no bytes are outstanding.
 static inline void mbar_init(unsigned long long *bar, unsigned arrivals) { *bar = (unsigned long long)arrivals << 48; }
-static inline void mbar_arrive(unsigned long long *bar) {
-    const unsigned long long need = *bar >> 48, got = ((*bar >> 32) & 0xffffull) + 1;
-    if (got == need) *bar = (need << 48) | ((*bar & 1ull) ^ 1ull);
-    else *bar = (need << 48) | (got << 32) | (*bar & 1ull);
+static inline void emu_mbar_update(unsigned long long *bar, unsigned long long got, bool tx_pending) {
+    const unsigned long long need = *bar >> 48, phase = *bar & 1ull;
+    if (got > need) { fprintf(stderr, "emu: more arrivals on an mbarrier than it was initialised for\n"); abort(); }
+    if (got == need && !tx_pending) *bar = (need << 48) | (phase ^ 1ull);
+    else *bar = (need << 48) | (tx_pending ? 1ull << 47 : 0ull) | (got << 32) | phase;
 }
+static inline void mbar_arrive(unsigned long long *bar) { emu_mbar_update(bar, ((*bar >> 32) & 0x7fffull) + 1, (*bar >> 47) & 1ull); }
 static inline void mbar_fence_init() {}
-static inline void mbar_arrive_expect_tx(unsigned long long *, unsigned) {}
+static inline void mbar_arrive_expect_tx(unsigned long long *bar, unsigned) { emu_mbar_update(bar, ((*bar >> 32) & 0x7fffull) + 1, true); }
 static inline void mbar_wait(unsigned long long *bar, unsigned parity) {
-    emu::spin_while_equal(reinterpret_cast<const volatile unsigned *>(bar), parity, "mbar_wait (TMA tile not delivered)");
+    emu::spin_while_equal(reinterpret_cast<const volatile unsigned *>(bar), parity, "mbar_wait (mbarrier phase not complete)");
 }
 static inline void tma_load_2d(void *dst, const CUtensorMap *m, int c_inner, int c_row, unsigned long long *bar) {
     if (reinterpret_cast<uintptr_t>(dst) & 127) { fprintf(stderr, "emu: TMA destination not 128-byte aligned\n"); abort(); }
@@ -172,7 +175,7 @@ static inline void tma_load_2d(void *dst, const CUtensorMap *m, int c_inner, int
             d[(size_t)r * m->box_inner + b] = (y >= 0 && (unsigned long long)y < m->rows && x >= 0 && (unsigned long long)x < m->inner_bytes)
                                                   ? m->base[(size_t)y * m->row_stride + x] : 0;
         }
-    *bar ^= 1ull;  // the phase completes
+    emu_mbar_update(bar, (*bar >> 32) & 0x7fffull, false);  // the bytes are there: the phase completes once every arrival is in
 }
 
 #define threadIdx (emu::g_cur->tid)
