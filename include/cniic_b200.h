@@ -12,7 +12,8 @@
  *     caller owns every buffer; the library keeps no pointer after return.
  *   - `cniic_ctx` owns one CUDA device + stream + scratch.  A ctx is NOT thread-safe; create one ctx per calling
  *     thread (bench.rs:27 calls codecs from rayon workers, one image per worker).  Different ctx objects may be
- *     used concurrently.
+ *     used concurrently; the two dense histogram key spaces (64 MB of colours, 534 MB of delta symbols) belong to the
+ *     DEVICE and are lent to one counting call at a time, so contexts share them instead of holding a copy each.
  *   - there is NO CPU fallback: without a usable CUDA device cniic_ctx_create fails with CNIIC_ERR_CUDA.
  *
  * Deterministic rules where the reference is random / unordered are stated at each function
