@@ -1291,15 +1291,21 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
             // are issued back to back, their return values (the guard-bit check) examined afterwards.  Per symbol: one VABSDIFF4 and
             // three logic operations decide whether all three |differences| are <= CR; the cube index is linear in the channels,
             // ((d0 + CR) * CS + (d1 + CR)) * CS + (d2 + CR) = (A(c) - A(p)) * CS + (b(c) - b(p)) + K with A(x) = CS * r + g (one
-            // IDP.4A per pixel), so no channel is extracted on the common path.
+            // IDP.4A per pixel), so no channel is extracted on the common path.  The global key of a far symbol is linear in the same
+            // way: ((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255) = (W(c) - W(p)) * 511 + (b(c) - b(p)) + K' with W(x) = 511 r + g
+            // = IDP.4A(x, (255, 1)) + (r << 8) -- three instructions per pixel instead of a dozen per far symbol, which matters
+            // because on a noisy image nine warp-instructions in ten have at least one far lane and run that path.
             constexpr uint32_t SPLAT_LIM = (127u - CR) * 0x01010101u;
             constexpr int K_CUBE = (CR * CS + CR) * CS + CR;
+            constexpr int K_FAR = (255 * 511 + 255) * 511 + 255;
             uint32_t old_v[16], slot[16];  // slot = cube index (bit 31 set: outside the cube, already counted globally)
             int pa = dp4a_uu(prev, uint32_t(CS) | (1u << 8), 0), pb = int(prev >> 16);
+            int pw = dp4a_uu(prev, 255u | (1u << 8), 0) + int(__byte_perm(prev, 0u, 0x4404));
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 const uint32_t c = pix[j], q = j ? pix[j - 1] : prev;
                 const int ca = dp4a_uu(c, uint32_t(CS) | (1u << 8), 0), cb = int(c >> 16);
+                const int cw = dp4a_uu(c, 255u | (1u << 8), 0) + int(__byte_perm(c, 0u, 0x4404));
                 const uint32_t ad = __vabsdiffu4(c, q);  // |difference| per channel
                 old_v[j] = 0;
                 if (((((ad & 0x7f7f7f7fu) + SPLAT_LIM) | ad) & 0x80808080u) == 0) {  // no channel differs by more than CR
@@ -1308,33 +1314,44 @@ __global__ void __launch_bounds__(256, NB) hilbert_tile_tma2_kernel(const __grid
                     old_v[j] = atomicAdd(&s_cube[ci >> 1], 1u << (16 * (ci & 1)));
                 } else {
                     slot[j] = 0x80000000u;
-                    const int d0 = int(c & 0xff) - int(q & 0xff), d1 = int((c >> 8) & 0xff) - int((q >> 8) & 0xff),
-                              d2 = int((c >> 16) & 0xff) - int((q >> 16) & 0xff);
-                    const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                    const uint32_t key = uint32_t((cw - pw) * 511 + (cb - pb + K_FAR));
                     atomicAdd(&bins[key], 1u);
                     atomicOr(&s_dirty[key >> (PAGE_SHIFT + 8)], 1u << ((key >> (PAGE_SHIFT + 3)) & 31));
                 }
-                pa = ca; pb = cb;
+                pa = ca; pb = cb; pw = cw;
             }
+            // guard bits: a counter that read 0x7fff before my increment is the one I pushed to 2^15 (far symbols read 0).  One OR
+            // over the sixteen answers decides whether anything has to be looked at
+            uint32_t any_full = 0;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const uint32_t ci = slot[j];
-                const int sh = 16 * (ci & 1);
-                if (!(ci >> 31) && ((old_v[j] >> sh) & 0x7fffu) == 0x7fffu)  // my increment set the guard bit: 2^15 counts leave the field
-                    cube_spill<CR>(s_cube, ci, bins, flags);
+            for (int j = 0; j < 16; j++) any_full |= ((old_v[j] >> (16 * (slot[j] & 1))) & 0x7fffu) + 1u;
+            if (any_full & 0x8000u) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint32_t ci = slot[j];
+                    const int sh = 16 * (ci & 1);
+                    if (!(ci >> 31) && ((old_v[j] >> sh) & 0x7fffu) == 0x7fffu)  // my increment set the guard bit: 2^15 counts leave the field
+                        cube_spill<CR>(s_cube, ci, bins, flags);
+                }
             }
         }
     }
     if (MODE == 2) {  // flush the CTA's near-zero counters into the global bins, then its dirty-page bits into the page flags
         __syncthreads();
+        // (the three digits of ci in base CS are carried along instead of divided out: ci advances by 256 = Q * CS + Rm)
+        constexpr int Q = 256 / CS, Rm = 256 % CS;
+        static_assert(Q + 1 < CS, "one carry per digit");
+        int e2 = tid % CS, e1 = (tid / CS) % CS, e0 = tid / (CS * CS);
         for (int ci = tid; ci < CN; ci += 256) {
             const uint32_t cnt = (s_cube[ci >> 1] >> (16 * (ci & 1))) & 0xffffu;
             if (cnt) {
-                const int d2 = ci % CS - CR, d1 = (ci / CS) % CS - CR, d0 = ci / (CS * CS) - CR;
-                const uint32_t key = uint32_t(((d0 + 255) * 511 + (d1 + 255)) * 511 + (d2 + 255));
+                const uint32_t key = uint32_t(((e0 - CR + 255) * 511 + (e1 - CR + 255)) * 511 + (e2 - CR + 255));
                 atomicAdd(&bins[key], cnt);
                 atomicOr(&s_dirty[key >> (PAGE_SHIFT + 8)], 1u << ((key >> (PAGE_SHIFT + 3)) & 31));
             }
+            e2 += Rm; e1 += Q;
+            if (e2 >= CS) { e2 -= CS; e1++; }
+            if (e1 >= CS) { e1 -= CS; e0++; }
         }
         __syncthreads();
         constexpr uint32_t NPAGES = (511u * 511u * 511u + PAGE - 1) / PAGE;
